@@ -1,0 +1,131 @@
+/*
+ * ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle_pixel.c header).  CPU restatement, in plain C, of the
+ * reference's ME / lookahead cost path (jpsdr/x264 core 165, 8-bit).  Every function cites the reference
+ * file:line it follows.  Parity status: pinned against oracle/_ref (the compiled, unmodified reference).
+ */
+#ifndef X264_B200_ORACLE_H
+#define X264_B200_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same indices as common/pixel.h:37-52 */
+enum { ORC_PIXEL_16x16, ORC_PIXEL_16x8, ORC_PIXEL_8x16, ORC_PIXEL_8x8, ORC_PIXEL_8x4, ORC_PIXEL_4x8,
+       ORC_PIXEL_4x4, ORC_PIXEL_4x16, ORC_PIXEL_NB };
+enum { ORC_SAD, ORC_SSD, ORC_SATD, ORC_SA8D };
+enum { ORC_ME_DIA, ORC_ME_HEX, ORC_ME_UMH };           /* x264.h X264_ME_DIA/HEX/UMH */
+#define ORC_COST_MAX (1<<28)                             /* encoder/me.h:30 */
+#define ORC_PAD 32                                       /* common/frame.h:32-33 PADH/PADV */
+
+extern const int orc_pixel_w[ORC_PIXEL_NB], orc_pixel_h[ORC_PIXEL_NB];
+
+typedef struct { uint32_t fenc_off, ref_off; } orc_cand_t;
+
+/* ---- pixel metrics (oracle_pixel.c) ---- */
+int  orc_sad ( const uint8_t *a, intptr_t sa, const uint8_t *b, intptr_t sb, int w, int h );
+int  orc_ssd ( const uint8_t *a, intptr_t sa, const uint8_t *b, intptr_t sb, int w, int h );
+int  orc_satd( const uint8_t *a, intptr_t sa, const uint8_t *b, intptr_t sb, int w, int h );
+int  orc_sa8d( const uint8_t *a, intptr_t sa, const uint8_t *b, intptr_t sb, int w, int h );
+int  orc_pixel_cmp( int metric, int i_pixel, const uint8_t *a, intptr_t sa, const uint8_t *b, intptr_t sb );
+void orc_pixel_cmp_batch( int metric, int i_pixel, const uint8_t *fenc, intptr_t fenc_stride,
+                          const uint8_t *ref, intptr_t ref_stride, const orc_cand_t *cand, int n, int32_t *out );
+void orc_pixel_cmp_mvfield( int metric, int i_pixel, const uint8_t *fenc, intptr_t fenc_stride,
+                            const uint8_t *ref, intptr_t ref_stride, int blocks_x, int blocks_y, int k_cands,
+                            const int16_t *mv, int32_t *out );
+
+/* ---- motion compensation / frame preparation (oracle_mc.c) ---- */
+/* weight: scale/denom/offset as in x264_weight_t (common/mc.h:235-245); enabled==0 means "no weightfn" */
+typedef struct { int enabled, scale, denom, offset; } orc_weight_t;
+
+void orc_plane_expand_border( uint8_t *pix, intptr_t stride, int width, int height, int padh, int padv );
+void orc_frame_init_lowres( const uint8_t *src, intptr_t src_stride, int width, int height,
+                            uint8_t *lowres[4], intptr_t dst_stride, int width_lowres, int lines_lowres );
+void orc_hpel_filter_plane( const uint8_t *src, intptr_t stride, int width, int height,
+                            uint8_t *dsth, uint8_t *dstv, uint8_t *dstc, intptr_t dst_stride, int pad );
+void orc_mc_luma( uint8_t *dst, intptr_t dst_stride, const uint8_t *const src[4], intptr_t src_stride,
+                  int mvx, int mvy, int w, int h, const orc_weight_t *wt );
+void orc_pixel_avg( uint8_t *dst, intptr_t sd, const uint8_t *a, intptr_t sa, const uint8_t *b, intptr_t sb,
+                    int w, int h, int weight );
+void orc_mc_weight( uint8_t *dst, intptr_t sd, const uint8_t *src, intptr_t ss, const orc_weight_t *wt, int w, int h );
+void orc_weight_scale_plane( uint8_t *dst, intptr_t sd, const uint8_t *src, intptr_t ss, int w, int h, const orc_weight_t *wt );
+/* table[0 .. 2*len] with the zero-mvd entry at table[len]; len = 2*4*mv_range */
+void orc_cost_mv_table( uint16_t *table, int len, int lambda );
+
+/* ---- motion search (oracle_me.c) ---- */
+typedef struct
+{
+    /* search configuration (x264_t fields read by me.c) */
+    int me_method;          /* h->mb.i_me_method */
+    int subpel_refine;      /* h->mb.i_subpel_refine */
+    int me_range;           /* h->param.analyse.i_me_range */
+    int mbcmp_is_satd;      /* encoder.c:1409-1427: mbcmp = SATD iff param subme > 1 */
+    int mv_min_spel[2], mv_max_spel[2];     /* h->mb.mv_min_spel / mv_max_spel */
+    int mv_limit_fpel[2][2];                /* h->mb.mv_limit_fpel */
+} orc_me_ctx_t;
+
+typedef struct
+{
+    int i_pixel;
+    const uint16_t *p_cost_mv;     /* centred table: p_cost_mv[mvd] */
+    const uint8_t *p_fref[4];      /* F,H,V,C planes at the block origin */
+    const uint8_t *p_fref_w;       /* weighted full-pel plane (== p_fref[0] when unweighted) */
+    const uint8_t *p_fenc;         /* block origin, stride fenc_stride */
+    intptr_t fenc_stride;
+    intptr_t stride;
+    orc_weight_t weight;
+    int16_t mvp[2];
+    /* out */
+    int cost_mv, cost;
+    int16_t mv[2];
+} orc_me_t;
+
+void orc_me_search_ref( const orc_me_ctx_t *c, orc_me_t *m, const int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );
+
+/* ---- lowres lookahead (oracle_lookahead.c) ---- */
+typedef struct
+{
+    int width, height;                 /* full-res luma size as given by the user (h->param.i_width/height) */
+    int mb_width, mb_height;           /* ceil/16 */
+    int subpel_refine;                 /* h->param.analyse.i_subpel_refine */
+    int me_method;                     /* h->param.analyse.i_me_method */
+    int me_range;                      /* h->param.analyse.i_me_range */
+    int mv_range;                      /* h->param.analyse.i_mv_range */
+    int bframes;                       /* h->param.i_bframe */
+    int bframe_bias;                   /* h->param.i_bframe_bias */
+    int weighted_bipred;               /* h->param.analyse.b_weighted_bipred */
+    int aq_mode;                       /* h->param.rc.i_aq_mode != 0 */
+    int do_edges;                      /* mbtree || vbv || tiny frame (slicetype.c:823) */
+    int vbv;                           /* row satds requested */
+} orc_la_params_t;
+
+typedef struct orc_la_frame orc_la_frame_t;
+struct orc_la_frame
+{
+    uint8_t *lowres_buf[4];            /* allocations */
+    uint8_t *lowres[4];                /* plane origins */
+    intptr_t stride_lowres;
+    int width_lowres, lines_lowres;
+    int mb_count, bframes;
+    int16_t (*lowres_mvs[2][17])[2];
+    int     *lowres_mv_costs[2][17];
+    uint16_t *lowres_costs[18][18];
+    int     *row_satds[18][18];
+    int     *intra_cost;
+    uint16_t *inv_qscale_factor;
+    int cost_est[18][18], cost_est_aq[18][18];
+    int intra_mbs[18];
+    int b_intra_calculated;
+};
+
+orc_la_frame_t *orc_la_frame_new( const orc_la_params_t *p, const uint8_t *luma, intptr_t luma_stride );
+void orc_la_frame_delete( orc_la_frame_t *f );
+int  orc_la_frame_cost( const orc_la_params_t *p, const uint16_t *cost_mv_centre,
+                        orc_la_frame_t **frames, int p0, int p1, int b );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

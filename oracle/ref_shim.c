@@ -1,0 +1,241 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- thin C-ABI exports around the UNMODIFIED reference (jpsdr/x264), compiled by
+ * oracle/Makefile.ref straight from /root/reference into oracle/_ref/libx264ref.so.  This file contains no
+ * reference code: it #includes the reference's encoder/analyse.c (which itself #includes slicetype.c) so that
+ * the file-static slicetype_* functions can be driven directly, and calls the reference's own functions.
+ * Used by tests/ to pin oracle/ and the CUDA path, and by bench.py --impl reference as the CPU arm.
+ */
+#include "encoder/analyse.c"          /* brings in common/common.h, me.h, slicetype.c, rdo.c ... */
+
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+
+x264_t *x264_encoder_open( x264_param_t *, void * );
+int     x264_encoder_encode( x264_t *, x264_nal_t **pp_nal, int *pi_nal, x264_picture_t *pic_in, x264_picture_t *pic_out );
+void    x264_encoder_close( x264_t * );
+int     x264_encoder_delayed_frames( x264_t * );
+
+#define XREF_API __attribute__((visibility("default")))
+
+XREF_API int xref_build( void ) { return X264_BUILD; }
+
+/* ------------------------------------------------------------------ encoder handle ------------------ */
+static void quiet_log( void *p, int level, const char *fmt, va_list ap ) { (void)p; (void)level; (void)fmt; (void)ap; }
+
+/* opts: "key=value:key=value" passed one by one to x264_param_parse (common/base.c:886) */
+XREF_API void *xref_open( int width, int height, const char *preset, const char *opts, int verbose )
+{
+    x264_param_t param;
+    if( x264_param_default_preset( &param, preset && preset[0] ? preset : "medium", NULL ) < 0 )
+        return NULL;
+    param.i_width = width;
+    param.i_height = height;
+    param.i_csp = X264_CSP_I420;
+    param.i_threads = 1;
+    param.i_lookahead_threads = 1;
+    param.i_fps_num = 25; param.i_fps_den = 1;
+    param.b_vfr_input = 0;
+    param.cpu = 0;                        /* C path: identical results to asm (checkasm) and deterministic */
+    if( !verbose )
+        param.pf_log = quiet_log;
+    else
+        param.i_log_level = X264_LOG_DEBUG;
+    if( opts && opts[0] )
+    {
+        char *dup = strdup( opts );
+        for( char *tok = strtok( dup, ":" ); tok; tok = strtok( NULL, ":" ) )
+        {
+            char *eq = strchr( tok, '=' );
+            if( eq ) *eq = 0;
+            int r = x264_param_parse( &param, tok, eq ? eq+1 : NULL );
+            if( r < 0 )
+            {
+                fprintf( stderr, "xref_open: bad option %s=%s (%d)\n", tok, eq ? eq+1 : "", r );
+                free( dup );
+                return NULL;
+            }
+        }
+        free( dup );
+    }
+    return x264_encoder_open( &param, NULL );
+}
+
+XREF_API void xref_close( void *hv ) { if( hv ) x264_encoder_close( (x264_t*)hv ); }
+
+XREF_API int xref_param( void *hv, const char *name )
+{
+    x264_t *h = hv;
+#define P(n,v) if( !strcmp( name, n ) ) return (v);
+    P( "mb_width", h->mb.i_mb_width ) P( "mb_height", h->mb.i_mb_height )
+    P( "subme", h->param.analyse.i_subpel_refine ) P( "me", h->param.analyse.i_me_method )
+    P( "merange", h->param.analyse.i_me_range ) P( "mvrange", h->param.analyse.i_mv_range )
+    P( "bframes", h->param.i_bframe ) P( "b_bias", h->param.i_bframe_bias ) P( "b_adapt", h->param.i_bframe_adaptive )
+    P( "weightb", h->param.analyse.b_weighted_bipred ) P( "weightp", h->param.analyse.i_weighted_pred )
+    P( "aq_mode", h->param.rc.i_aq_mode ) P( "mbtree", h->param.rc.b_mb_tree ) P( "vbv", h->param.rc.i_vbv_buffer_size )
+    P( "lookahead", h->param.rc.i_lookahead ) P( "lookahead_threads", h->param.i_lookahead_threads )
+    P( "scenecut", h->param.i_scenecut_threshold ) P( "keyint_max", h->param.i_keyint_max ) P( "keyint_min", h->param.i_keyint_min )
+    P( "sync_lookahead", h->param.i_sync_lookahead ) P( "threads", h->param.i_threads )
+    P( "stride", h->fdec->i_stride[0] ) P( "stride_lowres", h->fdec->i_stride_lowres )
+    P( "width_lowres", h->fdec->i_width_lowres ) P( "lines_lowres", h->fdec->i_lines_lowres )
+    P( "b_pyramid", h->param.i_bframe_pyramid ) P( "open_gop", h->param.b_open_gop ) P( "intra_refresh", h->param.b_intra_refresh )
+#undef P
+    return -9999;
+}
+
+/* ------------------------------------------------------------------ pixel table (B1) ---------------- */
+static x264_pixel_function_t g_pf;
+static x264_mc_functions_t   g_mc;
+static int g_tables_ready;
+static void tables_init( void )
+{
+    if( g_tables_ready ) return;
+    x264_pixel_init( 0, &g_pf );
+    x264_mc_init( 0, &g_mc, 1 );
+    g_tables_ready = 1;
+}
+
+/* metric: 0 sad, 1 ssd, 2 satd, 3 sa8d (sa8d: i_pixel 0 = 16x16, 3 = 8x8 only) */
+XREF_API int xref_pixel_cmp( int metric, int i_pixel, uint8_t *a, intptr_t sa, uint8_t *b, intptr_t sb )
+{
+    tables_init();
+    switch( metric )
+    {
+        case 0: return g_pf.sad[i_pixel]( a, sa, b, sb );
+        case 1: return g_pf.ssd[i_pixel]( a, sa, b, sb );
+        case 2: return g_pf.satd[i_pixel]( a, sa, b, sb );
+        case 3: return g_pf.sa8d[i_pixel]( a, sa, b, sb );
+    }
+    return -1;
+}
+
+typedef struct { uint32_t fenc_off, ref_off; } xref_cand_t;
+
+XREF_API void xref_pixel_cmp_batch( int metric, int i_pixel, uint8_t *fenc, intptr_t fenc_stride,
+                                    uint8_t *ref, intptr_t ref_stride, const xref_cand_t *cand, int n, int32_t *out )
+{
+    tables_init();
+    x264_pixel_cmp_t fn = metric == 0 ? g_pf.sad[i_pixel] : metric == 1 ? g_pf.ssd[i_pixel]
+                        : metric == 2 ? g_pf.satd[i_pixel] : g_pf.sa8d[i_pixel];
+    for( int i = 0; i < n; i++ )
+        out[i] = fn( fenc + cand[i].fenc_off, fenc_stride, ref + cand[i].ref_off, ref_stride );
+}
+
+/* x3/x4 entries: fenc is a FENC_STRIDE(16) block as in common/pixel.h:34-35 */
+XREF_API void xref_pixel_cmp_x4( int metric, int i_pixel, uint8_t *fenc16, uint8_t *p0, uint8_t *p1, uint8_t *p2, uint8_t *p3,
+                                 intptr_t stride, int *scores, int n_refs )
+{
+    tables_init();
+    if( n_refs == 3 )
+        ( metric == 0 ? g_pf.sad_x3[i_pixel] : g_pf.satd_x3[i_pixel] )( fenc16, p0, p1, p2, stride, scores );
+    else
+        ( metric == 0 ? g_pf.sad_x4[i_pixel] : g_pf.satd_x4[i_pixel] )( fenc16, p0, p1, p2, p3, stride, scores );
+}
+
+/* ------------------------------------------------------------------ mc table ------------------------ */
+static void make_weight( x264_weight_t *w, int enabled, int scale, int denom, int offset )
+{
+    memset( w, 0, sizeof(*w) );
+    if( enabled )
+    {
+        w->i_scale = scale; w->i_denom = denom; w->i_offset = offset;
+        w->weightfn = g_mc.weight;
+    }
+}
+
+XREF_API void xref_mc_luma( uint8_t *dst, intptr_t dst_stride, uint8_t *src0, uint8_t *src1, uint8_t *src2, uint8_t *src3,
+                            intptr_t src_stride, int mvx, int mvy, int w, int h, int wt_en, int scale, int denom, int offset )
+{
+    tables_init();
+    x264_weight_t wt; make_weight( &wt, wt_en, scale, denom, offset );
+    pixel *src[4] = { src0, src1, src2, src3 };
+    g_mc.mc_luma( dst, dst_stride, src, src_stride, mvx, mvy, w, h, &wt );
+}
+
+/* get_ref may return a pointer into the source: always copy the result into dst (stride dst_stride) */
+XREF_API void xref_get_ref( uint8_t *dst, intptr_t dst_stride, uint8_t *src0, uint8_t *src1, uint8_t *src2, uint8_t *src3,
+                            intptr_t src_stride, int mvx, int mvy, int w, int h, int wt_en, int scale, int denom, int offset )
+{
+    tables_init();
+    x264_weight_t wt; make_weight( &wt, wt_en, scale, denom, offset );
+    pixel *src[4] = { src0, src1, src2, src3 };
+    ALIGNED_ARRAY_64( pixel, tmp,[32*32] );
+    intptr_t st = 32;
+    pixel *r = g_mc.get_ref( tmp, &st, src, src_stride, mvx, mvy, w, h, &wt );
+    for( int y = 0; y < h; y++ )
+        memcpy( dst + y*dst_stride, r + y*st, w );
+}
+
+XREF_API void xref_avg( int i_pixel, uint8_t *dst, intptr_t sd, uint8_t *a, intptr_t sa, uint8_t *b, intptr_t sb, int weight )
+{
+    tables_init();
+    g_mc.avg[i_pixel]( dst, sd, a, sa, b, sb, weight );
+}
+
+XREF_API void xref_frame_init_lowres_core( uint8_t *src, uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc,
+                                           intptr_t src_stride, intptr_t dst_stride, int width, int height )
+{
+    tables_init();
+    g_mc.frame_init_lowres_core( src, d0, dh, dv, dc, src_stride, dst_stride, width, height );
+}
+
+/* Run the reference's real per-frame lowres preparation (mc.c:458-482) on a luma picture of the encoder's
+ * size; copies out the four padded lowres planes (stride_lowres x (lines_lowres+2*PADV)), origin included. */
+XREF_API int xref_frame_lowres( void *hv, const uint8_t *luma, intptr_t luma_stride, uint8_t *out4 )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = x264_frame_pop_unused( h, 0 );
+    if( !f ) return -1;
+    for( int y = 0; y < h->param.i_height; y++ )
+        memcpy( f->plane[0] + y*f->i_stride[0], luma + y*luma_stride, h->param.i_width );
+    x264_frame_expand_border_mod16( h, f );
+    x264_frame_init_lowres( h, f );
+    intptr_t st = f->i_stride_lowres;
+    size_t plane_bytes = (size_t)st * (f->i_lines_lowres + 2*PADV);
+    for( int i = 0; i < 4; i++ )
+        for( int y = 0; y < f->i_lines_lowres + 2*PADV; y++ )
+            memcpy( out4 + i*plane_bytes + y*st, f->lowres[i] + (y-PADV)*st - PADH, f->i_width_lowres + 2*PADH );
+    x264_frame_push_unused( h, f );
+    return 0;
+}
+
+/* Run the reference's hpel pipeline the way fdec_filter_row does (encoder.c:2470-2480): per MB row
+ * expand_border -> x264_frame_filter -> expand_border_filtered.  Copies out H,V,C padded planes
+ * (stride x (lines+2*PADV)), starting at (-PADH,-PADV). */
+XREF_API int xref_frame_hpel( void *hv, const uint8_t *luma, intptr_t luma_stride, uint8_t *out3, uint8_t *out_src )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = x264_frame_pop_unused( h, 1 );
+    if( !f ) return -1;
+    int W = h->mb.i_mb_width*16, H = h->mb.i_mb_height*16;
+    for( int y = 0; y < H; y++ )
+        memcpy( f->plane[0] + y*f->i_stride[0], luma + y*luma_stride, W );
+    f->b_kept_as_ref = 1;
+    h->i_threadslice_start = 0;
+    h->i_threadslice_end = h->mb.i_mb_height;
+    for( int mb_y = 0; mb_y < h->mb.i_mb_height; mb_y++ )
+    {
+        int end = mb_y == h->mb.i_mb_height - 1;
+        x264_frame_expand_border( h, f, mb_y );
+        x264_frame_filter( h, f, mb_y, end );
+        x264_frame_expand_border_filtered( h, f, mb_y, end );
+    }
+    intptr_t st = f->i_stride[0];
+    size_t plane_bytes = (size_t)st * (H + 2*PADV);
+    for( int y = 0; y < H + 2*PADV; y++ )
+    {
+        for( int i = 1; i < 4; i++ )
+            memcpy( out3 + (i-1)*plane_bytes + y*st, f->filtered[0][i] + (y-PADV)*st - PADH, W + 2*PADH );
+        if( out_src )
+            memcpy( out_src + y*st, f->plane[0] + (y-PADV)*st - PADH, W + 2*PADH );
+    }
+    x264_frame_push_unused( h, f );
+    return 0;
+}
+
+XREF_API void xref_cost_mv_table( void *hv, uint16_t *out, int len )
+{
+    x264_t *h = hv;
+    for( int i = -len; i <= len; i++ )
+        out[len+i] = h->cost_mv[X264_LOOKAHEAD_QP][i];
+}

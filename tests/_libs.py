@@ -1,0 +1,146 @@
+"""ctypes loaders for the test-side checkers: the plain-C oracle (oracle/liboracle.so) and the compiled,
+unmodified reference (oracle/_ref/libx264ref.so).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libx264ref.so")
+
+PIXEL_W = [16, 16, 8, 8, 8, 4, 4, 4]
+PIXEL_H = [16, 8, 16, 8, 4, 8, 4, 16]
+SAD, SSD, SATD, SA8D = 0, 1, 2, 3
+PAD = 32
+
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+i16p = np.ctypeslib.ndpointer(dtype=np.int16, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+cand_dtype = np.dtype([("fenc_off", np.uint32), ("ref_off", np.uint32)])
+candp = np.ctypeslib.ndpointer(dtype=cand_dtype, flags="C_CONTIGUOUS")
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        srcs = [os.path.join(ROOT, "oracle", f) for f in os.listdir(os.path.join(ROOT, "oracle"))
+                if f.startswith("oracle") and f.endswith((".c", ".h"))]
+        if (not os.path.exists(ORACLE_SO)) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+        L = C.CDLL(ORACLE_SO)
+        L.orc_pixel_cmp.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]
+        L.orc_pixel_cmp_batch.argtypes = [C.c_int, C.c_int, u8p, C.c_ssize_t, u8p, C.c_ssize_t, candp, C.c_int, i32p]
+        L.orc_pixel_cmp_mvfield.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t,
+                                            C.c_int, C.c_int, C.c_int, i16p, i32p]
+        L.orc_cost_mv_table.argtypes = [u16p, C.c_int, C.c_int]
+        _oracle = L
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_SO)
+        L.xref_open.restype = C.c_void_p
+        L.xref_open.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+        L.xref_close.argtypes = [C.c_void_p]
+        L.xref_param.argtypes = [C.c_void_p, C.c_char_p]
+        L.xref_pixel_cmp.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]
+        L.xref_pixel_cmp_batch.argtypes = [C.c_int, C.c_int, u8p, C.c_ssize_t, u8p, C.c_ssize_t, candp, C.c_int, i32p]
+        L.xref_cost_mv_table.argtypes = [C.c_void_p, u16p, C.c_int]
+        _ref = L
+    return _ref
+
+
+def ptr(a, off=0):
+    """address of numpy array element at flat byte offset `off`"""
+    return C.c_void_p(a.ctypes.data + off)
+
+
+class PaddedPlane:
+    """u8 plane with a PAD-pixel border, x264 layout: data[(y+PAD)*stride + x+PAD]"""
+
+    def __init__(self, width, height, stride=None, pad=PAD):
+        self.w, self.h, self.pad = width, height, pad
+        self.stride = stride or ((width + 2 * pad + 63) // 64 * 64)
+        self.buf = np.zeros((height + 2 * pad) * self.stride, dtype=np.uint8)
+        self.origin = pad * self.stride + pad
+
+    def view(self):
+        return self.buf.reshape(self.h + 2 * self.pad, self.stride)
+
+    def inner(self):
+        return self.view()[self.pad:self.pad + self.h, self.pad:self.pad + self.w]
+
+    def fill_border(self):
+        v = self.view()
+        p, w, h = self.pad, self.w, self.h
+        v[p:p + h, :p] = v[p:p + h, p:p + 1]
+        v[p:p + h, p + w:p + w + p] = v[p:p + h, p + w - 1:p + w]
+        v[:p, :w + 2 * p] = v[p:p + 1, :w + 2 * p]
+        v[p + h:, :w + 2 * p] = v[p + h - 1:p + h, :w + 2 * p]
+        return self
+
+    def off(self, x, y):
+        return self.origin + y * self.stride + x
+
+
+def worst_case_pair(n, rng):
+    """checkasm-style overflow patterns (tools/checkasm.c:381-394): maxed alternating differences"""
+    a = np.zeros(n, np.uint8)
+    b = np.zeros(n, np.uint8)
+    pat = rng.integers(0, 4)
+    idx = np.arange(n)
+    if pat == 0:
+        a[:] = 255
+    elif pat == 1:
+        b[:] = 255
+    elif pat == 2:
+        a[idx % 2 == 0] = 255
+        b[idx % 2 == 1] = 255
+    else:
+        a[(idx // 4) % 2 == 0] = 255
+        b[(idx // 4) % 2 == 1] = 255
+    return a, b
+
+
+def _bind_mc():
+    o, r = oracle(), (ref() if have_ref() else None)
+    vp, ss, ci = C.c_void_p, C.c_ssize_t, C.c_int
+    o.orc_frame_init_lowres.argtypes = [vp, ss, ci, ci, C.POINTER(vp), ss, ci, ci]
+    o.orc_hpel_filter_plane.argtypes = [vp, ss, ci, ci, vp, vp, vp, ss, ci]
+    o.orc_mc_luma.argtypes = [vp, ss, C.POINTER(vp), ss, ci, ci, ci, ci, vp]
+    o.orc_pixel_avg.argtypes = [vp, ss, vp, ss, vp, ss, ci, ci, ci]
+    if r is not None:
+        r.xref_mc_luma.argtypes = [vp, ss, vp, vp, vp, vp, ss] + [ci] * 8
+        r.xref_get_ref.argtypes = [vp, ss, vp, vp, vp, vp, ss] + [ci] * 8
+        r.xref_avg.argtypes = [ci, vp, ss, vp, ss, vp, ss, ci]
+        r.xref_frame_lowres.argtypes = [vp, vp, ss, vp]
+        r.xref_frame_hpel.argtypes = [vp, vp, ss, vp, vp]
+
+
+class OrcWeight(C.Structure):
+    _fields_ = [("enabled", C.c_int), ("scale", C.c_int), ("denom", C.c_int), ("offset", C.c_int)]
+
+
+def synth_luma(width, height, seed, kind="texture"):
+    """deterministic synthetic luma: smooth low-pass texture + noise, or pure noise"""
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, (height, width), dtype=np.uint8)
+    base = rng.integers(0, 256, (height // 8 + 3, width // 8 + 3)).astype(np.float32)
+    up = np.kron(base, np.ones((8, 8), np.float32))
+    k = np.ones(9, np.float32) / 9
+    up = np.apply_along_axis(lambda m: np.convolve(m, k, mode="same"), 0, up)
+    up = np.apply_along_axis(lambda m: np.convolve(m, k, mode="same"), 1, up)
+    img = up[4:4 + height, 4:4 + width] + rng.normal(0, 2.0, (height, width))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
