@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the x264 ME / lookahead cost path on B200 (see BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload satd|lookahead]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic input:
+  workload satd      : 16x16 SATD of every macroblock of 32 synthetic 4K frame pairs (1 036 800 candidates, each
+                       against a reference block displaced by a random full-pel vector within +-16) -- the
+                       "16x16 SATD macroblocks/s vs HBM roofline" half of BASELINE.json's metric.
+  workload lookahead : lowres lookahead frames/s at 4K (added when the lookahead kernels are in place).
+`value` is measured with the inputs resident in HBM; `e2e` goes through the host-buffer C-ABI entry point with
+pinned host memory, H2D/D2H copies inside the timed region.  Under torchrun (N>1) every rank processes its own
+batch (weak scaling, no data-path collective); timing is the max over ranks of device-event time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W4K, H4K = 3840, 2160
+PAD = 32
+N_PAIRS = 32                      # 32 x 32400 = 1 036 800 candidates ~ "1M candidates" of BASELINE config 5
+ALG_BYTES_16x16 = 2 * 16 * 16 + 4  # unique fenc block + unique ref block + one int32 result
+
+
+def x264_stride(width):
+    s = (width + 96 + 63) // 64 * 64          # align_stride(width + PADH2, 64, 1024), common/frame.c:30-36,87
+    if s % 1024 == 0:
+        s += 64
+    return s
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# synthetic input
+# ------------------------------------------------------------------------------------------------------
+def make_satd_inputs(seed, n_pairs, alloc):
+    """n_pairs padded 4K luma planes for fenc and ref (uniform random u8) + mv field"""
+    stride = x264_stride(W4K)
+    pitch = stride * (H4K + 2 * PAD)
+    rng = np.random.default_rng(seed)
+    fenc = alloc(pitch * n_pairs)
+    ref = alloc(pitch * n_pairs)
+    for buf in (fenc, ref):
+        for f in range(n_pairs):        # whole padded plane random: the border is as good as replicated data here
+            buf[f * pitch:(f + 1) * pitch] = rng.integers(0, 256, pitch, dtype=np.uint8)
+    mv = rng.integers(-16, 17, (n_pairs, H4K // 16, W4K // 16, 2)).astype(np.int16)
+    return fenc, ref, mv, stride, pitch
+
+
+def cand_list_for_frame(mv_f, stride):
+    by, bx = mv_f.shape[:2]
+    yy, xx = np.meshgrid(np.arange(by), np.arange(bx), indexing="ij")
+    org = PAD * stride + PAD
+    fo = org + yy * 16 * stride + xx * 16
+    ro = fo + mv_f[..., 1].astype(np.int64) * stride + mv_f[..., 0]
+    c = np.zeros(by * bx, dtype=[("fenc_off", np.uint32), ("ref_off", np.uint32)])
+    c["fenc_off"] = fo.reshape(-1)
+    c["ref_off"] = ro.reshape(-1)
+    return c
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own pixel table (oracle/_ref) or, if it did not travel, the oracle port
+# ------------------------------------------------------------------------------------------------------
+def cpu_satd_rate(fenc, ref, mv, stride, pitch, budget_s, n_frames_sample):
+    import _libs
+    if _libs.have_ref():
+        L, fn, kind = _libs.ref(), "xref_pixel_cmp_batch", "reference"
+    else:
+        L, fn, kind = _libs.oracle(), "orc_pixel_cmp_batch", "port"
+    f = getattr(L, fn)
+    cores = os.cpu_count() or 1
+    frames = list(range(min(n_frames_sample, mv.shape[0])))
+    cands = [cand_list_for_frame(mv[i], stride) for i in frames]
+    outs = [np.zeros(len(c), np.int32) for c in cands]
+
+    def work(tid, reps):
+        for _ in range(reps):
+            for i in frames[tid::cores]:
+                fv = fenc[i * pitch:(i + 1) * pitch]
+                rv = ref[i * pitch:(i + 1) * pitch]
+                f(2, 0, fv, stride, rv, stride, cands[i], len(cands[i]), outs[i])
+
+    def run(reps):
+        th = [threading.Thread(target=work, args=(t, reps)) for t in range(cores)]
+        t0 = time.perf_counter()
+        [t.start() for t in th]
+        [t.join() for t in th]
+        return time.perf_counter() - t0
+
+    t1 = run(1)
+    reps = max(1, int(budget_s / max(t1, 1e-3)))
+    t = run(reps)
+    n = reps * sum(len(c) for c in cands)
+    return n / t, kind, cores, "%d x %d 4K frames (%d candidates) on %d threads, %.1f s" % (reps, len(frames), n, cores, t)
+
+
+# ------------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        torch.cuda.set_device(local)
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_
+    return rank, world, local, dist
+
+
+def max_over_ranks(dist, v, local):
+    if dist is None:
+        return v
+    import torch
+    t = torch.tensor([v], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(local)
+
+
+def run_satd_b200(args, rank, world, local, dist):
+    import x264_b200 as x
+    ctx = x.Context(local)
+    info = ctx.device_info()
+    pinned = lambda n: ctx.malloc_host(n)
+    fenc, ref, mv, stride, pitch = make_satd_inputs(1 + rank, N_PAIRS, pinned)
+    n_cand = mv.shape[0] * mv.shape[1] * mv.shape[2]
+    d_fenc, d_ref = ctx.malloc(fenc.nbytes + 256), ctx.malloc(ref.nbytes + 256)
+    ctx.h2d(d_fenc, fenc)
+    ctx.h2d(d_ref, ref)
+    d_mv = ctx.upload(mv)
+    d_out = ctx.malloc(n_cand * 4)
+    org = PAD * stride + PAD
+    pf = (d_fenc + org, stride, pitch, W4K, H4K, N_PAIRS)
+    pr = (d_ref + org, stride, pitch, W4K, H4K, N_PAIRS)
+
+    def step():
+        ctx.pixel_cmp_mvfield(x.SATD, 0, pf, pr, 1, d_mv, d_out)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.sync()
+    sampler = ClockSampler(local)
+    barrier(dist, local)
+    sampler.start()
+    l0 = ctx.launches
+    t_wall0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop()
+    ctx.sync()
+    barrier(dist, local)
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launches - l0
+    ms = max_over_ranks(dist, ms, local)
+    clocks = sampler.stop()
+
+    # correctness spot check of the timed output against the checker (not part of the timed region)
+    import _libs
+    got = ctx.download(d_out, (n_cand,), np.int32)[:32400]
+    want = np.zeros(32400, np.int32)
+    c0 = cand_list_for_frame(mv[0], stride)
+    (_libs.ref().xref_pixel_cmp_batch if _libs.have_ref() else _libs.oracle().orc_pixel_cmp_batch)(
+        2, 0, fenc[:pitch], stride, ref[:pitch], stride, c0, len(c0), want)
+    parity_ok = bool(np.array_equal(got, want))
+
+    # e2e: host planes -> C-ABI host entry point -> host costs, copies inside the timed region
+    e2e_steps = max(1, min(args.steps, 5))
+    ctx.pixel_cmp_mvfield_host(x.SATD, 0, fenc, ref, stride, pitch, W4K, H4K, N_PAIRS, 1, mv)   # warm (allocs scratch)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out_h = ctx.pixel_cmp_mvfield_host(x.SATD, 0, fenc, ref, stride, pitch, W4K, H4K, N_PAIRS, 1, mv)
+    barrier(dist, local)
+    e2e_s = max_over_ranks(dist, time.perf_counter() - t0, local)
+    parity_ok &= bool(np.array_equal(out_h[:32400], want))
+
+    kernel_ms = ms / args.steps
+    peaks, peak_src = measured_peaks()
+    achieved = ALG_BYTES_16x16 * n_cand / (kernel_ms * 1e-3) / 1e9
+    res = {
+        "metric": "satd_16x16_macroblocks_per_sec_4k", "value": n_cand * world / (kernel_ms * 1e-3), "unit": "macroblocks/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4] at 4K: 16x16 SATD, %d candidates per GPU = every macroblock of %d "
+                               "random 3840x2160 luma frame pairs, ref displaced by a random full-pel mv in +-16" % (n_cand, N_PAIRS),
+                   "l2": "inputs %.0f MB per step > 126 MB L2, no flush needed" % ((fenc.nbytes + ref.nbytes) / 1e6),
+                   "kernel": "mvfield_kernel<SATD,16,16> TMA tile 128x64 +-16 halo, 2-stage", "parity_spot_check": parity_ok},
+        "clocks": clocks,
+        "e2e": {"value": n_cand * world * e2e_steps / e2e_s, "unit": "macroblocks/s",
+                "h2d_bytes_per_step": int(fenc.nbytes + ref.nbytes + mv.nbytes), "d2h_bytes_per_step": int(n_cand * 4),
+                "api": "x264cu_pixel_cmp_mvfield_host (pinned host planes)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ALG_BYTES_16x16 * n_cand, "kernel": "mvfield_kernel<SATD,16,16>"},
+        "wall_s": t_wall, "sm_count": info["sm_count"],
+    }
+    if rank == 0 and world == 1:
+        rate, kind, cores, sample = cpu_satd_rate(fenc, ref, mv, stride, pitch, args.cpu_budget, 8)
+        res["cpu_baseline"] = {"value": rate, "unit": "macroblocks/s", "cores": cores, "kind": kind, "sample": sample}
+    ctx.close()
+    return res
+
+
+def run_satd_reference(args, rank, world):
+    alloc = lambda n: np.empty(n, np.uint8)
+    fenc, ref, mv, stride, pitch = make_satd_inputs(1, 8, alloc)
+    rates = []
+    kind = cores = sample = None
+    for i in range(args.warmup + args.steps):
+        r, kind, cores, sample = cpu_satd_rate(fenc, ref, mv, stride, pitch, args.cpu_budget / max(1, args.steps), 8)
+        if i >= args.warmup:
+            rates.append(r)
+    v = float(np.mean(rates))
+    n_step = 8 * 32400
+    return {
+        "impl": "reference", "metric": "satd_16x16_macroblocks_per_sec_4k", "value": v, "unit": "macroblocks/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_step / v * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4] at 4K: 16x16 SATD, bounded sample of 8 of the 32 frame pairs per step"},
+        "cpu_baseline": {"value": v, "unit": "macroblocks/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "macroblocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference C path (pixf.satd[PIXEL_16x16], common/pixel.c:312); x86 asm unavailable: no nasm in the image",
+    }
+
+
+WORKLOADS = {"satd": (run_satd_b200, run_satd_reference)}
+DEFAULT_WORKLOAD = "satd"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if rank != 0:
+            return 0
+        print(json.dumps(WORKLOADS[args.workload or DEFAULT_WORKLOAD][1](args, rank, world)))
+        return 0
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    res = WORKLOADS[args.workload or DEFAULT_WORKLOAD][0](args, rank, world, local, dist)
+    if rank == 0:
+        print(json.dumps(res))
+    if dist is not None:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,136 @@
+/*
+ * x264_b200 -- B200-native (sm_100a) backend for x264's motion-estimation / lookahead cost path.
+ *
+ * C ABI (plain pointers and sizes, no C++/torch types).  These are the entry points a host written in C
+ * (the x264 encoder itself) binds; INTEGRATION.md shows the glue on the reference side.
+ * Every entry cites the reference interface it replaces (paths relative to jpsdr/x264).
+ *
+ * Conventions
+ *   - all functions return 0 on success, -1 on failure; x264cu_strerror() gives the reason.  There is no
+ *     CPU fallback anywhere: a missing device or a failed launch is an error.
+ *   - "d_" pointers are device (HBM) pointers, "h_" pointers are host pointers.
+ *   - planes are 8-bit luma in the reference's padded frame layout (common/frame.c:75-130): pixel (x,y)
+ *     lives at origin + y*stride + x and a border of X264CU_PAD pixels around the picture is readable.
+ *   - block-size indices are the reference's PIXEL_16x16 .. PIXEL_4x16 (common/pixel.h:37-52).
+ *   - calls on one context are serialised on that context's stream (the reference calls its OpenCL hooks
+ *     from exactly one thread too, encoder/lookahead.c:90).
+ */
+#ifndef X264_B200_H
+#define X264_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X264CU_PAD 32                      /* PADH / PADV, common/frame.h:32-33 */
+#define X264CU_BFRAME_MAX 16               /* X264_BFRAME_MAX, common/base.h:136 */
+
+enum x264cu_pixel_e                        /* common/pixel.h:37-52 */
+{
+    X264CU_PIXEL_16x16 = 0, X264CU_PIXEL_16x8 = 1, X264CU_PIXEL_8x16 = 2, X264CU_PIXEL_8x8 = 3,
+    X264CU_PIXEL_8x4 = 4, X264CU_PIXEL_4x8 = 5, X264CU_PIXEL_4x4 = 6, X264CU_PIXEL_4x16 = 7,
+    X264CU_PIXEL_NB = 8
+};
+
+enum x264cu_metric_e                       /* members of x264_pixel_function_t, common/pixel.h:78-144 */
+{
+    X264CU_SAD = 0,                        /* pixf.sad[]   common/pixel.c:55-80   */
+    X264CU_SSD = 1,                        /* pixf.ssd[]   common/pixel.c:85-110  */
+    X264CU_SATD = 2,                       /* pixf.satd[]  common/pixel.c:242-332 */
+    X264CU_SA8D = 3                        /* pixf.sa8d[]  common/pixel.c:334-381 (16x16 and 8x8 only) */
+};
+
+enum x264cu_me_e { X264CU_ME_DIA = 0, X264CU_ME_HEX = 1, X264CU_ME_UMH = 2 };   /* x264.h X264_ME_* */
+
+typedef struct x264cu_ctx x264cu_ctx_t;
+
+/* ------------------------------------------------------------------------------------------------
+ * context -- replaces x264_opencl_load_library / x264_opencl_lookahead_init / _delete
+ * (common/opencl.h:796-804, common/opencl.c:53, :411, :596).
+ * ---------------------------------------------------------------------------------------------- */
+int         x264cu_open( x264cu_ctx_t **ctx, int device );
+void        x264cu_close( x264cu_ctx_t *ctx );
+const char *x264cu_strerror( x264cu_ctx_t *ctx );            /* ctx may be NULL: last open() failure */
+int         x264cu_device_info( x264cu_ctx_t *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes );
+void       *x264cu_stream( x264cu_ctx_t *ctx );              /* the cudaStream_t all work is enqueued on */
+int         x264cu_sync( x264cu_ctx_t *ctx );                /* x264_opencl_flush, encoder/slicetype-cl.c:58 */
+/* number of kernels this context has launched since open (bench.py's gpu_launches) */
+uint64_t    x264cu_launch_count( x264cu_ctx_t *ctx );
+
+/* device-side stopwatch on the context's stream (CUDA events); used by bench.py for kernel timing */
+int         x264cu_timer_start( x264cu_ctx_t *ctx );
+int         x264cu_timer_stop( x264cu_ctx_t *ctx, float *elapsed_ms );    /* synchronises */
+
+/* device memory, so that a C host needs no CUDA headers */
+void *x264cu_malloc( x264cu_ctx_t *ctx, size_t bytes );
+void  x264cu_free( x264cu_ctx_t *ctx, void *d_ptr );
+void *x264cu_malloc_host( x264cu_ctx_t *ctx, size_t bytes );  /* page-locked staging (opencl.h:718) */
+void  x264cu_free_host( x264cu_ctx_t *ctx, void *h_ptr );
+int   x264cu_memcpy_h2d( x264cu_ctx_t *ctx, void *d_dst, const void *h_src, size_t bytes );
+int   x264cu_memcpy_d2h( x264cu_ctx_t *ctx, void *h_dst, const void *d_src, size_t bytes );
+int   x264cu_memset( x264cu_ctx_t *ctx, void *d_dst, int value, size_t bytes );
+
+/* ------------------------------------------------------------------------------------------------
+ * B1: batched twins of the x264_pixel_function_t table (common/pixel.h:78-144).
+ * A GPU cannot sit behind int cmp(pixel*,intptr_t,pixel*,intptr_t) one 256-byte block at a time, so
+ * each table entry is exported as "the same function over an array of candidates".
+ * ---------------------------------------------------------------------------------------------- */
+
+/* one candidate = one call of x264_pixel_cmp_t (common/pixel.h:33): byte offsets of the two blocks */
+typedef struct { uint32_t fenc_off, ref_off; } x264cu_cand_t;
+/* one x4 call (common/pixel.h:35): one fenc block against four reference blocks; x3 uses n_refs = 3 */
+typedef struct { uint32_t fenc_off, ref_off[4]; } x264cu_cand_x4_t;
+
+/* out[i] = pixf.<metric>[i_pixel]( d_fenc + cand[i].fenc_off, fenc_stride, d_ref + cand[i].ref_off, ref_stride ) */
+int x264cu_pixel_cmp_batch( x264cu_ctx_t *ctx, int metric, int i_pixel,
+                            const uint8_t *d_fenc, intptr_t fenc_stride,
+                            const uint8_t *d_ref, intptr_t ref_stride,
+                            const x264cu_cand_t *d_cand, int n, int32_t *d_out );
+
+/* pixf.sad_x3/x4, satd_x3/x4 (common/pixel.c:441-496): out[i*4+j], j < n_refs */
+int x264cu_pixel_cmp_x4_batch( x264cu_ctx_t *ctx, int metric, int i_pixel, int n_refs,
+                               const uint8_t *d_fenc, intptr_t fenc_stride,
+                               const uint8_t *d_ref, intptr_t ref_stride,
+                               const x264cu_cand_x4_t *d_cand, int n, int32_t *d_out );
+
+/* Host-buffer form of x264cu_pixel_cmp_batch: copies both planes and the candidate list to the device,
+ * runs the kernel, copies the costs back (what an encoder thread holding host frames would call). */
+int x264cu_pixel_cmp_batch_host( x264cu_ctx_t *ctx, int metric, int i_pixel,
+                                 const uint8_t *h_fenc, size_t fenc_bytes, intptr_t fenc_stride,
+                                 const uint8_t *h_ref, size_t ref_bytes, intptr_t ref_stride,
+                                 const x264cu_cand_t *h_cand, int n, int32_t *h_out );
+
+/* A stack of equally sized padded planes in HBM (e.g. the luma planes of consecutive frames). */
+typedef struct
+{
+    const uint8_t *d_origin;   /* pixel (0,0) of plane 0 */
+    intptr_t stride;           /* bytes per row, multiple of 16 */
+    intptr_t plane_pitch;      /* bytes between consecutive planes, multiple of 16 */
+    int width, height;         /* picture size; X264CU_PAD pixels around it are readable */
+    int n_planes;
+} x264cu_planes_t;
+
+/* MV-field form: the picture is tiled into blocks of size i_pixel; block (bx,by) of plane f is compared with the
+ * reference block displaced by the full-pel vector mv = d_mv[((k*n_planes + f)*blocks_y + by)*blocks_x + bx]
+ * (int16 x, int16 y), |mv| <= X264CU_PAD.  out has the same indexing.  This is the shape in which
+ * x264_me_search_ref evaluates candidates (encoder/me.c:63-141 COST_MV*): every block of the frame, one
+ * displaced reference block each, k_cands times.  Reference tiles (+halo) are staged through shared
+ * memory with TMA, so each byte of both planes crosses HBM once. */
+int x264cu_pixel_cmp_mvfield( x264cu_ctx_t *ctx, int metric, int i_pixel,
+                              const x264cu_planes_t *fenc, const x264cu_planes_t *ref,
+                              int k_cands, const int16_t *d_mv, int32_t *d_out );
+
+/* host-buffer form (planes and mv field on the host, padded layout as above; h_*_base = first byte of the
+ * allocation, i.e. origin - X264CU_PAD*stride - X264CU_PAD) */
+int x264cu_pixel_cmp_mvfield_host( x264cu_ctx_t *ctx, int metric, int i_pixel,
+                                   const uint8_t *h_fenc_base, const uint8_t *h_ref_base,
+                                   intptr_t stride, intptr_t plane_pitch, int width, int height, int n_planes,
+                                   int k_cands, const int16_t *h_mv, int32_t *h_out );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,46 @@
+// Internal context shared by the translation units of libx264_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/x264_b200.h"
+
+struct x264cu_ctx
+{
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    std::string err;
+    // driver entry point for TMA descriptors (no link-time libcuda dependency)
+    CUresult (*encode_tiled)( CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill ) = nullptr;
+    // scratch for the *_host entry points (grown on demand)
+    void *scratch[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    size_t scratch_bytes[6] = { 0, 0, 0, 0, 0, 0 };
+    struct x264cu_lookahead *lookahead = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+int  x264cu_fail( x264cu_ctx *ctx, const char *fmt, ... );
+void *x264cu_scratch( x264cu_ctx *ctx, int slot, size_t bytes );
+
+#define CU_CHECK( ctx, call )                                                                      \
+    do {                                                                                           \
+        cudaError_t e_ = ( call );                                                                 \
+        if( e_ != cudaSuccess )                                                                    \
+            return x264cu_fail( ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString( e_ ) ); \
+    } while( 0 )
+
+#define CU_LAUNCH_CHECK( ctx )                                                                     \
+    do {                                                                                           \
+        ( ctx )->launches++;                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if( e_ != cudaSuccess )                                                                    \
+            return x264cu_fail( ctx, "%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString( e_ ) ); \
+    } while( 0 )
