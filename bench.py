@@ -141,10 +141,13 @@ def cpu_satd_rate(fenc, ref, mv, stride, pitch, budget_s, n_frames_sample):
 
     def work(tid, reps):
         for _ in range(reps):
-            for i in frames[tid::cores]:
-                fv = fenc[i * pitch:(i + 1) * pitch]
-                rv = ref[i * pitch:(i + 1) * pitch]
-                f(2, 0, fv, stride, rv, stride, cands[i], len(cands[i]), outs[i])
+            for i in frames:
+                n = len(cands[i])
+                lo, hi = n * tid // cores, n * (tid + 1) // cores
+                if hi > lo:
+                    fv = fenc[i * pitch:(i + 1) * pitch]
+                    rv = ref[i * pitch:(i + 1) * pitch]
+                    f(2, 0, fv, stride, rv, stride, cands[i][lo:hi], hi - lo, outs[i][lo:hi])
 
     def run(reps):
         th = [threading.Thread(target=work, args=(t, reps)) for t in range(cores)]
@@ -239,7 +242,7 @@ def run_satd_b200(args, rank, world, local, dist):
     parity_ok = bool(np.array_equal(got, want))
 
     # e2e: host planes -> C-ABI host entry point -> host costs, copies inside the timed region
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 5)) if not args.quick else 1
     ctx.pixel_cmp_mvfield_host(x.SATD, 0, fenc, ref, stride, pitch, W4K, H4K, N_PAIRS, 1, mv)   # warm (allocs scratch)
     barrier(dist, local)
     t0 = time.perf_counter()
@@ -270,7 +273,7 @@ def run_satd_b200(args, rank, world, local, dist):
                      "algorithmic_bytes_per_launch": ALG_BYTES_16x16 * n_cand, "kernel": "mvfield_kernel<SATD,16,16>"},
         "wall_s": t_wall, "sm_count": info["sm_count"],
     }
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.quick:
         rate, kind, cores, sample = cpu_satd_rate(fenc, ref, mv, stride, pitch, args.cpu_budget, 8)
         res["cpu_baseline"] = {"value": rate, "unit": "macroblocks/s", "cores": cores, "kind": kind, "sample": sample}
     ctx.close()
@@ -311,6 +314,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
 
     if args.impl == "reference":

@@ -239,3 +239,73 @@ XREF_API void xref_cost_mv_table( void *hv, uint16_t *out, int len )
     for( int i = -len; i <= len; i++ )
         out[len+i] = h->cost_mv[X264_LOOKAHEAD_QP][i];
 }
+
+/* ------------------------------------------------------------------ motion search ------------------- */
+typedef struct
+{
+    int i_pixel, me_method, subpel_refine, me_range, qp;
+    int mv_min_spel[2], mv_max_spel[2];
+    int16_t mvp[2];
+    int i_mvc;
+    int16_t mvc[16][2];
+    int wt_en, wt_scale, wt_denom, wt_offset;
+    int use_thresh, halfpel_thresh;
+    /* out */
+    int16_t mv[2];
+    int cost, cost_mv, thresh_out;
+} xref_me_args_t;
+
+/* Drives the reference's x264_me_search_ref (encoder/me.c:182) on caller-supplied planes.
+ * fref[0..3] = F,H,V,C plane pointers at the block origin, fref_w = weighted full-pel plane (or fref[0]). */
+XREF_API void xref_me_search( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
+                              uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride )
+{
+    x264_t *h = hv;
+    tables_init();
+    ALIGNED_ARRAY_64( pixel, fenc_buf,[16*16] );
+    int bw = x264_pixel_size[a->i_pixel].w, bh = x264_pixel_size[a->i_pixel].h;
+    for( int y = 0; y < bh; y++ )
+        memcpy( fenc_buf + y*FENC_STRIDE, fenc + y*fenc_stride, bw );
+    x264_weight_t wt; make_weight( &wt, a->wt_en, a->wt_scale, a->wt_denom, a->wt_offset );
+    if( a->wt_en ) wt.weightfn = h->mc.weight;
+    x264_me_t m;
+    memset( &m, 0, sizeof(m) );
+    m.i_pixel = a->i_pixel;
+    m.p_cost_mv = h->cost_mv[a->qp];
+    m.i_ref_cost = 0;
+    m.i_ref = 0;
+    m.weight = &wt;
+    m.p_fref[0] = f0; m.p_fref[1] = f1; m.p_fref[2] = f2; m.p_fref[3] = f3;
+    m.p_fref_w = fref_w;
+    m.p_fenc[0] = fenc_buf;
+    m.i_stride[0] = stride;
+    m.mvp[0] = a->mvp[0]; m.mvp[1] = a->mvp[1];
+    int save_range = h->param.analyse.i_me_range;
+    h->param.analyse.i_me_range = a->me_range;
+    h->mb.i_me_method = a->me_method;
+    h->mb.i_subpel_refine = a->subpel_refine;
+    h->mb.b_chroma_me = 0;
+    for( int i = 0; i < 2; i++ )
+    {
+        h->mb.mv_min_spel[i] = a->mv_min_spel[i];
+        h->mb.mv_max_spel[i] = a->mv_max_spel[i];
+        h->mb.mv_limit_fpel[0][i] = a->mv_min_spel[i] >> 2;
+        h->mb.mv_limit_fpel[1][i] = a->mv_max_spel[i] >> 2;
+    }
+    ALIGNED_ARRAY_8( int16_t, mvc,[16],[2] );
+    memcpy( mvc, a->mvc, sizeof(mvc) );
+    int thresh = a->halfpel_thresh;
+    x264_me_search_ref( h, &m, mvc, a->i_mvc, a->use_thresh ? &thresh : NULL );
+    h->param.analyse.i_me_range = save_range;
+    a->mv[0] = m.mv[0]; a->mv[1] = m.mv[1];
+    a->cost = m.cost; a->cost_mv = m.cost_mv;
+    a->thresh_out = thresh;
+}
+
+XREF_API void xref_cost_mv_table_qp( void *hv, int qp, uint16_t *out, int len )
+{
+    x264_t *h = hv;
+    for( int i = -len; i <= len; i++ )
+        out[len+i] = h->cost_mv[qp][i];
+}
+XREF_API int xref_lambda( int qp ) { return x264_lambda_tab[qp]; }

@@ -144,3 +144,47 @@ def synth_luma(width, height, seed, kind="texture"):
     up = np.apply_along_axis(lambda m: np.convolve(m, k, mode="same"), 1, up)
     img = up[4:4 + height, 4:4 + width] + rng.normal(0, 2.0, (height, width))
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+class XrefMeArgs(C.Structure):
+    _fields_ = [("i_pixel", C.c_int), ("me_method", C.c_int), ("subpel_refine", C.c_int), ("me_range", C.c_int),
+                ("qp", C.c_int), ("mv_min_spel", C.c_int * 2), ("mv_max_spel", C.c_int * 2), ("mvp", C.c_int16 * 2),
+                ("i_mvc", C.c_int), ("mvc", (C.c_int16 * 2) * 16),
+                ("wt_en", C.c_int), ("wt_scale", C.c_int), ("wt_denom", C.c_int), ("wt_offset", C.c_int),
+                ("use_thresh", C.c_int), ("halfpel_thresh", C.c_int),
+                ("mv", C.c_int16 * 2), ("cost", C.c_int), ("cost_mv", C.c_int), ("thresh_out", C.c_int)]
+
+
+class OrcMeCtx(C.Structure):
+    _fields_ = [("me_method", C.c_int), ("subpel_refine", C.c_int), ("me_range", C.c_int), ("mbcmp_is_satd", C.c_int),
+                ("mv_min_spel", C.c_int * 2), ("mv_max_spel", C.c_int * 2), ("mv_limit_fpel", (C.c_int * 2) * 2)]
+
+
+class OrcMe(C.Structure):
+    _fields_ = [("i_pixel", C.c_int), ("p_cost_mv", C.c_void_p), ("p_fref", C.c_void_p * 4), ("p_fref_w", C.c_void_p),
+                ("p_fenc", C.c_void_p), ("fenc_stride", C.c_ssize_t), ("stride", C.c_ssize_t), ("weight", OrcWeight),
+                ("mvp", C.c_int16 * 2), ("cost_mv", C.c_int), ("cost", C.c_int), ("mv", C.c_int16 * 2)]
+
+
+def _bind_me():
+    o = oracle()
+    o.orc_me_search_ref.argtypes = [C.POINTER(OrcMeCtx), C.POINTER(OrcMe), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    if have_ref():
+        r = ref()
+        vp = C.c_void_p
+        r.xref_me_search.argtypes = [vp, C.POINTER(XrefMeArgs), vp, C.c_ssize_t, vp, vp, vp, vp, vp, C.c_ssize_t]
+        r.xref_cost_mv_table_qp.argtypes = [vp, C.c_int, u16p, C.c_int]
+
+
+def make_ref_planes(luma, stride=None):
+    """F plane + H,V,C half-pel planes (all padded, border filled) of a luma picture, via the oracle"""
+    _bind_mc()
+    h, w = luma.shape
+    F = PaddedPlane(w, h, stride=stride)
+    F.inner()[:] = luma
+    F.fill_border()
+    H, V, Cc = PaddedPlane(w, h, stride=F.stride), PaddedPlane(w, h, stride=F.stride), PaddedPlane(w, h, stride=F.stride)
+    src = np.ascontiguousarray(luma)
+    oracle().orc_hpel_filter_plane(ptr(src), w, w, h, ptr(H.buf, H.origin), ptr(V.buf, V.origin), ptr(Cc.buf, Cc.origin),
+                                   F.stride, PAD)
+    return [F, H, V, Cc]

@@ -13,6 +13,7 @@
 // bound is HBM bandwidth: 2*W*H + 4 algorithmic bytes per candidate.
 #include "ctx.h"
 #include "pixel_dev.cuh"
+#include <stdlib.h>
 
 using namespace x264cu;
 
@@ -143,9 +144,12 @@ mvfield_kernel( const __grid_constant__ CUtensorMap tm_fenc, const __grid_consta
 {
     using G = BlockGeom<BW, BH>;
     using T = TileCfg<TW, TH, R>;
+    static_assert( T::FP == T::RP, "fenc and ref tiles share one row pitch" );
+    constexpr int PITCH = T::FP;
     constexpr bool PERM = METRIC != M_SA8D;            // xor-permuted row order (bank spreading); see DESIGN.md
     constexpr int REG_X = TW / 32, REG_Y = TH / 16, N_REG = REG_X * REG_Y;
-    constexpr int TASKS_PER_WARP = ( N_REG + NWARPS - 1 ) / NWARPS;
+    static_assert( N_REG % NWARPS == 0, "regions must divide evenly over the warps" );
+    constexpr int TASKS_PER_WARP = N_REG / NWARPS;
 
     extern __shared__ __align__( 1024 ) uint8_t smem[];
     uint64_t *full = (uint64_t *)( smem + NSTAGE * T::STAGE_BYTES + 64 );
@@ -160,98 +164,130 @@ mvfield_kernel( const __grid_constant__ CUtensorMap tm_fenc, const __grid_consta
     }
     __syncthreads();
 
-    auto issue = [&]( int tile, int stage ) {
-        int f = tile / ( p.tiles_x * p.tiles_y );
-        int t2 = tile - f * ( p.tiles_x * p.tiles_y );
-        int ty = t2 / p.tiles_x, tx = t2 - ty * p.tiles_x;
+    // tile cursor (tx,ty,f) advanced incrementally by gridDim.x tiles: no divisions in the loop
+    const int tiles_per_plane = p.tiles_x * p.tiles_y;
+    int f = blockIdx.x / tiles_per_plane;
+    int t2 = blockIdx.x - f * tiles_per_plane;
+    int ty = t2 / p.tiles_x, tx = t2 - ty * p.tiles_x;
+    const int step_f = gridDim.x / tiles_per_plane;
+    const int step_r = gridDim.x - step_f * tiles_per_plane;
+    const int step_y = step_r / p.tiles_x, step_x = step_r - step_y * p.tiles_x;
+    auto advance = [&]( int &ax, int &ay, int &af ) {
+        ax += step_x;
+        if( ax >= p.tiles_x ) { ax -= p.tiles_x; ay++; }
+        ay += step_y;
+        if( ay >= p.tiles_y ) { ay -= p.tiles_y; af++; }
+        af += step_f;
+    };
+    auto issue = [&]( int ax, int ay, int af, int stage ) {
         uint8_t *dst = smem + stage * T::STAGE_BYTES;
         mbar_expect_tx( &full[stage], T::STAGE_BYTES );
         // tensor coordinates are relative to (-PAD,-PAD) of the padded plane
-        tma_load_3d( dst, &tm_fenc, &full[stage], X264CU_PAD + tx * TW, X264CU_PAD + ty * TH, f );
-        tma_load_3d( dst + T::FENC_BYTES, &tm_ref, &full[stage], X264CU_PAD + tx * TW - R, X264CU_PAD + ty * TH - R, f );
+        tma_load_3d( dst, &tm_fenc, &full[stage], X264CU_PAD + ax * TW, X264CU_PAD + ay * TH, af );
+        tma_load_3d( dst + T::FENC_BYTES, &tm_ref, &full[stage], X264CU_PAD + ax * TW - R, X264CU_PAD + ay * TH - R, af );
     };
 
+    // producer cursor runs NSTAGE tiles ahead of the consumer cursor (thread 0 only)
+    int ptx = tx, pty = ty, pf = f, ptile = blockIdx.x;
     if( threadIdx.x == 0 )
         for( int s = 0; s < NSTAGE; s++ )
         {
-            int tile = blockIdx.x + s * gridDim.x;
-            if( tile < p.n_tiles ) issue( tile, s );
+            if( ptile < p.n_tiles ) issue( ptx, pty, pf, s );
+            advance( ptx, pty, pf );
+            ptile += gridDim.x;
         }
 
+    // lane-constant geometry of this warp's tasks
+    int lane_sm[TASKS_PER_WARP];       // byte offset of the lane's 4x4 inside a tile (row 0 of its sub-block)
+    int lane_blk[TASKS_PER_WARP];      // block index offset inside the plane's block grid
+    int lane_px[TASKS_PER_WARP], lane_py[TASKS_PER_WARP];
+#pragma unroll
+    for( int t = 0; t < TASKS_PER_WARP; t++ )
+    {
+        int reg = warp + t * NWARPS;
+        int ry = reg / REG_X, rx = reg - ry * REG_X;
+        lane_px[t] = rx * 32 + 4 * qx;
+        lane_py[t] = ry * 16 + 4 * qy;
+        lane_sm[t] = lane_py[t] * PITCH + lane_px[t];
+        lane_blk[t] = ( lane_py[t] / BH ) * p.blocks_x + lane_px[t] / BW;
+    }
+    int row_off[4];
+#pragma unroll
+    for( int j = 0; j < 4; j++ ) row_off[j] = ( PERM ? ( j ^ qy ) : j ) * PITCH;
+
     const int blocks_per_plane = p.blocks_x * p.blocks_y;
+    const size_t k_stride = (size_t)p.n_planes * blocks_per_plane;
+    const bool lead = G::leader( lane );
     int it = 0;
     for( int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++ )
     {
         const int stage = it % NSTAGE;
         const uint32_t parity = ( it / NSTAGE ) & 1;
-        int f = tile / ( p.tiles_x * p.tiles_y );
-        int t2 = tile - f * ( p.tiles_x * p.tiles_y );
-        int ty = t2 / p.tiles_x, tx = t2 - ty * p.tiles_x;
         const int x0 = tx * TW, y0 = ty * TH;
+        const int tile_blk = ( f * p.blocks_y + y0 / BH ) * p.blocks_x + x0 / BW;
+        const bool full_tile = ( x0 + TW <= p.width ) && ( y0 + TH <= p.height );
 
-        // per-task geometry and the first candidate's vectors are fetched before waiting on the tile
-        int px[TASKS_PER_WARP], py[TASKS_PER_WARP], oidx[TASKS_PER_WARP];
+        int oidx[TASKS_PER_WARP];
         uint32_t mvw[TASKS_PER_WARP];
 #pragma unroll
         for( int t = 0; t < TASKS_PER_WARP; t++ )
         {
-            int reg = warp + t * NWARPS;
-            int ry = reg / REG_X, rx = reg - ry * REG_X;
-            px[t] = rx * 32 + 4 * qx;
-            py[t] = ry * 16 + 4 * qy;
-            bool ok = reg < N_REG && x0 + px[t] < p.width && y0 + py[t] < p.height;
-            int gbx = ( x0 + px[t] ) / BW, gby = ( y0 + py[t] ) / BH;
-            oidx[t] = ok ? ( f * p.blocks_y + gby ) * p.blocks_x + gbx : -1;
+            bool ok = full_tile || ( x0 + lane_px[t] < p.width && y0 + lane_py[t] < p.height );
+            oidx[t] = ok ? tile_blk + lane_blk[t] : -1;
             mvw[t] = ok ? __ldg( (const uint32_t *)p.mv + oidx[t] ) : 0u;
         }
 
         mbar_wait( &full[stage], parity );
-        const uint32_t *sf = (const uint32_t *)( smem + stage * T::STAGE_BYTES );
-        const uint8_t *sr8 = smem + stage * T::STAGE_BYTES + T::FENC_BYTES;
+        const uint8_t *sf = smem + stage * T::STAGE_BYTES;
+        const uint8_t *sr = sf + T::FENC_BYTES + R * PITCH + R;
 
         for( int k = 0; k < p.k_cands; k++ )
         {
 #pragma unroll
             for( int t = 0; t < TASKS_PER_WARP; t++ )
             {
-                uint32_t mvcur = mvw[t];
-                if( k + 1 < p.k_cands && oidx[t] >= 0 )      // prefetch the next candidate's vector
-                    mvw[t] = __ldg( (const uint32_t *)p.mv + (size_t)( k + 1 ) * p.n_planes * blocks_per_plane + oidx[t] );
-                if( warp + t * NWARPS >= N_REG ) continue;      // warp-uniform
-                int mx = (int16_t)( mvcur & 0xffff ), my = (int16_t)( mvcur >> 16 );
+                const uint32_t mvcur = mvw[t];
+                const int mx = (int16_t)( mvcur & 0xffff ), my = (int16_t)( mvcur >> 16 );
                 uint32_t a[4], b[4];
 #pragma unroll
                 for( int j = 0; j < 4; j++ )
-                    a[j] = sf[( ( py[t] + ( PERM ? ( j ^ qy ) : j ) ) * T::FP + px[t] ) >> 2];
-                bool inside = ( mx >= -R ) & ( mx <= R ) & ( my >= -R ) & ( my <= R );
+                    a[j] = *(const uint32_t *)( sf + lane_sm[t] + row_off[j] );
+                const bool inside = (unsigned)( mx + R ) <= 2u * R && (unsigned)( my + R ) <= 2u * R;
                 if( __all_sync( 0xffffffffu, inside ) )
                 {
-                    int rxp = px[t] + R + mx, ryp = py[t] + R + my;
-                    uint32_t sh = ( (uint32_t)rxp & 3u ) * 8u;
+                    const int o = lane_sm[t] + my * PITCH + mx;           // relative to the halo origin
+                    const uint8_t *q = sr + ( o & ~3 );
+                    const uint32_t sh = ( (uint32_t)o & 3u ) * 8u;
 #pragma unroll
                     for( int j = 0; j < 4; j++ )
                     {
-                        const uint32_t *q = (const uint32_t *)( sr8 + ( ryp + ( PERM ? ( j ^ qy ) : j ) ) * T::RP + ( rxp & ~3 ) );
-                        b[j] = funnel( q[0], q[1], sh );
+                        const uint32_t *w = (const uint32_t *)( q + row_off[j] );
+                        b[j] = funnel( w[0], w[1], sh );
                     }
                 }
                 else
                 {   // vector outside the staged halo (rare): fetch this candidate straight from global memory
                     const uint8_t *g = p.ref_origin + (intptr_t)f * p.ref_plane_pitch
-                                     + (intptr_t)( y0 + py[t] + my ) * p.ref_stride + ( x0 + px[t] + mx );
+                                     + (intptr_t)( y0 + lane_py[t] + my ) * p.ref_stride + ( x0 + lane_px[t] + mx );
 #pragma unroll
                     for( int j = 0; j < 4; j++ )
                         b[j] = oidx[t] >= 0 ? ldg_unaligned4( g + (intptr_t)( PERM ? ( j ^ qy ) : j ) * p.ref_stride ) : 0u;
                 }
+                if( k + 1 < p.k_cands && oidx[t] >= 0 )                  // next candidate's vector (uniform branch on k)
+                    mvw[t] = __ldg( (const uint32_t *)p.mv + ( k + 1 ) * k_stride + oidx[t] );
                 int v = G::reduce( metric4x4<METRIC>( a, b, lane ) );
-                if( oidx[t] >= 0 && G::leader( lane ) )
-                    p.out[(size_t)k * p.n_planes * blocks_per_plane + oidx[t]] = metric_finish<METRIC>( v );
+                if( lead && oidx[t] >= 0 )
+                    p.out[k * k_stride + oidx[t]] = metric_finish<METRIC>( v );
             }
         }
         __syncthreads();                                        // everyone is done reading this stage
-        int next = tile + NSTAGE * gridDim.x;
-        if( threadIdx.x == 0 && next < p.n_tiles )
-            issue( next, stage );
+        if( threadIdx.x == 0 )
+        {
+            if( ptile < p.n_tiles ) issue( ptx, pty, pf, stage );
+            advance( ptx, pty, pf );
+            ptile += gridDim.x;
+        }
+        advance( tx, ty, f );
     }
 }
 
@@ -321,11 +357,10 @@ static int make_tensor_map( x264cu_ctx *ctx, CUtensorMap *tm, const x264cu_plane
     return 0;
 }
 
-template <int METRIC, int BW, int BH>
+template <int METRIC, int BW, int BH, int TW = 128, int TH = 64, int R = 16, int NSTAGE = 2, int NWARPS = 4>
 static int launch_mvfield( x264cu_ctx *ctx, const x264cu_planes_t *fenc, const x264cu_planes_t *ref, int k_cands,
                            const int16_t *d_mv, int32_t *d_out )
 {
-    constexpr int TW = 128, TH = 64, R = 16, NSTAGE = 2, NWARPS = 8;
     using T = TileCfg<TW, TH, R>;
     CUtensorMap tm_fenc, tm_ref;
     if( make_tensor_map( ctx, &tm_fenc, fenc, T::FP, TH ) || make_tensor_map( ctx, &tm_ref, ref, T::RP, T::RH ) )
@@ -426,6 +461,21 @@ int x264cu_pixel_cmp_mvfield( x264cu_ctx_t *ctx, int metric, int i_pixel, const 
         return x264cu_fail( ctx, "mvfield: %dx%d is not a multiple of the %dx%d block", fenc->width, fenc->height,
                             k_pixel_w[i_pixel], k_pixel_h[i_pixel] );
     if( fenc->n_planes <= 0 ) return 0;
+    if( metric == X264CU_SATD && i_pixel == X264CU_PIXEL_16x16 )
+    {   // tuning hook (profiling only): alternative tile / pipeline shapes for the headline kernel
+        static int cfg = -1;
+        if( cfg < 0 ) { const char *e = getenv( "X264CU_MVF_CFG" ); cfg = e ? atoi( e ) : 0; }
+        switch( cfg )
+        {
+            case 1: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 2, 8>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 2: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 3, 4>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 3: return launch_mvfield<M_SATD, 16, 16, 128, 128, 16, 2, 8>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 4: return launch_mvfield<M_SATD, 16, 16, 128, 128, 16, 2, 4>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 5: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 2, 2>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 6: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 4, 4>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            default: break;
+        }
+    }
     switch( metric )
     {
         case X264CU_SAD:  MVF_SIZE( M_SAD ) break;
