@@ -126,36 +126,133 @@ struct MvFieldParams
 
 template <int TW, int TH, int R> struct TileCfg
 {
-    static constexpr int FP = TW + 32;                 // fenc smem pitch: = 32 (mod 128) keeps the 4 row groups on distinct banks
+    static constexpr int FP = TW + 32;                 // fenc smem pitch (TMA box width; 16-byte multiple)
     static constexpr int RP = TW + 2 * R;              // ref smem pitch
     static constexpr int RH = TH + 2 * R;
     static constexpr int FENC_BYTES = FP * TH;
     static constexpr int REF_BYTES = RP * RH;
     static constexpr int STAGE_BYTES = FENC_BYTES + REF_BYTES;
-    static_assert( FP % 128 == 32 && RP % 128 == 32, "smem pitches must be 32 mod 128" );
+    static_assert( FP == RP, "fenc and ref tiles share one row pitch" );
     static_assert( FP <= 256 && RP <= 256 && RH <= 256, "TMA box dimension limit" );
     static_assert( STAGE_BYTES % 128 == 0 && FENC_BYTES % 128 == 0, "TMA smem alignment" );
 };
 
+// shared-memory loads with compile-time immediates (one LDS each, no address arithmetic in the hot loop)
+template <int OFF> __device__ __forceinline__ uint32_t lds_off( uint32_t addr )
+{
+    uint32_t v;
+    asm volatile( "ld.shared.b32 %0, [%1+%2];" : "=r"( v ) : "r"( addr ), "n"( OFF ) );
+    return v;
+}
+
+// One 4-row strip of a task: the lane owns the 4x4 block at tile column 4*lane, rows S*4 .. S*4+3 of the task.
+template <int METRIC, int PITCH, int S>
+__device__ __forceinline__ void strip_load( uint32_t fenc_addr, uint32_t ref_addr, uint32_t sh, uint32_t a[4], uint32_t b[4] )
+{
+    a[0] = lds_off<( S * 4 + 0 ) * PITCH>( fenc_addr );
+    a[1] = lds_off<( S * 4 + 1 ) * PITCH>( fenc_addr );
+    a[2] = lds_off<( S * 4 + 2 ) * PITCH>( fenc_addr );
+    a[3] = lds_off<( S * 4 + 3 ) * PITCH>( fenc_addr );
+    b[0] = funnel( lds_off<( S * 4 + 0 ) * PITCH>( ref_addr ), lds_off<( S * 4 + 0 ) * PITCH + 4>( ref_addr ), sh );
+    b[1] = funnel( lds_off<( S * 4 + 1 ) * PITCH>( ref_addr ), lds_off<( S * 4 + 1 ) * PITCH + 4>( ref_addr ), sh );
+    b[2] = funnel( lds_off<( S * 4 + 2 ) * PITCH>( ref_addr ), lds_off<( S * 4 + 2 ) * PITCH + 4>( ref_addr ), sh );
+    b[3] = funnel( lds_off<( S * 4 + 3 ) * PITCH>( ref_addr ), lds_off<( S * 4 + 3 ) * PITCH + 4>( ref_addr ), sh );
+}
+
+template <int METRIC, int PITCH, int NY, int S>
+__device__ __forceinline__ int strips_metric( uint32_t fenc_addr, uint32_t ref_addr, uint32_t sh, int lane )
+{
+    if constexpr( S >= NY )
+        return 0;
+    else if constexpr( METRIC == M_SA8D )
+    {   // 8x8 Hadamard = two vertically adjacent 4x4 coefficient sets of this lane + the horizontal neighbour lane
+        uint32_t a[4], b[4];
+        int c0[16], c1[16];
+        strip_load<METRIC, PITCH, S>( fenc_addr, ref_addr, sh, a, b );
+        had4x4( a, b, c0 );
+        strip_load<METRIC, PITCH, S + 1>( fenc_addr, ref_addr, sh, a, b );
+        had4x4( a, b, c1 );
+        int acc = 0;
+#pragma unroll
+        for( int i = 0; i < 16; i++ )
+        {
+            int u = c0[i] + c1[i], d = c0[i] - c1[i];
+            int tu = __shfl_xor_sync( 0xffffffffu, u, 1 ), td = __shfl_xor_sync( 0xffffffffu, d, 1 );
+            acc += abs( ( lane & 1 ) ? tu - u : u + tu ) + abs( ( lane & 1 ) ? td - d : d + td );
+        }
+        return acc + strips_metric<METRIC, PITCH, NY, S + 2>( fenc_addr, ref_addr, sh, lane );
+    }
+    else
+    {
+        uint32_t a[4], b[4];
+        strip_load<METRIC, PITCH, S>( fenc_addr, ref_addr, sh, a, b );
+        int v = METRIC == M_SAD ? sad4x4( a, b ) : METRIC == M_SSD ? ssd4x4( a, b ) : satd4x4( a, b );
+        return v + strips_metric<METRIC, PITCH, NY, S + 1>( fenc_addr, ref_addr, sh, lane );
+    }
+}
+
+// Same strip walk with the reference rows fetched from global memory (vectors outside the staged halo).
+template <int METRIC, int PITCH, int NY>
+__device__ __noinline__ int strips_metric_global( uint32_t fenc_addr, const uint8_t *g, intptr_t ref_stride, int lane )
+{
+    int acc = 0;
+    int cprev[16];
+    for( int s = 0; s < NY; s++ )
+    {
+        uint32_t a[4], b[4];
+#pragma unroll
+        for( int j = 0; j < 4; j++ )
+        {
+            asm volatile( "ld.shared.b32 %0, [%1];" : "=r"( a[j] ) : "r"( fenc_addr + ( s * 4 + j ) * PITCH ) );
+            b[j] = ldg_unaligned4( g + (intptr_t)( s * 4 + j ) * ref_stride );
+        }
+        if( METRIC == M_SA8D )
+        {
+            int c[16];
+            had4x4( a, b, c );
+            if( s & 1 )
+            {
+#pragma unroll
+                for( int i = 0; i < 16; i++ )
+                {
+                    int u = cprev[i] + c[i], d = cprev[i] - c[i];
+                    int tu = __shfl_xor_sync( 0xffffffffu, u, 1 ), td = __shfl_xor_sync( 0xffffffffu, d, 1 );
+                    acc += abs( ( lane & 1 ) ? tu - u : u + tu ) + abs( ( lane & 1 ) ? td - d : d + td );
+                }
+            }
+            else
+            {
+#pragma unroll
+                for( int i = 0; i < 16; i++ ) cprev[i] = c[i];
+            }
+        }
+        else
+            acc += METRIC == M_SAD ? sad4x4( a, b ) : METRIC == M_SSD ? ssd4x4( a, b ) : satd4x4( a, b );
+    }
+    return acc;
+}
+
+// Work decomposition: a warp task is one row of blocks across the 128-pixel tile: lane l owns the 4-pixel
+// column 4*l and walks the block's BH/4 four-row strips in registers; the BW/4 lanes of a block are summed with
+// xor-shuffles.  Every shared-memory load of the fenc tile reads 128 contiguous bytes of one row.
 template <int METRIC, int BW, int BH, int TW, int TH, int R, int NSTAGE, int NWARPS>
 __global__ void __launch_bounds__( NWARPS * 32 )
 mvfield_kernel( const __grid_constant__ CUtensorMap tm_fenc, const __grid_constant__ CUtensorMap tm_ref,
                 const MvFieldParams p )
 {
-    using G = BlockGeom<BW, BH>;
     using T = TileCfg<TW, TH, R>;
-    static_assert( T::FP == T::RP, "fenc and ref tiles share one row pitch" );
+    static_assert( TW == 128, "one lane per 4-pixel column of the tile" );
     constexpr int PITCH = T::FP;
-    constexpr bool PERM = METRIC != M_SA8D;            // xor-permuted row order (bank spreading); see DESIGN.md
-    constexpr int REG_X = TW / 32, REG_Y = TH / 16, N_REG = REG_X * REG_Y;
-    static_assert( N_REG % NWARPS == 0, "regions must divide evenly over the warps" );
-    constexpr int TASKS_PER_WARP = N_REG / NWARPS;
+    constexpr int LX = BW / 4, NY = BH / 4;
+    constexpr int N_TASKS = TH / BH;
+    static_assert( N_TASKS % NWARPS == 0, "block rows must divide evenly over the warps" );
+    constexpr int TASKS_PER_WARP = N_TASKS / NWARPS;
 
     extern __shared__ __align__( 1024 ) uint8_t smem[];
     uint64_t *full = (uint64_t *)( smem + NSTAGE * T::STAGE_BYTES + 64 );
+    const uint32_t smem_base = smem_u32( smem );
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int qx = lane & 7, qy = lane >> 3;
 
     if( threadIdx.x == 0 )
     {
@@ -165,18 +262,19 @@ mvfield_kernel( const __grid_constant__ CUtensorMap tm_fenc, const __grid_consta
     __syncthreads();
 
     // tile cursor (tx,ty,f) advanced incrementally by gridDim.x tiles: no divisions in the loop
-    const int tiles_per_plane = p.tiles_x * p.tiles_y;
+    const int tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+    const int tiles_per_plane = tiles_x * tiles_y;
     int f = blockIdx.x / tiles_per_plane;
     int t2 = blockIdx.x - f * tiles_per_plane;
-    int ty = t2 / p.tiles_x, tx = t2 - ty * p.tiles_x;
+    int ty = t2 / tiles_x, tx = t2 - ty * tiles_x;
     const int step_f = gridDim.x / tiles_per_plane;
     const int step_r = gridDim.x - step_f * tiles_per_plane;
-    const int step_y = step_r / p.tiles_x, step_x = step_r - step_y * p.tiles_x;
+    const int step_y = step_r / tiles_x, step_x = step_r - step_y * tiles_x;
     auto advance = [&]( int &ax, int &ay, int &af ) {
         ax += step_x;
-        if( ax >= p.tiles_x ) { ax -= p.tiles_x; ay++; }
+        if( ax >= tiles_x ) { ax -= tiles_x; ay++; }
         ay += step_y;
-        if( ay >= p.tiles_y ) { ay -= p.tiles_y; af++; }
+        if( ay >= tiles_y ) { ay -= tiles_y; af++; }
         af += step_f;
     };
     auto issue = [&]( int ax, int ay, int af, int stage ) {
@@ -197,93 +295,76 @@ mvfield_kernel( const __grid_constant__ CUtensorMap tm_fenc, const __grid_consta
             ptile += gridDim.x;
         }
 
-    // lane-constant geometry of this warp's tasks
-    int lane_sm[TASKS_PER_WARP];       // byte offset of the lane's 4x4 inside a tile (row 0 of its sub-block)
-    int lane_blk[TASKS_PER_WARP];      // block index offset inside the plane's block grid
-    int lane_px[TASKS_PER_WARP], lane_py[TASKS_PER_WARP];
-#pragma unroll
-    for( int t = 0; t < TASKS_PER_WARP; t++ )
-    {
-        int reg = warp + t * NWARPS;
-        int ry = reg / REG_X, rx = reg - ry * REG_X;
-        lane_px[t] = rx * 32 + 4 * qx;
-        lane_py[t] = ry * 16 + 4 * qy;
-        lane_sm[t] = lane_py[t] * PITCH + lane_px[t];
-        lane_blk[t] = ( lane_py[t] / BH ) * p.blocks_x + lane_px[t] / BW;
-    }
-    int row_off[4];
-#pragma unroll
-    for( int j = 0; j < 4; j++ ) row_off[j] = ( PERM ? ( j ^ qy ) : j ) * PITCH;
+    const int width = p.width, height = p.height, blocks_x = p.blocks_x, blocks_y = p.blocks_y;
+    const int n_tiles = p.n_tiles, k_cands = p.k_cands;
+    const uint32_t *__restrict__ mvp = (const uint32_t *)p.mv;
+    int32_t *__restrict__ outp = p.out;
+    const int k_stride = p.n_planes * blocks_x * blocks_y;
+    const int lane_blk = lane / LX;                      // block column of this lane inside the tile
+    const bool lead = lane % LX == 0;
+    const int lane_x = lane * 4;
 
-    const int blocks_per_plane = p.blocks_x * p.blocks_y;
-    const size_t k_stride = (size_t)p.n_planes * blocks_per_plane;
-    const bool lead = G::leader( lane );
     int it = 0;
-    for( int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, it++ )
+    for( int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++ )
     {
         const int stage = it % NSTAGE;
         const uint32_t parity = ( it / NSTAGE ) & 1;
         const int x0 = tx * TW, y0 = ty * TH;
-        const int tile_blk = ( f * p.blocks_y + y0 / BH ) * p.blocks_x + x0 / BW;
-        const bool full_tile = ( x0 + TW <= p.width ) && ( y0 + TH <= p.height );
+        const int tile_blk = ( f * blocks_y + y0 / BH ) * blocks_x + x0 / BW;
+        const bool col_ok = x0 + lane_x < width;
 
         int oidx[TASKS_PER_WARP];
         uint32_t mvw[TASKS_PER_WARP];
 #pragma unroll
         for( int t = 0; t < TASKS_PER_WARP; t++ )
         {
-            bool ok = full_tile || ( x0 + lane_px[t] < p.width && y0 + lane_py[t] < p.height );
-            oidx[t] = ok ? tile_blk + lane_blk[t] : -1;
-            mvw[t] = ok ? __ldg( (const uint32_t *)p.mv + oidx[t] ) : 0u;
+            const int row = warp + t * NWARPS;              // block row inside the tile
+            const bool ok = col_ok && y0 + row * BH < height;
+            oidx[t] = ok ? tile_blk + row * blocks_x + lane_blk : -1;
+            mvw[t] = ok ? __ldg( mvp + oidx[t] ) : 0u;
         }
 
         mbar_wait( &full[stage], parity );
-        const uint8_t *sf = smem + stage * T::STAGE_BYTES;
-        const uint8_t *sr = sf + T::FENC_BYTES + R * PITCH + R;
+        const uint32_t sf = smem_base + stage * T::STAGE_BYTES + lane_x;           // fenc tile, this lane's column
+        const uint32_t sr = sf + T::FENC_BYTES + R * PITCH + R;                    // ref tile at zero displacement
 
-        for( int k = 0; k < p.k_cands; k++ )
+        for( int k = 0; k < k_cands; k++ )
         {
 #pragma unroll
             for( int t = 0; t < TASKS_PER_WARP; t++ )
             {
+                const int row = warp + t * NWARPS;
                 const uint32_t mvcur = mvw[t];
+                if( k + 1 < k_cands )
+                    mvw[t] = oidx[t] >= 0 ? __ldg( mvp + ( k + 1 ) * k_stride + oidx[t] ) : 0u;
                 const int mx = (int16_t)( mvcur & 0xffff ), my = (int16_t)( mvcur >> 16 );
-                uint32_t a[4], b[4];
-#pragma unroll
-                for( int j = 0; j < 4; j++ )
-                    a[j] = *(const uint32_t *)( sf + lane_sm[t] + row_off[j] );
+                const uint32_t fa = sf + row * ( BH * PITCH );
                 const bool inside = (unsigned)( mx + R ) <= 2u * R && (unsigned)( my + R ) <= 2u * R;
+                int v;
                 if( __all_sync( 0xffffffffu, inside ) )
                 {
-                    const int o = lane_sm[t] + my * PITCH + mx;           // relative to the halo origin
-                    const uint8_t *q = sr + ( o & ~3 );
-                    const uint32_t sh = ( (uint32_t)o & 3u ) * 8u;
-#pragma unroll
-                    for( int j = 0; j < 4; j++ )
-                    {
-                        const uint32_t *w = (const uint32_t *)( q + row_off[j] );
-                        b[j] = funnel( w[0], w[1], sh );
-                    }
+                    const int o = row * ( BH * PITCH ) + my * PITCH + mx;
+                    const uint32_t ra = ( sr + o ) & ~3u;
+                    const uint32_t sh = ( ( sr + o ) & 3u ) * 8u;
+                    v = strips_metric<METRIC, PITCH, NY, 0>( fa, ra, sh, lane );
                 }
                 else
-                {   // vector outside the staged halo (rare): fetch this candidate straight from global memory
+                {
                     const uint8_t *g = p.ref_origin + (intptr_t)f * p.ref_plane_pitch
-                                     + (intptr_t)( y0 + lane_py[t] + my ) * p.ref_stride + ( x0 + lane_px[t] + mx );
-#pragma unroll
-                    for( int j = 0; j < 4; j++ )
-                        b[j] = oidx[t] >= 0 ? ldg_unaligned4( g + (intptr_t)( PERM ? ( j ^ qy ) : j ) * p.ref_stride ) : 0u;
+                                     + (intptr_t)( y0 + row * BH + my ) * p.ref_stride + ( x0 + lane_x + mx );
+                    v = oidx[t] >= 0 ? 1 : 0;
+                    v = strips_metric_global<METRIC, PITCH, NY>( fa, oidx[t] >= 0 ? g : p.ref_origin, p.ref_stride, lane );
                 }
-                if( k + 1 < p.k_cands && oidx[t] >= 0 )                  // next candidate's vector (uniform branch on k)
-                    mvw[t] = __ldg( (const uint32_t *)p.mv + ( k + 1 ) * k_stride + oidx[t] );
-                int v = G::reduce( metric4x4<METRIC>( a, b, lane ) );
+                if( LX >= 2 ) v += __shfl_xor_sync( 0xffffffffu, v, 1 );
+                if( LX >= 4 ) v += __shfl_xor_sync( 0xffffffffu, v, 2 );
                 if( lead && oidx[t] >= 0 )
-                    p.out[k * k_stride + oidx[t]] = metric_finish<METRIC>( v );
+                    outp[k * k_stride + oidx[t]] = metric_finish<METRIC>( v );
             }
         }
         __syncthreads();                                        // everyone is done reading this stage
         if( threadIdx.x == 0 )
         {
-            if( ptile < p.n_tiles ) issue( ptx, pty, pf, stage );
+            if( ptile < n_tiles ) issue( ptx, pty, pf, stage );
             advance( ptx, pty, pf );
             ptile += gridDim.x;
         }
@@ -467,12 +548,12 @@ int x264cu_pixel_cmp_mvfield( x264cu_ctx_t *ctx, int metric, int i_pixel, const 
         if( cfg < 0 ) { const char *e = getenv( "X264CU_MVF_CFG" ); cfg = e ? atoi( e ) : 0; }
         switch( cfg )
         {
-            case 1: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 2, 8>( ctx, fenc, ref, k_cands, d_mv, d_out );
-            case 2: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 3, 4>( ctx, fenc, ref, k_cands, d_mv, d_out );
-            case 3: return launch_mvfield<M_SATD, 16, 16, 128, 128, 16, 2, 8>( ctx, fenc, ref, k_cands, d_mv, d_out );
-            case 4: return launch_mvfield<M_SATD, 16, 16, 128, 128, 16, 2, 4>( ctx, fenc, ref, k_cands, d_mv, d_out );
-            case 5: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 2, 2>( ctx, fenc, ref, k_cands, d_mv, d_out );
-            case 6: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 4, 4>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 1: return launch_mvfield<M_SATD, 16, 16, 128, 128, 16, 2, 8>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 2: return launch_mvfield<M_SATD, 16, 16, 128, 128, 16, 2, 4>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 3: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 2, 2>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 4: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 3, 4>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 5: return launch_mvfield<M_SATD, 16, 16, 128, 64, 16, 1, 4>( ctx, fenc, ref, k_cands, d_mv, d_out );
+            case 6: return launch_mvfield<M_SATD, 16, 16, 128, 32, 16, 2, 2>( ctx, fenc, ref, k_cands, d_mv, d_out );
             default: break;
         }
     }
