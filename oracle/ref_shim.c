@@ -309,3 +309,96 @@ XREF_API void xref_cost_mv_table_qp( void *hv, int qp, uint16_t *out, int len )
         out[len+i] = h->cost_mv[qp][i];
 }
 XREF_API int xref_lambda( int qp ) { return x264_lambda_tab[qp]; }
+
+/* ------------------------------------------------------------------ lowres lookahead ---------------- */
+typedef struct
+{
+    x264_t *h;
+    int n;
+    x264_frame_t **frames;
+    x264_mb_analysis_t a;
+} xref_la_t;
+
+XREF_API void *xref_la_new( void *hv, int n )
+{
+    x264_t *h = hv;
+    xref_la_t *la = calloc( 1, sizeof(*la) );
+    la->h = h; la->n = n;
+    la->frames = calloc( n + 2, sizeof(x264_frame_t*) );
+    lowres_context_init( h, &la->a );                    /* slicetype.c:45-61 */
+    return la;
+}
+
+/* mc.c:458-482 on a fresh frame; inv_qscale (u16 per MB) optional, defaults to 256 */
+XREF_API int xref_la_set_frame( void *lav, int idx, const uint8_t *luma, intptr_t luma_stride, const uint16_t *inv_qscale )
+{
+    xref_la_t *la = lav;
+    x264_t *h = la->h;
+    x264_frame_t *f = la->frames[idx];
+    if( !f )
+    {
+        f = la->frames[idx] = x264_frame_pop_unused( h, 0 );
+        if( !f ) return -1;
+    }
+    for( int y = 0; y < h->param.i_height; y++ )
+        memcpy( f->plane[0] + y*f->i_stride[0], luma + y*luma_stride, h->param.i_width );
+    x264_frame_expand_border_mod16( h, f );
+    x264_frame_init_lowres( h, f );
+    f->b_intra_calculated = 0;
+    f->i_frame = idx;
+    if( f->i_inv_qscale_factor )
+        for( int i = 0; i < h->mb.i_mb_count; i++ )
+            f->i_inv_qscale_factor[i] = inv_qscale ? inv_qscale[i] : 256;
+    /* stale vectors of a recycled frame: the reference's own frames start zeroed (frame.c:287-293) */
+    for( int l = 0; l <= !!h->param.i_bframe; l++ )
+        for( int d = 0; d <= h->param.i_bframe; d++ )
+        {
+            memset( f->lowres_mvs[l][d], 0, 2*h->mb.i_mb_count*sizeof(int16_t) );
+            f->lowres_mvs[l][d][0][0] = 0x7FFF;
+        }
+    return 0;
+}
+
+XREF_API int xref_la_frame_cost( void *lav, int p0, int p1, int b )
+{
+    xref_la_t *la = lav;
+    return slicetype_frame_cost( la->h, &la->a, la->frames, p0, p1, b );
+}
+
+/* what: 0 lowres_mvs[i][j] (int16 x2 per MB), 1 lowres_mv_costs[i][j] (int), 2 lowres_costs[i][j] (u16),
+ *       3 i_intra_cost (int... stored as u16 in the reference: widened), 4 {cost_est, cost_est_aq, intra_mbs[i]}, 5 row_satds[i][j] */
+XREF_API void xref_la_get( void *lav, int idx, int what, int i, int j, void *out )
+{
+    xref_la_t *la = lav;
+    x264_t *h = la->h;
+    x264_frame_t *f = la->frames[idx];
+    int n = h->mb.i_mb_count;
+    switch( what )
+    {
+        case 0: memcpy( out, f->lowres_mvs[i][j], n * 4 ); break;
+        case 1: memcpy( out, f->lowres_mv_costs[i][j], n * sizeof(int) ); break;
+        case 2: memcpy( out, f->lowres_costs[i][j], n * 2 ); break;
+        case 3: for( int k = 0; k < n; k++ ) ((int*)out)[k] = f->i_intra_cost[k]; break;
+        case 4: ((int*)out)[0] = f->i_cost_est[i][j]; ((int*)out)[1] = f->i_cost_est_aq[i][j]; ((int*)out)[2] = f->i_intra_mbs[i]; break;
+        case 5: memcpy( out, f->i_row_satds[i][j], h->mb.i_mb_height * sizeof(int) ); break;
+    }
+}
+
+XREF_API void xref_la_get_lowres( void *lav, int idx, int plane, uint8_t *out )
+{
+    xref_la_t *la = lav;
+    x264_frame_t *f = la->frames[idx];
+    intptr_t st = f->i_stride_lowres;
+    for( int y = 0; y < f->i_lines_lowres + 2*PADV; y++ )
+        memcpy( out + y*st, f->lowres[plane] + (y-PADV)*st - PADH, f->i_width_lowres + 2*PADH );
+}
+
+XREF_API void xref_la_free( void *lav )
+{
+    xref_la_t *la = lav;
+    /* deleted, not pushed back: the encoder's unused-frame list has a fixed capacity (encoder.c frames.unused) */
+    for( int i = 0; i < la->n; i++ )
+        if( la->frames[i] ) x264_frame_delete( la->frames[i] );
+    free( la->frames );
+    free( la );
+}

@@ -188,3 +188,67 @@ def make_ref_planes(luma, stride=None):
     oracle().orc_hpel_filter_plane(ptr(src), w, w, h, ptr(H.buf, H.origin), ptr(V.buf, V.origin), ptr(Cc.buf, Cc.origin),
                                    F.stride, PAD)
     return [F, H, V, Cc]
+
+
+class OrcLaParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "mb_width", "mb_height", "subpel_refine", "me_method", "me_range",
+                                       "mv_range", "bframes", "bframe_bias", "weighted_bipred", "aq_mode", "do_edges", "vbv")]
+
+
+def _bind_la():
+    o = oracle()
+    vp, ci = C.c_void_p, C.c_int
+    o.orc_la_frame_new.restype = vp
+    o.orc_la_frame_new.argtypes = [C.POINTER(OrcLaParams), vp, C.c_ssize_t]
+    o.orc_la_frame_delete.argtypes = [vp]
+    o.orc_la_frame_cost.argtypes = [C.POINTER(OrcLaParams), vp, C.POINTER(vp), ci, ci, ci]
+    o.orc_la_frame_get.argtypes = [vp, ci, ci, ci, vp]
+    o.orc_la_frame_set_qscale.argtypes = [vp, u16p]
+    o.orc_la_frame_plane.restype = vp
+    o.orc_la_frame_plane.argtypes = [vp, ci]
+    o.orc_la_frame_stride.argtypes = [vp]
+    if have_ref():
+        r = ref()
+        r.xref_la_new.restype = vp
+        r.xref_la_new.argtypes = [vp, ci]
+        r.xref_la_set_frame.argtypes = [vp, ci, vp, C.c_ssize_t, vp]
+        r.xref_la_frame_cost.argtypes = [vp, ci, ci, ci]
+        r.xref_la_get.argtypes = [vp, ci, ci, ci, ci, vp]
+        r.xref_la_get_lowres.argtypes = [vp, ci, ci, vp]
+        r.xref_la_free.argtypes = [vp]
+
+
+def la_params_from_ref(hnd, width, height):
+    """orc_la_params_t mirroring an opened reference encoder (x264_t fields)"""
+    r = ref()
+    g = lambda n: r.xref_param(hnd, n.encode())
+    p = OrcLaParams()
+    p.width, p.height = width, height
+    p.mb_width, p.mb_height = g("mb_width"), g("mb_height")
+    p.subpel_refine, p.me_method, p.me_range, p.mv_range = g("subme"), g("me"), g("merange"), g("mvrange")
+    p.bframes, p.bframe_bias, p.weighted_bipred = g("bframes"), g("b_bias"), g("weightb")
+    p.aq_mode = int(g("aq_mode") != 0)
+    p.vbv = int(g("vbv") != 0)
+    p.do_edges = int(g("mbtree") != 0 or g("vbv") != 0)
+    return p
+
+
+def synth_sequence(width, height, n, seed, cut_at=None):
+    """moving low-pass texture with per-frame global motion (integer + half-pel), optional scene cut"""
+    rng = np.random.default_rng(seed)
+    master = synth_luma(2 * width + 128, 2 * height + 128, seed).astype(np.float32)
+    master2 = synth_luma(2 * width + 128, 2 * height + 128, seed + 1).astype(np.float32)
+    frames = []
+    x = y = 32.0
+    for i in range(n):
+        if cut_at is not None and i == cut_at:
+            master = master2
+        x += rng.integers(-6, 7) / 1.0
+        y += rng.integers(-4, 5) / 1.0
+        x = float(np.clip(x, 0, 120))
+        y = float(np.clip(y, 0, 120))
+        xi, yi = int(x), int(y)
+        crop = master[yi:yi + 2 * height:2, xi:xi + 2 * width:2]
+        img = crop + rng.normal(0, 1.5, crop.shape)
+        frames.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+    return frames
