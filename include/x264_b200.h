@@ -130,6 +130,82 @@ int x264cu_pixel_cmp_mvfield_host( x264cu_ctx_t *ctx, int metric, int i_pixel,
                                    intptr_t stride, intptr_t plane_pitch, int width, int height, int n_planes,
                                    int k_cands, const int16_t *h_mv, int32_t *h_out );
 
+/* ------------------------------------------------------------------------------------------------
+ * B1 (mc table): frame preparation twins of x264_mc_functions_t entries (common/mc.h:267-340).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* x264_frame_init_lowres (common/mc.c:458-507) + x264_frame_expand_border_lowres (common/frame.c:627-631):
+ * d_luma is the picture as the user supplied it (width x height, any stride); it is treated as expanded to
+ * the next multiple of 16 by edge replication (x264_frame_expand_border_mod16, common/frame.c:640-665).
+ * d_lowres[i] are the origins of the F,H,V,C planes (lowres_stride bytes per row, X264CU_PAD border each side,
+ * width_lowres = 8*ceil(width/16), lines_lowres = 8*ceil(height/16)). */
+int x264cu_frame_init_lowres( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, int width, int height,
+                              uint8_t *const d_lowres[4], intptr_t lowres_stride );
+
+/* hpel_filter as driven over a whole frame by x264_frame_filter + x264_frame_expand_border_filtered
+ * (common/mc.c:172-196, :704-746; common/frame.c:596-625): fills the H, V and C half-pel planes (origins given,
+ * same stride, X264CU_PAD border) from a width x height luma plane; also (re)writes the border of d_src itself
+ * when expand_src != 0 (x264_frame_expand_border, frame.c:562-594). */
+int x264cu_hpel_filter( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, int width, int height,
+                        uint8_t *d_h, uint8_t *d_v, uint8_t *d_c, int expand_src );
+
+/* ------------------------------------------------------------------------------------------------
+ * B2: the lowres lookahead, the seam where common/opencl.c + encoder/slicetype-cl.c sit today
+ * (hooks called from slicetype_frame_cost, encoder/slicetype.c:878-897).  Results are those of the
+ * reference's CPU path (slicetype_mb_cost, slicetype.c:514-791) with one lookahead thread, bit for bit.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct x264cu_lookahead x264cu_lookahead_t;
+
+typedef struct
+{
+    int width, height;            /* h->param.i_width / i_height */
+    int subpel_refine;            /* h->param.analyse.i_subpel_refine */
+    int me_method;                /* h->param.analyse.i_me_method (X264CU_ME_*) */
+    int me_range;                 /* h->param.analyse.i_me_range */
+    int mv_range;                 /* h->param.analyse.i_mv_range (after validation) */
+    int bframes;                  /* h->param.i_bframe */
+    int bframe_bias;              /* h->param.i_bframe_bias */
+    int weighted_bipred;          /* h->param.analyse.b_weighted_bipred */
+    int aq_mode;                  /* h->param.rc.i_aq_mode != 0 */
+    int mb_tree;                  /* h->param.rc.b_mb_tree */
+    int vbv;                      /* h->param.rc.i_vbv_buffer_size != 0 */
+    int n_slots;                  /* frames resident in HBM at once (>= lookahead + bframes + 3) */
+} x264cu_lookahead_params_t;
+
+/* x264_opencl_lookahead_init / _delete (common/opencl.c:411, :596) */
+int  x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *params, x264cu_lookahead_t **out );
+void x264cu_lookahead_close( x264cu_lookahead_t *la );
+
+/* x264_opencl_lowres_init (encoder/slicetype-cl.c:82): upload the luma of one frame into `slot`, build its
+ * lowres planes on the device and reset its memoised costs / vectors (x264_frame_init_lowres, mc.c:458-482).
+ * h_inv_qscale: fenc->i_inv_qscale_factor (u16 per MB) or NULL for 256 (AQ off). */
+int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
+                                const uint16_t *h_inv_qscale );
+/* same with the luma already in HBM */
+int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const uint8_t *d_luma, intptr_t luma_stride,
+                                       const uint16_t *h_inv_qscale );
+
+/* slicetype_frame_cost (encoder/slicetype.c:836-995): frames[] maps the reference's frame indices to slots
+ * (frames[p0], frames[b], frames[p1] are read).  Returns the frame score in *score. */
+int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score );
+
+/* x264_opencl_slicetype_prep (encoder/slicetype-cl.c:653): run a batch of lowres motion searches in ONE launch so
+ * that the GPU is filled; job i searches frame slot fenc[i] against slot ref[i] as list[i] (0/1) at distance
+ * dist[i] >= 1.  Searches are pure functions of the two frames (no weighted prediction), so doing them ahead of
+ * time does not change any later x264cu_lookahead_frame_cost result.  Already-searched jobs are skipped. */
+int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int *fenc, const int *ref,
+                                   const int *list, const int *dist );
+
+/* read back per-MB results of one slot (the arrays x264_frame_t holds, common/frame.h:97-141) */
+int x264cu_lookahead_get_mvs( x264cu_lookahead_t *la, int slot, int list, int dist_minus1, int16_t *h_mvs, int32_t *h_mv_costs );
+int x264cu_lookahead_get_costs( x264cu_lookahead_t *la, int slot, int b_minus_p0, int p1_minus_b, uint16_t *h_lowres_costs );
+int x264cu_lookahead_get_intra( x264cu_lookahead_t *la, int slot, int32_t *h_intra_costs );
+int x264cu_lookahead_get_row_satds( x264cu_lookahead_t *la, int slot, int b_minus_p0, int p1_minus_b, int32_t *h_rows );
+/* cost_est / cost_est_aq / intra_mbs as memoised on the host side (i_cost_est[18][18] etc.); -1 = not computed */
+int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int b_minus_p0, int p1_minus_b,
+                                   int *cost_est, int *cost_est_aq, int *intra_mbs );
+int x264cu_lookahead_get_lowres_plane( x264cu_lookahead_t *la, int slot, int plane, uint8_t *h_out, intptr_t *stride );
+
 #ifdef __cplusplus
 }
 #endif

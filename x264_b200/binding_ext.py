@@ -1,6 +1,110 @@
-"""argtypes for entry points beyond the pixel table; filled in as the translation units land."""
+"""argtypes for the entry points beyond the pixel table (frame preparation, lookahead)"""
 import ctypes as C
+
+import numpy as np
+
+
+class LookaheadParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "subpel_refine", "me_method", "me_range", "mv_range", "bframes",
+                                       "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv", "n_slots")]
 
 
 def bind(L):
-    pass
+    vp, ci, ss = C.c_void_p, C.c_int, C.c_ssize_t
+    L.x264cu_frame_init_lowres.argtypes = [vp, vp, ss, ci, ci, C.POINTER(vp), ss]
+    L.x264cu_hpel_filter.argtypes = [vp, vp, ss, ci, ci, vp, vp, vp, ci]
+    L.x264cu_lookahead_open.argtypes = [vp, C.POINTER(LookaheadParams), C.POINTER(vp)]
+    L.x264cu_lookahead_close.argtypes = [vp]
+    L.x264cu_lookahead_frame_put.argtypes = [vp, ci, vp, ss, vp]
+    L.x264cu_lookahead_frame_put_device.argtypes = [vp, ci, vp, ss, vp]
+    L.x264cu_lookahead_frame_cost.argtypes = [vp, C.POINTER(ci), ci, ci, ci, C.POINTER(ci)]
+    L.x264cu_lookahead_search_batch.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
+    L.x264cu_lookahead_get_mvs.argtypes = [vp, ci, ci, ci, vp, vp]
+    L.x264cu_lookahead_get_costs.argtypes = [vp, ci, ci, ci, vp]
+    L.x264cu_lookahead_get_intra.argtypes = [vp, ci, vp]
+    L.x264cu_lookahead_get_row_satds.argtypes = [vp, ci, ci, ci, vp]
+    L.x264cu_lookahead_get_cost_est.argtypes = [vp, ci, ci, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
+    L.x264cu_lookahead_get_lowres_plane.argtypes = [vp, ci, ci, vp, C.POINTER(ss)]
+
+
+class Lookahead:
+    """Mirror of the reference's lookahead offload hooks (x264_opencl_lowres_init / _motionsearch / _finalize_cost,
+    encoder/slicetype-cl.c) as one object: frame_put() == lowres_init, frame_cost() == slicetype_frame_cost."""
+
+    def __init__(self, ctx, width, height, subpel_refine=7, me_method=1, me_range=16, mv_range=512, bframes=3,
+                 bframe_bias=0, weighted_bipred=1, aq_mode=1, mb_tree=1, vbv=0, n_slots=8):
+        self.ctx = ctx
+        self.L = ctx.L
+        self.p = LookaheadParams(width, height, subpel_refine, me_method, me_range, mv_range, bframes, bframe_bias,
+                                 weighted_bipred, aq_mode, mb_tree, vbv, n_slots)
+        h = C.c_void_p()
+        ctx.check(self.L.x264cu_lookahead_open(ctx.h, C.byref(self.p), C.byref(h)))
+        self.h = h
+        self.mb_w, self.mb_h = (width + 15) // 16, (height + 15) // 16
+        self.mb_count = self.mb_w * self.mb_h
+
+    def close(self):
+        if self.h:
+            self.L.x264cu_lookahead_close(self.h)
+            self.h = None
+
+    def frame_put(self, slot, luma, inv_qscale=None):
+        luma = np.ascontiguousarray(luma, dtype=np.uint8)
+        q = None
+        if inv_qscale is not None:
+            q = np.ascontiguousarray(inv_qscale, dtype=np.uint16)
+        self.ctx.check(self.L.x264cu_lookahead_frame_put(self.h, slot, luma.ctypes.data, luma.shape[1],
+                                                         q.ctypes.data if q is not None else None))
+
+    def frame_put_device(self, slot, d_luma, stride, inv_qscale=None):
+        q = None
+        if inv_qscale is not None:
+            q = np.ascontiguousarray(inv_qscale, dtype=np.uint16)
+        self.ctx.check(self.L.x264cu_lookahead_frame_put_device(self.h, slot, int(d_luma), stride,
+                                                                q.ctypes.data if q is not None else None))
+
+    def frame_cost(self, frames, p0, p1, b):
+        arr = (C.c_int * len(frames))(*frames)
+        sc = C.c_int()
+        self.ctx.check(self.L.x264cu_lookahead_frame_cost(self.h, arr, p0, p1, b, C.byref(sc)))
+        return sc.value
+
+    def search_batch(self, jobs):
+        """jobs: list of (fenc_slot, ref_slot, list, dist)"""
+        n = len(jobs)
+        cols = [(C.c_int * n)(*[j[k] for j in jobs]) for k in range(4)]
+        self.ctx.check(self.L.x264cu_lookahead_search_batch(self.h, n, *cols))
+
+    def get_mvs(self, slot, lst, dist_minus1):
+        mv = np.zeros((self.mb_count, 2), np.int16)
+        co = np.zeros(self.mb_count, np.int32)
+        self.ctx.check(self.L.x264cu_lookahead_get_mvs(self.h, slot, lst, dist_minus1, mv.ctypes.data, co.ctypes.data))
+        return mv, co
+
+    def get_costs(self, slot, i0, i1):
+        out = np.zeros(self.mb_count, np.uint16)
+        self.ctx.check(self.L.x264cu_lookahead_get_costs(self.h, slot, i0, i1, out.ctypes.data))
+        return out
+
+    def get_intra(self, slot):
+        out = np.zeros(self.mb_count, np.int32)
+        self.ctx.check(self.L.x264cu_lookahead_get_intra(self.h, slot, out.ctypes.data))
+        return out
+
+    def get_row_satds(self, slot, i0, i1):
+        out = np.zeros(self.mb_h, np.int32)
+        self.ctx.check(self.L.x264cu_lookahead_get_row_satds(self.h, slot, i0, i1, out.ctypes.data))
+        return out
+
+    def get_cost_est(self, slot, i0, i1):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self.ctx.check(self.L.x264cu_lookahead_get_cost_est(self.h, slot, i0, i1, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def get_lowres_plane(self, slot, plane):
+        st = C.c_ssize_t()
+        self.ctx.check(self.L.x264cu_lookahead_get_lowres_plane(self.h, slot, plane, None, C.byref(st)))
+        rows = self.mb_h * 8 + 64
+        out = np.zeros(rows * st.value, np.uint8)
+        self.ctx.check(self.L.x264cu_lookahead_get_lowres_plane(self.h, slot, plane, out.ctypes.data, C.byref(st)))
+        return out.reshape(rows, st.value)

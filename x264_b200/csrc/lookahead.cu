@@ -1,3 +1,934 @@
-// placeholder until the lookahead kernels land
+// Lowres lookahead on the GPU: the slot that common/opencl.c + encoder/slicetype-cl.c fill in the reference, with the
+// results of the reference's CPU path (encoder/slicetype.c:514-995, one lookahead thread), bit for bit.
+//
+// slicetype_mb_cost is split along its data dependencies:
+//   intra_kernel    lowres intra cost of every MB (3 or 10 modes)            -- no dependencies, once per frame
+//   search_kernel   lowres_mvs / lowres_mv_costs of one (frame, list, distance) -- reverse-raster dependency on the
+//                   right / below / below-left / below-right neighbours (slicetype.c:662-680): one warp per MB ROW,
+//                   rows pipelined two MBs apart through per-row progress flags in HBM; many jobs per launch
+//   finalize_kernel bidir candidates, list choice, intra-vs-inter, AQ scaling, row and frame sums, lowres_costs
+//                   -- per-MB parallel once the vectors exist
+// The memoisation / order logic of slicetype_frame_cost (sentinels, do_search, b_intra_calculated) stays on the host,
+// in x264cu_lookahead_frame_cost below.
 #include "ctx.h"
+#include "lookahead_dev.cuh"
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+using namespace x264cu;
+
+#define LOWRES_COST_MASK 0x3fff          /* common/frame.h:107-112 */
+#define LOWRES_COST_SHIFT 14
+#define LA_MAX_B ( X264CU_BFRAME_MAX )
+
+struct LaDims
+{
+    int mb_w, mb_h, mb_count;
+    int stride;                      // lowres stride
+    int B;                           // bframes
+    int subme;                       // param subpel_refine
+    int me_method, subpel, me_range; // what lowres_context_init selects (slicetype.c:45-61)
+    int mv_range2;                   // 2 * i_mv_range
+    int bipred_weighted, aq, do_edges;
+    int cost_len;                    // half length of the cost_mv table
+};
+
+struct LaSlotDev
+{
+    uint8_t *planes[4];              // origins of F,H,V,C
+    int16_t *mvs;                    // [2][B+1][mb_count][2]
+    int32_t *mv_costs;               // [2][B+1][mb_count]
+    uint16_t *costs;                 // [(B+2)*(B+2)][mb_count]
+    int32_t *intra;                  // [mb_count]
+    uint16_t *qscale;                // [mb_count]
+    int32_t *row_satds;              // [(B+2)*(B+2)][mb_h]
+    int32_t *progress;               // [2][B+1][mb_h]
+};
+
+struct LaSearchJob
+{
+    const uint8_t *fenc;             // F plane origin of the frame being searched
+    const uint8_t *ref[4];
+    int16_t *mvs;                    // [mb_count][2]
+    int32_t *mv_costs;
+    int32_t *progress;               // [mb_h], preset to mb_w (nothing done)
+};
+
+struct LaFinalizeArgs
+{
+    const uint8_t *fenc;
+    const uint8_t *ref0[4], *ref1[4];
+    const int16_t *mvs0, *mvs1;      // this frame's vectors for the two lists (mvs1 NULL for P)
+    const int32_t *cost0, *cost1;
+    const int16_t *mvr;              // fref1's L0 vectors at distance p1-p0 (temporal direct) or NULL
+    const int32_t *intra;
+    const uint16_t *qscale;
+    uint16_t *costs;                 // lowres_costs[b-p0][p1-b]
+    int32_t *row_inter, *row_intra;  // row_satds slots
+    int32_t *record;                 // {cost_est, cost_est_aq, intra_mbs, intra_cost_est, intra_cost_est_aq}
+    int b_bidir, b_inter, dist_scale_factor, bipred_weight;
+};
+
+// ------------------------------------------------------------------------------------------------
+// lane geometry shared by the per-MB-parallel kernels: 4 lanes per MB (4x4 quadrants), 8 MBs per warp
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_quad( const uint8_t *p, int stride, uint32_t a[4] )
+{
+#pragma unroll
+    for( int r = 0; r < 4; r++ ) a[r] = ldg4u( p + r * stride );
+}
+
+// ------------------------------------------------------------------------------------------------
+// intra: slicetype.c:714-757 + predict.c (8x8c DC/H/V/P, 8x8 filtered DDL..HU)
+// ------------------------------------------------------------------------------------------------
+#define F1( a, b ) ( ( ( a ) + ( b ) + 1 ) >> 1 )
+#define F2( a, b, c ) ( ( ( a ) + 2 * ( b ) + ( c ) + 2 ) >> 2 )
+
+__global__ void __launch_bounds__( 256 )
+intra_kernel( LaDims d, const uint8_t *__restrict__ plane, int32_t *__restrict__ intra )
+{
+    // per MB edge arrays in shared memory: raw top t[-1..15], raw left l[0..7], filtered ft[-1..15], fl[-1..7]
+    __shared__ uint8_t s_t[64][20], s_l[64][8], s_ft[64][20], s_fl[64][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane & 3, mbl = warp * 8 + ( lane >> 2 );
+    const int mb = blockIdx.x * 64 + mbl;
+    const bool valid = mb < d.mb_count;
+    const int mbc = valid ? mb : d.mb_count - 1;
+    const int mb_y = mbc / d.mb_w, mb_x = mbc - mb_y * d.mb_w;
+    const uint8_t *src = plane + ( mb_y * 8 ) * d.stride + mb_x * 8;
+    // stage edges: lane q loads a quarter
+    for( int i = q; i < 17; i += 4 ) s_t[mbl][i] = src[-d.stride + i - 1];
+    for( int i = q; i < 8; i += 4 ) s_l[mbl][i] = src[i * d.stride - 1];
+    __syncwarp();
+    {
+        const uint8_t *t = &s_t[mbl][1];               // t[-1] = corner
+        const uint8_t *l = s_l[mbl];
+        uint8_t *ft = &s_ft[mbl][1], *fl = &s_fl[mbl][1];
+        if( q == 0 )
+        {   // predict_8x8_filter with every neighbour available, predict.c:632-680
+            int lt = t[-1];
+            ft[-1] = fl[-1] = ( t[0] + 2*lt + l[0] + 2 ) >> 2;
+            fl[0] = ( lt + 2*l[0] + l[1] + 2 ) >> 2;
+            for( int y = 1; y < 7; y++ ) fl[y] = F2( l[y-1], l[y], l[y+1] );
+            fl[7] = ( l[6] + 3*l[7] + 2 ) >> 2;
+            ft[0] = ( lt + 2*t[0] + t[1] + 2 ) >> 2;
+            for( int x = 1; x < 15; x++ ) ft[x] = F2( t[x-1], t[x], t[x+1] );
+            ft[15] = ( t[14] + 3*t[15] + 2 ) >> 2;
+        }
+    }
+    __syncwarp();
+    const uint8_t *t = &s_t[mbl][1], *l = s_l[mbl];
+    const uint8_t *ft = &s_ft[mbl][1], *fl = &s_fl[mbl][1];
+    const int qx = ( q & 1 ) * 4, qy = ( q >> 1 ) * 4;
+    uint32_t a[4];
+    load_quad( src + qy * d.stride + qx, d.stride, a );
+    const bool satd = d.subme > 1;
+    int best = LA_COST_MAX;
+    const int n_modes = satd ? 10 : 3;
+    // plane-prediction parameters (predict.c:282-310)
+    int pb = 0, pc = 0, pi00 = 0;
+    if( satd )
+    {
+        int H = 0, V = 0;
+        for( int i = 0; i < 4; i++ )
+        {
+            H += ( i + 1 ) * ( t[4+i] - t[2-i] );
+            V += ( i + 1 ) * ( l[i+4] - ( i == 3 ? t[-1] : l[2-i] ) );
+        }
+        int pa = 16 * ( l[7] + t[7] );
+        pb = ( 17*H + 16 ) >> 5; pc = ( 17*V + 16 ) >> 5;
+        pi00 = pa - 3*pb - 3*pc + 16;
+    }
+    // 8x8c DC values (predict.c:221-257)
+    int s0 = t[0] + t[1] + t[2] + t[3], s1 = t[4] + t[5] + t[6] + t[7];
+    int s2 = l[0] + l[1] + l[2] + l[3], s3 = l[4] + l[5] + l[6] + l[7];
+    const int dcq = q == 0 ? ( s0 + s2 + 4 ) >> 3 : q == 1 ? ( s1 + 2 ) >> 2 : q == 2 ? ( s3 + 2 ) >> 2 : ( s1 + s3 + 4 ) >> 3;
+    for( int mode = 0; mode < n_modes; mode++ )
+    {
+        uint32_t b[4];
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            const int y = qy + r;
+            uint32_t w = 0;
+#pragma unroll
+            for( int c = 0; c < 4; c++ )
+            {
+                const int x = qx + c;
+                int v;
+                switch( mode )
+                {
+                case 0: v = dcq; break;
+                case 1: v = l[y]; break;                                          /* 8x8c H */
+                case 2: v = t[x]; break;                                          /* 8x8c V */
+                case 3: v = min( max( ( pi00 + pb*x + pc*y ) >> 5, 0 ), 255 ); break;   /* 8x8c P */
+                case 4: /* DDL */
+                    v = ( x == 7 && y == 7 ) ? F2( ft[14], ft[15], ft[15] ) : F2( ft[x+y], ft[x+y+1], ft[x+y+2] );
+                    break;
+                case 5: /* DDR */
+                {
+                    int dd = x - y;
+                    v = dd > 0 ? F2( ft[dd-2], ft[dd-1], ft[dd] ) : dd == 0 ? F2( fl[0], ft[-1], ft[0] ) : F2( fl[-dd], fl[-dd-1], fl[-dd-2] );
+                    break;
+                }
+                case 6: /* VR */
+                {
+                    int z = 2*x - y, k = x - ( y >> 1 );
+                    if( z >= 0 ) v = ( z & 1 ) ? F2( ft[k-2], ft[k-1], ft[k] ) : F1( ft[k-1], ft[k] );
+                    else if( z == -1 ) v = F2( fl[0], ft[-1], ft[0] );
+                    else v = F2( fl[y-2*x-1], fl[y-2*x-2], fl[y-2*x-3] );
+                    break;
+                }
+                case 7: /* HD */
+                {
+                    int i = 2*( 7 - y ) + x;
+                    if( i == 15 ) v = F2( fl[0], ft[-1], ft[0] );
+                    else if( i < 16 ) { int k = 6 - ( i >> 1 ); v = ( i & 1 ) ? F2( fl[k-1], fl[k], fl[k+1] ) : F1( fl[k], fl[k+1] ); }
+                    else { int k = i - 16; v = F2( ft[k+1], ft[k], ft[k-1] ); }
+                    break;
+                }
+                case 8: /* VL */
+                {
+                    int k = x + ( y >> 1 );
+                    v = ( y & 1 ) ? F2( ft[k], ft[k+1], ft[k+2] ) : F1( ft[k], ft[k+1] );
+                    break;
+                }
+                default: /* HU */
+                {
+                    int i = 2*y + x, k = i >> 1;
+                    if( i >= 14 ) v = fl[7];
+                    else if( i == 13 ) v = F2( fl[6], fl[7], fl[7] );
+                    else v = ( i & 1 ) ? F2( fl[k], fl[k+1], fl[k+2] ) : F1( fl[k], fl[k+1] );
+                    break;
+                }
+                }
+                w |= (uint32_t)v << ( 8*c );
+            }
+            b[r] = w;
+        }
+        int c = quad_sum( satd ? satd4x4( a, b ) : sad4x4( a, b ) );
+        best = min( best, c );
+    }
+    if( valid && q == 0 )
+        intra[mb] = best + 5 + 4;                 // + intra_penalty (5*lambda, lambda = 1) + lowres_penalty (slicetype.c:745)
+}
+
+// ------------------------------------------------------------------------------------------------
+// search: one warp = one MB row, rows bottom-up; slicetype.c:654-705 + me.c
+// ------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__( NW * 32 )
+search_kernel( LaDims d, const LaSearchJob *__restrict__ jobs, const uint16_t *__restrict__ cost_mv_g )
+{
+    extern __shared__ uint16_t s_cost[];
+    for( int i = threadIdx.x; i < 2 * d.cost_len + 1; i += blockDim.x ) s_cost[i] = cost_mv_g[i];
+    __syncthreads();
+    const uint16_t *cost_mv = s_cost + d.cost_len;
+
+    const LaSearchJob job = jobs[blockIdx.y];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int start_y = min( d.mb_h - 1, d.mb_h - 2 + d.do_edges ), end_y = max( 0, 1 - d.do_edges );
+    const int start_x = d.mb_w - 2 + d.do_edges, end_x = 1 - d.do_edges;
+    const int mb_y = start_y - ( blockIdx.x * NW + warp );
+    if( mb_y < end_y ) return;
+    const int q = lane & 3, qx = ( q & 1 ) * 4, qy = ( q >> 1 ) * 4;
+
+    volatile int32_t *progress = job.progress;
+    int16_t *mvs = job.mvs;
+    // right neighbour's vector is produced by this warp itself
+    int right_x = 0, right_y = 0;
+    if( start_x + 1 < d.mb_w )
+    {   // the never-searched edge column keeps whatever the frame reset left there (zeros, frame.c:287-293)
+        const int16_t *e = mvs + 2 * ( mb_y * d.mb_w + start_x + 1 );
+        right_x = e[0]; right_y = e[1];
+    }
+    const int mv_range = d.mv_range2;
+    for( int mb_x = start_x; mb_x >= end_x; mb_x-- )
+    {
+        const int mb_xy = mb_y * d.mb_w + mb_x;
+        // wait for the row below to have passed column mb_x-1 (it runs right to left)
+        if( mb_y < d.mb_h - 1 && mb_y + 1 <= start_y )
+        {
+            const int need = max( mb_x - 1, end_x );
+            if( lane == 0 )
+            {
+                int ns = 32;
+                while( progress[mb_y + 1] > need ) { __nanosleep( ns ); if( ns < 1024 ) ns <<= 1; }
+            }
+            __syncwarp();
+            __threadfence();
+        }
+        LaMe m;
+        const int pel = ( mb_y * 8 ) * d.stride + mb_x * 8;
+        load_quad( job.fenc + pel + qy * d.stride + qx, d.stride, m.fenc );
+#pragma unroll
+        for( int i = 0; i < 4; i++ ) m.fref[i] = job.ref[i] + pel + qy * d.stride + qx;
+        m.fref_w = m.fref[0];
+        m.stride = d.stride;
+        m.cost_mv = cost_mv;
+        m.w.enabled = 0; m.w.scale = m.w.denom = m.w.offset = 0;
+        m.satd = d.subme > 1;
+        m.min_spel_x = max( 4*( -8*mb_x - 12 ), -mv_range );
+        m.max_spel_x = min( 4*( 8*( d.mb_w - mb_x - 1 ) + 12 ), mv_range - 1 );
+        m.min_spel_y = max( 4*( -8*mb_y - 12 ), -mv_range );
+        m.max_spel_y = min( 4*( 8*( d.mb_h - mb_y - 1 ) + 12 ), mv_range - 1 );
+        m.x_min = m.min_spel_x >> 2; m.x_max = m.max_spel_x >> 2;
+        m.y_min = m.min_spel_y >> 2; m.y_max = m.max_spel_y >> 2;
+
+        // reverse-order predictors: right, below, below-left, below-right (slicetype.c:658-680)
+        int mvcx[4] = { 0, 0, 0, 0 }, mvcy[4] = { 0, 0, 0, 0 }, i_mvc = 0;
+        if( mb_x < d.mb_w - 1 ) { mvcx[0] = right_x; mvcy[0] = right_y; i_mvc = 1; }
+        if( mb_y < d.mb_h - 1 )
+        {
+            const int16_t *below = mvs + 2 * ( mb_xy + d.mb_w );
+            int vx = __ldcg( (const int *)below ) ;
+            int bx = (int16_t)( vx & 0xffff ), by = (int16_t)( vx >> 16 );
+            if( i_mvc == 0 ) { mvcx[0] = bx; mvcy[0] = by; } else { mvcx[1] = bx; mvcy[1] = by; }
+            i_mvc++;
+            if( mb_x > 0 )
+            {
+                int v2 = __ldcg( (const int *)( below - 2 ) );
+                int cx = (int16_t)( v2 & 0xffff ), cy = (int16_t)( v2 >> 16 );
+                if( i_mvc == 1 ) { mvcx[1] = cx; mvcy[1] = cy; } else { mvcx[2] = cx; mvcy[2] = cy; }
+                i_mvc++;
+            }
+            if( mb_x < d.mb_w - 1 )
+            {
+                int v3 = __ldcg( (const int *)( below + 2 ) );
+                int cx = (int16_t)( v3 & 0xffff ), cy = (int16_t)( v3 >> 16 );
+                if( i_mvc == 1 ) { mvcx[1] = cx; mvcy[1] = cy; } else if( i_mvc == 2 ) { mvcx[2] = cx; mvcy[2] = cy; } else { mvcx[3] = cx; mvcy[3] = cy; }
+                i_mvc++;
+            }
+        }
+        if( i_mvc <= 1 ) { m.mvpx = mvcx[0]; m.mvpy = mvcy[0]; }
+        else
+        {   // x264_median_mv of the first three (the third is zero when only two exist), base.h:232-246
+            m.mvpx = max( min( mvcx[0], mvcx[1] ), min( max( mvcx[0], mvcx[1] ), mvcx[2] ) );
+            m.mvpy = max( min( mvcy[0], mvcy[1] ), min( max( mvcy[0], mvcy[1] ), mvcy[2] ) );
+        }
+        int mvx = 0, mvy = 0, cost = 0;
+        bool skip = false;
+        if( !( m.mvpx | m.mvpy ) )
+        {   // zero-predictor fast skip, slicetype.c:684-692
+            uint32_t b[4];
+            load_quad( m.fref[0], d.stride, b );
+            cost = quad_sum( m.satd ? satd4x4( m.fenc, b ) : sad4x4( m.fenc, b ) );
+            cost = __shfl_sync( 0xffffffffu, cost, 0 );
+            skip = cost < 64;
+        }
+        if( !skip )
+        {
+            la_me_search( m, d.me_method, d.subpel, d.me_range, mvcx, mvcy, i_mvc, lane, mvx, mvy, cost );
+            cost -= cost_mv[0];
+            if( mvx | mvy ) cost += 5;                              // 5 * lambda
+        }
+        if( lane == 0 )
+        {
+            *(int *)( mvs + 2 * mb_xy ) = (int)pack_mv( mvx, mvy );
+            job.mv_costs[mb_xy] = cost;
+            __threadfence();
+            progress[mb_y] = mb_x;
+        }
+        right_x = mvx; right_y = mvy;
+    }
+    if( lane == 0 ) { __threadfence(); progress[mb_y] = -1; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: slicetype.c:579-652, :706-712, :758-790
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t avg4w( uint32_t a, uint32_t b, int weight )     // pixel_avg_weight_wxh, mc.c:63-75
+{
+    uint32_t out = 0;
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        int p = ( a >> ( 8*i ) ) & 255, qv = ( b >> ( 8*i ) ) & 255;
+        int v = ( p * weight + qv * ( 64 - weight ) + 32 ) >> 6;
+        v = min( max( v, 0 ), 255 );
+        out |= (uint32_t)v << ( 8*i );
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__( 256 )
+finalize_kernel( LaDims d, LaFinalizeArgs A )
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane & 3;
+    const int mb = ( blockIdx.x * 8 + warp ) * 8 + ( lane >> 2 );
+    const bool in_frame = mb < d.mb_count;
+    const int mbc = in_frame ? mb : d.mb_count - 1;
+    const int mb_y = mbc / d.mb_w, mb_x = mbc - mb_y * d.mb_w;
+    // MBs the reference visits (slicetype.c:823-833)
+    const bool visited = in_frame && ( d.do_edges || d.mb_w <= 2 || d.mb_h <= 2 ||
+                                       ( mb_x >= 1 && mb_x <= d.mb_w - 2 && mb_y >= 1 && mb_y <= d.mb_h - 2 ) );
+    const bool score_mb = ( mb_x > 0 && mb_x < d.mb_w - 1 && mb_y > 0 && mb_y < d.mb_h - 1 ) || d.mb_w <= 2 || d.mb_h <= 2;
+    const int qx = ( q & 1 ) * 4, qy = ( q >> 1 ) * 4;
+    const int pel = ( mb_y * 8 ) * d.stride + mb_x * 8 + qy * d.stride + qx;
+    const bool satd = d.subme > 1;
+    int bcost = LA_COST_MAX, list_used = 0;
+
+    if( A.b_inter )
+    {
+        uint32_t a[4];
+        load_quad( A.fenc + pel, d.stride, a );
+        LaMe m0, m1;
+        m0.stride = m1.stride = d.stride;
+        m0.w.enabled = m1.w.enabled = 0;
+#pragma unroll
+        for( int i = 0; i < 4; i++ ) { m0.fref[i] = A.ref0[i] + pel; m1.fref[i] = ( A.b_bidir ? A.ref1[i] : A.ref0[i] ) + pel; }
+        const int v0 = *(const int *)( A.mvs0 + 2 * mbc );
+        const int mv0x = (int16_t)( v0 & 0xffff ), mv0y = (int16_t)( v0 >> 16 );
+        const int c0 = A.cost0[mbc];
+        auto try_bidir = [&]( int ax, int ay, int bx, int by, int penalty ) {
+            uint32_t p1[4], p2[4];
+            if( d.subme <= 1 )
+            {   // half-pel planes addressed directly, slicetype.c:589-596
+                int h1 = ( ( ax & 2 ) >> 1 ) + ( ay & 2 ), h2 = ( ( bx & 2 ) >> 1 ) + ( by & 2 );
+                load_quad( m0.fref[h1] + ( ax >> 2 ) + ( ay >> 2 ) * d.stride, d.stride, p1 );
+                load_quad( m1.fref[h2] + ( bx >> 2 ) + ( by >> 2 ) * d.stride, d.stride, p2 );
+            }
+            else
+            {
+                qpel4x4( m0, ax, ay, p1 );
+                qpel4x4( m1, bx, by, p2 );
+            }
+#pragma unroll
+            for( int r = 0; r < 4; r++ )
+                p1[r] = A.bipred_weight == 32 ? __vavgu4( p1[r], p2[r] ) : avg4w( p1[r], p2[r], A.bipred_weight );
+            int c = penalty + quad_sum( satd ? satd4x4( a, p1 ) : sad4x4( a, p1 ) );
+            if( c < bcost ) { bcost = c; list_used = 3; }
+        };
+        int mv1x = 0, mv1y = 0, c1 = 0;
+        if( A.b_bidir )
+        {
+            const int v1 = *(const int *)( A.mvs1 + 2 * mbc );
+            mv1x = (int16_t)( v1 & 0xffff ); mv1y = (int16_t)( v1 >> 16 );
+            c1 = A.cost1[mbc];
+            int d0x = 0, d0y = 0, d1x = 0, d1y = 0;
+            if( A.mvr )
+            {   // temporal direct, slicetype.c:629-642
+                const int vr = *(const int *)( A.mvr + 2 * mbc );
+                const int rx = (int16_t)( vr & 0xffff ), ry = (int16_t)( vr >> 16 );
+                const int mv_range = d.mv_range2;
+                const int minx = max( 4*( -8*mb_x - 12 ), -mv_range ), maxx = min( 4*( 8*( d.mb_w - mb_x - 1 ) + 12 ), mv_range - 1 );
+                const int miny = max( 4*( -8*mb_y - 12 ), -mv_range ), maxy = min( 4*( 8*( d.mb_h - mb_y - 1 ) + 12 ), mv_range - 1 );
+                d0x = ( rx * A.dist_scale_factor + 128 ) >> 8;
+                d0y = ( ry * A.dist_scale_factor + 128 ) >> 8;
+                d1x = d0x - rx; d1y = d0y - ry;
+                d0x = (int16_t)d0x; d0y = (int16_t)d0y; d1x = (int16_t)d1x; d1y = (int16_t)d1y;
+                d0x = clip3i( d0x, minx, maxx ); d0y = clip3i( d0y, miny, maxy );
+                d1x = clip3i( d1x, minx, maxx ); d1y = clip3i( d1y, miny, maxy );
+                if( d.subme <= 1 ) { d0x &= ~1; d0y &= ~1; d1x &= ~1; d1y &= ~1; }
+            }
+            try_bidir( d0x, d0y, d1x, d1y, 0 );
+            // the zero-vector pair is tried only when the temporal pair is not already zero; computed for all
+            // lanes (uniform code), applied per MB
+            {
+                uint32_t p1[4], p2[4];
+                load_quad( m0.fref[0], d.stride, p1 );
+                load_quad( m1.fref[0], d.stride, p2 );
+#pragma unroll
+                for( int r = 0; r < 4; r++ )
+                    p1[r] = A.bipred_weight == 32 ? __vavgu4( p1[r], p2[r] ) : avg4w( p1[r], p2[r], A.bipred_weight );
+                int c = quad_sum( satd ? satd4x4( a, p1 ) : sad4x4( a, p1 ) );
+                if( ( d0x | d0y | d1x | d1y ) && c < bcost ) { bcost = c; list_used = 3; }
+            }
+        }
+        if( c0 < bcost ) { bcost = c0; list_used = 1; }
+        if( A.b_bidir )
+        {
+            if( c1 < bcost ) { bcost = c1; list_used = 2; }
+            // (mv0, mv1) pair with the 5*lambda penalty; evaluated by every lane group, applied where a vector is non-zero
+            int sb = bcost, sl = list_used;
+            try_bidir( mv0x, mv0y, mv1x, mv1y, 5 );
+            if( !( mv0x | mv0y | mv1x | mv1y ) ) { bcost = sb; list_used = sl; }
+        }
+    }
+
+    const int icost = A.intra[mbc];
+    bcost += 4;                                                     // lowres_penalty
+    int b_intra = 0;
+    if( !A.b_bidir )
+    {
+        b_intra = icost < bcost;
+        if( b_intra ) { bcost = icost; list_used = 0; }
+    }
+    const int qs = d.aq ? A.qscale[mbc] : 256;
+    const int icost_aq = d.aq ? ( icost * qs + 128 ) >> 8 : icost;
+    const int bcost_aq = d.aq ? ( bcost * qs + 128 ) >> 8 : bcost;
+    const bool lead = visited && q == 0;
+    // frame-level sums: {cost_est, cost_est_aq, intra_mbs, intra cost_est, intra cost_est_aq}
+    int sums[5];
+    sums[0] = ( lead && score_mb && A.b_inter ) ? bcost : 0;
+    sums[1] = ( lead && score_mb && A.b_inter ) ? bcost_aq : 0;
+    sums[2] = ( lead && score_mb && !A.b_bidir ) ? b_intra : 0;
+    sums[3] = ( lead && score_mb ) ? icost : 0;
+    sums[4] = ( lead && score_mb ) ? icost_aq : 0;
+#pragma unroll
+    for( int i = 0; i < 5; i++ )
+    {
+        int v = __reduce_add_sync( 0xffffffffu, sums[i] );
+        if( lane == 0 && v ) atomicAdd( &A.record[i], v );
+    }
+    if( lead )
+    {
+        if( A.b_inter ) atomicAdd( &A.row_inter[mb_y], bcost_aq );
+        atomicAdd( &A.row_intra[mb_y], icost_aq );
+        A.costs[mb] = (uint16_t)( min( bcost, LOWRES_COST_MASK ) + ( list_used << LOWRES_COST_SHIFT ) );
+    }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct LaSlotHost
+{
+    LaSlotDev dev;
+    uint8_t *plane_buf;              // 4 planes
+    bool in_use = false;
+    bool intra_on_device = false;    // intra costs computed for the current picture
+    int b_intra_calculated = 0;
+    int cost_est[LA_MAX_B + 2][LA_MAX_B + 2], cost_est_aq[LA_MAX_B + 2][LA_MAX_B + 2];
+    int intra_mbs[LA_MAX_B + 2];
+    bool row_satds_valid[LA_MAX_B + 2][LA_MAX_B + 2];
+    bool searched[2][LA_MAX_B + 1];  // the 0x7FFF sentinel of lowres_mvs[l][d][0][0], kept on the host
+};
+
+struct x264cu_lookahead
+{
+    x264cu_ctx *ctx;
+    x264cu_lookahead_params_t p;
+    LaDims d;
+    int wl, ll;
+    size_t plane_bytes;              // one padded lowres plane
+    std::vector<LaSlotHost> slots;
+    uint16_t *d_cost_mv = nullptr;
+    uint8_t *d_luma = nullptr;       // staging for one full-res luma picture
+    size_t luma_bytes = 0;
+    uint8_t *h_luma = nullptr;       // pinned staging
+    int32_t *d_record = nullptr, *h_record = nullptr;
+    LaSearchJob *d_jobs = nullptr, *h_jobs = nullptr;
+    int max_jobs = 0;
+    uint16_t *h_qscale = nullptr;
+};
+
+static int la_stride_lowres( int wl )
+{
+    int s = ( wl + 96 + 63 ) & ~63;          // align_stride( width + PADH2, 64, 2048 ), common/frame.c:30-36, :125
+    if( !( s & 2047 ) ) s += 64;
+    return s;
+}
+
 extern "C" void x264cu_lookahead_close_internal( x264cu_ctx *ctx ) { (void)ctx; }
+
+extern "C" {
+
+void x264cu_lookahead_close( x264cu_lookahead_t *la )
+{
+    if( !la ) return;
+    cudaSetDevice( la->ctx->device );
+    cudaStreamSynchronize( la->ctx->stream );
+    for( auto &s : la->slots )
+    {
+        cudaFree( s.plane_buf ); cudaFree( s.dev.mvs ); cudaFree( s.dev.mv_costs ); cudaFree( s.dev.costs );
+        cudaFree( s.dev.intra ); cudaFree( s.dev.qscale ); cudaFree( s.dev.row_satds ); cudaFree( s.dev.progress );
+    }
+    cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record ); cudaFree( la->d_jobs );
+    cudaFreeHost( la->h_luma ); cudaFreeHost( la->h_record ); cudaFreeHost( la->h_jobs ); cudaFreeHost( la->h_qscale );
+    delete la;
+}
+
+int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p, x264cu_lookahead_t **out )
+{
+    if( !ctx || !p || !out ) return -1;
+    *out = nullptr;
+    if( p->width < 16 || p->height < 16 ) return x264cu_fail( ctx, "lookahead_open: picture %dx%d too small", p->width, p->height );
+    if( p->bframes < 0 || p->bframes > LA_MAX_B ) return x264cu_fail( ctx, "lookahead_open: bframes %d out of range", p->bframes );
+    if( p->me_method < X264CU_ME_DIA || p->me_method > X264CU_ME_UMH )
+        return x264cu_fail( ctx, "lookahead_open: me_method %d not supported (esa/tesa are outside this backend)", p->me_method );
+    if( p->n_slots < 2 ) return x264cu_fail( ctx, "lookahead_open: need at least 2 frame slots" );
+    if( p->mv_range < 32 || p->mv_range > 4096 ) return x264cu_fail( ctx, "lookahead_open: mv_range %d out of range", p->mv_range );
+    x264cu_lookahead *la = new x264cu_lookahead;
+    la->ctx = ctx; la->p = *p;
+    LaDims &d = la->d;
+    d.mb_w = ( p->width + 15 ) >> 4; d.mb_h = ( p->height + 15 ) >> 4; d.mb_count = d.mb_w * d.mb_h;
+    la->wl = d.mb_w * 8; la->ll = d.mb_h * 8;
+    d.stride = la_stride_lowres( la->wl );
+    d.B = p->bframes;
+    d.subme = p->subpel_refine;
+    if( p->subpel_refine > 1 ) { d.me_method = p->me_method < X264CU_ME_HEX ? p->me_method : X264CU_ME_HEX; d.subpel = 4; }
+    else { d.me_method = X264CU_ME_DIA; d.subpel = 2; }
+    d.me_range = p->me_range;
+    d.mv_range2 = 2 * p->mv_range;
+    d.bipred_weighted = p->weighted_bipred; d.aq = p->aq_mode != 0;
+    d.do_edges = p->mb_tree || p->vbv || d.mb_w <= 2 || d.mb_h <= 2;
+    d.cost_len = 2 * 4 * p->mv_range;
+    la->plane_bytes = (size_t)d.stride * ( la->ll + 2 * X264CU_PAD ) + 256;
+
+    cudaSetDevice( ctx->device );
+    bool ok = true;
+    auto alloc = [&]( void **ptr, size_t n ) { if( cudaMalloc( ptr, n ) != cudaSuccess ) ok = false; else cudaMemsetAsync( *ptr, 0, n, ctx->stream ); };
+    la->slots.resize( p->n_slots );
+    const int B1 = d.B + 1, B2 = ( d.B + 2 ) * ( d.B + 2 );
+    for( auto &s : la->slots )
+    {
+        memset( &s.dev, 0, sizeof( s.dev ) );
+        s.plane_buf = nullptr;
+        alloc( (void **)&s.plane_buf, 4 * la->plane_bytes );
+        if( !ok ) break;
+        for( int i = 0; i < 4; i++ )
+            s.dev.planes[i] = s.plane_buf + i * la->plane_bytes + (size_t)X264CU_PAD * d.stride + X264CU_PAD + 32;
+        alloc( (void **)&s.dev.mvs, (size_t)2 * B1 * d.mb_count * 4 + 64 );
+        alloc( (void **)&s.dev.mv_costs, (size_t)2 * B1 * d.mb_count * 4 );
+        alloc( (void **)&s.dev.costs, (size_t)B2 * d.mb_count * 2 );
+        alloc( (void **)&s.dev.intra, (size_t)d.mb_count * 4 );
+        alloc( (void **)&s.dev.qscale, (size_t)d.mb_count * 2 );
+        alloc( (void **)&s.dev.row_satds, (size_t)B2 * d.mb_h * 4 );
+        alloc( (void **)&s.dev.progress, (size_t)2 * B1 * d.mb_h * 4 );
+    }
+    la->luma_bytes = (size_t)( ( p->width + 63 ) & ~63 ) * p->height + 64;
+    alloc( (void **)&la->d_luma, la->luma_bytes );
+    alloc( (void **)&la->d_cost_mv, ( 2 * d.cost_len + 1 ) * 2 + 16 );
+    alloc( (void **)&la->d_record, 64 );
+    la->max_jobs = 4096;
+    alloc( (void **)&la->d_jobs, la->max_jobs * sizeof( LaSearchJob ) );
+    if( ok && cudaMallocHost( (void **)&la->h_luma, la->luma_bytes ) != cudaSuccess ) ok = false;
+    if( ok && cudaMallocHost( (void **)&la->h_record, 64 ) != cudaSuccess ) ok = false;
+    if( ok && cudaMallocHost( (void **)&la->h_jobs, la->max_jobs * sizeof( LaSearchJob ) ) != cudaSuccess ) ok = false;
+    if( ok && cudaMallocHost( (void **)&la->h_qscale, d.mb_count * 2 ) != cudaSuccess ) ok = false;
+    if( !ok )
+    {
+        x264cu_fail( ctx, "lookahead_open: out of device / pinned memory" );
+        x264cu_lookahead_close( la );
+        return -1;
+    }
+    // cost_mv[X264_LOOKAHEAD_QP]: lambda = x264_lambda_tab[12] = 1 (analyse.c:143-157, :179-188, tables.c:99).
+    // Built on the host with the same float expressions as the reference and uploaded.
+    std::vector<uint16_t> tab( 2 * d.cost_len + 1 );
+    for( int i = 0; i <= d.cost_len; i++ )
+    {
+        float l = i ? log2f( (float)( i + 1 ) ) * 2.0f + 1.718f : 0.718f;
+        int c = (int)( 1 * l + .5f );
+        if( c > 65535 ) c = 65535;
+        tab[d.cost_len + i] = tab[d.cost_len - i] = (uint16_t)c;
+    }
+    if( cudaMemcpyAsync( la->d_cost_mv, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice, ctx->stream ) != cudaSuccess ||
+        cudaStreamSynchronize( ctx->stream ) != cudaSuccess )
+    {
+        x264cu_fail( ctx, "lookahead_open: cost table upload failed" );
+        x264cu_lookahead_close( la );
+        return -1;
+    }
+    *out = la;
+    return 0;
+}
+
+static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_qscale )
+{
+    x264cu_ctx *ctx = la->ctx;
+    LaSlotHost &s = la->slots[slot];
+    const LaDims &d = la->d;
+    // x264_frame_init_lowres's memo reset (mc.c:472-481) + zeroed vectors (frame.c:287-293)
+    memset( s.cost_est, -1, sizeof( s.cost_est ) );
+    memset( s.cost_est_aq, -1, sizeof( s.cost_est_aq ) );
+    memset( s.intra_mbs, 0, sizeof( s.intra_mbs ) );
+    memset( s.row_satds_valid, 0, sizeof( s.row_satds_valid ) );
+    memset( s.searched, 0, sizeof( s.searched ) );
+    s.b_intra_calculated = 0;
+    s.intra_on_device = false;
+    s.in_use = true;
+    CU_CHECK( ctx, cudaMemsetAsync( s.dev.mvs, 0, (size_t)2 * ( d.B + 1 ) * d.mb_count * 4, ctx->stream ) );
+    if( h_inv_qscale )
+    {
+        memcpy( la->h_qscale, h_inv_qscale, d.mb_count * 2 );
+        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, la->h_qscale, d.mb_count * 2, cudaMemcpyHostToDevice, ctx->stream ) );
+        CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );            // h_qscale is reused by the next put
+    }
+    else
+    {
+        for( int i = 0; i < d.mb_count; i++ ) la->h_qscale[i] = 256;
+        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, la->h_qscale, d.mb_count * 2, cudaMemcpyHostToDevice, ctx->stream ) );
+        CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
+    }
+    return 0;
+}
+
+int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const uint8_t *d_luma, intptr_t luma_stride,
+                                       const uint16_t *h_inv_qscale )
+{
+    if( !la ) return -1;
+    if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( la->ctx, "frame_put: slot %d out of range", slot );
+    LaSlotHost &s = la->slots[slot];
+    if( x264cu_frame_init_lowres( la->ctx, d_luma, luma_stride, la->p.width, la->p.height, s.dev.planes, la->d.stride ) ) return -1;
+    return la_reset_slot( la, slot, h_inv_qscale );
+}
+
+int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
+                                const uint16_t *h_inv_qscale )
+{
+    if( !la ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( ctx, "frame_put: slot %d out of range", slot );
+    const int w = la->p.width, h = la->p.height;
+    const intptr_t st = ( w + 63 ) & ~63;
+    CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );               // staging buffer free again
+    for( int y = 0; y < h; y++ )
+        memcpy( la->h_luma + y * st, h_luma + y * luma_stride, w );
+    CU_CHECK( ctx, cudaMemcpyAsync( la->d_luma, la->h_luma, (size_t)st * h, cudaMemcpyHostToDevice, ctx->stream ) );
+    return x264cu_lookahead_frame_put_device( la, slot, la->d_luma, st, h_inv_qscale );
+}
+
+// enqueue the searches listed in h_jobs[0..n) as one launch
+static int la_launch_searches( x264cu_lookahead *la, int n )
+{
+    x264cu_ctx *ctx = la->ctx;
+    const LaDims &d = la->d;
+    if( n <= 0 ) return 0;
+    constexpr int NW = 8;
+    const int rows = d.mb_h - ( d.do_edges ? 0 : 2 );
+    if( rows <= 0 ) return 0;
+    CU_CHECK( ctx, cudaMemcpyAsync( la->d_jobs, la->h_jobs, n * sizeof( LaSearchJob ), cudaMemcpyHostToDevice, ctx->stream ) );
+    dim3 grid( ( rows + NW - 1 ) / NW, n );
+    size_t smem = ( 2 * d.cost_len + 1 ) * 2 + 16;
+    static bool attr = false;
+    if( !attr )
+    {
+        CU_CHECK( ctx, cudaFuncSetAttribute( search_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 ) );
+        attr = true;
+    }
+    if( smem > 200 * 1024 ) return x264cu_fail( ctx, "lookahead: mv cost table does not fit in shared memory" );
+    search_kernel<NW><<<grid, NW * 32, smem, ctx->stream>>>( d, la->d_jobs, la->d_cost_mv );
+    CU_LAUNCH_CHECK( ctx );
+    CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );               // h_jobs reusable; results visible
+    return 0;
+}
+
+static void la_fill_job( x264cu_lookahead *la, LaSearchJob &j, int fenc_slot, int ref_slot, int list, int dist )
+{
+    const LaDims &d = la->d;
+    LaSlotHost &f = la->slots[fenc_slot], &r = la->slots[ref_slot];
+    const size_t idx = (size_t)list * ( d.B + 1 ) + ( dist - 1 );
+    j.fenc = f.dev.planes[0];
+    for( int i = 0; i < 4; i++ ) j.ref[i] = r.dev.planes[i];
+    j.mvs = f.dev.mvs + idx * d.mb_count * 2;
+    j.mv_costs = f.dev.mv_costs + idx * d.mb_count;
+    j.progress = f.dev.progress + idx * d.mb_h;
+}
+
+static int la_reset_progress( x264cu_lookahead *la, const LaSearchJob &j )
+{
+    // "nothing done yet" = a column index larger than any real one (0x7F7F7F7F)
+    CU_CHECK( la->ctx, cudaMemsetAsync( j.progress, 0x7F, (size_t)la->d.mb_h * 4, la->ctx->stream ) );
+    return 0;
+}
+
+int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int *fenc, const int *ref, const int *list, const int *dist )
+{
+    if( !la ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    int n = 0;
+    for( int i = 0; i < n_jobs; i++ )
+    {
+        if( fenc[i] < 0 || fenc[i] >= (int)la->slots.size() || ref[i] < 0 || ref[i] >= (int)la->slots.size() ||
+            list[i] < 0 || list[i] > 1 || dist[i] < 1 || dist[i] > la->d.B + 1 )
+            return x264cu_fail( ctx, "search_batch: bad job %d", i );
+        if( list[i] == 1 && la->d.B == 0 ) return x264cu_fail( ctx, "search_batch: list 1 without b-frames" );
+        LaSlotHost &f = la->slots[fenc[i]];
+        if( !f.in_use || !la->slots[ref[i]].in_use ) return x264cu_fail( ctx, "search_batch: empty slot in job %d", i );
+        if( f.searched[list[i]][dist[i] - 1] ) continue;
+        f.searched[list[i]][dist[i] - 1] = true;
+        if( n == la->max_jobs )
+        {
+            if( la_launch_searches( la, n ) ) return -1;
+            n = 0;
+        }
+        la_fill_job( la, la->h_jobs[n], fenc[i], ref[i], list[i], dist[i] );
+        if( la_reset_progress( la, la->h_jobs[n] ) ) return -1;
+        n++;
+    }
+    return la_launch_searches( la, n );
+}
+
+int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
+{
+    if( !la || !frames || !score ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    const LaDims &d = la->d;
+    if( !( p0 <= b && b <= p1 ) || b - p0 > d.B + 1 || p1 - b > d.B + 1 )
+        return x264cu_fail( ctx, "frame_cost: bad frame triple (%d,%d,%d)", p0, p1, b );
+    const int sb = frames[b], s0 = frames[p0], s1 = frames[p1];
+    for( int s : { sb, s0, s1 } )
+        if( s < 0 || s >= (int)la->slots.size() || !la->slots[s].in_use ) return x264cu_fail( ctx, "frame_cost: empty slot %d", s );
+    LaSlotHost &fenc = la->slots[sb];
+    const int i0 = b - p0, i1 = p1 - b;
+    // memo check, slicetype.c:848-849
+    if( fenc.cost_est[i0][i1] >= 0 && ( !la->p.vbv || fenc.row_satds_valid[i0][i1] ) )
+    {
+        *score = fenc.cost_est[i0][i1];
+        return 0;
+    }
+    // do_search / sentinels, slicetype.c:855-866 (weighted prediction is analysed by the caller; not used here)
+    int n = 0;
+    if( b != p0 && !fenc.searched[0][i0 - 1] )
+    {
+        fenc.searched[0][i0 - 1] = true;
+        la_fill_job( la, la->h_jobs[n], sb, s0, 0, i0 );
+        if( la_reset_progress( la, la->h_jobs[n] ) ) return -1;
+        n++;
+    }
+    if( b != p1 && !fenc.searched[1][i1 - 1] )
+    {
+        fenc.searched[1][i1 - 1] = true;
+        la_fill_job( la, la->h_jobs[n], sb, s1, 1, i1 );
+        if( la_reset_progress( la, la->h_jobs[n] ) ) return -1;
+        n++;
+    }
+    if( !fenc.intra_on_device )
+    {
+        intra_kernel<<<( d.mb_count + 63 ) / 64, 256, 0, ctx->stream>>>( d, fenc.dev.planes[0], fenc.dev.intra );
+        CU_LAUNCH_CHECK( ctx );
+        fenc.intra_on_device = true;
+    }
+    if( la_launch_searches( la, n ) ) return -1;
+
+    int dist_scale_factor = 128;
+    if( p1 != p0 ) dist_scale_factor = ( ( ( b - p0 ) << 8 ) + ( ( p1 - p0 ) >> 1 ) ) / ( p1 - p0 );
+    LaFinalizeArgs A;
+    memset( &A, 0, sizeof( A ) );
+    const int B1 = d.B + 1, B2w = d.B + 2;
+    A.fenc = fenc.dev.planes[0];
+    for( int i = 0; i < 4; i++ ) { A.ref0[i] = la->slots[s0].dev.planes[i]; A.ref1[i] = la->slots[s1].dev.planes[i]; }
+    A.b_inter = p0 != p1;
+    A.b_bidir = b < p1;
+    if( b != p0 )
+    {
+        A.mvs0 = fenc.dev.mvs + (size_t)( 0 * B1 + i0 - 1 ) * d.mb_count * 2;
+        A.cost0 = fenc.dev.mv_costs + (size_t)( 0 * B1 + i0 - 1 ) * d.mb_count;
+    }
+    if( b != p1 )
+    {
+        A.mvs1 = fenc.dev.mvs + (size_t)( 1 * B1 + i1 - 1 ) * d.mb_count * 2;
+        A.cost1 = fenc.dev.mv_costs + (size_t)( 1 * B1 + i1 - 1 ) * d.mb_count;
+    }
+    if( A.b_bidir && p1 - p0 - 1 <= d.B && la->slots[s1].searched[0][p1 - p0 - 1] )
+        A.mvr = la->slots[s1].dev.mvs + (size_t)( 0 * B1 + p1 - p0 - 1 ) * d.mb_count * 2;
+    A.intra = fenc.dev.intra;
+    A.qscale = fenc.dev.qscale;
+    A.costs = fenc.dev.costs + (size_t)( i0 * B2w + i1 ) * d.mb_count;
+    // row sums (slicetype.c:968-977): the inter rows of this request go to row_satds[b-p0][p1-b]; the intra rows
+    // go to row_satds[0][0] only while b_intra_calculated is unset.  Anything else lands in scratch rows.
+    int32_t *scratch_rows = (int32_t *)x264cu_scratch( ctx, 4, (size_t)2 * d.mb_h * 4 );
+    if( !scratch_rows ) return -1;
+    A.row_inter = A.b_inter ? fenc.dev.row_satds + (size_t)( i0 * B2w + i1 ) * d.mb_h : scratch_rows;
+    A.row_intra = !fenc.b_intra_calculated ? fenc.dev.row_satds : scratch_rows + d.mb_h;
+    A.record = la->d_record;
+    A.dist_scale_factor = dist_scale_factor;
+    A.bipred_weight = d.bipred_weighted ? 64 - ( dist_scale_factor >> 2 ) : 32;
+    CU_CHECK( ctx, cudaMemsetAsync( la->d_record, 0, 64, ctx->stream ) );
+    CU_CHECK( ctx, cudaMemsetAsync( A.row_inter, 0, d.mb_h * 4, ctx->stream ) );
+    CU_CHECK( ctx, cudaMemsetAsync( A.row_intra, 0, d.mb_h * 4, ctx->stream ) );
+    finalize_kernel<<<( d.mb_count + 63 ) / 64, 256, 0, ctx->stream>>>( d, A );
+    CU_LAUNCH_CHECK( ctx );
+    CU_CHECK( ctx, cudaMemcpyAsync( la->h_record, la->d_record, 32, cudaMemcpyDeviceToHost, ctx->stream ) );
+    CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
+
+    // accumulator hand-over in the reference's order, slicetype.c:946-989
+    const int32_t *r = la->h_record;
+    if( b == p1 ) fenc.intra_mbs[i0] = r[2];
+    if( !fenc.b_intra_calculated ) { fenc.cost_est[0][0] = 0; fenc.cost_est_aq[0][0] = 0; }
+    fenc.cost_est[i0][i1] = 0; fenc.cost_est_aq[i0][i1] = 0;
+    if( !fenc.b_intra_calculated ) { fenc.cost_est[0][0] += r[3]; fenc.cost_est_aq[0][0] += r[4]; }
+    fenc.cost_est[i0][i1] += r[0]; fenc.cost_est_aq[i0][i1] += r[1];
+    if( la->p.vbv )
+    {
+        fenc.row_satds_valid[i0][i1] = true;
+        if( !fenc.b_intra_calculated ) fenc.row_satds_valid[0][0] = true;
+    }
+    int sc = fenc.cost_est[i0][i1];
+    if( b != p1 ) sc = (int)( (uint64_t)sc * 100 / ( 120 + la->p.bframe_bias ) );
+    else fenc.b_intra_calculated = 1;
+    fenc.cost_est[i0][i1] = sc;
+    *score = sc;
+    return 0;
+}
+
+static int la_check_slot( x264cu_lookahead *la, int slot )
+{
+    if( !la ) return -1;
+    if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use )
+        return x264cu_fail( la->ctx, "lookahead: slot %d is empty / out of range", slot );
+    return 0;
+}
+
+int x264cu_lookahead_get_mvs( x264cu_lookahead_t *la, int slot, int list, int dist_minus1, int16_t *h_mvs, int32_t *h_mv_costs )
+{
+    if( la_check_slot( la, slot ) ) return -1;
+    const LaDims &d = la->d;
+    if( list < 0 || list > 1 || dist_minus1 < 0 || dist_minus1 > d.B ) return x264cu_fail( la->ctx, "get_mvs: bad index" );
+    const size_t idx = (size_t)list * ( d.B + 1 ) + dist_minus1;
+    if( h_mvs ) CU_CHECK( la->ctx, cudaMemcpyAsync( h_mvs, la->slots[slot].dev.mvs + idx * d.mb_count * 2, d.mb_count * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
+    if( h_mv_costs ) CU_CHECK( la->ctx, cudaMemcpyAsync( h_mv_costs, la->slots[slot].dev.mv_costs + idx * d.mb_count, d.mb_count * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
+    CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
+    if( h_mvs && !la->slots[slot].searched[list][dist_minus1] ) h_mvs[0] = 0x7FFF;      // the reference's sentinel (mc.c:478-480)
+    return 0;
+}
+
+int x264cu_lookahead_get_costs( x264cu_lookahead_t *la, int slot, int i0, int i1, uint16_t *h_out )
+{
+    if( la_check_slot( la, slot ) ) return -1;
+    const LaDims &d = la->d;
+    if( i0 < 0 || i1 < 0 || i0 > d.B + 1 || i1 > d.B + 1 ) return x264cu_fail( la->ctx, "get_costs: bad index" );
+    CU_CHECK( la->ctx, cudaMemcpyAsync( h_out, la->slots[slot].dev.costs + (size_t)( i0 * ( d.B + 2 ) + i1 ) * d.mb_count, d.mb_count * 2, cudaMemcpyDeviceToHost, la->ctx->stream ) );
+    CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
+    return 0;
+}
+
+int x264cu_lookahead_get_intra( x264cu_lookahead_t *la, int slot, int32_t *h_out )
+{
+    if( la_check_slot( la, slot ) ) return -1;
+    CU_CHECK( la->ctx, cudaMemcpyAsync( h_out, la->slots[slot].dev.intra, la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
+    CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
+    return 0;
+}
+
+int x264cu_lookahead_get_row_satds( x264cu_lookahead_t *la, int slot, int i0, int i1, int32_t *h_rows )
+{
+    if( la_check_slot( la, slot ) ) return -1;
+    const LaDims &d = la->d;
+    if( i0 < 0 || i1 < 0 || i0 > d.B + 1 || i1 > d.B + 1 ) return x264cu_fail( la->ctx, "get_row_satds: bad index" );
+    CU_CHECK( la->ctx, cudaMemcpyAsync( h_rows, la->slots[slot].dev.row_satds + (size_t)( i0 * ( d.B + 2 ) + i1 ) * d.mb_h, d.mb_h * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
+    CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
+    return 0;
+}
+
+int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int i0, int i1, int *cost_est, int *cost_est_aq, int *intra_mbs )
+{
+    if( la_check_slot( la, slot ) ) return -1;
+    const LaDims &d = la->d;
+    if( i0 < 0 || i1 < 0 || i0 > d.B + 1 || i1 > d.B + 1 ) return x264cu_fail( la->ctx, "get_cost_est: bad index" );
+    LaSlotHost &s = la->slots[slot];
+    if( cost_est ) *cost_est = s.cost_est[i0][i1];
+    if( cost_est_aq ) *cost_est_aq = s.cost_est_aq[i0][i1];
+    if( intra_mbs ) *intra_mbs = s.intra_mbs[i0];
+    return 0;
+}
+
+int x264cu_lookahead_get_lowres_plane( x264cu_lookahead_t *la, int slot, int plane, uint8_t *h_out, intptr_t *stride )
+{
+    if( la_check_slot( la, slot ) ) return -1;
+    if( plane < 0 || plane > 3 ) return x264cu_fail( la->ctx, "get_lowres_plane: bad plane" );
+    const LaDims &d = la->d;
+    if( stride ) *stride = d.stride;
+    if( h_out )
+    {   // padded plane starting at (-PAD,-PAD), stride bytes per row, ll + 2*PAD rows
+        const uint8_t *src = la->slots[slot].dev.planes[plane] - (size_t)X264CU_PAD * d.stride - X264CU_PAD;
+        CU_CHECK( la->ctx, cudaMemcpyAsync( h_out, src, (size_t)d.stride * ( la->ll + 2 * X264CU_PAD ) - 64, cudaMemcpyDeviceToHost, la->ctx->stream ) );
+        CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
+    }
+    return 0;
+}
+
+} // extern "C"
