@@ -925,7 +925,7 @@ int x264cu_lookahead_get_lowres_plane( x264cu_lookahead_t *la, int slot, int pla
     if( h_out )
     {   // padded plane starting at (-PAD,-PAD), stride bytes per row, ll + 2*PAD rows
         const uint8_t *src = la->slots[slot].dev.planes[plane] - (size_t)X264CU_PAD * d.stride - X264CU_PAD;
-        CU_CHECK( la->ctx, cudaMemcpyAsync( h_out, src, (size_t)d.stride * ( la->ll + 2 * X264CU_PAD ) - 64, cudaMemcpyDeviceToHost, la->ctx->stream ) );
+        CU_CHECK( la->ctx, cudaMemcpyAsync( h_out, src, (size_t)d.stride * ( la->ll + 2 * X264CU_PAD ), cudaMemcpyDeviceToHost, la->ctx->stream ) );
         CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
     }
     return 0;
