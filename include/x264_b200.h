@@ -206,6 +206,48 @@ int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int b_minus
                                    int *cost_est, int *cost_est_aq, int *intra_mbs );
 int x264cu_lookahead_get_lowres_plane( x264cu_lookahead_t *la, int slot, int plane, uint8_t *h_out, intptr_t *stride );
 
+/* ------------------------------------------------------------------------------------------------
+ * Slice-type decision on top of the GPU lookahead: the host control flow of x264_slicetype_decide /
+ * x264_slicetype_analyse / scenecut / slicetype_path (encoder/slicetype.c:1288-1974) and the frame queue of
+ * encoder/lookahead.c:192-250 (synchronous lookahead: param.i_sync_lookahead == 0), calling
+ * x264cu_lookahead_frame_cost exactly where the reference calls slicetype_frame_cost -- MB-tree's and the
+ * rate control's cost requests included, because the memoised B costs depend on request order
+ * (slicetype.c:629-642).  Plain C; no device code.
+ * Not covered (rejected at open): weighted P prediction analysis, VBV lookahead, open-GOP, intra refresh,
+ * forced frame types, 2-pass stats.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct x264cu_slicetype x264cu_slicetype_t;
+
+typedef struct
+{
+    x264cu_lookahead_params_t la; /* la.n_slots is ignored (sized internally) */
+    int keyint_max, keyint_min;   /* h->param.i_keyint_max / i_keyint_min (after validation) */
+    int scenecut_threshold;       /* h->param.i_scenecut_threshold */
+    int b_adapt;                  /* h->param.i_bframe_adaptive: 0 none, 1 fast, 2 trellis */
+    int b_pyramid;                /* h->param.i_bframe_pyramid: 0 none, 1 strict, 2 normal */
+    int rc_lookahead;             /* h->param.rc.i_lookahead */
+    int psy;                      /* h->param.analyse.b_psy */
+    int frame_reference;          /* h->param.i_frame_reference */
+    int rc_cqp;                   /* h->param.rc.i_rc_method == X264_RC_CQP */
+} x264cu_slicetype_params_t;
+
+enum { X264CU_TYPE_AUTO = 0, X264CU_TYPE_IDR = 1, X264CU_TYPE_I = 2, X264CU_TYPE_P = 3, X264CU_TYPE_BREF = 4,
+       X264CU_TYPE_B = 5 };       /* x264.h:274-280 */
+
+int  x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *params, x264cu_slicetype_t **out );
+void x264cu_slicetype_close( x264cu_slicetype_t *st );
+/* One x264_encoder_encode step as far as the lookahead is concerned (encoder.c:3323-3450): h_luma != NULL queues a
+ * picture (x264_lookahead_put_frame), NULL flushes.  When the encoder would have picked a frame to encode,
+ * *out_frame is its display index and *out_type its decided type (coded order); otherwise *out_frame = -1.
+ * Returns 0, or -1 on error.  While flushing, *out_frame == -1 means the stream is drained. */
+int  x264cu_slicetype_step( x264cu_slicetype_t *st, const uint8_t *h_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
+                            int *out_frame, int *out_type );
+/* the lookahead object underneath (for reading per-MB results) and the slot a display index currently occupies (-1 if gone) */
+x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *st );
+int  x264cu_slicetype_slot_of( x264cu_slicetype_t *st, int frame );
+/* number of slicetype_frame_cost requests issued so far (memo hits included) */
+long x264cu_slicetype_cost_requests( x264cu_slicetype_t *st );
+
 #ifdef __cplusplus
 }
 #endif

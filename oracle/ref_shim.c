@@ -78,6 +78,7 @@ XREF_API int xref_param( void *hv, const char *name )
     P( "sync_lookahead", h->param.i_sync_lookahead ) P( "threads", h->param.i_threads )
     P( "stride", h->fdec->i_stride[0] ) P( "stride_lowres", h->fdec->i_stride_lowres )
     P( "width_lowres", h->fdec->i_width_lowres ) P( "lines_lowres", h->fdec->i_lines_lowres )
+    P( "psy", h->param.analyse.b_psy ) P( "ref", h->param.i_frame_reference )
     P( "b_pyramid", h->param.i_bframe_pyramid ) P( "open_gop", h->param.b_open_gop ) P( "intra_refresh", h->param.b_intra_refresh )
 #undef P
     return -9999;
@@ -401,4 +402,42 @@ XREF_API void xref_la_free( void *lav )
         if( la->frames[i] ) x264_frame_delete( la->frames[i] );
     free( la->frames );
     free( la );
+}
+
+/* ------------------------------------------------------------------ whole-encoder frame types ------- */
+/* Encode n luma pictures (chroma = 128) with the opened encoder and report, in coded (output) order, the display
+ * index (pts) and decided type (X264_TYPE_*) of every frame.  This is the reference's own answer to "which slice
+ * types does the lookahead choose".  Returns the number of frames output. */
+XREF_API int xref_encode_types( void *hv, const uint8_t *luma, int n, int *out_idx, int *out_type )
+{
+    x264_t *h = hv;
+    int w = h->param.i_width, ht = h->param.i_height;
+    int cw = ( w + 1 ) / 2, ch = ( ht + 1 ) / 2;
+    uint8_t *chroma = malloc( (size_t)cw * ch );
+    memset( chroma, 128, (size_t)cw * ch );
+    int n_out = 0;
+    x264_nal_t *nal; int i_nal;
+    x264_picture_t pic_in, pic_out;
+    for( int i = 0; i < n; i++ )
+    {
+        x264_picture_init( &pic_in );
+        pic_in.img.i_csp = X264_CSP_I420;
+        pic_in.img.i_plane = 3;
+        pic_in.img.plane[0] = (uint8_t*)luma + (size_t)i * w * ht; pic_in.img.i_stride[0] = w;
+        pic_in.img.plane[1] = chroma; pic_in.img.i_stride[1] = cw;
+        pic_in.img.plane[2] = chroma; pic_in.img.i_stride[2] = cw;
+        pic_in.i_pts = i;
+        pic_in.i_type = X264_TYPE_AUTO;
+        int sz = x264_encoder_encode( h, &nal, &i_nal, &pic_in, &pic_out );
+        if( sz < 0 ) { free( chroma ); return -1; }
+        if( sz > 0 ) { out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
+    }
+    while( x264_encoder_delayed_frames( h ) > 0 )
+    {
+        int sz = x264_encoder_encode( h, &nal, &i_nal, NULL, &pic_out );
+        if( sz < 0 ) { free( chroma ); return -1; }
+        if( sz > 0 ) { out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
+    }
+    free( chroma );
+    return n_out;
 }

@@ -252,3 +252,26 @@ def synth_sequence(width, height, n, seed, cut_at=None):
         img = crop + rng.normal(0, 1.5, crop.shape)
         frames.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
     return frames
+
+
+_st_oracle = None
+
+
+def slicetype_oracle_lib():
+    """the product's host slice-type logic (x264_b200/csrc/slicetype.c) linked against the CPU oracle instead of the GPU
+    lookahead, so that its control flow can be checked against the reference's encoder without a device"""
+    global _st_oracle
+    if _st_oracle is None:
+        oracle()
+        out_dir = os.path.join(ROOT, "tests", "_build")
+        os.makedirs(out_dir, exist_ok=True)
+        so = os.path.join(out_dir, "libslicetype_oracle.so")
+        srcs = [os.path.join(ROOT, "x264_b200", "csrc", "slicetype.c"), os.path.join(ROOT, "tests", "csrc", "slicetype_oracle_glue.c")]
+        deps = srcs + [ORACLE_SO, os.path.join(ROOT, "include", "x264_b200.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=gnu99", "-o", so] + srcs +
+                                  ["-L" + os.path.dirname(ORACLE_SO), "-loracle", "-Wl,-rpath," + os.path.dirname(ORACLE_SO), "-lm"])
+        L = C.CDLL(so)
+        from x264_b200.binding_ext import bind
+        _st_oracle = L
+    return _st_oracle

@@ -1,0 +1,71 @@
+/* TEST INFRASTRUCTURE: lets the product's host-side slice-type logic (x264_b200/csrc/slicetype.c) run on a machine
+ * without a GPU by standing in for the five x264cu_lookahead_* entry points it calls with the CPU oracle
+ * (oracle/oracle_lookahead.c).  Built by tests/_libs.py into tests/_build/libslicetype_oracle.so; never shipped. */
+#include "../../include/x264_b200.h"
+#include "../../oracle/oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+int orc_la_frame_cost( const orc_la_params_t *p, const uint16_t *cost_mv_centre, orc_la_frame_t **frames, int p0, int p1, int b );
+
+struct x264cu_lookahead
+{
+    orc_la_params_t p;
+    int n_slots;
+    orc_la_frame_t **slots;
+    uint16_t *tab;
+    int tab_len;
+};
+
+int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *q, x264cu_lookahead_t **out )
+{
+    (void)ctx;
+    x264cu_lookahead_t *la = calloc( 1, sizeof( *la ) );
+    la->p.width = q->width; la->p.height = q->height;
+    la->p.mb_width = ( q->width + 15 ) >> 4; la->p.mb_height = ( q->height + 15 ) >> 4;
+    la->p.subpel_refine = q->subpel_refine; la->p.me_method = q->me_method; la->p.me_range = q->me_range;
+    la->p.mv_range = q->mv_range; la->p.bframes = q->bframes; la->p.bframe_bias = q->bframe_bias;
+    la->p.weighted_bipred = q->weighted_bipred; la->p.aq_mode = q->aq_mode; la->p.vbv = q->vbv;
+    la->p.do_edges = q->mb_tree || q->vbv;
+    la->n_slots = q->n_slots;
+    la->slots = calloc( q->n_slots, sizeof( void * ) );
+    la->tab_len = 2 * 4 * q->mv_range;
+    la->tab = malloc( ( 2 * la->tab_len + 1 ) * 2 );
+    orc_cost_mv_table( la->tab, la->tab_len, 1 );
+    *out = la;
+    return 0;
+}
+
+void x264cu_lookahead_close( x264cu_lookahead_t *la )
+{
+    if( !la ) return;
+    for( int i = 0; i < la->n_slots; i++ ) orc_la_frame_delete( la->slots[i] );
+    free( la->slots ); free( la->tab ); free( la );
+}
+
+void orc_la_frame_set_qscale( orc_la_frame_t *f, const uint16_t *inv_qscale );
+
+int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride, const uint16_t *q )
+{
+    orc_la_frame_delete( la->slots[slot] );
+    la->slots[slot] = orc_la_frame_new( &la->p, h_luma, luma_stride );
+    if( q ) orc_la_frame_set_qscale( la->slots[slot], q );
+    return 0;
+}
+
+int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
+{
+    orc_la_frame_t *fr[300];
+    for( int i = p0; i <= p1; i++ ) fr[i] = la->slots[frames[i]];
+    *score = orc_la_frame_cost( &la->p, la->tab + la->tab_len, fr, p0, p1, b );
+    return 0;
+}
+
+int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int i0, int i1, int *ce, int *ceaq, int *imb )
+{
+    orc_la_frame_t *f = la->slots[slot];
+    if( ce ) *ce = f->cost_est[i0][i1];
+    if( ceaq ) *ceaq = f->cost_est_aq[i0][i1];
+    if( imb ) *imb = f->intra_mbs[i0];
+    return 0;
+}

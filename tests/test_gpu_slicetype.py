@@ -1,0 +1,41 @@
+"""End-to-end parity of the slice-type decisions: raw luma -> x264cu_slicetype_step (CUDA lookahead underneath) versus the
+frame types the reference ENCODER itself outputs for the same pictures (oracle/_ref travels with the snapshot), or, if it
+did not travel, versus the same host logic running on the CPU oracle.  Identical decisions, frame by frame, coded order."""
+import numpy as np
+import pytest
+import x264_b200 as x
+import _libs
+from _libs import have_ref, synth_sequence, slicetype_oracle_lib
+import test_slicetype_host as host
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = x.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("case", host.CASES + [("medium", "weightp=0:no-psy=1:bframes=3:rc-lookahead=20", (640, 360), 48, 23)])
+def test_gpu_frame_types(ctx, case):
+    preset, opts, (w, h), n, cut = case
+    frames = synth_sequence(w, h, n, seed=n + w, cut_at=cut)
+    if cut is not None and n > cut + 9:
+        frames[cut + 7] = np.full_like(frames[0], 235)
+        frames[cut + 8] = np.full_like(frames[0], 235)
+    if not have_ref():
+        pytest.skip("compiled reference did not travel")
+    p, want = host.reference_types(preset, opts, w, h, frames)
+    st = x.Slicetype(ctx, w, h, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
+                     b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy,
+                     frame_reference=p.frame_reference, rc_cqp=0,
+                     subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
+                     bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
+                     aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0)
+    try:
+        got = st.decide(frames)
+    finally:
+        st.close()
+    assert got == want, (case, [z for z in zip(got, want) if z[0] != z[1]][:6])

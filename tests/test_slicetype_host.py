@@ -1,0 +1,88 @@
+"""The host-side slice-type logic (x264_b200/csrc/slicetype.c: decide / analyse / scenecut / trellis path / MB-tree's
+request order / the synchronous frame queue) against the reference ENCODER's own frame-type output, on CPU: the five
+lookahead entry points it calls are served by the oracle here (tests/csrc/slicetype_oracle_glue.c); on the GPU box
+tests/test_gpu_slicetype.py runs the same comparison with the CUDA lookahead underneath."""
+import ctypes as C
+import numpy as np
+import pytest
+import _libs
+from _libs import ref, have_ref, slicetype_oracle_lib, synth_sequence
+from x264_b200.binding_ext import SlicetypeParams, LookaheadParams
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="compiled reference not present")
+
+# (preset, options, (w,h), n_frames, cut_at)
+# Weighted-prediction analysis in the lookahead (x264_weights_analyse, slicetype.c:284-501) is not part of this round:
+# the cases switch it off.  NB "weightp=0" alone is not enough: with mb-tree AND psy the encoder turns it back on as
+# X264_WEIGHTP_FAKE (encoder.c:1316-1317), hence no-psy (or no-mbtree) below.
+CASES = [
+    ("medium", "weightp=0:no-psy=1:bframes=3:rc-lookahead=10:keyint=30:min-keyint=3", (112, 80), 40, 17),
+    ("medium", "weightp=0:no-psy=1:bframes=3:b-adapt=2:rc-lookahead=12:keyint=40", (96, 64), 36, 20),
+    ("medium", "weightp=0:bframes=2:b-adapt=0:no-mbtree=1:rc-lookahead=0:scenecut=0:keyint=12", (64, 48), 30, None),
+    ("medium", "weightp=0:no-psy=1:bframes=4:b-pyramid=none:rc-lookahead=8:subme=1", (80, 64), 30, 9),
+    ("ultrafast", "keyint=20", (64, 48), 45, 21),
+    ("medium", "weightp=0:no-psy=1:bframes=0:rc-lookahead=5:keyint=25", (64, 64), 30, 11),
+    ("slower", "weightp=0:no-psy=1:bframes=3:rc-lookahead=16:keyint=50:me=umh", (96, 80), 30, 13),
+    ("medium", "weightp=0:no-mbtree=1:bframes=3:b-adapt=2:rc-lookahead=20:keyint=60", (128, 96), 48, 25),
+]
+
+
+def params_from_ref(hnd, w, h):
+    r = ref()
+    g = lambda n: r.xref_param(hnd, n.encode())
+    la = LookaheadParams(w, h, g("subme"), min(g("me"), 2), g("merange"), g("mvrange"), g("bframes"), g("b_bias"), g("weightb"),
+                         int(g("aq_mode") != 0), g("mbtree"), g("vbv"), 0)
+    assert g("weightp") == 0, "the case must leave lookahead weightp analysis off"
+    return SlicetypeParams(la, g("keyint_max"), g("keyint_min"), g("scenecut"), g("b_adapt"), g("b_pyramid"), g("lookahead"),
+                           g("psy"), g("ref"), 0)
+
+
+def decide_with(lib, p, frames):
+    lib.x264cu_slicetype_open.argtypes = [C.c_void_p, C.POINTER(SlicetypeParams), C.POINTER(C.c_void_p)]
+    lib.x264cu_slicetype_step.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.x264cu_slicetype_close.argtypes = [C.c_void_p]
+    st = C.c_void_p()
+    assert lib.x264cu_slicetype_open(C.c_void_p(1), C.byref(p), C.byref(st)) == 0
+    out = []
+    fr, ty = C.c_int(), C.c_int()
+    for f in frames:
+        assert lib.x264cu_slicetype_step(st, f.ctypes.data, f.shape[1], None, C.byref(fr), C.byref(ty)) == 0
+        if fr.value >= 0:
+            out.append((fr.value, ty.value))
+    while True:
+        assert lib.x264cu_slicetype_step(st, None, 0, None, C.byref(fr), C.byref(ty)) == 0
+        if fr.value < 0:
+            break
+        out.append((fr.value, ty.value))
+    lib.x264cu_slicetype_close(st)
+    return out
+
+
+def reference_types(preset, opts, w, h, frames):
+    r = ref()
+    r.xref_encode_types.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    hnd = r.xref_open(w, h, preset.encode(), opts.encode(), 0)
+    assert hnd
+    try:
+        p = params_from_ref(hnd, w, h)
+        n = len(frames)
+        luma = np.ascontiguousarray(np.stack(frames))
+        idx = (C.c_int * (n + 8))()
+        typ = (C.c_int * (n + 8))()
+        k = r.xref_encode_types(hnd, luma.ctypes.data, n, idx, typ)
+        assert k == n
+        return p, [(idx[i], typ[i]) for i in range(k)]
+    finally:
+        r.xref_close(hnd)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_frame_types_match_reference_encoder(case):
+    preset, opts, (w, h), n, cut = case
+    frames = synth_sequence(w, h, n, seed=n + w, cut_at=cut)
+    if cut is not None and n > cut + 9:          # a two-frame flash, which must not become a scene cut
+        frames[cut + 7] = np.full_like(frames[0], 235)
+        frames[cut + 8] = np.full_like(frames[0], 235)
+    p, want = reference_types(preset, opts, w, h, frames)
+    got = decide_with(slicetype_oracle_lib(), p, frames)
+    assert got == want, (case, [x for x in zip(got, want) if x[0] != x[1]][:6])

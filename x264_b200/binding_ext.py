@@ -9,8 +9,24 @@ class LookaheadParams(C.Structure):
                                        "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv", "n_slots")]
 
 
+class SlicetypeParams(C.Structure):
+    _fields_ = [("la", LookaheadParams)] + [(n, C.c_int) for n in ("keyint_max", "keyint_min", "scenecut_threshold", "b_adapt",
+                                                                  "b_pyramid", "rc_lookahead", "psy", "frame_reference", "rc_cqp")]
+
+
+TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "BREF", 5: "B"}
+
+
 def bind(L):
     vp, ci, ss = C.c_void_p, C.c_int, C.c_ssize_t
+    L.x264cu_slicetype_open.argtypes = [vp, C.POINTER(SlicetypeParams), C.POINTER(vp)]
+    L.x264cu_slicetype_close.argtypes = [vp]
+    L.x264cu_slicetype_step.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
+    L.x264cu_slicetype_lookahead.argtypes = [vp]
+    L.x264cu_slicetype_lookahead.restype = vp
+    L.x264cu_slicetype_slot_of.argtypes = [vp, ci]
+    L.x264cu_slicetype_cost_requests.argtypes = [vp]
+    L.x264cu_slicetype_cost_requests.restype = C.c_long
     L.x264cu_frame_init_lowres.argtypes = [vp, vp, ss, ci, ci, C.POINTER(vp), ss]
     L.x264cu_hpel_filter.argtypes = [vp, vp, ss, ci, ci, vp, vp, vp, ci]
     L.x264cu_lookahead_open.argtypes = [vp, C.POINTER(LookaheadParams), C.POINTER(vp)]
@@ -108,3 +124,58 @@ class Lookahead:
         out = np.zeros(rows * st.value, np.uint8)
         self.ctx.check(self.L.x264cu_lookahead_get_lowres_plane(self.h, slot, plane, out.ctypes.data, C.byref(st)))
         return out.reshape(rows, st.value)
+
+
+class Slicetype:
+    """x264_lookahead_put_frame / x264_lookahead_get_frames + x264_slicetype_decide on the GPU lookahead.
+    decide(frames) runs a whole sequence the way x264_encoder_encode would and returns [(display_index, type)] in coded order."""
+
+    def __init__(self, ctx, width, height, keyint_max=250, keyint_min=25, scenecut_threshold=40, b_adapt=1, b_pyramid=2,
+                 rc_lookahead=40, psy=1, frame_reference=3, rc_cqp=0, **la_kwargs):
+        self.ctx, self.L = ctx, ctx.L
+        la = dict(subpel_refine=7, me_method=1, me_range=16, mv_range=512, bframes=3, bframe_bias=0, weighted_bipred=1,
+                  aq_mode=1, mb_tree=1, vbv=0, n_slots=0)
+        la.update(la_kwargs)
+        lp = LookaheadParams(width, height, la["subpel_refine"], la["me_method"], la["me_range"], la["mv_range"], la["bframes"],
+                             la["bframe_bias"], la["weighted_bipred"], la["aq_mode"], la["mb_tree"], la["vbv"], la["n_slots"])
+        self.p = SlicetypeParams(lp, keyint_max, keyint_min, scenecut_threshold, b_adapt, b_pyramid, rc_lookahead, psy,
+                                 frame_reference, rc_cqp)
+        h = C.c_void_p()
+        if self.L.x264cu_slicetype_open(ctx.h, C.byref(self.p), C.byref(h)) != 0:
+            from .binding import X264CUError
+            raise X264CUError("x264cu_slicetype_open failed: " + ctx.L.x264cu_strerror(ctx.h).decode())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.x264cu_slicetype_close(self.h)
+            self.h = None
+
+    def step(self, luma=None, inv_qscale=None):
+        fr, ty = C.c_int(), C.c_int()
+        if luma is not None:
+            luma = np.ascontiguousarray(luma, dtype=np.uint8)
+            q = None if inv_qscale is None else np.ascontiguousarray(inv_qscale, dtype=np.uint16)
+            rc = self.L.x264cu_slicetype_step(self.h, luma.ctypes.data, luma.shape[1], q.ctypes.data if q is not None else None,
+                                              C.byref(fr), C.byref(ty))
+        else:
+            rc = self.L.x264cu_slicetype_step(self.h, None, 0, None, C.byref(fr), C.byref(ty))
+        self.ctx.check(rc)
+        return fr.value, ty.value
+
+    def decide(self, frames):
+        out = []
+        for f in frames:
+            fr, ty = self.step(f)
+            if fr >= 0:
+                out.append((fr, ty))
+        while True:
+            fr, ty = self.step(None)
+            if fr < 0:
+                break
+            out.append((fr, ty))
+        return out
+
+    @property
+    def cost_requests(self):
+        return int(self.L.x264cu_slicetype_cost_requests(self.h))

@@ -1,0 +1,654 @@
+/* Host control flow of the slice-type decision (plain C, no device code): a from-scratch restatement of
+ * x264_slicetype_decide / x264_slicetype_analyse / scenecut / slicetype_path / slicetype_path_cost and of the request
+ * sequence of macroblock_tree (encoder/slicetype.c:1091-1184, :1288-1974) plus the synchronous frame queue of
+ * encoder/lookahead.c:192-250, issuing x264cu_lookahead_frame_cost wherever the reference issues
+ * slicetype_frame_cost.  The order of those requests is part of the result (H3 in SURVEY.md): the memoised B costs
+ * depend on whether the later reference's P search had already run (slicetype.c:629-642). */
+#include "../../include/x264_b200.h"
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#define LOOKAHEAD_MAX 250                 /* X264_LOOKAHEAD_MAX, common/base.h:140 */
+#define BFRAME_MAX X264CU_BFRAME_MAX
+#define COST_MAX64 ( 1ULL << 60 )
+
+#define T_AUTO X264CU_TYPE_AUTO
+#define T_IDR X264CU_TYPE_IDR
+#define T_I X264CU_TYPE_I
+#define T_P X264CU_TYPE_P
+#define T_BREF X264CU_TYPE_BREF
+#define T_B X264CU_TYPE_B
+#define IS_I( t ) ( ( t ) == T_I || ( t ) == T_IDR )
+#define IS_B( t ) ( ( t ) == T_B || ( t ) == T_BREF )
+#define AUTO_OR_I( t ) ( ( t ) == T_AUTO || IS_I( t ) )
+#define AUTO_OR_B( t ) ( ( t ) == T_AUTO || IS_B( t ) )
+
+typedef struct
+{
+    int i_frame;          /* display index */
+    int slot;             /* lookahead slot holding its lowres planes */
+    int i_type, i_forced_type;
+    int b_scenecut;       /* frame.c:792 */
+    int i_bframes;
+} st_frame_t;
+
+struct x264cu_slicetype
+{
+    x264cu_ctx_t *ctx;
+    x264cu_lookahead_t *la;
+    x264cu_slicetype_params_t p;
+    int slicetype_length, delay;          /* encoder.c:1602-1612 (one thread, no sync lookahead, cfr) */
+    int b_analyse_keyframe;               /* lookahead.c:140 */
+    int i_last_keyframe;
+    st_frame_t *next[LOOKAHEAD_MAX + 8];  /* lookahead->next */
+    int n_next;
+    st_frame_t *current[BFRAME_MAX + 4];  /* h->frames.current */
+    int n_current;
+    st_frame_t *last_nonb;
+    int i_input;
+    int n_slots;
+    unsigned char *slot_used;
+    long requests;
+    int mb_w, mb_h;
+    int failed;
+};
+
+static int num_mbs( const x264cu_slicetype_t *s )          /* NUM_MBS, slicetype.c:794-797 */
+{
+    return s->mb_w > 2 && s->mb_h > 2 ? ( s->mb_w - 2 ) * ( s->mb_h - 2 ) : s->mb_w * s->mb_h;
+}
+
+/* slicetype_frame_cost( h, a, frames, p0, p1, b ) */
+static int frame_cost( x264cu_slicetype_t *s, st_frame_t **frames, int p0, int p1, int b )
+{
+    int slots[LOOKAHEAD_MAX + 4];
+    for( int i = p0; i <= p1; i++ ) slots[i] = frames[i]->slot;
+    int score = 0;
+    s->requests++;
+    if( x264cu_lookahead_frame_cost( s->la, slots, p0, p1, b, &score ) )
+    {
+        s->failed = 1;
+        return 0;
+    }
+    return score;
+}
+
+static void cost_est( x264cu_slicetype_t *s, st_frame_t *f, int i0, int i1, int *ce, int *imb )
+{
+    int a = 0, aq = 0, m = 0;
+    if( x264cu_lookahead_get_cost_est( s->la, f->slot, i0, i1, &a, &aq, &m ) ) s->failed = 1;
+    if( ce ) *ce = a;
+    if( imb ) *imb = m;
+}
+
+/* slicetype.c:1288-1330 */
+static unsigned long long path_cost( x264cu_slicetype_t *s, st_frame_t **frames, char *path, unsigned long long threshold )
+{
+    unsigned long long cost = 0;
+    int loc = 1, cur_nonb = 0;
+    path--;                                  /* the first path element is really the second frame */
+    while( path[loc] )
+    {
+        int next_nonb = loc;
+        while( path[next_nonb] == 'B' ) next_nonb++;
+        if( path[next_nonb] == 'P' )
+            cost += frame_cost( s, frames, cur_nonb, next_nonb, next_nonb );
+        else
+            cost += frame_cost( s, frames, next_nonb, next_nonb, next_nonb );
+        if( cost > threshold )
+            break;
+        if( s->p.b_pyramid && next_nonb - cur_nonb > 2 )
+        {
+            int middle = cur_nonb + ( next_nonb - cur_nonb ) / 2;
+            cost += frame_cost( s, frames, cur_nonb, next_nonb, middle );
+            for( int next_b = loc; next_b < middle && cost < threshold; next_b++ )
+                cost += frame_cost( s, frames, cur_nonb, middle, next_b );
+            for( int next_b = middle + 1; next_b < next_nonb && cost < threshold; next_b++ )
+                cost += frame_cost( s, frames, middle, next_nonb, next_b );
+        }
+        else
+            for( int next_b = loc; next_b < next_nonb && cost < threshold; next_b++ )
+                cost += frame_cost( s, frames, cur_nonb, next_nonb, next_b );
+        loc = next_nonb + 1;
+        cur_nonb = next_nonb;
+    }
+    return cost;
+}
+
+/* Viterbi step, slicetype.c:1333-1382 */
+static void slicetype_path( x264cu_slicetype_t *s, st_frame_t **frames, int length, char ( *best_paths )[LOOKAHEAD_MAX + 1] )
+{
+    char paths[2][LOOKAHEAD_MAX + 1];
+    int num_paths = s->p.la.bframes + 1 < length ? s->p.la.bframes + 1 : length;
+    unsigned long long best_cost = COST_MAX64;
+    int best_possible = 0, idx = 0;
+    for( int path = 0; path < num_paths; path++ )
+    {
+        int len = length - ( path + 1 );
+        memcpy( paths[idx], best_paths[len % ( BFRAME_MAX + 1 )], len );
+        memset( paths[idx] + len, 'B', path );
+        strcpy( paths[idx] + len + path, "P" );
+        int possible = 1;
+        for( int i = 1; i <= length; i++ )
+        {
+            int t = frames[i]->i_type;
+            if( t == T_AUTO ) continue;
+            if( IS_B( t ) )
+                possible = possible && ( i < len || i == length || paths[idx][i-1] == 'B' );
+            else
+            {
+                possible = possible && ( i < len || paths[idx][i-1] != 'B' );
+                paths[idx][i-1] = IS_I( t ) ? 'I' : 'P';
+            }
+        }
+        if( possible || !best_possible )
+        {
+            if( possible && !best_possible )
+                best_cost = COST_MAX64;
+            unsigned long long cost = path_cost( s, frames, paths[idx], best_cost );
+            if( cost < best_cost )
+            {
+                best_cost = cost;
+                best_possible = possible;
+                idx ^= 1;
+            }
+        }
+    }
+    memcpy( best_paths[length % ( BFRAME_MAX + 1 )], paths[idx ^ 1], length );
+}
+
+/* slicetype.c:1384-1428 */
+static int scenecut_internal( x264cu_slicetype_t *s, st_frame_t **frames, int p0, int p1, int real_scenecut )
+{
+    st_frame_t *frame = frames[p1];
+    (void)real_scenecut;
+    frame_cost( s, frames, p0, p1, p1 );
+    int icost, pcost;
+    cost_est( s, frame, 0, 0, &icost, NULL );
+    cost_est( s, frame, p1 - p0, 0, &pcost, NULL );
+    float f_bias;
+    int i_gop_size = frame->i_frame - s->i_last_keyframe;
+    float f_thresh_max = s->p.scenecut_threshold / 100.0;
+    float f_thresh_min = f_thresh_max * 0.25;
+    if( s->p.keyint_min == s->p.keyint_max )
+        f_thresh_min = f_thresh_max;
+    if( i_gop_size <= s->p.keyint_min / 4 )
+        f_bias = f_thresh_min / 4;
+    else if( i_gop_size <= s->p.keyint_min )
+        f_bias = f_thresh_min * i_gop_size / s->p.keyint_min;
+    else
+        f_bias = f_thresh_min + ( f_thresh_max - f_thresh_min ) * ( i_gop_size - s->p.keyint_min )
+                 / ( s->p.keyint_max - s->p.keyint_min );
+    return pcost >= ( 1.0 - f_bias ) * icost;
+}
+
+/* slicetype.c:1430-1468 */
+static int scenecut( x264cu_slicetype_t *s, st_frame_t **frames, int p0, int p1, int real_scenecut, int num_frames, int i_max_search )
+{
+    if( real_scenecut && s->p.la.bframes )
+    {
+        int origmaxp1 = p0 + 1;
+        if( s->p.b_adapt == 2 )
+            origmaxp1 += s->p.la.bframes;
+        else
+            origmaxp1++;
+        int maxp1 = origmaxp1 < num_frames ? origmaxp1 : num_frames;
+        for( int curp1 = p1; curp1 <= maxp1; curp1++ )
+            if( !scenecut_internal( s, frames, p0, curp1, 0 ) )
+                for( int i = curp1; i > p0; i-- )
+                    frames[i]->b_scenecut = 0;
+        for( int curp0 = p0; curp0 <= maxp1; curp0++ )
+            if( origmaxp1 > i_max_search || ( curp0 < maxp1 && scenecut_internal( s, frames, curp0, maxp1, 0 ) ) )
+                frames[curp0]->b_scenecut = 0;
+    }
+    if( !frames[p1]->b_scenecut )
+        return 0;
+    return scenecut_internal( s, frames, p0, p1, real_scenecut );
+}
+
+/* the slicetype_frame_cost requests of macroblock_tree, slicetype.c:1091-1184 (the propagation itself is not part
+ * of this backend; only its requests matter for later memoised costs) */
+static void mbtree_requests( x264cu_slicetype_t *s, st_frame_t **frames, int num_frames, int b_intra )
+{
+    int idx = !b_intra;
+    int last_nonb, cur_nonb = 1, bframes = 0;
+    int i = num_frames;
+    if( b_intra )
+        frame_cost( s, frames, 0, 0, 0 );
+    while( i > 0 && IS_B( frames[i]->i_type ) ) i--;
+    last_nonb = i;
+    if( !s->p.rc_lookahead )
+    {
+        if( b_intra ) return;
+    }
+    else if( last_nonb < idx )
+        return;
+    while( i-- > idx )
+    {
+        cur_nonb = i;
+        while( IS_B( frames[cur_nonb]->i_type ) && cur_nonb > 0 ) cur_nonb--;
+        if( cur_nonb < idx )
+            break;
+        frame_cost( s, frames, cur_nonb, last_nonb, last_nonb );
+        bframes = last_nonb - cur_nonb - 1;
+        if( s->p.b_pyramid && bframes > 1 )
+        {
+            int middle = ( bframes + 1 ) / 2 + cur_nonb;
+            frame_cost( s, frames, cur_nonb, last_nonb, middle );
+            while( i > cur_nonb )
+            {
+                int p0 = i > middle ? middle : cur_nonb;
+                int p1 = i < middle ? middle : last_nonb;
+                if( i != middle )
+                    frame_cost( s, frames, p0, p1, i );
+                i--;
+            }
+        }
+        else
+            while( i > cur_nonb )
+            {
+                frame_cost( s, frames, cur_nonb, last_nonb, i );
+                i--;
+            }
+        last_nonb = cur_nonb;
+    }
+    if( !s->p.rc_lookahead )
+        frame_cost( s, frames, 0, last_nonb, last_nonb );
+}
+
+/* x264_slicetype_analyse, slicetype.c:1473-1743 */
+static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
+{
+    st_frame_t *frames[LOOKAHEAD_MAX + 3] = { NULL };
+    int num_frames, orig_num_frames, keyint_limit, framecnt;
+    int i_max_search = s->n_next < LOOKAHEAD_MAX ? s->n_next : LOOKAHEAD_MAX;
+    const int bf = s->p.la.bframes;
+    /* b_deterministic */
+    if( i_max_search > s->slicetype_length + 1 - intra_minigop )
+        i_max_search = s->slicetype_length + 1 - intra_minigop;
+    int keyframe = !!intra_minigop;
+    if( !s->last_nonb )
+        return;
+    frames[0] = s->last_nonb;
+    for( framecnt = 0; framecnt < i_max_search; framecnt++ )
+        frames[framecnt + 1] = s->next[framecnt];
+    if( !framecnt )
+    {
+        if( s->p.la.mb_tree )
+            mbtree_requests( s, frames, 0, keyframe );
+        return;
+    }
+    keyint_limit = s->p.keyint_max - frames[0]->i_frame + s->i_last_keyframe - 1;
+    orig_num_frames = num_frames = framecnt < keyint_limit ? framecnt : keyint_limit;
+    if( s->p.psy && s->p.la.mb_tree )
+        num_frames = framecnt;
+    else if( num_frames == 0 )
+    {
+        frames[1]->i_type = T_I;
+        return;
+    }
+    if( AUTO_OR_I( frames[1]->i_type ) && s->p.scenecut_threshold &&
+        scenecut( s, frames, 0, 1, 1, orig_num_frames, i_max_search ) )
+    {
+        if( frames[1]->i_type == T_AUTO )
+            frames[1]->i_type = T_I;
+        return;
+    }
+    /* Close GOP at IDR-frames */
+    for( int j = 2; j <= num_frames; j++ )
+        if( frames[j]->i_type == T_IDR && AUTO_OR_B( frames[j-1]->i_type ) )
+            frames[j-1]->i_type = T_P;
+
+    int num_analysed_frames = num_frames;
+    int reset_start;
+    if( bf )
+    {
+        if( s->p.b_adapt == 2 )
+        {
+            if( num_frames > 1 )
+            {
+                static char best_paths[BFRAME_MAX + 1][LOOKAHEAD_MAX + 1];
+                memset( best_paths, 0, sizeof( best_paths ) );
+                strcpy( best_paths[1], "P" );
+                int best_path_index = num_frames % ( BFRAME_MAX + 1 );
+                for( int j = 2; j <= num_frames; j++ )
+                    slicetype_path( s, frames, j, best_paths );
+                for( int j = 1; j < num_frames; j++ )
+                {
+                    if( best_paths[best_path_index][j-1] != 'B' )
+                    {
+                        if( AUTO_OR_B( frames[j]->i_type ) )
+                            frames[j]->i_type = T_P;
+                    }
+                    else if( frames[j]->i_type == T_AUTO )
+                        frames[j]->i_type = T_B;
+                }
+            }
+        }
+        else if( s->p.b_adapt == 1 )
+        {
+            int last_nonb = 0, num_bframes = bf;
+            char path[LOOKAHEAD_MAX + 1];
+            for( int j = 1; j < num_frames; j++ )
+            {
+                if( j - 1 > 0 && IS_B( frames[j-1]->i_type ) )
+                    num_bframes--;
+                else
+                {
+                    last_nonb = j - 1;
+                    num_bframes = bf;
+                }
+                if( !num_bframes )
+                {
+                    if( AUTO_OR_B( frames[j]->i_type ) )
+                        frames[j]->i_type = T_P;
+                    continue;
+                }
+                if( frames[j]->i_type != T_AUTO )
+                    continue;
+                if( IS_B( frames[j+1]->i_type ) )
+                {
+                    frames[j]->i_type = T_P;
+                    continue;
+                }
+                int bframes = j - last_nonb - 1;
+                memset( path, 'B', bframes );
+                strcpy( path + bframes, "PP" );
+                unsigned long long cost_p = path_cost( s, frames + last_nonb, path, COST_MAX64 );
+                strcpy( path + bframes, "BP" );
+                unsigned long long cost_b = path_cost( s, frames + last_nonb, path, cost_p );
+                frames[j]->i_type = cost_b < cost_p ? T_B : T_P;
+            }
+        }
+        else
+        {
+            int num_bframes = bf;
+            for( int j = 1; j < num_frames; j++ )
+            {
+                if( !num_bframes )
+                {
+                    if( AUTO_OR_B( frames[j]->i_type ) )
+                        frames[j]->i_type = T_P;
+                }
+                else if( frames[j]->i_type == T_AUTO )
+                    frames[j]->i_type = IS_B( frames[j+1]->i_type ) ? T_P : T_B;
+                if( IS_B( frames[j]->i_type ) )
+                    num_bframes--;
+                else
+                    num_bframes = bf;
+            }
+        }
+        if( AUTO_OR_B( frames[num_frames]->i_type ) )
+            frames[num_frames]->i_type = T_P;
+
+        int num_bframes = 0;
+        while( num_bframes < num_frames && IS_B( frames[num_bframes + 1]->i_type ) )
+            num_bframes++;
+        /* Check scenecut on the first minigop. */
+        for( int j = 1; j < num_bframes + 1; j++ )
+            if( frames[j]->i_forced_type == T_AUTO && AUTO_OR_I( frames[j+1]->i_forced_type ) &&
+                s->p.scenecut_threshold && scenecut( s, frames, j, j + 1, 0, orig_num_frames, i_max_search ) )
+            {
+                frames[j]->i_type = T_P;
+                num_analysed_frames = j;
+                break;
+            }
+        reset_start = keyframe ? 1 : ( num_bframes + 2 < num_analysed_frames + 1 ? num_bframes + 2 : num_analysed_frames + 1 );
+    }
+    else
+    {
+        for( int j = 1; j <= num_frames; j++ )
+            if( AUTO_OR_B( frames[j]->i_type ) )
+                frames[j]->i_type = T_P;
+        reset_start = !keyframe + 1;
+    }
+
+    if( s->p.la.mb_tree )
+        mbtree_requests( s, frames, num_frames < s->p.keyint_max ? num_frames : s->p.keyint_max, keyframe );
+
+    /* Enforce keyframe limit. */
+    {
+        int last_keyframe = s->i_last_keyframe, last_possible = 0;
+        for( int j = 1; j <= num_frames; j++ )
+        {
+            st_frame_t *frm = frames[j];
+            int keyframe_dist = frm->i_frame - last_keyframe;
+            if( AUTO_OR_I( frm->i_forced_type ) )
+                if( !IS_B( frames[j-1]->i_forced_type ) )
+                    last_possible = j;
+            if( keyframe_dist >= s->p.keyint_max )
+            {
+                if( last_possible != 0 && last_possible != j )
+                {
+                    j = last_possible;
+                    frm = frames[j];
+                    keyframe_dist = frm->i_frame - last_keyframe;
+                }
+                last_possible = 0;
+                if( frm->i_type != T_IDR )
+                    frm->i_type = T_IDR;
+            }
+            if( frm->i_type == T_I && keyframe_dist >= s->p.keyint_min )
+                if( frm->i_forced_type != T_I )
+                    frm->i_type = T_IDR;
+            if( frm->i_type == T_IDR )
+            {
+                last_keyframe = frm->i_frame;
+                if( j > 1 && IS_B( frames[j-1]->i_type ) )
+                    frames[j-1]->i_type = T_P;
+            }
+        }
+    }
+    /* Restore frametypes for all frames that haven't actually been decided yet. */
+    for( int j = reset_start; j <= num_frames; j++ )
+        frames[j]->i_type = frames[j]->i_forced_type;
+}
+
+/* x264_slicetype_decide, slicetype.c:1745-1974 (type decision + the rate-control cost requests) */
+static int slicetype_decide( x264cu_slicetype_t *s )
+{
+    st_frame_t *frames[BFRAME_MAX + 2];
+    st_frame_t *frm;
+    int bframes, brefs;
+    if( !s->n_next )
+        return 0;
+    if( ( s->p.la.bframes && s->p.b_adapt ) || s->p.scenecut_threshold || s->p.la.mb_tree )
+        slicetype_analyse( s, 0 );
+
+    for( bframes = 0, brefs = 0;; bframes++ )
+    {
+        frm = s->next[bframes];
+        if( frm->i_type == T_BREF && s->p.b_pyramid < 2 && brefs == s->p.b_pyramid )
+            frm->i_type = T_B;
+        else if( frm->i_type == T_BREF && s->p.b_pyramid == 2 && brefs && s->p.frame_reference <= ( brefs + 3 ) )
+            frm->i_type = T_B;
+        /* Limit GOP size */
+        if( frm->i_frame - s->i_last_keyframe >= s->p.keyint_max )
+        {
+            if( frm->i_type == T_AUTO || frm->i_type == T_I )
+                frm->i_type = T_IDR;
+            if( frm->i_type != T_IDR )
+                frm->i_type = T_IDR;
+        }
+        if( frm->i_type == T_I && frm->i_frame - s->i_last_keyframe >= s->p.keyint_min )
+            frm->i_type = T_IDR;
+        if( frm->i_type == T_IDR )
+        {
+            s->i_last_keyframe = frm->i_frame;
+            if( bframes > 0 )
+            {
+                bframes--;
+                s->next[bframes]->i_type = T_P;
+            }
+        }
+        if( bframes == s->p.la.bframes || bframes + 1 >= s->n_next )
+        {
+            if( frm->i_type == T_AUTO || IS_B( frm->i_type ) )
+                frm->i_type = T_P;
+        }
+        if( frm->i_type == T_BREF )
+            brefs++;
+        if( frm->i_type == T_AUTO )
+            frm->i_type = T_B;
+        else if( !IS_B( frm->i_type ) )
+            break;
+    }
+    s->next[bframes]->i_bframes = bframes;
+    /* insert a bref into the sequence */
+    if( s->p.b_pyramid && bframes > 1 && !brefs )
+    {
+        s->next[( bframes - 1 ) / 2]->i_type = T_BREF;
+        brefs++;
+    }
+    /* frame costs ahead of time for x264_rc_analyse_slice */
+    if( !s->p.rc_cqp )
+    {
+        int p0, p1, b;
+        p1 = b = bframes + 1;
+        frames[0] = s->last_nonb;
+        memcpy( &frames[1], s->next, ( bframes + 1 ) * sizeof( st_frame_t * ) );
+        p0 = IS_I( s->next[bframes]->i_type ) ? bframes + 1 : 0;
+        frame_cost( s, frames, p0, p1, b );
+    }
+    /* shift sequence to coded order */
+    if( bframes )
+    {
+        int idx_list[2] = { brefs + 1, 1 };
+        for( int i = 0; i < bframes; i++ )
+        {
+            int idx = idx_list[s->next[i]->i_type == T_BREF]++;
+            frames[idx] = s->next[i];
+        }
+        frames[0] = s->next[bframes];
+        memcpy( s->next, frames, ( bframes + 1 ) * sizeof( st_frame_t * ) );
+    }
+    return bframes;
+}
+
+static void release_frame( x264cu_slicetype_t *s, st_frame_t *f )
+{
+    if( !f ) return;
+    s->slot_used[f->slot] = 0;
+    free( f );
+}
+
+/* x264_lookahead_get_frames without a lookahead thread, lookahead.c:223-250 */
+static void lookahead_get_frames( x264cu_slicetype_t *s )
+{
+    if( s->n_current || !s->n_next )
+        return;
+    slicetype_decide( s );
+    /* lookahead_update_last_nonb */
+    st_frame_t *new_nonb = s->next[0];
+    int shift_frames = new_nonb->i_bframes + 1;
+    st_frame_t *old = s->last_nonb;
+    s->last_nonb = new_nonb;
+    /* the frames leave `next` for the encoder; last_nonb stays referenced until it is replaced */
+    for( int i = 0; i < shift_frames; i++ )
+        s->current[s->n_current++] = s->next[i];
+    memmove( s->next, s->next + shift_frames, ( s->n_next - shift_frames ) * sizeof( st_frame_t * ) );
+    s->n_next -= shift_frames;
+    s->next[s->n_next] = NULL;
+    if( old )
+    {   /* released unless the encoder side still holds it (it never does: frames are handed out by value) */
+        int held = 0;
+        for( int i = 0; i < s->n_current; i++ ) held |= s->current[i] == old;
+        if( !held ) release_frame( s, old );
+    }
+    if( s->b_analyse_keyframe && IS_I( s->last_nonb->i_type ) )
+        slicetype_analyse( s, shift_frames );
+}
+
+int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p, x264cu_slicetype_t **out )
+{
+    if( !ctx || !p || !out ) return -1;
+    *out = NULL;
+    if( p->la.vbv || p->keyint_max < 1 || p->keyint_min < 1 || p->b_adapt < 0 || p->b_adapt > 2 || p->b_pyramid < 0 || p->b_pyramid > 2 )
+        return -1;
+    x264cu_slicetype_t *s = calloc( 1, sizeof( *s ) );
+    if( !s ) return -1;
+    s->ctx = ctx;
+    s->p = *p;
+    /* encoder.c:1602-1609 */
+    s->delay = p->b_adapt == 2 ? ( p->la.bframes > 3 ? p->la.bframes : 3 ) * 4 : p->la.bframes;
+    if( p->la.mb_tree && p->rc_lookahead > s->delay )
+        s->delay = p->rc_lookahead;
+    s->slicetype_length = s->delay;
+    s->b_analyse_keyframe = p->la.mb_tree != 0;
+    s->i_last_keyframe = -p->keyint_max;
+    s->n_slots = s->delay + p->la.bframes + 8;
+    s->slot_used = calloc( s->n_slots, 1 );
+    s->p.la.n_slots = s->n_slots;
+    s->mb_w = ( p->la.width + 15 ) >> 4;
+    s->mb_h = ( p->la.height + 15 ) >> 4;
+    if( !s->slot_used || x264cu_lookahead_open( ctx, &s->p.la, &s->la ) )
+    {
+        free( s->slot_used );
+        free( s );
+        return -1;
+    }
+    *out = s;
+    return 0;
+}
+
+void x264cu_slicetype_close( x264cu_slicetype_t *s )
+{
+    if( !s ) return;
+    for( int i = 0; i < s->n_next; i++ ) free( s->next[i] );
+    for( int i = 0; i < s->n_current; i++ ) if( s->current[i] != s->last_nonb ) free( s->current[i] );
+    free( s->last_nonb );
+    x264cu_lookahead_close( s->la );
+    free( s->slot_used );
+    free( s );
+}
+
+int x264cu_slicetype_step( x264cu_slicetype_t *s, const uint8_t *h_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
+                           int *out_frame, int *out_type )
+{
+    if( !s || !out_frame || !out_type ) return -1;
+    *out_frame = -1; *out_type = T_AUTO;
+    if( h_luma )
+    {
+        int slot = -1;
+        for( int i = 0; i < s->n_slots; i++ )
+            if( !s->slot_used[i] ) { slot = i; break; }
+        if( slot < 0 || s->n_next >= LOOKAHEAD_MAX + 4 ) return -1;
+        if( x264cu_lookahead_frame_put( s->la, slot, h_luma, luma_stride, h_inv_qscale ) ) return -1;
+        st_frame_t *f = calloc( 1, sizeof( *f ) );
+        if( !f ) return -1;
+        f->i_frame = s->i_input++;
+        f->slot = slot;
+        f->b_scenecut = 1;
+        s->slot_used[slot] = 1;
+        s->next[s->n_next++] = f;
+        s->next[s->n_next] = NULL;
+        if( s->i_input <= s->delay )               /* encoder.c:3428: nothing to encode yet */
+            return 0;
+    }
+    lookahead_get_frames( s );
+    if( s->failed ) return -1;
+    if( !s->n_current )
+        return 0;
+    st_frame_t *f = s->current[0];
+    memmove( s->current, s->current + 1, ( s->n_current - 1 ) * sizeof( st_frame_t * ) );
+    s->n_current--;
+    *out_frame = f->i_frame;
+    *out_type = f->i_type;
+    if( f != s->last_nonb )
+        release_frame( s, f );
+    return 0;
+}
+
+x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *s ) { return s ? s->la : NULL; }
+
+int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame )
+{
+    if( !s ) return -1;
+    if( s->last_nonb && s->last_nonb->i_frame == frame ) return s->last_nonb->slot;
+    for( int i = 0; i < s->n_next; i++ ) if( s->next[i]->i_frame == frame ) return s->next[i]->slot;
+    for( int i = 0; i < s->n_current; i++ ) if( s->current[i]->i_frame == frame ) return s->current[i]->slot;
+    return -1;
+}
+
+long x264cu_slicetype_cost_requests( x264cu_slicetype_t *s ) { return s ? s->requests : 0; }
