@@ -242,6 +242,13 @@ void x264cu_slicetype_close( x264cu_slicetype_t *st );
  * Returns 0, or -1 on error.  While flushing, *out_frame == -1 means the stream is drained. */
 int  x264cu_slicetype_step( x264cu_slicetype_t *st, const uint8_t *h_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
                             int *out_frame, int *out_type );
+/* same with the picture already in HBM (8-byte aligned base and stride) */
+int  x264cu_slicetype_step_device( x264cu_slicetype_t *st, const uint8_t *d_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
+                                   int *out_frame, int *out_type );
+/* prefetch = 1 (default): when a picture is queued, its lowres searches against the previous bframes+1 pictures are
+ * launched at once on a second stream (the x264_opencl_slicetype_prep idea, encoder/slicetype-cl.c:653); 0: every search
+ * runs on demand inside the cost request that needs it.  The decisions are identical either way. */
+void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *st, int prefetch );
 /* the lookahead object underneath (for reading per-MB results) and the slot a display index currently occupies (-1 if gone) */
 x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *st );
 int  x264cu_slicetype_slot_of( x264cu_slicetype_t *st, int frame );

@@ -316,7 +316,8 @@ typedef struct
 {
     x264_t *h;
     int n;
-    x264_frame_t **frames;
+    x264_frame_t **frames;        /* the frames[] array handed to slicetype_frame_cost */
+    x264_frame_t **slots;         /* when used through xref_la_remap: slot -> frame, frames[] is rebuilt per request */
     x264_mb_analysis_t a;
 } xref_la_t;
 
@@ -326,6 +327,7 @@ XREF_API void *xref_la_new( void *hv, int n )
     xref_la_t *la = calloc( 1, sizeof(*la) );
     la->h = h; la->n = n;
     la->frames = calloc( n + 2, sizeof(x264_frame_t*) );
+    la->slots = la->frames;
     lowres_context_init( h, &la->a );                    /* slicetype.c:45-61 */
     return la;
 }
@@ -335,10 +337,10 @@ XREF_API int xref_la_set_frame( void *lav, int idx, const uint8_t *luma, intptr_
 {
     xref_la_t *la = lav;
     x264_t *h = la->h;
-    x264_frame_t *f = la->frames[idx];
+    x264_frame_t *f = la->slots[idx];
     if( !f )
     {
-        f = la->frames[idx] = x264_frame_pop_unused( h, 0 );
+        f = la->slots[idx] = x264_frame_pop_unused( h, 0 );
         if( !f ) return -1;
     }
     for( int y = 0; y < h->param.i_height; y++ )
@@ -372,7 +374,7 @@ XREF_API void xref_la_get( void *lav, int idx, int what, int i, int j, void *out
 {
     xref_la_t *la = lav;
     x264_t *h = la->h;
-    x264_frame_t *f = la->frames[idx];
+    x264_frame_t *f = idx >= 300 ? la->slots[idx-300] : la->frames[idx];      /* >= 300: address by slot (xref_la_remap users) */
     int n = h->mb.i_mb_count;
     switch( what )
     {
@@ -394,9 +396,23 @@ XREF_API void xref_la_get_lowres( void *lav, int idx, int plane, uint8_t *out )
         memcpy( out + y*st, f->lowres[plane] + (y-PADV)*st - PADH, f->i_width_lowres + 2*PADH );
 }
 
+/* slot-addressed use (bench / slicetype glue): frames[i] = slot table[frames_in[i]] for i in p0..p1 */
+XREF_API void xref_la_remap( void *lav, const int *frames_in, int p0, int p1 )
+{
+    xref_la_t *la = lav;
+    if( la->slots == la->frames )
+    {
+        la->slots = calloc( la->n + 2, sizeof(x264_frame_t*) );
+        memcpy( la->slots, la->frames, ( la->n + 2 ) * sizeof(x264_frame_t*) );
+        la->frames = calloc( 512, sizeof(x264_frame_t*) );
+    }
+    for( int i = p0; i <= p1; i++ ) la->frames[i] = la->slots[frames_in[i]];
+}
+
 XREF_API void xref_la_free( void *lav )
 {
     xref_la_t *la = lav;
+    if( la->slots != la->frames ) { free( la->frames ); la->frames = la->slots; }
     /* deleted, not pushed back: the encoder's unused-frame list has a fixed capacity (encoder.c frames.unused) */
     for( int i = 0; i < la->n; i++ )
         if( la->frames[i] ) x264_frame_delete( la->frames[i] );

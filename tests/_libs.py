@@ -275,3 +275,23 @@ def slicetype_oracle_lib():
         from x264_b200.binding_ext import bind
         _st_oracle = L
     return _st_oracle
+
+
+_st_ref = None
+
+
+def slicetype_ref_lib():
+    """host slice-type logic linked against the compiled reference's own slicetype_frame_cost (bench.py's CPU arm)"""
+    global _st_ref
+    if _st_ref is None:
+        out_dir = os.path.join(ROOT, "tests", "_build")
+        os.makedirs(out_dir, exist_ok=True)
+        so = os.path.join(out_dir, "libslicetype_ref.so")
+        srcs = [os.path.join(ROOT, "x264_b200", "csrc", "slicetype.c"), os.path.join(ROOT, "tests", "csrc", "slicetype_ref_glue.c")]
+        deps = srcs + [REF_SO, os.path.join(ROOT, "include", "x264_b200.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=gnu99", "-o", so] + srcs +
+                                  ["-L" + os.path.dirname(REF_SO), "-lx264ref", "-Wl,-rpath," + os.path.dirname(REF_SO), "-lm"])
+        _st_ref = C.CDLL(so)
+        _st_ref.slicetype_ref_glue_config.argtypes = [C.c_char_p, C.c_char_p]
+    return _st_ref

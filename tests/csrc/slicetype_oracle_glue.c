@@ -69,3 +69,16 @@ int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int i0, int
     if( imb ) *imb = f->intra_mbs[i0];
     return 0;
 }
+
+int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const uint8_t *d, intptr_t st, const uint16_t *q )
+{
+    (void)la; (void)slot; (void)d; (void)st; (void)q;
+    return -1;          /* no device in the CPU harness */
+}
+
+/* prefetching is a pure scheduling hint: the oracle computes every search on demand */
+int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n, const int *fenc, const int *ref, const int *list, const int *dist )
+{
+    (void)la; (void)n; (void)fenc; (void)ref; (void)list; (void)dist;
+    return 0;
+}

@@ -1,0 +1,69 @@
+/* TEST / BENCH INFRASTRUCTURE: the product's host-side slice-type logic (x264_b200/csrc/slicetype.c) driving the UNMODIFIED
+ * reference's own slicetype_frame_cost (through oracle/_ref/libx264ref.so) instead of the GPU lookahead.  This is the CPU
+ * arm of bench.py's lookahead workload: identical decision workload, reference cost function, host cores. */
+#include "../../include/x264_b200.h"
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+void *xref_open( int width, int height, const char *preset, const char *opts, int verbose );
+void  xref_close( void *h );
+void *xref_la_new( void *h, int n );
+int   xref_la_set_frame( void *la, int idx, const uint8_t *luma, intptr_t stride, const uint16_t *q );
+int   xref_la_frame_cost( void *la, int p0, int p1, int b );
+void  xref_la_get( void *la, int idx, int what, int i, int j, void *out );
+void  xref_la_free( void *la );
+void  xref_la_remap( void *la, const int *frames, int p0, int p1 );
+
+struct x264cu_lookahead { void *h, *la; int n_slots; };
+
+static const char *g_preset = "medium";
+static const char *g_opts = "";
+void slicetype_ref_glue_config( const char *preset, const char *opts ) { g_preset = preset; g_opts = opts; }
+
+int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *q, x264cu_lookahead_t **out )
+{
+    (void)ctx;
+    x264cu_lookahead_t *la = calloc( 1, sizeof( *la ) );
+    la->h = xref_open( q->width, q->height, g_preset, g_opts, 0 );
+    if( !la->h ) { free( la ); return -1; }
+    la->n_slots = q->n_slots;
+    la->la = xref_la_new( la->h, q->n_slots + 300 );
+    *out = la;
+    return 0;
+}
+void x264cu_lookahead_close( x264cu_lookahead_t *la )
+{
+    if( !la ) return;
+    xref_la_free( la->la );
+    xref_close( la->h );
+    free( la );
+}
+int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t stride, const uint16_t *q )
+{
+    return xref_la_set_frame( la->la, slot, h_luma, stride, q );
+}
+int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const uint8_t *d, intptr_t st, const uint16_t *q )
+{
+    (void)la; (void)slot; (void)d; (void)st; (void)q; return -1;
+}
+int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n, const int *a, const int *b, const int *c, const int *d )
+{
+    (void)la; (void)n; (void)a; (void)b; (void)c; (void)d; return 0;
+}
+int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
+{
+    /* the reference takes a frames[] array of frame pointers: map indices p0..p1 to the slots' frames */
+    xref_la_remap( la->la, frames, p0, p1 );
+    *score = xref_la_frame_cost( la->la, p0, p1, b );
+    return 0;
+}
+int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int i0, int i1, int *ce, int *ceaq, int *imb )
+{
+    int e[3];
+    xref_la_get( la->la, slot + 300, 4, i0, i1, e );      /* +300: slot table (see ref_shim.c xref_la_get) */
+    if( ce ) *ce = e[0];
+    if( ceaq ) *ceaq = e[1];
+    if( imb ) *imb = e[2];
+    return 0;
+}

@@ -22,6 +22,8 @@ def bind(L):
     L.x264cu_slicetype_open.argtypes = [vp, C.POINTER(SlicetypeParams), C.POINTER(vp)]
     L.x264cu_slicetype_close.argtypes = [vp]
     L.x264cu_slicetype_step.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
+    L.x264cu_slicetype_step_device.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
+    L.x264cu_slicetype_set_prefetch.argtypes = [vp, ci]
     L.x264cu_slicetype_lookahead.argtypes = [vp]
     L.x264cu_slicetype_lookahead.restype = vp
     L.x264cu_slicetype_slot_of.argtypes = [vp, ci]
@@ -162,6 +164,14 @@ class Slicetype:
             rc = self.L.x264cu_slicetype_step(self.h, None, 0, None, C.byref(fr), C.byref(ty))
         self.ctx.check(rc)
         return fr.value, ty.value
+
+    def step_device(self, d_luma, stride):
+        fr, ty = C.c_int(), C.c_int()
+        self.ctx.check(self.L.x264cu_slicetype_step_device(self.h, int(d_luma), stride, None, C.byref(fr), C.byref(ty)))
+        return fr.value, ty.value
+
+    def set_prefetch(self, on):
+        self.L.x264cu_slicetype_set_prefetch(self.h, int(on))
 
     def decide(self, frames):
         out = []

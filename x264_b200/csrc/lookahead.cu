@@ -55,6 +55,9 @@ struct LaSearchJob
     int32_t *progress;               // [mb_h], preset to mb_w (nothing done)
 };
 
+#define LA_PACK 48
+struct LaJobPack { LaSearchJob j[LA_PACK]; };     // passed by value as a kernel parameter: no staging copy, no sync
+
 struct LaFinalizeArgs
 {
     const uint8_t *fenc;
@@ -219,14 +222,14 @@ intra_kernel( LaDims d, const uint8_t *__restrict__ plane, int32_t *__restrict__
 // ------------------------------------------------------------------------------------------------
 template <int NW>
 __global__ void __launch_bounds__( NW * 32 )
-search_kernel( LaDims d, const LaSearchJob *__restrict__ jobs, const uint16_t *__restrict__ cost_mv_g )
+search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uint16_t *__restrict__ cost_mv_g )
 {
     extern __shared__ uint16_t s_cost[];
     for( int i = threadIdx.x; i < 2 * d.cost_len + 1; i += blockDim.x ) s_cost[i] = cost_mv_g[i];
     __syncthreads();
     const uint16_t *cost_mv = s_cost + d.cost_len;
 
-    const LaSearchJob job = jobs[blockIdx.y];
+    const LaSearchJob &job = jobs.j[blockIdx.y];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int start_y = min( d.mb_h - 1, d.mb_h - 2 + d.do_edges ), end_y = max( 0, 1 - d.do_edges );
     const int start_x = d.mb_w - 2 + d.do_edges, end_x = 1 - d.do_edges;
@@ -495,6 +498,7 @@ struct LaSlotHost
     int intra_mbs[LA_MAX_B + 2];
     bool row_satds_valid[LA_MAX_B + 2][LA_MAX_B + 2];
     bool searched[2][LA_MAX_B + 1];  // the 0x7FFF sentinel of lowres_mvs[l][d][0][0], kept on the host
+    int pending[2][LA_MAX_B + 1];    // event index of a prefetched search still in flight on the search stream, or -1
 };
 
 struct x264cu_lookahead
@@ -510,8 +514,12 @@ struct x264cu_lookahead
     size_t luma_bytes = 0;
     uint8_t *h_luma = nullptr;       // pinned staging
     int32_t *d_record = nullptr, *h_record = nullptr;
-    LaSearchJob *d_jobs = nullptr, *h_jobs = nullptr;
-    int max_jobs = 0;
+    LaJobPack pack;                  // jobs being assembled for the next launch
+    cudaStream_t search_stream = nullptr;
+    cudaEvent_t ev[64];
+    int ev_next = 0, n_ev = 0;
+    cudaEvent_t ev_main = nullptr;
+    int last_prefetch_ev = -1;
     uint16_t *h_qscale = nullptr;
 };
 
@@ -536,8 +544,11 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
         cudaFree( s.plane_buf ); cudaFree( s.dev.mvs ); cudaFree( s.dev.mv_costs ); cudaFree( s.dev.costs );
         cudaFree( s.dev.intra ); cudaFree( s.dev.qscale ); cudaFree( s.dev.row_satds ); cudaFree( s.dev.progress );
     }
-    cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record ); cudaFree( la->d_jobs );
-    cudaFreeHost( la->h_luma ); cudaFreeHost( la->h_record ); cudaFreeHost( la->h_jobs ); cudaFreeHost( la->h_qscale );
+    cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record );
+    cudaFreeHost( la->h_luma ); cudaFreeHost( la->h_record ); cudaFreeHost( la->h_qscale );
+    if( la->search_stream ) { cudaStreamSynchronize( la->search_stream ); cudaStreamDestroy( la->search_stream ); }
+    for( int i = 0; i < la->n_ev; i++ ) cudaEventDestroy( la->ev[i] );
+    if( la->ev_main ) cudaEventDestroy( la->ev_main );
     delete la;
 }
 
@@ -593,11 +604,14 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     alloc( (void **)&la->d_luma, la->luma_bytes );
     alloc( (void **)&la->d_cost_mv, ( 2 * d.cost_len + 1 ) * 2 + 16 );
     alloc( (void **)&la->d_record, 64 );
-    la->max_jobs = 4096;
-    alloc( (void **)&la->d_jobs, la->max_jobs * sizeof( LaSearchJob ) );
+    if( cudaStreamCreateWithFlags( &la->search_stream, cudaStreamNonBlocking ) != cudaSuccess ) ok = false;
+    for( int i = 0; ok && i < 64; i++ )
+    {
+        if( cudaEventCreateWithFlags( &la->ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false; else la->n_ev++;
+    }
+    if( ok && cudaEventCreateWithFlags( &la->ev_main, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_luma, la->luma_bytes ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_record, 64 ) != cudaSuccess ) ok = false;
-    if( ok && cudaMallocHost( (void **)&la->h_jobs, la->max_jobs * sizeof( LaSearchJob ) ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_qscale, d.mb_count * 2 ) != cudaSuccess ) ok = false;
     if( !ok )
     {
@@ -637,6 +651,7 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
     memset( s.intra_mbs, 0, sizeof( s.intra_mbs ) );
     memset( s.row_satds_valid, 0, sizeof( s.row_satds_valid ) );
     memset( s.searched, 0, sizeof( s.searched ) );
+    memset( s.pending, -1, sizeof( s.pending ) );
     s.b_intra_calculated = 0;
     s.intra_on_device = false;
     s.in_use = true;
@@ -662,6 +677,9 @@ int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const u
     if( !la ) return -1;
     if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( la->ctx, "frame_put: slot %d out of range", slot );
     LaSlotHost &s = la->slots[slot];
+    // prefetched searches may still be reading the picture that occupied this slot
+    if( la->last_prefetch_ev >= 0 )
+        CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, la->ev[la->last_prefetch_ev], 0 ) );
     if( x264cu_frame_init_lowres( la->ctx, d_luma, luma_stride, la->p.width, la->p.height, s.dev.planes, la->d.stride ) ) return -1;
     return la_reset_slot( la, slot, h_inv_qscale );
 }
@@ -681,8 +699,8 @@ int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t 
     return x264cu_lookahead_frame_put_device( la, slot, la->d_luma, st, h_inv_qscale );
 }
 
-// enqueue the searches listed in h_jobs[0..n) as one launch
-static int la_launch_searches( x264cu_lookahead *la, int n )
+// enqueue the n searches assembled in la->pack as one launch on `stream` (no host synchronisation)
+static int la_launch_searches( x264cu_lookahead *la, int n, cudaStream_t stream )
 {
     x264cu_ctx *ctx = la->ctx;
     const LaDims &d = la->d;
@@ -690,7 +708,6 @@ static int la_launch_searches( x264cu_lookahead *la, int n )
     constexpr int NW = 8;
     const int rows = d.mb_h - ( d.do_edges ? 0 : 2 );
     if( rows <= 0 ) return 0;
-    CU_CHECK( ctx, cudaMemcpyAsync( la->d_jobs, la->h_jobs, n * sizeof( LaSearchJob ), cudaMemcpyHostToDevice, ctx->stream ) );
     dim3 grid( ( rows + NW - 1 ) / NW, n );
     size_t smem = ( 2 * d.cost_len + 1 ) * 2 + 16;
     static bool attr = false;
@@ -700,9 +717,8 @@ static int la_launch_searches( x264cu_lookahead *la, int n )
         attr = true;
     }
     if( smem > 200 * 1024 ) return x264cu_fail( ctx, "lookahead: mv cost table does not fit in shared memory" );
-    search_kernel<NW><<<grid, NW * 32, smem, ctx->stream>>>( d, la->d_jobs, la->d_cost_mv );
+    search_kernel<NW><<<grid, NW * 32, smem, stream>>>( d, la->pack, la->d_cost_mv );
     CU_LAUNCH_CHECK( ctx );
-    CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );               // h_jobs reusable; results visible
     return 0;
 }
 
@@ -718,10 +734,22 @@ static void la_fill_job( x264cu_lookahead *la, LaSearchJob &j, int fenc_slot, in
     j.progress = f.dev.progress + idx * d.mb_h;
 }
 
-static int la_reset_progress( x264cu_lookahead *la, const LaSearchJob &j )
+static int la_reset_progress( x264cu_lookahead *la, const LaSearchJob &j, cudaStream_t stream )
 {
     // "nothing done yet" = a column index larger than any real one (0x7F7F7F7F)
-    CU_CHECK( la->ctx, cudaMemsetAsync( j.progress, 0x7F, (size_t)la->d.mb_h * 4, la->ctx->stream ) );
+    CU_CHECK( la->ctx, cudaMemsetAsync( j.progress, 0x7F, (size_t)la->d.mb_h * 4, stream ) );
+    return 0;
+}
+
+// make the main stream wait for a prefetched search that may still be running on the search stream
+static int la_wait_pending( x264cu_lookahead *la, LaSlotHost &s, int list, int dm1 )
+{
+    int e = s.pending[list][dm1];
+    if( e >= 0 )
+    {
+        CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, la->ev[e], 0 ) );
+        s.pending[list][dm1] = -1;
+    }
     return 0;
 }
 
@@ -729,7 +757,12 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
 {
     if( !la ) return -1;
     x264cu_ctx *ctx = la->ctx;
-    int n = 0;
+    // everything queued so far on the main stream (lowres planes, vector resets) must be visible to the searches
+    CU_CHECK( ctx, cudaEventRecord( la->ev_main, ctx->stream ) );
+    CU_CHECK( ctx, cudaStreamWaitEvent( la->search_stream, la->ev_main, 0 ) );
+    int n = 0, launched = 0;
+    struct Mark { int slot, list, dm1; };
+    std::vector<Mark> marks;
     for( int i = 0; i < n_jobs; i++ )
     {
         if( fenc[i] < 0 || fenc[i] >= (int)la->slots.size() || ref[i] < 0 || ref[i] >= (int)la->slots.size() ||
@@ -740,16 +773,27 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
         if( !f.in_use || !la->slots[ref[i]].in_use ) return x264cu_fail( ctx, "search_batch: empty slot in job %d", i );
         if( f.searched[list[i]][dist[i] - 1] ) continue;
         f.searched[list[i]][dist[i] - 1] = true;
-        if( n == la->max_jobs )
+        if( n == LA_PACK )
         {
-            if( la_launch_searches( la, n ) ) return -1;
-            n = 0;
+            if( la_launch_searches( la, n, la->search_stream ) ) return -1;
+            n = 0; launched = 1;
         }
-        la_fill_job( la, la->h_jobs[n], fenc[i], ref[i], list[i], dist[i] );
-        if( la_reset_progress( la, la->h_jobs[n] ) ) return -1;
+        la_fill_job( la, la->pack.j[n], fenc[i], ref[i], list[i], dist[i] );
+        if( la_reset_progress( la, la->pack.j[n], la->search_stream ) ) return -1;
+        marks.push_back( Mark{ fenc[i], list[i], dist[i] - 1 } );
         n++;
     }
-    return la_launch_searches( la, n );
+    if( la_launch_searches( la, n, la->search_stream ) ) return -1;
+    if( n || launched )
+    {
+        const int e = la->ev_next;
+        la->ev_next = ( la->ev_next + 1 ) % la->n_ev;
+        CU_CHECK( ctx, cudaEventSynchronize( la->ev[e] ) );           // ring slot reuse: its previous recording is long done
+        CU_CHECK( ctx, cudaEventRecord( la->ev[e], la->search_stream ) );
+        for( auto &m : marks ) la->slots[m.slot].pending[m.list][m.dm1] = e;
+        la->last_prefetch_ev = e;
+    }
+    return 0;
 }
 
 int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
@@ -775,15 +819,15 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
     if( b != p0 && !fenc.searched[0][i0 - 1] )
     {
         fenc.searched[0][i0 - 1] = true;
-        la_fill_job( la, la->h_jobs[n], sb, s0, 0, i0 );
-        if( la_reset_progress( la, la->h_jobs[n] ) ) return -1;
+        la_fill_job( la, la->pack.j[n], sb, s0, 0, i0 );
+        if( la_reset_progress( la, la->pack.j[n], ctx->stream ) ) return -1;
         n++;
     }
     if( b != p1 && !fenc.searched[1][i1 - 1] )
     {
         fenc.searched[1][i1 - 1] = true;
-        la_fill_job( la, la->h_jobs[n], sb, s1, 1, i1 );
-        if( la_reset_progress( la, la->h_jobs[n] ) ) return -1;
+        la_fill_job( la, la->pack.j[n], sb, s1, 1, i1 );
+        if( la_reset_progress( la, la->pack.j[n], ctx->stream ) ) return -1;
         n++;
     }
     if( !fenc.intra_on_device )
@@ -792,7 +836,11 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
         CU_LAUNCH_CHECK( ctx );
         fenc.intra_on_device = true;
     }
-    if( la_launch_searches( la, n ) ) return -1;
+    if( la_launch_searches( la, n, ctx->stream ) ) return -1;
+    // prefetched searches this request reads (its own two lists and the temporal-direct vectors of the later reference)
+    if( b != p0 && la_wait_pending( la, fenc, 0, i0 - 1 ) ) return -1;
+    if( b != p1 && la_wait_pending( la, fenc, 1, i1 - 1 ) ) return -1;
+    if( b < p1 && p1 - p0 - 1 <= d.B && la_wait_pending( la, la->slots[s1], 0, p1 - p0 - 1 ) ) return -1;
 
     int dist_scale_factor = 128;
     if( p1 != p0 ) dist_scale_factor = ( ( ( b - p0 ) << 8 ) + ( ( p1 - p0 ) >> 1 ) ) / ( p1 - p0 );
@@ -858,6 +906,7 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
 static int la_check_slot( x264cu_lookahead *la, int slot )
 {
     if( !la ) return -1;
+    cudaStreamSynchronize( la->search_stream );          // read-backs see prefetched searches too
     if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use )
         return x264cu_fail( la->ctx, "lookahead: slot %d is empty / out of range", slot );
     return 0;

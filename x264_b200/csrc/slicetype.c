@@ -52,6 +52,9 @@ struct x264cu_slicetype
     long requests;
     int mb_w, mb_h;
     int failed;
+    int prefetch;
+    st_frame_t *recent[BFRAME_MAX + 2];   /* the last bframes+1 queued pictures, newest first (prefetch partners) */
+    int n_recent;
 };
 
 static int num_mbs( const x264cu_slicetype_t *s )          /* NUM_MBS, slicetype.c:794-797 */
@@ -530,6 +533,13 @@ static void release_frame( x264cu_slicetype_t *s, st_frame_t *f )
 {
     if( !f ) return;
     s->slot_used[f->slot] = 0;
+    for( int k = 0; k < s->n_recent; k++ )
+        if( s->recent[k] == f )
+        {
+            memmove( s->recent + k, s->recent + k + 1, ( s->n_recent - k - 1 ) * sizeof( st_frame_t * ) );
+            s->n_recent--;
+            break;
+        }
     free( f );
 }
 
@@ -582,6 +592,7 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
     s->p.la.n_slots = s->n_slots;
     s->mb_w = ( p->la.width + 15 ) >> 4;
     s->mb_h = ( p->la.height + 15 ) >> 4;
+    s->prefetch = 1;
     if( !s->slot_used || x264cu_lookahead_open( ctx, &s->p.la, &s->la ) )
     {
         free( s->slot_used );
@@ -603,18 +614,19 @@ void x264cu_slicetype_close( x264cu_slicetype_t *s )
     free( s );
 }
 
-int x264cu_slicetype_step( x264cu_slicetype_t *s, const uint8_t *h_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
-                           int *out_frame, int *out_type )
+static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_device, intptr_t luma_stride, const uint16_t *h_inv_qscale,
+                        int *out_frame, int *out_type )
 {
     if( !s || !out_frame || !out_type ) return -1;
     *out_frame = -1; *out_type = T_AUTO;
-    if( h_luma )
+    if( luma )
     {
         int slot = -1;
         for( int i = 0; i < s->n_slots; i++ )
             if( !s->slot_used[i] ) { slot = i; break; }
         if( slot < 0 || s->n_next >= LOOKAHEAD_MAX + 4 ) return -1;
-        if( x264cu_lookahead_frame_put( s->la, slot, h_luma, luma_stride, h_inv_qscale ) ) return -1;
+        if( on_device ? x264cu_lookahead_frame_put_device( s->la, slot, luma, luma_stride, h_inv_qscale )
+                      : x264cu_lookahead_frame_put( s->la, slot, luma, luma_stride, h_inv_qscale ) ) return -1;
         st_frame_t *f = calloc( 1, sizeof( *f ) );
         if( !f ) return -1;
         f->i_frame = s->i_input++;
@@ -623,6 +635,28 @@ int x264cu_slicetype_step( x264cu_slicetype_t *s, const uint8_t *h_luma, intptr_
         s->slot_used[slot] = 1;
         s->next[s->n_next++] = f;
         s->next[s->n_next] = NULL;
+        if( s->prefetch )
+        {   /* every (picture, earlier picture) pair the decision could ask about: list 0 at distance d <= bframes+1 from the
+             * new picture, list 1 at distance d <= bframes towards it */
+            int jf[2 * ( BFRAME_MAX + 2 )], jr[2 * ( BFRAME_MAX + 2 )], jl[2 * ( BFRAME_MAX + 2 )], jd[2 * ( BFRAME_MAX + 2 )], n = 0;
+            for( int k = 0; k < s->n_recent; k++ )
+            {
+                st_frame_t *o = s->recent[k];
+                int d = f->i_frame - o->i_frame;
+                if( !s->slot_used[o->slot] || d < 1 || d > s->p.la.bframes + 1 ) continue;
+                jf[n] = f->slot; jr[n] = o->slot; jl[n] = 0; jd[n] = d; n++;
+                if( d <= s->p.la.bframes ) { jf[n] = o->slot; jr[n] = f->slot; jl[n] = 1; jd[n] = d; n++; }
+            }
+            if( n && x264cu_lookahead_search_batch( s->la, n, jf, jr, jl, jd ) ) return -1;
+        }
+        /* remember by value: the st_frame_t may be freed once the picture is encoded, its slot id stays meaningful only
+         * while slot_used says so AND it still holds this picture -- tracked through the frame number */
+        {
+            int keep = s->p.la.bframes + 1;
+            if( s->n_recent < keep ) s->n_recent++;
+            for( int k = s->n_recent - 1; k > 0; k-- ) s->recent[k] = s->recent[k-1];
+            s->recent[0] = f;
+        }
         if( s->i_input <= s->delay )               /* encoder.c:3428: nothing to encode yet */
             return 0;
     }
@@ -639,6 +673,20 @@ int x264cu_slicetype_step( x264cu_slicetype_t *s, const uint8_t *h_luma, intptr_
         release_frame( s, f );
     return 0;
 }
+
+int x264cu_slicetype_step( x264cu_slicetype_t *s, const uint8_t *h_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
+                           int *out_frame, int *out_type )
+{
+    return step_common( s, h_luma, 0, luma_stride, h_inv_qscale, out_frame, out_type );
+}
+
+int x264cu_slicetype_step_device( x264cu_slicetype_t *s, const uint8_t *d_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
+                                  int *out_frame, int *out_type )
+{
+    return step_common( s, d_luma, 1, luma_stride, h_inv_qscale, out_frame, out_type );
+}
+
+void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *s, int prefetch ) { if( s ) s->prefetch = !!prefetch; }
 
 x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *s ) { return s ? s->la : NULL; }
 
