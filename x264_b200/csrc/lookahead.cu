@@ -220,6 +220,17 @@ intra_kernel( LaDims d, const uint8_t *__restrict__ plane, int32_t *__restrict__
 // ------------------------------------------------------------------------------------------------
 // search: one warp = one MB row, rows bottom-up; slicetype.c:654-705 + me.c
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire( const int *p )
+{
+    int v;
+    asm volatile( "ld.acquire.gpu.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
+    return v;
+}
+__device__ __forceinline__ void st_release( int *p, int v )
+{
+    asm volatile( "st.release.gpu.global.s32 [%0], %1;" ::"l"( p ), "r"( v ) : "memory" );
+}
+
 template <int NW>
 __global__ void __launch_bounds__( NW * 32 )
 search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uint16_t *__restrict__ cost_mv_g )
@@ -237,7 +248,6 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
     if( mb_y < end_y ) return;
     const int q = lane & 3, qx = ( q & 1 ) * 4, qy = ( q >> 1 ) * 4;
 
-    volatile int32_t *progress = job.progress;
     int16_t *mvs = job.mvs;
     // right neighbour's vector is produced by this warp itself
     int right_x = 0, right_y = 0;
@@ -250,17 +260,28 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
     for( int mb_x = start_x; mb_x >= end_x; mb_x-- )
     {
         const int mb_xy = mb_y * d.mb_w + mb_x;
-        // wait for the row below to have passed column mb_x-1 (it runs right to left)
-        if( mb_y < d.mb_h - 1 && mb_y + 1 <= start_y )
+        // wait for the row below to have passed column mb_x-1 (it runs right to left).  Lane 0 acquires the flag and is
+        // the only lane that then reads the neighbours' vectors (broadcast by shuffle): acquire/release, no full fences.
+        int nb0 = 0, nb1 = 0, nb2 = 0;                   // below, below-left, below-right
+        if( mb_y < d.mb_h - 1 )
         {
-            const int need = max( mb_x - 1, end_x );
             if( lane == 0 )
             {
-                int ns = 32;
-                while( progress[mb_y + 1] > need ) { __nanosleep( ns ); if( ns < 1024 ) ns <<= 1; }
+                if( mb_y + 1 <= start_y )
+                {
+                    const int need = max( mb_x - 1, end_x );
+                    int spins = 0;
+                    while( ld_acquire( &job.progress[mb_y + 1] ) > need )
+                        if( ++spins > 64 ) __nanosleep( 64 );
+                }
+                const int *below = (const int *)( mvs + 2 * ( mb_xy + d.mb_w ) );
+                nb0 = __ldcg( below );
+                if( mb_x > 0 ) nb1 = __ldcg( below - 1 );
+                if( mb_x < d.mb_w - 1 ) nb2 = __ldcg( below + 1 );
             }
-            __syncwarp();
-            __threadfence();
+            nb0 = __shfl_sync( 0xffffffffu, nb0, 0 );
+            nb1 = __shfl_sync( 0xffffffffu, nb1, 0 );
+            nb2 = __shfl_sync( 0xffffffffu, nb2, 0 );
         }
         LaMe m;
         const int pel = ( mb_y * 8 ) * d.stride + mb_x * 8;
@@ -284,22 +305,18 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
         if( mb_x < d.mb_w - 1 ) { mvcx[0] = right_x; mvcy[0] = right_y; i_mvc = 1; }
         if( mb_y < d.mb_h - 1 )
         {
-            const int16_t *below = mvs + 2 * ( mb_xy + d.mb_w );
-            int vx = __ldcg( (const int *)below ) ;
-            int bx = (int16_t)( vx & 0xffff ), by = (int16_t)( vx >> 16 );
+            int bx = (int16_t)( nb0 & 0xffff ), by = (int16_t)( nb0 >> 16 );
             if( i_mvc == 0 ) { mvcx[0] = bx; mvcy[0] = by; } else { mvcx[1] = bx; mvcy[1] = by; }
             i_mvc++;
             if( mb_x > 0 )
             {
-                int v2 = __ldcg( (const int *)( below - 2 ) );
-                int cx = (int16_t)( v2 & 0xffff ), cy = (int16_t)( v2 >> 16 );
+                int cx = (int16_t)( nb1 & 0xffff ), cy = (int16_t)( nb1 >> 16 );
                 if( i_mvc == 1 ) { mvcx[1] = cx; mvcy[1] = cy; } else { mvcx[2] = cx; mvcy[2] = cy; }
                 i_mvc++;
             }
             if( mb_x < d.mb_w - 1 )
             {
-                int v3 = __ldcg( (const int *)( below + 2 ) );
-                int cx = (int16_t)( v3 & 0xffff ), cy = (int16_t)( v3 >> 16 );
+                int cx = (int16_t)( nb2 & 0xffff ), cy = (int16_t)( nb2 >> 16 );
                 if( i_mvc == 1 ) { mvcx[1] = cx; mvcy[1] = cy; } else if( i_mvc == 2 ) { mvcx[2] = cx; mvcy[2] = cy; } else { mvcx[3] = cx; mvcy[3] = cy; }
                 i_mvc++;
             }
@@ -330,12 +347,11 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
         {
             *(int *)( mvs + 2 * mb_xy ) = (int)pack_mv( mvx, mvy );
             job.mv_costs[mb_xy] = cost;
-            __threadfence();
-            progress[mb_y] = mb_x;
+            st_release( &job.progress[mb_y], mb_x );
         }
         right_x = mvx; right_y = mvy;
     }
-    if( lane == 0 ) { __threadfence(); progress[mb_y] = -1; }
+    if( lane == 0 ) st_release( &job.progress[mb_y], -1 );
 }
 
 // ------------------------------------------------------------------------------------------------

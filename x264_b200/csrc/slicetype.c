@@ -55,9 +55,14 @@ struct x264cu_slicetype
     int prefetch;
     st_frame_t *recent[BFRAME_MAX + 2];   /* the last bframes+1 queued pictures, newest first (prefetch partners) */
     int n_recent;
+    /* prefetch jobs gathered over a few pictures so that one launch fills the GPU (each search is a thin wavefront) */
+    int pj_fenc[256], pj_ref[256], pj_list[256], pj_dist[256], pj_fframe[256], pj_rframe[256], n_pj, pj_pictures;
+    int prefetch_group;                   /* pictures per prefetch launch */
 };
 
-static int num_mbs( const x264cu_slicetype_t *s )          /* NUM_MBS, slicetype.c:794-797 */
+int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame );
+
+static inline int num_mbs( const x264cu_slicetype_t *s )          /* NUM_MBS, slicetype.c:794-797 */
 {
     return s->mb_w > 2 && s->mb_h > 2 ? ( s->mb_w - 2 ) * ( s->mb_h - 2 ) : s->mb_w * s->mb_h;
 }
@@ -593,6 +598,7 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
     s->mb_w = ( p->la.width + 15 ) >> 4;
     s->mb_h = ( p->la.height + 15 ) >> 4;
     s->prefetch = 1;
+    s->prefetch_group = s->delay >= 12 ? 4 : 1;
     if( !s->slot_used || x264cu_lookahead_open( ctx, &s->p.la, &s->la ) )
     {
         free( s->slot_used );
@@ -612,6 +618,23 @@ void x264cu_slicetype_close( x264cu_slicetype_t *s )
     x264cu_lookahead_close( s->la );
     free( s->slot_used );
     free( s );
+}
+
+/* launch the gathered searches; jobs whose pictures have left their slots in the meantime are dropped */
+static int flush_prefetch( x264cu_slicetype_t *s )
+{
+    int n = 0;
+    for( int i = 0; i < s->n_pj; i++ )
+    {
+        if( x264cu_slicetype_slot_of( s, s->pj_fframe[i] ) != s->pj_fenc[i] || x264cu_slicetype_slot_of( s, s->pj_rframe[i] ) != s->pj_ref[i] )
+            continue;
+        s->pj_fenc[n] = s->pj_fenc[i]; s->pj_ref[n] = s->pj_ref[i]; s->pj_list[n] = s->pj_list[i]; s->pj_dist[n] = s->pj_dist[i];
+        n++;
+    }
+    s->n_pj = 0;
+    s->pj_pictures = 0;
+    if( n && x264cu_lookahead_search_batch( s->la, n, s->pj_fenc, s->pj_ref, s->pj_list, s->pj_dist ) ) return -1;
+    return 0;
 }
 
 static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_device, intptr_t luma_stride, const uint16_t *h_inv_qscale,
@@ -638,16 +661,22 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
         if( s->prefetch )
         {   /* every (picture, earlier picture) pair the decision could ask about: list 0 at distance d <= bframes+1 from the
              * new picture, list 1 at distance d <= bframes towards it */
-            int jf[2 * ( BFRAME_MAX + 2 )], jr[2 * ( BFRAME_MAX + 2 )], jl[2 * ( BFRAME_MAX + 2 )], jd[2 * ( BFRAME_MAX + 2 )], n = 0;
             for( int k = 0; k < s->n_recent; k++ )
             {
                 st_frame_t *o = s->recent[k];
                 int d = f->i_frame - o->i_frame;
-                if( !s->slot_used[o->slot] || d < 1 || d > s->p.la.bframes + 1 ) continue;
-                jf[n] = f->slot; jr[n] = o->slot; jl[n] = 0; jd[n] = d; n++;
-                if( d <= s->p.la.bframes ) { jf[n] = o->slot; jr[n] = f->slot; jl[n] = 1; jd[n] = d; n++; }
+                if( !s->slot_used[o->slot] || d < 1 || d > s->p.la.bframes + 1 || s->n_pj + 2 > 256 ) continue;
+                int n = s->n_pj;
+                s->pj_fenc[n] = f->slot; s->pj_ref[n] = o->slot; s->pj_list[n] = 0; s->pj_dist[n] = d;
+                s->pj_fframe[n] = f->i_frame; s->pj_rframe[n] = o->i_frame; n++;
+                if( d <= s->p.la.bframes )
+                {
+                    s->pj_fenc[n] = o->slot; s->pj_ref[n] = f->slot; s->pj_list[n] = 1; s->pj_dist[n] = d;
+                    s->pj_fframe[n] = o->i_frame; s->pj_rframe[n] = f->i_frame; n++;
+                }
+                s->n_pj = n;
             }
-            if( n && x264cu_lookahead_search_batch( s->la, n, jf, jr, jl, jd ) ) return -1;
+            if( ++s->pj_pictures >= s->prefetch_group && flush_prefetch( s ) ) return -1;
         }
         /* remember by value: the st_frame_t may be freed once the picture is encoded, its slot id stays meaningful only
          * while slot_used says so AND it still holds this picture -- tracked through the frame number */
@@ -660,6 +689,7 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
         if( s->i_input <= s->delay )               /* encoder.c:3428: nothing to encode yet */
             return 0;
     }
+    if( !luma && s->n_pj && flush_prefetch( s ) ) return -1;
     lookahead_get_frames( s );
     if( s->failed ) return -1;
     if( !s->n_current )
