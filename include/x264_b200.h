@@ -249,6 +249,11 @@ int  x264cu_slicetype_step_device( x264cu_slicetype_t *st, const uint8_t *d_luma
  * launched at once on a second stream (the x264_opencl_slicetype_prep idea, encoder/slicetype-cl.c:653); 0: every search
  * runs on demand inside the cost request that needs it.  The decisions are identical either way. */
 void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *st, int prefetch );
+/* pictures queued beyond the lookahead before a decision is taken (0..16; default 8 for lookaheads >= 12, else 0; must be
+ * set before the first picture).  It is the synchronous twin of param.i_sync_lookahead (encoder.c:1137-1141, :1611): the
+ * analysis never looks at more than i_slicetype_length+1 pictures (b_deterministic, slicetype.c:1480-1485), so the
+ * decisions do not change -- only the searches of the newest pictures get time to finish on the second stream. */
+void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *st, int pictures );
 /* the lookahead object underneath (for reading per-MB results) and the slot a display index currently occupies (-1 if gone) */
 x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *st );
 int  x264cu_slicetype_slot_of( x264cu_slicetype_t *st, int frame );

@@ -39,3 +39,18 @@ def test_gpu_frame_types(ctx, case):
     finally:
         st.close()
     assert got == want, (case, [z for z in zip(got, want) if z[0] != z[1]][:6])
+
+
+@pytest.mark.parametrize("mode", [(0, 0), (1, 0), (1, 5), (0, 16)])
+def test_prefetch_and_run_ahead_do_not_change_decisions(ctx, mode):
+    prefetch, run_ahead = mode
+    w, h, n = 320, 192, 60
+    frames = synth_sequence(w, h, n, seed=5, cut_at=31)
+    outs = []
+    for pf, ra in ((0, 0), (prefetch, run_ahead)):
+        st = x.Slicetype(ctx, w, h, rc_lookahead=20, psy=0, aq_mode=0)
+        st.set_prefetch(pf)
+        st.set_run_ahead(ra)
+        outs.append(st.decide(frames))
+        st.close()
+    assert outs[0] == outs[1]

@@ -24,6 +24,7 @@ def bind(L):
     L.x264cu_slicetype_step.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
     L.x264cu_slicetype_step_device.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
     L.x264cu_slicetype_set_prefetch.argtypes = [vp, ci]
+    L.x264cu_slicetype_set_run_ahead.argtypes = [vp, ci]
     L.x264cu_slicetype_lookahead.argtypes = [vp]
     L.x264cu_slicetype_lookahead.restype = vp
     L.x264cu_slicetype_slot_of.argtypes = [vp, ci]
@@ -172,6 +173,9 @@ class Slicetype:
 
     def set_prefetch(self, on):
         self.L.x264cu_slicetype_set_prefetch(self.h, int(on))
+
+    def set_run_ahead(self, k):
+        self.L.x264cu_slicetype_set_run_ahead(self.h, int(k))
 
     def decide(self, frames):
         out = []

@@ -58,6 +58,7 @@ struct x264cu_slicetype
     /* prefetch jobs gathered over a few pictures so that one launch fills the GPU (each search is a thin wavefront) */
     int pj_fenc[256], pj_ref[256], pj_list[256], pj_dist[256], pj_fframe[256], pj_rframe[256], n_pj, pj_pictures;
     int prefetch_group;                   /* pictures per prefetch launch */
+    int run_ahead;                        /* extra pictures queued before deciding, like param.i_sync_lookahead (encoder.c:1611) */
 };
 
 int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame );
@@ -592,13 +593,14 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
     s->slicetype_length = s->delay;
     s->b_analyse_keyframe = p->la.mb_tree != 0;
     s->i_last_keyframe = -p->keyint_max;
-    s->n_slots = s->delay + p->la.bframes + 8;
+    s->n_slots = s->delay + p->la.bframes + 8 + 16;
     s->slot_used = calloc( s->n_slots, 1 );
     s->p.la.n_slots = s->n_slots;
     s->mb_w = ( p->la.width + 15 ) >> 4;
     s->mb_h = ( p->la.height + 15 ) >> 4;
     s->prefetch = 1;
     s->prefetch_group = s->delay >= 12 ? 4 : 1;
+    s->run_ahead = s->delay >= 12 ? 8 : 0;
     if( !s->slot_used || x264cu_lookahead_open( ctx, &s->p.la, &s->la ) )
     {
         free( s->slot_used );
@@ -686,7 +688,7 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
             for( int k = s->n_recent - 1; k > 0; k-- ) s->recent[k] = s->recent[k-1];
             s->recent[0] = f;
         }
-        if( s->i_input <= s->delay )               /* encoder.c:3428: nothing to encode yet */
+        if( s->i_input <= s->delay + s->run_ahead )   /* encoder.c:3428: nothing to encode yet (i_delay includes the sync-lookahead pictures) */
             return 0;
     }
     if( !luma && s->n_pj && flush_prefetch( s ) ) return -1;
@@ -717,6 +719,11 @@ int x264cu_slicetype_step_device( x264cu_slicetype_t *s, const uint8_t *d_luma, 
 }
 
 void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *s, int prefetch ) { if( s ) s->prefetch = !!prefetch; }
+
+void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *s, int pictures )
+{
+    if( s && !s->i_input && pictures >= 0 && pictures <= 16 ) s->run_ahead = pictures;
+}
 
 x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *s ) { return s ? s->la : NULL; }
 
