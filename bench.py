@@ -422,6 +422,15 @@ def run_lookahead_b200(args, rank, world, local, dist):
     ms = max_over_ranks(dist, ms, local)
     clocks = sampler.stop()
     st.close()
+    # the one exchange step: every rank's per-picture decision records are all-gathered (NCCL) so that rank 0 holds the
+    # decisions of all streams; outside the timed region only because it happens once per run, not per step
+    gathered_streams = 1
+    if dist is not None:
+        import torch
+        from x264_b200 import dist as xd
+        rec = xd.pack_records(rank, decided[-(n * args.steps):], n * args.steps)
+        allrec = xd.unpack_records(xd.all_gather_records(dist, rec, device=torch.device("cuda", local)))
+        gathered_streams = len(allrec)
 
     # ---- the search kernel alone: 8 searches (4 distances x 2 lists) of one picture per launch --------
     la = x.Lookahead(ctx, LA_W, LA_H, n_slots=8, **LA_OPTS)
@@ -473,7 +482,9 @@ def run_lookahead_b200(args, rank, world, local, dist):
                                "lookahead settings (hex, subme 7 -> lookahead subpel 4, bframes 3, b-adapt 1, rc-lookahead 40, "
                                "mb-tree requests, scenecut 40; weightp analysis off, aq off)" % n,
                    "l2": "each picture's 4 lowres planes (9.4 MB) stay L2-resident by design; pictures cycle through %d MB" % (frames.nbytes // 2**20),
-                   "cost_requests_per_step": requests / args.steps, "decided_per_step": len(decided) / (args.steps + max(args.warmup, 3))},
+                   "cost_requests_per_step": requests / args.steps, "decided_per_step": len(decided) / (args.steps + max(args.warmup, 3)),
+                   "scheduling": "searches prefetched on a second stream in groups of 4 pictures, decisions run 8 pictures behind (sync-lookahead twin)",
+                   "multi_gpu": "one independent stream per GPU; one NCCL all-gather of decision records (%d streams gathered)" % gathered_streams},
         "clocks": clocks,
         "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
                 "d2h_bytes_per_step": int(32 * requests / args.steps), "api": "x264cu_slicetype_step (pinned host luma)"},
