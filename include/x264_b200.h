@@ -260,6 +260,50 @@ int  x264cu_slicetype_slot_of( x264cu_slicetype_t *st, int frame );
 /* number of slicetype_frame_cost requests issued so far (memo hits included) */
 long x264cu_slicetype_cost_requests( x264cu_slicetype_t *st );
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched twin of x264_me_search_ref + refine_subpel (encoder/me.h:58-60, encoder/me.c:182-992): one job = one call.
+ * Luma only (no chroma ME), DIA / HEX / UMH, every partition size and sub-pel level.  One warp runs one search with the
+ * reference's control flow; jobs are independent (their predictors are inputs), which is how the full-resolution
+ * motion-estimation stage is replayed from recorded x264_me_t inputs (BASELINE config 3).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct
+{
+    int32_t  i_pixel;                /* m->i_pixel, PIXEL_16x16 .. PIXEL_4x4 */
+    uint32_t fenc_off;               /* byte offset of the block in the fenc plane */
+    uint32_t ref_off;                /* byte offset of the co-located block in each reference plane */
+    int16_t  mvp[2];                 /* m->mvp */
+    int16_t  mvc[8][2];              /* candidate predictors (mvc argument) */
+    int32_t  i_mvc;                  /* 0..8 */
+    int16_t  mv_min_spel[2], mv_max_spel[2];   /* h->mb.mv_min_spel / mv_max_spel; mv_limit_fpel = these >> 2 */
+    int32_t  halfpel_thresh;         /* *p_halfpel_thresh, or -1 for NULL */
+} x264cu_me_job_t;
+
+typedef struct
+{
+    int16_t mv[2];                   /* m->mv */
+    int32_t cost;                    /* m->cost */
+    int32_t cost_mv;                 /* m->cost_mv (undefined after a half-pel early exit, as in the reference) */
+    int32_t halfpel_thresh;          /* updated *p_halfpel_thresh */
+} x264cu_me_result_t;
+
+typedef struct
+{
+    int me_method;                   /* h->mb.i_me_method (X264CU_ME_DIA/HEX/UMH) */
+    int subpel_refine;               /* h->mb.i_subpel_refine */
+    int me_range;                    /* h->param.analyse.i_me_range */
+    int mbcmp_satd;                  /* encoder.c:1409-1427: mbcmp is SATD iff the encoder's subme > 1 */
+    int lambda;                      /* a->i_lambda: cost_mv = lambda * bits (analyse.c:143-157) */
+    int mv_range;                    /* h->param.analyse.i_mv_range: sizes the cost table */
+    int weight_enabled, weight_scale, weight_denom, weight_offset;   /* m->weight[0] (common/mc.h:235-245) */
+} x264cu_me_params_t;
+
+/* d_fref[4]: F,H,V,C plane origins of the reference (x264cu_hpel_filter output), d_fref_w: the weighted full-pel plane or
+ * d_fref[0].  All planes share ref_stride and are padded by X264CU_PAD. */
+int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *params,
+                            const uint8_t *d_fenc, intptr_t fenc_stride,
+                            const uint8_t *const d_fref[4], const uint8_t *d_fref_w, intptr_t ref_stride,
+                            const x264cu_me_job_t *d_jobs, int n, x264cu_me_result_t *d_results );
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,8 @@ that the build and the symbol table can be checked), but every compute call need
 from .binding import (lib, lib_path, Context, X264CUError, PIXEL_W, PIXEL_H, PIXEL_NAMES, cand_dtype,
                       cand_x4_dtype, SAD, SSD, SATD, SA8D, PAD, exported_symbols, header_symbols)
 
-from .binding_ext import Lookahead, LookaheadParams, Slicetype, SlicetypeParams, TYPE_NAMES
+from .binding_ext import (Lookahead, LookaheadParams, Slicetype, SlicetypeParams, TYPE_NAMES, MeParams, me_job_dtype,
+                          me_result_dtype, me_search_batch)
 
-__all__ = ["Lookahead", "LookaheadParams", "Slicetype", "SlicetypeParams", "TYPE_NAMES", "lib", "lib_path", "Context", "X264CUError", "PIXEL_W", "PIXEL_H", "PIXEL_NAMES", "cand_dtype",
+__all__ = ["MeParams", "me_job_dtype", "me_result_dtype", "me_search_batch", "Lookahead", "LookaheadParams", "Slicetype", "SlicetypeParams", "TYPE_NAMES", "lib", "lib_path", "Context", "X264CUError", "PIXEL_W", "PIXEL_H", "PIXEL_NAMES", "cand_dtype",
            "cand_x4_dtype", "SAD", "SSD", "SATD", "SA8D", "PAD", "exported_symbols", "header_symbols"]

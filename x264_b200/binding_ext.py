@@ -9,6 +9,27 @@ class LookaheadParams(C.Structure):
                                        "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv", "n_slots")]
 
 
+class MeJob(C.Structure):
+    _fields_ = [("i_pixel", C.c_int32), ("fenc_off", C.c_uint32), ("ref_off", C.c_uint32), ("mvp", C.c_int16 * 2),
+                ("mvc", (C.c_int16 * 2) * 8), ("i_mvc", C.c_int32), ("mv_min_spel", C.c_int16 * 2), ("mv_max_spel", C.c_int16 * 2),
+                ("halfpel_thresh", C.c_int32)]
+
+
+class MeResult(C.Structure):
+    _fields_ = [("mv", C.c_int16 * 2), ("cost", C.c_int32), ("cost_mv", C.c_int32), ("halfpel_thresh", C.c_int32)]
+
+
+class MeParams(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("me_method", "subpel_refine", "me_range", "mbcmp_satd", "lambda_", "mv_range",
+                                       "weight_enabled", "weight_scale", "weight_denom", "weight_offset")]
+
+
+me_job_dtype = np.dtype([("i_pixel", np.int32), ("fenc_off", np.uint32), ("ref_off", np.uint32), ("mvp", np.int16, (2,)),
+                         ("mvc", np.int16, (8, 2)), ("i_mvc", np.int32), ("mv_min_spel", np.int16, (2,)),
+                         ("mv_max_spel", np.int16, (2,)), ("halfpel_thresh", np.int32)])
+me_result_dtype = np.dtype([("mv", np.int16, (2,)), ("cost", np.int32), ("cost_mv", np.int32), ("halfpel_thresh", np.int32)])
+
+
 class SlicetypeParams(C.Structure):
     _fields_ = [("la", LookaheadParams)] + [(n, C.c_int) for n in ("keyint_max", "keyint_min", "scenecut_threshold", "b_adapt",
                                                                   "b_pyramid", "rc_lookahead", "psy", "frame_reference", "rc_cqp")]
@@ -19,6 +40,7 @@ TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "BREF", 5: "B"}
 
 def bind(L):
     vp, ci, ss = C.c_void_p, C.c_int, C.c_ssize_t
+    L.x264cu_me_search_batch.argtypes = [vp, C.POINTER(MeParams), vp, ss, C.POINTER(vp), vp, ss, vp, ci, vp]
     L.x264cu_slicetype_open.argtypes = [vp, C.POINTER(SlicetypeParams), C.POINTER(vp)]
     L.x264cu_slicetype_close.argtypes = [vp]
     L.x264cu_slicetype_step.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
@@ -193,3 +215,18 @@ class Slicetype:
     @property
     def cost_requests(self):
         return int(self.L.x264cu_slicetype_cost_requests(self.h))
+
+
+def me_search_batch(ctx, params, d_fenc, fenc_stride, d_fref, d_fref_w, ref_stride, jobs):
+    """jobs: numpy array of me_job_dtype (host) -> numpy array of me_result_dtype.  d_* are device addresses."""
+    assert jobs.dtype == me_job_dtype and C.sizeof(MeJob) == me_job_dtype.itemsize and C.sizeof(MeResult) == me_result_dtype.itemsize
+    n = len(jobs)
+    d_jobs = ctx.upload(jobs)
+    d_res = ctx.malloc(max(n, 1) * me_result_dtype.itemsize)
+    arr = (C.c_void_p * 4)(*[int(p) for p in d_fref])
+    ctx.check(ctx.L.x264cu_me_search_batch(ctx.h, C.byref(params), int(d_fenc), fenc_stride, arr,
+                                           int(d_fref_w) if d_fref_w else None, ref_stride, d_jobs, n, d_res))
+    out = ctx.download(d_res, (n,), me_result_dtype)
+    ctx.free(d_jobs)
+    ctx.free(d_res)
+    return out

@@ -116,7 +116,7 @@ __device__ __forceinline__ uint32_t pack_mv( int x, int y ) { return ( (uint32_t
 
 // x264_me_search_ref for one lowres MB.  All control flow is warp-uniform; `slot` = lane>>2.
 // mvc: up to 4 candidate vectors (qpel), i_mvc of them valid.  Results: mv (qpel) and cost, uniform.
-__device__ __noinline__ void la_me_search( LaMe &m, int me_method, int subpel_refine, int me_range,
+static __device__ __noinline__ void la_me_search( LaMe &m, int me_method, int subpel_refine, int me_range,
                                            const int *mvc_x, const int *mvc_y, int i_mvc, int lane,
                                            int &out_mvx, int &out_mvy, int &out_cost )
 {
