@@ -80,6 +80,35 @@ __device__ __forceinline__ void qpel4x4( const LaMe &m, int mvx, int mvy, uint32
     }
 }
 
+// same as qpel4x4 with the plane pointers passed individually (selected with ?: instead of an indexed local array)
+__device__ __forceinline__ void qpel4x4_p( const uint8_t *f0, const uint8_t *f1, const uint8_t *f2, const uint8_t *f3, int stride,
+                                           const LaWeight &w, int mvx, int mvy, uint32_t b[4] )
+{
+    const uint32_t R0 = 0x54FE5454u, R1 = 0xBABABA10u;
+    const int idx = ( ( mvy & 3 ) << 2 ) + ( mvx & 3 );
+    const int off = ( mvy >> 2 ) * stride + ( mvx >> 2 );
+    const int k0 = ( R0 >> ( 2*idx ) ) & 3, k1 = ( R1 >> ( 2*idx ) ) & 3;
+    const uint8_t *s1 = ( k0 == 0 ? f0 : k0 == 1 ? f1 : k0 == 2 ? f2 : f3 ) + off + ( ( mvy & 3 ) == 3 ? stride : 0 );
+    if( idx & 5 )
+    {
+        const uint8_t *s2 = ( k1 == 0 ? f0 : k1 == 1 ? f1 : k1 == 2 ? f2 : f3 ) + off + ( ( mvx & 3 ) == 3 ? 1 : 0 );
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+            b[r] = __vavgu4( ldg4u( s1 + r * stride ), ldg4u( s2 + r * stride ) );
+    }
+    else
+    {
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+            b[r] = ldg4u( s1 + r * stride );
+    }
+    if( w.enabled )
+    {
+#pragma unroll
+        for( int r = 0; r < 4; r++ ) b[r] = weight4( b[r], w );
+    }
+}
+
 __device__ __forceinline__ int quad_sum( int v )          // sum over the 4 lanes of one candidate slot
 {
     v += __shfl_xor_sync( 0xffffffffu, v, 1 );

@@ -8,8 +8,12 @@
 // warp-wide minimum over packed (cost<<8 | order) keys, applied round by round.
 #pragma once
 #include "lookahead_dev.cuh"
+#include <stdio.h>
 
 namespace x264cu {
+
+// i-th signed 4-bit entry of a packed table (keeps the small offset tables in immediates instead of local memory)
+__device__ __forceinline__ int nib( unsigned long long tab, int i ) { return (int)( (long long)( tab << ( 60 - 4*i ) ) >> 60 ); }
 
 struct MeShared                       // per-launch constants
 {
@@ -27,7 +31,7 @@ struct MeWarp
     static constexpr int LX = BW / 4, LY = BH / 4, L = LX * LY, S = 32 / L;
     // per-lane
     uint32_t fenc[4];
-    const uint8_t *fref[4], *fref_w;
+    const uint8_t *fref0, *fref1, *fref2, *fref3, *fref_w;
     int stride;
     const uint16_t *cost_mv;
     int mvpx, mvpy;
@@ -58,12 +62,8 @@ struct MeWarp
     __device__ __forceinline__ int cost_fpel( int mx, int my ) const { return sad_fpel( mx, my ) + bits_fpel( mx, my ); }
     __device__ __forceinline__ int cost_qpel( int mx, int my, bool use_mbcmp ) const
     {
-        LaMe t;
-#pragma unroll
-        for( int i = 0; i < 4; i++ ) t.fref[i] = fref[i];
-        t.stride = stride; t.w = w;
         uint32_t b[4];
-        qpel4x4( t, mx, my, b );
+        qpel4x4_p( fref0, fref1, fref2, fref3, stride, w, mx, my, b );
         int d = ( use_mbcmp && satd ) ? satd4x4( fenc, b ) : sad4x4( fenc, b );
         return group_sum( d ) + __ldg( cost_mv + ( mx - mvpx ) ) + __ldg( cost_mv + ( my - mvpy ) );
     }
@@ -82,6 +82,10 @@ struct MeWarp
             const int c = cost_fpel( ok ? cx : bmx, ok ? cy : bmy );
             int key = ok ? ( c << 8 ) | i : 0x7fffffff;
             key = warp_min( key );
+#ifdef ME_DEBUG
+            if( blockIdx.x == 0 && threadIdx.x < 32 && ( threadIdx.x % L ) == 0 )
+                printf( "  try lane %d i %d n %d cand %d %d ok %d c %d key %x bcost %d\n", threadIdx.x, i, n, cx, cy, (int)ok, c, key, bcost );
+#endif
             if( key != 0x7fffffff && ( key >> 8 ) < bcost )
             {
                 const int w = key & 255;
@@ -184,8 +188,7 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
 #pragma unroll
         for( int r = 0; r < 4; r++ ) m.fenc[r] = ldg4u( f + r * g.fenc_stride );
         const int o = ref_off + sy * g.stride + sx;
-#pragma unroll
-        for( int i = 0; i < 4; i++ ) m.fref[i] = g.fref[i] + o;
+        m.fref0 = g.fref[0] + o; m.fref1 = g.fref[1] + o; m.fref2 = g.fref[2] + o; m.fref3 = g.fref[3] + o;
         m.fref_w = g.fref_w + o;
     }
     m.min_spel_x = limits[0]; m.min_spel_y = limits[1]; m.max_spel_x = limits[2]; m.max_spel_y = limits[3];
@@ -197,18 +200,28 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
     uint32_t pmv, bpred_mv = 0;
 
     // ---- predictor stage, me.c:216-318 ----
-    int cx[8], cy[8], n = 0;
+    // candidates kept as packed (x | y<<16) words in ONE local array (two dynamically indexed local arrays were seen
+    // to alias in the generated code)
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;      // packed (x | y<<16), kept in registers
+    int n = 0;
+    auto cget = [&]( int k ) { return k == 0 ? c0 : k == 1 ? c1 : k == 2 ? c2 : k == 3 ? c3 : k == 4 ? c4 : k == 5 ? c5 : k == 6 ? c6 : c7; };
+    auto cput = [&]( int k, uint32_t v ) {
+        if( k == 0 ) c0 = v; else if( k == 1 ) c1 = v; else if( k == 2 ) c2 = v; else if( k == 3 ) c3 = v;
+        else if( k == 4 ) c4 = v; else if( k == 5 ) c5 = v; else if( k == 6 ) c6 = v; else c7 = v; };
+#define CX( k ) ( (int)(int16_t)( cget( k ) & 0xffff ) )
+#define CY( k ) ( (int)(int16_t)( cget( k ) >> 16 ) )
     if( subpel >= 3 )
     {
         int bpx = clip3i( mvpx, m.x_min*4, m.x_max*4 ), bpy = clip3i( mvpy, m.y_min*4, m.y_max*4 );
         pmv = pack_mv( bpx, bpy );
         pmx = LA_FPEL( bpx ); pmy = LA_FPEL( bpy );
-        for( int i = 0; i < i_mvc; i++ )
+        for( int i = 0; i < 8; i++ )
         {
+            if( i >= i_mvc ) break;
             int vx = mvc[2*i], vy = mvc[2*i+1];
             uint32_t mv = pack_mv( vx, vy );
             if( !mv || mv == pmv ) continue;
-            cx[n] = clip3i( vx, m.x_min*4, m.x_max*4 ); cy[n] = clip3i( vy, m.y_min*4, m.y_max*4 );
+            cput( n, pack_mv( clip3i( vx, m.x_min*4, m.x_max*4 ), clip3i( vy, m.y_min*4, m.y_max*4 ) ) );
             n++;
         }
         int pmv_cost = m.cost_qpel( bpx, bpy, false );           // every slot computes it: uniform value
@@ -220,11 +233,11 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
             {
                 const int i = base + m.slot;
                 const int ii = min( i, n - 1 );
-                const int c = m.cost_qpel( cx[ii], cy[ii], false );
+                const int c = m.cost_qpel( CX( ii ), CY( ii ), false );
                 int key = i < n ? ( c << 4 ) + i + 1 : 0x7fffffff;
                 best = min( best, warp_min( key ) );
             }
-            if( best & 15 ) { bpx = cx[( best & 15 ) - 1]; bpy = cy[( best & 15 ) - 1]; }
+            if( best & 15 ) { bpx = CX( ( best & 15 ) - 1 ); bpy = CY( ( best & 15 ) - 1 ); }
             bpred_cost = best >> 4;
         }
         m.bmx = LA_FPEL( bpx ); m.bmy = LA_FPEL( bpy );
@@ -252,12 +265,13 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
         m.bmy = pmy = clip3i( LA_FPEL( mvpy ), m.y_min, m.y_max );
         pmv = pack_mv( m.bmx, m.bmy );
         m.bcost = m.sad_fpel( m.bmx, m.bmy );                     // no mv cost on the rounded predictor (me.c:283-291)
-        for( int i = 0; i < i_mvc; i++ )
+        for( int i = 0; i < 8; i++ )
         {
+            if( i >= i_mvc ) break;
             int rx = ( mvc[2*i] + 2 ) >> 2, ry = ( mvc[2*i+1] + 2 ) >> 2;
             uint32_t mv = pack_mv( rx, ry );
             if( !mv || mv == pmv ) continue;
-            cx[n] = clip3i( rx, m.x_min, m.x_max ); cy[n] = clip3i( ry, m.y_min, m.y_max );
+            cput( n, pack_mv( clip3i( rx, m.x_min, m.x_max ), clip3i( ry, m.y_min, m.y_max ) ) );
             n++;
         }
         if( n > 0 )
@@ -267,11 +281,15 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
             {
                 const int i = base + m.slot;
                 const int ii = min( i, n - 1 );
-                const int c = m.cost_fpel( cx[ii], cy[ii] );
+                const int c = m.cost_fpel( CX( ii ), CY( ii ) );
                 int key = i < n ? ( c << 4 ) + i + 1 : 0x7fffffff;
+#ifdef ME_DEBUG
+                if( blockIdx.x == 0 && threadIdx.x < 32 && ( threadIdx.x % M::L ) == 0 )
+                    printf( "  pred lane %d i %d ii %d n %d cand %d %d c %d key %x bcost %d\n", threadIdx.x, i, ii, n, CX( ii ), CY( ii ), c, key, m.bcost );
+#endif
                 best = min( best, warp_min( key ) );
             }
-            if( best & 15 ) { m.bmx = cx[( best & 15 ) - 1]; m.bmy = cy[( best & 15 ) - 1]; }
+            if( best & 15 ) { m.bmx = CX( ( best & 15 ) - 1 ); m.bmy = CY( ( best & 15 ) - 1 ); }
             m.bcost = best >> 4;
         }
         if( pmv )
@@ -281,6 +299,11 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
         }
     }
 
+#ifdef ME_DEBUG
+    if( blockIdx.x == 0 && threadIdx.x == 0 )
+        printf( "dbg method %d subpel %d range %d i_mvc %d mvp %d %d lim %d %d %d %d n %d start %d %d cost %d pmv %x L %d S %d\n", g.me_method, subpel, me_range, i_mvc,
+                mvpx, mvpy, m.x_min, m.y_min, m.x_max, m.y_max, n, m.bmx, m.bmy, m.bcost, pmv, M::L, M::S );
+#endif
     // ---- integer search ----
     if( g.me_method == X264CU_ME_DIA )
     {
@@ -316,8 +339,8 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
             if( m.bcost == ucost2 && m.bcost < ( 2000 >> shift ) )
             {
                 // octagon: (0,-2) (-1,-1) (1,-1) (-2,0) (2,0) (-1,1) (1,1) (0,2)
-                m.try_list( 8, omx, omy, []( int i ) { const int t[8] = { 0, -1, 1, -2, 2, -1, 1, 0 }; return t[i]; },
-                            []( int i ) { const int t[8] = { -2, -1, -1, 0, 0, 1, 1, 2 }; return t[i]; }, false );
+                m.try_list( 8, omx, omy, []( int i ) { return nib( 0x01F2E1F0ull, i ); },
+                            []( int i ) { return nib( 0x21100FFEull, i ); }, false );
                 if( m.bcost == ucost1 && m.bcost < ( 500 >> shift ) )
                     done = true;
                 else if( m.bcost == ucost2 )
@@ -325,8 +348,8 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
                     const int range = ( me_range >> 1 ) | 1;
                     m.cross( omx, omy, 3, range, range );
                     // (-1,-2) (1,-2) (-2,-1) (2,-1) (-2,1) (2,1) (-1,2) (1,2)
-                    m.try_list( 8, omx, omy, []( int i ) { const int t[8] = { -1, 1, -2, 2, -2, 2, -1, 1 }; return t[i]; },
-                                []( int i ) { const int t[8] = { -2, -2, -1, -1, 1, 1, 2, 2 }; return t[i]; }, false );
+                    m.try_list( 8, omx, omy, []( int i ) { return nib( 0x1F2E2E1Full, i ); },
+                                []( int i ) { return nib( 0x2211FFEEull, i ); }, false );
                     if( m.bcost == ucost2 )
                         done = true;
                     cross_start = range + 2;
@@ -366,8 +389,8 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
                 {
                     const int sc = i;
                     m.try_list( 16, omx, omy,
-                                [=]( int j ) { const int t[16] = { 0, 0, -2, 2, -4, 4, -4, 4, -4, 4, -4, 4, -4, 4, -2, 2 }; return t[j] * sc; },
-                                [=]( int j ) { const int t[16] = { -4, 4, -3, -3, -2, -2, -1, -1, 0, 0, 1, 1, 2, 2, 3, 3 }; return t[j] * sc; }, true );
+                                [=]( int j ) { return nib( 0x2E4C4C4C4C4C2E00ull, j ) * sc; },
+                                [=]( int j ) { return nib( 0x33221100FFEEDD4Cull, j ) * sc; }, true );
                 } while( ++i <= me_range >> 2 );
                 if( m.bmy <= m.y_max && m.bmy >= m.y_min && m.bmx <= m.x_max && m.bmx >= m.x_min )
                     m.hex_refine( me_range );
@@ -375,6 +398,10 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
         }
     }
 
+#ifdef ME_DEBUG
+    if( blockIdx.x == 0 && threadIdx.x == 0 )
+        printf( "dbg after int search %d %d cost %d\n", m.bmx, m.bmy, m.bcost );
+#endif
     // ---- back to quarter-pel, me.c:774-789 ----
     int qx, qy, qcost;
     if( subpel < 3 )
@@ -460,5 +487,8 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
     out_mvx = qx; out_mvy = qy; out_cost = qcost;
     out_cost_mv = __ldg( g.cost_mv + ( qx - mvpx ) ) + __ldg( g.cost_mv + ( qy - mvpy ) );
 }
+
+#undef CX
+#undef CY
 
 } // namespace x264cu
