@@ -348,7 +348,7 @@ def cpu_lookahead_rate(frames, budget_s):
     else:
         lib, kind = _libs.slicetype_oracle_lib(), "port"
     la = LookaheadParams(LA_W, LA_H, *[LA_OPTS[k] for k in ("subpel_refine", "me_method", "me_range", "mv_range", "bframes",
-                                                            "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv")], 0)
+                                                            "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv")], 0, 0)
     p = SlicetypeParams(la, *[LA_ST[k] for k in ("keyint_max", "keyint_min", "scenecut_threshold", "b_adapt", "b_pyramid",
                                                   "rc_lookahead", "psy", "frame_reference", "rc_cqp")])
     lib.x264cu_slicetype_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]

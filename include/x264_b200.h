@@ -170,6 +170,8 @@ typedef struct
     int mb_tree;                  /* h->param.rc.b_mb_tree */
     int vbv;                      /* h->param.rc.i_vbv_buffer_size != 0 */
     int n_slots;                  /* frames resident in HBM at once (>= lookahead + bframes + 3) */
+    int weighted_pred;            /* h->param.analyse.i_weighted_pred != 0 (X264_WEIGHTP_FAKE included, encoder.c:1316-1317):
+                                     run the lookahead weight analysis (slicetype.c:284-501) on first P-type searches */
 } x264cu_lookahead_params_t;
 
 /* x264_opencl_lookahead_init / _delete (common/opencl.c:411, :596) */
@@ -204,6 +206,9 @@ int x264cu_lookahead_get_row_satds( x264cu_lookahead_t *la, int slot, int b_minu
 /* cost_est / cost_est_aq / intra_mbs as memoised on the host side (i_cost_est[18][18] etc.); -1 = not computed */
 int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int b_minus_p0, int p1_minus_b,
                                    int *cost_est, int *cost_est_aq, int *intra_mbs );
+/* the luma weight x264_weights_analyse left in fenc->weight[0][0] (slicetype.c:284-501, common/mc.h:30-46) when this
+ * slot's picture was last costed as a P frame: out[4] = { enabled, i_scale, i_denom, i_offset } */
+int x264cu_lookahead_get_weight( x264cu_lookahead_t *la, int slot, int *out4 );
 int x264cu_lookahead_get_lowres_plane( x264cu_lookahead_t *la, int slot, int plane, uint8_t *h_out, intptr_t *stride );
 
 /* ------------------------------------------------------------------------------------------------

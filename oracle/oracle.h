@@ -99,6 +99,7 @@ typedef struct
     int aq_mode;                       /* h->param.rc.i_aq_mode != 0 */
     int do_edges;                      /* mbtree || vbv || tiny frame (slicetype.c:823) */
     int vbv;                           /* row satds requested */
+    int weighted_pred;                 /* h->param.analyse.i_weighted_pred != 0 (incl. X264_WEIGHTP_FAKE, encoder.c:1316) */
 } orc_la_params_t;
 
 typedef struct orc_la_frame orc_la_frame_t;
@@ -118,6 +119,10 @@ struct orc_la_frame
     int cost_est[18][18], cost_est_aq[18][18];
     int intra_mbs[18];
     int b_intra_calculated;
+    uint64_t pixel_sum, pixel_ssd;     /* i_pixel_sum[0] / i_pixel_ssd[0] as left by x264_adaptive_quant_frame (ratecontrol.c:304-415) */
+    int i_frame;
+    orc_weight_t weight;               /* fenc->weight[0][0] after the last lookahead analysis */
+    uint8_t *weighted_buf;             /* fenc->weighted[0]: weighted copy of the reference's padded F plane */
 };
 
 orc_la_frame_t *orc_la_frame_new( const orc_la_params_t *p, const uint8_t *luma, intptr_t luma_stride );

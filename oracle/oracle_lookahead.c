@@ -11,6 +11,7 @@
 #include "oracle.h"
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #define FDEC 32                      /* FDEC_STRIDE, common/common.h:571 */
 #define LOWRES_COST_MASK 0x3fff      /* common/frame.h:107-112 */
@@ -54,6 +55,13 @@ orc_la_frame_t *orc_la_frame_new( const orc_la_params_t *p, const uint8_t *luma,
         f->lowres[i] = f->lowres_buf[i] + ORC_PAD * f->stride_lowres + ORC_PAD;
     }
     orc_frame_init_lowres( src, W16, W16, H16, f->lowres, f->stride_lowres, f->width_lowres, f->lines_lowres );
+    {   /* frame statistics of x264_adaptive_quant_frame (ratecontrol.c:225-233, :405-414): sum and sum of squares over the
+         * mod-16 picture, then ssd = sqr - (sum^2 + N/2)/N */
+        uint64_t sum = 0, sqr = 0, N = (uint64_t)W16 * H16;
+        for( size_t i = 0; i < (size_t)W16 * H16; i++ ) { sum += src[i]; sqr += (uint64_t)src[i] * src[i]; }
+        f->pixel_sum = sum;
+        f->pixel_ssd = sqr - ( sum * sum + N / 2 ) / N;
+    }
     free( src );
     for( int l = 0; l < 2; l++ )
         for( int d = 0; d <= p->bframes; d++ )
@@ -72,6 +80,7 @@ orc_la_frame_t *orc_la_frame_new( const orc_la_params_t *p, const uint8_t *luma,
     memset( f->cost_est, -1, sizeof( f->cost_est ) );
     memset( f->cost_est_aq, -1, sizeof( f->cost_est_aq ) );
     f->intra_cost = calloc( f->mb_count, sizeof(int) );
+    for( int i = 0; i < f->mb_count; i++ ) f->intra_cost[i] = 0xFFFF;     /* memset( i_intra_cost, -1 ), frame.c:288 */
     f->inv_qscale_factor = malloc( f->mb_count * sizeof(uint16_t) );
     for( int i = 0; i < f->mb_count; i++ ) f->inv_qscale_factor[i] = 256;
     return f;
@@ -87,6 +96,7 @@ void orc_la_frame_delete( orc_la_frame_t *f )
         for( int j = 0; j < f->bframes+2; j++ ) { free( f->lowres_costs[i][j] ); free( f->row_satds[i][j] ); }
     free( f->intra_cost );
     free( f->inv_qscale_factor );
+    free( f->weighted_buf );
     free( f );
 }
 
@@ -101,6 +111,7 @@ void orc_la_frame_get( orc_la_frame_t *f, int what, int i, int j, void *out )
         case 3: memcpy( out, f->intra_cost, f->mb_count * sizeof(int) ); break;
         case 4: ((int*)out)[0] = f->cost_est[i][j]; ((int*)out)[1] = f->cost_est_aq[i][j]; ((int*)out)[2] = f->intra_mbs[i]; break;
         case 5: memcpy( out, f->row_satds[i][j], ( f->lines_lowres / 8 ) * sizeof(int) ); break;
+        case 6: ((int*)out)[0] = f->weight.enabled; ((int*)out)[1] = f->weight.scale; ((int*)out)[2] = f->weight.denom; ((int*)out)[3] = f->weight.offset; break;
     }
 }
 void orc_la_frame_set_qscale( orc_la_frame_t *f, const uint16_t *inv_qscale ) { memcpy( f->inv_qscale_factor, inv_qscale, f->mb_count * 2 ); }
@@ -468,6 +479,97 @@ static void la_mb_cost( la_t *L, int mb_x, int mb_y )
         }
     }
     fenc->lowres_costs[b-p0][p1-b][mb_xy] = imin( bcost, LOWRES_COST_MASK ) + ( list_used << LOWRES_COST_SHIFT );
+    if( p0 == p1 )   /* i_intra_cost IS lowres_costs[0][0] (frame.c:287): an I request leaves the clipped value behind */
+        fenc->intra_cost[mb_xy] = fenc->lowres_costs[0][0][mb_xy];
+}
+
+/* ---------------------------------------------------------------- lookahead weightp ---------------- */
+static int ue_bits( unsigned v ) { int n = 0; v++; while( v >> ( n + 1 ) ) n++; return 2*n + 1; }      /* bs_size_ue, bitstream.h:278 */
+static int se_bits( int v ) { int t = 1 - 2*v; if( t < 0 ) t = 2*v; int n = 0; while( t >> ( n + 1 ) ) n++; return 2*n + 1; }   /* bs_size_se */
+
+/* weight_cost_luma, slicetype.c:191-222: per 8x8 block min( mbcmp( weighted ref, fenc ), intra cost ) + header bits */
+static unsigned weight_cost_luma( const orc_la_params_t *p, orc_la_frame_t *fenc, const uint8_t *src, const orc_weight_t *w )
+{
+    unsigned cost = 0;
+    intptr_t stride = fenc->stride_lowres;
+    int i_mb = 0;
+    uint8_t buf[8*8];
+    for( int y = 0; y < fenc->lines_lowres; y += 8 )
+        for( int x = 0; x < fenc->width_lowres; x += 8, i_mb++ )
+        {
+            const uint8_t *s = src + y*stride + x, *f = fenc->lowres[0] + y*stride + x;
+            int cmp;
+            if( w )
+            {
+                orc_mc_weight( buf, 8, s, stride, w, 8, 8 );
+                cmp = p->subpel_refine > 1 ? orc_satd( buf, 8, f, stride, 8, 8 ) : orc_sad( buf, 8, f, stride, 8, 8 );
+            }
+            else
+                cmp = p->subpel_refine > 1 ? orc_satd( s, stride, f, stride, 8, 8 ) : orc_sad( s, stride, f, stride, 8, 8 );
+            /* i_intra_cost aliases the u16 lowres_costs[0][0] array (frame.c:287) */
+            int icost = (uint16_t)fenc->intra_cost[i_mb];
+            cost += cmp < icost ? cmp : icost;
+        }
+    if( w )   /* weight_slice_header_cost, slicetype.c:170-189, one slice, lambda 1 */
+        cost += 10 + ue_bits( w->denom ) * 2 + 2 * ( se_bits( w->scale ) + se_bits( w->offset ) );
+    return cost;
+}
+
+int orc_la_frame_cost( const orc_la_params_t *p, const uint16_t *cost_mv_centre, orc_la_frame_t **frames, int p0, int p1, int b );
+
+/* x264_weights_analyse with b_lookahead = 1, slicetype.c:284-501 (luma only).  Leaves fenc->weight / weighted_buf. */
+static void la_weights_analyse( const orc_la_params_t *p, const uint16_t *cost_mv, orc_la_frame_t *fenc, orc_la_frame_t *ref )
+{
+    const float epsilon = 1.f / 128.f;
+    orc_weight_t none = { 0, 1, 0, 0 };
+    fenc->weight = none;
+    int zero_bias = !ref->pixel_ssd;
+    float fenc_var = fenc->pixel_ssd + zero_bias, ref_var = ref->pixel_ssd + zero_bias;
+    float guess_scale = sqrtf( fenc_var / ref_var );
+    float npix = (float)( ( fenc->lines_lowres * 2 ) * ( fenc->width_lowres * 2 ) );
+    float fenc_mean = (float)( fenc->pixel_sum + zero_bias ) / ( ( fenc->lines_lowres * 2 ) * ( fenc->width_lowres * 2 ) );
+    float ref_mean  = (float)( ref->pixel_sum + zero_bias ) / ( ( fenc->lines_lowres * 2 ) * ( fenc->width_lowres * 2 ) );
+    (void)npix;
+    if( fabsf( ref_mean - fenc_mean ) < 0.5f && fabsf( 1.f - guess_scale ) < epsilon )
+        return;
+    /* weight_get_h264( round( guess_scale * 128 ), 0 ), slicetype.c:64-75 */
+    int denom = 7, scale = (int)round( guess_scale * 128 );
+    while( denom > 0 && scale > 127 ) { denom--; scale >>= 1; }
+    if( scale > 127 ) scale = 127;
+    int mindenom = denom, minscale = scale, minoff = 0, found = 0;
+    if( !fenc->b_intra_calculated )
+    {
+        orc_la_frame_t *one[1] = { fenc };
+        orc_la_frame_cost( p, cost_mv, one, 0, 0, 0 );
+    }
+    const uint8_t *mcbuf = ref->lowres[0];
+    unsigned origscore, minscore;
+    origscore = minscore = weight_cost_luma( p, fenc, mcbuf, NULL );
+    if( !minscore )
+        return;
+    {   /* scale_dist = offset_dist = 0 in the lookahead: exactly one (scale, offset) pair is tried */
+        int cur_scale = minscale;
+        int cur_offset = fenc_mean - ref_mean * cur_scale / ( 1 << mindenom ) + 0.5f;
+        if( cur_offset < -128 || cur_offset > 127 )
+        {
+            cur_offset = clip3( cur_offset, -128, 127 );
+            double v = ( 1 << mindenom ) * ( fenc_mean - cur_offset ) / ref_mean + 0.5f;
+            cur_scale = (int)( v < 0 ? 0 : v > 127 ? 127 : v );
+        }
+        orc_weight_t w = { 1, cur_scale, mindenom, cur_offset };
+        unsigned s = weight_cost_luma( p, fenc, mcbuf, &w );
+        if( s < minscore ) { minscore = s; minscale = cur_scale; minoff = cur_offset; found = 1; }
+    }
+    while( mindenom > 0 && !( minscale & 1 ) ) { mindenom--; minscale >>= 1; }
+    if( !found || ( minscale == 1 << mindenom && minoff == 0 ) || (float)minscore / origscore > 0.998f )
+        return;
+    fenc->weight.enabled = 1; fenc->weight.scale = minscale; fenc->weight.denom = mindenom; fenc->weight.offset = minoff;
+    /* x264_weight_scale_plane over the whole padded reference plane, slicetype.c:489-500 */
+    size_t plane = (size_t)ref->stride_lowres * ( ref->lines_lowres + 2*ORC_PAD );
+    free( fenc->weighted_buf );
+    fenc->weighted_buf = malloc( plane + 64 );
+    orc_mc_weight( fenc->weighted_buf, ref->stride_lowres, ref->lowres_buf[0], ref->stride_lowres, &fenc->weight,
+                   (int)ref->stride_lowres, ref->lines_lowres + 2*ORC_PAD );
 }
 
 /* slicetype_frame_cost with one lookahead thread, encoder/slicetype.c:836-995.  `w` may be NULL. */
@@ -488,6 +590,15 @@ int orc_la_frame_cost_w( const orc_la_params_t *p, const uint16_t *cost_mv_centr
     if( L.do_search[0] )
     {
         if( w && w->enabled && b == p1 ) { L.w = w; L.weighted_plane = weighted_plane; }
+        else if( p->weighted_pred && b == p1 )
+        {   /* slicetype.c:857-864 */
+            la_weights_analyse( p, cost_mv_centre, fenc, frames[p0] );
+            if( fenc->weight.enabled )
+            {
+                L.w = &fenc->weight;
+                L.weighted_plane = fenc->weighted_buf + ORC_PAD * fenc->stride_lowres + ORC_PAD;
+            }
+        }
         fenc->lowres_mvs[0][b-p0-1][0][0] = 0;
     }
     if( L.do_search[1] ) fenc->lowres_mvs[1][p1-b-1][0][0] = 0;

@@ -346,6 +346,11 @@ XREF_API int xref_la_set_frame( void *lav, int idx, const uint8_t *luma, intptr_
     for( int y = 0; y < h->param.i_height; y++ )
         memcpy( f->plane[0] + y*f->i_stride[0], luma + y*luma_stride, h->param.i_width );
     x264_frame_expand_border_mod16( h, f );
+    /* frame statistics the lookahead weight analysis reads (i_pixel_sum / i_pixel_ssd), exactly as the encoder fills them
+     * before x264_frame_init_lowres (encoder.c:3417); chroma is flat 128 */
+    for( int y = 0; y < f->i_lines[1]; y++ )
+        memset( f->plane[1] + y*f->i_stride[1], 128, f->i_width[1] );
+    x264_adaptive_quant_frame( h, f, NULL );
     x264_frame_init_lowres( h, f );
     f->b_intra_calculated = 0;
     f->i_frame = idx;
@@ -384,6 +389,8 @@ XREF_API void xref_la_get( void *lav, int idx, int what, int i, int j, void *out
         case 3: for( int k = 0; k < n; k++ ) ((int*)out)[k] = f->i_intra_cost[k]; break;
         case 4: ((int*)out)[0] = f->i_cost_est[i][j]; ((int*)out)[1] = f->i_cost_est_aq[i][j]; ((int*)out)[2] = f->i_intra_mbs[i]; break;
         case 5: memcpy( out, f->i_row_satds[i][j], h->mb.i_mb_height * sizeof(int) ); break;
+        case 6: ((int*)out)[0] = !!f->weight[0][0].weightfn; ((int*)out)[1] = f->weight[0][0].i_scale;
+                ((int*)out)[2] = f->weight[0][0].i_denom; ((int*)out)[3] = f->weight[0][0].i_offset; break;
     }
 }
 

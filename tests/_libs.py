@@ -192,7 +192,7 @@ def make_ref_planes(luma, stride=None):
 
 class OrcLaParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("width", "height", "mb_width", "mb_height", "subpel_refine", "me_method", "me_range",
-                                       "mv_range", "bframes", "bframe_bias", "weighted_bipred", "aq_mode", "do_edges", "vbv")]
+                                       "mv_range", "bframes", "bframe_bias", "weighted_bipred", "aq_mode", "do_edges", "vbv", "weighted_pred")]
 
 
 def _bind_la():
@@ -230,6 +230,7 @@ def la_params_from_ref(hnd, width, height):
     p.aq_mode = int(g("aq_mode") != 0)
     p.vbv = int(g("vbv") != 0)
     p.do_edges = int(g("mbtree") != 0 or g("vbv") != 0)
+    p.weighted_pred = int(g("weightp") != 0)
     return p
 
 

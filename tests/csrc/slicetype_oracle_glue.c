@@ -27,6 +27,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *q
     la->p.mv_range = q->mv_range; la->p.bframes = q->bframes; la->p.bframe_bias = q->bframe_bias;
     la->p.weighted_bipred = q->weighted_bipred; la->p.aq_mode = q->aq_mode; la->p.vbv = q->vbv;
     la->p.do_edges = q->mb_tree || q->vbv;
+    la->p.weighted_pred = q->weighted_pred;
     la->n_slots = q->n_slots;
     la->slots = calloc( q->n_slots, sizeof( void * ) );
     la->tab_len = 2 * 4 * q->mv_range;

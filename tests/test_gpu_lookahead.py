@@ -23,6 +23,10 @@ CONFIGS = [
     (64, 48, 0, 0, 16, 2, 1, 0, 0, 0),
     (80, 64, 7, 1, 16, 3, 1, 1, 1, 1),
     (352, 288, 7, 1, 16, 3, 1, 1, 1, 0),
+    # an 11th field = weighted_pred: the lookahead weight analysis (slicetype.c:284-501) on a fade
+    (112, 80, 7, 1, 16, 3, 1, 1, 1, 0, 1),
+    (96, 64, 2, 1, 16, 2, 1, 0, 0, 0, 1),
+    (176, 144, 7, 2, 16, 3, 1, 1, 1, 0, 1),
 ]
 
 
@@ -35,8 +39,9 @@ def ctx():
 
 
 def oracle_params(cfg, mv_range=512):
-    w, h, subme, me, merange, bframes, weightb, aq, mbtree, vbv = cfg
+    w, h, subme, me, merange, bframes, weightb, aq, mbtree, vbv = cfg[:10]
     p = OrcLaParams()
+    p.weighted_pred = cfg[10] if len(cfg) > 10 else 0
     p.width, p.height = w, h
     p.mb_width, p.mb_height = (w + 15) // 16, (h + 15) // 16
     p.subpel_refine, p.me_method, p.me_range, p.mv_range = subme, me, merange, mv_range
@@ -47,17 +52,21 @@ def oracle_params(cfg, mv_range=512):
 
 @pytest.mark.parametrize("cfg", CONFIGS)
 def test_frame_cost_matches_oracle(ctx, cfg):
-    w, h, subme, me, merange, bframes, weightb, aq, mbtree, vbv = cfg
+    w, h, subme, me, merange, bframes, weightb, aq, mbtree, vbv = cfg[:10]
     o = oracle()
     p = oracle_params(cfg)
     nfr = 6
     frames = synth_sequence(w, h, nfr, seed=w + h, cut_at=4)
+    if p.weighted_pred:
+        frames = [np.clip(f.astype(np.float32) * (0.55 + 0.09 * i) + 3 * i, 0, 255).astype(np.uint8) for i, f in enumerate(frames)]
+    weights_seen = []
     n = 2 * 4 * p.mv_range
     tab = np.zeros(2 * n + 1, np.uint16)
     o.orc_cost_mv_table(tab, n, 1)
     rng = np.random.default_rng(1)
     la = x.Lookahead(ctx, w, h, subpel_refine=subme, me_method=me, me_range=merange, mv_range=p.mv_range, bframes=bframes,
-                     weighted_bipred=weightb, aq_mode=aq, mb_tree=mbtree, vbv=vbv, n_slots=nfr)
+                     weighted_bipred=weightb, aq_mode=aq, mb_tree=mbtree, vbv=vbv, n_slots=nfr,
+                     weighted_pred=p.weighted_pred)
     ofr = (C.c_void_p * (nfr + 2))()
     try:
         for i, f in enumerate(frames):
@@ -85,6 +94,12 @@ def test_frame_cost_matches_oracle(ctx, cfg):
             s_gpu = la.frame_cost(slots, p0, p1, b)
             s_orc = o.orc_la_frame_cost(C.byref(p), tab.ctypes.data + 2 * n, ofr, p0, p1, b)
             tag = (cfg, p0, p1, b)
+            if p.weighted_pred and b == p1 and p0 != p1:
+                w2 = np.zeros(4, np.int32)
+                o.orc_la_frame_get(ofr[b], 6, 0, 0, ptr(w2))
+                assert la.get_weight(b) == tuple(w2), (tag, "weights", la.get_weight(b), w2)
+                if w2[0]:
+                    weights_seen.append(tuple(w2))
             # vectors / vector costs of every searched list
             for l in range(2 if bframes else 1):
                 for d in range(bframes + 1):
@@ -118,6 +133,8 @@ def test_frame_cost_matches_oracle(ctx, cfg):
                 o.orc_la_frame_get(ofr[b], 5, b - p0, p1 - b, ptr(r2))
                 assert np.array_equal(la.get_row_satds(b, b - p0, p1 - b), r2), (tag, "row_satds")
             assert s_gpu == s_orc, (tag, "score", s_gpu, s_orc)
+        if p.weighted_pred:
+            assert weights_seen, "the fade should have produced at least one weighted P search"
     finally:
         for i in range(nfr):
             if ofr[i]:

@@ -25,6 +25,9 @@ def test_gpu_frame_types(ctx, case):
     if cut is not None and n > cut + 9:
         frames[cut + 7] = np.full_like(frames[0], 235)
         frames[cut + 8] = np.full_like(frames[0], 235)
+    if cut is not None:
+        for i in range(min(10, cut)):
+            frames[i] = np.clip(frames[i].astype(np.float32) * (0.35 + 0.065 * i) + 2 * i, 0, 255).astype(np.uint8)
     if not have_ref():
         pytest.skip("compiled reference did not travel")
     p, want = host.reference_types(preset, opts, w, h, frames)
@@ -33,7 +36,7 @@ def test_gpu_frame_types(ctx, case):
                      frame_reference=p.frame_reference, rc_cqp=0,
                      subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
                      bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
-                     aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0)
+                     aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0, weighted_pred=p.la.weighted_pred)
     try:
         got = st.decide(frames)
     finally:

@@ -51,11 +51,14 @@ def compare_frame(r, la, of, idx, p, tag, written):
 
 
 CONFIGS = [
-    ("medium", "weightp=0:bframes=3", (112, 80)),
+    ("medium", "bframes=3", (112, 80)),                                  # default weightp=2 + mb-tree + psy
+    ("medium", "weightp=1:bframes=2:subme=1", (96, 64)),
+    ("medium", "weightp=0:bframes=3", (112, 80)),                        # X264_WEIGHTP_FAKE (encoder.c:1316-1317)
     ("medium", "weightp=0:bframes=3:subme=1:no-mbtree=1", (112, 80)),
     ("medium", "weightp=0:bframes=4:me=umh:merange=24:aq-mode=0", (96, 96)),
     ("medium", "weightp=0:bframes=3:me=dia:weightb=0:no-mbtree=1", (100, 60)),
     ("ultrafast", "bframes=2", (64, 48)),
+    ("medium", "no-mbtree=1:bframes=2:subme=2:aq-mode=0", (96, 64)),      # weights analysis with border MBs never costed
     ("medium", "weightp=0:bframes=3:vbv-maxrate=1000:vbv-bufsize=1000", (80, 64)),
 ]
 
@@ -71,6 +74,9 @@ def test_frame_cost_matches_reference(cfg):
         p = la_params_from_ref(hnd, w, h)
         nfr = 6
         frames = synth_sequence(w, h, nfr, seed=w + h, cut_at=4)
+        if p.weighted_pred:
+            # a fade: the lookahead weight analysis (slicetype.c:284-501) must find (and both sides agree on) weights
+            frames = [np.clip(f.astype(np.float32) * (0.55 + 0.09 * i) + 3 * i, 0, 255).astype(np.uint8) for i, f in enumerate(frames)]
         n = 2 * 4 * p.mv_range
         tab = np.zeros(2 * n + 1, np.uint16)
         r.xref_cost_mv_table(hnd, tab, n)
@@ -84,17 +90,26 @@ def test_frame_cost_matches_reference(cfg):
             o.orc_la_frame_set_qscale(ofr[i], q)
         reqs = [q for q in REQUESTS if q[1] < nfr and q[1] - q[0] <= p.bframes + 1]
         written = {i: set() for i in range(nfr)}
+        weights_seen = []
         for (p0, p1, b) in reqs:
             if not (p0 == p1 and written[b]):      # an I request after any other request is a memo hit: nothing is written
                 written[b].add((b - p0, p1 - b))
             s1 = r.xref_la_frame_cost(la, p0, p1, b)
             s2 = o.orc_la_frame_cost(C.byref(p), tab.ctypes.data + 2 * n, ofr, p0, p1, b)
+            if p.weighted_pred and b == p1 and p0 != p1:
+                w1 = np.zeros(4, np.int32); w2 = np.zeros(4, np.int32)
+                r.xref_la_get(la, b, 6, 0, 0, ptr(w1)); o.orc_la_frame_get(ofr[b], 6, 0, 0, ptr(w2))
+                if w1[0] or w2[0]:
+                    weights_seen.append(tuple(w1))
+                    assert np.array_equal(w1, w2), (cfg, "weights", p0, p1, b, w1, w2)
             assert s1 == s2, (cfg, p0, p1, b, s1, s2)
             compare_frame(r, la, ofr[b], b, p, (cfg, p0, p1, b), written[b])
             if p.vbv:
                 a = np.zeros(p.mb_height, np.int32); bb = np.zeros(p.mb_height, np.int32)
                 r.xref_la_get(la, b, 5, b - p0, p1 - b, ptr(a)); o.orc_la_frame_get(ofr[b], 5, b - p0, p1 - b, ptr(bb))
                 assert np.array_equal(a, bb), (cfg, "row_satds", p0, p1, b)
+        if p.weighted_pred and 'weightp=0' not in opts:
+            assert weights_seen, 'the fade should have produced at least one weighted P search'
         for i in range(nfr):
             o.orc_la_frame_delete(ofr[i])
         r.xref_la_free(la)

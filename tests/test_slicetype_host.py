@@ -12,9 +12,8 @@ from x264_b200.binding_ext import SlicetypeParams, LookaheadParams
 pytestmark = pytest.mark.skipif(not have_ref(), reason="compiled reference not present")
 
 # (preset, options, (w,h), n_frames, cut_at)
-# Weighted-prediction analysis in the lookahead (x264_weights_analyse, slicetype.c:284-501) is not part of this round:
-# the cases switch it off.  NB "weightp=0" alone is not enough: with mb-tree AND psy the encoder turns it back on as
-# X264_WEIGHTP_FAKE (encoder.c:1316-1317), hence no-psy (or no-mbtree) below.
+# NB "weightp=0" alone does not switch the lookahead weight analysis off: with mb-tree AND psy the encoder turns it back on
+# as X264_WEIGHTP_FAKE (encoder.c:1316-1317); no-psy / no-mbtree cases run without it, the last four with it.
 CASES = [
     ("medium", "weightp=0:no-psy=1:bframes=3:rc-lookahead=10:keyint=30:min-keyint=3", (112, 80), 40, 17),
     ("medium", "weightp=0:no-psy=1:bframes=3:b-adapt=2:rc-lookahead=12:keyint=40", (96, 64), 36, 20),
@@ -24,6 +23,11 @@ CASES = [
     ("medium", "weightp=0:no-psy=1:bframes=0:rc-lookahead=5:keyint=25", (64, 64), 30, 11),
     ("slower", "weightp=0:no-psy=1:bframes=3:rc-lookahead=16:keyint=50:me=umh", (96, 80), 30, 13),
     ("medium", "weightp=0:no-mbtree=1:bframes=3:b-adapt=2:rc-lookahead=20:keyint=60", (128, 96), 48, 25),
+    # lookahead weight analysis on (x264_weights_analyse, slicetype.c:284-501): the default preset, fake weights, weightp 1
+    ("medium", "bframes=3:rc-lookahead=10:keyint=30:min-keyint=3", (112, 80), 40, 17),
+    ("medium", "weightp=0:bframes=3:rc-lookahead=12", (96, 64), 36, 20),
+    ("medium", "weightp=1:bframes=4:b-adapt=2:rc-lookahead=14", (96, 80), 36, 14),
+    ("slow", "rc-lookahead=16:keyint=50", (128, 96), 40, 19),
 ]
 
 
@@ -31,8 +35,7 @@ def params_from_ref(hnd, w, h):
     r = ref()
     g = lambda n: r.xref_param(hnd, n.encode())
     la = LookaheadParams(w, h, g("subme"), min(g("me"), 2), g("merange"), g("mvrange"), g("bframes"), g("b_bias"), g("weightb"),
-                         int(g("aq_mode") != 0), g("mbtree"), g("vbv"), 0)
-    assert g("weightp") == 0, "the case must leave lookahead weightp analysis off"
+                         int(g("aq_mode") != 0), g("mbtree"), g("vbv"), 0, int(g("weightp") != 0))
     return SlicetypeParams(la, g("keyint_max"), g("keyint_min"), g("scenecut"), g("b_adapt"), g("b_pyramid"), g("lookahead"),
                            g("psy"), g("ref"), 0)
 
@@ -83,6 +86,9 @@ def test_frame_types_match_reference_encoder(case):
     if cut is not None and n > cut + 9:          # a two-frame flash, which must not become a scene cut
         frames[cut + 7] = np.full_like(frames[0], 235)
         frames[cut + 8] = np.full_like(frames[0], 235)
+    if cut is not None:                          # a fade-in over the first pictures: exercises the weight analysis
+        for i in range(min(10, cut)):
+            frames[i] = np.clip(frames[i].astype(np.float32) * (0.35 + 0.065 * i) + 2 * i, 0, 255).astype(np.uint8)
     p, want = reference_types(preset, opts, w, h, frames)
     got = decide_with(slicetype_oracle_lib(), p, frames)
     assert got == want, (case, [x for x in zip(got, want) if x[0] != x[1]][:6])

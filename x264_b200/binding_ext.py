@@ -6,7 +6,7 @@ import numpy as np
 
 class LookaheadParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("width", "height", "subpel_refine", "me_method", "me_range", "mv_range", "bframes",
-                                       "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv", "n_slots")]
+                                       "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv", "n_slots", "weighted_pred")]
 
 
 class MeJob(C.Structure):
@@ -64,6 +64,7 @@ def bind(L):
     L.x264cu_lookahead_get_costs.argtypes = [vp, ci, ci, ci, vp]
     L.x264cu_lookahead_get_intra.argtypes = [vp, ci, vp]
     L.x264cu_lookahead_get_row_satds.argtypes = [vp, ci, ci, ci, vp]
+    L.x264cu_lookahead_get_weight.argtypes = [vp, ci, C.POINTER(ci)]
     L.x264cu_lookahead_get_cost_est.argtypes = [vp, ci, ci, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
     L.x264cu_lookahead_get_lowres_plane.argtypes = [vp, ci, ci, vp, C.POINTER(ss)]
 
@@ -73,11 +74,11 @@ class Lookahead:
     encoder/slicetype-cl.c) as one object: frame_put() == lowres_init, frame_cost() == slicetype_frame_cost."""
 
     def __init__(self, ctx, width, height, subpel_refine=7, me_method=1, me_range=16, mv_range=512, bframes=3,
-                 bframe_bias=0, weighted_bipred=1, aq_mode=1, mb_tree=1, vbv=0, n_slots=8):
+                 bframe_bias=0, weighted_bipred=1, aq_mode=1, mb_tree=1, vbv=0, n_slots=8, weighted_pred=0):
         self.ctx = ctx
         self.L = ctx.L
         self.p = LookaheadParams(width, height, subpel_refine, me_method, me_range, mv_range, bframes, bframe_bias,
-                                 weighted_bipred, aq_mode, mb_tree, vbv, n_slots)
+                                 weighted_bipred, aq_mode, mb_tree, vbv, n_slots, weighted_pred)
         h = C.c_void_p()
         ctx.check(self.L.x264cu_lookahead_open(ctx.h, C.byref(self.p), C.byref(h)))
         self.h = h
@@ -142,6 +143,11 @@ class Lookahead:
         self.ctx.check(self.L.x264cu_lookahead_get_cost_est(self.h, slot, i0, i1, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def get_weight(self, slot):
+        w = (C.c_int * 4)()
+        self.ctx.check(self.L.x264cu_lookahead_get_weight(self.h, slot, w))
+        return tuple(w)
+
     def get_lowres_plane(self, slot, plane):
         st = C.c_ssize_t()
         self.ctx.check(self.L.x264cu_lookahead_get_lowres_plane(self.h, slot, plane, None, C.byref(st)))
@@ -159,10 +165,10 @@ class Slicetype:
                  rc_lookahead=40, psy=1, frame_reference=3, rc_cqp=0, **la_kwargs):
         self.ctx, self.L = ctx, ctx.L
         la = dict(subpel_refine=7, me_method=1, me_range=16, mv_range=512, bframes=3, bframe_bias=0, weighted_bipred=1,
-                  aq_mode=1, mb_tree=1, vbv=0, n_slots=0)
+                  aq_mode=1, mb_tree=1, vbv=0, n_slots=0, weighted_pred=0)
         la.update(la_kwargs)
         lp = LookaheadParams(width, height, la["subpel_refine"], la["me_method"], la["me_range"], la["mv_range"], la["bframes"],
-                             la["bframe_bias"], la["weighted_bipred"], la["aq_mode"], la["mb_tree"], la["vbv"], la["n_slots"])
+                             la["bframe_bias"], la["weighted_bipred"], la["aq_mode"], la["mb_tree"], la["vbv"], la["n_slots"], la["weighted_pred"])
         self.p = SlicetypeParams(lp, keyint_max, keyint_min, scenecut_threshold, b_adapt, b_pyramid, rc_lookahead, psy,
                                  frame_reference, rc_cqp)
         h = C.c_void_p()

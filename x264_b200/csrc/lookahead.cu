@@ -53,9 +53,11 @@ struct LaSearchJob
     int16_t *mvs;                    // [mb_count][2]
     int32_t *mv_costs;
     int32_t *progress;               // [mb_h], preset to mb_w (nothing done)
+    const uint8_t *ref_w;            // weighted full-pel plane (origin) or NULL
+    int w_enabled, w_scale, w_denom, w_offset;
 };
 
-#define LA_PACK 48
+#define LA_PACK 40
 struct LaJobPack { LaSearchJob j[LA_PACK]; };     // passed by value as a kernel parameter: no staging copy, no sync
 
 struct LaFinalizeArgs
@@ -65,7 +67,7 @@ struct LaFinalizeArgs
     const int16_t *mvs0, *mvs1;      // this frame's vectors for the two lists (mvs1 NULL for P)
     const int32_t *cost0, *cost1;
     const int16_t *mvr;              // fref1's L0 vectors at distance p1-p0 (temporal direct) or NULL
-    const int32_t *intra;
+    int32_t *intra;
     const uint16_t *qscale;
     uint16_t *costs;                 // lowres_costs[b-p0][p1-b]
     int32_t *row_inter, *row_intra;  // row_satds slots
@@ -288,10 +290,10 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
         load_quad( job.fenc + pel + qy * d.stride + qx, d.stride, m.fenc );
 #pragma unroll
         for( int i = 0; i < 4; i++ ) m.fref[i] = job.ref[i] + pel + qy * d.stride + qx;
-        m.fref_w = m.fref[0];
+        m.fref_w = job.ref_w ? job.ref_w + pel + qy * d.stride + qx : m.fref[0];
         m.stride = d.stride;
         m.cost_mv = cost_mv;
-        m.w.enabled = 0; m.w.scale = m.w.denom = m.w.offset = 0;
+        m.w.enabled = job.w_enabled; m.w.scale = job.w_scale; m.w.denom = job.w_denom; m.w.offset = job.w_offset;
         m.satd = d.subme > 1;
         m.min_spel_x = max( 4*( -8*mb_x - 12 ), -mv_range );
         m.max_spel_x = min( 4*( 8*( d.mb_w - mb_x - 1 ) + 12 ), mv_range - 1 );
@@ -497,7 +499,73 @@ finalize_kernel( LaDims d, LaFinalizeArgs A )
         if( A.b_inter ) atomicAdd( &A.row_inter[mb_y], bcost_aq );
         atomicAdd( &A.row_intra[mb_y], icost_aq );
         A.costs[mb] = (uint16_t)( min( bcost, LOWRES_COST_MASK ) + ( list_used << LOWRES_COST_SHIFT ) );
+        // i_intra_cost IS lowres_costs[0][0] in the reference (frame.c:287): an I request leaves the clipped value behind
+        if( !A.b_inter ) A.intra[mb] = min( bcost, LOWRES_COST_MASK );
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lookahead weighted prediction (slicetype.c:284-501, luma, b_lookahead = 1)
+// ------------------------------------------------------------------------------------------------
+// frame statistics of x264_adaptive_quant_frame (ratecontrol.c:225-233): sum and sum of squares over the mod-16 picture
+__global__ void __launch_bounds__( 256 )
+luma_stats_kernel( const uint8_t *__restrict__ src, intptr_t stride, int width, int height, int w16, int h16, unsigned long long *out )
+{
+    unsigned long long sum = 0, sqr = 0;
+    const int groups = w16 / 4;
+    for( int i = blockIdx.x * blockDim.x + threadIdx.x; i < groups * h16; i += gridDim.x * blockDim.x )
+    {
+        int y = i / groups, x = ( i - y * groups ) * 4;
+        const uint8_t *row = src + (intptr_t)min( y, height - 1 ) * stride;
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
+        {
+            unsigned v = row[min( x + k, width - 1 )];
+            sum += v; sqr += v * v;
+        }
+    }
+    for( int m = 16; m; m >>= 1 )
+    {
+        sum += __shfl_xor_sync( 0xffffffffu, sum, m );
+        sqr += __shfl_xor_sync( 0xffffffffu, sqr, m );
+    }
+    if( ( threadIdx.x & 31 ) == 0 ) { atomicAdd( &out[0], sum ); atomicAdd( &out[1], sqr ); }
+}
+
+// weight_cost_luma, slicetype.c:191-222 (without the header bits): sum over MBs of min( mbcmp( w(ref), fenc ), intra )
+__global__ void __launch_bounds__( 256 )
+weight_cost_kernel( LaDims d, const uint8_t *__restrict__ fenc, const uint8_t *__restrict__ ref, const int32_t *__restrict__ intra,
+                    LaWeight w, unsigned int *out )
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane & 3;
+    const int mb = ( blockIdx.x * 8 + warp ) * 8 + ( lane >> 2 );
+    const bool valid = mb < d.mb_count;
+    const int mbc = valid ? mb : d.mb_count - 1;
+    const int mb_y = mbc / d.mb_w, mb_x = mbc - mb_y * d.mb_w;
+    const int pel = ( mb_y * 8 + ( q >> 1 ) * 4 ) * d.stride + mb_x * 8 + ( q & 1 ) * 4;
+    uint32_t a[4], b[4];
+    load_quad( fenc + pel, d.stride, a );
+    load_quad( ref + pel, d.stride, b );
+    if( w.enabled )
+    {
+#pragma unroll
+        for( int r = 0; r < 4; r++ ) b[r] = weight4( b[r], w );
+    }
+    int cmp = quad_sum( d.subme > 1 ? satd4x4( b, a ) : sad4x4( b, a ) );
+    int icost = (int)(uint16_t)intra[mbc];                  // i_intra_cost is a u16 array in the reference (frame.h:135)
+    // border MBs are never costed without do_edges: their i_intra_cost keeps its initial 0xFFFF (frame.c:288)
+    if( !d.do_edges && ( mb_x == 0 || mb_y == 0 || mb_x == d.mb_w - 1 || mb_y == d.mb_h - 1 ) ) icost = 0xFFFF;
+    int v = ( valid && q == 0 ) ? min( cmp, icost ) : 0;
+    v = __reduce_add_sync( 0xffffffffu, v );
+    if( lane == 0 && v ) atomicAdd( out, (unsigned int)v );
+}
+
+// x264_weight_scale_plane over a whole padded plane (slicetype.c:489-500, frame.c:825-841)
+__global__ void __launch_bounds__( 256 )
+weight_plane_kernel( const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t n_words, LaWeight w )
+{
+    for( size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x )
+        dst[i] = weight4( src[i], w );
 }
 
 // ================================================================================================
@@ -515,6 +583,10 @@ struct LaSlotHost
     bool row_satds_valid[LA_MAX_B + 2][LA_MAX_B + 2];
     bool searched[2][LA_MAX_B + 1];  // the 0x7FFF sentinel of lowres_mvs[l][d][0][0], kept on the host
     int pending[2][LA_MAX_B + 1];    // event index of a prefetched search still in flight on the search stream, or -1
+    unsigned long long *d_stats;     // {sum, sum of squares} of the mod-16 luma
+    unsigned long long pixel_sum, pixel_ssd;   // i_pixel_sum[0] / i_pixel_ssd[0] (ratecontrol.c:405-414), valid once stats_ready
+    bool stats_ready;
+    LaWeight weight;                 // fenc->weight[0][0] of the last lookahead analysis
 };
 
 struct x264cu_lookahead
@@ -537,6 +609,8 @@ struct x264cu_lookahead
     cudaEvent_t ev_main = nullptr;
     int last_prefetch_ev = -1;
     uint16_t *h_qscale = nullptr;
+    uint8_t *d_weight_plane = nullptr;   // h->mb.p_weight_buf[0]: weighted copy of one reference F plane (padded)
+    unsigned long long *h_stats = nullptr;
 };
 
 static int la_stride_lowres( int wl )
@@ -558,9 +632,10 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     for( auto &s : la->slots )
     {
         cudaFree( s.plane_buf ); cudaFree( s.dev.mvs ); cudaFree( s.dev.mv_costs ); cudaFree( s.dev.costs );
-        cudaFree( s.dev.intra ); cudaFree( s.dev.qscale ); cudaFree( s.dev.row_satds ); cudaFree( s.dev.progress );
+        cudaFree( s.dev.intra ); cudaFree( s.dev.qscale ); cudaFree( s.dev.row_satds ); cudaFree( s.dev.progress ); cudaFree( s.d_stats );
     }
-    cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record );
+    cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record ); cudaFree( la->d_weight_plane );
+    cudaFreeHost( la->h_stats );
     cudaFreeHost( la->h_luma ); cudaFreeHost( la->h_record ); cudaFreeHost( la->h_qscale );
     if( la->search_stream ) { cudaStreamSynchronize( la->search_stream ); cudaStreamDestroy( la->search_stream ); }
     for( int i = 0; i < la->n_ev; i++ ) cudaEventDestroy( la->ev[i] );
@@ -615,11 +690,15 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         alloc( (void **)&s.dev.qscale, (size_t)d.mb_count * 2 );
         alloc( (void **)&s.dev.row_satds, (size_t)B2 * d.mb_h * 4 );
         alloc( (void **)&s.dev.progress, (size_t)2 * B1 * d.mb_h * 4 );
+        s.d_stats = nullptr;
+        alloc( (void **)&s.d_stats, 16 );
     }
     la->luma_bytes = (size_t)( ( p->width + 63 ) & ~63 ) * p->height + 64;
     alloc( (void **)&la->d_luma, la->luma_bytes );
     alloc( (void **)&la->d_cost_mv, ( 2 * d.cost_len + 1 ) * 2 + 16 );
     alloc( (void **)&la->d_record, 64 );
+    alloc( (void **)&la->d_weight_plane, la->plane_bytes );
+    if( ok && cudaMallocHost( (void **)&la->h_stats, 16 ) != cudaSuccess ) ok = false;
     if( cudaStreamCreateWithFlags( &la->search_stream, cudaStreamNonBlocking ) != cudaSuccess ) ok = false;
     for( int i = 0; ok && i < 64; i++ )
     {
@@ -671,6 +750,8 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
     s.b_intra_calculated = 0;
     s.intra_on_device = false;
     s.in_use = true;
+    s.stats_ready = false;
+    s.weight.enabled = 0; s.weight.scale = 1; s.weight.denom = 0; s.weight.offset = 0;
     CU_CHECK( ctx, cudaMemsetAsync( s.dev.mvs, 0, (size_t)2 * ( d.B + 1 ) * d.mb_count * 4, ctx->stream ) );
     if( h_inv_qscale )
     {
@@ -697,6 +778,13 @@ int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const u
     if( la->last_prefetch_ev >= 0 )
         CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, la->ev[la->last_prefetch_ev], 0 ) );
     if( x264cu_frame_init_lowres( la->ctx, d_luma, luma_stride, la->p.width, la->p.height, s.dev.planes, la->d.stride ) ) return -1;
+    if( la->p.weighted_pred )
+    {
+        CU_CHECK( la->ctx, cudaMemsetAsync( s.d_stats, 0, 16, la->ctx->stream ) );
+        luma_stats_kernel<<<la->ctx->sm_count * 2, 256, 0, la->ctx->stream>>>( d_luma, luma_stride, la->p.width, la->p.height,
+                                                                               la->d.mb_w * 16, la->d.mb_h * 16, s.d_stats );
+        CU_LAUNCH_CHECK( la->ctx );
+    }
     return la_reset_slot( la, slot, h_inv_qscale );
 }
 
@@ -748,6 +836,8 @@ static void la_fill_job( x264cu_lookahead *la, LaSearchJob &j, int fenc_slot, in
     j.mvs = f.dev.mvs + idx * d.mb_count * 2;
     j.mv_costs = f.dev.mv_costs + idx * d.mb_count;
     j.progress = f.dev.progress + idx * d.mb_h;
+    j.ref_w = nullptr;
+    j.w_enabled = 0; j.w_scale = 1; j.w_denom = 0; j.w_offset = 0;
 }
 
 static int la_reset_progress( x264cu_lookahead *la, const LaSearchJob &j, cudaStream_t stream )
@@ -812,6 +902,97 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
     return 0;
 }
 
+static int ue_bits( unsigned v ) { int n = 0; v++; while( v >> ( n + 1 ) ) n++; return 2*n + 1; }       /* bs_size_ue */
+static int se_bits( int v ) { int t = 1 - 2*v; if( t < 0 ) t = 2*v; int n = 0; while( t >> ( n + 1 ) ) n++; return 2*n + 1; }  /* bs_size_se */
+
+static int la_fetch_stats( x264cu_lookahead *la, LaSlotHost &s )
+{
+    if( s.stats_ready ) return 0;
+    x264cu_ctx *ctx = la->ctx;
+    CU_CHECK( ctx, cudaMemcpyAsync( la->h_stats, s.d_stats, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
+    CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
+    const unsigned long long sum = la->h_stats[0], sqr = la->h_stats[1];
+    const unsigned long long N = (unsigned long long)( la->d.mb_w * 16 ) * ( la->d.mb_h * 16 );
+    s.pixel_sum = sum;
+    s.pixel_ssd = sqr - ( sum * sum + N / 2 ) / N;                   /* ratecontrol.c:405-414 */
+    s.stats_ready = true;
+    return 0;
+}
+
+static int la_weight_cost( x264cu_lookahead *la, LaSlotHost &fenc, LaSlotHost &ref, const LaWeight &w, unsigned *out )
+{
+    x264cu_ctx *ctx = la->ctx;
+    const LaDims &d = la->d;
+    unsigned int *d_acc = (unsigned int *)( la->d_record + 8 );
+    CU_CHECK( ctx, cudaMemsetAsync( d_acc, 0, 4, ctx->stream ) );
+    weight_cost_kernel<<<( d.mb_count + 63 ) / 64, 256, 0, ctx->stream>>>( d, fenc.dev.planes[0], ref.dev.planes[0], fenc.dev.intra, w, d_acc );
+    CU_LAUNCH_CHECK( ctx );
+    CU_CHECK( ctx, cudaMemcpyAsync( la->h_record + 8, d_acc, 4, cudaMemcpyDeviceToHost, ctx->stream ) );
+    CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
+    unsigned c = (unsigned)la->h_record[8];
+    if( w.enabled )                /* weight_slice_header_cost, slicetype.c:170-189: one slice, lambda 1 */
+        c += 10 + ue_bits( w.denom ) * 2 + 2 * ( se_bits( w.scale ) + se_bits( w.offset ) );
+    *out = c;
+    return 0;
+}
+
+/* x264_weights_analyse( h, fenc, ref, b_lookahead = 1 ), slicetype.c:284-501: luma only; the float expressions are the
+ * reference's.  On success fenc.weight holds the weight (enabled = 0: none) and la->d_weight_plane the weighted plane. */
+static int la_weights_analyse( x264cu_lookahead *la, int fenc_slot, int ref_slot )
+{
+    x264cu_ctx *ctx = la->ctx;
+    LaSlotHost &fenc = la->slots[fenc_slot], &ref = la->slots[ref_slot];
+    const LaDims &d = la->d;
+    fenc.weight.enabled = 0; fenc.weight.scale = 1; fenc.weight.denom = 0; fenc.weight.offset = 0;
+    if( la_fetch_stats( la, fenc ) || la_fetch_stats( la, ref ) ) return -1;
+    const float epsilon = 1.f / 128.f;
+    const int zero_bias = !ref.pixel_ssd;
+    const float fenc_var = fenc.pixel_ssd + zero_bias, ref_var = ref.pixel_ssd + zero_bias;
+    const float guess_scale = sqrtf( fenc_var / ref_var );
+    const int npix = ( d.mb_h * 16 ) * ( d.mb_w * 16 );
+    const float fenc_mean = (float)( fenc.pixel_sum + zero_bias ) / npix;
+    const float ref_mean = (float)( ref.pixel_sum + zero_bias ) / npix;
+    if( fabsf( ref_mean - fenc_mean ) < 0.5f && fabsf( 1.f - guess_scale ) < epsilon )
+        return 0;
+    int denom = 7, scale = (int)round( guess_scale * 128 );               /* weight_get_h264, slicetype.c:64-75 */
+    while( denom > 0 && scale > 127 ) { denom--; scale >>= 1; }
+    if( scale > 127 ) scale = 127;
+    int mindenom = denom, minscale = scale, minoff = 0, found = 0;
+    if( !fenc.b_intra_calculated )
+    {   /* slicetype.c:364-369: an intra-only request on fenc first */
+        int one[1] = { fenc_slot }, sc;
+        if( x264cu_lookahead_frame_cost( la, one, 0, 0, 0, &sc ) ) return -1;
+    }
+    LaWeight none; none.enabled = 0; none.scale = 1; none.denom = 0; none.offset = 0;
+    unsigned origscore, minscore;
+    if( la_weight_cost( la, fenc, ref, none, &origscore ) ) return -1;
+    minscore = origscore;
+    if( !minscore )
+        return 0;
+    {   /* scale_dist = offset_dist = 0 in the lookahead: one (scale, offset) pair */
+        int cur_scale = minscale;
+        int cur_offset = fenc_mean - ref_mean * cur_scale / ( 1 << mindenom ) + 0.5f;
+        if( cur_offset < -128 || cur_offset > 127 )
+        {
+            cur_offset = cur_offset < -128 ? -128 : 127;
+            double v = ( 1 << mindenom ) * ( fenc_mean - cur_offset ) / ref_mean + 0.5f;
+            cur_scale = (int)( v < 0 ? 0 : v > 127 ? 127 : v );
+        }
+        LaWeight w; w.enabled = 1; w.scale = cur_scale; w.denom = mindenom; w.offset = cur_offset;
+        unsigned s;
+        if( la_weight_cost( la, fenc, ref, w, &s ) ) return -1;
+        if( s < minscore ) { minscore = s; minscale = cur_scale; minoff = cur_offset; found = 1; }
+    }
+    while( mindenom > 0 && !( minscale & 1 ) ) { mindenom--; minscale >>= 1; }
+    if( !found || ( minscale == 1 << mindenom && minoff == 0 ) || (float)minscore / origscore > 0.998f )
+        return 0;
+    fenc.weight.enabled = 1; fenc.weight.scale = minscale; fenc.weight.denom = mindenom; fenc.weight.offset = minoff;
+    const size_t words = ( (size_t)d.stride * ( la->ll + 2 * X264CU_PAD ) + 128 ) / 4;
+    weight_plane_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>( (const uint32_t *)( ref.plane_buf ), (uint32_t *)la->d_weight_plane, words, fenc.weight );
+    CU_LAUNCH_CHECK( ctx );
+    return 0;
+}
+
 int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
 {
     if( !la || !frames || !score ) return -1;
@@ -834,8 +1015,19 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
     int n = 0;
     if( b != p0 && !fenc.searched[0][i0 - 1] )
     {
+        if( la->p.weighted_pred && b == p1 )
+        {   /* slicetype.c:857-864: weights are analysed only when this first search of the pair is P-type.  The analysis
+             * may itself issue an intra-only request, which reuses la->pack: run it before the job list is assembled */
+            if( la_weights_analyse( la, sb, s0 ) ) return -1;
+        }
         fenc.searched[0][i0 - 1] = true;
         la_fill_job( la, la->pack.j[n], sb, s0, 0, i0 );
+        if( la->p.weighted_pred && b == p1 && fenc.weight.enabled )
+        {
+            LaSearchJob &j = la->pack.j[n];
+            j.ref_w = la->d_weight_plane + ( la->slots[s0].dev.planes[0] - la->slots[s0].plane_buf );
+            j.w_enabled = 1; j.w_scale = fenc.weight.scale; j.w_denom = fenc.weight.denom; j.w_offset = fenc.weight.offset;
+        }
         if( la_reset_progress( la, la->pack.j[n], ctx->stream ) ) return -1;
         n++;
     }
@@ -938,6 +1130,16 @@ int x264cu_lookahead_get_mvs( x264cu_lookahead_t *la, int slot, int list, int di
     if( h_mv_costs ) CU_CHECK( la->ctx, cudaMemcpyAsync( h_mv_costs, la->slots[slot].dev.mv_costs + idx * d.mb_count, d.mb_count * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
     CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
     if( h_mvs && !la->slots[slot].searched[list][dist_minus1] ) h_mvs[0] = 0x7FFF;      // the reference's sentinel (mc.c:478-480)
+    return 0;
+}
+
+int x264cu_lookahead_get_weight( x264cu_lookahead_t *la, int slot, int *out4 )
+{
+    if( !la || !out4 ) return -1;
+    if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use )
+        return x264cu_fail( la->ctx, "lookahead: slot %d is empty / out of range", slot );
+    const LaWeight &w = la->slots[slot].weight;
+    out4[0] = w.enabled; out4[1] = w.scale; out4[2] = w.denom; out4[3] = w.offset;
     return 0;
 }
 

@@ -669,8 +669,12 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
                 int d = f->i_frame - o->i_frame;
                 if( !s->slot_used[o->slot] || d < 1 || d > s->p.la.bframes + 1 || s->n_pj + 2 > 256 ) continue;
                 int n = s->n_pj;
-                s->pj_fenc[n] = f->slot; s->pj_ref[n] = o->slot; s->pj_list[n] = 0; s->pj_dist[n] = d;
-                s->pj_fframe[n] = f->i_frame; s->pj_rframe[n] = o->i_frame; n++;
+                if( !s->p.la.weighted_pred )
+                {   /* a list-0 search may be weighted if it is first requested as a P cost (slicetype.c:857-864): only
+                     * without weighted prediction is it a pure function of the two pictures */
+                    s->pj_fenc[n] = f->slot; s->pj_ref[n] = o->slot; s->pj_list[n] = 0; s->pj_dist[n] = d;
+                    s->pj_fframe[n] = f->i_frame; s->pj_rframe[n] = o->i_frame; n++;
+                }
                 if( d <= s->p.la.bframes )
                 {
                     s->pj_fenc[n] = o->slot; s->pj_ref[n] = f->slot; s->pj_list[n] = 1; s->pj_dist[n] = d;
