@@ -313,6 +313,7 @@ LA_OPTS = dict(subpel_refine=7, me_method=1, me_range=16, mv_range=512, bframes=
 LA_ST = dict(keyint_max=250, keyint_min=25, scenecut_threshold=40, b_adapt=1, b_pyramid=2, rc_lookahead=40, psy=0,
              frame_reference=3, rc_cqp=0)
 LA_REF_OPTS = b"weightp=0:no-psy=1:aq-mode=0:bframes=3:rc-lookahead=40"          # the same configuration, reference spelling
+LA_REF_OPTS_W = b"weightp=2:aq-mode=0:bframes=3:rc-lookahead=40"                  # --weightp 1: preset medium's own weightp / psy
 # algorithmic bytes of one lowres motion search at WxH: fenc lowres + 4 reference lowres planes + 8 B/MB out
 LA_SEARCH_BYTES = LA_W * LA_H // 4 + LA_W * LA_H + 8 * ((LA_W + 15) // 16) * ((LA_H + 15) // 16)
 
@@ -336,7 +337,7 @@ def make_la_frames(seed, n, alloc):
     return out
 
 
-def cpu_lookahead_rate(frames, budget_s):
+def cpu_lookahead_rate(frames, budget_s, weightp=0):
     """the same decision workload on the host: the product's host slice-type logic over the reference's own
     slicetype_frame_cost (oracle/_ref) -- or over the oracle port if the reference did not travel.  One thread:
     the reference's lookahead with more threads returns different results (slicetype.c:668)."""
@@ -344,12 +345,12 @@ def cpu_lookahead_rate(frames, budget_s):
     from x264_b200.binding_ext import SlicetypeParams, LookaheadParams
     if _libs.have_ref():
         lib, kind = _libs.slicetype_ref_lib(), "reference"
-        lib.slicetype_ref_glue_config(b"medium", LA_REF_OPTS)
+        lib.slicetype_ref_glue_config(b"medium", LA_REF_OPTS_W if weightp else LA_REF_OPTS)
     else:
         lib, kind = _libs.slicetype_oracle_lib(), "port"
     la = LookaheadParams(LA_W, LA_H, *[LA_OPTS[k] for k in ("subpel_refine", "me_method", "me_range", "mv_range", "bframes",
-                                                            "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv")], 0, 0)
-    p = SlicetypeParams(la, *[LA_ST[k] for k in ("keyint_max", "keyint_min", "scenecut_threshold", "b_adapt", "b_pyramid",
+                                                            "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv")], 0, int(weightp))
+    p = SlicetypeParams(la, *[dict(LA_ST, psy=1 if weightp else 0)[k] for k in ("keyint_max", "keyint_min", "scenecut_threshold", "b_adapt", "b_pyramid",
                                                   "rc_lookahead", "psy", "frame_reference", "rc_cqp")])
     lib.x264cu_slicetype_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.x264cu_slicetype_step.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -390,8 +391,10 @@ def run_lookahead_b200(args, rank, world, local, dist):
     d_frames = ctx.malloc(frames.nbytes + 256)
     ctx.h2d(d_frames, frames)
 
+    la_st = dict(LA_ST, psy=1) if args.weightp else LA_ST
+
     def make_st():
-        return x.Slicetype(ctx, LA_W, LA_H, **LA_ST, **LA_OPTS)
+        return x.Slicetype(ctx, LA_W, LA_H, **la_st, **LA_OPTS, weighted_pred=args.weightp)
 
     # ---- device-resident pictures -----------------------------------------------------------------
     st = make_st()
@@ -445,10 +448,10 @@ def run_lookahead_b200(args, rank, world, local, dist):
         for i in range(5):
             la.frame_put_device(i, d_frames + i * LA_W * LA_H, stride)     # resets the memo -> searches run again
         ctx.sync()
-        t1 = time.perf_counter()
-        la.search_batch(jobs)
-        la.get_intra(0)                                                      # synchronises both streams
-        k_ms.append((time.perf_counter() - t1) * 1e3)
+        ctx.timer_start()                                                    # event on the context's stream ...
+        la.search_batch(jobs)                                                # ... which the search stream is ordered after
+        la.join()                                                            # and the context's stream after the searches
+        k_ms.append(ctx.timer_stop())
     la.close()
     search_ms = float(np.median(k_ms))
 
@@ -480,7 +483,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "3840x2160 lowres lookahead + slice-type decision, %d pictures per step per GPU, preset-medium "
                                "lookahead settings (hex, subme 7 -> lookahead subpel 4, bframes 3, b-adapt 1, rc-lookahead 40, "
-                               "mb-tree requests, scenecut 40; weightp analysis off, aq off)" % n,
+                               "mb-tree requests, scenecut 40; lookahead weightp analysis %s, aq off)" % (n, "on" if args.weightp else "off"),
                    "l2": "each picture's 4 lowres planes (9.4 MB) stay L2-resident by design; pictures cycle through %d MB" % (frames.nbytes // 2**20),
                    "cost_requests_per_step": requests / args.steps, "decided_per_step": len(decided) / (args.steps + max(args.warmup, 3)),
                    "scheduling": "searches prefetched on a second stream in groups of 4 pictures, decisions run 8 pictures behind (sync-lookahead twin)",
@@ -496,7 +499,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
         "wall_s": wall, "sm_count": info["sm_count"],
     }
     if rank == 0 and world == 1 and not args.quick:
-        rate, kind, cores, sample, _ = cpu_lookahead_rate(frames, args.cpu_budget)
+        rate, kind, cores, sample, _ = cpu_lookahead_rate(frames, args.cpu_budget, args.weightp)
         res["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
     ctx.close()
     return res
@@ -506,7 +509,7 @@ def run_lookahead_reference(args, rank, world):
     frames = make_la_frames(2160, LA_FRAMES, lambda b: np.empty(b, np.uint8))
     rates = []
     for i in range(args.warmup + args.steps):
-        r, kind, cores, sample, _ = cpu_lookahead_rate(frames, args.cpu_budget / max(1, args.steps))
+        r, kind, cores, sample, _ = cpu_lookahead_rate(frames, args.cpu_budget / max(1, args.steps), args.weightp)
         if i >= args.warmup:
             rates.append(r)
     v = float(np.mean(rates))
@@ -533,6 +536,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--weightp", type=int, default=0, choices=[0, 1], help="lookahead workload: weightp analysis (slicetype.c:284-501) on")
     ap.add_argument("--quick", action="store_true", help="tuning runs: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
 
@@ -546,6 +550,14 @@ def main():
 
     rank, world, local, dist = dist_setup(args.gpus)
     res = WORKLOADS[args.workload or DEFAULT_WORKLOAD][0](args, rank, world, local, dist)
+    if args.workload is None and not args.quick:
+        # the second half of BASELINE.json's metric rides on the same line: 16x16 SATD macroblocks/s vs the HBM roofline
+        a2 = argparse.Namespace(**vars(args))
+        a2.steps, a2.warmup, a2.quick = 20, 3, True
+        sat = run_satd_b200(a2, rank, world, local, dist)
+        res["satd_16x16"] = {k: sat[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "roofline", "e2e", "gpu_launches")}
+        res["satd_16x16"]["workload"] = sat["config"]["workload"]
+        res["satd_16x16"]["parity_spot_check"] = sat["config"]["parity_spot_check"]
     if rank == 0:
         print(json.dumps(res))
     if dist is not None:

@@ -197,6 +197,9 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
  * time does not change any later x264cu_lookahead_frame_cost result.  Already-searched jobs are skipped. */
 int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int *fenc, const int *ref,
                                    const int *list, const int *dist );
+/* x264_opencl_flush without the host block (encoder/slicetype-cl.c:100-127): order the context's stream after every
+ * search queued by x264cu_lookahead_search_batch, so that work (or a timer event) queued next sees them finished */
+int x264cu_lookahead_join( x264cu_lookahead_t *la );
 
 /* read back per-MB results of one slot (the arrays x264_frame_t holds, common/frame.h:97-141) */
 int x264cu_lookahead_get_mvs( x264cu_lookahead_t *la, int slot, int list, int dist_minus1, int16_t *h_mvs, int32_t *h_mv_costs );

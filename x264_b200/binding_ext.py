@@ -60,6 +60,7 @@ def bind(L):
     L.x264cu_lookahead_frame_put_device.argtypes = [vp, ci, vp, ss, vp]
     L.x264cu_lookahead_frame_cost.argtypes = [vp, C.POINTER(ci), ci, ci, ci, C.POINTER(ci)]
     L.x264cu_lookahead_search_batch.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]
+    L.x264cu_lookahead_join.argtypes = [vp]
     L.x264cu_lookahead_get_mvs.argtypes = [vp, ci, ci, ci, vp, vp]
     L.x264cu_lookahead_get_costs.argtypes = [vp, ci, ci, ci, vp]
     L.x264cu_lookahead_get_intra.argtypes = [vp, ci, vp]
@@ -116,6 +117,9 @@ class Lookahead:
         n = len(jobs)
         cols = [(C.c_int * n)(*[j[k] for j in jobs]) for k in range(4)]
         self.ctx.check(self.L.x264cu_lookahead_search_batch(self.h, n, *cols))
+
+    def join(self):
+        self.ctx.check(self.L.x264cu_lookahead_join(self.h))
 
     def get_mvs(self, slot, lst, dist_minus1):
         mv = np.zeros((self.mb_count, 2), np.int16)

@@ -5,7 +5,8 @@
 //   intra_kernel    lowres intra cost of every MB (3 or 10 modes)            -- no dependencies, once per frame
 //   search_kernel   lowres_mvs / lowres_mv_costs of one (frame, list, distance) -- reverse-raster dependency on the
 //                   right / below / below-left / below-right neighbours (slicetype.c:662-680): one warp per MB ROW,
-//                   rows pipelined two MBs apart through per-row progress flags in HBM; many jobs per launch
+//                   rows pipelined two MBs apart through self-validating (generation, mv) records; the reference planes
+//                   are staged in a per-warp sliding shared-memory window (cp.async); many jobs per launch
 //   finalize_kernel bidir candidates, list choice, intra-vs-inter, AQ scaling, row and frame sums, lowres_costs
 //                   -- per-MB parallel once the vectors exist
 // The memoisation / order logic of slicetype_frame_cost (sentinels, do_search, b_intra_calculated) stays on the host,
@@ -43,7 +44,7 @@ struct LaSlotDev
     int32_t *intra;                  // [mb_count]
     uint16_t *qscale;                // [mb_count]
     int32_t *row_satds;              // [(B+2)*(B+2)][mb_h]
-    int32_t *progress;               // [2][B+1][mb_h]
+    unsigned long long *recs;        // [2][B+1][mb_count] (generation << 32 | mv): how the rows of a search hand over vectors
 };
 
 struct LaSearchJob
@@ -52,7 +53,8 @@ struct LaSearchJob
     const uint8_t *ref[4];
     int16_t *mvs;                    // [mb_count][2]
     int32_t *mv_costs;
-    int32_t *progress;               // [mb_h], preset to mb_w (nothing done)
+    unsigned long long *recs;        // [mb_count] self-validating (gen << 32 | mv) records, see search_kernel
+    unsigned int gen;                // the slot's generation: a record is this search's iff its high word equals it
     const uint8_t *ref_w;            // weighted full-pel plane (origin) or NULL
     int w_enabled, w_scale, w_denom, w_offset;
 };
@@ -222,72 +224,125 @@ intra_kernel( LaDims d, const uint8_t *__restrict__ plane, int32_t *__restrict__
 // ------------------------------------------------------------------------------------------------
 // search: one warp = one MB row, rows bottom-up; slicetype.c:654-705 + me.c
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire( const int *p )
+// 64-bit relaxed accesses are single-copy atomic: a record (generation << 32 | mv) is either entirely there or not,
+// so the rows of a search synchronise on the data itself -- no fences, no cache invalidation
+__device__ __forceinline__ unsigned long long ld_relaxed64( const unsigned long long *p )
 {
-    int v;
-    asm volatile( "ld.acquire.gpu.global.s32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
+    unsigned long long v;
+    asm volatile( "ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"( v ) : "l"( p ) : "memory" );
     return v;
 }
-__device__ __forceinline__ void st_release( int *p, int v )
+__device__ __forceinline__ void st_relaxed64( unsigned long long *p, unsigned long long v )
 {
-    asm volatile( "st.release.gpu.global.s32 [%0], %1;" ::"l"( p ), "r"( v ) : "memory" );
+    asm volatile( "st.relaxed.gpu.global.u64 [%0], %1;" ::"l"( p ), "l"( v ) : "memory" );
 }
 
+__device__ __forceinline__ void cp_async16( uint32_t saddr, const void *g )
+{
+    asm volatile( "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"( saddr ), "l"( g ) : "memory" );
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile( "cp.async.wait_all;" ::: "memory" ); }
+
+// One warp per macroblock ROW, rows pipelined two columns apart (the reverse-raster predictor dependency of
+// slicetype.c:658-680).  Work items (row group, job) are handed out by an atomic ticket, row groups first, so that an
+// item only ever waits on items with smaller tickets, i.e. CTAs that are already running -- the grid may be larger than
+// what is resident.  Each warp keeps a sliding shared-memory window of the reference planes (LaWin) fed by cp.async.
 template <int NW>
 __global__ void __launch_bounds__( NW * 32 )
-search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uint16_t *__restrict__ cost_mv_g )
+search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uint16_t *__restrict__ cost_mv_g, int n_jobs,
+               unsigned int *__restrict__ ticket )
 {
-    extern __shared__ uint16_t s_cost[];
+    extern __shared__ __align__( 16 ) uint8_t s_raw[];
+    __shared__ unsigned int s_ticket;
+    uint16_t *s_cost = (uint16_t *)s_raw;
     for( int i = threadIdx.x; i < 2 * d.cost_len + 1; i += blockDim.x ) s_cost[i] = cost_mv_g[i];
+    if( threadIdx.x == 0 ) s_ticket = atomicAdd( ticket, 1u );
     __syncthreads();
     const uint16_t *cost_mv = s_cost + d.cost_len;
-
-    const LaSearchJob &job = jobs.j[blockIdx.y];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared( s_raw ) + ( ( ( 2 * d.cost_len + 1 ) * 2 + 15 ) & ~15 ) + warp * LA_WIN_BYTES;
+
+    const int row_group = s_ticket / n_jobs;
+    const LaSearchJob &job = jobs.j[s_ticket - row_group * n_jobs];
     const int start_y = min( d.mb_h - 1, d.mb_h - 2 + d.do_edges ), end_y = max( 0, 1 - d.do_edges );
     const int start_x = d.mb_w - 2 + d.do_edges, end_x = 1 - d.do_edges;
-    const int mb_y = start_y - ( blockIdx.x * NW + warp );
+    const int mb_y = start_y - ( row_group * NW + warp );
     if( mb_y < end_y ) return;
     const int q = lane & 3, qx = ( q & 1 ) * 4, qy = ( q >> 1 ) * 4;
 
+    // ---- reference window ---------------------------------------------------------------------------
+    const uint8_t *g0 = job.ref_w ? job.ref_w : job.ref[0], *g1 = job.ref[1], *g2 = job.ref[2], *g3 = job.ref[3];
+    const int n_chunks = d.stride >> 4;
+    const int win_row0 = mb_y * 8 - LA_WIN_VR;
+    auto load_chunk = [&]( int k ) {
+#pragma unroll
+        for( int j = 0; j < 4 * LA_WIN_ROWS / 32; j++ )
+        {
+            const int i = lane + 32 * j, p = i / LA_WIN_ROWS, r = i - p * LA_WIN_ROWS;
+            const uint8_t *g = ( p == 0 ? g0 : p == 1 ? g1 : p == 2 ? g2 : g3 ) + (ptrdiff_t)( win_row0 + r ) * d.stride + k * 16 - 64;
+            cp_async16( win_base + p * LA_WIN_PLANE + r * 128 + ( k & 7 ) * 16, g );
+        }
+    };
+    int kc = ( start_x * 8 + 64 ) >> 4;
+    for( int k = max( kc - 3, 0 ); k <= min( kc + 3, n_chunks - 1 ); k++ ) load_chunk( k );
+    cp_async_wait_all();
+    __syncwarp();
+    if( kc - 4 >= 0 ) load_chunk( kc - 4 );
+
     int16_t *mvs = job.mvs;
-    // right neighbour's vector is produced by this warp itself
+    // right neighbour's vector is produced by this warp itself; the never-searched edge column keeps what the frame
+    // reset left there: zeros (frame.c:287-293)
     int right_x = 0, right_y = 0;
-    if( start_x + 1 < d.mb_w )
-    {   // the never-searched edge column keeps whatever the frame reset left there (zeros, frame.c:287-293)
-        const int16_t *e = mvs + 2 * ( mb_y * d.mb_w + start_x + 1 );
-        right_x = e[0]; right_y = e[1];
-    }
     const int mv_range = d.mv_range2;
     for( int mb_x = start_x; mb_x >= end_x; mb_x-- )
     {
         const int mb_xy = mb_y * d.mb_w + mb_x;
-        // wait for the row below to have passed column mb_x-1 (it runs right to left).  Lane 0 acquires the flag and is
-        // the only lane that then reads the neighbours' vectors (broadcast by shuffle): acquire/release, no full fences.
+        LaMe m;
+        const int pel = ( mb_y * 8 ) * d.stride + mb_x * 8;
+        // nothing about fenc depends on the neighbours: have it in flight while the flag is polled
+        load_quad( job.fenc + pel + qy * d.stride + qx, d.stride, m.fenc );
+        {   // slide the window: chunk kc-3 (requested two macroblocks ago) becomes valid, chunk kc-4 is requested
+            const int k = ( mb_x * 8 + 64 ) >> 4;
+            if( k != kc )
+            {
+                kc = k;
+                cp_async_wait_all();
+                __syncwarp();
+                if( kc - 4 >= 0 ) load_chunk( kc - 4 );
+            }
+        }
+        // the vectors below, below-left and below-right come from the warp of the row below (it runs right to left, so
+        // below-left is the last to appear).  Lanes 0..2 poll one record each until it carries this search's generation.
         int nb0 = 0, nb1 = 0, nb2 = 0;                   // below, below-left, below-right
         if( mb_y < d.mb_h - 1 )
         {
-            if( lane == 0 )
+            const int nx = mb_x + ( lane == 1 ? -1 : lane == 2 ? 1 : 0 );
+            // columns / rows outside the searched range are never written: they read as the reset value, zero
+            const bool need = lane < 3 && mb_y + 1 <= start_y && nx >= end_x && nx <= start_x;
+            const unsigned long long *rp = job.recs + ( mb_xy + d.mb_w + ( nx - mb_x ) );
+            unsigned long long r = 0;
+            for( int spins = 0;; )
             {
-                if( mb_y + 1 <= start_y )
-                {
-                    const int need = max( mb_x - 1, end_x );
-                    int spins = 0;
-                    while( ld_acquire( &job.progress[mb_y + 1] ) > need )
-                        if( ++spins > 64 ) __nanosleep( 64 );
-                }
-                const int *below = (const int *)( mvs + 2 * ( mb_xy + d.mb_w ) );
-                nb0 = __ldcg( below );
-                if( mb_x > 0 ) nb1 = __ldcg( below - 1 );
-                if( mb_x < d.mb_w - 1 ) nb2 = __ldcg( below + 1 );
+                bool ok = true;
+                if( need ) { r = ld_relaxed64( rp ); ok = (unsigned int)( r >> 32 ) == job.gen; }
+                if( __all_sync( 0xffffffffu, ok ) ) break;
+                if( ++spins > 16 ) __nanosleep( 40 );
             }
-            nb0 = __shfl_sync( 0xffffffffu, nb0, 0 );
-            nb1 = __shfl_sync( 0xffffffffu, nb1, 0 );
-            nb2 = __shfl_sync( 0xffffffffu, nb2, 0 );
+            const int v = need ? (int)(unsigned int)r : 0;
+            nb0 = __shfl_sync( 0xffffffffu, v, 0 );
+            nb1 = __shfl_sync( 0xffffffffu, v, 1 );
+            nb2 = __shfl_sync( 0xffffffffu, v, 2 );
         }
-        LaMe m;
-        const int pel = ( mb_y * 8 ) * d.stride + mb_x * 8;
-        load_quad( job.fenc + pel + qy * d.stride + qx, d.stride, m.fenc );
+        m.win.base = win_base;
+        m.win.bx = mb_x * 8 + qx + 64;
+        m.win.ry = qy + LA_WIN_VR;
+        {   // loaded chunks [vlo, vhi): both words of a 4-px read lie inside <=> 16*vlo <= x <= 16*vhi - 5
+            const int vlo = max( kc - 3, 0 ), vhi = min( kc + 4, n_chunks );
+            m.win.dxlo = 16 * vlo - m.win.bx;
+            m.win.dxspan = (unsigned)( 16 * ( vhi - vlo ) - 5 );
+        }
+        m.win.on = true;
+        m.win.p0w = job.ref_w != nullptr;
 #pragma unroll
         for( int i = 0; i < 4; i++ ) m.fref[i] = job.ref[i] + pel + qy * d.stride + qx;
         m.fref_w = job.ref_w ? job.ref_w + pel + qy * d.stride + qx : m.fref[0];
@@ -334,7 +389,7 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
         if( !( m.mvpx | m.mvpy ) )
         {   // zero-predictor fast skip, slicetype.c:684-692
             uint32_t b[4];
-            load_quad( m.fref[0], d.stride, b );
+            la_load4( m, 0, 0, 0, b );
             cost = quad_sum( m.satd ? satd4x4( m.fenc, b ) : sad4x4( m.fenc, b ) );
             cost = __shfl_sync( 0xffffffffu, cost, 0 );
             skip = cost < 64;
@@ -347,13 +402,14 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
         }
         if( lane == 0 )
         {
-            *(int *)( mvs + 2 * mb_xy ) = (int)pack_mv( mvx, mvy );
+            const unsigned int mv = pack_mv( mvx, mvy );
+            st_relaxed64( job.recs + mb_xy, ( (unsigned long long)job.gen << 32 ) | mv );
+            *(int *)( mvs + 2 * mb_xy ) = (int)mv;
             job.mv_costs[mb_xy] = cost;
-            st_release( &job.progress[mb_y], mb_x );
         }
         right_x = mvx; right_y = mvy;
     }
-    if( lane == 0 ) st_release( &job.progress[mb_y], -1 );
+    cp_async_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -398,6 +454,7 @@ finalize_kernel( LaDims d, LaFinalizeArgs A )
         LaMe m0, m1;
         m0.stride = m1.stride = d.stride;
         m0.w.enabled = m1.w.enabled = 0;
+        m0.win.on = m1.win.on = false; m0.win.p0w = m1.win.p0w = false;
 #pragma unroll
         for( int i = 0; i < 4; i++ ) { m0.fref[i] = A.ref0[i] + pel; m1.fref[i] = ( A.b_bidir ? A.ref1[i] : A.ref0[i] ) + pel; }
         const int v0 = *(const int *)( A.mvs0 + 2 * mbc );
@@ -581,6 +638,7 @@ struct LaSlotHost
     int cost_est[LA_MAX_B + 2][LA_MAX_B + 2], cost_est_aq[LA_MAX_B + 2][LA_MAX_B + 2];
     int intra_mbs[LA_MAX_B + 2];
     bool row_satds_valid[LA_MAX_B + 2][LA_MAX_B + 2];
+    unsigned int gen = 0;            // bumped at every reset: stale (gen << 32 | mv) records of earlier pictures are invalid
     bool searched[2][LA_MAX_B + 1];  // the 0x7FFF sentinel of lowres_mvs[l][d][0][0], kept on the host
     int pending[2][LA_MAX_B + 1];    // event index of a prefetched search still in flight on the search stream, or -1
     unsigned long long *d_stats;     // {sum, sum of squares} of the mod-16 luma
@@ -609,6 +667,8 @@ struct x264cu_lookahead
     cudaEvent_t ev_main = nullptr;
     int last_prefetch_ev = -1;
     uint16_t *h_qscale = nullptr;
+    unsigned int *d_tickets = nullptr;   // work-distribution counters of the search launches (ring of 64)
+    unsigned int ticket_next = 0;
     uint8_t *d_weight_plane = nullptr;   // h->mb.p_weight_buf[0]: weighted copy of one reference F plane (padded)
     unsigned long long *h_stats = nullptr;
 };
@@ -632,9 +692,9 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     for( auto &s : la->slots )
     {
         cudaFree( s.plane_buf ); cudaFree( s.dev.mvs ); cudaFree( s.dev.mv_costs ); cudaFree( s.dev.costs );
-        cudaFree( s.dev.intra ); cudaFree( s.dev.qscale ); cudaFree( s.dev.row_satds ); cudaFree( s.dev.progress ); cudaFree( s.d_stats );
+        cudaFree( s.dev.intra ); cudaFree( s.dev.qscale ); cudaFree( s.dev.row_satds ); cudaFree( s.dev.recs ); cudaFree( s.d_stats );
     }
-    cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record ); cudaFree( la->d_weight_plane );
+    cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record ); cudaFree( la->d_weight_plane ); cudaFree( la->d_tickets );
     cudaFreeHost( la->h_stats );
     cudaFreeHost( la->h_luma ); cudaFreeHost( la->h_record ); cudaFreeHost( la->h_qscale );
     if( la->search_stream ) { cudaStreamSynchronize( la->search_stream ); cudaStreamDestroy( la->search_stream ); }
@@ -689,7 +749,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         alloc( (void **)&s.dev.intra, (size_t)d.mb_count * 4 );
         alloc( (void **)&s.dev.qscale, (size_t)d.mb_count * 2 );
         alloc( (void **)&s.dev.row_satds, (size_t)B2 * d.mb_h * 4 );
-        alloc( (void **)&s.dev.progress, (size_t)2 * B1 * d.mb_h * 4 );
+        alloc( (void **)&s.dev.recs, (size_t)2 * B1 * d.mb_count * 8 );
         s.d_stats = nullptr;
         alloc( (void **)&s.d_stats, 16 );
     }
@@ -698,6 +758,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     alloc( (void **)&la->d_cost_mv, ( 2 * d.cost_len + 1 ) * 2 + 16 );
     alloc( (void **)&la->d_record, 64 );
     alloc( (void **)&la->d_weight_plane, la->plane_bytes );
+    alloc( (void **)&la->d_tickets, 64 * 4 );
     if( ok && cudaMallocHost( (void **)&la->h_stats, 16 ) != cudaSuccess ) ok = false;
     if( cudaStreamCreateWithFlags( &la->search_stream, cudaStreamNonBlocking ) != cudaSuccess ) ok = false;
     for( int i = 0; ok && i < 64; i++ )
@@ -748,6 +809,7 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
     memset( s.searched, 0, sizeof( s.searched ) );
     memset( s.pending, -1, sizeof( s.pending ) );
     s.b_intra_calculated = 0;
+    s.gen++;
     s.intra_on_device = false;
     s.in_use = true;
     s.stats_ready = false;
@@ -812,16 +874,19 @@ static int la_launch_searches( x264cu_lookahead *la, int n, cudaStream_t stream 
     constexpr int NW = 8;
     const int rows = d.mb_h - ( d.do_edges ? 0 : 2 );
     if( rows <= 0 ) return 0;
-    dim3 grid( ( rows + NW - 1 ) / NW, n );
-    size_t smem = ( 2 * d.cost_len + 1 ) * 2 + 16;
+    const int groups = ( rows + NW - 1 ) / NW;
+    size_t smem = ( ( ( 2 * d.cost_len + 1 ) * 2 + 15 ) & ~(size_t)15 ) + (size_t)NW * LA_WIN_BYTES;
     static bool attr = false;
     if( !attr )
     {
-        CU_CHECK( ctx, cudaFuncSetAttribute( search_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 ) );
+        CU_CHECK( ctx, cudaFuncSetAttribute( search_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024 ) );
         attr = true;
     }
-    if( smem > 200 * 1024 ) return x264cu_fail( ctx, "lookahead: mv cost table does not fit in shared memory" );
-    search_kernel<NW><<<grid, NW * 32, smem, stream>>>( d, la->pack, la->d_cost_mv );
+    if( smem > 226 * 1024 ) return x264cu_fail( ctx, "lookahead: mv cost table + reference windows do not fit in shared memory" );
+    // ticket counters: a ring, one per launch, re-zeroed in stream order before use
+    unsigned int *t = la->d_tickets + ( la->ticket_next++ & 63 );
+    CU_CHECK( ctx, cudaMemsetAsync( t, 0, 4, stream ) );
+    search_kernel<NW><<<groups * n, NW * 32, smem, stream>>>( d, la->pack, la->d_cost_mv, n, t );
     CU_LAUNCH_CHECK( ctx );
     return 0;
 }
@@ -835,16 +900,10 @@ static void la_fill_job( x264cu_lookahead *la, LaSearchJob &j, int fenc_slot, in
     for( int i = 0; i < 4; i++ ) j.ref[i] = r.dev.planes[i];
     j.mvs = f.dev.mvs + idx * d.mb_count * 2;
     j.mv_costs = f.dev.mv_costs + idx * d.mb_count;
-    j.progress = f.dev.progress + idx * d.mb_h;
+    j.recs = f.dev.recs + idx * d.mb_count;
+    j.gen = f.gen;
     j.ref_w = nullptr;
     j.w_enabled = 0; j.w_scale = 1; j.w_denom = 0; j.w_offset = 0;
-}
-
-static int la_reset_progress( x264cu_lookahead *la, const LaSearchJob &j, cudaStream_t stream )
-{
-    // "nothing done yet" = a column index larger than any real one (0x7F7F7F7F)
-    CU_CHECK( la->ctx, cudaMemsetAsync( j.progress, 0x7F, (size_t)la->d.mb_h * 4, stream ) );
-    return 0;
 }
 
 // make the main stream wait for a prefetched search that may still be running on the search stream
@@ -885,7 +944,6 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
             n = 0; launched = 1;
         }
         la_fill_job( la, la->pack.j[n], fenc[i], ref[i], list[i], dist[i] );
-        if( la_reset_progress( la, la->pack.j[n], la->search_stream ) ) return -1;
         marks.push_back( Mark{ fenc[i], list[i], dist[i] - 1 } );
         n++;
     }
@@ -899,6 +957,14 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
         for( auto &m : marks ) la->slots[m.slot].pending[m.list][m.dm1] = e;
         la->last_prefetch_ev = e;
     }
+    return 0;
+}
+
+int x264cu_lookahead_join( x264cu_lookahead_t *la )
+{
+    if( !la ) return -1;
+    if( la->last_prefetch_ev >= 0 )
+        CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, la->ev[la->last_prefetch_ev], 0 ) );
     return 0;
 }
 
@@ -1028,14 +1094,12 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
             j.ref_w = la->d_weight_plane + ( la->slots[s0].dev.planes[0] - la->slots[s0].plane_buf );
             j.w_enabled = 1; j.w_scale = fenc.weight.scale; j.w_denom = fenc.weight.denom; j.w_offset = fenc.weight.offset;
         }
-        if( la_reset_progress( la, la->pack.j[n], ctx->stream ) ) return -1;
         n++;
     }
     if( b != p1 && !fenc.searched[1][i1 - 1] )
     {
         fenc.searched[1][i1 - 1] = true;
         la_fill_job( la, la->pack.j[n], sb, s1, 1, i1 );
-        if( la_reset_progress( la, la->pack.j[n], ctx->stream ) ) return -1;
         n++;
     }
     if( !fenc.intra_on_device )

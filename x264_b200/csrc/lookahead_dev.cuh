@@ -36,9 +36,37 @@ __device__ __forceinline__ uint32_t weight4( uint32_t v, const LaWeight &w )   /
     return out;
 }
 
+// Per-warp shared-memory window of the four reference planes around the warp's macroblock row.  The search warp walks
+// its row right to left; the window is, per plane, LA_WIN_ROWS rows of a 128-byte ring of columns (8 chunks of 16 px:
+// byte = biased column & 127), so that the 4 rows of a 4x4 read sit at immediate offsets +128 B.  A candidate whose
+// pixels lie outside the loaded chunks / rows is read from global memory instead (same values, slower).
+#define LA_WIN_ROWS 48
+#define LA_WIN_VR 20                                   /* rows above the MB row: window rows = -20 .. +27 */
+#define LA_WIN_PLANE ( LA_WIN_ROWS * 128 )
+#define LA_WIN_BYTES ( 4 * LA_WIN_PLANE )
+struct LaWin
+{
+    uint32_t base;                // shared-space address of this warp's window
+    int bx;                       // this lane's quadrant origin, biased column (plane x + 64 >= 0)
+    int ry;                       // this lane's quadrant origin, window row
+    int dxlo;                     // in the window <=> (unsigned)( dx - dxlo ) <= dxspan && (unsigned)( dy + ry ) <= LA_WIN_ROWS - 4
+    unsigned dxspan;
+    bool on;                      // window in use (search kernel) or not (finalize)
+    bool p0w;                     // window plane 0 holds the WEIGHTED full-pel plane, not F
+};
+
+template <int OFF>
+__device__ __forceinline__ uint32_t la_lds( uint32_t addr )
+{
+    uint32_t v;
+    asm volatile( "ld.shared.u32 %0, [%1+%2];" : "=r"( v ) : "r"( addr ), "n"( OFF ) );
+    return v;
+}
+
 // warp-uniform search context + per-lane fenc quadrant
 struct LaMe
 {
+    LaWin win;
     const uint8_t *fref[4];       // F,H,V,C plane pointers at this lane's 4x4 quadrant of the MB
     const uint8_t *fref_w;        // weighted full-pel plane (== fref[0] without weights)
     int stride;
@@ -51,6 +79,34 @@ struct LaMe
     bool satd;                    // mbcmp is SATD
 };
 
+#define LA_PLANE_W 4              /* la_load4 plane selector: the (possibly weighted) full-pel search plane */
+
+// this lane's 4x4 of plane `plane` (0..3 = F,H,V,C unweighted, LA_PLANE_W = fref_w) displaced by (dx,dy) full pixels
+__device__ __forceinline__ void la_load4( const LaMe &m, int plane, int dx, int dy, uint32_t b[4] )
+{
+    const LaWin &w = m.win;
+    const int x = w.bx + dx, r = w.ry + dy;
+    const bool in_win = w.on && (unsigned)( dx - w.dxlo ) <= w.dxspan && (unsigned)r <= LA_WIN_ROWS - 4 && !( plane == 0 && w.p0w );
+    if( in_win )
+    {
+        const int slot = plane == LA_PLANE_W ? 0 : plane;
+        const uint32_t pb = w.base + slot * LA_WIN_PLANE + ( r << 7 );
+        const uint32_t a0 = pb + ( x & 124 ), a1 = pb + ( ( x + 4 ) & 124 );
+        const uint32_t sh = ( (uint32_t)x & 3u ) * 8u;
+        b[0] = __funnelshift_r( la_lds<0>( a0 ), la_lds<0>( a1 ), sh );
+        b[1] = __funnelshift_r( la_lds<128>( a0 ), la_lds<128>( a1 ), sh );
+        b[2] = __funnelshift_r( la_lds<256>( a0 ), la_lds<256>( a1 ), sh );
+        b[3] = __funnelshift_r( la_lds<384>( a0 ), la_lds<384>( a1 ), sh );
+    }
+    else
+    {
+        const uint8_t *s = plane == LA_PLANE_W ? m.fref_w : plane == 0 ? m.fref[0] : plane == 1 ? m.fref[1] : plane == 2 ? m.fref[2] : m.fref[3];
+        s += dy * m.stride + dx;
+#pragma unroll
+        for( int i = 0; i < 4; i++ ) b[i] = ldg4u( s + i * m.stride );
+    }
+}
+
 // get_ref (common/mc.c:198-249, tables.c:183-184): this lane's 4x4 of the block interpolated at quarter-pel mv
 __device__ __forceinline__ void qpel4x4( const LaMe &m, int mvx, int mvy, uint32_t b[4] )
 {
@@ -58,20 +114,14 @@ __device__ __forceinline__ void qpel4x4( const LaMe &m, int mvx, int mvy, uint32
     const uint32_t R0 = 0x54FE5454u;    // idx 0..15, 2 bits per entry: 0,1,1,1, 0,1,1,1, 2,3,3,3, 0,1,1,1
     const uint32_t R1 = 0xBABABA10u;    // 0,0,1,0, 2,2,3,2, 2,2,3,2, 2,2,3,2
     const int idx = ( ( mvy & 3 ) << 2 ) + ( mvx & 3 );
-    const int off = ( mvy >> 2 ) * m.stride + ( mvx >> 2 );
-    const uint8_t *s1 = m.fref[( R0 >> ( 2*idx ) ) & 3] + off + ( ( mvy & 3 ) == 3 ? m.stride : 0 );
+    const int fx = mvx >> 2, fy = mvy >> 2;
+    la_load4( m, ( R0 >> ( 2*idx ) ) & 3, fx, fy + ( ( mvy & 3 ) == 3 ), b );
     if( idx & 5 )
     {
-        const uint8_t *s2 = m.fref[( R1 >> ( 2*idx ) ) & 3] + off + ( ( mvx & 3 ) == 3 ? 1 : 0 );
+        uint32_t c[4];
+        la_load4( m, ( R1 >> ( 2*idx ) ) & 3, fx + ( ( mvx & 3 ) == 3 ), fy, c );
 #pragma unroll
-        for( int r = 0; r < 4; r++ )
-            b[r] = __vavgu4( ldg4u( s1 + r * m.stride ), ldg4u( s2 + r * m.stride ) );      // (a+b+1)>>1
-    }
-    else
-    {
-#pragma unroll
-        for( int r = 0; r < 4; r++ )
-            b[r] = ldg4u( s1 + r * m.stride );
+        for( int r = 0; r < 4; r++ ) b[r] = __vavgu4( b[r], c[r] );      // (a+b+1)>>1
     }
     if( m.w.enabled )
     {
@@ -120,9 +170,7 @@ __device__ __forceinline__ int quad_sum( int v )          // sum over the 4 lane
 __device__ __forceinline__ int la_sad_fpel( const LaMe &m, int mx, int my )
 {
     uint32_t b[4];
-    const uint8_t *s = m.fref_w + my * m.stride + mx;
-#pragma unroll
-    for( int r = 0; r < 4; r++ ) b[r] = ldg4u( s + r * m.stride );
+    la_load4( m, LA_PLANE_W, mx, my, b );
     return quad_sum( sad4x4( m.fenc, b ) );
 }
 __device__ __forceinline__ int la_bits_fpel( const LaMe &m, int mx, int my )      // BITS_MVD, me.c:60-61
@@ -145,7 +193,7 @@ __device__ __forceinline__ uint32_t pack_mv( int x, int y ) { return ( (uint32_t
 
 // x264_me_search_ref for one lowres MB.  All control flow is warp-uniform; `slot` = lane>>2.
 // mvc: up to 4 candidate vectors (qpel), i_mvc of them valid.  Results: mv (qpel) and cost, uniform.
-static __device__ __noinline__ void la_me_search( LaMe &m, int me_method, int subpel_refine, int me_range,
+static __device__ __forceinline__ void la_me_search( LaMe &m, int me_method, int subpel_refine, int me_range,
                                            const int *mvc_x, const int *mvc_y, int i_mvc, int lane,
                                            int &out_mvx, int &out_mvy, int &out_cost )
 {
