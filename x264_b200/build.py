@@ -8,7 +8,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libx264_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"] + (["-DME_DEBUG"] if os.environ.get("ME_DEBUG") else [])
+         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"] + (["-DME_DEBUG"] if os.environ.get("ME_DEBUG") else []) + \
+        (["-DLA_PROFILE"] if os.environ.get("LA_PROFILE") else [])
 
 
 def sources():

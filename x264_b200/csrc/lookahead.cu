@@ -19,6 +19,12 @@
 
 using namespace x264cu;
 
+#include <time.h>
+// host-side wait accounting (printed at close when X264CU_STATS is set): where the calling thread blocks on the GPU
+struct LaHostStats { double put_sync = 0, cost_sync = 0, weight_sync = 0, ev_sync = 0; long n_put = 0, n_cost = 0, n_weight = 0, n_batch = 0, n_jobs = 0; };
+static inline double la_now() { timespec t; clock_gettime( CLOCK_MONOTONIC, &t ); return t.tv_sec + 1e-9 * t.tv_nsec; }
+#define LA_TIMED( acc, cnt, stmt ) do { double _t = la_now(); stmt; ( acc ) += la_now() - _t; ( cnt )++; } while( 0 )
+
 #define LOWRES_COST_MASK 0x3fff          /* common/frame.h:107-112 */
 #define LOWRES_COST_SHIFT 14
 #define LA_MAX_B ( X264CU_BFRAME_MAX )
@@ -237,9 +243,9 @@ __device__ __forceinline__ void st_relaxed64( unsigned long long *p, unsigned lo
     asm volatile( "st.relaxed.gpu.global.u64 [%0], %1;" ::"l"( p ), "l"( v ) : "memory" );
 }
 
-__device__ __forceinline__ void cp_async16( uint32_t saddr, const void *g )
+__device__ __forceinline__ void cp_async8( uint32_t saddr, const void *g )
 {
-    asm volatile( "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"( saddr ), "l"( g ) : "memory" );
+    asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;" ::"r"( saddr ), "l"( g ) : "memory" );
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile( "cp.async.wait_all;" ::: "memory" ); }
 
@@ -247,6 +253,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile( "cp.async.wa
 // slicetype.c:658-680).  Work items (row group, job) are handed out by an atomic ticket, row groups first, so that an
 // item only ever waits on items with smaller tickets, i.e. CTAs that are already running -- the grid may be larger than
 // what is resident.  Each warp keeps a sliding shared-memory window of the reference planes (LaWin) fed by cp.async.
+#ifdef LA_PROFILE
+// cycles summed over all search warps: {poll, setup, predictors, full-pel, sub-pel, window slide, macroblocks, searched macroblocks}
+__device__ unsigned long long g_la_prof[8];
+extern "C" int x264cu_debug_la_profile( unsigned long long *out8, int reset )
+{
+    if( cudaMemcpyFromSymbol( out8, g_la_prof, sizeof( g_la_prof ) ) != cudaSuccess ) return -1;
+    if( reset ) { unsigned long long z[8] = { 0 }; cudaMemcpyToSymbol( g_la_prof, z, sizeof( z ) ); }
+    return 0;
+}
+#endif
+
 template <int NW>
 __global__ void __launch_bounds__( NW * 32 )
 search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uint16_t *__restrict__ cost_mv_g, int n_jobs,
@@ -254,13 +271,18 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
 {
     extern __shared__ __align__( 16 ) uint8_t s_raw[];
     __shared__ unsigned int s_ticket;
-    uint16_t *s_cost = (uint16_t *)s_raw;
-    for( int i = threadIdx.x; i < 2 * d.cost_len + 1; i += blockDim.x ) s_cost[i] = cost_mv_g[i];
+    __shared__ uint16_t s_cost[2 * LA_COST_HALF + 2];
     if( threadIdx.x == 0 ) s_ticket = atomicAdd( ticket, 1u );
+    const uint16_t *cost_mv = cost_mv_g + d.cost_len;
+    for( int i = threadIdx.x; i <= 2 * LA_COST_HALF; i += blockDim.x )
+    {   // the table is symmetric around its centre and at least cost_len long on either side
+        const int idx = i - LA_COST_HALF;
+        s_cost[i] = abs( idx ) <= d.cost_len ? cost_mv[idx] : 0xFFFF;
+    }
     __syncthreads();
-    const uint16_t *cost_mv = s_cost + d.cost_len;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared( s_raw ) + ( ( ( 2 * d.cost_len + 1 ) * 2 + 15 ) & ~15 ) + warp * LA_WIN_BYTES;
+    const uint32_t win_base = (uint32_t)__cvta_generic_to_shared( s_raw ) + warp * LA_WIN_BYTES;
+    const uint32_t cost_s = (uint32_t)__cvta_generic_to_shared( s_cost + LA_COST_HALF );
 
     const int row_group = s_ticket / n_jobs;
     const LaSearchJob &job = jobs.j[s_ticket - row_group * n_jobs];
@@ -272,18 +294,19 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
 
     // ---- reference window ---------------------------------------------------------------------------
     const uint8_t *g0 = job.ref_w ? job.ref_w : job.ref[0], *g1 = job.ref[1], *g2 = job.ref[2], *g3 = job.ref[3];
-    const int n_chunks = d.stride >> 4;
+    const int n_chunks = d.stride >> 3;
     const int win_row0 = mb_y * 8 - LA_WIN_VR;
     auto load_chunk = [&]( int k ) {
 #pragma unroll
         for( int j = 0; j < 4 * LA_WIN_ROWS / 32; j++ )
         {
             const int i = lane + 32 * j, p = i / LA_WIN_ROWS, r = i - p * LA_WIN_ROWS;
-            const uint8_t *g = ( p == 0 ? g0 : p == 1 ? g1 : p == 2 ? g2 : g3 ) + (ptrdiff_t)( win_row0 + r ) * d.stride + k * 16 - 64;
-            cp_async16( win_base + p * LA_WIN_PLANE + r * 128 + ( k & 7 ) * 16, g );
+            const uint8_t *g = ( p == 0 ? g0 : p == 1 ? g1 : p == 2 ? g2 : g3 ) + (ptrdiff_t)( win_row0 + r ) * d.stride + k * 8 - 64;
+            cp_async8( win_base + p * LA_WIN_PLANE + r * LA_WIN_PITCH + ( k & 7 ) * 8, g );
         }
     };
-    int kc = ( start_x * 8 + 64 ) >> 4;
+    // chunk of the macroblock itself = mb_x + 8 (biased column >> 3); chunks [kc-3, kc+3] are valid while kc-4 is in flight
+    int kc = start_x + 8;
     for( int k = max( kc - 3, 0 ); k <= min( kc + 3, n_chunks - 1 ); k++ ) load_chunk( k );
     cp_async_wait_all();
     __syncwarp();
@@ -294,52 +317,59 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
     // reset left there: zeros (frame.c:287-293)
     int right_x = 0, right_y = 0;
     const int mv_range = d.mv_range2;
+    // Vectors of the row below (below, below-left, below-right) come from another warp, through self-validating
+    // records.  That row runs right to left too, so one NEW record is needed per macroblock -- below-left -- and the
+    // other two are the previous macroblock's below-left and below.  Its load is issued one macroblock early
+    // (speculatively: it is re-polled if the generation is not there yet), as is the load of the next fenc block, so
+    // that no L2 round trip sits between two searches of a row.
+    const bool has_below = mb_y < d.mb_h - 1;
+    const unsigned long long *rrow = job.recs + ( mb_y + 1 ) * d.mb_w;       // dereferenced only where rec_needed()
+    // columns / rows outside the searched range are never written: they read as the reset value, zero
+    auto rec_needed = [&]( int c ) { return has_below && mb_y + 1 <= start_y && c >= end_x && c <= start_x; };
+    auto rec_poll = [&]( unsigned long long r, const unsigned long long *p ) {
+        for( int spins = 0; (unsigned int)( r >> 32 ) != job.gen; r = ld_relaxed64( p ) )
+            if( ++spins > 16 ) __nanosleep( 40 );
+        return (int)(unsigned int)r;
+    };
+    int nb0 = 0, nb2 = 0;                                                      // below, below-right
+    unsigned long long spec = 0;
+    if( rec_needed( start_x ) ) nb0 = rec_poll( 0, rrow + start_x );
+    if( rec_needed( start_x - 1 ) ) spec = ld_relaxed64( rrow + start_x - 1 );
+    uint32_t fenc_next[4];
+    load_quad( job.fenc + ( mb_y * 8 + qy ) * d.stride + start_x * 8 + qx, d.stride, fenc_next );
+#ifdef LA_PROFILE
+    long long pr[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, t_prof = clock64();
+#endif
     for( int mb_x = start_x; mb_x >= end_x; mb_x-- )
     {
         const int mb_xy = mb_y * d.mb_w + mb_x;
         LaMe m;
+#ifdef LA_PROFILE
+        m.prof[0] = m.prof[1] = m.prof[2] = 0;
+#endif
         const int pel = ( mb_y * 8 ) * d.stride + mb_x * 8;
-        // nothing about fenc depends on the neighbours: have it in flight while the flag is polled
-        load_quad( job.fenc + pel + qy * d.stride + qx, d.stride, m.fenc );
-        {   // slide the window: chunk kc-3 (requested two macroblocks ago) becomes valid, chunk kc-4 is requested
-            const int k = ( mb_x * 8 + 64 ) >> 4;
-            if( k != kc )
-            {
-                kc = k;
-                cp_async_wait_all();
-                __syncwarp();
-                if( kc - 4 >= 0 ) load_chunk( kc - 4 );
-            }
+#pragma unroll
+        for( int i = 0; i < 4; i++ ) m.fenc[i] = fenc_next[i];
+        if( mb_x + 8 != kc )
+        {   // slide the window: chunk kc-3 (requested one macroblock ago) becomes valid, chunk kc-4 is requested
+            kc = mb_x + 8;
+            cp_async_wait_all();
+            __syncwarp();
+            if( kc - 4 >= 0 ) load_chunk( kc - 4 );
         }
-        // the vectors below, below-left and below-right come from the warp of the row below (it runs right to left, so
-        // below-left is the last to appear).  Lanes 0..2 poll one record each until it carries this search's generation.
-        int nb0 = 0, nb1 = 0, nb2 = 0;                   // below, below-left, below-right
-        if( mb_y < d.mb_h - 1 )
-        {
-            const int nx = mb_x + ( lane == 1 ? -1 : lane == 2 ? 1 : 0 );
-            // columns / rows outside the searched range are never written: they read as the reset value, zero
-            const bool need = lane < 3 && mb_y + 1 <= start_y && nx >= end_x && nx <= start_x;
-            const unsigned long long *rp = job.recs + ( mb_xy + d.mb_w + ( nx - mb_x ) );
-            unsigned long long r = 0;
-            for( int spins = 0;; )
-            {
-                bool ok = true;
-                if( need ) { r = ld_relaxed64( rp ); ok = (unsigned int)( r >> 32 ) == job.gen; }
-                if( __all_sync( 0xffffffffu, ok ) ) break;
-                if( ++spins > 16 ) __nanosleep( 40 );
-            }
-            const int v = need ? (int)(unsigned int)r : 0;
-            nb0 = __shfl_sync( 0xffffffffu, v, 0 );
-            nb1 = __shfl_sync( 0xffffffffu, v, 1 );
-            nb2 = __shfl_sync( 0xffffffffu, v, 2 );
-        }
+        LA_TICK( pr[5], t_prof );
+        int nb1 = 0;                                                           // below-left
+        if( rec_needed( mb_x - 1 ) ) nb1 = rec_poll( spec, rrow + mb_x - 1 );
+        if( rec_needed( mb_x - 2 ) ) spec = ld_relaxed64( rrow + mb_x - 2 );
+        if( mb_x > end_x ) load_quad( job.fenc + pel - 8 + qy * d.stride + qx, d.stride, fenc_next );
+        LA_TICK( pr[0], t_prof );
         m.win.base = win_base;
         m.win.bx = mb_x * 8 + qx + 64;
         m.win.ry = qy + LA_WIN_VR;
-        {   // loaded chunks [vlo, vhi): both words of a 4-px read lie inside <=> 16*vlo <= x <= 16*vhi - 5
+        {   // loaded chunks [vlo, vhi): both words of a 4-px read lie inside <=> 8*vlo <= x <= 8*vhi - 5
             const int vlo = max( kc - 3, 0 ), vhi = min( kc + 4, n_chunks );
-            m.win.dxlo = 16 * vlo - m.win.bx;
-            m.win.dxspan = (unsigned)( 16 * ( vhi - vlo ) - 5 );
+            m.win.dxlo = 8 * vlo - m.win.bx;
+            m.win.dxspan = (unsigned)( 8 * ( vhi - vlo ) - 5 );
         }
         m.win.on = true;
         m.win.p0w = job.ref_w != nullptr;
@@ -348,6 +378,7 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
         m.fref_w = job.ref_w ? job.ref_w + pel + qy * d.stride + qx : m.fref[0];
         m.stride = d.stride;
         m.cost_mv = cost_mv;
+        m.cost_s = cost_s;
         m.w.enabled = job.w_enabled; m.w.scale = job.w_scale; m.w.denom = job.w_denom; m.w.offset = job.w_offset;
         m.satd = d.subme > 1;
         m.min_spel_x = max( 4*( -8*mb_x - 12 ), -mv_range );
@@ -394,10 +425,11 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
             cost = __shfl_sync( 0xffffffffu, cost, 0 );
             skip = cost < 64;
         }
+        LA_TICK( pr[1], t_prof );
         if( !skip )
         {
             la_me_search( m, d.me_method, d.subpel, d.me_range, mvcx, mvcy, i_mvc, lane, mvx, mvy, cost );
-            cost -= cost_mv[0];
+            cost -= la_cost( m, 0 );
             if( mvx | mvy ) cost += 5;                              // 5 * lambda
         }
         if( lane == 0 )
@@ -408,7 +440,16 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
             job.mv_costs[mb_xy] = cost;
         }
         right_x = mvx; right_y = mvy;
+        nb2 = nb0; nb0 = nb1;
+#ifdef LA_PROFILE
+        t_prof = clock64();
+        pr[2] += m.prof[0]; pr[3] += m.prof[1]; pr[4] += m.prof[2]; pr[6]++; pr[7] += !skip;
+#endif
     }
+#ifdef LA_PROFILE
+    if( lane == 0 )
+        for( int i = 0; i < 8; i++ ) atomicAdd( &g_la_prof[i], (unsigned long long)pr[i] );
+#endif
     cp_async_wait_all();
 }
 
@@ -661,12 +702,23 @@ struct x264cu_lookahead
     uint8_t *h_luma = nullptr;       // pinned staging
     int32_t *d_record = nullptr, *h_record = nullptr;
     LaJobPack pack;                  // jobs being assembled for the next launch
-    cudaStream_t search_stream = nullptr;
+    cudaStream_t search_streams[2] = {};     // prefetch launches alternate: the drain of one wavefront overlaps the fill of the next
+    cudaStream_t search_stream = nullptr;     // the one the current search_batch call uses
+    unsigned int batch_no = 0;
+    int last_ev_of[2] = { -1, -1 };
     cudaEvent_t ev[64];
     int ev_next = 0, n_ev = 0;
     cudaEvent_t ev_main = nullptr;
     int last_prefetch_ev = -1;
     uint16_t *h_qscale = nullptr;
+    LaHostStats st;
+    bool stats_on = false;
+    cudaEvent_t tm_ev[64][2] = {};       // X264CU_STATS: device time of each search launch
+    bool tm_live[64] = {};
+    double search_busy_ms = 0;
+    uint16_t *d_qscale_flat = nullptr;   // mb_count x 256: the factors of a picture without AQ
+    cudaEvent_t qs_ev[4] = {};           // guards of the pinned qscale staging ring
+    unsigned int qs_next = 0;
     unsigned int *d_tickets = nullptr;   // work-distribution counters of the search launches (ring of 64)
     unsigned int ticket_next = 0;
     uint8_t *d_weight_plane = nullptr;   // h->mb.p_weight_buf[0]: weighted copy of one reference F plane (padded)
@@ -689,6 +741,22 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     if( !la ) return;
     cudaSetDevice( la->ctx->device );
     cudaStreamSynchronize( la->ctx->stream );
+    if( la->stats_on )
+    {
+        cudaDeviceSynchronize();
+        for( int i = 0; i < 64; i++ )
+            if( la->tm_live[i] )
+            {
+                float ms = 0;
+                cudaEventElapsedTime( &ms, la->tm_ev[i][0], la->tm_ev[i][1] );
+                la->search_busy_ms += ms;
+            }
+        fprintf( stderr, "x264cu lookahead: search kernels busy %.1f ms on the device\n", la->search_busy_ms );
+    }
+    if( la->stats_on )
+        fprintf( stderr, "x264cu lookahead host waits: frame_put %.1f ms / %ld, frame_cost %.1f ms / %ld, weights %.1f ms / %ld, event ring %.1f ms; "
+                 "%ld search launches, %ld searches\n", la->st.put_sync * 1e3, la->st.n_put, la->st.cost_sync * 1e3, la->st.n_cost,
+                 la->st.weight_sync * 1e3, la->st.n_weight, la->st.ev_sync * 1e3, la->st.n_batch, la->st.n_jobs );
     for( auto &s : la->slots )
     {
         cudaFree( s.plane_buf ); cudaFree( s.dev.mvs ); cudaFree( s.dev.mv_costs ); cudaFree( s.dev.costs );
@@ -697,7 +765,10 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record ); cudaFree( la->d_weight_plane ); cudaFree( la->d_tickets );
     cudaFreeHost( la->h_stats );
     cudaFreeHost( la->h_luma ); cudaFreeHost( la->h_record ); cudaFreeHost( la->h_qscale );
-    if( la->search_stream ) { cudaStreamSynchronize( la->search_stream ); cudaStreamDestroy( la->search_stream ); }
+    cudaFree( la->d_qscale_flat );
+    for( int i = 0; i < 4; i++ ) if( la->qs_ev[i] ) cudaEventDestroy( la->qs_ev[i] );
+    for( int i = 0; i < 2; i++ )
+        if( la->search_streams[i] ) { cudaStreamSynchronize( la->search_streams[i] ); cudaStreamDestroy( la->search_streams[i] ); }
     for( int i = 0; i < la->n_ev; i++ ) cudaEventDestroy( la->ev[i] );
     if( la->ev_main ) cudaEventDestroy( la->ev_main );
     delete la;
@@ -715,6 +786,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     if( p->mv_range < 32 || p->mv_range > 4096 ) return x264cu_fail( ctx, "lookahead_open: mv_range %d out of range", p->mv_range );
     x264cu_lookahead *la = new x264cu_lookahead;
     la->ctx = ctx; la->p = *p;
+    la->stats_on = getenv( "X264CU_STATS" ) != nullptr;
     LaDims &d = la->d;
     d.mb_w = ( p->width + 15 ) >> 4; d.mb_h = ( p->height + 15 ) >> 4; d.mb_count = d.mb_w * d.mb_h;
     la->wl = d.mb_w * 8; la->ll = d.mb_h * 8;
@@ -760,7 +832,9 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     alloc( (void **)&la->d_weight_plane, la->plane_bytes );
     alloc( (void **)&la->d_tickets, 64 * 4 );
     if( ok && cudaMallocHost( (void **)&la->h_stats, 16 ) != cudaSuccess ) ok = false;
-    if( cudaStreamCreateWithFlags( &la->search_stream, cudaStreamNonBlocking ) != cudaSuccess ) ok = false;
+    for( int i = 0; i < 2; i++ )
+        if( cudaStreamCreateWithFlags( &la->search_streams[i], cudaStreamNonBlocking ) != cudaSuccess ) ok = false;
+    la->search_stream = la->search_streams[0];
     for( int i = 0; ok && i < 64; i++ )
     {
         if( cudaEventCreateWithFlags( &la->ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false; else la->n_ev++;
@@ -768,7 +842,17 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     if( ok && cudaEventCreateWithFlags( &la->ev_main, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_luma, la->luma_bytes ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_record, 64 ) != cudaSuccess ) ok = false;
-    if( ok && cudaMallocHost( (void **)&la->h_qscale, d.mb_count * 2 ) != cudaSuccess ) ok = false;
+    if( ok && cudaMallocHost( (void **)&la->h_qscale, (size_t)4 * d.mb_count * 2 ) != cudaSuccess ) ok = false;
+    for( int i = 0; i < 4 && ok; i++ )
+        if( cudaEventCreateWithFlags( &la->qs_ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
+    alloc( (void **)&la->d_qscale_flat, (size_t)d.mb_count * 2 );
+    if( ok )
+    {
+        std::vector<uint16_t> flat( d.mb_count, 256 );
+        // same stream as alloc()'s clearing memset, so it lands after it
+        if( cudaMemcpyAsync( la->d_qscale_flat, flat.data(), (size_t)d.mb_count * 2, cudaMemcpyHostToDevice, ctx->stream ) != cudaSuccess ||
+            cudaStreamSynchronize( ctx->stream ) != cudaSuccess ) ok = false;
+    }
     if( !ok )
     {
         x264cu_fail( ctx, "lookahead_open: out of device / pinned memory" );
@@ -816,17 +900,17 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
     s.weight.enabled = 0; s.weight.scale = 1; s.weight.denom = 0; s.weight.offset = 0;
     CU_CHECK( ctx, cudaMemsetAsync( s.dev.mvs, 0, (size_t)2 * ( d.B + 1 ) * d.mb_count * 4, ctx->stream ) );
     if( h_inv_qscale )
-    {
-        memcpy( la->h_qscale, h_inv_qscale, d.mb_count * 2 );
-        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, la->h_qscale, d.mb_count * 2, cudaMemcpyHostToDevice, ctx->stream ) );
-        CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );            // h_qscale is reused by the next put
+    {   // staged through a ring of pinned buffers: the caller's array may be reused as soon as this returns, and the
+        // calling thread never waits for the stream
+        const int k = la->qs_next++ & 3;
+        uint16_t *stage = la->h_qscale + (size_t)k * d.mb_count;
+        LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->qs_ev[k] ) ) );
+        memcpy( stage, h_inv_qscale, d.mb_count * 2 );
+        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, stage, d.mb_count * 2, cudaMemcpyHostToDevice, ctx->stream ) );
+        CU_CHECK( ctx, cudaEventRecord( la->qs_ev[k], ctx->stream ) );
     }
-    else
-    {
-        for( int i = 0; i < d.mb_count; i++ ) la->h_qscale[i] = 256;
-        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, la->h_qscale, d.mb_count * 2, cudaMemcpyHostToDevice, ctx->stream ) );
-        CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
-    }
+    else        // no AQ: every factor is 256 (x264_adaptive_quant_frame with aq off, ratecontrol.c:308-330)
+        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, la->d_qscale_flat, d.mb_count * 2, cudaMemcpyDeviceToDevice, ctx->stream ) );
     return 0;
 }
 
@@ -837,8 +921,9 @@ int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const u
     if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( la->ctx, "frame_put: slot %d out of range", slot );
     LaSlotHost &s = la->slots[slot];
     // prefetched searches may still be reading the picture that occupied this slot
-    if( la->last_prefetch_ev >= 0 )
-        CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, la->ev[la->last_prefetch_ev], 0 ) );
+    for( int i = 0; i < 2; i++ )
+        if( la->last_ev_of[i] >= 0 )
+            CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, la->ev[la->last_ev_of[i]], 0 ) );
     if( x264cu_frame_init_lowres( la->ctx, d_luma, luma_stride, la->p.width, la->p.height, s.dev.planes, la->d.stride ) ) return -1;
     if( la->p.weighted_pred )
     {
@@ -875,19 +960,34 @@ static int la_launch_searches( x264cu_lookahead *la, int n, cudaStream_t stream 
     const int rows = d.mb_h - ( d.do_edges ? 0 : 2 );
     if( rows <= 0 ) return 0;
     const int groups = ( rows + NW - 1 ) / NW;
-    size_t smem = ( ( ( 2 * d.cost_len + 1 ) * 2 + 15 ) & ~(size_t)15 ) + (size_t)NW * LA_WIN_BYTES;
+    size_t smem = (size_t)NW * LA_WIN_BYTES;
     static bool attr = false;
     if( !attr )
     {
-        CU_CHECK( ctx, cudaFuncSetAttribute( search_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024 ) );
+        CU_CHECK( ctx, cudaFuncSetAttribute( search_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
+        CU_CHECK( ctx, cudaFuncSetAttribute( search_kernel<NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
         attr = true;
     }
-    if( smem > 226 * 1024 ) return x264cu_fail( ctx, "lookahead: mv cost table + reference windows do not fit in shared memory" );
     // ticket counters: a ring, one per launch, re-zeroed in stream order before use
     unsigned int *t = la->d_tickets + ( la->ticket_next++ & 63 );
     CU_CHECK( ctx, cudaMemsetAsync( t, 0, 4, stream ) );
+    la->st.n_batch++; la->st.n_jobs += n;
+    const int ti = ( la->ticket_next - 1 ) & 63;
+    if( la->stats_on )
+    {
+        if( !la->tm_ev[ti][0] ) { cudaEventCreate( &la->tm_ev[ti][0] ); cudaEventCreate( &la->tm_ev[ti][1] ); }
+        if( la->tm_live[ti] )
+        {
+            float ms = 0;
+            cudaEventSynchronize( la->tm_ev[ti][1] );
+            cudaEventElapsedTime( &ms, la->tm_ev[ti][0], la->tm_ev[ti][1] );
+            la->search_busy_ms += ms;
+        }
+        cudaEventRecord( la->tm_ev[ti][0], stream );
+    }
     search_kernel<NW><<<groups * n, NW * 32, smem, stream>>>( d, la->pack, la->d_cost_mv, n, t );
     CU_LAUNCH_CHECK( ctx );
+    if( la->stats_on ) { cudaEventRecord( la->tm_ev[ti][1], stream ); la->tm_live[ti] = true; }
     return 0;
 }
 
@@ -924,6 +1024,8 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
     x264cu_ctx *ctx = la->ctx;
     // everything queued so far on the main stream (lowres planes, vector resets) must be visible to the searches
     CU_CHECK( ctx, cudaEventRecord( la->ev_main, ctx->stream ) );
+    const int si = la->batch_no++ & 1;
+    la->search_stream = la->search_streams[si];
     CU_CHECK( ctx, cudaStreamWaitEvent( la->search_stream, la->ev_main, 0 ) );
     int n = 0, launched = 0;
     struct Mark { int slot, list, dm1; };
@@ -952,10 +1054,11 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
     {
         const int e = la->ev_next;
         la->ev_next = ( la->ev_next + 1 ) % la->n_ev;
-        CU_CHECK( ctx, cudaEventSynchronize( la->ev[e] ) );           // ring slot reuse: its previous recording is long done
+        { long dummy = 0; LA_TIMED( la->st.ev_sync, dummy, CU_CHECK( ctx, cudaEventSynchronize( la->ev[e] ) ) ); }   // ring slot reuse: its previous recording is long done
         CU_CHECK( ctx, cudaEventRecord( la->ev[e], la->search_stream ) );
         for( auto &m : marks ) la->slots[m.slot].pending[m.list][m.dm1] = e;
         la->last_prefetch_ev = e;
+        la->last_ev_of[si] = e;
     }
     return 0;
 }
@@ -963,8 +1066,9 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
 int x264cu_lookahead_join( x264cu_lookahead_t *la )
 {
     if( !la ) return -1;
-    if( la->last_prefetch_ev >= 0 )
-        CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, la->ev[la->last_prefetch_ev], 0 ) );
+    for( int i = 0; i < 2; i++ )
+        if( la->last_ev_of[i] >= 0 )
+            CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, la->ev[la->last_ev_of[i]], 0 ) );
     return 0;
 }
 
@@ -1153,7 +1257,7 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
     finalize_kernel<<<( d.mb_count + 63 ) / 64, 256, 0, ctx->stream>>>( d, A );
     CU_LAUNCH_CHECK( ctx );
     CU_CHECK( ctx, cudaMemcpyAsync( la->h_record, la->d_record, 32, cudaMemcpyDeviceToHost, ctx->stream ) );
-    CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
+    LA_TIMED( la->st.cost_sync, la->st.n_cost, CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) ) );
 
     // accumulator hand-over in the reference's order, slicetype.c:946-989
     const int32_t *r = la->h_record;
@@ -1178,7 +1282,7 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
 static int la_check_slot( x264cu_lookahead *la, int slot )
 {
     if( !la ) return -1;
-    cudaStreamSynchronize( la->search_stream );          // read-backs see prefetched searches too
+    for( int i = 0; i < 2; i++ ) cudaStreamSynchronize( la->search_streams[i] );          // read-backs see prefetched searches too
     if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use )
         return x264cu_fail( la->ctx, "lookahead: slot %d is empty / out of range", slot );
     return 0;
@@ -1237,7 +1341,10 @@ int x264cu_lookahead_get_row_satds( x264cu_lookahead_t *la, int slot, int i0, in
 
 int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int i0, int i1, int *cost_est, int *cost_est_aq, int *intra_mbs )
 {
-    if( la_check_slot( la, slot ) ) return -1;
+    // the memo lives on the host (x264cu_lookahead_frame_cost has already synchronised on what it returns): no device wait
+    if( !la ) return -1;
+    if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use )
+        return x264cu_fail( la->ctx, "lookahead: slot %d is empty / out of range", slot );
     const LaDims &d = la->d;
     if( i0 < 0 || i1 < 0 || i0 > d.B + 1 || i1 > d.B + 1 ) return x264cu_fail( la->ctx, "get_cost_est: bad index" );
     LaSlotHost &s = la->slots[slot];

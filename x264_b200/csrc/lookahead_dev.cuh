@@ -11,6 +11,13 @@ namespace x264cu {
 
 #define LA_COST_MAX ( 1 << 28 )                 /* encoder/me.h:30 */
 
+// phase timing of the search kernel (build with LA_PROFILE=1 in the environment; tools/la_phase_profile.py)
+#ifdef LA_PROFILE
+#define LA_TICK( acc, t ) do { long long _n = clock64(); ( acc ) += _n - ( t ); ( t ) = _n; } while( 0 )
+#else
+#define LA_TICK( acc, t ) do {} while( 0 )
+#endif
+
 __device__ __forceinline__ uint32_t ldg4u( const uint8_t *p )      // 4 pixels at any byte address
 {
     uintptr_t u = (uintptr_t)p;
@@ -37,12 +44,14 @@ __device__ __forceinline__ uint32_t weight4( uint32_t v, const LaWeight &w )   /
 }
 
 // Per-warp shared-memory window of the four reference planes around the warp's macroblock row.  The search warp walks
-// its row right to left; the window is, per plane, LA_WIN_ROWS rows of a 128-byte ring of columns (8 chunks of 16 px:
-// byte = biased column & 127), so that the 4 rows of a 4x4 read sit at immediate offsets +128 B.  A candidate whose
-// pixels lie outside the loaded chunks / rows is read from global memory instead (same values, slower).
+// its row right to left; the window is, per plane, LA_WIN_ROWS rows of a 64-byte ring of columns (8 chunks of 8 px, one
+// per macroblock step: byte = biased column & 63) at a pitch of 72 bytes -- the 4 rows of a 4x4 read sit at immediate
+// offsets, and the quadrant 4 rows further down falls into other banks.  13.5 KB per warp: two 8-warp CTAs per SM.  A candidate whose pixels lie outside the loaded chunks / rows (motion beyond
+// about +-20 lowres pixels) is read from global memory instead (same values, slower).
 #define LA_WIN_ROWS 48
 #define LA_WIN_VR 20                                   /* rows above the MB row: window rows = -20 .. +27 */
-#define LA_WIN_PLANE ( LA_WIN_ROWS * 128 )
+#define LA_WIN_PITCH 72
+#define LA_WIN_PLANE ( LA_WIN_ROWS * LA_WIN_PITCH )
 #define LA_WIN_BYTES ( 4 * LA_WIN_PLANE )
 struct LaWin
 {
@@ -71,13 +80,31 @@ struct LaMe
     const uint8_t *fref_w;        // weighted full-pel plane (== fref[0] without weights)
     int stride;
     uint32_t fenc[4];             // this lane's fenc quadrant rows
-    const uint16_t *cost_mv;      // centred table (shared memory)
+    const uint16_t *cost_mv;      // centred table in global memory (the rare far entries)
+    uint32_t cost_s;              // shared-space address of entry 0 of the table's centre part, |index| <= LA_COST_HALF
     int mvpx, mvpy;
     int min_spel_x, min_spel_y, max_spel_x, max_spel_y;
     int x_min, y_min, x_max, y_max;
     LaWeight w;
     bool satd;                    // mbcmp is SATD
+#ifdef LA_PROFILE
+    long long prof[3];            // cycles in: predictors, full-pel search, sub-pel refine
+#endif
 };
+
+#define LA_COST_HALF 512          /* mv - mvp distances (quarter-pel) kept in shared memory: +-128 pixels */
+
+// p_cost_mv[idx] (analyse.c:143-202 table, centred): the entries a search normally touches are in shared memory
+__device__ __forceinline__ int la_cost( const LaMe &m, int idx )
+{
+    if( (unsigned)( idx + LA_COST_HALF ) <= 2u * LA_COST_HALF )
+    {
+        uint32_t v;
+        asm volatile( "ld.shared.u16 %0, [%1];" : "=r"( v ) : "r"( m.cost_s + 2 * idx ) );
+        return (int)v;
+    }
+    return __ldg( m.cost_mv + idx );
+}
 
 #define LA_PLANE_W 4              /* la_load4 plane selector: the (possibly weighted) full-pel search plane */
 
@@ -90,13 +117,13 @@ __device__ __forceinline__ void la_load4( const LaMe &m, int plane, int dx, int 
     if( in_win )
     {
         const int slot = plane == LA_PLANE_W ? 0 : plane;
-        const uint32_t pb = w.base + slot * LA_WIN_PLANE + ( r << 7 );
-        const uint32_t a0 = pb + ( x & 124 ), a1 = pb + ( ( x + 4 ) & 124 );
+        const uint32_t pb = w.base + slot * LA_WIN_PLANE + r * LA_WIN_PITCH;
+        const uint32_t a0 = pb + ( x & 60 ), a1 = pb + ( ( x + 4 ) & 60 );
         const uint32_t sh = ( (uint32_t)x & 3u ) * 8u;
         b[0] = __funnelshift_r( la_lds<0>( a0 ), la_lds<0>( a1 ), sh );
-        b[1] = __funnelshift_r( la_lds<128>( a0 ), la_lds<128>( a1 ), sh );
-        b[2] = __funnelshift_r( la_lds<256>( a0 ), la_lds<256>( a1 ), sh );
-        b[3] = __funnelshift_r( la_lds<384>( a0 ), la_lds<384>( a1 ), sh );
+        b[1] = __funnelshift_r( la_lds<LA_WIN_PITCH>( a0 ), la_lds<LA_WIN_PITCH>( a1 ), sh );
+        b[2] = __funnelshift_r( la_lds<2 * LA_WIN_PITCH>( a0 ), la_lds<2 * LA_WIN_PITCH>( a1 ), sh );
+        b[3] = __funnelshift_r( la_lds<3 * LA_WIN_PITCH>( a0 ), la_lds<3 * LA_WIN_PITCH>( a1 ), sh );
     }
     else
     {
@@ -175,7 +202,7 @@ __device__ __forceinline__ int la_sad_fpel( const LaMe &m, int mx, int my )
 }
 __device__ __forceinline__ int la_bits_fpel( const LaMe &m, int mx, int my )      // BITS_MVD, me.c:60-61
 {
-    return m.cost_mv[mx*4 - m.mvpx] + m.cost_mv[my*4 - m.mvpy];
+    return la_cost( m, mx*4 - m.mvpx ) + la_cost( m, my*4 - m.mvpy );
 }
 // quarter-pel candidate, SAD (fpelcmp) or mbcmp (COST_MV_HPEL / COST_MV_SAD / COST_MV_SATD), incl. mv bits
 __device__ __forceinline__ int la_cost_qpel( const LaMe &m, int mx, int my, bool use_mbcmp )
@@ -183,7 +210,7 @@ __device__ __forceinline__ int la_cost_qpel( const LaMe &m, int mx, int my, bool
     uint32_t b[4];
     qpel4x4( m, mx, my, b );
     int d = ( use_mbcmp && m.satd ) ? satd4x4( m.fenc, b ) : sad4x4( m.fenc, b );
-    return quad_sum( d ) + m.cost_mv[mx - m.mvpx] + m.cost_mv[my - m.mvpy];
+    return quad_sum( d ) + la_cost( m, mx - m.mvpx ) + la_cost( m, my - m.mvpy );
 }
 
 __device__ __forceinline__ int warp_min( int v ) { return __reduce_min_sync( 0xffffffffu, v ); }
@@ -200,6 +227,9 @@ static __device__ __forceinline__ void la_me_search( LaMe &m, int me_method, int
     const int slot = lane >> 2;
     int bmx, bmy, bcost = LA_COST_MAX, bpred_cost = LA_COST_MAX;
     uint32_t pmv, bpred_mv = 0;
+#ifdef LA_PROFILE
+    long long t_prof = clock64();
+#endif
 
     if( subpel_refine >= 3 )
     {   // me.c:216-275: sub-pel predictors
@@ -227,20 +257,26 @@ static __device__ __forceinline__ void la_me_search( LaMe &m, int me_method, int
                     n++;
                 }
             }
-        // slot 0 = the predictor, slots 1..n = candidates
+        // slot 0 = the predictor, slots 1..n = candidates.  The two full-pel probes that follow in the reference (the
+        // rounded winner and the zero vector, me.c:247-272) do not depend on anything but the winner's identity: every
+        // slot also measures ITS candidate rounded to full-pel (slot 5: the zero vector), the winner's is picked after.
         int sx = bpx, sy = bpy;
         if( slot == 1 ) { sx = cx[0]; sy = cy[0]; }
         if( slot == 2 ) { sx = cx[1]; sy = cy[1]; }
         if( slot == 3 ) { sx = cx[2]; sy = cy[2]; }
         if( slot == 4 ) { sx = cx[3]; sy = cy[3]; }
+        if( slot >= 5 ) { sx = 0; sy = 0; }
         int c = la_cost_qpel( m, sx, sy, false );
+        const int fx = LA_FPEL( sx ), fy = LA_FPEL( sy );
+        const int fc = la_sad_fpel( m, fx, fy ) + la_bits_fpel( m, fx, fy );
         int pmv_cost = __shfl_sync( 0xffffffffu, c, 0 );
         bpred_cost = pmv_cost;
+        int w = 0;
         if( n > 0 )
         {
             int key = slot <= n ? ( c << 4 ) + slot : 0x7fffffff;
             key = warp_min( key );
-            int w = key & 15;
+            w = key & 15;
             if( w == 1 ) { bpx = cx[0]; bpy = cy[0]; }
             if( w == 2 ) { bpx = cx[1]; bpy = cy[1]; }
             if( w == 3 ) { bpx = cx[2]; bpy = cy[2]; }
@@ -249,10 +285,7 @@ static __device__ __forceinline__ void la_me_search( LaMe &m, int me_method, int
         }
         bmx = LA_FPEL( bpx ); bmy = LA_FPEL( bpy );
         bpred_mv = pack_mv( bpx, bpy );
-        // the two possible full-pel probes (rounded predictor, zero vector) are independent: one step
-        int fx = slot == 0 ? bmx : 0, fy = slot == 0 ? bmy : 0;
-        int fc = la_sad_fpel( m, fx, fy ) + la_bits_fpel( m, fx, fy );
-        int c_bm = __shfl_sync( 0xffffffffu, fc, 0 ), c_zero = __shfl_sync( 0xffffffffu, fc, 4 );
+        int c_bm = __shfl_sync( 0xffffffffu, fc, w * 4 ), c_zero = __shfl_sync( 0xffffffffu, fc, 20 );
         if( bpred_mv & 0x00030003 ) { if( c_bm < bcost ) bcost = c_bm; }
         else bcost = bpred_cost;
         if( pmv )
@@ -310,6 +343,7 @@ static __device__ __forceinline__ void la_me_search( LaMe &m, int me_method, int
     }
 
     auto in_range = [&]( int x, int y ) { return x >= m.x_min && x <= m.x_max && y >= m.y_min && y <= m.y_max; };
+    LA_TICK( m.prof[0], t_prof );
 
     if( me_method == X264CU_ME_DIA )
     {   // me.c:322-342
@@ -376,13 +410,14 @@ static __device__ __forceinline__ void la_me_search( LaMe &m, int me_method, int
         bcost = k3 >> 4;
     }
 
+    LA_TICK( m.prof[1], t_prof );
     // -> quarter-pel, me.c:774-789
     int mvx, mvy, cost;
     if( subpel_refine < 3 )
     {
         cost = bcost;
         if( pack_mv( bmx, bmy ) == pmv )
-            cost += m.cost_mv[bmx*4 - m.mvpx] + m.cost_mv[bmy*4 - m.mvpy];
+            cost += la_cost( m, bmx*4 - m.mvpx ) + la_cost( m, bmy*4 - m.mvpy );
         mvx = bmx*4; mvy = bmy*4;
     }
     else if( bpred_cost < bcost )
@@ -421,18 +456,18 @@ static __device__ __forceinline__ void la_me_search( LaMe &m, int me_method, int
             }
             qcost = key >> 6;
         }
-        if( m.satd )
-        {   // re-measure the winner with mbcmp, me.c:925-929
-            int c = la_cost_qpel( m, qx, qy, true );
-            qcost = __shfl_sync( 0xffffffffu, c, 0 );
-        }
-        if( subpel_refine >= 4 )
-        {   // one quarter-pel diamond iteration (bdir = -1: nothing is skipped), me.c:946-963
-            if( !( qy <= m.min_spel_y || qy >= m.max_spel_y || qx <= m.min_spel_x || qx >= m.max_spel_x ) )
+        // me.c:925-963: the winner is re-measured with mbcmp (when that is SATD) and one quarter-pel diamond iteration
+        // follows (bdir = -1: nothing is skipped).  The re-measurement and the four diamond points only depend on the
+        // half-pel winner: ONE step, slot 4 taking the centre.
+        const bool do_qpel = subpel_refine >= 4 && !( qy <= m.min_spel_y || qy >= m.max_spel_y || qx <= m.min_spel_x || qx >= m.max_spel_x );
+        if( m.satd || do_qpel )
+        {
+            const int dx = !do_qpel ? 0 : slot == 2 ? -1 : slot == 3 ? 1 : 0;
+            const int dy = !do_qpel ? 0 : slot == 0 ? -1 : slot == 1 ? 1 : 0;
+            int c = la_cost_qpel( m, qx + dx, qy + dy, true );
+            if( m.satd ) qcost = __shfl_sync( 0xffffffffu, c, 16 );
+            if( do_qpel )
             {
-                const int dx = slot == 2 ? -1 : slot == 3 ? 1 : 0;
-                const int dy = slot == 0 ? -1 : slot == 1 ? 1 : 0;
-                int c = la_cost_qpel( m, qx + dx, qy + dy, true );
                 int key = slot < 4 ? ( c << 2 ) + slot : 0x7fffffff;
                 key = warp_min( key );
                 if( ( key >> 2 ) < qcost )
@@ -446,6 +481,7 @@ static __device__ __forceinline__ void la_me_search( LaMe &m, int me_method, int
         }
         mvx = qx; mvy = qy; cost = qcost;
     }
+    LA_TICK( m.prof[2], t_prof );
     out_mvx = mvx; out_mvy = mvy; out_cost = cost;
 }
 

@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <time.h>
+static double st_now( void ) { struct timespec t; clock_gettime( CLOCK_MONOTONIC, &t ); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 #define LOOKAHEAD_MAX 250                 /* X264_LOOKAHEAD_MAX, common/base.h:140 */
 #define BFRAME_MAX X264CU_BFRAME_MAX
@@ -58,6 +60,7 @@ struct x264cu_slicetype
     /* prefetch jobs gathered over a few pictures so that one launch fills the GPU (each search is a thin wavefront) */
     int pj_fenc[256], pj_ref[256], pj_list[256], pj_dist[256], pj_fframe[256], pj_rframe[256], n_pj, pj_pictures;
     int prefetch_group;                   /* pictures per prefetch launch */
+    double t_put, t_batch, t_cost, t_step; long n_cost_calls;   /* X264CU_STATS: where the calling thread's time goes */
     int run_ahead;                        /* extra pictures queued before deciding, like param.i_sync_lookahead (encoder.c:1611) */
 };
 
@@ -75,7 +78,10 @@ static int frame_cost( x264cu_slicetype_t *s, st_frame_t **frames, int p0, int p
     for( int i = p0; i <= p1; i++ ) slots[i] = frames[i]->slot;
     int score = 0;
     s->requests++;
-    if( x264cu_lookahead_frame_cost( s->la, slots, p0, p1, b, &score ) )
+    double t0_ = st_now();
+    int rc_ = x264cu_lookahead_frame_cost( s->la, slots, p0, p1, b, &score );
+    s->t_cost += st_now() - t0_; s->n_cost_calls++;
+    if( rc_ )
     {
         s->failed = 1;
         return 0;
@@ -601,6 +607,12 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
     s->prefetch = 1;
     s->prefetch_group = s->delay >= 12 ? 4 : 1;
     s->run_ahead = s->delay >= 12 ? 8 : 0;
+    {   /* tuning hooks (bench experiments): X264CU_RUN_AHEAD=<0..16>, X264CU_PREFETCH_GROUP=<1..8> */
+        const char *e = getenv( "X264CU_RUN_AHEAD" );
+        if( e && atoi( e ) >= 0 && atoi( e ) <= 16 ) s->run_ahead = atoi( e );
+        e = getenv( "X264CU_PREFETCH_GROUP" );
+        if( e && atoi( e ) >= 1 && atoi( e ) <= 8 ) s->prefetch_group = atoi( e );
+    }
     if( !s->slot_used || x264cu_lookahead_open( ctx, &s->p.la, &s->la ) )
     {
         free( s->slot_used );
@@ -617,6 +629,10 @@ void x264cu_slicetype_close( x264cu_slicetype_t *s )
     for( int i = 0; i < s->n_next; i++ ) free( s->next[i] );
     for( int i = 0; i < s->n_current; i++ ) if( s->current[i] != s->last_nonb ) free( s->current[i] );
     free( s->last_nonb );
+    if( getenv( "X264CU_STATS" ) )
+        fprintf( stderr, "x264cu slicetype host time: step %.1f ms = frame_put %.1f + search_batch %.1f + frame_cost %.1f (%ld calls) + logic %.1f\n",
+                 s->t_step * 1e3, s->t_put * 1e3, s->t_batch * 1e3, s->t_cost * 1e3, s->n_cost_calls,
+                 ( s->t_step - s->t_put - s->t_batch - s->t_cost ) * 1e3 );
     x264cu_lookahead_close( s->la );
     free( s->slot_used );
     free( s );
@@ -635,8 +651,10 @@ static int flush_prefetch( x264cu_slicetype_t *s )
     }
     s->n_pj = 0;
     s->pj_pictures = 0;
-    if( n && x264cu_lookahead_search_batch( s->la, n, s->pj_fenc, s->pj_ref, s->pj_list, s->pj_dist ) ) return -1;
-    return 0;
+    double t0_ = st_now();
+    int rc_ = n ? x264cu_lookahead_search_batch( s->la, n, s->pj_fenc, s->pj_ref, s->pj_list, s->pj_dist ) : 0;
+    s->t_batch += st_now() - t0_;
+    return rc_ ? -1 : 0;
 }
 
 static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_device, intptr_t luma_stride, const uint16_t *h_inv_qscale,
@@ -650,8 +668,11 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
         for( int i = 0; i < s->n_slots; i++ )
             if( !s->slot_used[i] ) { slot = i; break; }
         if( slot < 0 || s->n_next >= LOOKAHEAD_MAX + 4 ) return -1;
-        if( on_device ? x264cu_lookahead_frame_put_device( s->la, slot, luma, luma_stride, h_inv_qscale )
-                      : x264cu_lookahead_frame_put( s->la, slot, luma, luma_stride, h_inv_qscale ) ) return -1;
+        double t0_ = st_now();
+        int rc_ = on_device ? x264cu_lookahead_frame_put_device( s->la, slot, luma, luma_stride, h_inv_qscale )
+                            : x264cu_lookahead_frame_put( s->la, slot, luma, luma_stride, h_inv_qscale );
+        s->t_put += st_now() - t0_;
+        if( rc_ ) return -1;
         st_frame_t *f = calloc( 1, sizeof( *f ) );
         if( !f ) return -1;
         f->i_frame = s->i_input++;
@@ -713,13 +734,19 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
 int x264cu_slicetype_step( x264cu_slicetype_t *s, const uint8_t *h_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
                            int *out_frame, int *out_type )
 {
-    return step_common( s, h_luma, 0, luma_stride, h_inv_qscale, out_frame, out_type );
+    double t0 = st_now();
+    int rc = step_common( s, h_luma, 0, luma_stride, h_inv_qscale, out_frame, out_type );
+    if( s ) s->t_step += st_now() - t0;
+    return rc;
 }
 
 int x264cu_slicetype_step_device( x264cu_slicetype_t *s, const uint8_t *d_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
                                   int *out_frame, int *out_type )
 {
-    return step_common( s, d_luma, 1, luma_stride, h_inv_qscale, out_frame, out_type );
+    double t0 = st_now();
+    int rc = step_common( s, d_luma, 1, luma_stride, h_inv_qscale, out_frame, out_type );
+    if( s ) s->t_step += st_now() - t0;
+    return rc;
 }
 
 void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *s, int prefetch ) { if( s ) s->prefetch = !!prefetch; }
