@@ -83,3 +83,4 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n, const int *fen
     (void)la; (void)n; (void)fenc; (void)ref; (void)list; (void)dist;
     return 0;
 }
+void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on ) { (void)la; (void)on; }

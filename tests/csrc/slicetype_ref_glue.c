@@ -67,3 +67,4 @@ int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int i0, int
     if( imb ) *imb = e[2];
     return 0;
 }
+void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on ) { (void)la; (void)on; }

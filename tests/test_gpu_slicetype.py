@@ -57,3 +57,22 @@ def test_prefetch_and_run_ahead_do_not_change_decisions(ctx, mode):
         outs.append(st.decide(frames))
         st.close()
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("async_upload", [0, 1])
+def test_page_locked_pictures_are_read_in_place(ctx, async_upload):
+    """x264cu_lookahead_frame_put from page-locked memory (copied by the DMA engine on the upload stream, no staging copy;
+    with async_upload the call does not wait for it) gives the decisions of the staged path"""
+    w, h, n = 320, 192, 48
+    frames = synth_sequence(w, h, n, seed=9, cut_at=20)
+    st = x.Slicetype(ctx, w, h, rc_lookahead=20, psy=0, aq_mode=0)
+    want = st.decide(frames)
+    st.close()
+    pinned = ctx.malloc_host(n * w * h).reshape(n, h, w)
+    for i in range(n):
+        pinned[i] = frames[i]
+    st = x.Slicetype(ctx, w, h, rc_lookahead=20, psy=0, aq_mode=0)
+    st.set_async_upload(async_upload)
+    got = st.decide([pinned[i] for i in range(n)])
+    st.close()
+    assert got == want

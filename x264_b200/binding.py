@@ -45,7 +45,11 @@ def lib():
         return _lib
     from . import build as _b
     path = _b.LIB
-    if _b.needs_build():
+    if os.environ.get("X264CU_LIB"):          # tuning hook: a variant built by `build.py --variant` (tools/)
+        path = os.environ["X264CU_LIB"]
+        if not os.path.exists(path):
+            raise X264CUError("X264CU_LIB=%s does not exist" % path)
+    elif _b.needs_build():
         if os.path.exists(_b.NVCC):
             path = _b.build()
         elif not os.path.exists(path):

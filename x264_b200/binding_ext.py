@@ -47,6 +47,8 @@ def bind(L):
     L.x264cu_slicetype_step_device.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
     L.x264cu_slicetype_set_prefetch.argtypes = [vp, ci]
     L.x264cu_slicetype_set_run_ahead.argtypes = [vp, ci]
+    L.x264cu_slicetype_set_async_upload.argtypes = [vp, ci]
+    L.x264cu_lookahead_set_async_upload.argtypes = [vp, ci]
     L.x264cu_slicetype_lookahead.argtypes = [vp]
     L.x264cu_slicetype_lookahead.restype = vp
     L.x264cu_slicetype_slot_of.argtypes = [vp, ci]
@@ -208,6 +210,10 @@ class Slicetype:
 
     def set_run_ahead(self, k):
         self.L.x264cu_slicetype_set_run_ahead(self.h, int(k))
+
+    def set_async_upload(self, on):
+        """page-locked pictures passed to step() are read in place; keep them unmodified until the next step() returns"""
+        self.L.x264cu_slicetype_set_async_upload(self.h, int(on))
 
     def decide(self, frames):
         out = []

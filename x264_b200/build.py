@@ -27,19 +27,24 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant: tuning builds (tools/): libx264_b200_<variant>.so with extra -D flags, objects kept apart; the binding
+    loads it instead of the product library when X264CU_LIB points at it."""
+    if not variant and not force and not needs_build():
         return LIB
     cu, c = sources()
     objs = []
     procs = []
+    lib = LIB if not variant else os.path.join(CSRC, "libx264_b200_%s.so" % variant)
+    odir = CSRC if not variant else os.path.join(CSRC, "build", variant)
+    os.makedirs(odir, exist_ok=True)
     for f in cu:
-        o = os.path.join(CSRC, f[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, f), "-o", o]
+        o = os.path.join(odir, f[:-3] + ".o")
+        cmd = [NVCC] + FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, f), "-o", o]
         procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for f in c:
-        o = os.path.join(CSRC, f[:-2] + ".o")
+        o = os.path.join(odir, f[:-2] + ".o")
         cmd = ["gcc", "-O2", "-fPIC", "-std=gnu99", "-Wall", "-I" + os.path.join(HERE, "..", "include"),
                "-c", os.path.join(CSRC, f), "-o", o]
         procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -52,10 +57,12 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("x264_b200: CUDA build failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lm"]
+    cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lm"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

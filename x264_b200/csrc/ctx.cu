@@ -118,6 +118,8 @@ int x264cu_sync( x264cu_ctx_t *ctx )
 {
     if( !ctx ) return -1;
     CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
+    for( cudaStream_t st : ctx->aux_streams )          // uploads / prefetched searches of the lookahead (x264_opencl_flush)
+        CU_CHECK( ctx, cudaStreamSynchronize( st ) );
     return 0;
 }
 

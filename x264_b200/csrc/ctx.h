@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 #include "../../include/x264_b200.h"
 
 struct x264cu_ctx
@@ -25,10 +26,13 @@ struct x264cu_ctx
     size_t scratch_bytes[6] = { 0, 0, 0, 0, 0, 0 };
     struct x264cu_lookahead *lookahead = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaStream_t> aux_streams;   // streams of live lookahead objects: x264cu_sync waits for them too
 };
 
 int  x264cu_fail( x264cu_ctx *ctx, const char *fmt, ... );
 void *x264cu_scratch( x264cu_ctx *ctx, int slot, size_t bytes );
+int  x264cu_frame_init_lowres_on( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d_luma, intptr_t luma_stride, int width, int height,
+                                  uint8_t *const d_lowres[4], intptr_t lowres_stride );
 
 #define CU_CHECK( ctx, call )                                                                      \
     do {                                                                                           \

@@ -131,10 +131,9 @@ hpel_kernel( const uint8_t *__restrict__ src, intptr_t stride, int width, int he
 
 } // namespace
 
-extern "C" {
-
-int x264cu_frame_init_lowres( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, int width, int height,
-                              uint8_t *const d_lowres[4], intptr_t lowres_stride )
+// the same launch on a stream of the caller's choice (the lookahead's upload stream)
+int x264cu_frame_init_lowres_on( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d_luma, intptr_t luma_stride, int width, int height,
+                                 uint8_t *const d_lowres[4], intptr_t lowres_stride )
 {
     if( !ctx ) return -1;
     if( width < 2 || height < 2 ) return x264cu_fail( ctx, "frame_init_lowres: bad size %dx%d", width, height );
@@ -146,10 +145,19 @@ int x264cu_frame_init_lowres( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t
     // the vector fast path needs 8-byte aligned source rows; otherwise every pixel takes the clamped path
     const int aligned = !( (uintptr_t)d_luma & 7 ) && !( luma_stride & 7 );
     dim3 block( 256 ), grid( ( ( wl + 2*X264CU_PAD ) / 4 + 255 ) / 256, ll + 2*X264CU_PAD );
-    lowres_kernel<<<grid, block, 0, ctx->stream>>>( d_luma, luma_stride, width, height, d_lowres[0], d_lowres[1],
-                                                    d_lowres[2], d_lowres[3], lowres_stride, wl, ll, aligned );
+    lowres_kernel<<<grid, block, 0, stream>>>( d_luma, luma_stride, width, height, d_lowres[0], d_lowres[1],
+                                               d_lowres[2], d_lowres[3], lowres_stride, wl, ll, aligned );
     CU_LAUNCH_CHECK( ctx );
     return 0;
+}
+
+extern "C" {
+
+int x264cu_frame_init_lowres( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, int width, int height,
+                              uint8_t *const d_lowres[4], intptr_t lowres_stride )
+{
+    if( !ctx ) return -1;
+    return x264cu_frame_init_lowres_on( ctx, ctx->stream, d_luma, luma_stride, width, height, d_lowres, lowres_stride );
 }
 
 int x264cu_hpel_filter( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, int width, int height,

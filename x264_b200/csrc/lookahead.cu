@@ -91,6 +91,13 @@ __device__ __forceinline__ void load_quad( const uint8_t *p, int stride, uint32_
 #pragma unroll
     for( int r = 0; r < 4; r++ ) a[r] = ldg4u( p + r * stride );
 }
+// the same for a 4-byte aligned address (a quadrant of a macroblock at vector zero: plane origins and strides are multiples
+// of 4): plain word loads, nothing that has to wait for them at the point of issue
+__device__ __forceinline__ void load_quad_aligned( const uint8_t *p, int stride, uint32_t a[4] )
+{
+#pragma unroll
+    for( int r = 0; r < 4; r++ ) a[r] = __ldg( (const uint32_t *)( p + r * stride ) );
+}
 
 // ------------------------------------------------------------------------------------------------
 // intra: slicetype.c:714-757 + predict.c (8x8c DC/H/V/P, 8x8 filtered DDL..HU)
@@ -264,8 +271,11 @@ extern "C" int x264cu_debug_la_profile( unsigned long long *out8, int reset )
 }
 #endif
 
+#ifndef LA_MIN_CTAS
+#define LA_MIN_CTAS 2                                  /* resident CTAs per SM the register allocation is sized for */
+#endif
 template <int NW>
-__global__ void __launch_bounds__( NW * 32 )
+__global__ void __launch_bounds__( NW * 32, LA_MIN_CTAS )
 search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uint16_t *__restrict__ cost_mv_g, int n_jobs,
                unsigned int *__restrict__ ticket )
 {
@@ -336,7 +346,7 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
     if( rec_needed( start_x ) ) nb0 = rec_poll( 0, rrow + start_x );
     if( rec_needed( start_x - 1 ) ) spec = ld_relaxed64( rrow + start_x - 1 );
     uint32_t fenc_next[4];
-    load_quad( job.fenc + ( mb_y * 8 + qy ) * d.stride + start_x * 8 + qx, d.stride, fenc_next );
+    load_quad_aligned( job.fenc + ( mb_y * 8 + qy ) * d.stride + start_x * 8 + qx, d.stride, fenc_next );
 #ifdef LA_PROFILE
     long long pr[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, t_prof = clock64();
 #endif
@@ -361,7 +371,7 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
         int nb1 = 0;                                                           // below-left
         if( rec_needed( mb_x - 1 ) ) nb1 = rec_poll( spec, rrow + mb_x - 1 );
         if( rec_needed( mb_x - 2 ) ) spec = ld_relaxed64( rrow + mb_x - 2 );
-        if( mb_x > end_x ) load_quad( job.fenc + pel - 8 + qy * d.stride + qx, d.stride, fenc_next );
+        if( mb_x > end_x ) load_quad_aligned( job.fenc + pel - 8 + qy * d.stride + qx, d.stride, fenc_next );
         LA_TICK( pr[0], t_prof );
         m.win.base = win_base;
         m.win.bx = mb_x * 8 + qx + 64;
@@ -491,7 +501,7 @@ finalize_kernel( LaDims d, LaFinalizeArgs A )
     if( A.b_inter )
     {
         uint32_t a[4];
-        load_quad( A.fenc + pel, d.stride, a );
+        load_quad_aligned( A.fenc + pel, d.stride, a );
         LaMe m0, m1;
         m0.stride = m1.stride = d.stride;
         m0.w.enabled = m1.w.enabled = 0;
@@ -547,8 +557,8 @@ finalize_kernel( LaDims d, LaFinalizeArgs A )
             // lanes (uniform code), applied per MB
             {
                 uint32_t p1[4], p2[4];
-                load_quad( m0.fref[0], d.stride, p1 );
-                load_quad( m1.fref[0], d.stride, p2 );
+                load_quad_aligned( m0.fref[0], d.stride, p1 );
+                load_quad_aligned( m1.fref[0], d.stride, p2 );
 #pragma unroll
                 for( int r = 0; r < 4; r++ )
                     p1[r] = A.bipred_weight == 32 ? __vavgu4( p1[r], p2[r] ) : avg4w( p1[r], p2[r], A.bipred_weight );
@@ -642,8 +652,8 @@ weight_cost_kernel( LaDims d, const uint8_t *__restrict__ fenc, const uint8_t *_
     const int mb_y = mbc / d.mb_w, mb_x = mbc - mb_y * d.mb_w;
     const int pel = ( mb_y * 8 + ( q >> 1 ) * 4 ) * d.stride + mb_x * 8 + ( q & 1 ) * 4;
     uint32_t a[4], b[4];
-    load_quad( fenc + pel, d.stride, a );
-    load_quad( ref + pel, d.stride, b );
+    load_quad_aligned( fenc + pel, d.stride, a );
+    load_quad_aligned( ref + pel, d.stride, b );
     if( w.enabled )
     {
 #pragma unroll
@@ -686,6 +696,8 @@ struct LaSlotHost
     unsigned long long pixel_sum, pixel_ssd;   // i_pixel_sum[0] / i_pixel_ssd[0] (ratecontrol.c:405-414), valid once stats_ready
     bool stats_ready;
     LaWeight weight;                 // fenc->weight[0][0] of the last lookahead analysis
+    cudaEvent_t ev_ready = nullptr;  // recorded on the upload stream when the picture's planes / reset arrays are in place
+    bool main_waited = true;         // the context's stream has been ordered after ev_ready
 };
 
 struct x264cu_lookahead
@@ -699,7 +711,14 @@ struct x264cu_lookahead
     uint16_t *d_cost_mv = nullptr;
     uint8_t *d_luma = nullptr;       // staging for one full-res luma picture
     size_t luma_bytes = 0;
-    uint8_t *h_luma = nullptr;       // pinned staging
+    uint8_t *h_luma[2] = { nullptr, nullptr };   // pinned staging ring for pictures handed over in pageable memory
+    cudaEvent_t h_luma_ev[2] = {};   // ... each guarded by the event of its last copy
+    unsigned int h_luma_next = 0;
+    cudaStream_t up_stream = nullptr;    // upload stream: H2D copy, lowres planes and slot reset of a queued picture run beside the analysis
+    cudaEvent_t ev_up_guard = nullptr;   // main-stream work queued before a put (it may still read the slot's previous picture)
+    cudaEvent_t ev_zero_copy = nullptr;  // last copy that read the caller's own page-locked buffer
+    bool zero_copy_live = false;
+    bool async_upload = false;           // x264cu_lookahead_set_async_upload
     int32_t *d_record = nullptr, *h_record = nullptr;
     LaJobPack pack;                  // jobs being assembled for the next launch
     cudaStream_t search_streams[2] = {};     // prefetch launches alternate: the drain of one wavefront overlaps the fill of the next
@@ -741,6 +760,8 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     if( !la ) return;
     cudaSetDevice( la->ctx->device );
     cudaStreamSynchronize( la->ctx->stream );
+    if( la->up_stream ) cudaStreamSynchronize( la->up_stream );
+    for( int i = 0; i < 2; i++ ) if( la->search_streams[i] ) cudaStreamSynchronize( la->search_streams[i] );
     if( la->stats_on )
     {
         cudaDeviceSynchronize();
@@ -764,7 +785,17 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     }
     cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record ); cudaFree( la->d_weight_plane ); cudaFree( la->d_tickets );
     cudaFreeHost( la->h_stats );
-    cudaFreeHost( la->h_luma ); cudaFreeHost( la->h_record ); cudaFreeHost( la->h_qscale );
+    {
+        auto &ax = la->ctx->aux_streams;
+        for( size_t i = 0; i < ax.size(); )
+            if( ax[i] == la->up_stream || ax[i] == la->search_streams[0] || ax[i] == la->search_streams[1] ) ax.erase( ax.begin() + i ); else i++;
+    }
+    if( la->up_stream ) { cudaStreamSynchronize( la->up_stream ); cudaStreamDestroy( la->up_stream ); }
+    for( int i = 0; i < 2; i++ ) { cudaFreeHost( la->h_luma[i] ); if( la->h_luma_ev[i] ) cudaEventDestroy( la->h_luma_ev[i] ); }
+    if( la->ev_up_guard ) cudaEventDestroy( la->ev_up_guard );
+    if( la->ev_zero_copy ) cudaEventDestroy( la->ev_zero_copy );
+    for( auto &s : la->slots ) if( s.ev_ready ) cudaEventDestroy( s.ev_ready );
+    cudaFreeHost( la->h_record ); cudaFreeHost( la->h_qscale );
     cudaFree( la->d_qscale_flat );
     for( int i = 0; i < 4; i++ ) if( la->qs_ev[i] ) cudaEventDestroy( la->qs_ev[i] );
     for( int i = 0; i < 2; i++ )
@@ -824,6 +855,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         alloc( (void **)&s.dev.recs, (size_t)2 * B1 * d.mb_count * 8 );
         s.d_stats = nullptr;
         alloc( (void **)&s.d_stats, 16 );
+        if( ok && cudaEventCreateWithFlags( &s.ev_ready, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     }
     la->luma_bytes = (size_t)( ( p->width + 63 ) & ~63 ) * p->height + 64;
     alloc( (void **)&la->d_luma, la->luma_bytes );
@@ -840,7 +872,14 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         if( cudaEventCreateWithFlags( &la->ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false; else la->n_ev++;
     }
     if( ok && cudaEventCreateWithFlags( &la->ev_main, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
-    if( ok && cudaMallocHost( (void **)&la->h_luma, la->luma_bytes ) != cudaSuccess ) ok = false;
+    for( int i = 0; i < 2; i++ )
+    {
+        if( ok && cudaMallocHost( (void **)&la->h_luma[i], la->luma_bytes ) != cudaSuccess ) ok = false;
+        if( ok && cudaEventCreateWithFlags( &la->h_luma_ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
+    }
+    if( ok && cudaStreamCreateWithFlags( &la->up_stream, cudaStreamNonBlocking ) != cudaSuccess ) ok = false;
+    if( ok && cudaEventCreateWithFlags( &la->ev_up_guard, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
+    if( ok && cudaEventCreateWithFlags( &la->ev_zero_copy, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_record, 64 ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_qscale, (size_t)4 * d.mb_count * 2 ) != cudaSuccess ) ok = false;
     for( int i = 0; i < 4 && ok; i++ )
@@ -876,11 +915,13 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         x264cu_lookahead_close( la );
         return -1;
     }
+    ctx->aux_streams.push_back( la->up_stream );
+    for( int i = 0; i < 2; i++ ) ctx->aux_streams.push_back( la->search_streams[i] );
     *out = la;
     return 0;
 }
 
-static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_qscale )
+static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_qscale, cudaStream_t stream )
 {
     x264cu_ctx *ctx = la->ctx;
     LaSlotHost &s = la->slots[slot];
@@ -898,7 +939,7 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
     s.in_use = true;
     s.stats_ready = false;
     s.weight.enabled = 0; s.weight.scale = 1; s.weight.denom = 0; s.weight.offset = 0;
-    CU_CHECK( ctx, cudaMemsetAsync( s.dev.mvs, 0, (size_t)2 * ( d.B + 1 ) * d.mb_count * 4, ctx->stream ) );
+    CU_CHECK( ctx, cudaMemsetAsync( s.dev.mvs, 0, (size_t)2 * ( d.B + 1 ) * d.mb_count * 4, stream ) );
     if( h_inv_qscale )
     {   // staged through a ring of pinned buffers: the caller's array may be reused as soon as this returns, and the
         // calling thread never waits for the stream
@@ -906,11 +947,56 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
         uint16_t *stage = la->h_qscale + (size_t)k * d.mb_count;
         LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->qs_ev[k] ) ) );
         memcpy( stage, h_inv_qscale, d.mb_count * 2 );
-        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, stage, d.mb_count * 2, cudaMemcpyHostToDevice, ctx->stream ) );
-        CU_CHECK( ctx, cudaEventRecord( la->qs_ev[k], ctx->stream ) );
+        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, stage, d.mb_count * 2, cudaMemcpyHostToDevice, stream ) );
+        CU_CHECK( ctx, cudaEventRecord( la->qs_ev[k], stream ) );
     }
     else        // no AQ: every factor is 256 (x264_adaptive_quant_frame with aq off, ratecontrol.c:308-330)
-        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, la->d_qscale_flat, d.mb_count * 2, cudaMemcpyDeviceToDevice, ctx->stream ) );
+        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qscale, la->d_qscale_flat, d.mb_count * 2, cudaMemcpyDeviceToDevice, stream ) );
+    return 0;
+}
+
+// Order the upload stream after everything that may still read the picture leaving `slot`: the work queued so far on the
+// context's stream (cost requests, on-demand searches) and the prefetched searches in flight.
+static int la_put_begin( x264cu_lookahead *la )
+{
+    x264cu_ctx *ctx = la->ctx;
+    CU_CHECK( ctx, cudaEventRecord( la->ev_up_guard, ctx->stream ) );
+    CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev_up_guard, 0 ) );
+    for( int i = 0; i < 2; i++ )
+        if( la->last_ev_of[i] >= 0 )
+            CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev[la->last_ev_of[i]], 0 ) );
+    return 0;
+}
+
+// lowres planes, luma statistics and memo reset of `slot` from a picture in HBM, all on the upload stream; the slot's
+// ev_ready is what its later readers (searches, cost requests, read-backs) are ordered after
+static int la_put_finish( x264cu_lookahead *la, int slot, const uint8_t *d_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale )
+{
+    x264cu_ctx *ctx = la->ctx;
+    LaSlotHost &s = la->slots[slot];
+    if( x264cu_frame_init_lowres_on( ctx, la->up_stream, d_luma, luma_stride, la->p.width, la->p.height, s.dev.planes, la->d.stride ) ) return -1;
+    if( la->p.weighted_pred )
+    {
+        CU_CHECK( ctx, cudaMemsetAsync( s.d_stats, 0, 16, la->up_stream ) );
+        luma_stats_kernel<<<ctx->sm_count * 2, 256, 0, la->up_stream>>>( d_luma, luma_stride, la->p.width, la->p.height,
+                                                                        la->d.mb_w * 16, la->d.mb_h * 16, s.d_stats );
+        CU_LAUNCH_CHECK( ctx );
+    }
+    if( la_reset_slot( la, slot, h_inv_qscale, la->up_stream ) ) return -1;
+    CU_CHECK( ctx, cudaEventRecord( s.ev_ready, la->up_stream ) );
+    s.main_waited = false;
+    return 0;
+}
+
+// the context's stream reads `slot` next: order it after the slot's upload (once per picture)
+static int la_slot_ready( x264cu_lookahead *la, int slot )
+{
+    LaSlotHost &s = la->slots[slot];
+    if( !s.main_waited )
+    {
+        CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, s.ev_ready, 0 ) );
+        s.main_waited = true;
+    }
     return 0;
 }
 
@@ -919,21 +1005,12 @@ int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const u
 {
     if( !la ) return -1;
     if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( la->ctx, "frame_put: slot %d out of range", slot );
-    LaSlotHost &s = la->slots[slot];
-    // prefetched searches may still be reading the picture that occupied this slot
-    for( int i = 0; i < 2; i++ )
-        if( la->last_ev_of[i] >= 0 )
-            CU_CHECK( la->ctx, cudaStreamWaitEvent( la->ctx->stream, la->ev[la->last_ev_of[i]], 0 ) );
-    if( x264cu_frame_init_lowres( la->ctx, d_luma, luma_stride, la->p.width, la->p.height, s.dev.planes, la->d.stride ) ) return -1;
-    if( la->p.weighted_pred )
-    {
-        CU_CHECK( la->ctx, cudaMemsetAsync( s.d_stats, 0, 16, la->ctx->stream ) );
-        luma_stats_kernel<<<la->ctx->sm_count * 2, 256, 0, la->ctx->stream>>>( d_luma, luma_stride, la->p.width, la->p.height,
-                                                                               la->d.mb_w * 16, la->d.mb_h * 16, s.d_stats );
-        CU_LAUNCH_CHECK( la->ctx );
-    }
-    return la_reset_slot( la, slot, h_inv_qscale );
+    // d_luma is complete in the context's stream order (la_put_begin orders the upload stream after that stream)
+    if( la_put_begin( la ) ) return -1;
+    return la_put_finish( la, slot, d_luma, luma_stride, h_inv_qscale );
 }
+
+void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on ) { if( la ) la->async_upload = on != 0; }
 
 int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
                                 const uint16_t *h_inv_qscale )
@@ -943,11 +1020,33 @@ int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t 
     if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( ctx, "frame_put: slot %d out of range", slot );
     const int w = la->p.width, h = la->p.height;
     const intptr_t st = ( w + 63 ) & ~63;
-    CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );               // staging buffer free again
-    for( int y = 0; y < h; y++ )
-        memcpy( la->h_luma + y * st, h_luma + y * luma_stride, w );
-    CU_CHECK( ctx, cudaMemcpyAsync( la->d_luma, la->h_luma, (size_t)st * h, cudaMemcpyHostToDevice, ctx->stream ) );
-    return x264cu_lookahead_frame_put_device( la, slot, la->d_luma, st, h_inv_qscale );
+    if( la->zero_copy_live )
+    {   // the previous picture was read in place: that copy ended long ago in steady state
+        LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->ev_zero_copy ) ) );
+        la->zero_copy_live = false;
+    }
+    if( la_put_begin( la ) ) return -1;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes( &at, h_luma ) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    if( !pinned ) cudaGetLastError();
+    if( pinned )
+    {   // page-locked source (x264cu_malloc_host, like the reference's pinned page-locked staging, opencl.h:718): the DMA
+        // engine reads it in place, the calling thread neither copies nor waits
+        CU_CHECK( ctx, cudaMemcpy2DAsync( la->d_luma, st, h_luma, luma_stride, w, h, cudaMemcpyHostToDevice, la->up_stream ) );
+        CU_CHECK( ctx, cudaEventRecord( la->ev_zero_copy, la->up_stream ) );
+        if( la->async_upload ) la->zero_copy_live = true;
+        else LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->ev_zero_copy ) ) );
+    }
+    else
+    {   // pageable source: staged through a ring of two pinned buffers, so that the caller's buffer is free on return
+        const int k = la->h_luma_next++ & 1;
+        LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->h_luma_ev[k] ) ) );
+        for( int y = 0; y < h; y++ )
+            memcpy( la->h_luma[k] + y * st, h_luma + y * luma_stride, w );
+        CU_CHECK( ctx, cudaMemcpyAsync( la->d_luma, la->h_luma[k], (size_t)st * h, cudaMemcpyHostToDevice, la->up_stream ) );
+        CU_CHECK( ctx, cudaEventRecord( la->h_luma_ev[k], la->up_stream ) );
+    }
+    return la_put_finish( la, slot, la->d_luma, st, h_inv_qscale );
 }
 
 // enqueue the n searches assembled in la->pack as one launch on `stream` (no host synchronisation)
@@ -1030,6 +1129,16 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
     int n = 0, launched = 0;
     struct Mark { int slot, list, dm1; };
     std::vector<Mark> marks;
+    {   // the pictures of these jobs may still be on their way in on the upload stream
+        std::vector<char> seen( la->slots.size(), 0 );
+        for( int i = 0; i < n_jobs; i++ )
+            for( int sl : { fenc[i], ref[i] } )
+                if( sl >= 0 && sl < (int)la->slots.size() && !seen[sl] )
+                {
+                    seen[sl] = 1;
+                    CU_CHECK( ctx, cudaStreamWaitEvent( la->search_stream, la->slots[sl].ev_ready, 0 ) );
+                }
+    }
     for( int i = 0; i < n_jobs; i++ )
     {
         if( fenc[i] < 0 || fenc[i] >= (int)la->slots.size() || ref[i] < 0 || ref[i] >= (int)la->slots.size() ||
@@ -1175,6 +1284,8 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
         if( s < 0 || s >= (int)la->slots.size() || !la->slots[s].in_use ) return x264cu_fail( ctx, "frame_cost: empty slot %d", s );
     LaSlotHost &fenc = la->slots[sb];
     const int i0 = b - p0, i1 = p1 - b;
+    for( int s : { sb, s0, s1 } )
+        if( la_slot_ready( la, s ) ) return -1;
     // memo check, slicetype.c:848-849
     if( fenc.cost_est[i0][i1] >= 0 && ( !la->p.vbv || fenc.row_satds_valid[i0][i1] ) )
     {
@@ -1285,7 +1396,7 @@ static int la_check_slot( x264cu_lookahead *la, int slot )
     for( int i = 0; i < 2; i++ ) cudaStreamSynchronize( la->search_streams[i] );          // read-backs see prefetched searches too
     if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use )
         return x264cu_fail( la->ctx, "lookahead: slot %d is empty / out of range", slot );
-    return 0;
+    return la_slot_ready( la, slot );
 }
 
 int x264cu_lookahead_get_mvs( x264cu_lookahead_t *la, int slot, int list, int dist_minus1, int16_t *h_mvs, int32_t *h_mv_costs )

@@ -43,13 +43,22 @@ __device__ __forceinline__ uint32_t weight4( uint32_t v, const LaWeight &w )   /
     return out;
 }
 
+// four rows at once, out of line: the search kernel calls it from many inlined sites but only for weighted references
+static __device__ __noinline__ uint4 weight4x4( uint4 v, int enabled, int scale, int denom, int offset )
+{
+    LaWeight w = { enabled, scale, denom, offset };
+    return make_uint4( weight4( v.x, w ), weight4( v.y, w ), weight4( v.z, w ), weight4( v.w, w ) );
+}
+
 // Per-warp shared-memory window of the four reference planes around the warp's macroblock row.  The search warp walks
 // its row right to left; the window is, per plane, LA_WIN_ROWS rows of a 64-byte ring of columns (8 chunks of 8 px, one
 // per macroblock step: byte = biased column & 63) at a pitch of 72 bytes -- the 4 rows of a 4x4 read sit at immediate
-// offsets, and the quadrant 4 rows further down falls into other banks.  13.5 KB per warp: two 8-warp CTAs per SM.  A candidate whose pixels lie outside the loaded chunks / rows (motion beyond
-// about +-20 lowres pixels) is read from global memory instead (same values, slower).
-#define LA_WIN_ROWS 48
-#define LA_WIN_VR 20                                   /* rows above the MB row: window rows = -20 .. +27 */
+// offsets, and the quadrant 4 rows further down falls into other banks.  9 KB per warp.  A candidate whose pixels lie outside the loaded chunks / rows (motion beyond
+// +-12 lowres pixels vertically, about +-24 horizontally) is read from global memory instead (same values, slower).
+#ifndef LA_WIN_ROWS
+#define LA_WIN_ROWS 32                                 /* measured: 32 rows (motion within +-12) beat 48 by 16 % at 4K: a third fewer */
+#define LA_WIN_VR 12                                   /* cp.async per step.  Rows above the MB row: window rows = -12 .. +19 */
+#endif
 #define LA_WIN_PITCH 72
 #define LA_WIN_PLANE ( LA_WIN_ROWS * LA_WIN_PITCH )
 #define LA_WIN_BYTES ( 4 * LA_WIN_PLANE )
@@ -94,7 +103,9 @@ struct LaMe
 
 #define LA_COST_HALF 512          /* mv - mvp distances (quarter-pel) kept in shared memory: +-128 pixels */
 
-// p_cost_mv[idx] (analyse.c:143-202 table, centred): the entries a search normally touches are in shared memory
+// p_cost_mv[idx] (analyse.c:143-202 table, centred): the entries a search normally touches are in shared memory; a vector
+// further than 128 pixels from its predictor takes the out-of-line global read
+static __device__ __noinline__ int la_cost_far( const uint16_t *cost_mv, int idx ) { return __ldg( cost_mv + idx ); }
 __device__ __forceinline__ int la_cost( const LaMe &m, int idx )
 {
     if( (unsigned)( idx + LA_COST_HALF ) <= 2u * LA_COST_HALF )
@@ -103,21 +114,53 @@ __device__ __forceinline__ int la_cost( const LaMe &m, int idx )
         asm volatile( "ld.shared.u16 %0, [%1];" : "=r"( v ) : "r"( m.cost_s + 2 * idx ) );
         return (int)v;
     }
-    return __ldg( m.cost_mv + idx );
+    return la_cost_far( m.cost_mv, idx );
 }
 
 #define LA_PLANE_W 4              /* la_load4 plane selector: the (possibly weighted) full-pel search plane */
 
-// this lane's 4x4 of plane `plane` (0..3 = F,H,V,C unweighted, LA_PLANE_W = fref_w) displaced by (dx,dy) full pixels
+// The rare path of la_load4, out of line (one copy instead of one per call site): some lane's block lies outside the
+// shared-memory window (motion beyond the window's reach, or the unweighted F plane while the window holds the weighted
+// one).  Lanes inside the window still read it; the others read the plane itself.  Scalars only: a reference to the
+// register-resident LaMe would force it into local memory.
+static __device__ __noinline__ uint4 la_load4_mixed( bool in_win, uint32_t pb, int x, const uint8_t *g, int stride )
+{
+    uint4 v;
+    if( in_win )
+    {
+        const uint32_t a0 = pb + ( x & 60 ), a1 = pb + ( ( x + 4 ) & 60 );
+        const uint32_t sh = ( (uint32_t)x & 3u ) * 8u;
+        v.x = __funnelshift_r( la_lds<0>( a0 ), la_lds<0>( a1 ), sh );
+        v.y = __funnelshift_r( la_lds<LA_WIN_PITCH>( a0 ), la_lds<LA_WIN_PITCH>( a1 ), sh );
+        v.z = __funnelshift_r( la_lds<2 * LA_WIN_PITCH>( a0 ), la_lds<2 * LA_WIN_PITCH>( a1 ), sh );
+        v.w = __funnelshift_r( la_lds<3 * LA_WIN_PITCH>( a0 ), la_lds<3 * LA_WIN_PITCH>( a1 ), sh );
+    }
+    else
+    {
+        v.x = ldg4u( g ); v.y = ldg4u( g + stride ); v.z = ldg4u( g + 2 * stride ); v.w = ldg4u( g + 3 * stride );
+    }
+    return v;
+}
+
+// this lane's 4x4 of plane `plane` (0..3 = F,H,V,C unweighted, LA_PLANE_W = fref_w) displaced by (dx,dy) full pixels.
+// With the window on (search kernel) every lane of the warp must call it together (warp votes inside).
 __device__ __forceinline__ void la_load4( const LaMe &m, int plane, int dx, int dy, uint32_t b[4] )
 {
     const LaWin &w = m.win;
+    if( !w.on )
+    {   // finalize / weight kernels: straight from the planes (L2-resident)
+        const uint8_t *s = plane == LA_PLANE_W ? m.fref_w : plane == 0 ? m.fref[0] : plane == 1 ? m.fref[1] : plane == 2 ? m.fref[2] : m.fref[3];
+        s += dy * m.stride + dx;
+#pragma unroll
+        for( int i = 0; i < 4; i++ ) b[i] = ldg4u( s + i * m.stride );
+        return;
+    }
     const int x = w.bx + dx, r = w.ry + dy;
-    const bool in_win = w.on && (unsigned)( dx - w.dxlo ) <= w.dxspan && (unsigned)r <= LA_WIN_ROWS - 4 && !( plane == 0 && w.p0w );
-    if( in_win )
+    const bool in_win = (unsigned)( dx - w.dxlo ) <= w.dxspan && (unsigned)r <= LA_WIN_ROWS - 4 && !( plane == 0 && w.p0w );
+    const int slot = plane == LA_PLANE_W ? 0 : plane;
+    const uint32_t pb = w.base + slot * LA_WIN_PLANE + r * LA_WIN_PITCH;
+    if( __all_sync( 0xffffffffu, in_win ) )
     {
-        const int slot = plane == LA_PLANE_W ? 0 : plane;
-        const uint32_t pb = w.base + slot * LA_WIN_PLANE + r * LA_WIN_PITCH;
         const uint32_t a0 = pb + ( x & 60 ), a1 = pb + ( ( x + 4 ) & 60 );
         const uint32_t sh = ( (uint32_t)x & 3u ) * 8u;
         b[0] = __funnelshift_r( la_lds<0>( a0 ), la_lds<0>( a1 ), sh );
@@ -128,13 +171,14 @@ __device__ __forceinline__ void la_load4( const LaMe &m, int plane, int dx, int 
     else
     {
         const uint8_t *s = plane == LA_PLANE_W ? m.fref_w : plane == 0 ? m.fref[0] : plane == 1 ? m.fref[1] : plane == 2 ? m.fref[2] : m.fref[3];
-        s += dy * m.stride + dx;
-#pragma unroll
-        for( int i = 0; i < 4; i++ ) b[i] = ldg4u( s + i * m.stride );
+        const uint4 v = la_load4_mixed( in_win, pb, x, s + dy * m.stride + dx, m.stride );
+        b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
     }
 }
 
-// get_ref (common/mc.c:198-249, tables.c:183-184): this lane's 4x4 of the block interpolated at quarter-pel mv
+// get_ref (common/mc.c:198-249, tables.c:183-184): this lane's 4x4 of the block interpolated at quarter-pel mv.
+// Warp-uniform control flow: the second plane is read by every lane as soon as one lane needs it (a lane that does not
+// reads its first block again: (a+a+1)>>1 == a).
 __device__ __forceinline__ void qpel4x4( const LaMe &m, int mvx, int mvy, uint32_t b[4] )
 {
     // hpel_ref0 = {0,1,1,1,0,1,1,1,2,3,3,3,0,1,1,1}, hpel_ref1 = {0,0,1,0,2,2,3,2,2,2,3,2,2,2,3,2}: 2 bits each
@@ -142,18 +186,20 @@ __device__ __forceinline__ void qpel4x4( const LaMe &m, int mvx, int mvy, uint32
     const uint32_t R1 = 0xBABABA10u;    // 0,0,1,0, 2,2,3,2, 2,2,3,2, 2,2,3,2
     const int idx = ( ( mvy & 3 ) << 2 ) + ( mvx & 3 );
     const int fx = mvx >> 2, fy = mvy >> 2;
-    la_load4( m, ( R0 >> ( 2*idx ) ) & 3, fx, fy + ( ( mvy & 3 ) == 3 ), b );
-    if( idx & 5 )
+    const int p0 = ( R0 >> ( 2*idx ) ) & 3, y0 = fy + ( ( mvy & 3 ) == 3 );
+    la_load4( m, p0, fx, y0, b );
+    const bool two = ( idx & 5 ) != 0;
+    if( !m.win.on ? two : __any_sync( 0xffffffffu, two ) )
     {
         uint32_t c[4];
-        la_load4( m, ( R1 >> ( 2*idx ) ) & 3, fx + ( ( mvx & 3 ) == 3 ), fy, c );
+        la_load4( m, two ? ( R1 >> ( 2*idx ) ) & 3 : p0, two ? fx + ( ( mvx & 3 ) == 3 ) : fx, two ? fy : y0, c );
 #pragma unroll
         for( int r = 0; r < 4; r++ ) b[r] = __vavgu4( b[r], c[r] );      // (a+b+1)>>1
     }
     if( m.w.enabled )
     {
-#pragma unroll
-        for( int r = 0; r < 4; r++ ) b[r] = weight4( b[r], m.w );
+        const uint4 v = weight4x4( make_uint4( b[0], b[1], b[2], b[3] ), 1, m.w.scale, m.w.denom, m.w.offset );
+        b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
     }
 }
 

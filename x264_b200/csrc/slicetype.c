@@ -756,6 +756,8 @@ void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *s, int pictures )
     if( s && !s->i_input && pictures >= 0 && pictures <= 16 ) s->run_ahead = pictures;
 }
 
+void x264cu_slicetype_set_async_upload( x264cu_slicetype_t *s, int on ) { if( s ) x264cu_lookahead_set_async_upload( s->la, on ); }
+
 x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *s ) { return s ? s->la : NULL; }
 
 int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame )
