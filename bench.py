@@ -466,7 +466,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
         st.step(frames[i])
     barrier(dist, local)
     t1 = time.perf_counter()
-    e2e_steps = 1 if args.quick else max(1, min(args.steps, 3))
+    e2e_steps = 3 if args.quick else max(1, min(args.steps, 10))
     e2e_types = []
     for _ in range(e2e_steps):
         for i in range(n):
@@ -491,7 +491,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
                                "mb-tree requests, scenecut 40; lookahead weightp analysis %s, aq off)" % (n, "on" if args.weightp else "off"),
                    "l2": "each picture's 4 lowres planes (9.4 MB) stay L2-resident by design; pictures cycle through %d MB" % (frames.nbytes // 2**20),
                    "cost_requests_per_step": requests / args.steps, "decided_per_step": len(decided) / (args.steps + max(args.warmup, 3)),
-                   "scheduling": "searches prefetched on a second stream in groups of 4 pictures, decisions run 8 pictures behind (sync-lookahead twin)",
+                   "scheduling": "searches prefetched on two low-priority streams in groups of 12 pictures (84 searches per launch), decisions run 24 pictures behind the newest one (sync-lookahead twin); uploads on their own stream",
                    "multi_gpu": "one independent stream per GPU; one NCCL all-gather of decision records (%d streams gathered)" % gathered_streams},
         "clocks": clocks,
         "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),

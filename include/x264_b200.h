@@ -204,6 +204,12 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
  * time does not change any later x264cu_lookahead_frame_cost result.  Already-searched jobs are skipped. */
 int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int *fenc, const int *ref,
                                    const int *list, const int *dist );
+/* 1 if x264_weights_analyse( fenc, ref ) would leave at its early exit (means and variances of the two pictures agree:
+ * no weight, slicetype.c:316-330) -- then the list-0 search of that pair is the same whether it is first requested as a P or
+ * as a B cost, and may be run ahead of time with x264cu_lookahead_search_batch.  0 if a weight may be chosen (fade): that
+ * search must wait for its first cost request.  Always 1 without weighted prediction.  -1 on error.  Waits for the uploads
+ * of the two pictures only (their luma statistics travel back with them). */
+int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int fenc_slot, int ref_slot );
 /* x264_opencl_flush without the host block (encoder/slicetype-cl.c:100-127): order the context's stream after every
  * search queued by x264cu_lookahead_search_batch, so that work (or a timer event) queued next sees them finished */
 int x264cu_lookahead_join( x264cu_lookahead_t *la );
@@ -264,7 +270,7 @@ int  x264cu_slicetype_step_device( x264cu_slicetype_t *st, const uint8_t *d_luma
  * launched at once on a second stream (the x264_opencl_slicetype_prep idea, encoder/slicetype-cl.c:653); 0: every search
  * runs on demand inside the cost request that needs it.  The decisions are identical either way. */
 void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *st, int prefetch );
-/* pictures queued beyond the lookahead before a decision is taken (0..16; default 8 for lookaheads >= 12, else 0; must be
+/* pictures queued beyond the lookahead before a decision is taken (0..32; default 24 for lookaheads >= 12, else 0; must be
  * set before the first picture).  It is the synchronous twin of param.i_sync_lookahead (encoder.c:1137-1141, :1611): the
  * analysis never looks at more than i_slicetype_length+1 pictures (b_deterministic, slicetype.c:1480-1485), so the
  * decisions do not change -- only the searches of the newest pictures get time to finish on the second stream. */

@@ -68,3 +68,4 @@ int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int i0, int
     return 0;
 }
 void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on ) { (void)la; (void)on; }
+int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int a, int b ) { (void)la; (void)a; (void)b; return 0; }

@@ -44,7 +44,7 @@ def test_gpu_frame_types(ctx, case):
     assert got == want, (case, [z for z in zip(got, want) if z[0] != z[1]][:6])
 
 
-@pytest.mark.parametrize("mode", [(0, 0), (1, 0), (1, 5), (0, 16)])
+@pytest.mark.parametrize("mode", [(0, 0), (1, 0), (1, 5), (0, 16), (1, 24), (1, 32)])
 def test_prefetch_and_run_ahead_do_not_change_decisions(ctx, mode):
     prefetch, run_ahead = mode
     w, h, n = 320, 192, 60
@@ -76,3 +76,23 @@ def test_page_locked_pictures_are_read_in_place(ctx, async_upload):
     got = st.decide([pinned[i] for i in range(n)])
     st.close()
     assert got == want
+
+
+@pytest.mark.parametrize("mode", [(1, 0), (1, 24)])
+def test_prefetch_with_weighted_prediction(ctx, mode):
+    """with the lookahead's weight analysis on, list-0 searches are run ahead of time only for pairs whose analysis ends at
+    its early exit (x264cu_lookahead_weight_trivial); a fade (weights chosen) and a cut in the sequence: same decisions and
+    same per-picture weights as the on-demand path"""
+    prefetch, run_ahead = mode
+    w, h, n = 320, 192, 60
+    frames = synth_sequence(w, h, n, seed=11, cut_at=40)
+    for i in range(12):                      # fade-in: weights are chosen here
+        frames[i] = np.clip(frames[i].astype(np.float32) * (0.3 + 0.06 * i) + 3 * i, 0, 255).astype(np.uint8)
+    outs = []
+    for pf, ra in ((0, 0), (prefetch, run_ahead)):
+        st = x.Slicetype(ctx, w, h, rc_lookahead=20, psy=1, aq_mode=0, weighted_pred=1)
+        st.set_prefetch(pf)
+        st.set_run_ahead(ra)
+        outs.append(st.decide(frames))
+        st.close()
+    assert outs[0] == outs[1]

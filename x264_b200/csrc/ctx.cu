@@ -64,7 +64,11 @@ int x264cu_open( x264cu_ctx_t **out, int device )
     ctx->cc_major = prop.major;
     ctx->cc_minor = prop.minor;
     ctx->hbm_bytes = prop.totalGlobalMem;
-    if( ( e = cudaStreamCreateWithFlags( &ctx->stream, cudaStreamNonBlocking ) ) != cudaSuccess )
+    // highest priority: what the calling thread waits for (cost requests) is placed ahead of the lookahead's background
+    // streams (prefetched searches) whenever an SM has room
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange( &prio_lo, &prio_hi );
+    if( ( e = cudaStreamCreateWithPriority( &ctx->stream, cudaStreamNonBlocking, prio_hi ) ) != cudaSuccess )
     {
         x264cu_fail( nullptr, "x264cu_open: cudaStreamCreate -> %s", cudaGetErrorString( e ) );
         delete ctx;

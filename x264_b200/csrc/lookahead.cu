@@ -65,7 +65,9 @@ struct LaSearchJob
     int w_enabled, w_scale, w_denom, w_offset;
 };
 
-#define LA_PACK 40
+#ifndef LA_PACK
+#define LA_PACK 128                 /* 96 bytes each: 12 KB of kernel parameters */
+#endif
 struct LaJobPack { LaSearchJob j[LA_PACK]; };     // passed by value as a kernel parameter: no staging copy, no sync
 
 struct LaFinalizeArgs
@@ -274,8 +276,13 @@ extern "C" int x264cu_debug_la_profile( unsigned long long *out8, int reset )
 #ifndef LA_MIN_CTAS
 #define LA_MIN_CTAS 2                                  /* resident CTAs per SM the register allocation is sized for */
 #endif
+#ifdef LA_MAXNREG
+#define LA_SEARCH_BOUNDS __maxnreg__( LA_MAXNREG )
+#else
+#define LA_SEARCH_BOUNDS __launch_bounds__( NW * 32, LA_MIN_CTAS )
+#endif
 template <int NW>
-__global__ void __launch_bounds__( NW * 32, LA_MIN_CTAS )
+__global__ void LA_SEARCH_BOUNDS
 search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uint16_t *__restrict__ cost_mv_g, int n_jobs,
                unsigned int *__restrict__ ticket )
 {
@@ -336,9 +343,13 @@ search_kernel( const LaDims d, const __grid_constant__ LaJobPack jobs, const uin
     const unsigned long long *rrow = job.recs + ( mb_y + 1 ) * d.mb_w;       // dereferenced only where rec_needed()
     // columns / rows outside the searched range are never written: they read as the reset value, zero
     auto rec_needed = [&]( int c ) { return has_below && mb_y + 1 <= start_y && c >= end_x && c <= start_x; };
+#ifndef LA_POLL_SPINS
+#define LA_POLL_SPINS 16
+#define LA_POLL_NS 40
+#endif
     auto rec_poll = [&]( unsigned long long r, const unsigned long long *p ) {
         for( int spins = 0; (unsigned int)( r >> 32 ) != job.gen; r = ld_relaxed64( p ) )
-            if( ++spins > 16 ) __nanosleep( 40 );
+            if( ++spins > LA_POLL_SPINS ) __nanosleep( LA_POLL_NS );
         return (int)(unsigned int)r;
     };
     int nb0 = 0, nb2 = 0;                                                      // below, below-right
@@ -480,12 +491,15 @@ __device__ __forceinline__ uint32_t avg4w( uint32_t a, uint32_t b, int weight ) 
     return out;
 }
 
-__global__ void __launch_bounds__( 256 )
+// 128-thread blocks at <= 64 registers: one fits on an SM beside two resident search CTAs (LA_FIN_THREADS * 64 registers are
+// what the search kernel's register cap leaves free), so a cost request does not wait for a search CTA to retire
+#define LA_FIN_THREADS 128
+__global__ void __launch_bounds__( LA_FIN_THREADS, 8 )
 finalize_kernel( LaDims d, LaFinalizeArgs A )
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = lane & 3;
-    const int mb = ( blockIdx.x * 8 + warp ) * 8 + ( lane >> 2 );
+    const int mb = ( blockIdx.x * ( blockDim.x >> 5 ) + warp ) * 8 + ( lane >> 2 );
     const bool in_frame = mb < d.mb_count;
     const int mbc = in_frame ? mb : d.mb_count - 1;
     const int mb_y = mbc / d.mb_w, mb_x = mbc - mb_y * d.mb_w;
@@ -690,7 +704,8 @@ struct LaSlotHost
     int intra_mbs[LA_MAX_B + 2];
     bool row_satds_valid[LA_MAX_B + 2][LA_MAX_B + 2];
     unsigned int gen = 0;            // bumped at every reset: stale (gen << 32 | mv) records of earlier pictures are invalid
-    bool searched[2][LA_MAX_B + 1];  // the 0x7FFF sentinel of lowres_mvs[l][d][0][0], kept on the host
+    bool searched[2][LA_MAX_B + 1];  // a search of this (list, distance) has been launched (on demand or ahead of time)
+    bool requested[2][LA_MAX_B + 1]; // ... and a cost request has asked for it: the reference's 0x7FFF sentinel of lowres_mvs[l][d][0][0] is gone
     int pending[2][LA_MAX_B + 1];    // event index of a prefetched search still in flight on the search stream, or -1
     unsigned long long *d_stats;     // {sum, sum of squares} of the mod-16 luma
     unsigned long long pixel_sum, pixel_ssd;   // i_pixel_sum[0] / i_pixel_ssd[0] (ratecontrol.c:405-414), valid once stats_ready
@@ -863,9 +878,11 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     alloc( (void **)&la->d_record, 64 );
     alloc( (void **)&la->d_weight_plane, la->plane_bytes );
     alloc( (void **)&la->d_tickets, 64 * 4 );
-    if( ok && cudaMallocHost( (void **)&la->h_stats, 16 ) != cudaSuccess ) ok = false;
-    for( int i = 0; i < 2; i++ )
-        if( cudaStreamCreateWithFlags( &la->search_streams[i], cudaStreamNonBlocking ) != cudaSuccess ) ok = false;
+    if( ok && cudaMallocHost( (void **)&la->h_stats, 16 * (size_t)p->n_slots ) != cudaSuccess ) ok = false;   // {sum, sqr} per slot
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange( &prio_lo, &prio_hi );
+    for( int i = 0; i < 2; i++ )        // background work: lowest priority (the context's stream has the highest)
+        if( cudaStreamCreateWithPriority( &la->search_streams[i], cudaStreamNonBlocking, prio_lo ) != cudaSuccess ) ok = false;
     la->search_stream = la->search_streams[0];
     for( int i = 0; ok && i < 64; i++ )
     {
@@ -877,7 +894,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         if( ok && cudaMallocHost( (void **)&la->h_luma[i], la->luma_bytes ) != cudaSuccess ) ok = false;
         if( ok && cudaEventCreateWithFlags( &la->h_luma_ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     }
-    if( ok && cudaStreamCreateWithFlags( &la->up_stream, cudaStreamNonBlocking ) != cudaSuccess ) ok = false;
+    if( ok && cudaStreamCreateWithPriority( &la->up_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->ev_up_guard, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->ev_zero_copy, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_record, 64 ) != cudaSuccess ) ok = false;
@@ -932,6 +949,7 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
     memset( s.intra_mbs, 0, sizeof( s.intra_mbs ) );
     memset( s.row_satds_valid, 0, sizeof( s.row_satds_valid ) );
     memset( s.searched, 0, sizeof( s.searched ) );
+    memset( s.requested, 0, sizeof( s.requested ) );
     memset( s.pending, -1, sizeof( s.pending ) );
     s.b_intra_calculated = 0;
     s.gen++;
@@ -981,8 +999,14 @@ static int la_put_finish( x264cu_lookahead *la, int slot, const uint8_t *d_luma,
         luma_stats_kernel<<<ctx->sm_count * 2, 256, 0, la->up_stream>>>( d_luma, luma_stride, la->p.width, la->p.height,
                                                                         la->d.mb_w * 16, la->d.mb_h * 16, s.d_stats );
         CU_LAUNCH_CHECK( ctx );
+        // read back with the upload: whoever needs the statistics waits for this slot's ev_ready, not for a stream
+        CU_CHECK( ctx, cudaMemcpyAsync( la->h_stats + 2 * slot, s.d_stats, 16, cudaMemcpyDeviceToHost, la->up_stream ) );
     }
     if( la_reset_slot( la, slot, h_inv_qscale, la->up_stream ) ) return -1;
+    // the intra costs are a function of the picture alone (slicetype.c:714-757): computed here, off the request path
+    intra_kernel<<<( la->d.mb_count + 63 ) / 64, 256, 0, la->up_stream>>>( la->d, s.dev.planes[0], s.dev.intra );
+    CU_LAUNCH_CHECK( ctx );
+    s.intra_on_device = true;
     CU_CHECK( ctx, cudaEventRecord( s.ev_ready, la->up_stream ) );
     s.main_waited = false;
     return 0;
@@ -1188,9 +1212,9 @@ static int la_fetch_stats( x264cu_lookahead *la, LaSlotHost &s )
 {
     if( s.stats_ready ) return 0;
     x264cu_ctx *ctx = la->ctx;
-    CU_CHECK( ctx, cudaMemcpyAsync( la->h_stats, s.d_stats, 16, cudaMemcpyDeviceToHost, ctx->stream ) );
-    CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
-    const unsigned long long sum = la->h_stats[0], sqr = la->h_stats[1];
+    const size_t slot = &s - la->slots.data();
+    LA_TIMED( la->st.weight_sync, la->st.n_weight, CU_CHECK( ctx, cudaEventSynchronize( s.ev_ready ) ) );
+    const unsigned long long sum = la->h_stats[2 * slot], sqr = la->h_stats[2 * slot + 1];
     const unsigned long long N = (unsigned long long)( la->d.mb_w * 16 ) * ( la->d.mb_h * 16 );
     s.pixel_sum = sum;
     s.pixel_ssd = sqr - ( sum * sum + N / 2 ) / N;                   /* ratecontrol.c:405-414 */
@@ -1272,6 +1296,25 @@ static int la_weights_analyse( x264cu_lookahead *la, int fenc_slot, int ref_slot
     return 0;
 }
 
+int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int fenc_slot, int ref_slot )
+{
+    if( !la ) return -1;
+    if( !la->p.weighted_pred ) return 1;
+    for( int s : { fenc_slot, ref_slot } )
+        if( s < 0 || s >= (int)la->slots.size() || !la->slots[s].in_use ) return x264cu_fail( la->ctx, "weight_trivial: empty slot %d", s );
+    LaSlotHost &fenc = la->slots[fenc_slot], &ref = la->slots[ref_slot];
+    if( la_fetch_stats( la, fenc ) || la_fetch_stats( la, ref ) ) return -1;
+    // the early exit of x264_weights_analyse (slicetype.c:316-330), same float expressions as la_weights_analyse
+    const float epsilon = 1.f / 128.f;
+    const int zero_bias = !ref.pixel_ssd;
+    const float fenc_var = fenc.pixel_ssd + zero_bias, ref_var = ref.pixel_ssd + zero_bias;
+    const float guess_scale = sqrtf( fenc_var / ref_var );
+    const int npix = ( la->d.mb_h * 16 ) * ( la->d.mb_w * 16 );
+    const float fenc_mean = (float)( fenc.pixel_sum + zero_bias ) / npix;
+    const float ref_mean = (float)( ref.pixel_sum + zero_bias ) / npix;
+    return fabsf( ref_mean - fenc_mean ) < 0.5f && fabsf( 1.f - guess_scale ) < epsilon;
+}
+
 int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
 {
     if( !la || !frames || !score ) return -1;
@@ -1292,30 +1335,43 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
         *score = fenc.cost_est[i0][i1];
         return 0;
     }
-    // do_search / sentinels, slicetype.c:855-866 (weighted prediction is analysed by the caller; not used here)
+    // do_search / sentinels, slicetype.c:855-866.  `requested` is the reference's state (has a cost request asked for this
+    // pair yet), `searched` ours (has its search been launched, possibly ahead of time by x264cu_lookahead_search_batch)
     int n = 0;
-    if( b != p0 && !fenc.searched[0][i0 - 1] )
+    if( b != p0 && !fenc.requested[0][i0 - 1] )
     {
+        fenc.requested[0][i0 - 1] = true;
         if( la->p.weighted_pred && b == p1 )
-        {   /* slicetype.c:857-864: weights are analysed only when this first search of the pair is P-type.  The analysis
-             * may itself issue an intra-only request, which reuses la->pack: run it before the job list is assembled */
-            if( la_weights_analyse( la, sb, s0 ) ) return -1;
+        {   /* slicetype.c:857-864: weights are analysed only when this first search of the pair is P-type */
+            if( fenc.searched[0][i0 - 1] )
+            {   // searched ahead of time: only done for pairs whose analysis ends at its early exit (x264cu_lookahead_weight_trivial)
+                fenc.weight.enabled = 0; fenc.weight.scale = 1; fenc.weight.denom = 0; fenc.weight.offset = 0;
+            }
+            /* The analysis may itself issue an intra-only request, which reuses la->pack: run it before the job list is assembled */
+            else if( la_weights_analyse( la, sb, s0 ) ) return -1;
         }
-        fenc.searched[0][i0 - 1] = true;
-        la_fill_job( la, la->pack.j[n], sb, s0, 0, i0 );
-        if( la->p.weighted_pred && b == p1 && fenc.weight.enabled )
+        if( !fenc.searched[0][i0 - 1] )
         {
-            LaSearchJob &j = la->pack.j[n];
-            j.ref_w = la->d_weight_plane + ( la->slots[s0].dev.planes[0] - la->slots[s0].plane_buf );
-            j.w_enabled = 1; j.w_scale = fenc.weight.scale; j.w_denom = fenc.weight.denom; j.w_offset = fenc.weight.offset;
+            fenc.searched[0][i0 - 1] = true;
+            la_fill_job( la, la->pack.j[n], sb, s0, 0, i0 );
+            if( la->p.weighted_pred && b == p1 && fenc.weight.enabled )
+            {
+                LaSearchJob &j = la->pack.j[n];
+                j.ref_w = la->d_weight_plane + ( la->slots[s0].dev.planes[0] - la->slots[s0].plane_buf );
+                j.w_enabled = 1; j.w_scale = fenc.weight.scale; j.w_denom = fenc.weight.denom; j.w_offset = fenc.weight.offset;
+            }
+            n++;
         }
-        n++;
     }
-    if( b != p1 && !fenc.searched[1][i1 - 1] )
+    if( b != p1 && !fenc.requested[1][i1 - 1] )
     {
-        fenc.searched[1][i1 - 1] = true;
-        la_fill_job( la, la->pack.j[n], sb, s1, 1, i1 );
-        n++;
+        fenc.requested[1][i1 - 1] = true;
+        if( !fenc.searched[1][i1 - 1] )
+        {
+            fenc.searched[1][i1 - 1] = true;
+            la_fill_job( la, la->pack.j[n], sb, s1, 1, i1 );
+            n++;
+        }
     }
     if( !fenc.intra_on_device )
     {
@@ -1348,7 +1404,8 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
         A.mvs1 = fenc.dev.mvs + (size_t)( 1 * B1 + i1 - 1 ) * d.mb_count * 2;
         A.cost1 = fenc.dev.mv_costs + (size_t)( 1 * B1 + i1 - 1 ) * d.mb_count;
     }
-    if( A.b_bidir && p1 - p0 - 1 <= d.B && la->slots[s1].searched[0][p1 - p0 - 1] )
+    // temporal direct only if the reference itself would have those vectors by now (slicetype.c:629-635), however early we searched
+    if( A.b_bidir && p1 - p0 - 1 <= d.B && la->slots[s1].requested[0][p1 - p0 - 1] )
         A.mvr = la->slots[s1].dev.mvs + (size_t)( 0 * B1 + p1 - p0 - 1 ) * d.mb_count * 2;
     A.intra = fenc.dev.intra;
     A.qscale = fenc.dev.qscale;
@@ -1365,7 +1422,7 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
     CU_CHECK( ctx, cudaMemsetAsync( la->d_record, 0, 64, ctx->stream ) );
     CU_CHECK( ctx, cudaMemsetAsync( A.row_inter, 0, d.mb_h * 4, ctx->stream ) );
     CU_CHECK( ctx, cudaMemsetAsync( A.row_intra, 0, d.mb_h * 4, ctx->stream ) );
-    finalize_kernel<<<( d.mb_count + 63 ) / 64, 256, 0, ctx->stream>>>( d, A );
+    finalize_kernel<<<( d.mb_count + LA_FIN_THREADS / 4 - 1 ) / ( LA_FIN_THREADS / 4 ), LA_FIN_THREADS, 0, ctx->stream>>>( d, A );
     CU_LAUNCH_CHECK( ctx );
     CU_CHECK( ctx, cudaMemcpyAsync( la->h_record, la->d_record, 32, cudaMemcpyDeviceToHost, ctx->stream ) );
     LA_TIMED( la->st.cost_sync, la->st.n_cost, CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) ) );

@@ -26,6 +26,8 @@ static double st_now( void ) { struct timespec t; clock_gettime( CLOCK_MONOTONIC
 #define AUTO_OR_I( t ) ( ( t ) == T_AUTO || IS_I( t ) )
 #define AUTO_OR_B( t ) ( ( t ) == T_AUTO || IS_B( t ) )
 
+#define ST_RUN_AHEAD_MAX 32
+
 typedef struct
 {
     int i_frame;          /* display index */
@@ -43,7 +45,7 @@ struct x264cu_slicetype
     int slicetype_length, delay;          /* encoder.c:1602-1612 (one thread, no sync lookahead, cfr) */
     int b_analyse_keyframe;               /* lookahead.c:140 */
     int i_last_keyframe;
-    st_frame_t *next[LOOKAHEAD_MAX + 8];  /* lookahead->next */
+    st_frame_t *next[LOOKAHEAD_MAX + ST_RUN_AHEAD_MAX + 8];  /* lookahead->next */
     int n_next;
     st_frame_t *current[BFRAME_MAX + 4];  /* h->frames.current */
     int n_current;
@@ -599,19 +601,21 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
     s->slicetype_length = s->delay;
     s->b_analyse_keyframe = p->la.mb_tree != 0;
     s->i_last_keyframe = -p->keyint_max;
-    s->n_slots = s->delay + p->la.bframes + 8 + 16;
+    s->n_slots = s->delay + p->la.bframes + 8 + ST_RUN_AHEAD_MAX;
     s->slot_used = calloc( s->n_slots, 1 );
     s->p.la.n_slots = s->n_slots;
     s->mb_w = ( p->la.width + 15 ) >> 4;
     s->mb_h = ( p->la.height + 15 ) >> 4;
     s->prefetch = 1;
-    s->prefetch_group = s->delay >= 12 ? 4 : 1;
-    s->run_ahead = s->delay >= 12 ? 8 : 0;
+    /* measured at 4K (B200): 8/4 -> 1000 pictures/s, 16/8 -> 1260, 24/12 -> 1410, 32/16 -> 1490: a launch needs several
+     * dozen independent wavefronts to fill the 148 SMs */
+    s->prefetch_group = s->delay >= 12 ? 12 : 1;
+    s->run_ahead = s->delay >= 12 ? 24 : 0;
     {   /* tuning hooks (bench experiments): X264CU_RUN_AHEAD=<0..16>, X264CU_PREFETCH_GROUP=<1..8> */
         const char *e = getenv( "X264CU_RUN_AHEAD" );
-        if( e && atoi( e ) >= 0 && atoi( e ) <= 16 ) s->run_ahead = atoi( e );
+        if( e && atoi( e ) >= 0 && atoi( e ) <= ST_RUN_AHEAD_MAX ) s->run_ahead = atoi( e );
         e = getenv( "X264CU_PREFETCH_GROUP" );
-        if( e && atoi( e ) >= 1 && atoi( e ) <= 8 ) s->prefetch_group = atoi( e );
+        if( e && atoi( e ) >= 1 && atoi( e ) <= 16 ) s->prefetch_group = atoi( e );
     }
     if( !s->slot_used || x264cu_lookahead_open( ctx, &s->p.la, &s->la ) )
     {
@@ -646,6 +650,13 @@ static int flush_prefetch( x264cu_slicetype_t *s )
     {
         if( x264cu_slicetype_slot_of( s, s->pj_fframe[i] ) != s->pj_fenc[i] || x264cu_slicetype_slot_of( s, s->pj_rframe[i] ) != s->pj_ref[i] )
             continue;
+        if( s->p.la.weighted_pred && s->pj_list[i] == 0 )
+        {   /* a list-0 search is weighted if it is first requested as a P cost and the analysis picks a weight
+             * (slicetype.c:857-864): it is a pure function of the two pictures only where the analysis cannot pick one */
+            int t = x264cu_lookahead_weight_trivial( s->la, s->pj_fenc[i], s->pj_ref[i] );
+            if( t < 0 ) return -1;
+            if( !t ) continue;
+        }
         s->pj_fenc[n] = s->pj_fenc[i]; s->pj_ref[n] = s->pj_ref[i]; s->pj_list[n] = s->pj_list[i]; s->pj_dist[n] = s->pj_dist[i];
         n++;
     }
@@ -667,7 +678,7 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
         int slot = -1;
         for( int i = 0; i < s->n_slots; i++ )
             if( !s->slot_used[i] ) { slot = i; break; }
-        if( slot < 0 || s->n_next >= LOOKAHEAD_MAX + 4 ) return -1;
+        if( slot < 0 || s->n_next >= LOOKAHEAD_MAX + ST_RUN_AHEAD_MAX + 4 ) return -1;
         double t0_ = st_now();
         int rc_ = on_device ? x264cu_lookahead_frame_put_device( s->la, slot, luma, luma_stride, h_inv_qscale )
                             : x264cu_lookahead_frame_put( s->la, slot, luma, luma_stride, h_inv_qscale );
@@ -690,9 +701,7 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
                 int d = f->i_frame - o->i_frame;
                 if( !s->slot_used[o->slot] || d < 1 || d > s->p.la.bframes + 1 || s->n_pj + 2 > 256 ) continue;
                 int n = s->n_pj;
-                if( !s->p.la.weighted_pred )
-                {   /* a list-0 search may be weighted if it is first requested as a P cost (slicetype.c:857-864): only
-                     * without weighted prediction is it a pure function of the two pictures */
+                {   /* with weighted prediction flush_prefetch drops the pairs whose weight analysis is not trivial */
                     s->pj_fenc[n] = f->slot; s->pj_ref[n] = o->slot; s->pj_list[n] = 0; s->pj_dist[n] = d;
                     s->pj_fframe[n] = f->i_frame; s->pj_rframe[n] = o->i_frame; n++;
                 }
@@ -753,7 +762,7 @@ void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *s, int prefetch ) { if( 
 
 void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *s, int pictures )
 {
-    if( s && !s->i_input && pictures >= 0 && pictures <= 16 ) s->run_ahead = pictures;
+    if( s && !s->i_input && pictures >= 0 && pictures <= ST_RUN_AHEAD_MAX ) s->run_ahead = pictures;
 }
 
 void x264cu_slicetype_set_async_upload( x264cu_slicetype_t *s, int on ) { if( s ) x264cu_lookahead_set_async_upload( s->la, on ); }
