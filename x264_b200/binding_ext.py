@@ -212,7 +212,7 @@ class Slicetype:
         self.L.x264cu_slicetype_set_run_ahead(self.h, int(k))
 
     def set_async_upload(self, on):
-        """page-locked pictures passed to step() are read in place; keep them unmodified until the next step() returns"""
+        """page-locked pictures passed to step() are read in place; keep them unmodified until four more pictures have been queued"""
         self.L.x264cu_slicetype_set_async_upload(self.h, int(on))
 
     def decide(self, frames):

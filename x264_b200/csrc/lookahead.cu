@@ -711,6 +711,8 @@ struct LaSlotHost
     unsigned long long pixel_sum, pixel_ssd;   // i_pixel_sum[0] / i_pixel_ssd[0] (ratecontrol.c:405-414), valid once stats_ready
     bool stats_ready;
     LaWeight weight;                 // fenc->weight[0][0] of the last lookahead analysis
+    int last_search_ev = -1;         // event (ring index, sequence number) of the last prefetch launch that reads this slot
+    unsigned long long last_search_seq = 0;
     cudaEvent_t ev_ready = nullptr;  // recorded on the upload stream when the picture's planes / reset arrays are in place
     bool main_waited = true;         // the context's stream has been ordered after ev_ready
 };
@@ -731,8 +733,10 @@ struct x264cu_lookahead
     unsigned int h_luma_next = 0;
     cudaStream_t up_stream = nullptr;    // upload stream: H2D copy, lowres planes and slot reset of a queued picture run beside the analysis
     cudaEvent_t ev_up_guard = nullptr;   // main-stream work queued before a put (it may still read the slot's previous picture)
-    cudaEvent_t ev_zero_copy = nullptr;  // last copy that read the caller's own page-locked buffer
-    bool zero_copy_live = false;
+#define LA_ZC_DEPTH 4
+    cudaEvent_t ev_zero_copy[LA_ZC_DEPTH] = {};  // the last copies that read the caller's own page-locked buffers (ring)
+    bool zero_copy_live[LA_ZC_DEPTH] = {};
+    unsigned int zc_next = 0;
     bool async_upload = false;           // x264cu_lookahead_set_async_upload
     int32_t *d_record = nullptr, *h_record = nullptr;
     LaJobPack pack;                  // jobs being assembled for the next launch
@@ -741,6 +745,7 @@ struct x264cu_lookahead
     unsigned int batch_no = 0;
     int last_ev_of[2] = { -1, -1 };
     cudaEvent_t ev[64];
+    unsigned long long ev_seq[64] = {}, ev_seq_next = 1;    // which recording each ring entry currently holds
     int ev_next = 0, n_ev = 0;
     cudaEvent_t ev_main = nullptr;
     int last_prefetch_ev = -1;
@@ -808,7 +813,7 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     if( la->up_stream ) { cudaStreamSynchronize( la->up_stream ); cudaStreamDestroy( la->up_stream ); }
     for( int i = 0; i < 2; i++ ) { cudaFreeHost( la->h_luma[i] ); if( la->h_luma_ev[i] ) cudaEventDestroy( la->h_luma_ev[i] ); }
     if( la->ev_up_guard ) cudaEventDestroy( la->ev_up_guard );
-    if( la->ev_zero_copy ) cudaEventDestroy( la->ev_zero_copy );
+    for( int i = 0; i < LA_ZC_DEPTH; i++ ) if( la->ev_zero_copy[i] ) cudaEventDestroy( la->ev_zero_copy[i] );
     for( auto &s : la->slots ) if( s.ev_ready ) cudaEventDestroy( s.ev_ready );
     cudaFreeHost( la->h_record ); cudaFreeHost( la->h_qscale );
     cudaFree( la->d_qscale_flat );
@@ -896,7 +901,8 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     }
     if( ok && cudaStreamCreateWithPriority( &la->up_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->ev_up_guard, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
-    if( ok && cudaEventCreateWithFlags( &la->ev_zero_copy, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
+    for( int i = 0; i < LA_ZC_DEPTH; i++ )
+        if( ok && cudaEventCreateWithFlags( &la->ev_zero_copy[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_record, 64 ) != cudaSuccess ) ok = false;
     if( ok && cudaMallocHost( (void **)&la->h_qscale, (size_t)4 * d.mb_count * 2 ) != cudaSuccess ) ok = false;
     for( int i = 0; i < 4 && ok; i++ )
@@ -974,15 +980,18 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
 }
 
 // Order the upload stream after everything that may still read the picture leaving `slot`: the work queued so far on the
-// context's stream (cost requests, on-demand searches) and the prefetched searches in flight.
-static int la_put_begin( x264cu_lookahead *la )
+// context's stream (cost requests, on-demand searches) and the last prefetch launch that involved the slot -- not the
+// launches in flight for OTHER pictures: an upload must not wait for the searches of the previous group.
+static int la_put_begin( x264cu_lookahead *la, int slot )
 {
     x264cu_ctx *ctx = la->ctx;
+    LaSlotHost &s = la->slots[slot];
     CU_CHECK( ctx, cudaEventRecord( la->ev_up_guard, ctx->stream ) );
     CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev_up_guard, 0 ) );
-    for( int i = 0; i < 2; i++ )
-        if( la->last_ev_of[i] >= 0 )
-            CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev[la->last_ev_of[i]], 0 ) );
+    // a ring entry recorded again since belongs to a launch that had finished by then (search_batch waits before reuse)
+    if( s.last_search_ev >= 0 && la->ev_seq[s.last_search_ev] == s.last_search_seq )
+        CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev[s.last_search_ev], 0 ) );
+    s.last_search_ev = -1;
     return 0;
 }
 
@@ -1030,7 +1039,7 @@ int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const u
     if( !la ) return -1;
     if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( la->ctx, "frame_put: slot %d out of range", slot );
     // d_luma is complete in the context's stream order (la_put_begin orders the upload stream after that stream)
-    if( la_put_begin( la ) ) return -1;
+    if( la_put_begin( la, slot ) ) return -1;
     return la_put_finish( la, slot, d_luma, luma_stride, h_inv_qscale );
 }
 
@@ -1044,22 +1053,26 @@ int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t 
     if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( ctx, "frame_put: slot %d out of range", slot );
     const int w = la->p.width, h = la->p.height;
     const intptr_t st = ( w + 63 ) & ~63;
-    if( la->zero_copy_live )
-    {   // the previous picture was read in place: that copy ended long ago in steady state
-        LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->ev_zero_copy ) ) );
-        la->zero_copy_live = false;
+    const int zc = la->zc_next++ % LA_ZC_DEPTH;
+    if( la->zero_copy_live[zc] )
+    {   // the picture queued LA_ZC_DEPTH calls ago was read in place: that copy ended long ago in steady state
+        LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->ev_zero_copy[zc] ) ) );
+        la->zero_copy_live[zc] = false;
     }
-    if( la_put_begin( la ) ) return -1;
+    if( la_put_begin( la, slot ) ) return -1;
     cudaPointerAttributes at;
     const bool pinned = cudaPointerGetAttributes( &at, h_luma ) == cudaSuccess && at.type == cudaMemoryTypeHost;
     if( !pinned ) cudaGetLastError();
     if( pinned )
     {   // page-locked source (x264cu_malloc_host, like the reference's pinned page-locked staging, opencl.h:718): the DMA
         // engine reads it in place, the calling thread neither copies nor waits
-        CU_CHECK( ctx, cudaMemcpy2DAsync( la->d_luma, st, h_luma, luma_stride, w, h, cudaMemcpyHostToDevice, la->up_stream ) );
-        CU_CHECK( ctx, cudaEventRecord( la->ev_zero_copy, la->up_stream ) );
-        if( la->async_upload ) la->zero_copy_live = true;
-        else LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->ev_zero_copy ) ) );
+        if( luma_stride == st && w == st )
+            CU_CHECK( ctx, cudaMemcpyAsync( la->d_luma, h_luma, (size_t)st * h, cudaMemcpyHostToDevice, la->up_stream ) );
+        else
+            CU_CHECK( ctx, cudaMemcpy2DAsync( la->d_luma, st, h_luma, luma_stride, w, h, cudaMemcpyHostToDevice, la->up_stream ) );
+        CU_CHECK( ctx, cudaEventRecord( la->ev_zero_copy[zc], la->up_stream ) );
+        if( la->async_upload ) la->zero_copy_live[zc] = true;
+        else LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->ev_zero_copy[zc] ) ) );
     }
     else
     {   // pageable source: staged through a ring of two pinned buffers, so that the caller's buffer is free on return
@@ -1189,7 +1202,10 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
         la->ev_next = ( la->ev_next + 1 ) % la->n_ev;
         { long dummy = 0; LA_TIMED( la->st.ev_sync, dummy, CU_CHECK( ctx, cudaEventSynchronize( la->ev[e] ) ) ); }   // ring slot reuse: its previous recording is long done
         CU_CHECK( ctx, cudaEventRecord( la->ev[e], la->search_stream ) );
+        la->ev_seq[e] = la->ev_seq_next++;
         for( auto &m : marks ) la->slots[m.slot].pending[m.list][m.dm1] = e;
+        for( int i = 0; i < n_jobs; i++ )
+            for( int sl : { fenc[i], ref[i] } ) { la->slots[sl].last_search_ev = e; la->slots[sl].last_search_seq = la->ev_seq[e]; }
         la->last_prefetch_ev = e;
         la->last_ev_of[si] = e;
     }
