@@ -149,6 +149,29 @@ int x264cu_frame_init_lowres( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t
 int x264cu_hpel_filter( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, int width, int height,
                         uint8_t *d_h, uint8_t *d_v, uint8_t *d_c, int expand_src );
 
+/* mc_luma / get_ref (common/mc.c:198-249, tables x264_hpel_ref0/1 common/tables.c:183-184): job i produces the w x h block
+ * (i_pixel) of the reference at quarter-pel vector (mvx, mvy) -- one half-pel plane or the rounded mean of two, then the
+ * optional explicit weight (mc_weight, mc.c:117-137) -- into d_dst + i*w*h (rows packed, stride w).  d_src = F,H,V,C planes
+ * (x264cu_hpel_filter output, padded); src_off = byte offset of the block at vector 0, the same in all four planes.
+ * weight = { enabled, i_scale, i_denom, i_offset } (x264_weight_t, common/mc.h:235-245) or NULL.  get_ref returns the same
+ * pixels (it only avoids the copy when no interpolation is needed, mc.c:244-248). */
+typedef struct { uint32_t src_off; int16_t mvx, mvy; } x264cu_mc_job_t;
+int x264cu_mc_luma_batch( x264cu_ctx_t *ctx, const uint8_t *const d_src[4], intptr_t src_stride, int i_pixel,
+                          const x264cu_mc_job_t *d_jobs, int n, const int weight[4], uint8_t *d_dst );
+
+/* mc.avg[i_pixel] (pixel_avg_WxH, common/mc.c:49-111): n packed w x h blocks a, b -> dst; weight 32 is the rounded mean,
+ * anything else clip( (a*weight + b*(64-weight) + 32) >> 6 ) (bi-prediction, i_bipred_weight) */
+int x264cu_pixel_avg_batch( x264cu_ctx_t *ctx, int i_pixel, const uint8_t *d_a, const uint8_t *d_b, int n, int weight, uint8_t *d_dst );
+
+/* x264_weight_scale_plane (common/frame.c:825-841) = mc.weight over a whole plane: dst = clip( ((src*scale + 2^(denom-1)) >> denom)
+ * + offset ), or src*scale + offset when denom is 0 (mc_weight, common/mc.c:117-137).  weight = { -, scale, denom, offset } */
+int x264cu_weight_scale_plane( x264cu_ctx_t *ctx, const uint8_t *d_src, uint8_t *d_dst, intptr_t stride, int width, int height,
+                               const int weight[4] );
+
+/* x264_pixel_ssd_wxh (common/pixel.c:112-151): sum of squared differences of two width x height planes (PSNR); synchronises */
+int x264cu_pixel_ssd_wxh( x264cu_ctx_t *ctx, const uint8_t *d_pix1, intptr_t stride1, const uint8_t *d_pix2, intptr_t stride2,
+                          int width, int height, uint64_t *h_ssd );
+
 /* ------------------------------------------------------------------------------------------------
  * B2: the lowres lookahead, the seam where common/opencl.c + encoder/slicetype-cl.c sit today
  * (hooks called from slicetype_frame_cost, encoder/slicetype.c:878-897).  Results are those of the

@@ -22,8 +22,9 @@ struct x264cu_ctx
                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill ) = nullptr;
     // scratch for the *_host entry points (grown on demand)
-    void *scratch[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-    size_t scratch_bytes[6] = { 0, 0, 0, 0, 0, 0 };
+    void *scratch[8] = {};
+    size_t scratch_bytes[8] = {};
+    int me_tab_lambda = -1, me_tab_range = -1;   // which cost_mv table scratch slot 5 currently holds (x264cu_me_search_batch)
     struct x264cu_lookahead *lookahead = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaStream_t> aux_streams;   // streams of live lookahead objects: x264cu_sync waits for them too

@@ -738,6 +738,7 @@ struct x264cu_lookahead
     bool zero_copy_live[LA_ZC_DEPTH] = {};
     unsigned int zc_next = 0;
     bool async_upload = false;           // x264cu_lookahead_set_async_upload
+    bool search_attr_set = false;
     int32_t *d_record = nullptr, *h_record = nullptr;
     LaJobPack pack;                  // jobs being assembled for the next launch
     cudaStream_t search_streams[2] = {};     // prefetch launches alternate: the drain of one wavefront overlaps the fill of the next
@@ -1097,12 +1098,11 @@ static int la_launch_searches( x264cu_lookahead *la, int n, cudaStream_t stream 
     if( rows <= 0 ) return 0;
     const int groups = ( rows + NW - 1 ) / NW;
     size_t smem = (size_t)NW * LA_WIN_BYTES;
-    static bool attr = false;
-    if( !attr )
+    if( !la->search_attr_set )                       // per device: one lookahead object belongs to one device
     {
         CU_CHECK( ctx, cudaFuncSetAttribute( search_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
         CU_CHECK( ctx, cudaFuncSetAttribute( search_kernel<NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared ) );
-        attr = true;
+        la->search_attr_set = true;
     }
     // ticket counters: a ring, one per launch, re-zeroed in stream order before use
     unsigned int *t = la->d_tickets + ( la->ticket_next++ & 63 );

@@ -55,12 +55,13 @@ extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params
         return x264cu_fail( ctx, "me_search_batch: method %d not supported (esa / tesa are outside this backend)", p->me_method );
     if( p->subpel_refine < 0 || p->subpel_refine > 11 || p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 )
         return x264cu_fail( ctx, "me_search_batch: bad parameters" );
-    // cost_mv[lambda] (analyse.c:143-157, :179-188), same float expressions as the reference; cached per (lambda, range)
-    static int cached_lambda = -1, cached_range = -1;
+    // cost_mv[lambda] (analyse.c:143-157, :179-188), same float expressions as the reference; kept in this context's scratch
+    // slot 5 (nobody else's) and rebuilt when (lambda, range) change
     const int len = 2 * 4 * p->mv_range;
+    const void *before = ctx->scratch[5];
     uint16_t *d_tab = (uint16_t *)x264cu_scratch( ctx, 5, ( 2 * len + 1 ) * 2 + 64 );
     if( !d_tab ) return -1;
-    if( cached_lambda != p->lambda || cached_range != p->mv_range )
+    if( ctx->me_tab_lambda != p->lambda || ctx->me_tab_range != p->mv_range || before != (const void *)d_tab )
     {
         std::vector<uint16_t> tab( 2 * len + 1 );
         for( int i = 0; i <= len; i++ )
@@ -72,7 +73,7 @@ extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params
         }
         CU_CHECK( ctx, cudaMemcpyAsync( d_tab, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice, ctx->stream ) );
         CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
-        cached_lambda = p->lambda; cached_range = p->mv_range;
+        ctx->me_tab_lambda = p->lambda; ctx->me_tab_range = p->mv_range;
     }
     MeShared g;
     g.fenc = d_fenc; g.fenc_stride = (int)fenc_stride;
