@@ -123,12 +123,27 @@ struct orc_la_frame
     int i_frame;
     orc_weight_t weight;               /* fenc->weight[0][0] after the last lookahead analysis */
     uint8_t *weighted_buf;             /* fenc->weighted[0]: weighted copy of the reference's padded F plane */
+    /* MB-tree (slicetype.c:1029-1184) */
+    uint16_t *propagate_cost;          /* i_propagate_cost */
+    float *qp_offset, *qp_offset_aq;   /* f_qp_offset / f_qp_offset_aq */
+    float weighted_cost_delta[17];     /* f_weighted_cost_delta (slicetype.c:462-463: X264_WEIGHTP_FAKE only = weighted_pred < 0) */
+    int mb_width;
 };
 
 orc_la_frame_t *orc_la_frame_new( const orc_la_params_t *p, const uint8_t *luma, intptr_t luma_stride );
 void orc_la_frame_delete( orc_la_frame_t *f );
 int  orc_la_frame_cost( const orc_la_params_t *p, const uint16_t *cost_mv_centre,
                         orc_la_frame_t **frames, int p0, int p1, int b );
+/* macroblock_tree_propagate (slicetype.c:1050-1089) with mbtree_propagate_cost / _list (common/mc.c:511-598);
+ * fps_factor = CLIP_DURATION(f_duration) / (CLIP_DURATION(average_duration) * 256) * MBTREE_PRECISION */
+void orc_la_mbtree_propagate( const orc_la_params_t *p, orc_la_frame_t **frames, int p0, int p1, int b, int referenced, float fps_factor );
+/* macroblock_tree_finish (slicetype.c:1029-1048): fps_factor = round( CLIP(avg) / CLIP(dur) * 256 / MBTREE_PRECISION ),
+ * strength = 5 * (1 - qcompress) */
+void orc_la_mbtree_finish( orc_la_frame_t *f, int fps_factor, int ref0_distance, float strength );
+void orc_la_mbtree_reset( orc_la_frame_t *f );
+void orc_la_frame_set_qp_offset_aq( orc_la_frame_t *f, const float *aq );
+void orc_la_frame_get_mbtree( orc_la_frame_t *f, int what, int i, void *out );
+float orc_log2( uint32_t x );           /* x264_log2, common/base.h:226-230 */
 
 #ifdef __cplusplus
 }

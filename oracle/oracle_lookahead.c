@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <stdio.h>
 
 #define FDEC 32                      /* FDEC_STRIDE, common/common.h:571 */
 #define LOWRES_COST_MASK 0x3fff      /* common/frame.h:107-112 */
@@ -82,6 +83,10 @@ orc_la_frame_t *orc_la_frame_new( const orc_la_params_t *p, const uint8_t *luma,
     f->intra_cost = calloc( f->mb_count, sizeof(int) );
     for( int i = 0; i < f->mb_count; i++ ) f->intra_cost[i] = 0xFFFF;     /* memset( i_intra_cost, -1 ), frame.c:288 */
     f->inv_qscale_factor = malloc( f->mb_count * sizeof(uint16_t) );
+    f->propagate_cost = calloc( f->mb_count, sizeof(uint16_t) );
+    f->qp_offset = calloc( f->mb_count, sizeof(float) );
+    f->qp_offset_aq = calloc( f->mb_count, sizeof(float) );
+    f->mb_width = p->mb_width;
     for( int i = 0; i < f->mb_count; i++ ) f->inv_qscale_factor[i] = 256;
     return f;
 }
@@ -97,6 +102,7 @@ void orc_la_frame_delete( orc_la_frame_t *f )
     free( f->intra_cost );
     free( f->inv_qscale_factor );
     free( f->weighted_buf );
+    free( f->propagate_cost ); free( f->qp_offset ); free( f->qp_offset_aq );
     free( f );
 }
 
@@ -518,7 +524,7 @@ static unsigned weight_cost_luma( const orc_la_params_t *p, orc_la_frame_t *fenc
 int orc_la_frame_cost( const orc_la_params_t *p, const uint16_t *cost_mv_centre, orc_la_frame_t **frames, int p0, int p1, int b );
 
 /* x264_weights_analyse with b_lookahead = 1, slicetype.c:284-501 (luma only).  Leaves fenc->weight / weighted_buf. */
-static void la_weights_analyse( const orc_la_params_t *p, const uint16_t *cost_mv, orc_la_frame_t *fenc, orc_la_frame_t *ref )
+static void la_weights_analyse( const orc_la_params_t *p, const uint16_t *cost_mv, orc_la_frame_t *fenc, orc_la_frame_t *ref, int delta_index )
 {
     const float epsilon = 1.f / 128.f;
     orc_weight_t none = { 0, 1, 0, 0 };
@@ -564,6 +570,8 @@ static void la_weights_analyse( const orc_la_params_t *p, const uint16_t *cost_m
     if( !found || ( minscale == 1 << mindenom && minoff == 0 ) || (float)minscore / origscore > 0.998f )
         return;
     fenc->weight.enabled = 1; fenc->weight.scale = minscale; fenc->weight.denom = mindenom; fenc->weight.offset = minoff;
+    if( p->weighted_pred < 0 )                                  /* X264_WEIGHTP_FAKE, slicetype.c:462-463 */
+        fenc->weighted_cost_delta[delta_index] = (float)minscore / origscore;
     /* x264_weight_scale_plane over the whole padded reference plane, slicetype.c:489-500 */
     size_t plane = (size_t)ref->stride_lowres * ( ref->lines_lowres + 2*ORC_PAD );
     free( fenc->weighted_buf );
@@ -592,7 +600,7 @@ int orc_la_frame_cost_w( const orc_la_params_t *p, const uint16_t *cost_mv_centr
         if( w && w->enabled && b == p1 ) { L.w = w; L.weighted_plane = weighted_plane; }
         else if( p->weighted_pred && b == p1 )
         {   /* slicetype.c:857-864 */
-            la_weights_analyse( p, cost_mv_centre, fenc, frames[p0] );
+            la_weights_analyse( p, cost_mv_centre, fenc, frames[p0], b - p0 - 1 );
             if( fenc->weight.enabled )
             {
                 L.w = &fenc->weight;
@@ -653,4 +661,135 @@ int orc_la_frame_cost_w( const orc_la_params_t *p, const uint16_t *cost_mv_centr
 int orc_la_frame_cost( const orc_la_params_t *p, const uint16_t *cost_mv_centre, orc_la_frame_t **frames, int p0, int p1, int b )
 {
     return orc_la_frame_cost_w( p, cost_mv_centre, frames, p0, p1, b, NULL, NULL );
+}
+
+/* ---------------------------------------------------------------- MB-tree ---------------------------- */
+/* x264_log2 (common/base.h:226-230): table look-up, 7 mantissa bits.  The table is the reference's x264_log2_lut
+ * (common/tables.c:66-85), whose entries are log2(1 + i/128) printed with five decimals */
+static const float *log2_lut( void )
+{
+    static float lut[128];
+    static int init = 0;
+    if( !init )
+    {
+        for( int i = 0; i < 128; i++ )
+        {
+            char buf[32];
+            snprintf( buf, sizeof( buf ), "%.5f", log2( 1.0 + i / 128.0 ) );
+            lut[i] = strtof( buf, NULL );
+        }
+        init = 1;
+    }
+    return lut;
+}
+/* the two halves of x264_log2: mantissa table entry and integer part */
+static float log2_frac( uint32_t x ) { int lz = __builtin_clz( x ); return log2_lut()[( x << lz >> 24 ) & 0x7f]; }
+float orc_log2( uint32_t x ) { return log2_frac( x ) + (float)( 31 - __builtin_clz( x ) ); }
+static float log2_int( uint32_t x ) { return (float)( 31 - __builtin_clz( x ) ); }
+
+void orc_la_mbtree_reset( orc_la_frame_t *f ) { memset( f->propagate_cost, 0, f->mb_count * sizeof(uint16_t) ); }
+void orc_la_frame_set_qp_offset_aq( orc_la_frame_t *f, const float *aq )
+{
+    memcpy( f->qp_offset_aq, aq, f->mb_count * sizeof(float) );
+    memcpy( f->qp_offset, aq, f->mb_count * sizeof(float) );
+}
+void orc_la_frame_get_mbtree( orc_la_frame_t *f, int what, int i, void *out )
+{
+    switch( what )
+    {
+        case 0: memcpy( out, f->qp_offset, f->mb_count * sizeof(float) ); break;
+        case 1: memcpy( out, f->qp_offset_aq, f->mb_count * sizeof(float) ); break;
+        case 2: memcpy( out, f->propagate_cost, f->mb_count * sizeof(uint16_t) ); break;
+        case 3: *(float*)out = f->weighted_cost_delta[i]; break;
+    }
+}
+
+static void clip_add( uint16_t *s, int x ) { int v = *s + x; *s = v > 65535 ? 65535 : v; }       /* MC_CLIP_ADD, mc.h */
+
+void orc_la_mbtree_propagate( const orc_la_params_t *p, orc_la_frame_t **frames, int p0, int p1, int b, int referenced, float fps_factor )
+{
+    orc_la_frame_t *fb = frames[b];
+    uint16_t *ref_costs[2] = { frames[p0]->propagate_cost, frames[p1]->propagate_cost };
+    int dist_scale_factor = ( ( ( b - p0 ) << 8 ) + ( ( p1 - p0 ) >> 1 ) ) / ( p1 - p0 );
+    int bipred_weight = p->weighted_bipred ? 64 - ( dist_scale_factor >> 2 ) : 32;
+    int bipred_weights[2] = { bipred_weight, 64 - bipred_weight };
+    int16_t (*mvs[2])[2] = { b != p0 ? fb->lowres_mvs[0][b-p0-1] : NULL, b != p1 ? fb->lowres_mvs[1][p1-b-1] : NULL };
+    const uint16_t *lowres_costs = fb->lowres_costs[b-p0][p1-b];
+    const unsigned width = p->mb_width, height = p->mb_height;
+    if( !referenced )                                   /* slicetype.c:1066-1067: one zeroed row is re-used as the input */
+        memset( fb->propagate_cost, 0, width * sizeof(uint16_t) );
+    for( unsigned mb_y = 0; mb_y < height; mb_y++ )
+    {
+        const uint16_t *propagate_in = fb->propagate_cost + ( referenced ? mb_y * width : 0 );
+        int16_t amount[width];
+        for( unsigned i = 0; i < width; i++ )
+        {   /* mbtree_propagate_cost, mc.c:511-527 */
+            unsigned mb = mb_y * width + i;
+            int intra_cost = (uint16_t)fb->intra_cost[mb];
+            int inter_cost = lowres_costs[mb] & 0x3fff;
+            if( inter_cost > intra_cost ) inter_cost = intra_cost;
+            float propagate_intra = intra_cost * fb->inv_qscale_factor[mb];
+            float propagate_amount = propagate_in[i] + propagate_intra * fps_factor;
+            float propagate_num = intra_cost - inter_cost;
+            float propagate_denom = intra_cost;
+            int v = (int)( propagate_amount * propagate_num / propagate_denom + 0.5f );
+            amount[i] = v > 32767 ? 32767 : v;
+        }
+        for( int list = 0; list < ( b != p1 ? 2 : 1 ); list++ )
+            for( unsigned i = 0; i < width; i++ )
+            {   /* mbtree_propagate_list, mc.c:529-598 */
+                unsigned mb = mb_y * width + i;
+                int lists_used = lowres_costs[mb] >> 14;
+                if( !( lists_used & ( 1 << list ) ) )
+                    continue;
+                int listamount = amount[i];
+                if( lists_used == 3 )
+                    listamount = ( listamount * bipred_weights[list] + 32 ) >> 6;
+                int x = mvs[list][mb][0], y = mvs[list][mb][1];
+                if( !( x | y ) )
+                {
+                    clip_add( &ref_costs[list][mb], listamount );
+                    continue;
+                }
+                unsigned mbx = (unsigned)( ( x >> 5 ) + (int)i ), mby = (unsigned)( ( y >> 5 ) + (int)mb_y );
+                unsigned idx0 = mbx + mby * width, idx2 = idx0 + width;
+                x &= 31; y &= 31;
+                int w0 = ( ( 32 - y ) * ( 32 - x ) * listamount + 512 ) >> 10;
+                int w1 = ( ( 32 - y ) * x * listamount + 512 ) >> 10;
+                int w2 = ( y * ( 32 - x ) * listamount + 512 ) >> 10;
+                int w3 = ( y * x * listamount + 512 ) >> 10;
+                if( mby < height )
+                {
+                    if( mbx < width ) clip_add( &ref_costs[list][idx0], w0 );
+                    if( mbx + 1 < width ) clip_add( &ref_costs[list][idx0 + 1], w1 );
+                }
+                if( mby + 1 < height )
+                {
+                    if( mbx < width ) clip_add( &ref_costs[list][idx2], w2 );
+                    if( mbx + 1 < width ) clip_add( &ref_costs[list][idx2 + 1], w3 );
+                }
+            }
+    }
+}
+
+void orc_la_mbtree_finish( orc_la_frame_t *f, int fps_factor, int ref0_distance, float strength )
+{
+    float weightdelta = 0.0f;
+    if( ref0_distance && f->weighted_cost_delta[ref0_distance-1] > 0 )
+        weightdelta = ( 1.0 - f->weighted_cost_delta[ref0_distance-1] );
+    for( int mb = 0; mb < f->mb_count; mb++ )
+    {
+        int intra_cost = ( (uint16_t)f->intra_cost[mb] * f->inv_qscale_factor[mb] + 128 ) >> 8;
+        if( intra_cost )
+        {
+            int propagate_cost = ( f->propagate_cost[mb] * fps_factor + 128 ) >> 8;
+            /* x264_log2(a) - x264_log2(b) + weightdelta with a = intra + propagate.  The reference is built with -ffast-math
+             * (configure:1413), which lets the compiler re-associate the five float terms; the association below is the one
+             * gcc 13 -O3 emits for slicetype.c:1044 (checked in the disassembly of oracle/_ref) and makes f_qp_offset
+             * bit-identical to that build; any other association differs by at most a few ulp of 16.0 */
+            uint32_t a = intra_cost + propagate_cost, b = intra_cost;
+            float log2_ratio = ( ( log2_frac( a ) - log2_int( b ) ) + ( log2_int( a ) + weightdelta ) ) - log2_frac( b );
+            f->qp_offset[mb] = f->qp_offset_aq[mb] - strength * log2_ratio;
+        }
+    }
 }

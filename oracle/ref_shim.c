@@ -394,6 +394,55 @@ XREF_API void xref_la_get( void *lav, int idx, int what, int i, int j, void *out
     }
 }
 
+/* MB-tree (slicetype.c:1029-1184), one call each, so that a test can replay macroblock_tree's sequence step by step */
+XREF_API void xref_la_set_type( void *lav, int idx, int type, float duration )
+{
+    xref_la_t *la = lav;
+    la->frames[idx]->i_type = type;
+    la->frames[idx]->f_duration = duration;
+}
+XREF_API void xref_la_mbtree_reset( void *lav, int idx )
+{
+    xref_la_t *la = lav;
+    memset( la->frames[idx]->i_propagate_cost, 0, la->h->mb.i_mb_count * sizeof(uint16_t) );
+}
+XREF_API void xref_la_mbtree_propagate( void *lav, float average_duration, int p0, int p1, int b, int referenced )
+{
+    xref_la_t *la = lav;
+    macroblock_tree_propagate( la->h, la->frames, average_duration, p0, p1, b, referenced );
+}
+XREF_API void xref_la_mbtree_finish( void *lav, int idx, float average_duration, int ref0_distance )
+{
+    xref_la_t *la = lav;
+    macroblock_tree_finish( la->h, la->frames[idx], average_duration, ref0_distance );
+}
+/* the whole of macroblock_tree( h, a, frames, num_frames, b_intra ) on frames[0..num_frames] with the types set before */
+XREF_API void xref_la_mbtree( void *lav, int num_frames, int b_intra )
+{
+    xref_la_t *la = lav;
+    macroblock_tree( la->h, &la->a, la->frames, num_frames, b_intra );
+}
+/* what: 0 f_qp_offset, 1 f_qp_offset_aq (float per MB), 2 i_propagate_cost (u16 per MB), 3 f_weighted_cost_delta[i] (one float) */
+XREF_API void xref_la_get_mbtree( void *lav, int idx, int what, int i, void *out )
+{
+    xref_la_t *la = lav;
+    x264_frame_t *f = la->frames[idx];
+    int n = la->h->mb.i_mb_count;
+    switch( what )
+    {
+        case 0: memcpy( out, f->f_qp_offset, n * sizeof(float) ); break;
+        case 1: memcpy( out, f->f_qp_offset_aq, n * sizeof(float) ); break;
+        case 2: memcpy( out, f->i_propagate_cost, n * sizeof(uint16_t) ); break;
+        case 3: *(float*)out = f->f_weighted_cost_delta[i]; break;
+    }
+}
+XREF_API void xref_la_set_qp_offset_aq( void *lav, int idx, const float *aq )
+{
+    xref_la_t *la = lav;
+    memcpy( la->frames[idx]->f_qp_offset_aq, aq, la->h->mb.i_mb_count * sizeof(float) );
+    memcpy( la->frames[idx]->f_qp_offset, aq, la->h->mb.i_mb_count * sizeof(float) );
+}
+
 XREF_API void xref_la_get_lowres( void *lav, int idx, int plane, uint8_t *out )
 {
     xref_la_t *la = lav;
@@ -431,6 +480,13 @@ XREF_API void xref_la_free( void *lav )
 /* Encode n luma pictures (chroma = 128) with the opened encoder and report, in coded (output) order, the display
  * index (pts) and decided type (X264_TYPE_*) of every frame.  This is the reference's own answer to "which slice
  * types does the lookahead choose".  Returns the number of frames output. */
+/* when set: xref_encode_types also stores, per coded frame, the f_qp_offset array the encoder used for it (MB-tree's output;
+ * mb_count floats each, coded order) */
+static float *xref_qp_capture;
+XREF_API void xref_set_qp_capture( float *buf ) { xref_qp_capture = buf; }
+#define XREF_CAPTURE_QP() do { if( xref_qp_capture && h->fenc ) \
+    memcpy( xref_qp_capture + (size_t)n_out * h->mb.i_mb_count, h->fenc->f_qp_offset, h->mb.i_mb_count * sizeof(float) ); } while( 0 )
+
 XREF_API int xref_encode_types( void *hv, const uint8_t *luma, int n, int *out_idx, int *out_type )
 {
     x264_t *h = hv;
@@ -453,13 +509,13 @@ XREF_API int xref_encode_types( void *hv, const uint8_t *luma, int n, int *out_i
         pic_in.i_type = X264_TYPE_AUTO;
         int sz = x264_encoder_encode( h, &nal, &i_nal, &pic_in, &pic_out );
         if( sz < 0 ) { free( chroma ); return -1; }
-        if( sz > 0 ) { out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
+        if( sz > 0 ) { XREF_CAPTURE_QP(); out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
     }
     while( x264_encoder_delayed_frames( h ) > 0 )
     {
         int sz = x264_encoder_encode( h, &nal, &i_nal, NULL, &pic_out );
         if( sz < 0 ) { free( chroma ); return -1; }
-        if( sz > 0 ) { out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
+        if( sz > 0 ) { XREF_CAPTURE_QP(); out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
     }
     free( chroma );
     return n_out;

@@ -207,6 +207,13 @@ def _bind_la():
     o.orc_la_frame_plane.restype = vp
     o.orc_la_frame_plane.argtypes = [vp, ci]
     o.orc_la_frame_stride.argtypes = [vp]
+    o.orc_la_mbtree_propagate.argtypes = [C.POINTER(OrcLaParams), C.POINTER(vp), ci, ci, ci, ci, C.c_float]
+    o.orc_la_mbtree_finish.argtypes = [vp, ci, ci, C.c_float]
+    o.orc_la_mbtree_reset.argtypes = [vp]
+    o.orc_la_frame_set_qp_offset_aq.argtypes = [vp, vp]
+    o.orc_la_frame_get_mbtree.argtypes = [vp, ci, ci, vp]
+    o.orc_log2.argtypes = [C.c_uint32]
+    o.orc_log2.restype = C.c_float
     if have_ref():
         r = ref()
         r.xref_la_new.restype = vp
@@ -216,6 +223,13 @@ def _bind_la():
         r.xref_la_get.argtypes = [vp, ci, ci, ci, ci, vp]
         r.xref_la_get_lowres.argtypes = [vp, ci, ci, vp]
         r.xref_la_free.argtypes = [vp]
+        r.xref_la_set_type.argtypes = [vp, ci, ci, C.c_float]
+        r.xref_la_mbtree_reset.argtypes = [vp, ci]
+        r.xref_la_mbtree_propagate.argtypes = [vp, C.c_float, ci, ci, ci, ci]
+        r.xref_la_mbtree_finish.argtypes = [vp, ci, C.c_float, ci]
+        r.xref_la_mbtree.argtypes = [vp, ci, ci]
+        r.xref_la_get_mbtree.argtypes = [vp, ci, ci, ci, vp]
+        r.xref_la_set_qp_offset_aq.argtypes = [vp, ci, vp]
 
 
 def la_params_from_ref(hnd, width, height):
@@ -230,7 +244,7 @@ def la_params_from_ref(hnd, width, height):
     p.aq_mode = int(g("aq_mode") != 0)
     p.vbv = int(g("vbv") != 0)
     p.do_edges = int(g("mbtree") != 0 or g("vbv") != 0)
-    p.weighted_pred = int(g("weightp") != 0)
+    p.weighted_pred = -1 if g("weightp") < 0 else int(g("weightp") != 0)      # X264_WEIGHTP_FAKE = -1 (encoder.c:1316-1317)
     return p
 
 
