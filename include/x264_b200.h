@@ -193,8 +193,9 @@ typedef struct
     int mb_tree;                  /* h->param.rc.b_mb_tree */
     int vbv;                      /* h->param.rc.i_vbv_buffer_size != 0 */
     int n_slots;                  /* frames resident in HBM at once (>= lookahead + bframes + 3) */
-    int weighted_pred;            /* h->param.analyse.i_weighted_pred != 0 (X264_WEIGHTP_FAKE included, encoder.c:1316-1317):
-                                     run the lookahead weight analysis (slicetype.c:284-501) on first P-type searches */
+    int weighted_pred;            /* h->param.analyse.i_weighted_pred: non-zero runs the lookahead weight analysis (slicetype.c:284-501)
+                                     on first P-type searches; -1 = X264_WEIGHTP_FAKE (encoder.c:1316-1317), which also records
+                                     f_weighted_cost_delta for MB-tree (slicetype.c:462-463) */
 } x264cu_lookahead_params_t;
 
 /* x264_opencl_lookahead_init / _delete (common/opencl.c:411, :596) */
@@ -250,6 +251,30 @@ int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int b_minus
 int x264cu_lookahead_get_weight( x264cu_lookahead_t *la, int slot, int *out4 );
 int x264cu_lookahead_get_lowres_plane( x264cu_lookahead_t *la, int slot, int plane, uint8_t *h_out, intptr_t *stride );
 
+/* ---- MB-tree (encoder/slicetype.c:1029-1184): propagation of each macroblock's "how much later pictures depend on it" back
+ * along the lowres vectors, and the quantiser offsets it yields.  Device twins of macroblock_tree_propagate
+ * (mbtree_propagate_cost / mbtree_propagate_list, common/mc.c:511-598) and macroblock_tree_finish; the sequence of calls is
+ * macroblock_tree's own (x264cu_slicetype_step issues it when mb_tree is set).  i_propagate_cost is integer and matches the
+ * reference exactly; f_qp_offset is float, evaluated operation by operation in the reference's order. ---- */
+/* fenc->f_qp_offset_aq (and the initial f_qp_offset) of the picture in `slot`: the AQ offsets of x264_adaptive_quant_frame
+ * (ratecontrol.c:225-420), NULL = all zero (AQ off).  Call after frame_put. */
+int x264cu_lookahead_frame_set_qp_offset_aq( x264cu_lookahead_t *la, int slot, const float *h_qp_offset_aq );
+/* memset( frame->i_propagate_cost, 0, ... ) */
+int x264cu_lookahead_mbtree_reset( x264cu_lookahead_t *la, int slot );
+/* XCHG( uint16_t*, a->i_propagate_cost, b->i_propagate_cost ) of the lookahead-less tree (slicetype.c:1125, :1177) */
+int x264cu_lookahead_mbtree_swap( x264cu_lookahead_t *la, int slot_a, int slot_b );
+/* macroblock_tree_propagate( h, frames, average_duration, p0, p1, b, referenced ); the cost (p0,p1,b) must have been requested.
+ * fps_factor = CLIP_DURATION(frames[b]->f_duration) / (CLIP_DURATION(average_duration) * 256) * MBTREE_PRECISION (slicetype.c:1063) */
+int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int referenced, float fps_factor );
+/* macroblock_tree_finish( h, frame, average_duration, ref0_distance ): fps_factor = round( CLIP_DURATION(average_duration) /
+ * CLIP_DURATION(frame->f_duration) * 256 / MBTREE_PRECISION ), strength = 5 * (1 - rc.f_qcompress) (slicetype.c:1031-1038);
+ * fps_factor = 0: f_qp_offset = f_qp_offset_aq (the lookahead-less intra case, slicetype.c:1121-1123) */
+int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_factor, int ref0_distance, float strength );
+int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *h_qp_offset );          /* f_qp_offset, one per MB */
+int x264cu_lookahead_get_propagate_cost( x264cu_lookahead_t *la, int slot, uint16_t *h_propagate_cost );
+/* f_weighted_cost_delta[dist_minus1] (slicetype.c:462-463; set only with weighted_pred < 0 = X264_WEIGHTP_FAKE) */
+float x264cu_lookahead_get_weighted_cost_delta( x264cu_lookahead_t *la, int slot, int dist_minus1 );
+
 /* ------------------------------------------------------------------------------------------------
  * Slice-type decision on top of the GPU lookahead: the host control flow of x264_slicetype_decide /
  * x264_slicetype_analyse / scenecut / slicetype_path (encoder/slicetype.c:1288-1974) and the frame queue of
@@ -273,6 +298,8 @@ typedef struct
     int psy;                      /* h->param.analyse.b_psy */
     int frame_reference;          /* h->param.i_frame_reference */
     int rc_cqp;                   /* h->param.rc.i_rc_method == X264_RC_CQP */
+    int fps_num, fps_den;         /* h->param.i_fps_num / i_fps_den (constant frame rate); 0 = 25/1.  MB-tree's duration factors */
+    float qcompress;              /* h->param.rc.f_qcompress; 0 = 0.6.  MB-tree strength = 5 * (1 - qcompress) */
 } x264cu_slicetype_params_t;
 
 enum { X264CU_TYPE_AUTO = 0, X264CU_TYPE_IDR = 1, X264CU_TYPE_I = 2, X264CU_TYPE_P = 3, X264CU_TYPE_BREF = 4,
@@ -304,6 +331,10 @@ void x264cu_slicetype_set_async_upload( x264cu_slicetype_t *st, int on );
 /* the lookahead object underneath (for reading per-MB results) and the slot a display index currently occupies (-1 if gone) */
 x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *st );
 int  x264cu_slicetype_slot_of( x264cu_slicetype_t *st, int frame );
+/* f_qp_offset of a picture still held by the lookahead (a frame just returned by x264cu_slicetype_step is, until the next
+ * call): MB-tree's quantiser offsets when mb_tree is set.  mb_count floats.  Non-B pictures only: B pictures are coded with
+ * f_qp_offset_aq (slicetype.c:1003), which the caller supplied, and have left the lookahead by then (-1). */
+int  x264cu_slicetype_get_qp_offset( x264cu_slicetype_t *st, int frame, float *h_qp_offset );
 /* number of slicetype_frame_cost requests issued so far (memo hits included) */
 long x264cu_slicetype_cost_requests( x264cu_slicetype_t *st );
 

@@ -401,10 +401,16 @@ XREF_API void xref_la_set_type( void *lav, int idx, int type, float duration )
     la->frames[idx]->i_type = type;
     la->frames[idx]->f_duration = duration;
 }
+#define XREF_LA_FRAME( la, idx ) ( (idx) >= 300 ? (la)->slots[(idx)-300] : (la)->frames[idx] )     /* >= 300: by slot, as in xref_la_get */
 XREF_API void xref_la_mbtree_reset( void *lav, int idx )
 {
     xref_la_t *la = lav;
-    memset( la->frames[idx]->i_propagate_cost, 0, la->h->mb.i_mb_count * sizeof(uint16_t) );
+    memset( XREF_LA_FRAME( la, idx )->i_propagate_cost, 0, la->h->mb.i_mb_count * sizeof(uint16_t) );
+}
+XREF_API void xref_la_mbtree_swap( void *lav, int a, int b )
+{
+    xref_la_t *la = lav;
+    XCHG( uint16_t*, XREF_LA_FRAME( la, a )->i_propagate_cost, XREF_LA_FRAME( la, b )->i_propagate_cost );
 }
 XREF_API void xref_la_mbtree_propagate( void *lav, float average_duration, int p0, int p1, int b, int referenced )
 {
@@ -414,7 +420,7 @@ XREF_API void xref_la_mbtree_propagate( void *lav, float average_duration, int p
 XREF_API void xref_la_mbtree_finish( void *lav, int idx, float average_duration, int ref0_distance )
 {
     xref_la_t *la = lav;
-    macroblock_tree_finish( la->h, la->frames[idx], average_duration, ref0_distance );
+    macroblock_tree_finish( la->h, XREF_LA_FRAME( la, idx ), average_duration, ref0_distance );
 }
 /* the whole of macroblock_tree( h, a, frames, num_frames, b_intra ) on frames[0..num_frames] with the types set before */
 XREF_API void xref_la_mbtree( void *lav, int num_frames, int b_intra )
@@ -426,7 +432,7 @@ XREF_API void xref_la_mbtree( void *lav, int num_frames, int b_intra )
 XREF_API void xref_la_get_mbtree( void *lav, int idx, int what, int i, void *out )
 {
     xref_la_t *la = lav;
-    x264_frame_t *f = la->frames[idx];
+    x264_frame_t *f = XREF_LA_FRAME( la, idx );
     int n = la->h->mb.i_mb_count;
     switch( what )
     {

@@ -85,3 +85,34 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n, const int *fen
 }
 void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on ) { (void)la; (void)on; }
 int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int a, int b ) { (void)la; (void)a; (void)b; return 0; }
+
+/* ---- MB-tree entries, served by oracle/oracle_lookahead.c: orc_la_mbtree_* ---- */
+int x264cu_lookahead_frame_set_qp_offset_aq( x264cu_lookahead_t *la, int slot, const float *aq )
+{
+    if( aq ) orc_la_frame_set_qp_offset_aq( la->slots[slot], aq );
+    return 0;
+}
+int x264cu_lookahead_mbtree_reset( x264cu_lookahead_t *la, int slot ) { orc_la_mbtree_reset( la->slots[slot] ); return 0; }
+int x264cu_lookahead_mbtree_swap( x264cu_lookahead_t *la, int a, int b )
+{
+    uint16_t *t = la->slots[a]->propagate_cost; la->slots[a]->propagate_cost = la->slots[b]->propagate_cost; la->slots[b]->propagate_cost = t;
+    return 0;
+}
+int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int referenced, float fps_factor )
+{
+    orc_la_frame_t *fr[300];
+    for( int i = p0; i <= p1; i++ ) fr[i] = la->slots[frames[i]];
+    orc_la_mbtree_propagate( &la->p, fr, p0, p1, b, referenced, fps_factor );
+    return 0;
+}
+int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_factor, int ref0_distance, float strength )
+{
+    if( !fps_factor ) memcpy( la->slots[slot]->qp_offset, la->slots[slot]->qp_offset_aq, la->slots[slot]->mb_count * sizeof(float) );
+    else orc_la_mbtree_finish( la->slots[slot], fps_factor, ref0_distance, strength );
+    return 0;
+}
+int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *out )
+{
+    memcpy( out, la->slots[slot]->qp_offset, la->slots[slot]->mb_count * sizeof(float) );
+    return 0;
+}

@@ -69,3 +69,28 @@ int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int i0, int
 }
 void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on ) { (void)la; (void)on; }
 int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int a, int b ) { (void)la; (void)a; (void)b; return 0; }
+
+/* ---- MB-tree entries, served by the reference's own macroblock_tree_propagate / _finish (all durations left at the frame
+ * pool's initial 0, i.e. clamped to the same 0.01 s: the factors of a constant frame rate) ---- */
+void xref_la_mbtree_reset( void *la, int idx );
+void xref_la_mbtree_swap( void *la, int a, int b );
+void xref_la_mbtree_propagate( void *la, float average_duration, int p0, int p1, int b, int referenced );
+void xref_la_mbtree_finish( void *la, int idx, float average_duration, int ref0_distance );
+void xref_la_get_mbtree( void *la, int idx, int what, int i, void *out );
+int x264cu_lookahead_frame_set_qp_offset_aq( x264cu_lookahead_t *la, int slot, const float *aq ) { (void)la; (void)slot; (void)aq; return 0; }
+int x264cu_lookahead_mbtree_reset( x264cu_lookahead_t *la, int slot ) { xref_la_mbtree_reset( la->la, slot + 300 ); return 0; }
+int x264cu_lookahead_mbtree_swap( x264cu_lookahead_t *la, int a, int b ) { xref_la_mbtree_swap( la->la, a + 300, b + 300 ); return 0; }
+int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int referenced, float fps_factor )
+{
+    (void)fps_factor;
+    xref_la_remap( la->la, frames, p0, p1 );
+    xref_la_mbtree_propagate( la->la, 0.0f, p0, p1, b, referenced );
+    return 0;
+}
+int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_factor, int ref0_distance, float strength )
+{
+    (void)fps_factor; (void)strength;
+    xref_la_mbtree_finish( la->la, slot + 300, 0.0f, ref0_distance );
+    return 0;
+}
+int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *out ) { xref_la_get_mbtree( la->la, slot + 300, 0, 0, out ); return 0; }

@@ -1,0 +1,140 @@
+"""GPU parity of MB-tree (x264cu_lookahead_mbtree_* = macroblock_tree_propagate / _finish, encoder/slicetype.c:1029-1184,
+common/mc.c:511-598): (1) macroblock_tree's call sequence replayed on the device and on the oracle (which
+tests/test_oracle_mbtree.py pins to the compiled reference): i_propagate_cost exact, f_qp_offset bit-exact; (2) end to end:
+the f_qp_offset of every non-B picture out of x264cu_slicetype_step versus the reference ENCODER's own (where it travelled)
+and versus the same host logic over the oracle."""
+import ctypes as C
+import numpy as np
+import pytest
+import x264_b200 as x
+import _libs
+from _libs import oracle, have_ref, ptr, OrcLaParams, synth_sequence, slicetype_oracle_lib
+import test_slicetype_host as host
+from test_oracle_mbtree import replay_macroblock_tree, T_P, T_B, T_BREF
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    _libs._bind_la()
+    c = x.Context(0)
+    yield c
+    c.close()
+
+
+# (w, h, bframes, weighted_pred, aq, types of frames 1..n, b_pyramid)
+REPLAY = [
+    (112, 80, 3, 0, 0, [T_B, T_B, T_P, T_B, T_P], False),
+    (112, 80, 3, -1, 1, [T_P, T_B, T_BREF, T_B, T_P], True),
+    (352, 288, 2, 1, 1, [T_B, T_P, T_B, T_B, T_P], False),
+]
+
+
+@pytest.mark.parametrize("cfg", REPLAY)
+def test_mbtree_replay_matches_oracle(ctx, cfg):
+    w, h, bframes, wp, aq_on, types, b_pyramid = cfg
+    o = oracle()
+    p = OrcLaParams()
+    p.width, p.height, p.mb_width, p.mb_height = w, h, (w + 15) // 16, (h + 15) // 16
+    p.subpel_refine, p.me_method, p.me_range, p.mv_range = 7, 1, 16, 512
+    p.bframes, p.bframe_bias, p.weighted_bipred, p.aq_mode, p.vbv, p.do_edges, p.weighted_pred = bframes, 0, 1, aq_on, 0, 1, wp
+    nfr = len(types) + 1
+    frames = synth_sequence(w, h, nfr, seed=w + 7, cut_at=None)
+    if wp:
+        frames = [np.clip(f.astype(np.float32) * (0.55 + 0.09 * i) + 3 * i, 0, 255).astype(np.uint8) for i, f in enumerate(frames)]
+    n = 2 * 4 * p.mv_range
+    tab = np.zeros(2 * n + 1, np.uint16)
+    o.orc_cost_mv_table(tab, n, 1)
+    nmb = p.mb_width * p.mb_height
+    la = x.Lookahead(ctx, w, h, bframes=bframes, aq_mode=aq_on, mb_tree=1, n_slots=nfr, weighted_pred=wp)
+    ofr = (C.c_void_p * (nfr + 2))()
+    rng = np.random.default_rng(3)
+    for i, f in enumerate(frames):
+        q = rng.integers(180, 400, nmb).astype(np.uint16) if aq_on else np.full(nmb, 256, np.uint16)
+        aq = (rng.normal(0, 1.5, nmb) if aq_on else np.zeros(nmb)).astype(np.float32)
+        la.frame_put(i, f, q)
+        la.set_qp_offset_aq(i, aq)
+        ofr[i] = o.orc_la_frame_new(C.byref(p), ptr(f), w)
+        o.orc_la_frame_set_qscale(ofr[i], q)
+        o.orc_la_frame_set_qp_offset_aq(ofr[i], ptr(aq))
+    slots = list(range(nfr))
+    fps_prop, fps_fin, strength = np.float32(0.5 / 256), 512, np.float32(5.0) * (np.float32(1.0) - np.float32(0.6))
+
+    def cost(p0, p1, b):
+        assert la.frame_cost(slots, p0, p1, b) == o.orc_la_frame_cost(C.byref(p), tab.ctypes.data + 2 * n, ofr, p0, p1, b), (p0, p1, b)
+
+    def reset(i):
+        la.mbtree_reset(i)
+        o.orc_la_mbtree_reset(ofr[i])
+
+    def propagate(p0, p1, b, referenced):
+        la.mbtree_propagate(slots, p0, p1, b, referenced, fps_prop)
+        o.orc_la_mbtree_propagate(C.byref(p), ofr, p0, p1, b, referenced, fps_prop)
+
+    def finish(i, dist):
+        la.mbtree_finish(i, fps_fin, dist, strength)
+        o.orc_la_mbtree_finish(ofr[i], fps_fin, dist, strength)
+
+    try:
+        # as in the encoder, every non-B picture has been costed against the previous one before the tree is built (the
+        # reference computes a picture's intra costs inside its first cost request, this backend when the picture is queued)
+        all_types = [T_P] + types
+        prev = 0
+        for k in range(1, nfr):
+            if all_types[k] == T_P:
+                cost(prev, k, k)
+                prev = k
+        touched = replay_macroblock_tree(all_types, b_pyramid, cost, reset, propagate, finish)
+        seen = False
+        for k in sorted(touched):
+            want = np.zeros(nmb, np.uint16)
+            o.orc_la_frame_get_mbtree(ofr[k], 2, 0, ptr(want))
+            got = la.get_propagate_cost(k)
+            assert np.array_equal(got, want), ("propagate_cost", k, np.argwhere(got != want)[:5])
+            seen |= bool(want.any())
+        assert seen
+        for k in range(1, nfr):
+            want = np.zeros(nmb, np.float32)
+            o.orc_la_frame_get_mbtree(ofr[k], 0, 0, ptr(want))
+            got = la.get_qp_offset(k)
+            assert np.array_equal(got, want), ("qp_offset", k, float(np.abs(got - want).max()))
+            for d in range(bframes + 1):
+                wd = C.c_float()
+                o.orc_la_frame_get_mbtree(ofr[k], 3, d, C.byref(wd))
+                assert la.get_weighted_cost_delta(k, d) == wd.value, ("weighted_cost_delta", k, d)
+    finally:
+        la.close()
+        for k in range(nfr):
+            o.orc_la_frame_delete(ofr[k])
+
+
+@pytest.mark.parametrize("case", host.MBTREE_CASES)
+def test_mbtree_qp_offsets_end_to_end(ctx, case):
+    preset, opts, (w, h), n, cut = case
+    frames = synth_sequence(w, h, n, seed=n + w, cut_at=cut)
+    qp_ref, qp_orc, qp_gpu = {}, {}, {}
+    if have_ref():
+        p, want = host.reference_types(preset, opts, w, h, frames, qp_ref)
+    else:
+        pytest.skip("compiled reference did not travel (its option parsing provides the parameters)")
+    want_orc = host.decide_with(slicetype_oracle_lib(), p, frames, qp_orc)
+    st = x.Slicetype(ctx, w, h, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
+                     b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy,
+                     frame_reference=p.frame_reference, rc_cqp=0,
+                     subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
+                     bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
+                     aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0, weighted_pred=p.la.weighted_pred)
+    try:
+        got = st.decide(frames, qp_gpu)
+    finally:
+        st.close()
+    assert got == want == want_orc
+    compared = 0
+    for fr, ty in want:
+        if ty in (4, 5):
+            continue
+        assert np.array_equal(qp_gpu[fr], qp_orc[fr]), ("vs oracle", fr, float(np.abs(qp_gpu[fr] - qp_orc[fr]).max()))
+        assert np.array_equal(qp_gpu[fr], qp_ref[fr]), ("vs reference encoder", fr, float(np.abs(qp_gpu[fr] - qp_ref[fr]).max()))
+        compared += 1
+    assert compared >= 5 and any(np.abs(q).max() > 0.5 for q in qp_gpu.values())

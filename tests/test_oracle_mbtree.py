@@ -21,6 +21,58 @@ CASES = [
 ]
 
 
+def replay_macroblock_tree(all_types, b_pyramid, cost, reset, propagate, finish):
+    """macroblock_tree( frames, num_frames = len(all_types) - 1, b_intra = 0 ) with rc-lookahead > 0 (slicetype.c:1091-1184) as a
+    sequence of calls of the four callbacks; returns the set of frames whose i_propagate_cost was reset (= is defined)"""
+    is_b = lambda t: t in (T_B, T_BREF)
+    touched = set()
+
+    def rst(i):
+        touched.add(i)
+        reset(i)
+
+    nfr = len(all_types)
+    i = nfr - 1
+    while i > 0 and is_b(all_types[i]):
+        i -= 1
+    last_nonb = i
+    rst(last_nonb)
+    bframes = 0
+    while i > 1:
+        i -= 1
+        cur_nonb = i
+        while is_b(all_types[cur_nonb]) and cur_nonb > 0:
+            cur_nonb -= 1
+        if cur_nonb < 1:
+            break
+        cost(cur_nonb, last_nonb, last_nonb)
+        rst(cur_nonb)
+        bframes = last_nonb - cur_nonb - 1
+        if b_pyramid and bframes > 1:
+            middle = (bframes + 1) // 2 + cur_nonb
+            cost(cur_nonb, last_nonb, middle)
+            rst(middle)
+            while i > cur_nonb:
+                p0 = middle if i > middle else cur_nonb
+                p1 = middle if i < middle else last_nonb
+                if i != middle:
+                    cost(p0, p1, i)
+                    propagate(p0, p1, i, 0)
+                i -= 1
+            propagate(cur_nonb, last_nonb, middle, 1)
+        else:
+            while i > cur_nonb:
+                cost(cur_nonb, last_nonb, i)
+                propagate(cur_nonb, last_nonb, i, 0)
+                i -= 1
+        propagate(cur_nonb, last_nonb, last_nonb, 1)
+        last_nonb = cur_nonb
+    finish(last_nonb, last_nonb)
+    if b_pyramid and bframes > 1:
+        finish(last_nonb + (bframes + 1) // 2, 0)
+    return touched
+
+
 def test_log2_table():
     _libs._bind_la()
     lut = (C.c_float * 128).in_dll(ref(), "x264_log2_lut")
@@ -62,8 +114,9 @@ def test_mbtree_matches_reference(case):
             o.orc_la_frame_set_qscale(ofr[i], q)
             o.orc_la_frame_set_qp_offset_aq(ofr[i], ptr(aq))
         all_types = [T_P] + types
-        cost = lambda p0, p1, b: (r.xref_la_frame_cost(la, p0, p1, b),
-                                  o.orc_la_frame_cost(C.byref(p), tab.ctypes.data + 2 * n, ofr, p0, p1, b))
+        def cost(p0, p1, b):
+            s1, s2 = r.xref_la_frame_cost(la, p0, p1, b), o.orc_la_frame_cost(C.byref(p), tab.ctypes.data + 2 * n, ofr, p0, p1, b)
+            assert s1 == s2, (p0, p1, b)
         fps_prop = np.float32(dur) / (np.float32(dur) * np.float32(256.0)) * np.float32(0.5)
         fps_fin = int(round(dur / dur * 256 / 0.5))
         strength = np.float32(5.0) * (np.float32(1.0) - np.float32(0.6))
@@ -72,10 +125,7 @@ def test_mbtree_matches_reference(case):
             r.xref_la_mbtree_propagate(la, dur, p0, p1, b, referenced)
             o.orc_la_mbtree_propagate(C.byref(p), ofr, p0, p1, b, referenced, fps_prop)
 
-        touched = set()
-
         def reset(i):
-            touched.add(i)
             r.xref_la_mbtree_reset(la, i)
             o.orc_la_mbtree_reset(ofr[i])
 
@@ -83,51 +133,8 @@ def test_mbtree_matches_reference(case):
             r.xref_la_mbtree_finish(la, i, dur, dist)
             o.orc_la_mbtree_finish(ofr[i], fps_fin, dist, strength)
 
-        # macroblock_tree( frames, num_frames = nfr - 1, b_intra = 0 ) with rc-lookahead > 0, slicetype.c:1091-1184
+        touched = replay_macroblock_tree(all_types, "b-pyramid=none" not in opts, cost, reset, propagate, finish)
         is_b = lambda t: t in (T_B, T_BREF)
-        b_pyramid = "b-pyramid=none" not in opts
-        i = nfr - 1
-        while i > 0 and is_b(all_types[i]):
-            i -= 1
-        last_nonb = i
-        reset(last_nonb)
-        bframes = 0
-        while i > 1:
-            i -= 1
-            cur_nonb = i
-            while is_b(all_types[cur_nonb]) and cur_nonb > 0:
-                cur_nonb -= 1
-            if cur_nonb < 1:
-                break
-            s = cost(cur_nonb, last_nonb, last_nonb)
-            assert s[0] == s[1]
-            reset(cur_nonb)
-            bframes = last_nonb - cur_nonb - 1
-            if b_pyramid and bframes > 1:
-                middle = (bframes + 1) // 2 + cur_nonb
-                s = cost(cur_nonb, last_nonb, middle)
-                assert s[0] == s[1]
-                reset(middle)
-                while i > cur_nonb:
-                    p0 = middle if i > middle else cur_nonb
-                    p1 = middle if i < middle else last_nonb
-                    if i != middle:
-                        s = cost(p0, p1, i)
-                        assert s[0] == s[1]
-                        propagate(p0, p1, i, 0)
-                    i -= 1
-                propagate(cur_nonb, last_nonb, middle, 1)
-            else:
-                while i > cur_nonb:
-                    s = cost(cur_nonb, last_nonb, i)
-                    assert s[0] == s[1]
-                    propagate(cur_nonb, last_nonb, i, 0)
-                    i -= 1
-            propagate(cur_nonb, last_nonb, last_nonb, 1)
-            last_nonb = cur_nonb
-        finish(last_nonb, last_nonb)
-        if b_pyramid and bframes > 1:
-            finish(last_nonb + (bframes + 1) // 2, 0)
         exact = total = 0
         checked_nonzero = False
         for k in range(1, nfr):          # frame 0 (the previous GOP's last non-B) is never touched with b_intra = 0: uninitialised in the reference

@@ -35,12 +35,13 @@ def params_from_ref(hnd, w, h):
     r = ref()
     g = lambda n: r.xref_param(hnd, n.encode())
     la = LookaheadParams(w, h, g("subme"), min(g("me"), 2), g("merange"), g("mvrange"), g("bframes"), g("b_bias"), g("weightb"),
-                         int(g("aq_mode") != 0), g("mbtree"), g("vbv"), 0, int(g("weightp") != 0))
+                         int(g("aq_mode") != 0), g("mbtree"), g("vbv"), 0, -1 if g("weightp") < 0 else int(g("weightp") != 0))
     return SlicetypeParams(la, g("keyint_max"), g("keyint_min"), g("scenecut"), g("b_adapt"), g("b_pyramid"), g("lookahead"),
                            g("psy"), g("ref"), 0)
 
 
-def decide_with(lib, p, frames):
+def decide_with(lib, p, frames, qp_out=None):
+    """qp_out: dict filled with frame -> f_qp_offset (MB-tree's output) for every non-B picture, read when it is returned"""
     lib.x264cu_slicetype_open.argtypes = [C.c_void_p, C.POINTER(SlicetypeParams), C.POINTER(C.c_void_p)]
     lib.x264cu_slicetype_step.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.x264cu_slicetype_close.argtypes = [C.c_void_p]
@@ -48,22 +49,34 @@ def decide_with(lib, p, frames):
     assert lib.x264cu_slicetype_open(C.c_void_p(1), C.byref(p), C.byref(st)) == 0
     out = []
     fr, ty = C.c_int(), C.c_int()
+    lib.x264cu_slicetype_get_qp_offset.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    nmb = ((p.la.width + 15) // 16) * ((p.la.height + 15) // 16)
+
+    def note():
+        out.append((fr.value, ty.value))
+        if qp_out is not None and ty.value not in (4, 5):
+            q = np.zeros(nmb, np.float32)
+            assert lib.x264cu_slicetype_get_qp_offset(st, fr.value, q.ctypes.data) == 0
+            qp_out[fr.value] = q
+
     for f in frames:
         assert lib.x264cu_slicetype_step(st, f.ctypes.data, f.shape[1], None, C.byref(fr), C.byref(ty)) == 0
         if fr.value >= 0:
-            out.append((fr.value, ty.value))
+            note()
     while True:
         assert lib.x264cu_slicetype_step(st, None, 0, None, C.byref(fr), C.byref(ty)) == 0
         if fr.value < 0:
             break
-        out.append((fr.value, ty.value))
+        note()
     lib.x264cu_slicetype_close(st)
     return out
 
 
-def reference_types(preset, opts, w, h, frames):
+def reference_types(preset, opts, w, h, frames, qp_out=None):
+    """qp_out: dict filled with frame -> the f_qp_offset array the reference encoder used for it"""
     r = ref()
     r.xref_encode_types.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    r.xref_set_qp_capture.argtypes = [C.c_void_p]
     hnd = r.xref_open(w, h, preset.encode(), opts.encode(), 0)
     assert hnd
     try:
@@ -72,8 +85,15 @@ def reference_types(preset, opts, w, h, frames):
         luma = np.ascontiguousarray(np.stack(frames))
         idx = (C.c_int * (n + 8))()
         typ = (C.c_int * (n + 8))()
+        nmb = ((w + 15) // 16) * ((h + 15) // 16)
+        cap = np.zeros((n + 8, nmb), np.float32)
+        r.xref_set_qp_capture(cap.ctypes.data if qp_out is not None else None)
         k = r.xref_encode_types(hnd, luma.ctypes.data, n, idx, typ)
+        r.xref_set_qp_capture(None)
         assert k == n
+        if qp_out is not None:
+            for i in range(k):
+                qp_out[idx[i]] = cap[i].copy()
         return p, [(idx[i], typ[i]) for i in range(k)]
     finally:
         r.xref_close(hnd)
@@ -92,3 +112,40 @@ def test_frame_types_match_reference_encoder(case):
     p, want = reference_types(preset, opts, w, h, frames)
     got = decide_with(slicetype_oracle_lib(), p, frames)
     assert got == want, (case, [x for x in zip(got, want) if x[0] != x[1]][:6])
+
+
+# MB-tree end to end: the f_qp_offset the reference ENCODER used for every non-B picture versus macroblock_tree in the
+# product's host logic (the device entry points served by the oracle here).  AQ off, so that f_qp_offset_aq is zero on both sides.
+MBTREE_CASES = [
+    ("medium", "aq-mode=0:weightp=0:no-psy=1:bframes=3:rc-lookahead=10:keyint=30:min-keyint=3", (112, 80), 60, 37),
+    ("medium", "aq-mode=0:weightp=0:bframes=3:b-adapt=2:rc-lookahead=12", (96, 64), 60, 41),          # fake weights (psy + mb-tree)
+    ("medium", "aq-mode=0:weightp=0:no-psy=1:bframes=2:b-pyramid=none:rc-lookahead=8", (96, 64), 50, 31),
+]
+
+
+def mbtree_compare(want_types, got_types, qp_ref, qp_got, n_frames, lookahead):
+    """frame types must agree everywhere; f_qp_offset is compared for every non-B picture (B pictures are coded with
+    f_qp_offset_aq).  Returns (pictures compared, pictures bit-exact, worst absolute difference)."""
+    assert got_types == want_types
+    compared = exact = 0
+    worst = 0.0
+    for fr, ty in want_types:
+        if ty in (4, 5):
+            continue
+        a, b = qp_ref[fr], qp_got[fr]
+        compared += 1
+        exact += int(np.array_equal(a, b))
+        worst = max(worst, float(np.abs(a - b).max()))
+    return compared, exact, worst
+
+
+@pytest.mark.parametrize("case", MBTREE_CASES)
+def test_mbtree_qp_offsets_match_reference_encoder(case):
+    preset, opts, (w, h), n, cut = case
+    frames = synth_sequence(w, h, n, seed=n + w, cut_at=cut)
+    qp_ref, qp_got = {}, {}
+    p, want = reference_types(preset, opts, w, h, frames, qp_ref)
+    got = decide_with(slicetype_oracle_lib(), p, frames, qp_got)
+    compared, exact, worst = mbtree_compare(want, got, qp_ref, qp_got, n, p.rc_lookahead)
+    assert compared >= 5 and any(np.abs(q).max() > 0.5 for q in qp_got.values())
+    assert exact == compared, "f_qp_offset bit-exact on %d of %d pictures, worst |diff| %.3g" % (exact, compared, worst)

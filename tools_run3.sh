@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_mbtree.py -x -q 2>&1 | grep -E "^E|passed|failed" | head -12

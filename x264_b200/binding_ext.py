@@ -32,7 +32,8 @@ me_result_dtype = np.dtype([("mv", np.int16, (2,)), ("cost", np.int32), ("cost_m
 
 class SlicetypeParams(C.Structure):
     _fields_ = [("la", LookaheadParams)] + [(n, C.c_int) for n in ("keyint_max", "keyint_min", "scenecut_threshold", "b_adapt",
-                                                                  "b_pyramid", "rc_lookahead", "psy", "frame_reference", "rc_cqp")]
+                                                                  "b_pyramid", "rc_lookahead", "psy", "frame_reference", "rc_cqp",
+                                                                  "fps_num", "fps_den")] + [("qcompress", C.c_float)]
 
 
 TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "BREF", 5: "B"}
@@ -48,6 +49,16 @@ def bind(L):
     L.x264cu_slicetype_set_prefetch.argtypes = [vp, ci]
     L.x264cu_slicetype_set_run_ahead.argtypes = [vp, ci]
     L.x264cu_slicetype_set_async_upload.argtypes = [vp, ci]
+    L.x264cu_slicetype_get_qp_offset.argtypes = [vp, ci, vp]
+    L.x264cu_lookahead_frame_set_qp_offset_aq.argtypes = [vp, ci, vp]
+    L.x264cu_lookahead_mbtree_reset.argtypes = [vp, ci]
+    L.x264cu_lookahead_mbtree_swap.argtypes = [vp, ci, ci]
+    L.x264cu_lookahead_mbtree_propagate.argtypes = [vp, C.POINTER(ci), ci, ci, ci, ci, C.c_float]
+    L.x264cu_lookahead_mbtree_finish.argtypes = [vp, ci, ci, ci, C.c_float]
+    L.x264cu_lookahead_get_qp_offset.argtypes = [vp, ci, vp]
+    L.x264cu_lookahead_get_propagate_cost.argtypes = [vp, ci, vp]
+    L.x264cu_lookahead_get_weighted_cost_delta.argtypes = [vp, ci, ci]
+    L.x264cu_lookahead_get_weighted_cost_delta.restype = C.c_float
     L.x264cu_lookahead_set_async_upload.argtypes = [vp, ci]
     L.x264cu_slicetype_lookahead.argtypes = [vp]
     L.x264cu_slicetype_lookahead.restype = vp
@@ -149,6 +160,34 @@ class Lookahead:
         self.ctx.check(self.L.x264cu_lookahead_get_cost_est(self.h, slot, i0, i1, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    # MB-tree (slicetype.c:1029-1184)
+    def set_qp_offset_aq(self, slot, aq):
+        a = None if aq is None else np.ascontiguousarray(aq, dtype=np.float32)
+        self.ctx.check(self.L.x264cu_lookahead_frame_set_qp_offset_aq(self.h, slot, a.ctypes.data if a is not None else None))
+
+    def mbtree_reset(self, slot):
+        self.ctx.check(self.L.x264cu_lookahead_mbtree_reset(self.h, slot))
+
+    def mbtree_propagate(self, frames, p0, p1, b, referenced, fps_factor):
+        arr = (C.c_int * len(frames))(*frames)
+        self.ctx.check(self.L.x264cu_lookahead_mbtree_propagate(self.h, arr, p0, p1, b, int(referenced), float(fps_factor)))
+
+    def mbtree_finish(self, slot, fps_factor, ref0_distance, strength):
+        self.ctx.check(self.L.x264cu_lookahead_mbtree_finish(self.h, slot, int(fps_factor), int(ref0_distance), float(strength)))
+
+    def get_qp_offset(self, slot):
+        out = np.zeros(self.mb_count, np.float32)
+        self.ctx.check(self.L.x264cu_lookahead_get_qp_offset(self.h, slot, out.ctypes.data))
+        return out
+
+    def get_propagate_cost(self, slot):
+        out = np.zeros(self.mb_count, np.uint16)
+        self.ctx.check(self.L.x264cu_lookahead_get_propagate_cost(self.h, slot, out.ctypes.data))
+        return out
+
+    def get_weighted_cost_delta(self, slot, dist_minus1):
+        return float(self.L.x264cu_lookahead_get_weighted_cost_delta(self.h, slot, dist_minus1))
+
     def get_weight(self, slot):
         w = (C.c_int * 4)()
         self.ctx.check(self.L.x264cu_lookahead_get_weight(self.h, slot, w))
@@ -182,6 +221,7 @@ class Slicetype:
             from .binding import X264CUError
             raise X264CUError("x264cu_slicetype_open failed: " + ctx.L.x264cu_strerror(ctx.h).decode())
         self.h = h
+        self.mb_count = ((width + 15) // 16) * ((height + 15) // 16)
 
     def close(self):
         if self.h:
@@ -215,17 +255,30 @@ class Slicetype:
         """page-locked pictures passed to step() are read in place; keep them unmodified until four more pictures have been queued"""
         self.L.x264cu_slicetype_set_async_upload(self.h, int(on))
 
-    def decide(self, frames):
+    def get_qp_offset(self, frame):
+        """f_qp_offset (MB-tree) of a non-B picture just returned by step()"""
+        out = np.zeros(self.mb_count, np.float32)
+        self.ctx.check(self.L.x264cu_slicetype_get_qp_offset(self.h, int(frame), out.ctypes.data))
+        return out
+
+    def decide(self, frames, qp_out=None):
+        """qp_out: dict filled with frame -> f_qp_offset for every non-B picture"""
         out = []
+
+        def note(fr, ty):
+            out.append((fr, ty))
+            if qp_out is not None and ty not in (4, 5):
+                qp_out[fr] = self.get_qp_offset(fr)
+
         for f in frames:
             fr, ty = self.step(f)
             if fr >= 0:
-                out.append((fr, ty))
+                note(fr, ty)
         while True:
             fr, ty = self.step(None)
             if fr < 0:
                 break
-            out.append((fr, ty))
+            note(fr, ty)
         return out
 
     @property

@@ -51,6 +51,8 @@ struct LaSlotDev
     uint16_t *qscale;                // [mb_count]
     int32_t *row_satds;              // [(B+2)*(B+2)][mb_h]
     unsigned long long *recs;        // [2][B+1][mb_count] (generation << 32 | mv): how the rows of a search hand over vectors
+    unsigned int *propagate;         // [mb_count] i_propagate_cost as a 32-bit accumulator (the reference's u16 saturates: clamped when read)
+    float *qp_offset, *qp_offset_aq; // [mb_count] f_qp_offset / f_qp_offset_aq
 };
 
 struct LaSearchJob
@@ -690,6 +692,93 @@ weight_plane_kernel( const uint32_t *__restrict__ src, uint32_t *__restrict__ ds
         dst[i] = weight4( src[i], w );
 }
 
+// ------------------------------------------------------------------------------------------------
+// MB-tree: macroblock_tree_propagate (slicetype.c:1050-1089) = mbtree_propagate_cost + mbtree_propagate_list
+// (common/mc.c:511-598) and macroblock_tree_finish (slicetype.c:1029-1048), one thread per macroblock.
+// The reference adds into u16 arrays with saturation, MB after MB; every addend is >= 0, so the result is
+// min( sum, 65535 ) whatever the order: here 32-bit atomics, clamped where the value is read.
+// Float expressions are evaluated operation by operation (no FMA contraction) in the reference's order.
+// ------------------------------------------------------------------------------------------------
+struct LaMbtreeArgs
+{
+    const unsigned int *prop_in;     // frame b's own accumulator (referenced frames) or NULL (all zero)
+    unsigned int *ref_costs[2];      // accumulators of p0 / p1 (the second NULL for P frames)
+    const int16_t *mvs[2];
+    const int32_t *intra;
+    const uint16_t *lowres_costs, *qscale;
+    int bipred_weight[2];
+    float fps_factor;
+};
+
+__global__ void __launch_bounds__( 256 )
+mbtree_propagate_kernel( LaDims d, LaMbtreeArgs A )
+{
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if( mb >= d.mb_count ) return;
+    const int mb_y = mb / d.mb_w, mb_x = mb - mb_y * d.mb_w;
+    // mbtree_propagate_cost, mc.c:511-527
+    const int intra_cost = (uint16_t)A.intra[mb];
+    const int lc = A.lowres_costs[mb];
+    const int inter_cost = min( intra_cost, lc & LOWRES_COST_MASK );
+    const float propagate_intra = (float)( intra_cost * (int)A.qscale[mb] );
+    const float propagate_in = (float)( A.prop_in ? min( A.prop_in[mb], 65535u ) : 0u );
+    const float propagate_amount = __fadd_rn( propagate_in, __fmul_rn( propagate_intra, A.fps_factor ) );
+    const float num = (float)( intra_cost - inter_cost ), denom = (float)intra_cost;
+    const int amount = min( __float2int_rz( __fadd_rn( __fdiv_rn( __fmul_rn( propagate_amount, num ), denom ), 0.5f ) ), 32767 );
+    const int lists_used = lc >> LOWRES_COST_SHIFT;
+    // mbtree_propagate_list, mc.c:529-598
+#pragma unroll
+    for( int list = 0; list < 2; list++ )
+    {
+        unsigned int *ref_costs = A.ref_costs[list];
+        if( !ref_costs || !( lists_used & ( 1 << list ) ) ) continue;
+        int listamount = amount;
+        if( lists_used == 3 ) listamount = ( listamount * A.bipred_weight[list] + 32 ) >> 6;
+        const int v = *(const int *)( A.mvs[list] + 2 * mb );
+        int x = (int16_t)( v & 0xffff ), y = (int16_t)( v >> 16 );
+        if( !v ) { if( listamount ) atomicAdd( &ref_costs[mb], (unsigned)listamount ); continue; }
+        const unsigned mbx = (unsigned)( ( x >> 5 ) + mb_x ), mby = (unsigned)( ( y >> 5 ) + mb_y );
+        const unsigned idx0 = mbx + mby * d.mb_w, idx2 = idx0 + d.mb_w;
+        x &= 31; y &= 31;
+        const int w0 = ( ( 32 - y ) * ( 32 - x ) * listamount + 512 ) >> 10, w1 = ( ( 32 - y ) * x * listamount + 512 ) >> 10;
+        const int w2 = ( y * ( 32 - x ) * listamount + 512 ) >> 10, w3 = ( y * x * listamount + 512 ) >> 10;
+        if( mby < (unsigned)d.mb_h )
+        {
+            if( mbx < (unsigned)d.mb_w && w0 ) atomicAdd( &ref_costs[idx0], (unsigned)w0 );
+            if( mbx + 1 < (unsigned)d.mb_w && w1 ) atomicAdd( &ref_costs[idx0 + 1], (unsigned)w1 );
+        }
+        if( mby + 1 < (unsigned)d.mb_h )
+        {
+            if( mbx < (unsigned)d.mb_w && w2 ) atomicAdd( &ref_costs[idx2], (unsigned)w2 );
+            if( mbx + 1 < (unsigned)d.mb_w && w3 ) atomicAdd( &ref_costs[idx2 + 1], (unsigned)w3 );
+        }
+    }
+}
+
+__constant__ float c_log2_lut[128];          // x264_log2_lut, common/tables.c:66-85
+
+__global__ void __launch_bounds__( 256 )
+mbtree_finish_kernel( int mb_count, const int32_t *__restrict__ intra, const uint16_t *__restrict__ qscale,
+                      const unsigned int *__restrict__ propagate, const float *__restrict__ qp_aq, float *__restrict__ qp,
+                      int fps_factor, float weightdelta, float strength )
+{
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if( mb >= mb_count ) return;
+    const int intra_cost = ( (int)(uint16_t)intra[mb] * (int)qscale[mb] + 128 ) >> 8;
+    if( !intra_cost ) return;
+    const int propagate_cost = (int)( ( min( propagate[mb], 65535u ) * (unsigned)fps_factor + 128u ) >> 8 );
+    // x264_log2( a ) - x264_log2( b ) + weightdelta (base.h:226-230).  The reference is built with -ffast-math (configure:1413),
+    // which lets the compiler re-associate the five float terms; this is the association gcc 13 -O3 emits for
+    // slicetype.c:1044 (read from the disassembly of the compiled reference): bit-identical to that build,
+    // a few ulp of 16.0 from any other
+    const uint32_t a = intra_cost + propagate_cost, b = intra_cost;
+    const int lza = __clz( a ), lzb = __clz( b );
+    const float fa = c_log2_lut[( a << lza >> 24 ) & 0x7f], fb = c_log2_lut[( b << lzb >> 24 ) & 0x7f];
+    const float ia = (float)( 31 - lza ), ib = (float)( 31 - lzb );
+    const float ratio = __fsub_rn( __fadd_rn( __fsub_rn( fa, ib ), __fadd_rn( ia, weightdelta ) ), fb );
+    qp[mb] = __fsub_rn( qp_aq[mb], __fmul_rn( strength, ratio ) );
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -711,6 +800,7 @@ struct LaSlotHost
     unsigned long long pixel_sum, pixel_ssd;   // i_pixel_sum[0] / i_pixel_ssd[0] (ratecontrol.c:405-414), valid once stats_ready
     bool stats_ready;
     LaWeight weight;                 // fenc->weight[0][0] of the last lookahead analysis
+    float weighted_cost_delta[LA_MAX_B + 1];   // f_weighted_cost_delta (slicetype.c:462-463, X264_WEIGHTP_FAKE only)
     int last_search_ev = -1;         // event (ring index, sequence number) of the last prefetch launch that reads this slot
     unsigned long long last_search_seq = 0;
     cudaEvent_t ev_ready = nullptr;  // recorded on the upload stream when the picture's planes / reset arrays are in place
@@ -803,6 +893,7 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     {
         cudaFree( s.plane_buf ); cudaFree( s.dev.mvs ); cudaFree( s.dev.mv_costs ); cudaFree( s.dev.costs );
         cudaFree( s.dev.intra ); cudaFree( s.dev.qscale ); cudaFree( s.dev.row_satds ); cudaFree( s.dev.recs ); cudaFree( s.d_stats );
+        cudaFree( s.dev.propagate ); cudaFree( s.dev.qp_offset ); cudaFree( s.dev.qp_offset_aq );
     }
     cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record ); cudaFree( la->d_weight_plane ); cudaFree( la->d_tickets );
     cudaFreeHost( la->h_stats );
@@ -874,6 +965,9 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         alloc( (void **)&s.dev.qscale, (size_t)d.mb_count * 2 );
         alloc( (void **)&s.dev.row_satds, (size_t)B2 * d.mb_h * 4 );
         alloc( (void **)&s.dev.recs, (size_t)2 * B1 * d.mb_count * 8 );
+        alloc( (void **)&s.dev.propagate, (size_t)d.mb_count * 4 );
+        alloc( (void **)&s.dev.qp_offset, (size_t)d.mb_count * 4 );
+        alloc( (void **)&s.dev.qp_offset_aq, (size_t)d.mb_count * 4 );
         s.d_stats = nullptr;
         alloc( (void **)&s.d_stats, 16 );
         if( ok && cudaEventCreateWithFlags( &s.ev_ready, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
@@ -939,6 +1033,21 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         x264cu_lookahead_close( la );
         return -1;
     }
+    {   // x264_log2_lut (common/tables.c:66-85): log2( 1 + i/128 ) printed with five decimals
+        float lut[128];
+        for( int i = 0; i < 128; i++ )
+        {
+            char buf[32];
+            snprintf( buf, sizeof( buf ), "%.5f", log2( 1.0 + i / 128.0 ) );
+            lut[i] = strtof( buf, nullptr );
+        }
+        if( cudaMemcpyToSymbol( c_log2_lut, lut, sizeof( lut ) ) != cudaSuccess )
+        {
+            x264cu_fail( ctx, "lookahead_open: log2 table upload failed" );
+            x264cu_lookahead_close( la );
+            return -1;
+        }
+    }
     ctx->aux_streams.push_back( la->up_stream );
     for( int i = 0; i < 2; i++ ) ctx->aux_streams.push_back( la->search_streams[i] );
     *out = la;
@@ -964,6 +1073,11 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
     s.in_use = true;
     s.stats_ready = false;
     s.weight.enabled = 0; s.weight.scale = 1; s.weight.denom = 0; s.weight.offset = 0;
+    memset( s.weighted_cost_delta, 0, sizeof( s.weighted_cost_delta ) );            // frame.c:798
+    {   // without AQ both offset arrays are zero (x264_adaptive_quant_frame, ratecontrol.c:308-330); see frame_set_qp_offset_aq
+        CU_CHECK( ctx, cudaMemsetAsync( s.dev.qp_offset, 0, (size_t)d.mb_count * 4, stream ) );
+        CU_CHECK( ctx, cudaMemsetAsync( s.dev.qp_offset_aq, 0, (size_t)d.mb_count * 4, stream ) );
+    }
     CU_CHECK( ctx, cudaMemsetAsync( s.dev.mvs, 0, (size_t)2 * ( d.B + 1 ) * d.mb_count * 4, stream ) );
     if( h_inv_qscale )
     {   // staged through a ring of pinned buffers: the caller's array may be reused as soon as this returns, and the
@@ -1257,7 +1371,7 @@ static int la_weight_cost( x264cu_lookahead *la, LaSlotHost &fenc, LaSlotHost &r
 
 /* x264_weights_analyse( h, fenc, ref, b_lookahead = 1 ), slicetype.c:284-501: luma only; the float expressions are the
  * reference's.  On success fenc.weight holds the weight (enabled = 0: none) and la->d_weight_plane the weighted plane. */
-static int la_weights_analyse( x264cu_lookahead *la, int fenc_slot, int ref_slot )
+static int la_weights_analyse( x264cu_lookahead *la, int fenc_slot, int ref_slot, int delta_index )
 {
     x264cu_ctx *ctx = la->ctx;
     LaSlotHost &fenc = la->slots[fenc_slot], &ref = la->slots[ref_slot];
@@ -1306,10 +1420,136 @@ static int la_weights_analyse( x264cu_lookahead *la, int fenc_slot, int ref_slot
     if( !found || ( minscale == 1 << mindenom && minoff == 0 ) || (float)minscore / origscore > 0.998f )
         return 0;
     fenc.weight.enabled = 1; fenc.weight.scale = minscale; fenc.weight.denom = mindenom; fenc.weight.offset = minoff;
+    if( la->p.weighted_pred < 0 )                                   /* X264_WEIGHTP_FAKE, slicetype.c:462-463 */
+        fenc.weighted_cost_delta[delta_index] = (float)minscore / origscore;
     const size_t words = ( (size_t)d.stride * ( la->ll + 2 * X264CU_PAD ) + 128 ) / 4;
     weight_plane_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>( (const uint32_t *)( ref.plane_buf ), (uint32_t *)la->d_weight_plane, words, fenc.weight );
     CU_LAUNCH_CHECK( ctx );
     return 0;
+}
+
+static int la_check_slot( x264cu_lookahead *la, int slot );
+
+/* ---- MB-tree (slicetype.c:1029-1184) ---- */
+int x264cu_lookahead_frame_set_qp_offset_aq( x264cu_lookahead_t *la, int slot, const float *h_aq )
+{
+    if( la_check_slot( la, slot ) ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    LaSlotHost &s = la->slots[slot];
+    const size_t n = (size_t)la->d.mb_count * 4;
+    if( h_aq )
+    {
+        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qp_offset_aq, h_aq, n, cudaMemcpyHostToDevice, ctx->stream ) );
+        CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );             // the caller's array is free on return
+    }
+    else
+        CU_CHECK( ctx, cudaMemsetAsync( s.dev.qp_offset_aq, 0, n, ctx->stream ) );
+    CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qp_offset, s.dev.qp_offset_aq, n, cudaMemcpyDeviceToDevice, ctx->stream ) );
+    return 0;
+}
+
+int x264cu_lookahead_mbtree_reset( x264cu_lookahead_t *la, int slot )
+{
+    if( !la ) return -1;
+    if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use ) return x264cu_fail( la->ctx, "mbtree_reset: empty slot %d", slot );
+    if( la_slot_ready( la, slot ) ) return -1;
+    CU_CHECK( la->ctx, cudaMemsetAsync( la->slots[slot].dev.propagate, 0, (size_t)la->d.mb_count * 4, la->ctx->stream ) );
+    return 0;
+}
+
+int x264cu_lookahead_mbtree_swap( x264cu_lookahead_t *la, int slot_a, int slot_b )
+{   // XCHG( uint16_t*, a->i_propagate_cost, b->i_propagate_cost ), slicetype.c:1125, :1177; work already queued keeps its pointers
+    if( !la ) return -1;
+    for( int s : { slot_a, slot_b } )
+        if( s < 0 || s >= (int)la->slots.size() || !la->slots[s].in_use ) return x264cu_fail( la->ctx, "mbtree_swap: empty slot %d", s );
+    if( la_slot_ready( la, slot_a ) || la_slot_ready( la, slot_b ) ) return -1;
+    std::swap( la->slots[slot_a].dev.propagate, la->slots[slot_b].dev.propagate );
+    return 0;
+}
+
+int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int referenced, float fps_factor )
+{
+    if( !la || !frames ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    const LaDims &d = la->d;
+    if( !( p0 < p1 && p0 < b && b <= p1 ) || b - p0 > d.B + 1 || p1 - b > d.B + 1 )
+        return x264cu_fail( ctx, "mbtree_propagate: bad frame triple (%d,%d,%d)", p0, p1, b );
+    const int sb = frames[b], s0 = frames[p0], s1 = frames[p1];
+    for( int s : { sb, s0, s1 } )
+        if( s < 0 || s >= (int)la->slots.size() || !la->slots[s].in_use ) return x264cu_fail( ctx, "mbtree_propagate: empty slot %d", s );
+    LaSlotHost &fb = la->slots[sb];
+    const int i0 = b - p0, i1 = p1 - b;
+    if( fb.cost_est[i0][i1] < 0 ) return x264cu_fail( ctx, "mbtree_propagate: the cost (%d,%d,%d) has not been requested", p0, p1, b );
+    for( int s : { sb, s0, s1 } )
+        if( la_slot_ready( la, s ) ) return -1;
+    const int B1 = d.B + 1;
+    LaMbtreeArgs A;
+    memset( &A, 0, sizeof( A ) );
+    const int dist_scale_factor = ( ( i0 << 8 ) + ( ( p1 - p0 ) >> 1 ) ) / ( p1 - p0 );
+    const int bw = d.bipred_weighted ? 64 - ( dist_scale_factor >> 2 ) : 32;
+    A.bipred_weight[0] = bw; A.bipred_weight[1] = 64 - bw;
+    A.ref_costs[0] = la->slots[s0].dev.propagate;
+    A.mvs[0] = fb.dev.mvs + (size_t)( 0 * B1 + i0 - 1 ) * d.mb_count * 2;
+    if( b != p1 )
+    {
+        A.ref_costs[1] = la->slots[s1].dev.propagate;
+        A.mvs[1] = fb.dev.mvs + (size_t)( 1 * B1 + i1 - 1 ) * d.mb_count * 2;
+    }
+    A.intra = fb.dev.intra; A.qscale = fb.dev.qscale;
+    A.lowres_costs = fb.dev.costs + (size_t)( i0 * ( d.B + 2 ) + i1 ) * d.mb_count;
+    A.fps_factor = fps_factor;
+    if( referenced ) A.prop_in = fb.dev.propagate;
+    else            // slicetype.c:1066-1067: the first row of the frame's own array is cleared and re-used as the all-zero input
+        CU_CHECK( ctx, cudaMemsetAsync( fb.dev.propagate, 0, (size_t)d.mb_w * 4, ctx->stream ) );
+    mbtree_propagate_kernel<<<( d.mb_count + 255 ) / 256, 256, 0, ctx->stream>>>( d, A );
+    CU_LAUNCH_CHECK( ctx );
+    return 0;
+}
+
+int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_factor, int ref0_distance, float strength )
+{
+    if( !la ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use ) return x264cu_fail( ctx, "mbtree_finish: empty slot %d", slot );
+    if( ref0_distance < 0 || ref0_distance > la->d.B + 1 ) return x264cu_fail( ctx, "mbtree_finish: bad distance %d", ref0_distance );
+    if( la_slot_ready( la, slot ) ) return -1;
+    LaSlotHost &f = la->slots[slot];
+    if( !fps_factor )
+    {   // lookahead-less intra case (slicetype.c:1121-1123): f_qp_offset = f_qp_offset_aq
+        CU_CHECK( ctx, cudaMemcpyAsync( f.dev.qp_offset, f.dev.qp_offset_aq, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToDevice, ctx->stream ) );
+        return 0;
+    }
+    float weightdelta = 0.0f;
+    if( ref0_distance && f.weighted_cost_delta[ref0_distance - 1] > 0 )
+        weightdelta = ( 1.0 - f.weighted_cost_delta[ref0_distance - 1] );
+    mbtree_finish_kernel<<<( la->d.mb_count + 255 ) / 256, 256, 0, ctx->stream>>>( la->d.mb_count, f.dev.intra, f.dev.qscale, f.dev.propagate,
+                                                                                  f.dev.qp_offset_aq, f.dev.qp_offset, fps_factor, weightdelta, strength );
+    CU_LAUNCH_CHECK( ctx );
+    return 0;
+}
+
+int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *h_qp_offset )
+{
+    if( la_check_slot( la, slot ) ) return -1;
+    CU_CHECK( la->ctx, cudaMemcpyAsync( h_qp_offset, la->slots[slot].dev.qp_offset, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
+    CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
+    return 0;
+}
+
+int x264cu_lookahead_get_propagate_cost( x264cu_lookahead_t *la, int slot, uint16_t *h_out )
+{
+    if( la_check_slot( la, slot ) ) return -1;
+    std::vector<unsigned int> tmp( la->d.mb_count );
+    CU_CHECK( la->ctx, cudaMemcpyAsync( tmp.data(), la->slots[slot].dev.propagate, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
+    CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
+    for( int i = 0; i < la->d.mb_count; i++ ) h_out[i] = (uint16_t)( tmp[i] > 65535u ? 65535u : tmp[i] );
+    return 0;
+}
+
+float x264cu_lookahead_get_weighted_cost_delta( x264cu_lookahead_t *la, int slot, int dist_minus1 )
+{
+    if( !la || slot < 0 || slot >= (int)la->slots.size() || dist_minus1 < 0 || dist_minus1 > la->d.B ) return -1.0f;
+    return la->slots[slot].weighted_cost_delta[dist_minus1];
 }
 
 int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int fenc_slot, int ref_slot )
@@ -1364,7 +1604,7 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
                 fenc.weight.enabled = 0; fenc.weight.scale = 1; fenc.weight.denom = 0; fenc.weight.offset = 0;
             }
             /* The analysis may itself issue an intra-only request, which reuses la->pack: run it before the job list is assembled */
-            else if( la_weights_analyse( la, sb, s0 ) ) return -1;
+            else if( la_weights_analyse( la, sb, s0, i0 - 1 ) ) return -1;
         }
         if( !fenc.searched[0][i0 - 1] )
         {

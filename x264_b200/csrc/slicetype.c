@@ -9,6 +9,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <time.h>
+#include <math.h>
 static double st_now( void ) { struct timespec t; clock_gettime( CLOCK_MONOTONIC, &t ); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 #define LOOKAHEAD_MAX 250                 /* X264_LOOKAHEAD_MAX, common/base.h:140 */
@@ -64,6 +65,7 @@ struct x264cu_slicetype
     int prefetch_group;                   /* pictures per prefetch launch */
     double t_put, t_batch, t_cost, t_step; long n_cost_calls;   /* X264CU_STATS: where the calling thread's time goes */
     int run_ahead;                        /* extra pictures queued before deciding, like param.i_sync_lookahead (encoder.c:1611) */
+    float duration, qcompress;            /* f_duration of every picture (constant frame rate), rc.f_qcompress */
 };
 
 int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame );
@@ -224,23 +226,67 @@ static int scenecut( x264cu_slicetype_t *s, st_frame_t **frames, int p0, int p1,
     return scenecut_internal( s, frames, p0, p1, real_scenecut );
 }
 
-/* the slicetype_frame_cost requests of macroblock_tree, slicetype.c:1091-1184 (the propagation itself is not part
- * of this backend; only its requests matter for later memoised costs) */
-static void mbtree_requests( x264cu_slicetype_t *s, st_frame_t **frames, int num_frames, int b_intra )
+/* CLIP_DURATION, ratecontrol.h: durations outside [0.01 s, 1 s] are clamped */
+static float clip_duration( float f ) { return f < 0.01f ? 0.01f : f > 1.00f ? 1.00f : f; }
+#define MBTREE_PRECISION 0.5f
+
+static void mbtree_reset( x264cu_slicetype_t *s, st_frame_t *f )
+{
+    if( x264cu_lookahead_mbtree_reset( s->la, f->slot ) ) s->failed = 1;
+}
+
+/* macroblock_tree_propagate, slicetype.c:1050-1089 (constant frame rate: every picture lasts s->duration) */
+static void mbtree_propagate( x264cu_slicetype_t *s, st_frame_t **frames, float average_duration, int p0, int p1, int b, int referenced )
+{
+    int slots[LOOKAHEAD_MAX + 4];
+    for( int i = p0; i <= p1; i++ ) slots[i] = frames[i]->slot;
+    float fps_factor = clip_duration( s->duration ) / ( clip_duration( average_duration ) * 256.0f ) * MBTREE_PRECISION;
+    if( x264cu_lookahead_mbtree_propagate( s->la, slots, p0, p1, b, referenced, fps_factor ) ) s->failed = 1;
+}
+
+/* macroblock_tree_finish, slicetype.c:1029-1048 */
+static void mbtree_finish( x264cu_slicetype_t *s, st_frame_t *f, float average_duration, int ref0_distance )
+{
+    int fps_factor = round( clip_duration( average_duration ) / clip_duration( s->duration ) * 256 / MBTREE_PRECISION );
+    float strength = 5.0f * ( 1.0f - s->qcompress );
+    if( x264cu_lookahead_mbtree_finish( s->la, f->slot, fps_factor, ref0_distance, strength ) ) s->failed = 1;
+}
+
+/* macroblock_tree, slicetype.c:1091-1184: the cost requests (they matter for later memoised costs, slicetype.c:629-642) and the
+ * propagation itself on the device.  Every picture carries the same duration here (constant frame rate); the reference reads
+ * frame->f_duration, which x264_slicetype_decide only assigns when a picture is decided (slicetype.c:1769) -- pictures still
+ * waiting in the lookahead carry whatever their recycled x264_frame_t held, i.e. the same value once the frame pool has been
+ * through one cycle, zero (clamped to 0.01 s) before. */
+static void macroblock_tree( x264cu_slicetype_t *s, st_frame_t **frames, int num_frames, int b_intra )
 {
     int idx = !b_intra;
     int last_nonb, cur_nonb = 1, bframes = 0;
     int i = num_frames;
+    float total_duration = 0.0;
+    for( int j = 0; j <= num_frames; j++ )
+        total_duration += s->duration;
+    float average_duration = total_duration / ( num_frames + 1 );
     if( b_intra )
         frame_cost( s, frames, 0, 0, 0 );
     while( i > 0 && IS_B( frames[i]->i_type ) ) i--;
     last_nonb = i;
     if( !s->p.rc_lookahead )
     {
-        if( b_intra ) return;
+        if( b_intra )
+        {   /* i_propagate_cost = 0, f_qp_offset = f_qp_offset_aq */
+            mbtree_reset( s, frames[0] );
+            if( x264cu_lookahead_mbtree_finish( s->la, frames[0]->slot, 0, 0, 0.0f ) ) s->failed = 1;
+            return;
+        }
+        if( x264cu_lookahead_mbtree_swap( s->la, frames[last_nonb]->slot, frames[0]->slot ) ) s->failed = 1;
+        mbtree_reset( s, frames[0] );
     }
-    else if( last_nonb < idx )
-        return;
+    else
+    {
+        if( last_nonb < idx )
+            return;
+        mbtree_reset( s, frames[last_nonb] );
+    }
     while( i-- > idx )
     {
         cur_nonb = i;
@@ -248,30 +294,45 @@ static void mbtree_requests( x264cu_slicetype_t *s, st_frame_t **frames, int num
         if( cur_nonb < idx )
             break;
         frame_cost( s, frames, cur_nonb, last_nonb, last_nonb );
+        mbtree_reset( s, frames[cur_nonb] );
         bframes = last_nonb - cur_nonb - 1;
         if( s->p.b_pyramid && bframes > 1 )
         {
             int middle = ( bframes + 1 ) / 2 + cur_nonb;
             frame_cost( s, frames, cur_nonb, last_nonb, middle );
+            mbtree_reset( s, frames[middle] );
             while( i > cur_nonb )
             {
                 int p0 = i > middle ? middle : cur_nonb;
                 int p1 = i < middle ? middle : last_nonb;
                 if( i != middle )
+                {
                     frame_cost( s, frames, p0, p1, i );
+                    mbtree_propagate( s, frames, average_duration, p0, p1, i, 0 );
+                }
                 i--;
             }
+            mbtree_propagate( s, frames, average_duration, cur_nonb, last_nonb, middle, 1 );
         }
         else
             while( i > cur_nonb )
             {
                 frame_cost( s, frames, cur_nonb, last_nonb, i );
+                mbtree_propagate( s, frames, average_duration, cur_nonb, last_nonb, i, 0 );
                 i--;
             }
+        mbtree_propagate( s, frames, average_duration, cur_nonb, last_nonb, last_nonb, 1 );
         last_nonb = cur_nonb;
     }
     if( !s->p.rc_lookahead )
+    {
         frame_cost( s, frames, 0, last_nonb, last_nonb );
+        mbtree_propagate( s, frames, average_duration, 0, last_nonb, last_nonb, 1 );
+        if( x264cu_lookahead_mbtree_swap( s->la, frames[last_nonb]->slot, frames[0]->slot ) ) s->failed = 1;
+    }
+    mbtree_finish( s, frames[last_nonb], average_duration, last_nonb );
+    if( s->p.b_pyramid && bframes > 1 )          /* vbv lookahead is not part of this backend (rejected at open) */
+        mbtree_finish( s, frames[last_nonb + ( bframes + 1 ) / 2], average_duration, 0 );
 }
 
 /* x264_slicetype_analyse, slicetype.c:1473-1743 */
@@ -293,7 +354,7 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
     if( !framecnt )
     {
         if( s->p.la.mb_tree )
-            mbtree_requests( s, frames, 0, keyframe );
+            macroblock_tree( s, frames, 0, keyframe );
         return;
     }
     keyint_limit = s->p.keyint_max - frames[0]->i_frame + s->i_last_keyframe - 1;
@@ -422,7 +483,7 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
     }
 
     if( s->p.la.mb_tree )
-        mbtree_requests( s, frames, num_frames < s->p.keyint_max ? num_frames : s->p.keyint_max, keyframe );
+        macroblock_tree( s, frames, num_frames < s->p.keyint_max ? num_frames : s->p.keyint_max, keyframe );
 
     /* Enforce keyframe limit. */
     {
@@ -606,6 +667,11 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
     s->p.la.n_slots = s->n_slots;
     s->mb_w = ( p->la.width + 15 ) >> 4;
     s->mb_h = ( p->la.height + 15 ) >> 4;
+    {   /* slicetype.c:1769-1771 with i_duration = 2 (progressive), vui.i_num_units_in_tick = fps_den, i_time_scale = 2*fps_num */
+        int num = p->fps_num > 0 ? p->fps_num : 25, den = p->fps_den > 0 ? p->fps_den : 1;
+        s->duration = (double)2 * den / ( 2.0 * num );
+        s->qcompress = p->qcompress > 0 ? p->qcompress : 0.6f;
+    }
     s->prefetch = 1;
     /* measured at 4K (B200): 8/4 -> 1000 pictures/s, 16/8 -> 1260, 24/12 -> 1410, 32/16 -> 1490: a launch needs several
      * dozen independent wavefronts to fill the 148 SMs */
@@ -776,6 +842,14 @@ int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame )
     for( int i = 0; i < s->n_next; i++ ) if( s->next[i]->i_frame == frame ) return s->next[i]->slot;
     for( int i = 0; i < s->n_current; i++ ) if( s->current[i]->i_frame == frame ) return s->current[i]->slot;
     return -1;
+}
+
+int x264cu_slicetype_get_qp_offset( x264cu_slicetype_t *s, int frame, float *h_qp_offset )
+{
+    if( !s || !h_qp_offset ) return -1;
+    int slot = x264cu_slicetype_slot_of( s, frame );
+    if( slot < 0 ) return -1;
+    return x264cu_lookahead_get_qp_offset( s->la, slot, h_qp_offset );
 }
 
 long x264cu_slicetype_cost_requests( x264cu_slicetype_t *s ) { return s ? s->requests : 0; }
