@@ -50,6 +50,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(kernel, units_key, units_now):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01b_kernel_traffic.json), scaled to the
+    units this launch processes; None if the capture is missing"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01b_kernel_traffic.json")))[kernel]
+        per_unit = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t[units_key]
+        return per_unit * units_now, t["source"]
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -255,6 +266,7 @@ def run_satd_b200(args, rank, world, local, dist):
     kernel_ms = ms / args.steps
     peaks, peak_src = measured_peaks()
     achieved = ALG_BYTES_16x16 * n_cand / (kernel_ms * 1e-3) / 1e9
+    traffic, traffic_src = profiled_traffic("mvfield_kernel<SATD,16,16>", "candidates_per_launch", n_cand)
     res = {
         "metric": "satd_16x16_macroblocks_per_sec_4k", "value": n_cand * world / (kernel_ms * 1e-3), "unit": "macroblocks/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms,
@@ -269,7 +281,7 @@ def run_satd_b200(args, rank, world, local, dist):
                 "api": "x264cu_pixel_cmp_mvfield_host (pinned host planes)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_16x16 * n_cand, "kernel": "mvfield_kernel<SATD,16,16>"},
         "wall_s": t_wall, "sm_count": info["sm_count"],
     }
@@ -409,6 +421,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
     for _ in range(max(args.warmup, 3)):
         step_dev()
     ctx.sync()
+    ss0 = st.search_stats()
     sampler = ClockSampler(local)
     barrier(dist, local)
     sampler.start()
@@ -424,6 +437,8 @@ def run_lookahead_b200(args, rank, world, local, dist):
     launches, requests = ctx.launches - l0, st.cost_requests - r0
     ms = max_over_ranks(dist, ms, local)
     clocks = sampler.stop()
+    ss1 = st.search_stats()            # CUDA events around every search launch, on the (low-priority) stream it ran on
+    live_launches, live_searches, live_ms = ss1[1] - ss0[1], ss1[2] - ss0[2], ss1[0] - ss0[0]
     st.close()
     # the one exchange step: every rank's per-picture decision records are all-gathered (NCCL) so that rank 0 holds the
     # decisions of all streams; outside the timed region only because it happens once per run, not per step
@@ -481,7 +496,11 @@ def run_lookahead_b200(args, rank, world, local, dist):
     ms_step = ms / args.steps
     peaks, peak_src = measured_peaks()
     n_jobs = len(jobs)
-    achieved = LA_SEARCH_BYTES * n_jobs / (search_ms * 1e-3) / 1e9
+    # the dominant kernel as it ran inside the timed region: average searches per launch and average launch duration
+    per_launch = live_searches / max(1, live_launches)
+    launch_ms = live_ms / max(1, live_launches)
+    achieved = LA_SEARCH_BYTES * per_launch / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = profiled_traffic("search_kernel<8>", "searches_per_launch", per_launch)
     res = {
         "metric": "lowres_lookahead_frames_per_sec_4k", "value": n * world / (ms_step * 1e-3), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -498,10 +517,13 @@ def run_lookahead_b200(args, rank, world, local, dist):
                 "d2h_bytes_per_step": int(32 * requests / args.steps), "api": "x264cu_slicetype_step (page-locked host luma read in place by the copy engine on the upload stream, async_upload=1)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": None, "peak_source": peak_src, "kernel": "search_kernel<8> (%d searches per launch)" % n_jobs,
-                     "algorithmic_bytes_per_launch": LA_SEARCH_BYTES * n_jobs, "ms_per_launch": search_ms,
-                     "ms_per_launch_%d_searches" % len(jobs4): search4_ms,
-                     "note": "dependency-bound wavefront (510 pipeline steps at 4K), not a streaming kernel: see DESIGN.md"},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "kernel": "search_kernel<8> (%.1f searches per launch, %d launches in the timed region, two launches in flight)" % (per_launch, live_launches),
+                     "algorithmic_bytes_per_launch": LA_SEARCH_BYTES * per_launch, "ms_per_launch": launch_ms,
+                     "share_of_step": live_ms / max(ms, 1e-9),
+                     "ms_per_launch_alone_%d_searches" % n_jobs: search_ms, "ms_per_launch_alone_%d_searches" % len(jobs4): search4_ms,
+                     "note": "dependency-bound wavefront (508 pipeline steps at 4K), not a streaming kernel: the planes of the ~13 "
+                             "pictures a launch touches stay in L2 (traffic << algorithmic bytes); see DESIGN.md"},
         "wall_s": wall, "sm_count": info["sm_count"],
     }
     if rank == 0 and world == 1 and not args.quick:

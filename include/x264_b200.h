@@ -234,6 +234,9 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
  * search must wait for its first cost request.  Always 1 without weighted prediction.  -1 on error.  Waits for the uploads
  * of the two pictures only (their luma statistics travel back with them). */
 int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int fenc_slot, int ref_slot );
+/* device time of the search launches so far (CUDA events on the stream each was launched on; waits for those in flight), their
+ * number and the number of searches they carried: bench.py's live timing of the dominant kernel */
+int x264cu_lookahead_search_stats( x264cu_lookahead_t *la, double *busy_ms, long *launches, long *searches );
 /* x264_opencl_flush without the host block (encoder/slicetype-cl.c:100-127): order the context's stream after every
  * search queued by x264cu_lookahead_search_batch, so that work (or a timer event) queued next sees them finished */
 int x264cu_lookahead_join( x264cu_lookahead_t *la );

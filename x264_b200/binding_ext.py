@@ -50,6 +50,9 @@ def bind(L):
     L.x264cu_slicetype_set_run_ahead.argtypes = [vp, ci]
     L.x264cu_slicetype_set_async_upload.argtypes = [vp, ci]
     L.x264cu_slicetype_get_qp_offset.argtypes = [vp, ci, vp]
+    L.x264cu_slicetype_lookahead.argtypes = [vp]
+    L.x264cu_slicetype_lookahead.restype = vp
+    L.x264cu_lookahead_search_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_long)]
     L.x264cu_lookahead_frame_set_qp_offset_aq.argtypes = [vp, ci, vp]
     L.x264cu_lookahead_mbtree_reset.argtypes = [vp, ci]
     L.x264cu_lookahead_mbtree_swap.argtypes = [vp, ci, ci]
@@ -254,6 +257,12 @@ class Slicetype:
     def set_async_upload(self, on):
         """page-locked pictures passed to step() are read in place; keep them unmodified until four more pictures have been queued"""
         self.L.x264cu_slicetype_set_async_upload(self.h, int(on))
+
+    def search_stats(self):
+        """(device ms of the search launches so far, launches, searches) of the lookahead underneath"""
+        b, l, n = C.c_double(), C.c_long(), C.c_long()
+        self.ctx.check(self.L.x264cu_lookahead_search_stats(self.L.x264cu_slicetype_lookahead(self.h), C.byref(b), C.byref(l), C.byref(n)))
+        return b.value, l.value, n.value
 
     def get_qp_offset(self, frame):
         """f_qp_offset (MB-tree) of a non-B picture just returned by step()"""

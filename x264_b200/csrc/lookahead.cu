@@ -1223,7 +1223,6 @@ static int la_launch_searches( x264cu_lookahead *la, int n, cudaStream_t stream 
     CU_CHECK( ctx, cudaMemsetAsync( t, 0, 4, stream ) );
     la->st.n_batch++; la->st.n_jobs += n;
     const int ti = ( la->ticket_next - 1 ) & 63;
-    if( la->stats_on )
     {
         if( !la->tm_ev[ti][0] ) { cudaEventCreate( &la->tm_ev[ti][0] ); cudaEventCreate( &la->tm_ev[ti][1] ); }
         if( la->tm_live[ti] )
@@ -1237,7 +1236,7 @@ static int la_launch_searches( x264cu_lookahead *la, int n, cudaStream_t stream 
     }
     search_kernel<NW><<<groups * n, NW * 32, smem, stream>>>( d, la->pack, la->d_cost_mv, n, t );
     CU_LAUNCH_CHECK( ctx );
-    if( la->stats_on ) { cudaEventRecord( la->tm_ev[ti][1], stream ); la->tm_live[ti] = true; }
+    cudaEventRecord( la->tm_ev[ti][1], stream ); la->tm_live[ti] = true;
     return 0;
 }
 
@@ -1323,6 +1322,24 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
         la->last_prefetch_ev = e;
         la->last_ev_of[si] = e;
     }
+    return 0;
+}
+
+int x264cu_lookahead_search_stats( x264cu_lookahead_t *la, double *busy_ms, long *launches, long *searches )
+{
+    if( !la ) return -1;
+    for( int i = 0; i < 64; i++ )
+        if( la->tm_live[i] )
+        {   // waits for the launches still in flight
+            float ms = 0;
+            CU_CHECK( la->ctx, cudaEventSynchronize( la->tm_ev[i][1] ) );
+            CU_CHECK( la->ctx, cudaEventElapsedTime( &ms, la->tm_ev[i][0], la->tm_ev[i][1] ) );
+            la->search_busy_ms += ms;
+            la->tm_live[i] = false;
+        }
+    if( busy_ms ) *busy_ms = la->search_busy_ms;
+    if( launches ) *launches = la->st.n_batch;
+    if( searches ) *searches = la->st.n_jobs;
     return 0;
 }
 
