@@ -43,7 +43,7 @@ enum x264cu_metric_e                       /* members of x264_pixel_function_t, 
     X264CU_SA8D = 3                        /* pixf.sa8d[]  common/pixel.c:334-381 (16x16 and 8x8 only) */
 };
 
-enum x264cu_me_e { X264CU_ME_DIA = 0, X264CU_ME_HEX = 1, X264CU_ME_UMH = 2 };   /* x264.h X264_ME_* */
+enum x264cu_me_e { X264CU_ME_DIA = 0, X264CU_ME_HEX = 1, X264CU_ME_UMH = 2, X264CU_ME_ESA = 3 };   /* x264.h X264_ME_* */
 
 typedef struct x264cu_ctx x264cu_ctx_t;
 
@@ -343,7 +343,8 @@ long x264cu_slicetype_cost_requests( x264cu_slicetype_t *st );
 
 /* ------------------------------------------------------------------------------------------------
  * Batched twin of x264_me_search_ref + refine_subpel (encoder/me.h:58-60, encoder/me.c:182-992): one job = one call.
- * Luma only (no chroma ME), DIA / HEX / UMH, every partition size and sub-pel level.  One warp runs one search with the
+ * Luma only (no chroma ME), DIA / HEX / UMH / ESA (exhaustive, me.c:618-771; TESA is not built), every partition size and
+ * sub-pel level.  One warp runs one search with the
  * reference's control flow; jobs are independent (their predictors are inputs), which is how the full-resolution
  * motion-estimation stage is replayed from recorded x264_me_t inputs (BASELINE config 3).
  * ---------------------------------------------------------------------------------------------- */

@@ -16,7 +16,7 @@ extern "C" {
 enum { ORC_PIXEL_16x16, ORC_PIXEL_16x8, ORC_PIXEL_8x16, ORC_PIXEL_8x8, ORC_PIXEL_8x4, ORC_PIXEL_4x8,
        ORC_PIXEL_4x4, ORC_PIXEL_4x16, ORC_PIXEL_NB };
 enum { ORC_SAD, ORC_SSD, ORC_SATD, ORC_SA8D };
-enum { ORC_ME_DIA, ORC_ME_HEX, ORC_ME_UMH };           /* x264.h X264_ME_DIA/HEX/UMH */
+enum { ORC_ME_DIA, ORC_ME_HEX, ORC_ME_UMH, ORC_ME_ESA };   /* x264.h X264_ME_DIA/HEX/UMH/ESA */
 #define ORC_COST_MAX (1<<28)                             /* encoder/me.h:30 */
 #define ORC_PAD 32                                       /* common/frame.h:32-33 PADH/PADV */
 

@@ -24,6 +24,7 @@ typedef struct
 
 static inline int clip3( int v, int lo, int hi ) { return v < lo ? lo : v > hi ? hi : v; }
 static inline int imin( int a, int b ) { return a < b ? a : b; }
+static inline int imax( int a, int b ) { return a > b ? a : b; }
 static inline uint32_t pack_mv( int x, int y ) { return ( (uint32_t)x & 0xFFFF ) + ( (uint32_t)y << 16 ); }  /* macroblock.h:395 */
 #define FPEL(v) (((v)+2)>>2)                                                                                  /* me.c:178 */
 
@@ -277,6 +278,22 @@ void orc_me_search_ref( const orc_me_ctx_t *c, orc_me_t *m, const int16_t (*mvc)
     case ORC_ME_HEX:
         hex_search( s, me_range );
         break;
+    case ORC_ME_ESA:                                                    /* me.c:618-771, the "just ADS and SAD" branch */
+    {
+        /* The reference scans the window row by row; per row the ADS prefilter (pixf.ads on the integral image, me.c:760) drops
+         * positions whose lower bound |sum(fenc) - sum(ref)| + mv cost already reaches the best cost, the rest go through
+         * COST_MV_X3_ABS / COST_MV in ascending x.  sum|a-b| >= |sum a - sum b|, so a dropped position can never be strictly
+         * better: the result is the first strictly smaller cost in raster order over the whole window -- which is what is
+         * restated here (the ADS arithmetic itself is a CPU-side accelerator, not part of the result).  The window's width is
+         * rounded up to a multiple of 4 like the reference's, which can reach up to 3 positions past mv_x_max. */
+        const int min_x = imax( s->bmx - me_range, s->x_min ), min_y = imax( s->bmy - me_range, s->y_min );
+        const int max_x = imin( s->bmx + me_range, s->x_max ), max_y = imin( s->bmy + me_range, s->y_max );
+        const int width = ( max_x - min_x + 3 ) & ~3;
+        for( int my = min_y; my <= max_y; my++ )
+            for( int mx = min_x; mx < min_x + width; mx++ )
+                try_fpel( s, mx, my );
+        break;
+    }
     case ORC_ME_UMH:                                                    /* me.c:422-616 */
     {
         static const uint8_t pixel_size_shift[7] = { 0, 1, 1, 2, 3, 3, 4 };

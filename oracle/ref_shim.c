@@ -258,10 +258,9 @@ typedef struct
 
 /* Drives the reference's x264_me_search_ref (encoder/me.c:182) on caller-supplied planes.
  * fref[0..3] = F,H,V,C plane pointers at the block origin, fref_w = weighted full-pel plane (or fref[0]). */
-XREF_API void xref_me_search( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
-                              uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride )
+static void me_search_common( x264_t *h, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
+                              uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride, uint16_t *integral )
 {
-    x264_t *h = hv;
     tables_init();
     ALIGNED_ARRAY_64( pixel, fenc_buf,[16*16] );
     int bw = x264_pixel_size[a->i_pixel].w, bh = x264_pixel_size[a->i_pixel].h;
@@ -278,6 +277,7 @@ XREF_API void xref_me_search( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr
     m.weight = &wt;
     m.p_fref[0] = f0; m.p_fref[1] = f1; m.p_fref[2] = f2; m.p_fref[3] = f3;
     m.p_fref_w = fref_w;
+    m.integral = integral;
     m.p_fenc[0] = fenc_buf;
     m.i_stride[0] = stride;
     m.mvp[0] = a->mvp[0]; m.mvp[1] = a->mvp[1];
@@ -301,6 +301,52 @@ XREF_API void xref_me_search( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr
     a->mv[0] = m.mv[0]; a->mv[1] = m.mv[1];
     a->cost = m.cost; a->cost_mv = m.cost_mv;
     a->thresh_out = thresh;
+}
+
+XREF_API void xref_me_search( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
+                              uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride )
+{
+    me_search_common( hv, a, fenc, fenc_stride, f0, f1, f2, f3, fref_w, stride, NULL );
+}
+
+/* ESA / TESA read the reference frame's integral image (me.c:636-760), which x264_frame_filter builds when the encoder was
+ * opened with me=esa|tesa: here the search runs against a reference frame the reference builds itself from ref_luma
+ * (picture-sized, mod 16); (bx, by) = position of the block.  The frame is kept until ref_luma changes. */
+XREF_API int xref_me_search_frame( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
+                                   const uint8_t *ref_luma, intptr_t ref_stride, int bx, int by )
+{
+    x264_t *h = hv;
+    static x264_frame_t *f;
+    static const uint8_t *f_src;
+    static x264_t *f_h;
+    if( !f || f_src != ref_luma || f_h != h )
+    {
+        if( f && f_h == h ) x264_frame_push_unused( h, f );
+        f = x264_frame_pop_unused( h, 1 );
+        if( !f ) return -1;
+        f_src = ref_luma; f_h = h;
+        int W = h->mb.i_mb_width*16, H = h->mb.i_mb_height*16;
+        for( int y = 0; y < H; y++ )
+            memcpy( f->plane[0] + y*f->i_stride[0], ref_luma + y*ref_stride, W );
+        f->b_kept_as_ref = 1;
+        h->i_threadslice_start = 0;
+        h->i_threadslice_end = h->mb.i_mb_height;
+        for( int mb_y = 0; mb_y < h->mb.i_mb_height; mb_y++ )
+        {
+            int end = mb_y == h->mb.i_mb_height - 1;
+            x264_frame_expand_border( h, f, mb_y );
+            x264_frame_filter( h, f, mb_y, end );
+            x264_frame_expand_border_filtered( h, f, mb_y, end );
+        }
+    }
+    if( !f->integral ) return -2;                       /* the encoder was not opened with me=esa */
+    intptr_t st = f->i_stride[0], off = by*st + bx;
+    x264_frame_t *save = h->fenc;
+    h->fenc = f;                                        /* me.c:645 reads h->fenc->i_lines[0] for the 4x4 plane of the integral */
+    me_search_common( h, a, fenc, fenc_stride, f->filtered[0][0] + off, f->filtered[0][1] + off, f->filtered[0][2] + off,
+                      f->filtered[0][3] + off, f->filtered[0][0] + off, st, f->integral + off );
+    h->fenc = save;
+    return 0;
 }
 
 XREF_API void xref_cost_mv_table_qp( void *hv, int qp, uint16_t *out, int len )

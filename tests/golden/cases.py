@@ -62,6 +62,7 @@ ME_W, ME_H, ME_MV_RANGE = 112, 96, 64
 ME_GROUPS = [  # (method, subpel_refine, me_range, mbcmp_is_satd, weight)
     (0, 2, 16, 1, (0, 0, 0, 0)), (0, 5, 8, 1, (0, 0, 0, 0)), (1, 1, 16, 0, (0, 0, 0, 0)), (1, 4, 16, 1, (0, 0, 0, 0)),
     (1, 7, 16, 1, (1, 70, 6, -3)), (2, 3, 24, 1, (0, 0, 0, 0)), (2, 9, 32, 1, (0, 0, 0, 0)), (2, 6, 16, 1, (1, 55, 6, 4)),
+    (3, 2, 8, 1, (0, 0, 0, 0)), (3, 7, 16, 1, (0, 0, 0, 0)),      # ESA (reference side: xref_me_search_frame, its own integral image)
 ]
 ME_JOBS = 40
 

@@ -137,8 +137,11 @@ def run_me(backend, gi, ctx=None):
     n = 2 * 4 * G.ME_MV_RANGE
     if backend == "ref":
         r = ref()
-        hnd = r.xref_open(G.ME_W, G.ME_H, b"medium", b"subme=7" if satd else b"subme=1", 0)
+        esa = method == 3
+        r.xref_me_search_frame.argtypes = [C.c_void_p, C.POINTER(XrefMeArgs), C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int]
+        hnd = r.xref_open(G.ME_W, G.ME_H, b"medium", (b"subme=7" if satd else b"subme=1") + (b":me=esa:merange=32:partitions=all" if esa else b""), 0)
         assert hnd
+        ref_l = np.ascontiguousarray(ref_l)
         for k, j in enumerate(jobs):
             off = planes[0].off(j["bx"], j["by"])
             a = XrefMeArgs()
@@ -150,8 +153,11 @@ def run_me(backend, gi, ctx=None):
                 a.mvc[i][0], a.mvc[i][1] = int(j["mvc"][i][0]), int(j["mvc"][i][1])
             a.wt_en, a.wt_scale, a.wt_denom, a.wt_offset = wt
             a.use_thresh, a.halfpel_thresh = int(j["use_thresh"]), j["thresh"]
-            r.xref_me_search(hnd, C.byref(a), ptr(fenc.buf, fenc.off(j["bx"], j["by"])), st,
-                             *[ptr(p.buf, off) for p in planes], ptr(wplane.buf, off), st)
+            if esa:     # the reference builds the frame (and its integral image) itself from the same luma
+                assert r.xref_me_search_frame(hnd, C.byref(a), ptr(fenc.buf, fenc.off(j["bx"], j["by"])), st, ptr(ref_l), G.ME_W, j["bx"], j["by"]) == 0
+            else:
+                r.xref_me_search(hnd, C.byref(a), ptr(fenc.buf, fenc.off(j["bx"], j["by"])), st,
+                                 *[ptr(p.buf, off) for p in planes], ptr(wplane.buf, off), st)
             out[k] = (a.mv[0], a.mv[1], a.cost, a.thresh_out if j["use_thresh"] else -1)
         r.xref_close(hnd)
     elif backend == "oracle":

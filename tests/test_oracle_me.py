@@ -110,3 +110,68 @@ def test_me_search_matches_reference(subme_param, kind):
             run_case(hnd, subme_param, tab, n, kind, rng, 60)
     finally:
         r.xref_close(hnd)
+
+
+@pytest.mark.parametrize("kind", ["texture", "flat", "noise"])
+def test_esa_matches_reference(kind):
+    """exhaustive search (me.c:618-771, the ADS + SAD branch): the reference runs on a frame it builds itself (its integral
+    image comes from x264_frame_filter); every partition size, three ranges, sub-pel levels 0 / 2 / 7"""
+    _libs._bind_me()
+    o, r = oracle(), ref()
+    r.xref_me_search_frame.argtypes = [C.c_void_p, C.POINTER(XrefMeArgs), C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int]
+    hnd = r.xref_open(W, H, b"medium", b"me=esa:merange=32:subme=7:partitions=all", 0)
+    assert hnd
+    try:
+        n = 2 * 4 * r.xref_param(hnd, b"mvrange")
+        tab = np.zeros(2 * n + 1, np.uint16)
+        r.xref_cost_mv_table_qp(hnd, 12, tab, n)
+        rng = np.random.default_rng(77 + len(kind))
+        for rep in range(3):
+            fenc_l, ref_l = _content(kind, rng)
+            ref_l = np.ascontiguousarray(ref_l)
+            planes = make_ref_planes(ref_l)
+            st = planes[0].stride
+            fenc = PaddedPlane(W, H, stride=st)
+            fenc.inner()[:] = fenc_l
+            for _ in range(40):
+                ip = int(rng.integers(0, 7))
+                bw, bh = PIXEL_W[ip], PIXEL_H[ip]
+                bx = int(rng.integers(0, (W - bw) // 4 + 1)) * 4
+                by = int(rng.integers(0, (H - bh) // 4 + 1)) * 4
+                subpel = int(rng.choice([0, 2, 7]))
+                me_range = int(rng.choice([4, 8, 16]))
+                mvr = 4 * 64
+                lim_min = [max(4 * (-bx - 24), -mvr), max(4 * (-by - 24), -mvr)]
+                lim_max = [min(4 * (W - bx - bw + 24), mvr - 1), min(4 * (H - by - bh + 24), mvr - 1)]
+                i_mvc = int(rng.integers(0, 5))
+                mvp = rng.integers(-12, 13, 2)
+                mvcs = rng.integers(-12, 13, (16, 2))
+                a = XrefMeArgs()
+                a.i_pixel, a.me_method, a.subpel_refine, a.me_range, a.qp = ip, 3, subpel, me_range, 12
+                for i in range(2):
+                    a.mv_min_spel[i], a.mv_max_spel[i], a.mvp[i] = lim_min[i], lim_max[i], int(mvp[i])
+                a.i_mvc = i_mvc
+                for i in range(16):
+                    a.mvc[i][0], a.mvc[i][1] = int(mvcs[i][0]), int(mvcs[i][1])
+                assert r.xref_me_search_frame(hnd, C.byref(a), ptr(fenc.buf, fenc.off(bx, by)), st, ptr(ref_l), W, bx, by) == 0
+                c = OrcMeCtx()
+                c.me_method, c.subpel_refine, c.me_range, c.mbcmp_is_satd = 3, subpel, me_range, 1
+                for i in range(2):
+                    c.mv_min_spel[i], c.mv_max_spel[i] = lim_min[i], lim_max[i]
+                    c.mv_limit_fpel[0][i], c.mv_limit_fpel[1][i] = lim_min[i] >> 2, lim_max[i] >> 2
+                off = planes[0].off(bx, by)
+                m = OrcMe()
+                m.i_pixel = ip
+                m.p_cost_mv = tab.ctypes.data + 2 * n
+                for i in range(4):
+                    m.p_fref[i] = planes[i].buf.ctypes.data + off
+                m.p_fref_w = planes[0].buf.ctypes.data + off
+                m.p_fenc = fenc.buf.ctypes.data + fenc.off(bx, by)
+                m.fenc_stride, m.stride = st, st
+                m.weight = OrcWeight(0, 0, 0, 0)
+                m.mvp[0], m.mvp[1] = int(mvp[0]), int(mvp[1])
+                mvc_arr = np.ascontiguousarray(mvcs.astype(np.int16))
+                o.orc_me_search_ref(C.byref(c), C.byref(m), ptr(mvc_arr), i_mvc, None)
+                assert (m.mv[0], m.mv[1], m.cost) == (a.mv[0], a.mv[1], a.cost), (kind, ip, subpel, me_range, tuple(mvp), i_mvc, bx, by)
+    finally:
+        r.xref_close(hnd)

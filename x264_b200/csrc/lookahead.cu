@@ -923,8 +923,8 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     *out = nullptr;
     if( p->width < 16 || p->height < 16 ) return x264cu_fail( ctx, "lookahead_open: picture %dx%d too small", p->width, p->height );
     if( p->bframes < 0 || p->bframes > LA_MAX_B ) return x264cu_fail( ctx, "lookahead_open: bframes %d out of range", p->bframes );
-    if( p->me_method < X264CU_ME_DIA || p->me_method > X264CU_ME_UMH )
-        return x264cu_fail( ctx, "lookahead_open: me_method %d not supported (esa/tesa are outside this backend)", p->me_method );
+    if( p->me_method < X264CU_ME_DIA || p->me_method > 4 )          // esa / tesa included: the lookahead never goes beyond hex (slicetype.c:50)
+        return x264cu_fail( ctx, "lookahead_open: me_method %d out of range", p->me_method );
     if( p->n_slots < 2 ) return x264cu_fail( ctx, "lookahead_open: need at least 2 frame slots" );
     if( p->mv_range < 32 || p->mv_range > 4096 ) return x264cu_fail( ctx, "lookahead_open: mv_range %d out of range", p->mv_range );
     x264cu_lookahead *la = new x264cu_lookahead;

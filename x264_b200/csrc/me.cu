@@ -51,8 +51,10 @@ extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params
 {
     if( !ctx || !p ) return -1;
     if( n <= 0 ) return 0;
-    if( p->me_method < X264CU_ME_DIA || p->me_method > X264CU_ME_UMH )
-        return x264cu_fail( ctx, "me_search_batch: method %d not supported (esa / tesa are outside this backend)", p->me_method );
+    if( p->me_method < X264CU_ME_DIA || p->me_method > X264CU_ME_ESA )
+        return x264cu_fail( ctx, "me_search_batch: method %d not supported (tesa is outside this backend)", p->me_method );
+    if( p->me_method == X264CU_ME_ESA && p->me_range > 120 )
+        return x264cu_fail( ctx, "me_search_batch: esa me_range %d > 120", p->me_range );
     if( p->subpel_refine < 0 || p->subpel_refine > 11 || p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 )
         return x264cu_fail( ctx, "me_search_batch: bad parameters" );
     // cost_mv[lambda] (analyse.c:143-157, :179-188), same float expressions as the reference; kept in this context's scratch

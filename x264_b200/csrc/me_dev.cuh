@@ -318,6 +318,19 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
     }
     else if( g.me_method == X264CU_ME_HEX )
         m.hex_refine( me_range );
+    else if( g.me_method == X264CU_ME_ESA )
+    {   // me.c:618-771, the "just ADS and SAD" branch.  The reference's ADS prefilter (pixf.ads over the integral image) only
+        // drops positions whose lower bound |sum(fenc) - sum(ref)| + mv cost already reaches the best cost: sum|a-b| >= |sum a -
+        // sum b|, so none of them could be strictly better.  The result is therefore the first strictly smaller cost in raster
+        // order over the window, which the warp computes by brute force, S positions per round, row after row (32/L SADs per
+        // round: no integral images, no prefilter).  The window's width is rounded up to a multiple of 4 as in the reference
+        // (up to 3 positions past mv_x_max, never range-checked).
+        const int min_x = max( m.bmx - me_range, m.x_min ), min_y = max( m.bmy - me_range, m.y_min );
+        const int max_x = min( m.bmx + me_range, m.x_max ), max_y = min( m.bmy + me_range, m.y_max );
+        const int width = ( max_x - min_x + 3 ) & ~3;
+        for( int my = min_y; my <= max_y; my++ )
+            m.try_list_v( width, min_x, my, []( int i ) { return i; }, []( int ) { return 0; }, []( int, int ) { return true; } );
+    }
     else
     {   // UMH, me.c:422-616
         const int shift = i_pixel == 0 ? 0 : i_pixel <= 2 ? 1 : i_pixel == 3 ? 2 : i_pixel <= 5 ? 3 : 4;   // pixel_size_shift
