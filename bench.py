@@ -458,6 +458,46 @@ def run_lookahead_b200(args, rank, world, local, dist):
         allrec = xd.unpack_records(xd.all_gather_records(dist, rec, device=torch.device("cuda", local)))
         gathered_streams = len(allrec)
 
+    # ---- ONE stream sharded over the GPUs: every rank is fed rank 0's pictures, searches split by picture, one
+    # all-gather of search results per prefetch group; reported beside the weak-scaling value, not instead of it ----------
+    sharded = None
+    if dist is not None:
+        import torch
+        from x264_b200 import dist as xd
+        same_frames = make_la_frames(2160, n, lambda b: ctx.malloc_host(b))
+        ctx.h2d(d_frames, same_frames)
+        st = make_st()
+        ex = xd.ShardExchange(dist, device=torch.device("cuda", local))
+        st.set_shard(rank, world, ex)
+        sh_types = []
+
+        def step_sh():
+            for i in range(n):
+                fr, ty = st.step_device(d_frames + i * LA_W * LA_H, stride)
+                if fr >= 0:
+                    sh_types.append((fr, ty))
+
+        for _ in range(3):
+            step_sh()
+        ctx.sync()
+        barrier(dist, local)
+        sh_steps = max(1, min(args.steps, 10))
+        ctx.timer_start()
+        for _ in range(sh_steps):
+            step_sh()
+        sh_ms = max_over_ranks(dist, ctx.timer_stop(), local)
+        ctx.sync()
+        st.close()
+        # every rank must have taken the same decisions
+        sig = torch.tensor([hash(tuple(sh_types)) & 0x7fffffffffff], dtype=torch.int64, device=torch.device("cuda", local))
+        sigs = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        sharded = {"value": n * sh_steps / (sh_ms * 1e-3), "unit": "frames/s", "steps": sh_steps,
+                   "note": "ONE 4K stream over %d GPUs: searches split by picture, decisions replicated, one NCCL all-gather of search "
+                           "results per 12-picture group (%.1f MB gathered per exchange, %d exchanges)" % (world, ex.bytes / max(ex.calls, 1) / 1e6, ex.calls),
+                   "same_decisions_on_every_rank": bool(all(int(t.item()) == int(sig.item()) for t in sigs))}
+        ctx.h2d(d_frames, frames)
+
     # ---- the search kernel alone: 8 searches (4 distances x 2 lists) of one picture per launch --------
     la = x.Lookahead(ctx, LA_W, LA_H, n_slots=8, **LA_OPTS)
     jobs = [(4, 4 - d, 0, d) for d in range(1, 5)] + [(4 - d, 4, 1, d) for d in range(1, 4)]
@@ -519,7 +559,8 @@ def run_lookahead_b200(args, rank, world, local, dist):
                    "l2": "each picture's 4 lowres planes (9.4 MB) stay L2-resident by design; pictures cycle through %d MB" % (frames.nbytes // 2**20),
                    "cost_requests_per_step": requests / args.steps, "decided_per_step": len(decided) / (args.steps + max(args.warmup, 3)),
                    "scheduling": "searches prefetched on two low-priority streams in groups of 12 pictures (84 searches per launch), decisions run 24 pictures behind the newest one (sync-lookahead twin); uploads on their own stream",
-                   "multi_gpu": "one independent stream per GPU; one NCCL all-gather of decision records (%d streams gathered)" % gathered_streams},
+                   "multi_gpu": "value / e2e: one independent stream per GPU (weak scaling), one NCCL all-gather of decision records (%d streams gathered); "
+                                "sharded_stream: ONE stream over all GPUs" % gathered_streams},
         "clocks": clocks,
         "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
                 "d2h_bytes_per_step": int(32 * requests / args.steps), "api": "x264cu_slicetype_step (page-locked host luma read in place by the copy engine on the upload stream, async_upload=1)"},
@@ -534,6 +575,8 @@ def run_lookahead_b200(args, rank, world, local, dist):
                              "pictures a launch touches stay in L2 (traffic << algorithmic bytes); see DESIGN.md"},
         "wall_s": wall, "sm_count": info["sm_count"],
     }
+    if sharded is not None:
+        res["sharded_stream"] = sharded
     if rank == 0 and world == 1 and not args.quick:
         rate, kind, cores, sample, _ = cpu_lookahead_rate(frames, args.cpu_budget, args.weightp, os.cpu_count() or 1)
         rate1, _, _, sample1, _ = cpu_lookahead_rate(frames, args.cpu_budget / 2, args.weightp, 1)

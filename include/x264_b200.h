@@ -228,6 +228,19 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
  * time does not change any later x264cu_lookahead_frame_cost result.  Already-searched jobs are skipped. */
 int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int *fenc, const int *ref,
                                    const int *list, const int *dist );
+/* ---- one picture stream sharded over several GPUs: a lowres search is a pure function of two pictures, so the
+ * searches of a window can be split between GPUs that all hold the pictures; what has to travel is the result of each search --
+ * lowres_mvs[list][dist-1] and lowres_mv_costs[list][dist-1] of the searched picture, x264cu_lookahead_search_bytes() =
+ * 8 bytes per macroblock -- in ONE all-gather per window.  export packs a locally searched result into d_dst, import installs
+ * a result searched elsewhere (the pair then counts as searched here; the reference-order state of x264cu_lookahead_frame_cost
+ * is untouched); both are enqueued on x264cu_lookahead_exchange_stream(), the stream the caller's collective must run on;
+ * import_done publishes everything imported since the last call to later cost requests. ---- */
+size_t x264cu_lookahead_search_bytes( x264cu_lookahead_t *la );
+void  *x264cu_lookahead_exchange_stream( x264cu_lookahead_t *la );
+int    x264cu_lookahead_export_search( x264cu_lookahead_t *la, int slot, int list, int dist, void *d_dst );
+int    x264cu_lookahead_import_search( x264cu_lookahead_t *la, int slot, int list, int dist, const void *d_src );
+int    x264cu_lookahead_import_done( x264cu_lookahead_t *la );
+
 /* 1 if x264_weights_analyse( fenc, ref ) would leave at its early exit (means and variances of the two pictures agree:
  * no weight, slicetype.c:316-330) -- then the list-0 search of that pair is the same whether it is first requested as a P or
  * as a B cost, and may be run ahead of time with x264cu_lookahead_search_batch.  0 if a weight may be chosen (fade): that
@@ -331,6 +344,15 @@ void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *st, int pictures );
 /* x264cu_lookahead_set_async_upload for the lookahead underneath: page-locked pictures are read in place and must stay
  * unmodified until four more pictures have been queued */
 void x264cu_slicetype_set_async_upload( x264cu_slicetype_t *st, int on );
+/* Sharded stream: this process is rank `rank` of `world` GPUs that are all fed the SAME pictures.  Every rank runs the same
+ * decisions; of each prefetch group it searches only the pairs whose searched picture has display index % world == rank, and
+ * the groups' results are exchanged with one all-gather each, one group late so that nobody waits for a search.  The callback
+ * does the collective (the caller owns the communicator: torch.distributed / NCCL):
+ *   phase 0: provide two device buffers, *d_send of bytes_per_rank and *d_recv of world * bytes_per_rank bytes
+ *   phase 1: all-gather d_send of every rank into d_recv (rank r's block at r * bytes_per_rank), enqueued on `stream`
+ * and returns 0 / -1.  Frame types and MB-tree offsets are those of a single GPU (tested). */
+typedef int (*x264cu_exchange_fn)( void *user, int phase, size_t bytes_per_rank, void **d_send, void **d_recv, void *stream );
+int  x264cu_slicetype_set_shard( x264cu_slicetype_t *st, int rank, int world, x264cu_exchange_fn fn, void *user );
 /* the lookahead object underneath (for reading per-MB results) and the slot a display index currently occupies (-1 if gone) */
 x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *st );
 int  x264cu_slicetype_slot_of( x264cu_slicetype_t *st, int frame );

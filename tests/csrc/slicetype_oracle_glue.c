@@ -116,3 +116,10 @@ int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *out
     memcpy( out, la->slots[slot]->qp_offset, la->slots[slot]->mb_count * sizeof(float) );
     return 0;
 }
+
+/* sharded-stream entries: nothing travels in the CPU harness (every search is computed where it is asked for) */
+size_t x264cu_lookahead_search_bytes( x264cu_lookahead_t *la ) { (void)la; return 8; }
+void *x264cu_lookahead_exchange_stream( x264cu_lookahead_t *la ) { (void)la; return 0; }
+int x264cu_lookahead_export_search( x264cu_lookahead_t *la, int slot, int list, int dist, void *d ) { (void)la; (void)slot; (void)list; (void)dist; (void)d; return 0; }
+int x264cu_lookahead_import_search( x264cu_lookahead_t *la, int slot, int list, int dist, const void *d ) { (void)la; (void)slot; (void)list; (void)dist; (void)d; return 0; }
+int x264cu_lookahead_import_done( x264cu_lookahead_t *la ) { (void)la; return 0; }

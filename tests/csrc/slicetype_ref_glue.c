@@ -94,3 +94,10 @@ int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_fa
     return 0;
 }
 int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *out ) { xref_la_get_mbtree( la->la, slot + 300, 0, 0, out ); return 0; }
+
+/* sharded-stream entries: nothing travels in the CPU harness (every search is computed where it is asked for) */
+size_t x264cu_lookahead_search_bytes( x264cu_lookahead_t *la ) { (void)la; return 8; }
+void *x264cu_lookahead_exchange_stream( x264cu_lookahead_t *la ) { (void)la; return 0; }
+int x264cu_lookahead_export_search( x264cu_lookahead_t *la, int slot, int list, int dist, void *d ) { (void)la; (void)slot; (void)list; (void)dist; (void)d; return 0; }
+int x264cu_lookahead_import_search( x264cu_lookahead_t *la, int slot, int list, int dist, const void *d ) { (void)la; (void)slot; (void)list; (void)dist; (void)d; return 0; }
+int x264cu_lookahead_import_done( x264cu_lookahead_t *la ) { (void)la; return 0; }

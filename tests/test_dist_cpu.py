@@ -1,5 +1,6 @@
-"""world_size-2 gloo test of the N>1 plumbing (x264_b200/dist.py): every rank contributes its stream's decision records,
-one all-gather, every rank ends up with all streams."""
+"""world_size-2 gloo tests of the N>1 plumbing (x264_b200/dist.py): (1) every rank contributes its stream's decision records,
+one all-gather, every rank ends up with all streams; (2) ONE stream sharded over two ranks: the host logic in sharded mode
+(job partition by picture, one exchange per prefetch group, one group late) takes the decisions of the unsharded run."""
 import json
 import os
 import subprocess
@@ -28,3 +29,22 @@ def test_pack_unpack_roundtrip():
     rec = xd.pack_records(7, d, 8)
     assert rec.shape == (8, xd.RECORD_INTS) and (rec[4:] == -1).all()
     assert xd.unpack_records(rec[None]) == {7: d}
+
+
+def _run_shard(tmp_path, world, tag):
+    port = str(30500 + (os.getpid() + world) % 1000)
+    outs = [str(tmp_path / ("%s%d.json" % (tag, r))) for r in range(world)]
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "_shard_worker.py"), str(r), str(world), port, outs[r]])
+             for r in range(world)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    return [json.load(open(o)) for o in outs]
+
+
+def test_sharded_stream_matches_single_rank(tmp_path):
+    single = _run_shard(tmp_path, 1, "s")[0]
+    both = _run_shard(tmp_path, 2, "d")
+    assert single["exchanges"] == 0
+    for r in both:
+        assert r["types"] == single["types"]
+        assert r["exchanges"] >= 3 and r["exchanges"] == both[0]["exchanges"] and r["bytes"] == both[0]["bytes"]

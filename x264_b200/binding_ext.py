@@ -50,6 +50,7 @@ def bind(L):
     L.x264cu_slicetype_set_run_ahead.argtypes = [vp, ci]
     L.x264cu_slicetype_set_async_upload.argtypes = [vp, ci]
     L.x264cu_slicetype_get_qp_offset.argtypes = [vp, ci, vp]
+    L.x264cu_slicetype_set_shard.argtypes = [vp, ci, ci, vp, vp]
     L.x264cu_slicetype_lookahead.argtypes = [vp]
     L.x264cu_slicetype_lookahead.restype = vp
     L.x264cu_lookahead_search_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_long)]
@@ -257,6 +258,12 @@ class Slicetype:
     def set_async_upload(self, on):
         """page-locked pictures passed to step() are read in place; keep them unmodified until four more pictures have been queued"""
         self.L.x264cu_slicetype_set_async_upload(self.h, int(on))
+
+    def set_shard(self, rank, world, exchange):
+        """one stream over `world` GPUs: exchange = x264_b200.dist.ShardExchange (kept alive by this object)"""
+        self._exchange = exchange
+        fn = C.cast(exchange.cb, C.c_void_p) if exchange is not None else None
+        self.ctx.check(self.L.x264cu_slicetype_set_shard(self.h, int(rank), int(world), fn, None))
 
     def search_stats(self):
         """(device ms of the search launches so far, launches, searches) of the lookahead underneath"""

@@ -805,6 +805,7 @@ struct LaSlotHost
     unsigned long long last_search_seq = 0;
     cudaEvent_t ev_ready = nullptr;  // recorded on the upload stream when the picture's planes / reset arrays are in place
     bool main_waited = true;         // the context's stream has been ordered after ev_ready
+    bool xch_dirty = false;
 };
 
 struct x264cu_lookahead
@@ -821,6 +822,7 @@ struct x264cu_lookahead
     uint8_t *h_luma[2] = { nullptr, nullptr };   // pinned staging ring for pictures handed over in pageable memory
     cudaEvent_t h_luma_ev[2] = {};   // ... each guarded by the event of its last copy
     unsigned int h_luma_next = 0;
+    cudaStream_t xch_stream = nullptr;   // exchange stream: export / import of search results between GPUs (sharded stream)
     cudaStream_t up_stream = nullptr;    // upload stream: H2D copy, lowres planes and slot reset of a queued picture run beside the analysis
     cudaEvent_t ev_up_guard = nullptr;   // main-stream work queued before a put (it may still read the slot's previous picture)
 #define LA_ZC_DEPTH 4
@@ -829,6 +831,8 @@ struct x264cu_lookahead
     unsigned int zc_next = 0;
     bool async_upload = false;           // x264cu_lookahead_set_async_upload
     bool search_attr_set = false;
+    struct XchMark { int slot, list, dm1; };
+    std::vector<XchMark> xch_marks;      // searches imported since the last x264cu_lookahead_import_done
     int32_t *d_record = nullptr, *h_record = nullptr;
     LaJobPack pack;                  // jobs being assembled for the next launch
     cudaStream_t search_streams[2] = {};     // prefetch launches alternate: the drain of one wavefront overlaps the fill of the next
@@ -872,6 +876,7 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     cudaSetDevice( la->ctx->device );
     cudaStreamSynchronize( la->ctx->stream );
     if( la->up_stream ) cudaStreamSynchronize( la->up_stream );
+    if( la->xch_stream ) cudaStreamSynchronize( la->xch_stream );
     for( int i = 0; i < 2; i++ ) if( la->search_streams[i] ) cudaStreamSynchronize( la->search_streams[i] );
     if( la->stats_on )
     {
@@ -900,9 +905,10 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     {
         auto &ax = la->ctx->aux_streams;
         for( size_t i = 0; i < ax.size(); )
-            if( ax[i] == la->up_stream || ax[i] == la->search_streams[0] || ax[i] == la->search_streams[1] ) ax.erase( ax.begin() + i ); else i++;
+            if( ax[i] == la->up_stream || ax[i] == la->xch_stream || ax[i] == la->search_streams[0] || ax[i] == la->search_streams[1] ) ax.erase( ax.begin() + i ); else i++;
     }
     if( la->up_stream ) { cudaStreamSynchronize( la->up_stream ); cudaStreamDestroy( la->up_stream ); }
+    if( la->xch_stream ) { cudaStreamSynchronize( la->xch_stream ); cudaStreamDestroy( la->xch_stream ); }
     for( int i = 0; i < 2; i++ ) { cudaFreeHost( la->h_luma[i] ); if( la->h_luma_ev[i] ) cudaEventDestroy( la->h_luma_ev[i] ); }
     if( la->ev_up_guard ) cudaEventDestroy( la->ev_up_guard );
     for( int i = 0; i < LA_ZC_DEPTH; i++ ) if( la->ev_zero_copy[i] ) cudaEventDestroy( la->ev_zero_copy[i] );
@@ -995,6 +1001,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         if( ok && cudaEventCreateWithFlags( &la->h_luma_ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     }
     if( ok && cudaStreamCreateWithPriority( &la->up_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
+    if( ok && cudaStreamCreateWithPriority( &la->xch_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->ev_up_guard, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     for( int i = 0; i < LA_ZC_DEPTH; i++ )
         if( ok && cudaEventCreateWithFlags( &la->ev_zero_copy[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
@@ -1049,6 +1056,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         }
     }
     ctx->aux_streams.push_back( la->up_stream );
+    ctx->aux_streams.push_back( la->xch_stream );
     for( int i = 0; i < 2; i++ ) ctx->aux_streams.push_back( la->search_streams[i] );
     *out = la;
     return 0;
@@ -1567,6 +1575,75 @@ float x264cu_lookahead_get_weighted_cost_delta( x264cu_lookahead_t *la, int slot
 {
     if( !la || slot < 0 || slot >= (int)la->slots.size() || dist_minus1 < 0 || dist_minus1 > la->d.B ) return -1.0f;
     return la->slots[slot].weighted_cost_delta[dist_minus1];
+}
+
+/* ---- one picture stream sharded over several GPUs: the results of a search (lowres_mvs + lowres_mv_costs of one
+ * (picture, list, distance)) leave the GPU that ran it / enter the GPUs that did not ---- */
+size_t x264cu_lookahead_search_bytes( x264cu_lookahead_t *la ) { return la ? (size_t)la->d.mb_count * 8 : 0; }
+void *x264cu_lookahead_exchange_stream( x264cu_lookahead_t *la ) { return la ? (void *)la->xch_stream : nullptr; }
+
+static int la_xch_args( x264cu_lookahead *la, int slot, int list, int dist, const char *who )
+{
+    if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use || list < 0 || list > 1 || dist < 1 || dist > la->d.B + 1 ||
+        ( list == 1 && !la->d.B ) )
+        return x264cu_fail( la->ctx, "%s: bad search (slot %d, list %d, distance %d)", who, slot, list, dist );
+    return 0;
+}
+
+int x264cu_lookahead_export_search( x264cu_lookahead_t *la, int slot, int list, int dist, void *d_dst )
+{
+    if( !la || !d_dst ) return -1;
+    if( la_xch_args( la, slot, list, dist, "export_search" ) ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    const LaDims &d = la->d;
+    LaSlotHost &s = la->slots[slot];
+    if( !s.searched[list][dist - 1] ) return x264cu_fail( ctx, "export_search: (slot %d, list %d, distance %d) has not been searched here", slot, list, dist );
+    const int e = s.pending[list][dist - 1];
+    if( e >= 0 ) CU_CHECK( ctx, cudaStreamWaitEvent( la->xch_stream, la->ev[e], 0 ) );       // the search itself, if still in flight
+    const size_t idx = (size_t)list * ( d.B + 1 ) + ( dist - 1 );
+    CU_CHECK( ctx, cudaMemcpyAsync( d_dst, s.dev.mvs + idx * d.mb_count * 2, (size_t)d.mb_count * 4, cudaMemcpyDeviceToDevice, la->xch_stream ) );
+    CU_CHECK( ctx, cudaMemcpyAsync( (uint8_t *)d_dst + (size_t)d.mb_count * 4, s.dev.mv_costs + idx * d.mb_count, (size_t)d.mb_count * 4,
+                                    cudaMemcpyDeviceToDevice, la->xch_stream ) );
+    return 0;
+}
+
+int x264cu_lookahead_import_search( x264cu_lookahead_t *la, int slot, int list, int dist, const void *d_src )
+{
+    if( !la || !d_src ) return -1;
+    if( la_xch_args( la, slot, list, dist, "import_search" ) ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    const LaDims &d = la->d;
+    LaSlotHost &s = la->slots[slot];
+    // the slot's upload (its vector arrays are cleared there) comes first
+    CU_CHECK( ctx, cudaStreamWaitEvent( la->xch_stream, s.ev_ready, 0 ) );
+    const size_t idx = (size_t)list * ( d.B + 1 ) + ( dist - 1 );
+    CU_CHECK( ctx, cudaMemcpyAsync( s.dev.mvs + idx * d.mb_count * 2, d_src, (size_t)d.mb_count * 4, cudaMemcpyDeviceToDevice, la->xch_stream ) );
+    CU_CHECK( ctx, cudaMemcpyAsync( s.dev.mv_costs + idx * d.mb_count, (const uint8_t *)d_src + (size_t)d.mb_count * 4, (size_t)d.mb_count * 4,
+                                    cudaMemcpyDeviceToDevice, la->xch_stream ) );
+    s.searched[list][dist - 1] = true;
+    s.xch_dirty = true;
+    la->xch_marks.push_back( { slot, list, dist - 1 } );
+    return 0;
+}
+
+int x264cu_lookahead_import_done( x264cu_lookahead_t *la )
+{   // one event for everything imported since the last call: cost requests (and the slots' next uploads) wait for it
+    if( !la ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    if( la->xch_marks.empty() ) return 0;
+    const int e = la->ev_next;
+    la->ev_next = ( la->ev_next + 1 ) % la->n_ev;
+    CU_CHECK( ctx, cudaEventSynchronize( la->ev[e] ) );                  // ring entry reuse
+    CU_CHECK( ctx, cudaEventRecord( la->ev[e], la->xch_stream ) );
+    la->ev_seq[e] = la->ev_seq_next++;
+    for( auto &m : la->xch_marks )
+    {
+        LaSlotHost &s = la->slots[m.slot];
+        s.pending[m.list][m.dm1] = e;
+        s.last_search_ev = e; s.last_search_seq = la->ev_seq[e];
+    }
+    la->xch_marks.clear();
+    return 0;
 }
 
 int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int fenc_slot, int ref_slot )

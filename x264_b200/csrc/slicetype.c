@@ -61,11 +61,16 @@ struct x264cu_slicetype
     st_frame_t *recent[BFRAME_MAX + 2];   /* the last bframes+1 queued pictures, newest first (prefetch partners) */
     int n_recent;
     /* prefetch jobs gathered over a few pictures so that one launch fills the GPU (each search is a thin wavefront) */
-    int pj_fenc[256], pj_ref[256], pj_list[256], pj_dist[256], pj_fframe[256], pj_rframe[256], n_pj, pj_pictures;
+    int pj_fenc[256], pj_ref[256], pj_list[256], pj_dist[256], pj_fframe[256], pj_rframe[256], pj_fframe2[256], n_pj, pj_pictures;
     int prefetch_group;                   /* pictures per prefetch launch */
     double t_put, t_batch, t_cost, t_step; long n_cost_calls;   /* X264CU_STATS: where the calling thread's time goes */
     int run_ahead;                        /* extra pictures queued before deciding, like param.i_sync_lookahead (encoder.c:1611) */
     float duration, qcompress;            /* f_duration of every picture (constant frame rate), rc.f_qcompress */
+    /* sharded stream (x264cu_slicetype_set_shard): the previous group's jobs, waiting for their exchange */
+    int shard_rank, shard_world;
+    x264cu_exchange_fn shard_fn;
+    void *shard_user;
+    int xj_slot[256], xj_list[256], xj_dist[256], xj_owner[256], xj_frame[256], n_xj;
 };
 
 int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame );
@@ -708,6 +713,43 @@ void x264cu_slicetype_close( x264cu_slicetype_t *s )
     free( s );
 }
 
+/* Sharded stream: all-gather the results of the previous group's searches (launched one group ago: nobody waits) and install
+ * the ones searched on other GPUs.  Every rank holds the same job list, so the layout of the exchange is known everywhere:
+ * rank r's k-th job sits at r * bytes_per_rank + k * search_bytes. */
+static int shard_exchange( x264cu_slicetype_t *s )
+{
+    if( !s->n_xj ) return 0;
+    int cnt[64] = { 0 }, maxc = 0;
+    for( int i = 0; i < s->n_xj; i++ ) cnt[s->xj_owner[i]]++;
+    for( int r = 0; r < s->shard_world; r++ ) if( cnt[r] > maxc ) maxc = cnt[r];
+    const size_t rec = x264cu_lookahead_search_bytes( s->la ), per_rank = (size_t)maxc * rec;
+    void *d_send = NULL, *d_recv = NULL;
+    if( s->shard_fn( s->shard_user, 0, per_rank, &d_send, &d_recv, x264cu_lookahead_exchange_stream( s->la ) ) || !d_send || !d_recv )
+        return -1;
+    int k = 0;
+    for( int i = 0; i < s->n_xj; i++ )
+        if( s->xj_owner[i] == s->shard_rank )
+        {   /* a picture that has left its slot since (end of stream) has nothing to send: the block stays as it is */
+            if( x264cu_slicetype_slot_of( s, s->xj_frame[i] ) == s->xj_slot[i] &&
+                x264cu_lookahead_export_search( s->la, s->xj_slot[i], s->xj_list[i], s->xj_dist[i], (char *)d_send + (size_t)k * rec ) )
+                return -1;
+            k++;
+        }
+    if( s->shard_fn( s->shard_user, 1, per_rank, &d_send, &d_recv, x264cu_lookahead_exchange_stream( s->la ) ) )
+        return -1;
+    int pos[64] = { 0 };
+    for( int i = 0; i < s->n_xj; i++ )
+    {
+        int r = s->xj_owner[i], kk = pos[r]++;
+        if( r == s->shard_rank || x264cu_slicetype_slot_of( s, s->xj_frame[i] ) != s->xj_slot[i] )
+            continue;
+        if( x264cu_lookahead_import_search( s->la, s->xj_slot[i], s->xj_list[i], s->xj_dist[i], (char *)d_recv + (size_t)r * per_rank + (size_t)kk * rec ) )
+            return -1;
+    }
+    s->n_xj = 0;
+    return x264cu_lookahead_import_done( s->la );
+}
+
 /* launch the gathered searches; jobs whose pictures have left their slots in the meantime are dropped */
 static int flush_prefetch( x264cu_slicetype_t *s )
 {
@@ -724,12 +766,33 @@ static int flush_prefetch( x264cu_slicetype_t *s )
             if( !t ) continue;
         }
         s->pj_fenc[n] = s->pj_fenc[i]; s->pj_ref[n] = s->pj_ref[i]; s->pj_list[n] = s->pj_list[i]; s->pj_dist[n] = s->pj_dist[i];
+        s->pj_fframe2[n] = s->pj_fframe[i];
         n++;
     }
     s->n_pj = 0;
     s->pj_pictures = 0;
     double t0_ = st_now();
-    int rc_ = n ? x264cu_lookahead_search_batch( s->la, n, s->pj_fenc, s->pj_ref, s->pj_list, s->pj_dist ) : 0;
+    int rc_ = 0;
+    if( s->shard_world > 1 )
+    {   /* first the exchange of the group launched one flush ago, then this group's own share */
+        if( shard_exchange( s ) ) return -1;
+        int m = 0;
+        for( int i = 0; i < n; i++ )
+        {
+            int owner = s->pj_fframe2[i] % s->shard_world;
+            s->xj_slot[i] = s->pj_fenc[i]; s->xj_list[i] = s->pj_list[i]; s->xj_dist[i] = s->pj_dist[i];
+            s->xj_owner[i] = owner; s->xj_frame[i] = s->pj_fframe2[i];
+            if( owner == s->shard_rank )
+            {
+                s->pj_fenc[m] = s->pj_fenc[i]; s->pj_ref[m] = s->pj_ref[i]; s->pj_list[m] = s->pj_list[i]; s->pj_dist[m] = s->pj_dist[i];
+                m++;
+            }
+        }
+        s->n_xj = n;
+        rc_ = m ? x264cu_lookahead_search_batch( s->la, m, s->pj_fenc, s->pj_ref, s->pj_list, s->pj_dist ) : 0;
+    }
+    else
+        rc_ = n ? x264cu_lookahead_search_batch( s->la, n, s->pj_fenc, s->pj_ref, s->pj_list, s->pj_dist ) : 0;
     s->t_batch += st_now() - t0_;
     return rc_ ? -1 : 0;
 }
@@ -792,6 +855,7 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
             return 0;
     }
     if( !luma && s->n_pj && flush_prefetch( s ) ) return -1;
+    if( !luma && s->shard_world > 1 && s->n_xj && shard_exchange( s ) ) return -1;
     lookahead_get_frames( s );
     if( s->failed ) return -1;
     if( !s->n_current )
@@ -829,6 +893,13 @@ void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *s, int prefetch ) { if( 
 void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *s, int pictures )
 {
     if( s && !s->i_input && pictures >= 0 && pictures <= ST_RUN_AHEAD_MAX ) s->run_ahead = pictures;
+}
+
+int x264cu_slicetype_set_shard( x264cu_slicetype_t *s, int rank, int world, x264cu_exchange_fn fn, void *user )
+{
+    if( !s || s->i_input || world < 1 || world > 64 || rank < 0 || rank >= world || ( world > 1 && !fn ) ) return -1;
+    s->shard_rank = rank; s->shard_world = world; s->shard_fn = fn; s->shard_user = user;
+    return 0;
 }
 
 void x264cu_slicetype_set_async_upload( x264cu_slicetype_t *s, int on ) { if( s ) x264cu_lookahead_set_async_upload( s->la, on ); }

@@ -1,9 +1,59 @@
 """Multi-GPU plumbing (torch.distributed: NCCL on GPUs, gloo in the CPU tests).
 
-Round 1 sharding: one independent picture stream per GPU (no data-path collective, SURVEY 8e "replicas" row for the
-searches), followed by ONE all-gather of the fixed-size per-picture decision records so that rank 0 holds every stream's
-slice-type decisions -- the exchange step the north-star describes for the lookahead results."""
+Two ways of using N GPUs:
+  * one independent picture stream per GPU (no data-path collective; bench.py's weak-scaling line), followed by ONE all-gather
+    of the fixed-size per-picture decision records so that rank 0 holds every stream's slice-type decisions;
+  * ONE stream sharded over the GPUs: every rank is fed the same pictures and takes the same decisions, the lowres
+    searches of each prefetch group are split by picture and their results (8 bytes per macroblock and search) exchanged with one
+    all-gather per group -- ShardExchange below is the collective x264cu_slicetype_set_shard calls back into."""
+import ctypes as C
+
 import numpy as np
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p)
+
+
+class ShardExchange:
+    """the all-gather of x264cu_slicetype_set_shard over torch.distributed: NCCL on the lookahead's exchange stream (device
+    buffers), or gloo on host buffers in the CPU harness, where nothing real travels"""
+
+    def __init__(self, dist, device=None):
+        import torch
+        self.torch, self.dist, self.device = torch, dist, device
+        self.world = dist.get_world_size()
+        self.send = self.recv = None
+        self.calls = 0
+        self.bytes = 0
+        self.cb = EXCHANGE_FN(self._call)          # keep the trampoline alive as long as this object
+
+    def _call(self, user, phase, per_rank, d_send, d_recv, stream):
+        try:
+            torch = self.torch
+            n = max(int(per_rank), 16)
+            if phase == 0:
+                if self.send is None or self.send.numel() < n:
+                    dev = self.device if self.device is not None else "cpu"
+                    self.send = torch.zeros(n, dtype=torch.uint8, device=dev)
+                    self.recv = torch.zeros(n * self.world, dtype=torch.uint8, device=dev)
+                self.cur = n
+                # rank r's block must sit at r * per_rank: gather into a view of exactly world * per_rank bytes
+                d_send[0] = self.send.data_ptr()
+                d_recv[0] = self.recv.data_ptr()
+                return 0
+            send, recv = self.send[:int(per_rank)] if per_rank else self.send[:0], self.recv[:int(per_rank) * self.world]
+            if per_rank:
+                if self.device is not None:
+                    with torch.cuda.stream(torch.cuda.ExternalStream(int(stream), device=self.device)):
+                        self.dist.all_gather_into_tensor(recv, send)
+                else:
+                    self.dist.all_gather_into_tensor(recv, send)
+            self.calls += 1
+            self.bytes += int(per_rank) * self.world
+            return 0
+        except Exception as e:                      # never let an exception cross the C boundary
+            import sys
+            sys.stderr.write("ShardExchange: %r\n" % (e,))
+            return -1
 
 RECORD_INTS = 4          # (stream, display index, slice type, reserved)
 
