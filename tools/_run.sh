@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/shard_check.py 2> gpurun_out/shard.err | tail -1 > gpurun_out/shard_2gpu.json; cat gpurun_out/shard_2gpu.json; tail -5 gpurun_out/shard.err | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_frame.py tests/test_golden.py tests/test_gpu_me.py tests/test_gpu_lookahead.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python tools/frame_bench.py 2>&1 | tail -1 | tee gpurun_out/frame_bench.json

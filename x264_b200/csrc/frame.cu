@@ -39,22 +39,29 @@ lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, 
     if( gx >= groups_x ) return;
     const int ox = gx * 4 - X264CU_PAD;
     const int y = clampi( oy, 0, ll-1 );
-    int rows[3][9];
-    if( fast_ok && oy == y && ox >= 0 && ox + 4 <= wl && 2*( ox + 4 ) + 1 <= width && 2*y + 2 < height )
-    {   // interior: rows 2y..2y+2, columns 2ox .. 2ox+8, all inside the picture; 8-byte aligned vector loads
+    if( fast_ok && ox >= 0 && ox + 4 <= wl && 2*( ox + 4 ) + 1 <= width )
+    {   // columns 2ox .. 2ox+8 inside the picture (rows are clamped: the rows of the top / bottom border repeat the edge rows'
+        // results, the last source row repeats below the picture).  8-byte aligned vector loads; the whole filter runs on packed
+        // bytes: FILTER(a,b,c,d) = avg( avg(a,b), avg(c,d) ) with avg(x,y) = (x+y+1)>>1 = __vavgu4 (mc.c:494-500)
+        uint32_t lo[3], hi[3], nx[3];
 #pragma unroll
         for( int r = 0; r < 3; r++ )
         {
-            const uint8_t *p = src + (intptr_t)( 2*y + r ) * src_stride + 2*ox;
-            uint2 v = *(const uint2 *)p;
-            rows[r][0] = v.x & 255; rows[r][1] = ( v.x >> 8 ) & 255; rows[r][2] = ( v.x >> 16 ) & 255; rows[r][3] = v.x >> 24;
-            rows[r][4] = v.y & 255; rows[r][5] = ( v.y >> 8 ) & 255; rows[r][6] = ( v.y >> 16 ) & 255; rows[r][7] = v.y >> 24;
-            rows[r][8] = p[8];
+            const uint8_t *p = src + (intptr_t)min( 2*y + r, height-1 ) * src_stride + 2*ox;
+            const uint2 v = __ldg( (const uint2 *)p );
+            lo[r] = v.x; hi[r] = v.y; nx[r] = __ldg( p + 8 );
         }
-        *(uint32_t *)( d0 + (intptr_t)oy*dst_stride + ox ) = filt4( rows[0], rows[1], 0 );
-        *(uint32_t *)( dh + (intptr_t)oy*dst_stride + ox ) = filt4( rows[0], rows[1], 1 );
-        *(uint32_t *)( dv + (intptr_t)oy*dst_stride + ox ) = filt4( rows[1], rows[2], 0 );
-        *(uint32_t *)( dc + (intptr_t)oy*dst_stride + ox ) = filt4( rows[1], rows[2], 1 );
+        // vertical means of rows (0,1) and (1,2), columns 0..8
+        const uint32_t a_lo = __vavgu4( lo[0], lo[1] ), a_hi = __vavgu4( hi[0], hi[1] ), a_nx = __vavgu4( nx[0], nx[1] );
+        const uint32_t b_lo = __vavgu4( lo[1], lo[2] ), b_hi = __vavgu4( hi[1], hi[2] ), b_nx = __vavgu4( nx[1], nx[2] );
+        // columns {0,2,4,6}, {1,3,5,7}, {2,4,6,8}
+        const uint32_t a_ev = __byte_perm( a_lo, a_hi, 0x6420 ), a_od = __byte_perm( a_lo, a_hi, 0x7531 );
+        const uint32_t b_ev = __byte_perm( b_lo, b_hi, 0x6420 ), b_od = __byte_perm( b_lo, b_hi, 0x7531 );
+        const uint32_t a_e2 = __byte_perm( a_ev, a_nx, 0x4321 ), b_e2 = __byte_perm( b_ev, b_nx, 0x4321 );
+        *(uint32_t *)( d0 + (intptr_t)oy*dst_stride + ox ) = __vavgu4( a_ev, a_od );
+        *(uint32_t *)( dh + (intptr_t)oy*dst_stride + ox ) = __vavgu4( a_od, a_e2 );
+        *(uint32_t *)( dv + (intptr_t)oy*dst_stride + ox ) = __vavgu4( b_ev, b_od );
+        *(uint32_t *)( dc + (intptr_t)oy*dst_stride + ox ) = __vavgu4( b_od, b_e2 );
         return;
     }
     // edges and border: per-pixel clamped coordinates (the picture is edge-replicated to the mod-16 size and one
@@ -129,6 +136,96 @@ hpel_kernel( const uint8_t *__restrict__ src, intptr_t stride, int width, int he
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// hpel, word path (4-byte aligned planes, width % 4 == 0): CTA = 128x16 output tile of the padded domain.  The source tile
+// (+halo) is staged as 32-bit words (interior tiles) or byte by byte with clamped coordinates (tiles touching the border: the
+// padded domain of the three planes is the filter of the edge-replicated source, frame.c:596-625); a thread produces 4
+// horizontally adjacent pixels per step: first the vertical 6-tap sums (V plane + 16-bit intermediates in shared memory,
+// mc.c:176-183), then the horizontal taps over the source row (H) and over the intermediates (C, mc.c:184-193).
+// ------------------------------------------------------------------------------------------------
+constexpr int FT_W = 128, FT_H = 16, FT_SW = 144, FT_WORDS = 34;     // smem row: columns x0-4 .. x0+131 = 34 words (+pad)
+
+__device__ __forceinline__ int tap6( int a, int b, int c, int d, int e, int f ) { return a + f - 5 * ( b + e ) + 20 * ( c + d ); }
+__device__ __forceinline__ uint32_t clip4( int a, int b, int c, int d, int add, int sh )
+{
+    a = clampi( ( a + add ) >> sh, 0, 255 ); b = clampi( ( b + add ) >> sh, 0, 255 );
+    c = clampi( ( c + add ) >> sh, 0, 255 ); d = clampi( ( d + add ) >> sh, 0, 255 );
+    return (uint32_t)a | ( (uint32_t)b << 8 ) | ( (uint32_t)c << 16 ) | ( (uint32_t)d << 24 );
+}
+
+__global__ void __launch_bounds__( 256 )
+hpel_words_kernel( const uint8_t *__restrict__ src, intptr_t stride, int width, int height,
+                   uint8_t *dh, uint8_t *dv, uint8_t *dc, uint8_t *dsrc_border )
+{
+    __shared__ __align__( 16 ) uint8_t s_src[FT_H + 5][FT_SW];       // rows y0-2 .. y0+18, columns x0-4 .. x0+131
+    __shared__ __align__( 16 ) int16_t s_v[FT_H][FT_SW];             // vertical tap sums, same columns
+    const int x0 = blockIdx.x * FT_W - X264CU_PAD, y0 = blockIdx.y * FT_H - X264CU_PAD;
+    const bool interior = x0 - 4 >= 0 && x0 + FT_W + 4 <= width && y0 - 2 >= 0 && y0 + FT_H + 3 <= height;
+    if( interior )
+    {
+        for( int i = threadIdx.x; i < ( FT_H + 5 ) * FT_WORDS; i += blockDim.x )
+        {
+            const int r = i / FT_WORDS, c = i - r * FT_WORDS;
+            *(uint32_t *)&s_src[r][4 * c] = __ldg( (const uint32_t *)( src + (intptr_t)( y0 + r - 2 ) * stride + x0 - 4 ) + c );
+        }
+    }
+    else
+    {
+        for( int i = threadIdx.x; i < ( FT_H + 5 ) * FT_WORDS * 4; i += blockDim.x )
+        {
+            const int r = i / ( FT_WORDS * 4 ), c = i - r * ( FT_WORDS * 4 );
+            const int sy = clampi( y0 + r - 2, 0, height - 1 ), sx = clampi( x0 + c - 4, 0, width - 1 );
+            s_src[r][c] = src[(intptr_t)sy * stride + sx];
+        }
+    }
+    __syncthreads();
+    const int full_w = width + 2 * X264CU_PAD, full_h = height + 2 * X264CU_PAD;
+    // vertical sums of every staged column (the C plane needs 2 / 3 columns beyond the tile), V plane of the tile's own columns
+    for( int i = threadIdx.x; i < FT_H * FT_WORDS; i += blockDim.x )
+    {
+        const int r = i / FT_WORDS, wc = i - r * FT_WORDS;
+        uint32_t w[6];
+#pragma unroll
+        for( int k = 0; k < 6; k++ ) w[k] = *(const uint32_t *)&s_src[r + k][4 * wc];
+        int v[4];
+#pragma unroll
+        for( int b = 0; b < 4; b++ )
+            v[b] = tap6( ( w[0] >> ( 8*b ) ) & 255, ( w[1] >> ( 8*b ) ) & 255, ( w[2] >> ( 8*b ) ) & 255,
+                         ( w[3] >> ( 8*b ) ) & 255, ( w[4] >> ( 8*b ) ) & 255, ( w[5] >> ( 8*b ) ) & 255 );
+        *(uint2 *)&s_v[r][4 * wc] = make_uint2( ( v[0] & 0xffff ) | ( (uint32_t)v[1] << 16 ), ( v[2] & 0xffff ) | ( (uint32_t)v[3] << 16 ) );
+        const int ox = x0 + 4 * ( wc - 1 ), oy = y0 + r;
+        if( wc >= 1 && wc <= FT_W / 4 && ox + X264CU_PAD < full_w && oy + X264CU_PAD < full_h )
+            *(uint32_t *)( dv + (intptr_t)oy * stride + ox ) = clip4( v[0], v[1], v[2], v[3], 16, 5 );
+    }
+    __syncthreads();
+    for( int i = threadIdx.x; i < FT_H * ( FT_W / 4 ); i += blockDim.x )
+    {
+        const int r = i / ( FT_W / 4 ), g = i - r * ( FT_W / 4 );
+        const int ox = x0 + 4 * g, oy = y0 + r;
+        if( ox + X264CU_PAD >= full_w || oy + X264CU_PAD >= full_h ) continue;
+        // source row of the output row, columns ox-4 .. ox+7 (bytes 0..11; the pixel of output k is byte 4+k)
+        const uint32_t *sw = (const uint32_t *)&s_src[r + 2][4 * g];
+        const uint32_t s0 = sw[0], s1 = sw[1], s2 = sw[2];
+        int b[12];
+#pragma unroll
+        for( int k = 0; k < 4; k++ ) { b[k] = ( s0 >> ( 8*k ) ) & 255; b[4 + k] = ( s1 >> ( 8*k ) ) & 255; b[8 + k] = ( s2 >> ( 8*k ) ) & 255; }
+        int h[4], c[4];
+#pragma unroll
+        for( int k = 0; k < 4; k++ ) h[k] = tap6( b[2 + k], b[3 + k], b[4 + k], b[5 + k], b[6 + k], b[7 + k] );
+        const uint32_t *vw = (const uint32_t *)&s_v[r][4 * g];        // 12 int16: columns ox-4 .. ox+7
+        int v[12];
+#pragma unroll
+        for( int k = 0; k < 6; k++ ) { const uint32_t t = vw[k]; v[2*k] = (int16_t)( t & 0xffff ); v[2*k + 1] = (int16_t)( t >> 16 ); }
+#pragma unroll
+        for( int k = 0; k < 4; k++ ) c[k] = tap6( v[2 + k], v[3 + k], v[4 + k], v[5 + k], v[6 + k], v[7 + k] );
+        const intptr_t o = (intptr_t)oy * stride + ox;
+        *(uint32_t *)( dh + o ) = clip4( h[0], h[1], h[2], h[3], 16, 5 );
+        *(uint32_t *)( dc + o ) = clip4( c[0], c[1], c[2], c[3], 512, 10 );
+        if( dsrc_border && ( ox < 0 || ox >= width || oy < 0 || oy >= height ) )
+            *(uint32_t *)( dsrc_border + o ) = s1;
+    }
+}
+
 } // namespace
 
 // the same launch on a stream of the caller's choice (the lookahead's upload stream)
@@ -165,6 +262,14 @@ int x264cu_hpel_filter( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, int 
 {
     if( !ctx ) return -1;
     if( width < 1 || height < 1 ) return x264cu_fail( ctx, "hpel_filter: bad size" );
+    const bool words = !( ( (uintptr_t)d_src | (uintptr_t)d_h | (uintptr_t)d_v | (uintptr_t)d_c | (uintptr_t)stride ) & 3 ) && !( width & 3 );
+    if( words )
+    {
+        dim3 grid( ( width + 2*X264CU_PAD + FT_W - 1 ) / FT_W, ( height + 2*X264CU_PAD + FT_H - 1 ) / FT_H );
+        hpel_words_kernel<<<grid, 256, 0, ctx->stream>>>( d_src, stride, width, height, d_h, d_v, d_c, expand_src ? d_src : nullptr );
+        CU_LAUNCH_CHECK( ctx );
+        return 0;
+    }
     dim3 grid( ( width + 2*X264CU_PAD + HT_W - 1 ) / HT_W, ( height + 2*X264CU_PAD + HT_H - 1 ) / HT_H );
     hpel_kernel<<<grid, 256, 0, ctx->stream>>>( d_src, stride, width, height, d_h, d_v, d_c, expand_src ? d_src : nullptr );
     CU_LAUNCH_CHECK( ctx );
