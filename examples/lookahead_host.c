@@ -1,0 +1,99 @@
+/* A host written in plain C -- what the reference (a C program) would look like on its side of the boundary: it includes
+ * include/x264_b200.h, links libx264_b200.so, and drives the lookahead the way x264_encoder_encode does
+ * (x264_lookahead_put_frame / x264_lookahead_get_frames -> x264cu_slicetype_step), reading MB-tree's quantiser offsets for the
+ * pictures it would encode.  No CUDA headers, no C++.
+ *
+ *   gcc -O2 -Iinclude examples/lookahead_host.c -o lookahead_host -Lx264_b200/csrc -lx264_b200 -Wl,-rpath,$PWD/x264_b200/csrc
+ *   ./lookahead_host WIDTH HEIGHT FRAMES [raw 8-bit luma file]      (without a file: a synthetic moving texture with a cut)
+ *
+ * Prints one line per picture in coded order: "frame <display index> type <I|P|B|b...> qp_offset_mean <f>".
+ * tests/test_gpu_c_host.py builds and runs it and compares its output with the Python binding's. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "x264_b200.h"
+
+static const char *type_name( int t )
+{
+    switch( t )
+    {
+        case X264CU_TYPE_IDR:  return "IDR";
+        case X264CU_TYPE_I:    return "I";
+        case X264CU_TYPE_P:    return "P";
+        case X264CU_TYPE_BREF: return "Bref";
+        case X264CU_TYPE_B:    return "B";
+        default:               return "?";
+    }
+}
+
+/* deterministic synthetic content: a smooth texture translated a little every picture, a hard cut at two thirds */
+static void synth( uint8_t *luma, int w, int h, int i, int n )
+{
+    int cut = i >= ( 2 * n ) / 3;
+    int ox = ( i * 3 ) % 17 + ( cut ? 91 : 0 ), oy = ( i * 2 ) % 11 + ( cut ? 47 : 0 );
+    for( int y = 0; y < h; y++ )
+        for( int x = 0; x < w; x++ )
+        {
+            int u = x + ox, v = y + oy;
+            int val = 128 + ( ( ( u * 7 + v * 3 ) % 64 ) - 32 ) + ( ( ( u / 8 + v / 8 ) & 1 ) ? 24 : -24 ) + ( cut ? ( u * v ) % 23 : ( u + 2 * v ) % 13 );
+            luma[(size_t)y * w + x] = (uint8_t)( val < 0 ? 0 : val > 255 ? 255 : val );
+        }
+}
+
+int main( int argc, char **argv )
+{
+    if( argc < 4 ) { fprintf( stderr, "usage: %s WIDTH HEIGHT FRAMES [luma.raw]\n", argv[0] ); return 2; }
+    const int w = atoi( argv[1] ), h = atoi( argv[2] );
+    int n = atoi( argv[3] );
+    FILE *in = argc > 4 ? fopen( argv[4], "rb" ) : NULL;
+    if( argc > 4 && !in ) { perror( argv[4] ); return 2; }
+
+    x264cu_ctx_t *ctx;
+    if( x264cu_open( &ctx, 0 ) ) { fprintf( stderr, "x264cu_open: %s\n", x264cu_strerror( NULL ) ); return 1; }   /* no CPU fallback */
+
+    x264cu_slicetype_params_t p;
+    memset( &p, 0, sizeof( p ) );
+    p.la.width = w; p.la.height = h;
+    p.la.subpel_refine = 7; p.la.me_method = X264CU_ME_HEX; p.la.me_range = 16; p.la.mv_range = 512;     /* preset medium */
+    p.la.bframes = 3; p.la.weighted_bipred = 1; p.la.aq_mode = 0; p.la.mb_tree = 1; p.la.weighted_pred = 0;
+    p.keyint_max = 250; p.keyint_min = 25; p.scenecut_threshold = 40; p.b_adapt = 1; p.b_pyramid = 2; p.rc_lookahead = 20;
+    p.psy = 0; p.frame_reference = 3; p.fps_num = 25; p.fps_den = 1; p.qcompress = 0.6f;
+    x264cu_slicetype_t *st;
+    if( x264cu_slicetype_open( ctx, &p, &st ) ) { fprintf( stderr, "slicetype_open: %s\n", x264cu_strerror( ctx ) ); return 1; }
+
+    const int mbs = ( ( w + 15 ) / 16 ) * ( ( h + 15 ) / 16 );
+    uint8_t *luma = x264cu_malloc_host( ctx, (size_t)w * h );          /* page-locked: read in place by the copy engine */
+    float *qp = malloc( sizeof( float ) * mbs );
+    if( !luma || !qp ) return 1;
+    int fed = 0, frame, type, rc = 0;
+    for( ;; )
+    {
+        const uint8_t *pic = NULL;
+        if( fed < n )
+        {
+            if( in ) { if( fread( luma, 1, (size_t)w * h, in ) != (size_t)w * h ) { n = fed; continue; } }
+            else synth( luma, w, h, fed, n );
+            pic = luma;
+            fed++;
+        }
+        if( x264cu_slicetype_step( st, pic, w, NULL, &frame, &type ) ) { fprintf( stderr, "step: %s\n", x264cu_strerror( ctx ) ); rc = 1; break; }
+        if( frame >= 0 )
+        {
+            double mean = 0;
+            if( type != X264CU_TYPE_B && type != X264CU_TYPE_BREF && !x264cu_slicetype_get_qp_offset( st, frame, qp ) )
+            {
+                for( int i = 0; i < mbs; i++ ) mean += qp[i];
+                mean /= mbs;
+            }
+            printf( "frame %d type %s qp_offset_mean %.4f\n", frame, type_name( type ), mean );
+        }
+        else if( !pic )
+            break;                                                     /* flushing and nothing left */
+    }
+    free( qp );
+    x264cu_free_host( ctx, luma );
+    x264cu_slicetype_close( st );
+    x264cu_close( ctx );
+    if( in ) fclose( in );
+    return rc;
+}

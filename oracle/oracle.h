@@ -144,6 +144,12 @@ void orc_la_mbtree_reset( orc_la_frame_t *f );
 void orc_la_frame_set_qp_offset_aq( orc_la_frame_t *f, const float *aq );
 void orc_la_frame_get_mbtree( orc_la_frame_t *f, int what, int i, void *out );
 float orc_log2( uint32_t x );           /* x264_log2, common/base.h:226-230 */
+float orc_log2_frac( uint32_t x );      /* its mantissa part alone: x264_log2_lut[(x<<lz>>24)&0x7f] */
+
+/* ---- adaptive quantisation (oracle_aq.c): x264_adaptive_quant_frame, aq-mode 0 / 1 ---- */
+void orc_adaptive_quant_frame( const uint8_t *luma, intptr_t stride, const uint8_t *cb, const uint8_t *cr, intptr_t cstride,
+                               int width, int height, int aq_mode, float aq_strength, float *qp_offset_aq, uint16_t *inv_qscale,
+                               uint64_t *stats );
 
 #ifdef __cplusplus
 }

@@ -683,7 +683,8 @@ static const float *log2_lut( void )
     return lut;
 }
 /* the two halves of x264_log2: mantissa table entry and integer part */
-static float log2_frac( uint32_t x ) { int lz = __builtin_clz( x ); return log2_lut()[( x << lz >> 24 ) & 0x7f]; }
+float orc_log2_frac( uint32_t x ) { int lz = __builtin_clz( x ); return log2_lut()[( x << lz >> 24 ) & 0x7f]; }
+#define log2_frac orc_log2_frac
 float orc_log2( uint32_t x ) { return log2_frac( x ) + (float)( 31 - __builtin_clz( x ) ); }
 static float log2_int( uint32_t x ) { return (float)( 31 - __builtin_clz( x ) ); }
 

@@ -572,3 +572,33 @@ XREF_API int xref_encode_types( void *hv, const uint8_t *luma, int n, int *out_i
     free( chroma );
     return n_out;
 }
+
+/* ------------------------------------------------------------------ adaptive quantisation ------------ */
+/* x264_adaptive_quant_frame (encoder/ratecontrol.c:305-420) on an I420 picture, the way x264_encoder_encode prepares it
+ * (x264_frame_copy_picture -> x264_frame_expand_border_mod16 -> x264_adaptive_quant_frame, encoder.c:3382-3417).
+ * out: f_qp_offset_aq (float per MB), i_inv_qscale_factor (u16 per MB), stats[6] = i_pixel_sum[3], i_pixel_ssd[3] */
+XREF_API int xref_aq_frame( void *hv, const uint8_t *luma, const uint8_t *cb, const uint8_t *cr, float *qp_offset_aq,
+                            uint16_t *inv_qscale, uint64_t *stats )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = x264_frame_pop_unused( h, 0 );
+    if( !f ) return -1;
+    int w = h->param.i_width, ht = h->param.i_height;
+    x264_picture_t pic;
+    x264_picture_init( &pic );
+    pic.img.i_csp = X264_CSP_I420;
+    pic.img.i_plane = 3;
+    pic.img.plane[0] = (uint8_t*)luma; pic.img.i_stride[0] = w;
+    pic.img.plane[1] = (uint8_t*)cb;   pic.img.i_stride[1] = ( w + 1 ) / 2;
+    pic.img.plane[2] = (uint8_t*)cr;   pic.img.i_stride[2] = ( w + 1 ) / 2;
+    if( x264_frame_copy_picture( h, f, &pic ) < 0 ) return -1;
+    if( h->param.i_width != 16 * h->mb.i_mb_width || h->param.i_height != 16 * h->mb.i_mb_height )
+        x264_frame_expand_border_mod16( h, f );
+    x264_adaptive_quant_frame( h, f, NULL );
+    int n = h->mb.i_mb_count;
+    memcpy( qp_offset_aq, f->f_qp_offset_aq, n * sizeof(float) );
+    if( f->i_inv_qscale_factor ) memcpy( inv_qscale, f->i_inv_qscale_factor, n * sizeof(uint16_t) );
+    for( int i = 0; i < 3; i++ ) { stats[i] = f->i_pixel_sum[i]; stats[3+i] = f->i_pixel_ssd[i]; }
+    x264_frame_push_unused( h, f );
+    return 0;
+}
