@@ -822,6 +822,8 @@ struct x264cu_lookahead
     uint8_t *h_luma[2] = { nullptr, nullptr };   // pinned staging ring for pictures handed over in pageable memory
     cudaEvent_t h_luma_ev[2] = {};   // ... each guarded by the event of its last copy
     unsigned int h_luma_next = 0;
+    cudaStream_t mt_stream = nullptr;    // MB-tree stream (propagate / finish / their read-backs)
+    cudaEvent_t ev_mt_dep = nullptr, ev_mt_guard = nullptr;
     cudaStream_t xch_stream = nullptr;   // exchange stream: export / import of search results between GPUs (sharded stream)
     cudaStream_t up_stream = nullptr;    // upload stream: H2D copy, lowres planes and slot reset of a queued picture run beside the analysis
     cudaEvent_t ev_up_guard = nullptr;   // main-stream work queued before a put (it may still read the slot's previous picture)
@@ -877,6 +879,7 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     cudaStreamSynchronize( la->ctx->stream );
     if( la->up_stream ) cudaStreamSynchronize( la->up_stream );
     if( la->xch_stream ) cudaStreamSynchronize( la->xch_stream );
+    if( la->mt_stream ) cudaStreamSynchronize( la->mt_stream );
     for( int i = 0; i < 2; i++ ) if( la->search_streams[i] ) cudaStreamSynchronize( la->search_streams[i] );
     if( la->stats_on )
     {
@@ -905,10 +908,13 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     {
         auto &ax = la->ctx->aux_streams;
         for( size_t i = 0; i < ax.size(); )
-            if( ax[i] == la->up_stream || ax[i] == la->xch_stream || ax[i] == la->search_streams[0] || ax[i] == la->search_streams[1] ) ax.erase( ax.begin() + i ); else i++;
+            if( ax[i] == la->up_stream || ax[i] == la->xch_stream || ax[i] == la->mt_stream || ax[i] == la->search_streams[0] || ax[i] == la->search_streams[1] ) ax.erase( ax.begin() + i ); else i++;
     }
     if( la->up_stream ) { cudaStreamSynchronize( la->up_stream ); cudaStreamDestroy( la->up_stream ); }
     if( la->xch_stream ) { cudaStreamSynchronize( la->xch_stream ); cudaStreamDestroy( la->xch_stream ); }
+    if( la->mt_stream ) { cudaStreamSynchronize( la->mt_stream ); cudaStreamDestroy( la->mt_stream ); }
+    if( la->ev_mt_dep ) cudaEventDestroy( la->ev_mt_dep );
+    if( la->ev_mt_guard ) cudaEventDestroy( la->ev_mt_guard );
     for( int i = 0; i < 2; i++ ) { cudaFreeHost( la->h_luma[i] ); if( la->h_luma_ev[i] ) cudaEventDestroy( la->h_luma_ev[i] ); }
     if( la->ev_up_guard ) cudaEventDestroy( la->ev_up_guard );
     for( int i = 0; i < LA_ZC_DEPTH; i++ ) if( la->ev_zero_copy[i] ) cudaEventDestroy( la->ev_zero_copy[i] );
@@ -1002,6 +1008,9 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     }
     if( ok && cudaStreamCreateWithPriority( &la->up_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaStreamCreateWithPriority( &la->xch_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
+    if( ok && cudaStreamCreateWithPriority( &la->mt_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
+    if( ok && cudaEventCreateWithFlags( &la->ev_mt_dep, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
+    if( ok && cudaEventCreateWithFlags( &la->ev_mt_guard, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->ev_up_guard, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     for( int i = 0; i < LA_ZC_DEPTH; i++ )
         if( ok && cudaEventCreateWithFlags( &la->ev_zero_copy[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
@@ -1057,6 +1066,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     }
     ctx->aux_streams.push_back( la->up_stream );
     ctx->aux_streams.push_back( la->xch_stream );
+    ctx->aux_streams.push_back( la->mt_stream );
     for( int i = 0; i < 2; i++ ) ctx->aux_streams.push_back( la->search_streams[i] );
     *out = la;
     return 0;
@@ -1111,6 +1121,8 @@ static int la_put_begin( x264cu_lookahead *la, int slot )
     LaSlotHost &s = la->slots[slot];
     CU_CHECK( ctx, cudaEventRecord( la->ev_up_guard, ctx->stream ) );
     CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev_up_guard, 0 ) );
+    CU_CHECK( ctx, cudaEventRecord( la->ev_mt_guard, la->mt_stream ) );            // MB-tree work on the slot's previous picture
+    CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev_mt_guard, 0 ) );
     // a ring entry recorded again since belongs to a launch that had finished by then (search_batch waits before reuse)
     if( s.last_search_ev >= 0 && la->ev_seq[s.last_search_ev] == s.last_search_seq )
         CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev[s.last_search_ev], 0 ) );
@@ -1455,21 +1467,30 @@ static int la_weights_analyse( x264cu_lookahead *la, int fenc_slot, int ref_slot
 
 static int la_check_slot( x264cu_lookahead *la, int slot );
 
+// MB-tree runs on its own stream, off the chain of work the calling thread waits for in a cost request: it only has to come after
+// what is queued on the context's stream so far (the finalize of the triple it propagates, on-demand searches, the slots' uploads)
+static int la_mt_begin( x264cu_lookahead *la )
+{
+    CU_CHECK( la->ctx, cudaEventRecord( la->ev_mt_dep, la->ctx->stream ) );
+    CU_CHECK( la->ctx, cudaStreamWaitEvent( la->mt_stream, la->ev_mt_dep, 0 ) );
+    return 0;
+}
+
 /* ---- MB-tree (slicetype.c:1029-1184) ---- */
 int x264cu_lookahead_frame_set_qp_offset_aq( x264cu_lookahead_t *la, int slot, const float *h_aq )
 {
-    if( la_check_slot( la, slot ) ) return -1;
+    if( la_check_slot( la, slot ) || la_mt_begin( la ) ) return -1;
     x264cu_ctx *ctx = la->ctx;
     LaSlotHost &s = la->slots[slot];
     const size_t n = (size_t)la->d.mb_count * 4;
     if( h_aq )
     {
-        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qp_offset_aq, h_aq, n, cudaMemcpyHostToDevice, ctx->stream ) );
-        CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );             // the caller's array is free on return
+        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qp_offset_aq, h_aq, n, cudaMemcpyHostToDevice, la->mt_stream ) );
+        CU_CHECK( ctx, cudaStreamSynchronize( la->mt_stream ) );             // the caller's array is free on return
     }
     else
-        CU_CHECK( ctx, cudaMemsetAsync( s.dev.qp_offset_aq, 0, n, ctx->stream ) );
-    CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qp_offset, s.dev.qp_offset_aq, n, cudaMemcpyDeviceToDevice, ctx->stream ) );
+        CU_CHECK( ctx, cudaMemsetAsync( s.dev.qp_offset_aq, 0, n, la->mt_stream ) );
+    CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qp_offset, s.dev.qp_offset_aq, n, cudaMemcpyDeviceToDevice, la->mt_stream ) );
     return 0;
 }
 
@@ -1477,8 +1498,8 @@ int x264cu_lookahead_mbtree_reset( x264cu_lookahead_t *la, int slot )
 {
     if( !la ) return -1;
     if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use ) return x264cu_fail( la->ctx, "mbtree_reset: empty slot %d", slot );
-    if( la_slot_ready( la, slot ) ) return -1;
-    CU_CHECK( la->ctx, cudaMemsetAsync( la->slots[slot].dev.propagate, 0, (size_t)la->d.mb_count * 4, la->ctx->stream ) );
+    if( la_slot_ready( la, slot ) || la_mt_begin( la ) ) return -1;
+    CU_CHECK( la->ctx, cudaMemsetAsync( la->slots[slot].dev.propagate, 0, (size_t)la->d.mb_count * 4, la->mt_stream ) );
     return 0;
 }
 
@@ -1487,7 +1508,7 @@ int x264cu_lookahead_mbtree_swap( x264cu_lookahead_t *la, int slot_a, int slot_b
     if( !la ) return -1;
     for( int s : { slot_a, slot_b } )
         if( s < 0 || s >= (int)la->slots.size() || !la->slots[s].in_use ) return x264cu_fail( la->ctx, "mbtree_swap: empty slot %d", s );
-    if( la_slot_ready( la, slot_a ) || la_slot_ready( la, slot_b ) ) return -1;
+    if( la_slot_ready( la, slot_a ) || la_slot_ready( la, slot_b ) || la_mt_begin( la ) ) return -1;
     std::swap( la->slots[slot_a].dev.propagate, la->slots[slot_b].dev.propagate );
     return 0;
 }
@@ -1507,6 +1528,7 @@ int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames
     if( fb.cost_est[i0][i1] < 0 ) return x264cu_fail( ctx, "mbtree_propagate: the cost (%d,%d,%d) has not been requested", p0, p1, b );
     for( int s : { sb, s0, s1 } )
         if( la_slot_ready( la, s ) ) return -1;
+    if( la_mt_begin( la ) ) return -1;
     const int B1 = d.B + 1;
     LaMbtreeArgs A;
     memset( &A, 0, sizeof( A ) );
@@ -1525,8 +1547,8 @@ int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames
     A.fps_factor = fps_factor;
     if( referenced ) A.prop_in = fb.dev.propagate;
     else            // slicetype.c:1066-1067: the first row of the frame's own array is cleared and re-used as the all-zero input
-        CU_CHECK( ctx, cudaMemsetAsync( fb.dev.propagate, 0, (size_t)d.mb_w * 4, ctx->stream ) );
-    mbtree_propagate_kernel<<<( d.mb_count + 255 ) / 256, 256, 0, ctx->stream>>>( d, A );
+        CU_CHECK( ctx, cudaMemsetAsync( fb.dev.propagate, 0, (size_t)d.mb_w * 4, la->mt_stream ) );
+    mbtree_propagate_kernel<<<( d.mb_count + 255 ) / 256, 256, 0, la->mt_stream>>>( d, A );
     CU_LAUNCH_CHECK( ctx );
     return 0;
 }
@@ -1537,17 +1559,17 @@ int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_fa
     x264cu_ctx *ctx = la->ctx;
     if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use ) return x264cu_fail( ctx, "mbtree_finish: empty slot %d", slot );
     if( ref0_distance < 0 || ref0_distance > la->d.B + 1 ) return x264cu_fail( ctx, "mbtree_finish: bad distance %d", ref0_distance );
-    if( la_slot_ready( la, slot ) ) return -1;
+    if( la_slot_ready( la, slot ) || la_mt_begin( la ) ) return -1;
     LaSlotHost &f = la->slots[slot];
     if( !fps_factor )
     {   // lookahead-less intra case (slicetype.c:1121-1123): f_qp_offset = f_qp_offset_aq
-        CU_CHECK( ctx, cudaMemcpyAsync( f.dev.qp_offset, f.dev.qp_offset_aq, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToDevice, ctx->stream ) );
+        CU_CHECK( ctx, cudaMemcpyAsync( f.dev.qp_offset, f.dev.qp_offset_aq, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToDevice, la->mt_stream ) );
         return 0;
     }
     float weightdelta = 0.0f;
     if( ref0_distance && f.weighted_cost_delta[ref0_distance - 1] > 0 )
         weightdelta = ( 1.0 - f.weighted_cost_delta[ref0_distance - 1] );
-    mbtree_finish_kernel<<<( la->d.mb_count + 255 ) / 256, 256, 0, ctx->stream>>>( la->d.mb_count, f.dev.intra, f.dev.qscale, f.dev.propagate,
+    mbtree_finish_kernel<<<( la->d.mb_count + 255 ) / 256, 256, 0, la->mt_stream>>>( la->d.mb_count, f.dev.intra, f.dev.qscale, f.dev.propagate,
                                                                                   f.dev.qp_offset_aq, f.dev.qp_offset, fps_factor, weightdelta, strength );
     CU_LAUNCH_CHECK( ctx );
     return 0;
@@ -1555,18 +1577,18 @@ int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_fa
 
 int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *h_qp_offset )
 {
-    if( la_check_slot( la, slot ) ) return -1;
-    CU_CHECK( la->ctx, cudaMemcpyAsync( h_qp_offset, la->slots[slot].dev.qp_offset, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
-    CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
+    if( la_check_slot( la, slot ) || la_mt_begin( la ) ) return -1;
+    CU_CHECK( la->ctx, cudaMemcpyAsync( h_qp_offset, la->slots[slot].dev.qp_offset, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->mt_stream ) );
+    CU_CHECK( la->ctx, cudaStreamSynchronize( la->mt_stream ) );
     return 0;
 }
 
 int x264cu_lookahead_get_propagate_cost( x264cu_lookahead_t *la, int slot, uint16_t *h_out )
 {
-    if( la_check_slot( la, slot ) ) return -1;
+    if( la_check_slot( la, slot ) || la_mt_begin( la ) ) return -1;
     std::vector<unsigned int> tmp( la->d.mb_count );
-    CU_CHECK( la->ctx, cudaMemcpyAsync( tmp.data(), la->slots[slot].dev.propagate, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
-    CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
+    CU_CHECK( la->ctx, cudaMemcpyAsync( tmp.data(), la->slots[slot].dev.propagate, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->mt_stream ) );
+    CU_CHECK( la->ctx, cudaStreamSynchronize( la->mt_stream ) );
     for( int i = 0; i < la->d.mb_count; i++ ) h_out[i] = (uint16_t)( tmp[i] > 65535u ? 65535u : tmp[i] );
     return 0;
 }
