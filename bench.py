@@ -524,7 +524,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
 
     # ---- e2e: host pictures through the public entry point, H2D inside --------------------------------
     st = make_st()
-    st.set_async_upload(1)        # the pictures live in page-locked memory and are not touched while queued (as x264 holds its frames)
+    st.set_async_upload(4)        # the pictures live in page-locked memory and are not touched while queued (as x264 holds its frames)
     for i in range(n):
         st.step(frames[i])
     barrier(dist, local)
@@ -563,7 +563,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
                                 "sharded_stream: ONE stream over all GPUs" % gathered_streams},
         "clocks": clocks,
         "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
-                "d2h_bytes_per_step": int(32 * requests / args.steps), "api": "x264cu_slicetype_step (page-locked host luma read in place by the copy engine on the upload stream, async_upload=1)"},
+                "d2h_bytes_per_step": int(32 * requests / args.steps), "api": "x264cu_slicetype_step (page-locked host luma read in place by the copy engine on the upload stream, async_upload=4)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

@@ -221,9 +221,9 @@ int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t 
 /* How h_luma is read.  Pageable memory is staged through the library's own pinned ring (the caller's buffer is free on
  * return).  Page-locked memory (x264cu_malloc_host; the reference stages through page-locked buffers too, opencl.h:718) is
  * read in place by the copy engine on the lookahead's upload stream: with async_upload = 0 (default) the call returns once
- * that copy has finished; with async_upload = 1 it returns at once and the buffer must stay unmodified until FOUR more
- * pictures have been queued on this lookahead (or x264cu_sync) -- x264 itself holds a queued x264_frame_t much longer:
- * its planes are untouched until the frame leaves the lookahead. */
+ * that copy has finished; with async_upload = N > 0 it returns at once, up to N copies are in flight (1 means 4, at most 32)
+ * and the buffer must stay unmodified until N more pictures have been queued on this lookahead (or x264cu_sync) -- x264 itself
+ * holds a queued x264_frame_t much longer: its planes are untouched until the frame leaves the lookahead. */
 void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on );
 /* same with the luma already in HBM */
 int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const uint8_t *d_luma, intptr_t luma_stride,
@@ -353,7 +353,7 @@ void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *st, int prefetch );
  * decisions do not change -- only the searches of the newest pictures get time to finish on the second stream. */
 void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *st, int pictures );
 /* x264cu_lookahead_set_async_upload for the lookahead underneath: page-locked pictures are read in place and must stay
- * unmodified until four more pictures have been queued */
+ * unmodified until `on` more pictures have been queued (1 means 4) */
 void x264cu_slicetype_set_async_upload( x264cu_slicetype_t *st, int on );
 /* Sharded stream: this process is rank `rank` of `world` GPUs that are all fed the SAME pictures.  Every rank runs the same
  * decisions; of each prefetch group it searches only the pairs whose searched picture has display index % world == rank, and

@@ -806,6 +806,7 @@ struct LaSlotHost
     cudaEvent_t ev_ready = nullptr;  // recorded on the upload stream when the picture's planes / reset arrays are in place
     bool main_waited = true;         // the context's stream has been ordered after ev_ready
     bool xch_dirty = false;
+    unsigned long long mt_last = 0;  // sequence number of the last MB-tree operation that touched this slot's arrays
 };
 
 struct x264cu_lookahead
@@ -823,15 +824,20 @@ struct x264cu_lookahead
     cudaEvent_t h_luma_ev[2] = {};   // ... each guarded by the event of its last copy
     unsigned int h_luma_next = 0;
     cudaStream_t mt_stream = nullptr;    // MB-tree stream (propagate / finish / their read-backs)
-    cudaEvent_t ev_mt_dep = nullptr, ev_mt_guard = nullptr;
+    cudaEvent_t ev_mt_dep = nullptr;
+    // checkpoints on the MB-tree stream: an upload into a slot waits for the first one recorded after the last MB-tree operation
+    // that touched the slot (long complete in steady state), not for whatever MB-tree work happens to be queued
+    cudaEvent_t ev_mt_ckpt[32] = {};
+    unsigned long long mt_ckpt_seq[32] = {}, mt_seq = 0;
+    unsigned int mt_ckpt_next = 0;
     cudaStream_t xch_stream = nullptr;   // exchange stream: export / import of search results between GPUs (sharded stream)
     cudaStream_t up_stream = nullptr;    // upload stream: H2D copy, lowres planes and slot reset of a queued picture run beside the analysis
     cudaEvent_t ev_up_guard = nullptr;   // main-stream work queued before a put (it may still read the slot's previous picture)
-#define LA_ZC_DEPTH 4
+#define LA_ZC_DEPTH 32
     cudaEvent_t ev_zero_copy[LA_ZC_DEPTH] = {};  // the last copies that read the caller's own page-locked buffers (ring)
     bool zero_copy_live[LA_ZC_DEPTH] = {};
     unsigned int zc_next = 0;
-    bool async_upload = false;           // x264cu_lookahead_set_async_upload
+    int async_upload = 0;                // x264cu_lookahead_set_async_upload: page-locked uploads in flight (0 = wait for each)
     bool search_attr_set = false;
     struct XchMark { int slot, list, dm1; };
     std::vector<XchMark> xch_marks;      // searches imported since the last x264cu_lookahead_import_done
@@ -914,7 +920,7 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     if( la->xch_stream ) { cudaStreamSynchronize( la->xch_stream ); cudaStreamDestroy( la->xch_stream ); }
     if( la->mt_stream ) { cudaStreamSynchronize( la->mt_stream ); cudaStreamDestroy( la->mt_stream ); }
     if( la->ev_mt_dep ) cudaEventDestroy( la->ev_mt_dep );
-    if( la->ev_mt_guard ) cudaEventDestroy( la->ev_mt_guard );
+    for( int i = 0; i < 32; i++ ) if( la->ev_mt_ckpt[i] ) cudaEventDestroy( la->ev_mt_ckpt[i] );
     for( int i = 0; i < 2; i++ ) { cudaFreeHost( la->h_luma[i] ); if( la->h_luma_ev[i] ) cudaEventDestroy( la->h_luma_ev[i] ); }
     if( la->ev_up_guard ) cudaEventDestroy( la->ev_up_guard );
     for( int i = 0; i < LA_ZC_DEPTH; i++ ) if( la->ev_zero_copy[i] ) cudaEventDestroy( la->ev_zero_copy[i] );
@@ -1010,7 +1016,8 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     if( ok && cudaStreamCreateWithPriority( &la->xch_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaStreamCreateWithPriority( &la->mt_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->ev_mt_dep, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
-    if( ok && cudaEventCreateWithFlags( &la->ev_mt_guard, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
+    for( int i = 0; i < 32; i++ )
+        if( ok && cudaEventCreateWithFlags( &la->ev_mt_ckpt[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->ev_up_guard, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     for( int i = 0; i < LA_ZC_DEPTH; i++ )
         if( ok && cudaEventCreateWithFlags( &la->ev_zero_copy[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
@@ -1121,8 +1128,20 @@ static int la_put_begin( x264cu_lookahead *la, int slot )
     LaSlotHost &s = la->slots[slot];
     CU_CHECK( ctx, cudaEventRecord( la->ev_up_guard, ctx->stream ) );
     CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev_up_guard, 0 ) );
-    CU_CHECK( ctx, cudaEventRecord( la->ev_mt_guard, la->mt_stream ) );            // MB-tree work on the slot's previous picture
-    CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev_mt_guard, 0 ) );
+    if( s.mt_last )
+    {   // MB-tree work on the slot's previous picture
+        int best = -1;
+        for( int i = 0; i < 32; i++ )
+            if( la->mt_ckpt_seq[i] >= s.mt_last && ( best < 0 || la->mt_ckpt_seq[i] < la->mt_ckpt_seq[best] ) ) best = i;
+        if( best < 0 )
+        {
+            best = la->mt_ckpt_next++ & 31;
+            CU_CHECK( ctx, cudaEventRecord( la->ev_mt_ckpt[best], la->mt_stream ) );
+            la->mt_ckpt_seq[best] = la->mt_seq;
+        }
+        CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev_mt_ckpt[best], 0 ) );
+        s.mt_last = 0;
+    }
     // a ring entry recorded again since belongs to a launch that had finished by then (search_batch waits before reuse)
     if( s.last_search_ev >= 0 && la->ev_seq[s.last_search_ev] == s.last_search_seq )
         CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev[s.last_search_ev], 0 ) );
@@ -1178,7 +1197,10 @@ int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const u
     return la_put_finish( la, slot, d_luma, luma_stride, h_inv_qscale );
 }
 
-void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on ) { if( la ) la->async_upload = on != 0; }
+void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on )
+{
+    if( la ) la->async_upload = on <= 0 ? 0 : on == 1 ? 4 : on > LA_ZC_DEPTH ? LA_ZC_DEPTH : on;
+}
 
 int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
                                 const uint16_t *h_inv_qscale )
@@ -1188,7 +1210,7 @@ int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t 
     if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( ctx, "frame_put: slot %d out of range", slot );
     const int w = la->p.width, h = la->p.height;
     const intptr_t st = ( w + 63 ) & ~63;
-    const int zc = la->zc_next++ % LA_ZC_DEPTH;
+    const int zc = la->zc_next++ % ( la->async_upload ? la->async_upload : 1 );
     if( la->zero_copy_live[zc] )
     {   // the picture queued LA_ZC_DEPTH calls ago was read in place: that copy ended long ago in steady state
         LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->ev_zero_copy[zc] ) ) );
@@ -1469,6 +1491,20 @@ static int la_check_slot( x264cu_lookahead *la, int slot );
 
 // MB-tree runs on its own stream, off the chain of work the calling thread waits for in a cost request: it only has to come after
 // what is queued on the context's stream so far (the finalize of the triple it propagates, on-demand searches, the slots' uploads)
+// after an MB-tree operation has been enqueued: note which slots it touched, drop a checkpoint every 8 operations
+static int la_mt_end( x264cu_lookahead *la, std::initializer_list<int> slots )
+{
+    la->mt_seq++;
+    for( int sl : slots ) la->slots[sl].mt_last = la->mt_seq;
+    if( !( la->mt_seq & 7 ) )
+    {
+        const int i = la->mt_ckpt_next++ & 31;
+        CU_CHECK( la->ctx, cudaEventRecord( la->ev_mt_ckpt[i], la->mt_stream ) );
+        la->mt_ckpt_seq[i] = la->mt_seq;
+    }
+    return 0;
+}
+
 static int la_mt_begin( x264cu_lookahead *la )
 {
     CU_CHECK( la->ctx, cudaEventRecord( la->ev_mt_dep, la->ctx->stream ) );
@@ -1491,7 +1527,7 @@ int x264cu_lookahead_frame_set_qp_offset_aq( x264cu_lookahead_t *la, int slot, c
     else
         CU_CHECK( ctx, cudaMemsetAsync( s.dev.qp_offset_aq, 0, n, la->mt_stream ) );
     CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qp_offset, s.dev.qp_offset_aq, n, cudaMemcpyDeviceToDevice, la->mt_stream ) );
-    return 0;
+    return la_mt_end( la, { slot } );
 }
 
 int x264cu_lookahead_mbtree_reset( x264cu_lookahead_t *la, int slot )
@@ -1500,7 +1536,7 @@ int x264cu_lookahead_mbtree_reset( x264cu_lookahead_t *la, int slot )
     if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use ) return x264cu_fail( la->ctx, "mbtree_reset: empty slot %d", slot );
     if( la_slot_ready( la, slot ) || la_mt_begin( la ) ) return -1;
     CU_CHECK( la->ctx, cudaMemsetAsync( la->slots[slot].dev.propagate, 0, (size_t)la->d.mb_count * 4, la->mt_stream ) );
-    return 0;
+    return la_mt_end( la, { slot } );
 }
 
 int x264cu_lookahead_mbtree_swap( x264cu_lookahead_t *la, int slot_a, int slot_b )
@@ -1510,7 +1546,7 @@ int x264cu_lookahead_mbtree_swap( x264cu_lookahead_t *la, int slot_a, int slot_b
         if( s < 0 || s >= (int)la->slots.size() || !la->slots[s].in_use ) return x264cu_fail( la->ctx, "mbtree_swap: empty slot %d", s );
     if( la_slot_ready( la, slot_a ) || la_slot_ready( la, slot_b ) || la_mt_begin( la ) ) return -1;
     std::swap( la->slots[slot_a].dev.propagate, la->slots[slot_b].dev.propagate );
-    return 0;
+    return la_mt_end( la, { slot_a, slot_b } );
 }
 
 int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int referenced, float fps_factor )
@@ -1550,7 +1586,7 @@ int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames
         CU_CHECK( ctx, cudaMemsetAsync( fb.dev.propagate, 0, (size_t)d.mb_w * 4, la->mt_stream ) );
     mbtree_propagate_kernel<<<( d.mb_count + 255 ) / 256, 256, 0, la->mt_stream>>>( d, A );
     CU_LAUNCH_CHECK( ctx );
-    return 0;
+    return la_mt_end( la, { sb, s0, s1 } );
 }
 
 int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_factor, int ref0_distance, float strength )
@@ -1564,7 +1600,7 @@ int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_fa
     if( !fps_factor )
     {   // lookahead-less intra case (slicetype.c:1121-1123): f_qp_offset = f_qp_offset_aq
         CU_CHECK( ctx, cudaMemcpyAsync( f.dev.qp_offset, f.dev.qp_offset_aq, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToDevice, la->mt_stream ) );
-        return 0;
+        return la_mt_end( la, { slot } );
     }
     float weightdelta = 0.0f;
     if( ref0_distance && f.weighted_cost_delta[ref0_distance - 1] > 0 )
@@ -1572,7 +1608,7 @@ int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_fa
     mbtree_finish_kernel<<<( la->d.mb_count + 255 ) / 256, 256, 0, la->mt_stream>>>( la->d.mb_count, f.dev.intra, f.dev.qscale, f.dev.propagate,
                                                                                   f.dev.qp_offset_aq, f.dev.qp_offset, fps_factor, weightdelta, strength );
     CU_LAUNCH_CHECK( ctx );
-    return 0;
+    return la_mt_end( la, { slot } );
 }
 
 int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *h_qp_offset )
