@@ -61,7 +61,14 @@ XREF_API void *xref_open( int width, int height, const char *preset, const char 
     return x264_encoder_open( &param, NULL );
 }
 
-XREF_API void xref_close( void *hv ) { if( hv ) x264_encoder_close( (x264_t*)hv ); }
+static x264_frame_t *me_frame;
+static x264_t *me_frame_h;
+XREF_API void xref_close( void *hv )
+{
+    if( !hv ) return;
+    if( me_frame_h == hv ) { me_frame = NULL; me_frame_h = NULL; }      /* the cached frame dies with its encoder */
+    x264_encoder_close( (x264_t*)hv );
+}
 
 XREF_API int xref_param( void *hv, const char *name )
 {
@@ -312,15 +319,27 @@ XREF_API void xref_me_search( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr
 /* ESA / TESA read the reference frame's integral image (me.c:636-760), which x264_frame_filter builds when the encoder was
  * opened with me=esa|tesa: here the search runs against a reference frame the reference builds itself from ref_luma
  * (picture-sized, mod 16); (bx, by) = position of the block.  The frame is kept until ref_luma changes. */
+static x264_frame_t *me_frame;           /* the reference frame xref_me_search_frame built last; dropped when its encoder closes */
+static const uint8_t *me_frame_src;
+static x264_t *me_frame_h;
+static uint64_t me_frame_hash;
+
 XREF_API int xref_me_search_frame( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
                                    const uint8_t *ref_luma, intptr_t ref_stride, int bx, int by )
 {
     x264_t *h = hv;
-    static x264_frame_t *f;
-    static const uint8_t *f_src;
-    static x264_t *f_h;
-    if( !f || f_src != ref_luma || f_h != h )
+#define f me_frame
+#define f_src me_frame_src
+#define f_h me_frame_h
+#define f_hash me_frame_hash
+    /* the cached frame is identified by the content, not by the address (buffers get recycled at the same address) */
+    uint64_t hash = 1469598103934665603ull;
+    for( int y = 0; y < h->mb.i_mb_height*16; y++ )
+        for( int x = 0; x < h->mb.i_mb_width*16; x++ )
+            hash = ( hash ^ ref_luma[y*ref_stride + x] ) * 1099511628211ull;
+    if( !f || f_src != ref_luma || f_h != h || f_hash != hash )
     {
+        f_hash = hash;
         if( f && f_h == h ) x264_frame_push_unused( h, f );
         f = x264_frame_pop_unused( h, 1 );
         if( !f ) return -1;
@@ -347,6 +366,10 @@ XREF_API int xref_me_search_frame( void *hv, xref_me_args_t *a, uint8_t *fenc, i
                       f->filtered[0][3] + off, f->filtered[0][0] + off, st, f->integral + off );
     h->fenc = save;
     return 0;
+#undef f
+#undef f_src
+#undef f_h
+#undef f_hash
 }
 
 XREF_API void xref_cost_mv_table_qp( void *hv, int qp, uint16_t *out, int len )
