@@ -172,13 +172,14 @@ int x264cu_weight_scale_plane( x264cu_ctx_t *ctx, const uint8_t *d_src, uint8_t 
 int x264cu_pixel_ssd_wxh( x264cu_ctx_t *ctx, const uint8_t *d_pix1, intptr_t stride1, const uint8_t *d_pix2, intptr_t stride2,
                           int width, int height, uint64_t *h_ssd );
 
-/* x264_adaptive_quant_frame( h, frame, NULL ) (encoder/ratecontrol.c:305-420), aq-mode 0 / 1: per macroblock the AC energy of
+/* x264_adaptive_quant_frame( h, frame, NULL ) (encoder/ratecontrol.c:305-420), aq-mode 0 - 3: per macroblock the AC energy of
  * the 16x16 luma block and the two 8x8 chroma blocks (ac_energy_mb), f_qp_offset_aq = aq_strength * 1.0397 * (x264_log2(energy)
  * - 14.427) and i_inv_qscale_factor = x264_exp2fix8 of it -- the two per-macroblock inputs of the lookahead (frame_put's
  * h_inv_qscale, frame_set_qp_offset_aq) -- from an I420 picture in HBM (luma width x height, Cb / Cr (width+1)/2 x (height+1)/2),
  * treated as edge-replicated to the macroblock grid.  Outputs stay on the device (mb_count entries each); h_stats (optional,
  * synchronises) = i_pixel_sum[3], i_pixel_ssd[3] as the function leaves them.  aq-mode 0 gives offsets 0 / factors 256, which is
- * what the reference initialises for MB-tree.  The auto-variance modes (2, 3) are not built. */
+ * what the reference initialises for MB-tree.  Modes 2 / 3 (auto-variance): qp = (energy+1)^(1/8) recentred on its frame mean,
+ * which is summed in single precision in the reference's raster order (one device thread) so that the result is bit-identical. */
 int x264cu_adaptive_quant_frame( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, const uint8_t *d_cb, const uint8_t *d_cr,
                                  intptr_t chroma_stride, int width, int height, int aq_mode, float aq_strength,
                                  float *d_qp_offset_aq, uint16_t *d_inv_qscale, uint64_t *h_stats );

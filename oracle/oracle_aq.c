@@ -2,7 +2,9 @@
  * x264_adaptive_quant_frame with aq-mode 0 / 1 (encoder/ratecontrol.c:225-420): per-macroblock AC energy of luma and both chroma
  * planes (ac_energy_mb, :261-303; pixel_var, common/pixel.c:183-203), f_qp_offset_aq = strength * (x264_log2(energy) - 14.427)
  * (:397), i_inv_qscale_factor = x264_exp2fix8( qp ) (common/base.h:218-224), frame sums i_pixel_sum / i_pixel_ssd (:405-414).
- * The auto-variance modes (2, 3) are not restated.  Pinned against the compiled reference by tests/test_oracle_aq.py.
+ * Auto-variance modes 2 / 3 (:352-392): qp = (energy+1)^(1/8), frame means of qp and qp^2 accumulated in raster order in single
+ * precision -- in the form the reference's -ffast-math build computes them (powf(x, .125f) = three square roots, qp*qp taken
+ * from the second one; disassembly of oracle/_ref).  Pinned against the compiled reference by tests/test_oracle_aq.py.
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use this file. */
 #include "oracle.h"
 #include <math.h>
@@ -49,7 +51,29 @@ void orc_adaptive_quant_frame( const uint8_t *luma, intptr_t stride, const uint8
     const int cw = ( width + 1 ) >> 1, ch = ( height + 1 ) >> 1;
     uint64_t sum[3] = { 0, 0, 0 }, ssd[3] = { 0, 0, 0 };
     const int active = aq_mode != 0 && aq_strength != 0;
-    const float strength = aq_strength * 1.0397f;
+    float strength = aq_strength * 1.0397f, avg_adj = 0.f, bias_strength = 0.f;
+    if( active && aq_mode >= 2 )
+    {   /* first pass, ratecontrol.c:352-372 */
+        uint64_t dsum[3] = { 0, 0, 0 }, dssd[3] = { 0, 0, 0 };           /* the statistics are accumulated by the second pass */
+        float avg_adj_pow2 = 0.f;
+        for( int mb_y = 0; mb_y < mb_h; mb_y++ )
+            for( int mb_x = 0; mb_x < mb_w; mb_x++ )
+            {
+                uint32_t energy = energy_block( luma, stride, 16*mb_x, 16*mb_y, 16, 16, width, height, 8, &dsum[0], &dssd[0] );
+                energy += energy_block( cb, cstride, 8*mb_x, 8*mb_y, 8, 8, cw, ch, 6, &dsum[1], &dssd[1] );
+                energy += energy_block( cr, cstride, 8*mb_x, 8*mb_y, 8, 8, cw, ch, 6, &dsum[2], &dssd[2] );
+                float q4 = sqrtf( sqrtf( (float)energy + 1.f ) );         /* (energy+1)^(1/4) = qp_adj * qp_adj under -ffast-math */
+                float qp = sqrtf( q4 );                                   /* powf( energy + 1, 0.125f ) */
+                qp_offset_aq[mb_x + mb_y * mb_w] = qp;
+                avg_adj += qp;
+                avg_adj_pow2 += q4;
+            }
+        avg_adj /= (float)( mb_w * mb_h );
+        avg_adj_pow2 /= (float)( mb_w * mb_h );
+        strength = avg_adj * aq_strength;
+        avg_adj = ( 0.5f * ( 14.f - avg_adj_pow2 ) ) / avg_adj + avg_adj;  /* avg_adj - 0.5f * (avg_adj_pow2 - 14.f) / avg_adj */
+        bias_strength = aq_strength;
+    }
     for( int mb_y = 0; mb_y < mb_h; mb_y++ )
         for( int mb_x = 0; mb_x < mb_w; mb_x++ )
         {
@@ -58,7 +82,14 @@ void orc_adaptive_quant_frame( const uint8_t *luma, intptr_t stride, const uint8
             energy += energy_block( cr, cstride, 8*mb_x, 8*mb_y, 8, 8, cw, ch, 6, &sum[2], &ssd[2] );
             const int mb = mb_x + mb_y * mb_w;
             float qp_adj = 0.f;
-            if( active )
+            if( active && aq_mode == 3 )
+            {
+                float qp = qp_offset_aq[mb];
+                qp_adj = ( qp - avg_adj ) * strength + ( 1.f - 14.f / ( qp * qp ) ) * bias_strength;
+            }
+            else if( active && aq_mode == 2 )
+                qp_adj = ( qp_offset_aq[mb] - avg_adj ) * strength;
+            else if( active )
             {   /* strength * (x264_log2(energy) - 14.427f) in the association the -ffast-math build of the reference uses
                  * (disassembly of oracle/_ref, ratecontrol.c:397): (integer part - 14.427) + table entry */
                 uint32_t e = energy > 1 ? energy : 1;

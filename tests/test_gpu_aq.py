@@ -34,7 +34,8 @@ def gpu_aq(ctx, luma, cb, cr, mode, strength):
     return q, i, stats
 
 
-@pytest.mark.parametrize("cfg", [((112, 80), 1, 1.0), ((100, 52), 1, 1.4), ((96, 64), 0, 1.0), ((1918, 1078), 1, 0.6), ((3840, 2160), 1, 1.0)])
+@pytest.mark.parametrize("cfg", [((112, 80), 1, 1.0), ((100, 52), 1, 1.4), ((96, 64), 0, 1.0), ((1918, 1078), 1, 0.6), ((3840, 2160), 1, 1.0),
+                                 ((112, 80), 2, 1.0), ((100, 52), 3, 1.3), ((640, 360), 2, 0.8), ((1920, 1080), 3, 1.0)])
 def test_adaptive_quant_frame(ctx, cfg):
     (w, h), mode, strength = cfg
     o, _ = bind() if have_ref() else (oracle(), None)

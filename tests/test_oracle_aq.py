@@ -30,7 +30,8 @@ def bind():
 
 
 @pytest.mark.parametrize("cfg", [((112, 80), "aq-mode=1"), ((100, 52), "aq-mode=1:aq-strength=1.4"), ((96, 64), "aq-mode=0"),
-                                 ((640, 360), "aq-mode=1:aq-strength=0.6")])
+                                 ((640, 360), "aq-mode=1:aq-strength=0.6"), ((112, 80), "aq-mode=2"), ((100, 52), "aq-mode=3:aq-strength=1.3"),
+                                 ((640, 360), "aq-mode=2:aq-strength=0.8"), ((640, 360), "aq-mode=3")])
 def test_adaptive_quant_matches_reference(cfg):
     (w, h), opts = cfg
     o, r = bind()
@@ -43,7 +44,7 @@ def test_adaptive_quant_matches_reference(cfg):
         ia, ib = np.zeros(nmb, np.uint16), np.zeros(nmb, np.uint16)
         sa, sb = np.zeros(6, np.uint64), np.zeros(6, np.uint64)
         assert r.xref_aq_frame(hnd, ptr(luma), ptr(cb), ptr(cr), ptr(qa), ptr(ia), ptr(sa)) == 0
-        mode = 0 if "aq-mode=0" in opts else 1
+        mode = int(opts.split("aq-mode=")[1][0])
         strength = float(opts.split("aq-strength=")[1]) if "aq-strength" in opts else 1.0
         o.orc_adaptive_quant_frame(ptr(luma), w, ptr(cb), ptr(cr), (w + 1) // 2, w, h, mode, strength, ptr(qb), ptr(ib), ptr(sb))
         assert np.array_equal(sa, sb), (sa, sb)

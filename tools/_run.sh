@@ -1,10 +1,6 @@
-mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py > gpurun_out/b_default.json 2> gpurun_out/b_default.err; tail -c 300 gpurun_out/b_default.err
-timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b_ref.json 2> gpurun_out/b_ref.err
-timeout 400 python bench.py --workload lookahead --weightp 1 > gpurun_out/b_la_w.json 2> gpurun_out/b_la_w.err
-python -c "
-import json
-for f in ('b_default','b_ref','b_la_w'):
-    d=json.load(open('gpurun_out/%s.json'%f)); print(f, round(d['value'],1), round(d['e2e']['value'],1), (d.get('cpu_baseline') or {}).get('value'), d.get('roofline',{}).get('share_of_step'), d.get('gpu_launches'))
-"
+L=$PWD/x264_b200/csrc
+timeout 600 python -m pytest tests/test_gpu_aq.py -x -q 2>&1 | tail -2
+for v in "" _nw10 _nw12; do
+ X264CU_LIB=$L/libx264_b200$v.so timeout 300 python bench.py --workload lookahead --quick --steps 10 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); r=d['roofline']; print('lib$v', round(d['value'],1), round(d['e2e']['value'],1), round(r['ms_per_launch'],2), round(r['share_of_step'],2))"
+done
+for v in _nw10 _nw12; do X264CU_LIB=$L/libx264_b200$v.so timeout 600 python -m pytest tests/test_gpu_lookahead.py tests/test_gpu_slicetype.py -x -q 2>&1 | tail -1; done

@@ -1,10 +1,13 @@
-// x264_adaptive_quant_frame (encoder/ratecontrol.c:225-420), aq-mode 0 / 1: the producer of the lookahead's per-macroblock inputs
+// x264_adaptive_quant_frame (encoder/ratecontrol.c:225-420), aq-mode 0 - 3: the producer of the lookahead's per-macroblock inputs
 // fenc->i_inv_qscale_factor / f_qp_offset_aq and of the frame statistics the lookahead weight analysis reads.
 //   ac_energy_mb (:261-303) = pixel_var of the 16x16 luma block and of the two 8x8 chroma blocks (common/pixel.c:183-203),
 //   f_qp_offset_aq = strength * (x264_log2( max(energy,1) ) - 14.427) (:397), i_inv_qscale_factor = x264_exp2fix8 (base.h:218-224).
 // One warp per macroblock: every lane sums 8 luma pixels (dp4a with ones / with itself), lanes 0-15 / 16-31 four pixels of Cb / Cr;
 // xor-shuffle reductions; lane 0 does the float step operation by operation in the order the reference's -ffast-math build uses
 // (see DESIGN.md section 2).  Pure streaming: 1.5 bytes read per pixel, 6 bytes written per macroblock.
+// The auto-variance modes (2, 3; :352-392) need the frame means of qp = (energy+1)^(1/8) and of qp^2, which the reference sums in
+// single precision in raster order: aq_means_kernel does exactly that, one thread, sequentially (65 us at 4K, once per picture,
+// beside the lookahead) -- a parallel reduction would round differently -- and aq_final_kernel applies them per macroblock.
 #include "ctx.h"
 #include <math.h>
 
@@ -17,8 +20,9 @@ __device__ __forceinline__ int clampi( int v, int lo, int hi ) { return min( max
 
 __global__ void __launch_bounds__( 256 )
 aq_kernel( const uint8_t *__restrict__ luma, intptr_t stride, const uint8_t *__restrict__ cb, const uint8_t *__restrict__ cr,
-           intptr_t cstride, int width, int height, int mb_w, int mb_count, int active, float strength,
-           float *__restrict__ qp_offset_aq, uint16_t *__restrict__ inv_qscale, unsigned long long *__restrict__ stats )
+           intptr_t cstride, int width, int height, int mb_w, int mb_count, int active, int aq_mode, float strength,
+           float *__restrict__ qp_offset_aq, uint16_t *__restrict__ inv_qscale, float *__restrict__ q4_out,
+           unsigned long long *__restrict__ stats )
 {
     const int lane = threadIdx.x & 31;
     const int mb = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
@@ -71,7 +75,14 @@ aq_kernel( const uint8_t *__restrict__ luma, intptr_t stride, const uint8_t *__r
         energy += sqr[2] - (unsigned)( (unsigned long long)sum[2] * sum[2] >> 6 );
         float qp_adj = 0.f;
         unsigned q = 256;
-        if( active )
+        if( active && aq_mode >= 2 )
+        {   // first pass of the auto-variance modes: powf( energy + 1, 0.125f ) as the reference's -ffast-math build computes it,
+            // three correctly rounded square roots; the second one doubles as qp * qp in the frame mean
+            const float q4 = __fsqrt_rn( __fsqrt_rn( __fadd_rn( __uint2float_rn( energy ), 1.f ) ) );
+            qp_adj = __fsqrt_rn( q4 );
+            q4_out[mb] = q4;
+        }
+        else if( active )
         {
             const unsigned e = max( energy, 1u );
             const int lz = __clz( e );
@@ -93,6 +104,37 @@ aq_kernel( const uint8_t *__restrict__ luma, intptr_t stride, const uint8_t *__r
     }
 }
 
+// avg_adj / avg_adj_pow2 of ratecontrol.c:352-372, summed in the reference's order; out = { avg_adj (final), strength }
+__global__ void aq_means_kernel( const float *__restrict__ qp, const float *__restrict__ q4, int mb_count, float aq_strength, float *out )
+{
+    if( threadIdx.x || blockIdx.x ) return;
+    float avg = 0.f, pow2 = 0.f;
+    for( int i = 0; i < mb_count; i++ )
+    {
+        avg = __fadd_rn( avg, qp[i] );
+        pow2 = __fadd_rn( pow2, q4[i] );
+    }
+    avg = __fdiv_rn( avg, (float)mb_count );
+    pow2 = __fdiv_rn( pow2, (float)mb_count );
+    out[1] = __fmul_rn( avg, aq_strength );
+    out[0] = __fadd_rn( __fdiv_rn( __fmul_rn( 0.5f, __fsub_rn( 14.f, pow2 ) ), avg ), avg );
+}
+
+__global__ void __launch_bounds__( 256 )
+aq_final_kernel( int mb_count, int aq_mode, float bias_strength, const float *__restrict__ means, float *__restrict__ qp_offset_aq,
+                 uint16_t *__restrict__ inv_qscale )
+{
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if( mb >= mb_count ) return;
+    const float avg = means[0], strength = means[1], qp = qp_offset_aq[mb];
+    float qp_adj = __fmul_rn( __fsub_rn( qp, avg ), strength );
+    if( aq_mode == 3 )
+        qp_adj = __fadd_rn( qp_adj, __fmul_rn( __fsub_rn( 1.f, __fdiv_rn( 14.f, __fmul_rn( qp, qp ) ) ), bias_strength ) );
+    const int i = __float2int_rz( __fadd_rn( __fmul_rn( qp_adj, -64.f / 6.f ), 512.5f ) );
+    qp_offset_aq[mb] = qp_adj;
+    inv_qscale[mb] = (uint16_t)( i < 0 ? 0u : i > 1023 ? 0xffffu : ( ( (unsigned)c_aq_exp2_lut[i & 63] + 256u ) << ( i >> 6 ) ) >> 8 );
+}
+
 } // namespace
 
 extern "C" int x264cu_adaptive_quant_frame( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, const uint8_t *d_cb,
@@ -102,8 +144,8 @@ extern "C" int x264cu_adaptive_quant_frame( x264cu_ctx_t *ctx, const uint8_t *d_
     if( !ctx ) return -1;
     if( !d_luma || !d_cb || !d_cr || !d_qp_offset_aq || !d_inv_qscale || width < 1 || height < 1 )
         return x264cu_fail( ctx, "adaptive_quant_frame: bad arguments" );
-    if( aq_mode < 0 || aq_mode > 1 )
-        return x264cu_fail( ctx, "adaptive_quant_frame: aq-mode %d not supported (the auto-variance modes are outside this backend)", aq_mode );
+    if( aq_mode < 0 || aq_mode > 3 )
+        return x264cu_fail( ctx, "adaptive_quant_frame: aq-mode %d out of range", aq_mode );
     if( !ctx->aq_tables )
     {
         float l2[128];
@@ -128,9 +170,22 @@ extern "C" int x264cu_adaptive_quant_frame( x264cu_ctx_t *ctx, const uint8_t *d_
         CU_CHECK( ctx, cudaMemsetAsync( d_stats, 0, 48, ctx->stream ) );
     }
     const int active = aq_mode != 0 && aq_strength != 0.f;
+    float *d_q4 = nullptr;
+    if( active && aq_mode >= 2 )
+    {   // scratch: (energy+1)^(1/4) per macroblock, then the two frame-level scalars
+        d_q4 = (float *)x264cu_scratch( ctx, 8, (size_t)( mb_count + 2 ) * 4 );
+        if( !d_q4 ) return -1;
+    }
     aq_kernel<<<( mb_count + 7 ) / 8, 256, 0, ctx->stream>>>( d_luma, luma_stride, d_cb, d_cr, chroma_stride, width, height, mb_w, mb_count,
-                                                              active, aq_strength * 1.0397f, d_qp_offset_aq, d_inv_qscale, d_stats );
+                                                              active, aq_mode, aq_strength * 1.0397f, d_qp_offset_aq, d_inv_qscale, d_q4, d_stats );
     CU_LAUNCH_CHECK( ctx );
+    if( d_q4 )
+    {
+        aq_means_kernel<<<1, 32, 0, ctx->stream>>>( d_qp_offset_aq, d_q4, mb_count, aq_strength, d_q4 + mb_count );
+        CU_LAUNCH_CHECK( ctx );
+        aq_final_kernel<<<( mb_count + 255 ) / 256, 256, 0, ctx->stream>>>( mb_count, aq_mode, aq_strength, d_q4 + mb_count, d_qp_offset_aq, d_inv_qscale );
+        CU_LAUNCH_CHECK( ctx );
+    }
     if( h_stats )
     {
         unsigned long long raw[6];

@@ -22,8 +22,8 @@ struct x264cu_ctx
                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill ) = nullptr;
     // scratch for the *_host entry points (grown on demand)
-    void *scratch[8] = {};
-    size_t scratch_bytes[8] = {};
+    void *scratch[12] = {};
+    size_t scratch_bytes[12] = {};
     bool aq_tables = false;                      // x264cu_adaptive_quant_frame's constant tables uploaded
     int me_tab_lambda = -1, me_tab_range = -1;   // which cost_mv table scratch slot 5 currently holds (x264cu_me_search_batch)
     struct x264cu_lookahead *lookahead = nullptr;

@@ -275,6 +275,9 @@ extern "C" int x264cu_debug_la_profile( unsigned long long *out8, int reset )
 }
 #endif
 
+#ifndef LA_NW
+#define LA_NW 8                                        /* warps (= macroblock rows) per CTA */
+#endif
 #ifndef LA_MIN_CTAS
 #define LA_MIN_CTAS 2                                  /* resident CTAs per SM the register allocation is sized for */
 #endif
@@ -1249,7 +1252,7 @@ static int la_launch_searches( x264cu_lookahead *la, int n, cudaStream_t stream 
     x264cu_ctx *ctx = la->ctx;
     const LaDims &d = la->d;
     if( n <= 0 ) return 0;
-    constexpr int NW = 8;
+    constexpr int NW = LA_NW;
     const int rows = d.mb_h - ( d.do_edges ? 0 : 2 );
     if( rows <= 0 ) return 0;
     const int groups = ( rows + NW - 1 ) / NW;
