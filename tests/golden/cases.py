@@ -140,3 +140,28 @@ def st_case(i):
     for k in range(min(10, cut)):                             # a fade-in
         frames[k] = np.clip(frames[k].astype(np.float32) * (0.35 + 0.065 * k) + 2 * k, 0, 255).astype(np.uint8)
     return frames
+
+
+# ---- x264_adaptive_quant_frame (encoder/ratecontrol.c:305-420) ----------------------------------------------------------
+AQ_CASES = [((112, 80), 1, 1.0), ((100, 52), 2, 1.0), ((96, 64), 3, 1.3)]       # (size, aq-mode, aq-strength)
+
+
+def aq_case(i):
+    (w, h), _, _ = AQ_CASES[i]
+    rng = np.random.default_rng(900 + i)
+    luma = synth_luma(w, h, seed=900 + i)
+    luma[: h // 3] = rng.integers(0, 256, (h // 3, w), dtype=np.uint8)
+    luma[h // 3: h // 2, : w // 2] = 77
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    cb = rng.integers(100, 156, (ch, cw), dtype=np.uint8)
+    cr = rng.integers(0, 256, (ch, cw), dtype=np.uint8)
+    return np.ascontiguousarray(luma), cb, cr
+
+
+# ---- MB-tree end to end: f_qp_offset of every non-B picture as the reference ENCODER used it (slicetype.c:1029-1184) -------
+MBTREE_CASE = ("medium", "aq-mode=0:weightp=0:no-psy=1:bframes=3:rc-lookahead=10:keyint=30:min-keyint=3", (112, 80), 48, 29)
+
+
+def mbtree_case():
+    preset, opts, (w, h), n, cut = MBTREE_CASE
+    return synth_sequence(w, h, n, seed=n + w + 1, cut_at=cut)

@@ -34,6 +34,10 @@ def main():
         out["la_%d_params" % ci], out["la_%d_in" % ci] = pbytes, dig
     for ci in range(len(G.ST_CASES)):
         out["st_%d" % ci], out["st_%d_params" % ci], out["st_%d_in" % ci] = R.run_st("ref", ci)
+    for ci in range(len(G.AQ_CASES)):
+        (q, iq, st), dig = R.run_aq("ref", ci)
+        out["aq_%d_qp" % ci], out["aq_%d_inv" % ci], out["aq_%d_stats" % ci], out["aq_%d_in" % ci] = q, iq, st, dig
+    out["mbtree_types"], out["mbtree_qp"], out["mbtree_params"], out["mbtree_in"] = R.run_mbtree("ref")
     np.savez_compressed(G.GOLDEN, **out)
     print("wrote %s: %d arrays, %d bytes" % (G.GOLDEN, len(out), os.path.getsize(G.GOLDEN)))
 

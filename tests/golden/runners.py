@@ -348,3 +348,63 @@ def run_st(backend, ci, params_bytes=None, ctx=None):
             finally:
                 st.close()
     return np.array(types, np.int32).reshape(-1, 2), np.frombuffer(bytes(p), np.uint8).copy(), dig
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_aq(backend, ci, ctx=None):
+    """-> (f_qp_offset_aq float32[mb], i_inv_qscale_factor u16[mb], stats u64[6])"""
+    (w, h), mode, strength = G.AQ_CASES[ci]
+    luma, cb, cr = G.aq_case(ci)
+    nmb = ((w + 15) // 16) * ((h + 15) // 16)
+    q, iq, st = np.zeros(nmb, np.float32), np.zeros(nmb, np.uint16), np.zeros(6, np.uint64)
+    if backend == "ref":
+        r = ref()
+        r.xref_aq_frame.argtypes = [C.c_void_p] * 7
+        hnd = r.xref_open(w, h, b"medium", ("aq-mode=%d:aq-strength=%g" % (mode, strength)).encode(), 0)
+        assert hnd and r.xref_aq_frame(hnd, ptr(luma), ptr(cb), ptr(cr), ptr(q), ptr(iq), ptr(st)) == 0
+        r.xref_close(hnd)
+    elif backend == "oracle":
+        o = oracle()
+        o.orc_adaptive_quant_frame.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_float,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]
+        o.orc_adaptive_quant_frame(ptr(luma), w, ptr(cb), ptr(cr), cb.shape[1], w, h, mode, strength, ptr(q), ptr(iq), ptr(st))
+    else:
+        ctx.L.x264cu_adaptive_quant_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int,
+                                                      C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        d_l, d_b, d_r = ctx.upload(luma), ctx.upload(cb), ctx.upload(cr)
+        d_q, d_i = ctx.malloc(nmb * 4), ctx.malloc(nmb * 2)
+        ctx.check(ctx.L.x264cu_adaptive_quant_frame(ctx.h, d_l, w, d_b, d_r, cb.shape[1], w, h, mode, strength, d_q, d_i, st.ctypes.data))
+        q, iq = ctx.download(d_q, (nmb,), np.float32), ctx.download(d_i, (nmb,), np.uint16)
+        for p in (d_l, d_b, d_r, d_q, d_i):
+            ctx.free(p)
+    return (q, iq, st), G.digest(luma, cb, cr)
+
+
+def run_mbtree(backend, params_bytes=None, ctx=None):
+    """-> (types int32[n,2], qp float32[k, mb] for the non-B pictures in coded order, SlicetypeParams bytes, digest)"""
+    import test_slicetype_host as host
+    from x264_b200.binding_ext import SlicetypeParams
+    preset, opts, (w, h), n, cut = G.MBTREE_CASE
+    frames = G.mbtree_case()
+    qp = {}
+    if backend == "ref":
+        p, types = host.reference_types(preset, opts, w, h, frames, qp)
+    else:
+        p = SlicetypeParams.from_buffer_copy(bytes(params_bytes))
+        if backend == "oracle":
+            types = host.decide_with(_libs.slicetype_oracle_lib(), p, frames, qp)
+        else:
+            import x264_b200 as x
+            st = x.Slicetype(ctx, w, h, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
+                             b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy,
+                             frame_reference=p.frame_reference, rc_cqp=0,
+                             subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
+                             bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
+                             aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0, weighted_pred=p.la.weighted_pred)
+            try:
+                types = st.decide(frames, qp)
+            finally:
+                st.close()
+    nonb = [f for f, t in types if t not in (4, 5)]
+    qarr = np.stack([np.asarray(qp[f], np.float32) for f in nonb])
+    return np.array(types, np.int32).reshape(-1, 2), qarr, np.frombuffer(bytes(p), np.uint8).copy(), G.digest(*frames)

@@ -76,3 +76,21 @@ def test_frame_types(request, backend, ci):
     _check_inputs("st_%d" % ci, dig)
     want = GOLD["st_%d" % ci]
     assert np.array_equal(got, want), (G.ST_CASES[ci], [z for z in zip(got.tolist(), want.tolist()) if z[0] != z[1]][:6])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("ci", range(len(G.AQ_CASES)))
+def test_adaptive_quant(request, backend, ci):
+    (q, iq, st), dig = R.run_aq(backend, ci, _ctx(request, backend))
+    _check_inputs("aq_%d" % ci, dig)
+    assert np.array_equal(st, GOLD["aq_%d_stats" % ci]) and np.array_equal(iq, GOLD["aq_%d_inv" % ci])
+    assert np.array_equal(q, GOLD["aq_%d_qp" % ci]), float(np.abs(q - GOLD["aq_%d_qp" % ci]).max())      # float, bit for bit
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_mbtree_qp_offsets(request, backend):
+    types, qp, _, dig = R.run_mbtree(backend, GOLD["mbtree_params"], _ctx(request, backend))
+    _check_inputs("mbtree", dig)
+    assert np.array_equal(types, GOLD["mbtree_types"])
+    assert qp.shape == GOLD["mbtree_qp"].shape and np.array_equal(qp, GOLD["mbtree_qp"]), float(np.abs(qp - GOLD["mbtree_qp"]).max())
+    assert np.abs(qp).max() > 0.5
