@@ -219,6 +219,11 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la );
  * h_inv_qscale: fenc->i_inv_qscale_factor (u16 per MB) or NULL for 256 (AQ off). */
 int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
                                 const uint16_t *h_inv_qscale );
+/* The same from an I420 picture, with x264_adaptive_quant_frame (encoder.c:3417, ratecontrol.c:305-420) run on the device:
+ * i_inv_qscale_factor and f_qp_offset_aq / f_qp_offset of the slot come from the picture itself (aq_mode 0..3,
+ * aq_strength = h->param.rc.f_aq_strength).  Cb / Cr: (width+1)/2 x (height+1)/2, chroma_stride bytes per row. */
+int x264cu_lookahead_frame_put_i420( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
+                                     const uint8_t *h_cb, const uint8_t *h_cr, intptr_t chroma_stride, int aq_mode, float aq_strength );
 /* How h_luma is read.  Pageable memory is staged through the library's own pinned ring (the caller's buffer is free on
  * return).  Page-locked memory (x264cu_malloc_host; the reference stages through page-locked buffers too, opencl.h:718) is
  * read in place by the copy engine on the lookahead's upload stream: with async_upload = 0 (default) the call returns once
@@ -328,6 +333,7 @@ typedef struct
     int rc_cqp;                   /* h->param.rc.i_rc_method == X264_RC_CQP */
     int fps_num, fps_den;         /* h->param.i_fps_num / i_fps_den (constant frame rate); 0 = 25/1.  MB-tree's duration factors */
     float qcompress;              /* h->param.rc.f_qcompress; 0 = 0.6.  MB-tree strength = 5 * (1 - qcompress) */
+    float aq_strength;            /* h->param.rc.f_aq_strength; 0 = 1.0.  Used by x264cu_slicetype_step_i420 (la.aq_mode = the mode, 0..3) */
 } x264cu_slicetype_params_t;
 
 enum { X264CU_TYPE_AUTO = 0, X264CU_TYPE_IDR = 1, X264CU_TYPE_I = 2, X264CU_TYPE_P = 3, X264CU_TYPE_BREF = 4,
@@ -341,6 +347,10 @@ void x264cu_slicetype_close( x264cu_slicetype_t *st );
  * Returns 0, or -1 on error.  While flushing, *out_frame == -1 means the stream is drained. */
 int  x264cu_slicetype_step( x264cu_slicetype_t *st, const uint8_t *h_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
                             int *out_frame, int *out_type );
+/* same from an I420 picture: adaptive quantisation (la.aq_mode, aq_strength) runs on the device too, so that the whole of
+ * x264_encoder_encode's preparation for the lookahead -- x264_adaptive_quant_frame, x264_frame_init_lowres, put_frame -- is here */
+int  x264cu_slicetype_step_i420( x264cu_slicetype_t *st, const uint8_t *h_luma, intptr_t luma_stride, const uint8_t *h_cb, const uint8_t *h_cr,
+                                 intptr_t chroma_stride, int *out_frame, int *out_type );
 /* same with the picture already in HBM (8-byte aligned base and stride) */
 int  x264cu_slicetype_step_device( x264cu_slicetype_t *st, const uint8_t *d_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
                                    int *out_frame, int *out_type );

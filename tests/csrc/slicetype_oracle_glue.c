@@ -123,3 +123,15 @@ void *x264cu_lookahead_exchange_stream( x264cu_lookahead_t *la ) { (void)la; ret
 int x264cu_lookahead_export_search( x264cu_lookahead_t *la, int slot, int list, int dist, void *d ) { (void)la; (void)slot; (void)list; (void)dist; (void)d; return 0; }
 int x264cu_lookahead_import_search( x264cu_lookahead_t *la, int slot, int list, int dist, const void *d ) { (void)la; (void)slot; (void)list; (void)dist; (void)d; return 0; }
 int x264cu_lookahead_import_done( x264cu_lookahead_t *la ) { (void)la; return 0; }
+
+/* I420 pictures: adaptive quantisation by the oracle (oracle/oracle_aq.c) */
+int x264cu_lookahead_frame_put_i420( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
+                                     const uint8_t *h_cb, const uint8_t *h_cr, intptr_t chroma_stride, int aq_mode, float aq_strength )
+{
+    orc_la_frame_delete( la->slots[slot] );
+    orc_la_frame_t *f = la->slots[slot] = orc_la_frame_new( &la->p, h_luma, luma_stride );
+    orc_adaptive_quant_frame( h_luma, luma_stride, h_cb, h_cr, chroma_stride, la->p.width, la->p.height, aq_mode, aq_strength,
+                              f->qp_offset_aq, f->inv_qscale_factor, NULL );
+    memcpy( f->qp_offset, f->qp_offset_aq, f->mb_count * sizeof(float) );
+    return 0;
+}

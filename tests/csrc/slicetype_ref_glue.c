@@ -101,3 +101,9 @@ void *x264cu_lookahead_exchange_stream( x264cu_lookahead_t *la ) { (void)la; ret
 int x264cu_lookahead_export_search( x264cu_lookahead_t *la, int slot, int list, int dist, void *d ) { (void)la; (void)slot; (void)list; (void)dist; (void)d; return 0; }
 int x264cu_lookahead_import_search( x264cu_lookahead_t *la, int slot, int list, int dist, const void *d ) { (void)la; (void)slot; (void)list; (void)dist; (void)d; return 0; }
 int x264cu_lookahead_import_done( x264cu_lookahead_t *la ) { (void)la; return 0; }
+int x264cu_lookahead_frame_put_i420( x264cu_lookahead_t *la, int slot, const uint8_t *y, intptr_t ys, const uint8_t *cb, const uint8_t *cr,
+                                     intptr_t cs, int aq_mode, float aq_strength )
+{
+    (void)la; (void)slot; (void)y; (void)ys; (void)cb; (void)cr; (void)cs; (void)aq_mode; (void)aq_strength;
+    return -1;          /* the bench's CPU arm feeds luma only */
+}

@@ -138,3 +138,40 @@ def test_mbtree_qp_offsets_end_to_end(ctx, case):
         assert np.array_equal(qp_gpu[fr], qp_ref[fr]), ("vs reference encoder", fr, float(np.abs(qp_gpu[fr] - qp_ref[fr]).max()))
         compared += 1
     assert compared >= 5 and any(np.abs(q).max() > 0.5 for q in qp_gpu.values())
+
+
+@pytest.mark.parametrize("case", host.DEFAULT_PATH_CASES)
+def test_default_path_i420_end_to_end(ctx, case):
+    """preset medium as it is (aq-mode 1, weightp 2, mb-tree, psy) and two variants: I420 pictures into x264cu_slicetype_step_i420
+    -- adaptive quantisation, weight analysis, lookahead, slice-type decision and MB-tree all on the device -- against the
+    reference ENCODER's frame types and f_qp_offset, and against the same host logic over the oracle"""
+    preset, opts, (w, h), n, cut = case
+    frames = synth_sequence(w, h, n, seed=n + w + 5, cut_at=cut)
+    for i in range(8):
+        frames[i] = np.clip(frames[i].astype(np.float32) * (0.4 + 0.07 * i) + 2 * i, 0, 255).astype(np.uint8)
+    cb = np.full(((h + 1) // 2, (w + 1) // 2), 128, np.uint8)
+    if not have_ref():
+        pytest.skip("compiled reference did not travel (its option parsing provides the parameters)")
+    qp_ref, qp_orc, qp_gpu = {}, {}, {}
+    p, want = host.reference_types(preset, opts, w, h, frames, qp_ref)
+    p.aq_strength = float(opts.split("aq-strength=")[1].split(":")[0]) if "aq-strength" in opts else 1.0
+    want_orc = host.decide_with(slicetype_oracle_lib(), p, frames, qp_orc, chroma=(cb, cb))
+    st = x.Slicetype(ctx, w, h, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
+                     b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy,
+                     frame_reference=p.frame_reference, rc_cqp=0, aq_strength=p.aq_strength,
+                     subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
+                     bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
+                     aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0, weighted_pred=p.la.weighted_pred)
+    try:
+        got = st.decide(frames, qp_gpu, chroma=[(cb, cb)] * n)
+    finally:
+        st.close()
+    assert got == want == want_orc
+    compared = 0
+    for fr, ty in want:
+        if ty in (4, 5):
+            continue
+        assert np.array_equal(qp_gpu[fr], qp_orc[fr]), ("vs oracle", fr, float(np.abs(qp_gpu[fr] - qp_orc[fr]).max()))
+        assert np.array_equal(qp_gpu[fr], qp_ref[fr]), ("vs reference encoder", fr, float(np.abs(qp_gpu[fr] - qp_ref[fr]).max()))
+        compared += 1
+    assert compared >= 5

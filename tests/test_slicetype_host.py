@@ -35,13 +35,14 @@ def params_from_ref(hnd, w, h):
     r = ref()
     g = lambda n: r.xref_param(hnd, n.encode())
     la = LookaheadParams(w, h, g("subme"), min(g("me"), 2), g("merange"), g("mvrange"), g("bframes"), g("b_bias"), g("weightb"),
-                         int(g("aq_mode") != 0), g("mbtree"), g("vbv"), 0, -1 if g("weightp") < 0 else int(g("weightp") != 0))
+                         g("aq_mode"), g("mbtree"), g("vbv"), 0, -1 if g("weightp") < 0 else int(g("weightp") != 0))
     return SlicetypeParams(la, g("keyint_max"), g("keyint_min"), g("scenecut"), g("b_adapt"), g("b_pyramid"), g("lookahead"),
                            g("psy"), g("ref"), 0)
 
 
-def decide_with(lib, p, frames, qp_out=None):
-    """qp_out: dict filled with frame -> f_qp_offset (MB-tree's output) for every non-B picture, read when it is returned"""
+def decide_with(lib, p, frames, qp_out=None, chroma=None):
+    """qp_out: dict filled with frame -> f_qp_offset (MB-tree's output) for every non-B picture, read when it is returned;
+    chroma: (cb, cr) planes fed with every picture through x264cu_slicetype_step_i420 (adaptive quantisation inside)"""
     lib.x264cu_slicetype_open.argtypes = [C.c_void_p, C.POINTER(SlicetypeParams), C.POINTER(C.c_void_p)]
     lib.x264cu_slicetype_step.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.x264cu_slicetype_close.argtypes = [C.c_void_p]
@@ -59,8 +60,13 @@ def decide_with(lib, p, frames, qp_out=None):
             assert lib.x264cu_slicetype_get_qp_offset(st, fr.value, q.ctypes.data) == 0
             qp_out[fr.value] = q
 
+    lib.x264cu_slicetype_step_i420.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     for f in frames:
-        assert lib.x264cu_slicetype_step(st, f.ctypes.data, f.shape[1], None, C.byref(fr), C.byref(ty)) == 0
+        if chroma is None:
+            assert lib.x264cu_slicetype_step(st, f.ctypes.data, f.shape[1], None, C.byref(fr), C.byref(ty)) == 0
+        else:
+            assert lib.x264cu_slicetype_step_i420(st, f.ctypes.data, f.shape[1], chroma[0].ctypes.data, chroma[1].ctypes.data, chroma[0].shape[1],
+                                                  C.byref(fr), C.byref(ty)) == 0
         if fr.value >= 0:
             note()
     while True:
@@ -149,3 +155,28 @@ def test_mbtree_qp_offsets_match_reference_encoder(case):
     compared, exact, worst = mbtree_compare(want, got, qp_ref, qp_got, n, p.rc_lookahead)
     assert compared >= 5 and any(np.abs(q).max() > 0.5 for q in qp_got.values())
     assert exact == compared, "f_qp_offset bit-exact on %d of %d pictures, worst |diff| %.3g" % (exact, compared, worst)
+
+
+# The whole default path: preset medium as it is (aq-mode 1, weightp 2, mb-tree, psy) and two variants, I420 pictures in, adaptive
+# quantisation + weight analysis + lookahead + MB-tree inside: frame types and f_qp_offset of every non-B picture against the
+# reference ENCODER.  (The reference shim feeds flat chroma, so does this test.)
+DEFAULT_PATH_CASES = [
+    ("medium", "bframes=3:rc-lookahead=10:keyint=30:min-keyint=3", (112, 80), 60, 37),
+    ("medium", "aq-mode=2:rc-lookahead=12:b-adapt=2", (96, 64), 50, 31),
+    ("medium", "aq-mode=3:aq-strength=1.3:weightp=1:bframes=2:rc-lookahead=8", (96, 64), 50, 27),
+]
+
+
+@pytest.mark.parametrize("case", DEFAULT_PATH_CASES)
+def test_default_presets_with_adaptive_quant_match_reference_encoder(case):
+    preset, opts, (w, h), n, cut = case
+    frames = synth_sequence(w, h, n, seed=n + w + 5, cut_at=cut)
+    for i in range(8):                                       # a fade-in: weights are chosen
+        frames[i] = np.clip(frames[i].astype(np.float32) * (0.4 + 0.07 * i) + 2 * i, 0, 255).astype(np.uint8)
+    flat = (np.full(((h + 1) // 2, (w + 1) // 2), 128, np.uint8), np.full(((h + 1) // 2, (w + 1) // 2), 128, np.uint8))
+    qp_ref, qp_got = {}, {}
+    p, want = reference_types(preset, opts, w, h, frames, qp_ref)
+    p.aq_strength = float(opts.split("aq-strength=")[1].split(":")[0]) if "aq-strength" in opts else 1.0
+    got = decide_with(slicetype_oracle_lib(), p, frames, qp_got, chroma=flat)
+    compared, exact, worst = mbtree_compare(want, got, qp_ref, qp_got, n, p.rc_lookahead)
+    assert compared >= 5 and exact == compared, "f_qp_offset bit-exact on %d of %d pictures, worst |diff| %.3g" % (exact, compared, worst)

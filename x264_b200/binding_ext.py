@@ -33,7 +33,7 @@ me_result_dtype = np.dtype([("mv", np.int16, (2,)), ("cost", np.int32), ("cost_m
 class SlicetypeParams(C.Structure):
     _fields_ = [("la", LookaheadParams)] + [(n, C.c_int) for n in ("keyint_max", "keyint_min", "scenecut_threshold", "b_adapt",
                                                                   "b_pyramid", "rc_lookahead", "psy", "frame_reference", "rc_cqp",
-                                                                  "fps_num", "fps_den")] + [("qcompress", C.c_float)]
+                                                                  "fps_num", "fps_den")] + [("qcompress", C.c_float), ("aq_strength", C.c_float)]
 
 
 TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "BREF", 5: "B"}
@@ -51,6 +51,7 @@ def bind(L):
     L.x264cu_slicetype_set_async_upload.argtypes = [vp, ci]
     L.x264cu_slicetype_get_qp_offset.argtypes = [vp, ci, vp]
     L.x264cu_slicetype_set_shard.argtypes = [vp, ci, ci, vp, vp]
+    L.x264cu_slicetype_step_i420.argtypes = [vp, vp, ss, vp, vp, ss, C.POINTER(ci), C.POINTER(ci)]
     L.x264cu_slicetype_lookahead.argtypes = [vp]
     L.x264cu_slicetype_lookahead.restype = vp
     L.x264cu_lookahead_search_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_long)]
@@ -211,7 +212,7 @@ class Slicetype:
     decide(frames) runs a whole sequence the way x264_encoder_encode would and returns [(display_index, type)] in coded order."""
 
     def __init__(self, ctx, width, height, keyint_max=250, keyint_min=25, scenecut_threshold=40, b_adapt=1, b_pyramid=2,
-                 rc_lookahead=40, psy=1, frame_reference=3, rc_cqp=0, **la_kwargs):
+                 rc_lookahead=40, psy=1, frame_reference=3, rc_cqp=0, fps_num=0, fps_den=0, qcompress=0.0, aq_strength=0.0, **la_kwargs):
         self.ctx, self.L = ctx, ctx.L
         la = dict(subpel_refine=7, me_method=1, me_range=16, mv_range=512, bframes=3, bframe_bias=0, weighted_bipred=1,
                   aq_mode=1, mb_tree=1, vbv=0, n_slots=0, weighted_pred=0)
@@ -219,7 +220,7 @@ class Slicetype:
         lp = LookaheadParams(width, height, la["subpel_refine"], la["me_method"], la["me_range"], la["mv_range"], la["bframes"],
                              la["bframe_bias"], la["weighted_bipred"], la["aq_mode"], la["mb_tree"], la["vbv"], la["n_slots"], la["weighted_pred"])
         self.p = SlicetypeParams(lp, keyint_max, keyint_min, scenecut_threshold, b_adapt, b_pyramid, rc_lookahead, psy,
-                                 frame_reference, rc_cqp)
+                                 frame_reference, rc_cqp, fps_num, fps_den, qcompress, aq_strength)
         h = C.c_void_p()
         if self.L.x264cu_slicetype_open(ctx.h, C.byref(self.p), C.byref(h)) != 0:
             from .binding import X264CUError
@@ -242,6 +243,14 @@ class Slicetype:
         else:
             rc = self.L.x264cu_slicetype_step(self.h, None, 0, None, C.byref(fr), C.byref(ty))
         self.ctx.check(rc)
+        return fr.value, ty.value
+
+    def step_i420(self, luma, cb, cr):
+        """one picture with its chroma planes: adaptive quantisation runs on the device (la.aq_mode, aq_strength)"""
+        fr, ty = C.c_int(), C.c_int()
+        luma, cb, cr = (np.ascontiguousarray(a, dtype=np.uint8) for a in (luma, cb, cr))
+        self.ctx.check(self.L.x264cu_slicetype_step_i420(self.h, luma.ctypes.data, luma.shape[1], cb.ctypes.data, cr.ctypes.data, cb.shape[1],
+                                                         C.byref(fr), C.byref(ty)))
         return fr.value, ty.value
 
     def step_device(self, d_luma, stride):
@@ -277,8 +286,8 @@ class Slicetype:
         self.ctx.check(self.L.x264cu_slicetype_get_qp_offset(self.h, int(frame), out.ctypes.data))
         return out
 
-    def decide(self, frames, qp_out=None):
-        """qp_out: dict filled with frame -> f_qp_offset for every non-B picture"""
+    def decide(self, frames, qp_out=None, chroma=None):
+        """qp_out: dict filled with frame -> f_qp_offset for every non-B picture; chroma: [(cb, cr)] per picture -> step_i420"""
         out = []
 
         def note(fr, ty):
@@ -286,8 +295,8 @@ class Slicetype:
             if qp_out is not None and ty not in (4, 5):
                 qp_out[fr] = self.get_qp_offset(fr)
 
-        for f in frames:
-            fr, ty = self.step(f)
+        for i, f in enumerate(frames):
+            fr, ty = self.step(f) if chroma is None else self.step_i420(f, chroma[i][0], chroma[i][1])
             if fr >= 0:
                 note(fr, ty)
         while True:

@@ -137,15 +137,12 @@ aq_final_kernel( int mb_count, int aq_mode, float bias_strength, const float *__
 
 } // namespace
 
-extern "C" int x264cu_adaptive_quant_frame( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, const uint8_t *d_cb,
-                                            const uint8_t *d_cr, intptr_t chroma_stride, int width, int height, int aq_mode,
-                                            float aq_strength, float *d_qp_offset_aq, uint16_t *d_inv_qscale, uint64_t *h_stats )
+// the launches on a stream of the caller's choice (the lookahead's upload stream); d_q4: mb_count + 2 floats of scratch for
+// the auto-variance modes; d_stats: 6 x u64 raw sums (zeroed here) or NULL
+int x264cu_adaptive_quant_frame_on( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d_luma, intptr_t luma_stride, const uint8_t *d_cb,
+                                    const uint8_t *d_cr, intptr_t chroma_stride, int width, int height, int aq_mode, float aq_strength,
+                                    float *d_qp_offset_aq, uint16_t *d_inv_qscale, float *d_q4, unsigned long long *d_stats )
 {
-    if( !ctx ) return -1;
-    if( !d_luma || !d_cb || !d_cr || !d_qp_offset_aq || !d_inv_qscale || width < 1 || height < 1 )
-        return x264cu_fail( ctx, "adaptive_quant_frame: bad arguments" );
-    if( aq_mode < 0 || aq_mode > 3 )
-        return x264cu_fail( ctx, "adaptive_quant_frame: aq-mode %d out of range", aq_mode );
     if( !ctx->aq_tables )
     {
         float l2[128];
@@ -162,30 +159,48 @@ extern "C" int x264cu_adaptive_quant_frame( x264cu_ctx_t *ctx, const uint8_t *d_
         ctx->aq_tables = true;
     }
     const int mb_w = ( width + 15 ) >> 4, mb_h = ( height + 15 ) >> 4, mb_count = mb_w * mb_h;
+    if( d_stats ) CU_CHECK( ctx, cudaMemsetAsync( d_stats, 0, 48, stream ) );
+    const int active = aq_mode != 0 && aq_strength != 0.f;
+    const bool two_pass = active && aq_mode >= 2;
+    if( two_pass && !d_q4 ) return x264cu_fail( ctx, "adaptive_quant_frame: no scratch for the auto-variance modes" );
+    aq_kernel<<<( mb_count + 7 ) / 8, 256, 0, stream>>>( d_luma, luma_stride, d_cb, d_cr, chroma_stride, width, height, mb_w, mb_count,
+                                                         active, aq_mode, aq_strength * 1.0397f, d_qp_offset_aq, d_inv_qscale, d_q4, d_stats );
+    CU_LAUNCH_CHECK( ctx );
+    if( two_pass )
+    {
+        aq_means_kernel<<<1, 32, 0, stream>>>( d_qp_offset_aq, d_q4, mb_count, aq_strength, d_q4 + mb_count );
+        CU_LAUNCH_CHECK( ctx );
+        aq_final_kernel<<<( mb_count + 255 ) / 256, 256, 0, stream>>>( mb_count, aq_mode, aq_strength, d_q4 + mb_count, d_qp_offset_aq, d_inv_qscale );
+        CU_LAUNCH_CHECK( ctx );
+    }
+    return 0;
+}
+
+extern "C" int x264cu_adaptive_quant_frame( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, const uint8_t *d_cb,
+                                            const uint8_t *d_cr, intptr_t chroma_stride, int width, int height, int aq_mode,
+                                            float aq_strength, float *d_qp_offset_aq, uint16_t *d_inv_qscale, uint64_t *h_stats )
+{
+    if( !ctx ) return -1;
+    if( !d_luma || !d_cb || !d_cr || !d_qp_offset_aq || !d_inv_qscale || width < 1 || height < 1 )
+        return x264cu_fail( ctx, "adaptive_quant_frame: bad arguments" );
+    if( aq_mode < 0 || aq_mode > 3 )
+        return x264cu_fail( ctx, "adaptive_quant_frame: aq-mode %d out of range", aq_mode );
+    const int mb_w = ( width + 15 ) >> 4, mb_h = ( height + 15 ) >> 4, mb_count = mb_w * mb_h;
     unsigned long long *d_stats = nullptr;
     if( h_stats )
     {
         d_stats = (unsigned long long *)x264cu_scratch( ctx, 7, 48 );
         if( !d_stats ) return -1;
-        CU_CHECK( ctx, cudaMemsetAsync( d_stats, 0, 48, ctx->stream ) );
     }
-    const int active = aq_mode != 0 && aq_strength != 0.f;
     float *d_q4 = nullptr;
-    if( active && aq_mode >= 2 )
+    if( aq_mode >= 2 && aq_strength != 0.f )
     {   // scratch: (energy+1)^(1/4) per macroblock, then the two frame-level scalars
         d_q4 = (float *)x264cu_scratch( ctx, 8, (size_t)( mb_count + 2 ) * 4 );
         if( !d_q4 ) return -1;
     }
-    aq_kernel<<<( mb_count + 7 ) / 8, 256, 0, ctx->stream>>>( d_luma, luma_stride, d_cb, d_cr, chroma_stride, width, height, mb_w, mb_count,
-                                                              active, aq_mode, aq_strength * 1.0397f, d_qp_offset_aq, d_inv_qscale, d_q4, d_stats );
-    CU_LAUNCH_CHECK( ctx );
-    if( d_q4 )
-    {
-        aq_means_kernel<<<1, 32, 0, ctx->stream>>>( d_qp_offset_aq, d_q4, mb_count, aq_strength, d_q4 + mb_count );
-        CU_LAUNCH_CHECK( ctx );
-        aq_final_kernel<<<( mb_count + 255 ) / 256, 256, 0, ctx->stream>>>( mb_count, aq_mode, aq_strength, d_q4 + mb_count, d_qp_offset_aq, d_inv_qscale );
-        CU_LAUNCH_CHECK( ctx );
-    }
+    if( x264cu_adaptive_quant_frame_on( ctx, ctx->stream, d_luma, luma_stride, d_cb, d_cr, chroma_stride, width, height, aq_mode, aq_strength,
+                                        d_qp_offset_aq, d_inv_qscale, d_q4, d_stats ) )
+        return -1;
     if( h_stats )
     {
         unsigned long long raw[6];

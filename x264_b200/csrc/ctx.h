@@ -36,6 +36,10 @@ void *x264cu_scratch( x264cu_ctx *ctx, int slot, size_t bytes );
 int  x264cu_frame_init_lowres_on( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d_luma, intptr_t luma_stride, int width, int height,
                                   uint8_t *const d_lowres[4], intptr_t lowres_stride );
 
+int  x264cu_adaptive_quant_frame_on( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d_luma, intptr_t luma_stride, const uint8_t *d_cb,
+                                     const uint8_t *d_cr, intptr_t chroma_stride, int width, int height, int aq_mode, float aq_strength,
+                                     float *d_qp_offset_aq, uint16_t *d_inv_qscale, float *d_q4, unsigned long long *d_stats );
+
 #define CU_CHECK( ctx, call )                                                                      \
     do {                                                                                           \
         cudaError_t e_ = ( call );                                                                 \

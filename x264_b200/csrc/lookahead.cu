@@ -821,6 +821,8 @@ struct x264cu_lookahead
     size_t plane_bytes;              // one padded lowres plane
     std::vector<LaSlotHost> slots;
     uint16_t *d_cost_mv = nullptr;
+    uint8_t *d_chroma = nullptr;     // staging for the two chroma planes of an I420 picture (frame_put_i420)
+    float *d_aq_q4 = nullptr;        // scratch of the auto-variance AQ modes
     uint8_t *d_luma = nullptr;       // staging for one full-res luma picture
     size_t luma_bytes = 0;
     uint8_t *h_luma[2] = { nullptr, nullptr };   // pinned staging ring for pictures handed over in pageable memory
@@ -912,6 +914,7 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
         cudaFree( s.dev.intra ); cudaFree( s.dev.qscale ); cudaFree( s.dev.row_satds ); cudaFree( s.dev.recs ); cudaFree( s.d_stats );
         cudaFree( s.dev.propagate ); cudaFree( s.dev.qp_offset ); cudaFree( s.dev.qp_offset_aq );
     }
+    cudaFree( la->d_chroma ); cudaFree( la->d_aq_q4 );
     cudaFree( la->d_cost_mv ); cudaFree( la->d_luma ); cudaFree( la->d_record ); cudaFree( la->d_weight_plane ); cudaFree( la->d_tickets );
     cudaFreeHost( la->h_stats );
     {
@@ -995,6 +998,8 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     }
     la->luma_bytes = (size_t)( ( p->width + 63 ) & ~63 ) * p->height + 64;
     alloc( (void **)&la->d_luma, la->luma_bytes );
+    alloc( (void **)&la->d_chroma, la->luma_bytes / 2 + 256 );
+    alloc( (void **)&la->d_aq_q4, (size_t)( d.mb_count + 2 ) * 4 );
     alloc( (void **)&la->d_cost_mv, ( 2 * d.cost_len + 1 ) * 2 + 16 );
     alloc( (void **)&la->d_record, 64 );
     alloc( (void **)&la->d_weight_plane, la->plane_bytes );
@@ -1154,7 +1159,10 @@ static int la_put_begin( x264cu_lookahead *la, int slot )
 
 // lowres planes, luma statistics and memo reset of `slot` from a picture in HBM, all on the upload stream; the slot's
 // ev_ready is what its later readers (searches, cost requests, read-backs) are ordered after
-static int la_put_finish( x264cu_lookahead *la, int slot, const uint8_t *d_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale )
+struct LaAq { const uint8_t *d_cb, *d_cr; intptr_t cstride; int mode; float strength; };
+
+static int la_put_finish( x264cu_lookahead *la, int slot, const uint8_t *d_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
+                          const LaAq *aq = nullptr )
 {
     x264cu_ctx *ctx = la->ctx;
     LaSlotHost &s = la->slots[slot];
@@ -1169,6 +1177,13 @@ static int la_put_finish( x264cu_lookahead *la, int slot, const uint8_t *d_luma,
         CU_CHECK( ctx, cudaMemcpyAsync( la->h_stats + 2 * slot, s.d_stats, 16, cudaMemcpyDeviceToHost, la->up_stream ) );
     }
     if( la_reset_slot( la, slot, h_inv_qscale, la->up_stream ) ) return -1;
+    if( aq )
+    {   // x264_adaptive_quant_frame (encoder.c:3417) on the device: i_inv_qscale_factor and f_qp_offset(_aq) straight into the slot
+        if( x264cu_adaptive_quant_frame_on( ctx, la->up_stream, d_luma, luma_stride, aq->d_cb, aq->d_cr, aq->cstride, la->p.width, la->p.height,
+                                            aq->mode, aq->strength, s.dev.qp_offset_aq, s.dev.qscale, la->d_aq_q4, nullptr ) )
+            return -1;
+        CU_CHECK( ctx, cudaMemcpyAsync( s.dev.qp_offset, s.dev.qp_offset_aq, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToDevice, la->up_stream ) );
+    }
     // the intra costs are a function of the picture alone (slicetype.c:714-757): computed here, off the request path
     intra_kernel<<<( la->d.mb_count + 63 ) / 64, 256, 0, la->up_stream>>>( la->d, s.dev.planes[0], s.dev.intra );
     CU_LAUNCH_CHECK( ctx );
@@ -1205,17 +1220,17 @@ void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on )
     if( la ) la->async_upload = on <= 0 ? 0 : on == 1 ? 4 : on > LA_ZC_DEPTH ? LA_ZC_DEPTH : on;
 }
 
-int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
-                                const uint16_t *h_inv_qscale )
+static int la_put_host( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride, const uint16_t *h_inv_qscale,
+                        const uint8_t *h_cb, const uint8_t *h_cr, intptr_t chroma_stride, int aq_mode, float aq_strength )
 {
-    if( !la ) return -1;
+    if( !la || !h_luma ) return -1;
     x264cu_ctx *ctx = la->ctx;
     if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( ctx, "frame_put: slot %d out of range", slot );
     const int w = la->p.width, h = la->p.height;
     const intptr_t st = ( w + 63 ) & ~63;
     const int zc = la->zc_next++ % ( la->async_upload ? la->async_upload : 1 );
     if( la->zero_copy_live[zc] )
-    {   // the picture queued LA_ZC_DEPTH calls ago was read in place: that copy ended long ago in steady state
+    {   // the picture queued async_upload calls ago was read in place: that copy ended long ago in steady state
         LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->ev_zero_copy[zc] ) ) );
         la->zero_copy_live[zc] = false;
     }
@@ -1223,6 +1238,16 @@ int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t 
     cudaPointerAttributes at;
     const bool pinned = cudaPointerGetAttributes( &at, h_luma ) == cudaSuccess && at.type == cudaMemoryTypeHost;
     if( !pinned ) cudaGetLastError();
+    LaAq aq;
+    if( h_cb )
+    {   // the chroma planes go first: pageable ones are consumed before cudaMemcpy2DAsync returns, page-locked ones fall under
+        // the same rule as the luma
+        const int cw = ( w + 1 ) >> 1, ch = ( h + 1 ) >> 1;
+        const intptr_t cst = ( cw + 63 ) & ~63;
+        aq.d_cb = la->d_chroma; aq.d_cr = la->d_chroma + (size_t)cst * ch; aq.cstride = cst; aq.mode = aq_mode; aq.strength = aq_strength;
+        CU_CHECK( ctx, cudaMemcpy2DAsync( (void *)aq.d_cb, cst, h_cb, chroma_stride, cw, ch, cudaMemcpyHostToDevice, la->up_stream ) );
+        CU_CHECK( ctx, cudaMemcpy2DAsync( (void *)aq.d_cr, cst, h_cr, chroma_stride, cw, ch, cudaMemcpyHostToDevice, la->up_stream ) );
+    }
     if( pinned )
     {   // page-locked source (x264cu_malloc_host, like the reference's pinned page-locked staging, opencl.h:718): the DMA
         // engine reads it in place, the calling thread neither copies nor waits
@@ -1243,7 +1268,21 @@ int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t 
         CU_CHECK( ctx, cudaMemcpyAsync( la->d_luma, la->h_luma[k], (size_t)st * h, cudaMemcpyHostToDevice, la->up_stream ) );
         CU_CHECK( ctx, cudaEventRecord( la->h_luma_ev[k], la->up_stream ) );
     }
-    return la_put_finish( la, slot, la->d_luma, st, h_inv_qscale );
+    return la_put_finish( la, slot, la->d_luma, st, h_inv_qscale, h_cb ? &aq : nullptr );
+}
+
+int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
+                                const uint16_t *h_inv_qscale )
+{
+    return la_put_host( la, slot, h_luma, luma_stride, h_inv_qscale, nullptr, nullptr, 0, 0, 0.f );
+}
+
+int x264cu_lookahead_frame_put_i420( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
+                                     const uint8_t *h_cb, const uint8_t *h_cr, intptr_t chroma_stride, int aq_mode, float aq_strength )
+{
+    if( !la || !h_cb || !h_cr ) return -1;
+    if( aq_mode < 0 || aq_mode > 3 ) return x264cu_fail( la->ctx, "frame_put_i420: aq-mode %d out of range", aq_mode );
+    return la_put_host( la, slot, h_luma, luma_stride, nullptr, h_cb, h_cr, chroma_stride, aq_mode, aq_strength );
 }
 
 // enqueue the n searches assembled in la->pack as one launch on `stream` (no host synchronisation)

@@ -798,7 +798,7 @@ static int flush_prefetch( x264cu_slicetype_t *s )
 }
 
 static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_device, intptr_t luma_stride, const uint16_t *h_inv_qscale,
-                        int *out_frame, int *out_type )
+                        int *out_frame, int *out_type, const uint8_t *cb, const uint8_t *cr, intptr_t chroma_stride )
 {
     if( !s || !out_frame || !out_type ) return -1;
     *out_frame = -1; *out_type = T_AUTO;
@@ -810,6 +810,8 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
         if( slot < 0 || s->n_next >= LOOKAHEAD_MAX + ST_RUN_AHEAD_MAX + 4 ) return -1;
         double t0_ = st_now();
         int rc_ = on_device ? x264cu_lookahead_frame_put_device( s->la, slot, luma, luma_stride, h_inv_qscale )
+                : cb        ? x264cu_lookahead_frame_put_i420( s->la, slot, luma, luma_stride, cb, cr, chroma_stride, s->p.la.aq_mode,
+                                                               s->p.aq_strength > 0 ? s->p.aq_strength : 1.0f )
                             : x264cu_lookahead_frame_put( s->la, slot, luma, luma_stride, h_inv_qscale );
         s->t_put += st_now() - t0_;
         if( rc_ ) return -1;
@@ -874,7 +876,17 @@ int x264cu_slicetype_step( x264cu_slicetype_t *s, const uint8_t *h_luma, intptr_
                            int *out_frame, int *out_type )
 {
     double t0 = st_now();
-    int rc = step_common( s, h_luma, 0, luma_stride, h_inv_qscale, out_frame, out_type );
+    int rc = step_common( s, h_luma, 0, luma_stride, h_inv_qscale, out_frame, out_type, NULL, NULL, 0 );
+    if( s ) s->t_step += st_now() - t0;
+    return rc;
+}
+
+int x264cu_slicetype_step_i420( x264cu_slicetype_t *s, const uint8_t *h_luma, intptr_t luma_stride, const uint8_t *h_cb, const uint8_t *h_cr,
+                                intptr_t chroma_stride, int *out_frame, int *out_type )
+{
+    if( h_luma && ( !h_cb || !h_cr ) ) return -1;
+    double t0 = st_now();
+    int rc = step_common( s, h_luma, 0, luma_stride, NULL, out_frame, out_type, h_luma ? h_cb : NULL, h_cr, chroma_stride );
     if( s ) s->t_step += st_now() - t0;
     return rc;
 }
@@ -883,7 +895,7 @@ int x264cu_slicetype_step_device( x264cu_slicetype_t *s, const uint8_t *d_luma, 
                                   int *out_frame, int *out_type )
 {
     double t0 = st_now();
-    int rc = step_common( s, d_luma, 1, luma_stride, h_inv_qscale, out_frame, out_type );
+    int rc = step_common( s, d_luma, 1, luma_stride, h_inv_qscale, out_frame, out_type, NULL, NULL, 0 );
     if( s ) s->t_step += st_now() - t0;
     return rc;
 }
