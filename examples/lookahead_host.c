@@ -4,7 +4,10 @@
  * pictures it would encode.  No CUDA headers, no C++.
  *
  *   gcc -O2 -Iinclude examples/lookahead_host.c -o lookahead_host -Lx264_b200/csrc -lx264_b200 -Wl,-rpath,$PWD/x264_b200/csrc
- *   ./lookahead_host WIDTH HEIGHT FRAMES [raw 8-bit luma file]      (without a file: a synthetic moving texture with a cut)
+ *   ./lookahead_host WIDTH HEIGHT FRAMES [raw 8-bit I420 file]      (without a file: a synthetic moving texture with a cut)
+ *
+ * Raw I420 in (Y, Cb, Cr planes per picture, as x264's raw demuxer reads them, input/raw.c:43-170): adaptive quantisation
+ * (aq-mode 1), lowres planes, lookahead, slice-type decision and MB-tree all run on the device (x264cu_slicetype_step_i420).
  *
  * Prints one line per picture in coded order: "frame <display index> type <I|P|B|b...> qp_offset_mean <f>".
  * tests/test_gpu_c_host.py builds and runs it and compares its output with the Python binding's. */
@@ -55,14 +58,16 @@ int main( int argc, char **argv )
     memset( &p, 0, sizeof( p ) );
     p.la.width = w; p.la.height = h;
     p.la.subpel_refine = 7; p.la.me_method = X264CU_ME_HEX; p.la.me_range = 16; p.la.mv_range = 512;     /* preset medium */
-    p.la.bframes = 3; p.la.weighted_bipred = 1; p.la.aq_mode = 0; p.la.mb_tree = 1; p.la.weighted_pred = 0;
+    p.la.bframes = 3; p.la.weighted_bipred = 1; p.la.aq_mode = 1; p.la.mb_tree = 1; p.la.weighted_pred = 0;
     p.keyint_max = 250; p.keyint_min = 25; p.scenecut_threshold = 40; p.b_adapt = 1; p.b_pyramid = 2; p.rc_lookahead = 20;
-    p.psy = 0; p.frame_reference = 3; p.fps_num = 25; p.fps_den = 1; p.qcompress = 0.6f;
+    p.psy = 0; p.frame_reference = 3; p.fps_num = 25; p.fps_den = 1; p.qcompress = 0.6f; p.aq_strength = 1.0f;
     x264cu_slicetype_t *st;
     if( x264cu_slicetype_open( ctx, &p, &st ) ) { fprintf( stderr, "slicetype_open: %s\n", x264cu_strerror( ctx ) ); return 1; }
 
     const int mbs = ( ( w + 15 ) / 16 ) * ( ( h + 15 ) / 16 );
-    uint8_t *luma = x264cu_malloc_host( ctx, (size_t)w * h );          /* page-locked: read in place by the copy engine */
+    const int cw = ( w + 1 ) / 2, ch = ( h + 1 ) / 2;
+    uint8_t *luma = x264cu_malloc_host( ctx, (size_t)w * h + 2 * (size_t)cw * ch );     /* page-locked: read in place by the copy engine */
+    uint8_t *cb = luma ? luma + (size_t)w * h : NULL, *cr = cb ? cb + (size_t)cw * ch : NULL;
     float *qp = malloc( sizeof( float ) * mbs );
     if( !luma || !qp ) return 1;
     int fed = 0, frame, type, rc = 0;
@@ -71,12 +76,13 @@ int main( int argc, char **argv )
         const uint8_t *pic = NULL;
         if( fed < n )
         {
-            if( in ) { if( fread( luma, 1, (size_t)w * h, in ) != (size_t)w * h ) { n = fed; continue; } }
-            else synth( luma, w, h, fed, n );
+            const size_t pic_bytes = (size_t)w * h + 2 * (size_t)cw * ch;
+            if( in ) { if( fread( luma, 1, pic_bytes, in ) != pic_bytes ) { n = fed; continue; } }
+            else { synth( luma, w, h, fed, n ); memset( cb, 128, 2 * (size_t)cw * ch ); }
             pic = luma;
             fed++;
         }
-        if( x264cu_slicetype_step( st, pic, w, NULL, &frame, &type ) ) { fprintf( stderr, "step: %s\n", x264cu_strerror( ctx ) ); rc = 1; break; }
+        if( x264cu_slicetype_step_i420( st, pic, w, cb, cr, cw, &frame, &type ) ) { fprintf( stderr, "step: %s\n", x264cu_strerror( ctx ) ); rc = 1; break; }
         if( frame >= 0 )
         {
             double mean = 0;

@@ -1,5 +1,5 @@
 """The boundary from the reference's side: a host written in plain C (examples/lookahead_host.c: only include/x264_b200.h and
-libx264_b200.so, built with gcc) drives the lookahead like x264_encoder_encode would.  Its frame types and MB-tree offsets must
+libx264_b200.so, built with gcc) reads raw I420 and drives the lookahead like x264_encoder_encode would (adaptive quantisation inside).  Its frame types and MB-tree offsets must
 be those the Python binding gets for the same pictures (which the other GPU tests pin to the reference)."""
 import os
 import subprocess
@@ -22,15 +22,19 @@ def test_plain_c_host_gets_the_same_decisions(tmp_path):
                            "-o", exe, "-L" + libdir, "-lx264_b200", "-Wl,-rpath," + libdir])
     w, h, n = 320, 192, 60
     frames = synth_sequence(w, h, n, seed=21, cut_at=37)
-    raw = str(tmp_path / "luma.raw")
-    np.stack(frames).tofile(raw)
+    rng = np.random.default_rng(2)
+    chroma = [(rng.integers(90, 170, (h // 2, w // 2), dtype=np.uint8), rng.integers(90, 170, (h // 2, w // 2), dtype=np.uint8)) for _ in range(n)]
+    raw = str(tmp_path / "pictures.i420")
+    with open(raw, "wb") as f:
+        for y, (cb, cr) in zip(frames, chroma):
+            f.write(y.tobytes()); f.write(cb.tobytes()); f.write(cr.tobytes())
     out = subprocess.run([exe, str(w), str(h), str(n), raw], check=True, capture_output=True, text=True, timeout=300).stdout
     got = [(int(l.split()[1]), l.split()[3], float(l.split()[5])) for l in out.strip().splitlines()]
     ctx = x.Context(0)
     try:
-        st = x.Slicetype(ctx, w, h, rc_lookahead=20, psy=0, aq_mode=0, mb_tree=1, bframes=3)
+        st = x.Slicetype(ctx, w, h, rc_lookahead=20, psy=0, aq_mode=1, aq_strength=1.0, mb_tree=1, bframes=3)
         qp = {}
-        want = st.decide(frames, qp)
+        want = st.decide(frames, qp, chroma=chroma)
         st.close()
     finally:
         ctx.close()

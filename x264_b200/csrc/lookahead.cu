@@ -1267,6 +1267,8 @@ static int la_put_host( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma,
             memcpy( la->h_luma[k] + y * st, h_luma + y * luma_stride, w );
         CU_CHECK( ctx, cudaMemcpyAsync( la->d_luma, la->h_luma[k], (size_t)st * h, cudaMemcpyHostToDevice, la->up_stream ) );
         CU_CHECK( ctx, cudaEventRecord( la->h_luma_ev[k], la->up_stream ) );
+        if( h_cb )      // chroma planes in page-locked memory beside a pageable luma: their copies must be over before the caller goes on
+            LA_TIMED( la->st.put_sync, la->st.n_put, CU_CHECK( ctx, cudaEventSynchronize( la->h_luma_ev[k] ) ) );
     }
     return la_put_finish( la, slot, la->d_luma, st, h_inv_qscale, h_cb ? &aq : nullptr );
 }
