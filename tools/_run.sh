@@ -1,2 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_mbtree.py tests/test_golden.py tests/test_gpu_slicetype.py tests/test_gpu_aq.py tests/test_gpu_c_host.py -m gpu -x -q 2>&1 | tail -6
-timeout 300 python bench.py --workload lookahead --quick --steps 10 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); r=d['roofline']; print('bench', round(d['value'],1), round(d['e2e']['value'],1))"
+timeout 300 python -m pytest tests/test_gpu_c_host.py -x -q 2>&1 | tail -2
+echo "== memcheck"; timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_aq.py tests/test_gpu_mbtree.py tests/test_gpu_mc.py tests/test_gpu_frame.py tests/test_golden.py -m gpu -x -q -k "not 3840 and not 1920 and not 1918 and not 352" 2>&1 | tail -4
+echo "== racecheck"; timeout 600 compute-sanitizer --tool racecheck --error-exitcode 3 python -m pytest tests/test_gpu_frame.py tests/test_gpu_lookahead.py -x -q -k "hpel and not 200 or cfg0" 2>&1 | tail -3

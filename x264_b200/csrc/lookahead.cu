@@ -998,7 +998,10 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     }
     la->luma_bytes = (size_t)( ( p->width + 63 ) & ~63 ) * p->height + 64;
     alloc( (void **)&la->d_luma, la->luma_bytes );
-    alloc( (void **)&la->d_chroma, la->luma_bytes / 2 + 256 );
+    {   // two chroma planes at a stride padded to 64 bytes (la_put_host)
+        const size_t cw = ( p->width + 1 ) >> 1, ch = ( p->height + 1 ) >> 1;
+        alloc( (void **)&la->d_chroma, 2 * ( ( cw + 63 ) & ~(size_t)63 ) * ch + 256 );
+    }
     alloc( (void **)&la->d_aq_q4, (size_t)( d.mb_count + 2 ) * 4 );
     alloc( (void **)&la->d_cost_mv, ( 2 * d.cost_len + 1 ) * 2 + 16 );
     alloc( (void **)&la->d_record, 64 );
