@@ -315,8 +315,7 @@ float x264cu_lookahead_get_weighted_cost_delta( x264cu_lookahead_t *la, int slot
  * x264cu_lookahead_frame_cost exactly where the reference calls slicetype_frame_cost -- MB-tree's and the
  * rate control's cost requests included, because the memoised B costs depend on request order
  * (slicetype.c:629-642).  Plain C; no device code.
- * Not covered (rejected at open): weighted P prediction analysis, VBV lookahead, open-GOP, intra refresh,
- * forced frame types, 2-pass stats.
+ * Not covered: VBV lookahead (rejected at open), forced frame types / qpfile, 2-pass stats, blu-ray compatible open-GOP.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct x264cu_slicetype x264cu_slicetype_t;
 
@@ -334,6 +333,8 @@ typedef struct
     int fps_num, fps_den;         /* h->param.i_fps_num / i_fps_den (constant frame rate); 0 = 25/1.  MB-tree's duration factors */
     float qcompress;              /* h->param.rc.f_qcompress; 0 = 0.6.  MB-tree strength = 5 * (1 - qcompress) */
     float aq_strength;            /* h->param.rc.f_aq_strength; 0 = 1.0.  Used by x264cu_slicetype_step_i420 (la.aq_mode = the mode, 0..3) */
+    int open_gop;                 /* h->param.b_open_gop (without b_bluray_compat) */
+    int intra_refresh;            /* h->param.b_intra_refresh: no keyframes but the first, scene cuts become I pictures */
 } x264cu_slicetype_params_t;
 
 enum { X264CU_TYPE_AUTO = 0, X264CU_TYPE_IDR = 1, X264CU_TYPE_I = 2, X264CU_TYPE_P = 3, X264CU_TYPE_BREF = 4,

@@ -86,6 +86,7 @@ XREF_API int xref_param( void *hv, const char *name )
     P( "stride", h->fdec->i_stride[0] ) P( "stride_lowres", h->fdec->i_stride_lowres )
     P( "width_lowres", h->fdec->i_width_lowres ) P( "lines_lowres", h->fdec->i_lines_lowres )
     P( "psy", h->param.analyse.b_psy ) P( "ref", h->param.i_frame_reference )
+    P( "open_gop", h->param.b_open_gop ) P( "intra_refresh", h->param.b_intra_refresh )
     P( "b_pyramid", h->param.i_bframe_pyramid ) P( "open_gop", h->param.b_open_gop ) P( "intra_refresh", h->param.b_intra_refresh )
 #undef P
     return -9999;

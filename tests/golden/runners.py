@@ -337,12 +337,7 @@ def run_st(backend, ci, params_bytes=None, ctx=None):
             types = host.decide_with(_libs.slicetype_oracle_lib(), p, frames)
         else:
             import x264_b200 as x
-            st = x.Slicetype(ctx, w, h, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
-                             b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy,
-                             frame_reference=p.frame_reference, rc_cqp=0,
-                             subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
-                             bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
-                             aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0, weighted_pred=p.la.weighted_pred)
+            st = x.Slicetype.from_params(ctx, p)
             try:
                 types = st.decide(frames)
             finally:
@@ -395,12 +390,7 @@ def run_mbtree(backend, params_bytes=None, ctx=None):
             types = host.decide_with(_libs.slicetype_oracle_lib(), p, frames, qp)
         else:
             import x264_b200 as x
-            st = x.Slicetype(ctx, w, h, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
-                             b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy,
-                             frame_reference=p.frame_reference, rc_cqp=0,
-                             subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
-                             bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
-                             aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0, weighted_pred=p.la.weighted_pred)
+            st = x.Slicetype.from_params(ctx, p)
             try:
                 types = st.decide(frames, qp)
             finally:

@@ -50,12 +50,7 @@ def slicetype_params(w, h, bframes=3, b_adapt=1, rc_lookahead=40, mb_tree=1, wei
 
 
 def gpu_decide(ctx, p, frames, qp=None, prefetch=None, run_ahead=None):
-    st = x.Slicetype(ctx, p.la.width, p.la.height, keyint_max=p.keyint_max, keyint_min=p.keyint_min,
-                     scenecut_threshold=p.scenecut_threshold, b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead,
-                     psy=p.psy, frame_reference=p.frame_reference, rc_cqp=0, subpel_refine=p.la.subpel_refine,
-                     me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range, bframes=p.la.bframes,
-                     bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred, aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree,
-                     vbv=0, weighted_pred=p.la.weighted_pred)
+    st = x.Slicetype.from_params(ctx, p)
     try:
         if prefetch is not None:
             st.set_prefetch(prefetch)

@@ -119,12 +119,7 @@ def test_mbtree_qp_offsets_end_to_end(ctx, case):
     else:
         pytest.skip("compiled reference did not travel (its option parsing provides the parameters)")
     want_orc = host.decide_with(slicetype_oracle_lib(), p, frames, qp_orc)
-    st = x.Slicetype(ctx, w, h, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
-                     b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy,
-                     frame_reference=p.frame_reference, rc_cqp=0,
-                     subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
-                     bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
-                     aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0, weighted_pred=p.la.weighted_pred)
+    st = x.Slicetype.from_params(ctx, p)
     try:
         got = st.decide(frames, qp_gpu)
     finally:
@@ -156,12 +151,7 @@ def test_default_path_i420_end_to_end(ctx, case):
     p, want = host.reference_types(preset, opts, w, h, frames, qp_ref)
     p.aq_strength = float(opts.split("aq-strength=")[1].split(":")[0]) if "aq-strength" in opts else 1.0
     want_orc = host.decide_with(slicetype_oracle_lib(), p, frames, qp_orc, chroma=(cb, cb))
-    st = x.Slicetype(ctx, w, h, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
-                     b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy,
-                     frame_reference=p.frame_reference, rc_cqp=0, aq_strength=p.aq_strength,
-                     subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
-                     bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
-                     aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0, weighted_pred=p.la.weighted_pred)
+    st = x.Slicetype.from_params(ctx, p)
     try:
         got = st.decide(frames, qp_gpu, chroma=[(cb, cb)] * n)
     finally:

@@ -31,12 +31,7 @@ def test_gpu_frame_types(ctx, case):
     if not have_ref():
         pytest.skip("compiled reference did not travel")
     p, want = host.reference_types(preset, opts, w, h, frames)
-    st = x.Slicetype(ctx, w, h, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
-                     b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy,
-                     frame_reference=p.frame_reference, rc_cqp=0,
-                     subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
-                     bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred,
-                     aq_mode=p.la.aq_mode, mb_tree=p.la.mb_tree, vbv=0, weighted_pred=p.la.weighted_pred)
+    st = x.Slicetype.from_params(ctx, p)
     try:
         got = st.decide(frames)
     finally:

@@ -28,6 +28,11 @@ CASES = [
     ("medium", "weightp=0:bframes=3:rc-lookahead=12", (96, 64), 36, 20),
     ("medium", "weightp=1:bframes=4:b-adapt=2:rc-lookahead=14", (96, 80), 36, 14),
     ("slow", "rc-lookahead=16:keyint=50", (128, 96), 40, 19),
+    # open GOP (keyframes become I, counted in display order) and periodic intra refresh (no keyframes but the first)
+    ("medium", "weightp=0:no-psy=1:open-gop=1:bframes=3:rc-lookahead=12:keyint=16:min-keyint=4", (96, 64), 60, 41),
+    ("medium", "open-gop=1:bframes=3:b-adapt=2:rc-lookahead=14:keyint=20", (96, 64), 56, 23),
+    ("medium", "weightp=0:no-psy=1:intra-refresh=1:bframes=2:rc-lookahead=10:keyint=24", (96, 64), 60, 31),
+    ("medium", "intra-refresh=1:rc-lookahead=12:keyint=30", (112, 80), 50, 17),
 ]
 
 
@@ -36,8 +41,10 @@ def params_from_ref(hnd, w, h):
     g = lambda n: r.xref_param(hnd, n.encode())
     la = LookaheadParams(w, h, g("subme"), min(g("me"), 2), g("merange"), g("mvrange"), g("bframes"), g("b_bias"), g("weightb"),
                          g("aq_mode"), g("mbtree"), g("vbv"), 0, -1 if g("weightp") < 0 else int(g("weightp") != 0))
-    return SlicetypeParams(la, g("keyint_max"), g("keyint_min"), g("scenecut"), g("b_adapt"), g("b_pyramid"), g("lookahead"),
-                           g("psy"), g("ref"), 0)
+    p = SlicetypeParams(la, g("keyint_max"), g("keyint_min"), g("scenecut"), g("b_adapt"), g("b_pyramid"), g("lookahead"),
+                        g("psy"), g("ref"), 0)
+    p.open_gop, p.intra_refresh = g("open_gop"), g("intra_refresh")
+    return p
 
 
 def decide_with(lib, p, frames, qp_out=None, chroma=None):

@@ -33,7 +33,8 @@ me_result_dtype = np.dtype([("mv", np.int16, (2,)), ("cost", np.int32), ("cost_m
 class SlicetypeParams(C.Structure):
     _fields_ = [("la", LookaheadParams)] + [(n, C.c_int) for n in ("keyint_max", "keyint_min", "scenecut_threshold", "b_adapt",
                                                                   "b_pyramid", "rc_lookahead", "psy", "frame_reference", "rc_cqp",
-                                                                  "fps_num", "fps_den")] + [("qcompress", C.c_float), ("aq_strength", C.c_float)]
+                                                                  "fps_num", "fps_den")] + [("qcompress", C.c_float), ("aq_strength", C.c_float),
+                                                                                                  ("open_gop", C.c_int), ("intra_refresh", C.c_int)]
 
 
 TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "BREF", 5: "B"}
@@ -212,7 +213,7 @@ class Slicetype:
     decide(frames) runs a whole sequence the way x264_encoder_encode would and returns [(display_index, type)] in coded order."""
 
     def __init__(self, ctx, width, height, keyint_max=250, keyint_min=25, scenecut_threshold=40, b_adapt=1, b_pyramid=2,
-                 rc_lookahead=40, psy=1, frame_reference=3, rc_cqp=0, fps_num=0, fps_den=0, qcompress=0.0, aq_strength=0.0, **la_kwargs):
+                 rc_lookahead=40, psy=1, frame_reference=3, rc_cqp=0, fps_num=0, fps_den=0, qcompress=0.0, aq_strength=0.0, open_gop=0, intra_refresh=0, **la_kwargs):
         self.ctx, self.L = ctx, ctx.L
         la = dict(subpel_refine=7, me_method=1, me_range=16, mv_range=512, bframes=3, bframe_bias=0, weighted_bipred=1,
                   aq_mode=1, mb_tree=1, vbv=0, n_slots=0, weighted_pred=0)
@@ -220,13 +221,24 @@ class Slicetype:
         lp = LookaheadParams(width, height, la["subpel_refine"], la["me_method"], la["me_range"], la["mv_range"], la["bframes"],
                              la["bframe_bias"], la["weighted_bipred"], la["aq_mode"], la["mb_tree"], la["vbv"], la["n_slots"], la["weighted_pred"])
         self.p = SlicetypeParams(lp, keyint_max, keyint_min, scenecut_threshold, b_adapt, b_pyramid, rc_lookahead, psy,
-                                 frame_reference, rc_cqp, fps_num, fps_den, qcompress, aq_strength)
+                                 frame_reference, rc_cqp, fps_num, fps_den, qcompress, aq_strength, open_gop, intra_refresh)
         h = C.c_void_p()
         if self.L.x264cu_slicetype_open(ctx.h, C.byref(self.p), C.byref(h)) != 0:
             from .binding import X264CUError
             raise X264CUError("x264cu_slicetype_open failed: " + ctx.L.x264cu_strerror(ctx.h).decode())
         self.h = h
         self.mb_count = ((width + 15) // 16) * ((height + 15) // 16)
+
+    @classmethod
+    def from_params(cls, ctx, p):
+        """from a filled SlicetypeParams (e.g. mirrored from an opened reference encoder by the tests)"""
+        return cls(ctx, p.la.width, p.la.height, keyint_max=p.keyint_max, keyint_min=p.keyint_min, scenecut_threshold=p.scenecut_threshold,
+                   b_adapt=p.b_adapt, b_pyramid=p.b_pyramid, rc_lookahead=p.rc_lookahead, psy=p.psy, frame_reference=p.frame_reference,
+                   rc_cqp=p.rc_cqp, fps_num=p.fps_num, fps_den=p.fps_den, qcompress=p.qcompress, aq_strength=p.aq_strength,
+                   open_gop=p.open_gop, intra_refresh=p.intra_refresh,
+                   subpel_refine=p.la.subpel_refine, me_method=p.la.me_method, me_range=p.la.me_range, mv_range=p.la.mv_range,
+                   bframes=p.la.bframes, bframe_bias=p.la.bframe_bias, weighted_bipred=p.la.weighted_bipred, aq_mode=p.la.aq_mode,
+                   mb_tree=p.la.mb_tree, vbv=p.la.vbv, weighted_pred=p.la.weighted_pred)
 
     def close(self):
         if self.h:

@@ -197,7 +197,7 @@ static int scenecut_internal( x264cu_slicetype_t *s, st_frame_t **frames, int p0
     float f_thresh_min = f_thresh_max * 0.25;
     if( s->p.keyint_min == s->p.keyint_max )
         f_thresh_min = f_thresh_max;
-    if( i_gop_size <= s->p.keyint_min / 4 )
+    if( i_gop_size <= s->p.keyint_min / 4 || s->p.intra_refresh )
         f_bias = f_thresh_min / 4;
     else if( i_gop_size <= s->p.keyint_min )
         f_bias = f_thresh_min * i_gop_size / s->p.keyint_min;
@@ -363,9 +363,11 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
         return;
     }
     keyint_limit = s->p.keyint_max - frames[0]->i_frame + s->i_last_keyframe - 1;
-    orig_num_frames = num_frames = framecnt < keyint_limit ? framecnt : keyint_limit;
+    orig_num_frames = num_frames = s->p.intra_refresh ? framecnt : framecnt < keyint_limit ? framecnt : keyint_limit;
     if( s->p.psy && s->p.la.mb_tree )
         num_frames = framecnt;
+    else if( s->p.open_gop && num_frames < framecnt )
+        num_frames++;
     else if( num_frames == 0 )
     {
         frames[1]->i_type = T_I;
@@ -491,6 +493,7 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
         macroblock_tree( s, frames, num_frames < s->p.keyint_max ? num_frames : s->p.keyint_max, keyframe );
 
     /* Enforce keyframe limit. */
+    if( !s->p.intra_refresh )
     {
         int last_keyframe = s->i_last_keyframe, last_possible = 0;
         for( int j = 1; j <= num_frames; j++ )
@@ -498,7 +501,7 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
             st_frame_t *frm = frames[j];
             int keyframe_dist = frm->i_frame - last_keyframe;
             if( AUTO_OR_I( frm->i_forced_type ) )
-                if( !IS_B( frames[j-1]->i_forced_type ) )
+                if( s->p.open_gop || !IS_B( frames[j-1]->i_forced_type ) )
                     last_possible = j;
             if( keyframe_dist >= s->p.keyint_max )
             {
@@ -510,11 +513,15 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
                 }
                 last_possible = 0;
                 if( frm->i_type != T_IDR )
-                    frm->i_type = T_IDR;
+                    frm->i_type = s->p.open_gop ? T_I : T_IDR;
             }
             if( frm->i_type == T_I && keyframe_dist >= s->p.keyint_min )
-                if( frm->i_forced_type != T_I )
+            {
+                if( s->p.open_gop )
+                    last_keyframe = frm->i_frame;             /* display order (no blu-ray compatibility mode here) */
+                else if( frm->i_forced_type != T_I )
                     frm->i_type = T_IDR;
+            }
             if( frm->i_type == T_IDR )
             {
                 last_keyframe = frm->i_frame;
@@ -546,16 +553,22 @@ static int slicetype_decide( x264cu_slicetype_t *s )
             frm->i_type = T_B;
         else if( frm->i_type == T_BREF && s->p.b_pyramid == 2 && brefs && s->p.frame_reference <= ( brefs + 3 ) )
             frm->i_type = T_B;
-        /* Limit GOP size */
-        if( frm->i_frame - s->i_last_keyframe >= s->p.keyint_max )
+        /* Limit GOP size, slicetype.c:1831-1845 */
+        if( ( !s->p.intra_refresh || frm->i_frame == 0 ) && frm->i_frame - s->i_last_keyframe >= s->p.keyint_max )
         {
+            const int key = s->p.open_gop && s->i_last_keyframe >= 0 ? T_I : T_IDR;
             if( frm->i_type == T_AUTO || frm->i_type == T_I )
-                frm->i_type = T_IDR;
-            if( frm->i_type != T_IDR )
-                frm->i_type = T_IDR;
+                frm->i_type = key;
+            if( frm->i_type != T_IDR && !( s->p.open_gop && frm->i_type == T_I ) )
+                frm->i_type = key;
         }
         if( frm->i_type == T_I && frm->i_frame - s->i_last_keyframe >= s->p.keyint_min )
-            frm->i_type = T_IDR;
+        {
+            if( s->p.open_gop )
+                s->i_last_keyframe = frm->i_frame;              /* display order */
+            else
+                frm->i_type = T_IDR;
+        }
         if( frm->i_type == T_IDR )
         {
             s->i_last_keyframe = frm->i_frame;
