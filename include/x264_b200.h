@@ -315,7 +315,7 @@ float x264cu_lookahead_get_weighted_cost_delta( x264cu_lookahead_t *la, int slot
  * x264cu_lookahead_frame_cost exactly where the reference calls slicetype_frame_cost -- MB-tree's and the
  * rate control's cost requests included, because the memoised B costs depend on request order
  * (slicetype.c:629-642).  Plain C; no device code.
- * Not covered: VBV lookahead (rejected at open), forced frame types / qpfile, 2-pass stats, blu-ray compatible open-GOP.
+ * Not covered: VBV lookahead (rejected at open), 2-pass stats, blu-ray compatible open-GOP.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct x264cu_slicetype x264cu_slicetype_t;
 
@@ -338,7 +338,7 @@ typedef struct
 } x264cu_slicetype_params_t;
 
 enum { X264CU_TYPE_AUTO = 0, X264CU_TYPE_IDR = 1, X264CU_TYPE_I = 2, X264CU_TYPE_P = 3, X264CU_TYPE_BREF = 4,
-       X264CU_TYPE_B = 5 };       /* x264.h:274-280 */
+       X264CU_TYPE_B = 5, X264CU_TYPE_KEYFRAME = 6 };       /* x264.h:274-281 */
 
 int  x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *params, x264cu_slicetype_t **out );
 void x264cu_slicetype_close( x264cu_slicetype_t *st );
@@ -364,6 +364,10 @@ void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *st, int prefetch );
  * analysis never looks at more than i_slicetype_length+1 pictures (b_deterministic, slicetype.c:1480-1485), so the
  * decisions do not change -- only the searches of the newest pictures get time to finish on the second stream. */
 void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *st, int pictures );
+/* pic_in->i_type of the NEXT picture queued with x264cu_slicetype_step* (forced frame types: a qpfile, an application's keyframe
+ * request; X264CU_TYPE_KEYFRAME = IDR, or I with open-GOP); AUTO again afterwards.  The analysis respects it exactly as
+ * x264_slicetype_analyse / x264_slicetype_decide do (i_forced_type, slicetype.c:1534-1539, :1656, :1690-1738, :1803-1828). */
+int  x264cu_slicetype_set_next_type( x264cu_slicetype_t *st, int type );
 /* x264cu_lookahead_set_async_upload for the lookahead underneath: page-locked pictures are read in place and must stay
  * unmodified until `on` more pictures have been queued (1 means 4) */
 void x264cu_slicetype_set_async_upload( x264cu_slicetype_t *st, int on );

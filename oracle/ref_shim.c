@@ -563,6 +563,10 @@ XREF_API void xref_set_qp_capture( float *buf ) { xref_qp_capture = buf; }
 #define XREF_CAPTURE_QP() do { if( xref_qp_capture && h->fenc ) \
     memcpy( xref_qp_capture + (size_t)n_out * h->mb.i_mb_count, h->fenc->f_qp_offset, h->mb.i_mb_count * sizeof(float) ); } while( 0 )
 
+/* when set: pic_in.i_type of picture i (X264_TYPE_*; forced frame types as a qpfile / an application would give them) */
+static const int *xref_forced_types;
+XREF_API void xref_set_forced_types( const int *types ) { xref_forced_types = types; }
+
 XREF_API int xref_encode_types( void *hv, const uint8_t *luma, int n, int *out_idx, int *out_type )
 {
     x264_t *h = hv;
@@ -582,7 +586,7 @@ XREF_API int xref_encode_types( void *hv, const uint8_t *luma, int n, int *out_i
         pic_in.img.plane[1] = chroma; pic_in.img.i_stride[1] = cw;
         pic_in.img.plane[2] = chroma; pic_in.img.i_stride[2] = cw;
         pic_in.i_pts = i;
-        pic_in.i_type = X264_TYPE_AUTO;
+        pic_in.i_type = xref_forced_types ? xref_forced_types[i] : X264_TYPE_AUTO;
         int sz = x264_encoder_encode( h, &nal, &i_nal, &pic_in, &pic_out );
         if( sz < 0 ) { free( chroma ); return -1; }
         if( sz > 0 ) { XREF_CAPTURE_QP(); out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }

@@ -91,3 +91,20 @@ def test_prefetch_with_weighted_prediction(ctx, mode):
         outs.append(st.decide(frames))
         st.close()
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("case", host.FORCED_CASES)
+def test_gpu_forced_frame_types(ctx, case):
+    """pic_in.i_type forced for some pictures (IDR / I / P / BREF / B / KEYFRAME): the decisions of the reference encoder"""
+    preset, opts, (w, h), n, cut, forced_at = case
+    frames = synth_sequence(w, h, n, seed=n + w + 9, cut_at=cut)
+    forced = [forced_at.get(i, 0) for i in range(n)]
+    if not have_ref():
+        pytest.skip("compiled reference did not travel")
+    p, want = host.reference_types(preset, opts, w, h, frames, forced=forced)
+    st = x.Slicetype.from_params(ctx, p)
+    try:
+        got = st.decide(frames, forced=forced)
+    finally:
+        st.close()
+    assert got == want, (case, [z for z in zip(got, want) if z[0] != z[1]][:6])

@@ -47,7 +47,7 @@ def params_from_ref(hnd, w, h):
     return p
 
 
-def decide_with(lib, p, frames, qp_out=None, chroma=None):
+def decide_with(lib, p, frames, qp_out=None, chroma=None, forced=None):
     """qp_out: dict filled with frame -> f_qp_offset (MB-tree's output) for every non-B picture, read when it is returned;
     chroma: (cb, cr) planes fed with every picture through x264cu_slicetype_step_i420 (adaptive quantisation inside)"""
     lib.x264cu_slicetype_open.argtypes = [C.c_void_p, C.POINTER(SlicetypeParams), C.POINTER(C.c_void_p)]
@@ -68,7 +68,10 @@ def decide_with(lib, p, frames, qp_out=None, chroma=None):
             qp_out[fr.value] = q
 
     lib.x264cu_slicetype_step_i420.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    for f in frames:
+    lib.x264cu_slicetype_set_next_type.argtypes = [C.c_void_p, C.c_int]
+    for i, f in enumerate(frames):
+        if forced is not None and forced[i]:
+            assert lib.x264cu_slicetype_set_next_type(st, int(forced[i])) == 0
         if chroma is None:
             assert lib.x264cu_slicetype_step(st, f.ctypes.data, f.shape[1], None, C.byref(fr), C.byref(ty)) == 0
         else:
@@ -85,7 +88,7 @@ def decide_with(lib, p, frames, qp_out=None, chroma=None):
     return out
 
 
-def reference_types(preset, opts, w, h, frames, qp_out=None):
+def reference_types(preset, opts, w, h, frames, qp_out=None, forced=None):
     """qp_out: dict filled with frame -> the f_qp_offset array the reference encoder used for it"""
     r = ref()
     r.xref_encode_types.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -101,7 +104,11 @@ def reference_types(preset, opts, w, h, frames, qp_out=None):
         nmb = ((w + 15) // 16) * ((h + 15) // 16)
         cap = np.zeros((n + 8, nmb), np.float32)
         r.xref_set_qp_capture(cap.ctypes.data if qp_out is not None else None)
+        r.xref_set_forced_types.argtypes = [C.c_void_p]
+        ft = (C.c_int * n)(*[int(t) for t in forced]) if forced is not None else None
+        r.xref_set_forced_types(ft)
         k = r.xref_encode_types(hnd, luma.ctypes.data, n, idx, typ)
+        r.xref_set_forced_types(None)
         r.xref_set_qp_capture(None)
         assert k == n
         if qp_out is not None:
@@ -187,3 +194,23 @@ def test_default_presets_with_adaptive_quant_match_reference_encoder(case):
     got = decide_with(slicetype_oracle_lib(), p, frames, qp_got, chroma=flat)
     compared, exact, worst = mbtree_compare(want, got, qp_ref, qp_got, n, p.rc_lookahead)
     assert compared >= 5 and exact == compared, "f_qp_offset bit-exact on %d of %d pictures, worst |diff| %.3g" % (exact, compared, worst)
+
+
+# forced frame types (pic_in.i_type: what a qpfile or an application's keyframe request sets): 1 IDR, 2 I, 3 P, 4 BREF, 5 B, 6 KEYFRAME
+FORCED_CASES = [
+    ("medium", "weightp=0:no-psy=1:bframes=3:rc-lookahead=10:keyint=60", (96, 64), 50, 27, {9: 1, 20: 6, 33: 2, 41: 3}),
+    ("medium", "bframes=3:b-adapt=2:rc-lookahead=12", (96, 64), 48, 30, {5: 5, 6: 5, 7: 3, 16: 6, 24: 4, 25: 5, 37: 1}),
+    ("medium", "weightp=0:no-psy=1:open-gop=1:bframes=2:rc-lookahead=8:keyint=20", (96, 64), 50, 35, {11: 6, 12: 5, 30: 2}),
+    ("medium", "weightp=0:no-mbtree=1:bframes=3:b-adapt=0:rc-lookahead=0:scenecut=0", (64, 48), 40, None, {3: 3, 10: 1, 11: 5, 12: 5, 13: 5, 14: 5, 20: 6}),
+]
+
+
+@pytest.mark.parametrize("case", FORCED_CASES)
+def test_forced_frame_types_match_reference_encoder(case):
+    preset, opts, (w, h), n, cut, forced_at = case
+    frames = synth_sequence(w, h, n, seed=n + w + 9, cut_at=cut)
+    forced = [forced_at.get(i, 0) for i in range(n)]
+    p, want = reference_types(preset, opts, w, h, frames, forced=forced)
+    got = decide_with(slicetype_oracle_lib(), p, frames, forced=forced)
+    assert got == want, (case, [x for x in zip(got, want) if x[0] != x[1]][:6])
+    assert all(dict(want)[i] in ((1, 2) if t == 6 else (t,)) for i, t in forced_at.items() if t in (1, 6)), "forced keyframes were honoured"

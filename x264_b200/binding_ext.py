@@ -52,6 +52,7 @@ def bind(L):
     L.x264cu_slicetype_set_async_upload.argtypes = [vp, ci]
     L.x264cu_slicetype_get_qp_offset.argtypes = [vp, ci, vp]
     L.x264cu_slicetype_set_shard.argtypes = [vp, ci, ci, vp, vp]
+    L.x264cu_slicetype_set_next_type.argtypes = [vp, ci]
     L.x264cu_slicetype_step_i420.argtypes = [vp, vp, ss, vp, vp, ss, C.POINTER(ci), C.POINTER(ci)]
     L.x264cu_slicetype_lookahead.argtypes = [vp]
     L.x264cu_slicetype_lookahead.restype = vp
@@ -298,8 +299,12 @@ class Slicetype:
         self.ctx.check(self.L.x264cu_slicetype_get_qp_offset(self.h, int(frame), out.ctypes.data))
         return out
 
-    def decide(self, frames, qp_out=None, chroma=None):
-        """qp_out: dict filled with frame -> f_qp_offset for every non-B picture; chroma: [(cb, cr)] per picture -> step_i420"""
+    def set_next_type(self, t):
+        self.ctx.check(self.L.x264cu_slicetype_set_next_type(self.h, int(t)))
+
+    def decide(self, frames, qp_out=None, chroma=None, forced=None):
+        """qp_out: dict filled with frame -> f_qp_offset for every non-B picture; chroma: [(cb, cr)] per picture -> step_i420;
+        forced: pic_in.i_type per picture (0 = auto)"""
         out = []
 
         def note(fr, ty):
@@ -308,6 +313,8 @@ class Slicetype:
                 qp_out[fr] = self.get_qp_offset(fr)
 
         for i, f in enumerate(frames):
+            if forced is not None and forced[i]:
+                self.set_next_type(forced[i])
             fr, ty = self.step(f) if chroma is None else self.step_i420(f, chroma[i][0], chroma[i][1])
             if fr >= 0:
                 note(fr, ty)

@@ -22,6 +22,7 @@ static double st_now( void ) { struct timespec t; clock_gettime( CLOCK_MONOTONIC
 #define T_P X264CU_TYPE_P
 #define T_BREF X264CU_TYPE_BREF
 #define T_B X264CU_TYPE_B
+#define T_KEYFRAME X264CU_TYPE_KEYFRAME
 #define IS_I( t ) ( ( t ) == T_I || ( t ) == T_IDR )
 #define IS_B( t ) ( ( t ) == T_B || ( t ) == T_BREF )
 #define AUTO_OR_I( t ) ( ( t ) == T_AUTO || IS_I( t ) )
@@ -71,6 +72,7 @@ struct x264cu_slicetype
     x264cu_exchange_fn shard_fn;
     void *shard_user;
     int xj_slot[256], xj_list[256], xj_dist[256], xj_owner[256], xj_frame[256], n_xj;
+    int next_forced_type;                 /* pic_in->i_type of the next queued picture (x264cu_slicetype_set_next_type) */
 };
 
 int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame );
@@ -380,6 +382,10 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
             frames[1]->i_type = T_I;
         return;
     }
+    /* Replace forced keyframes with I/IDR-frames, slicetype.c:1534-1539 */
+    for( int j = 1; j <= num_frames; j++ )
+        if( frames[j]->i_type == T_KEYFRAME )
+            frames[j]->i_type = s->p.open_gop ? T_I : T_IDR;
     /* Close GOP at IDR-frames */
     for( int j = 2; j <= num_frames; j++ )
         if( frames[j]->i_type == T_IDR && AUTO_OR_B( frames[j-1]->i_type ) )
@@ -553,6 +559,8 @@ static int slicetype_decide( x264cu_slicetype_t *s )
             frm->i_type = T_B;
         else if( frm->i_type == T_BREF && s->p.b_pyramid == 2 && brefs && s->p.frame_reference <= ( brefs + 3 ) )
             frm->i_type = T_B;
+        if( frm->i_type == T_KEYFRAME )
+            frm->i_type = s->p.open_gop ? T_I : T_IDR;
         /* Limit GOP size, slicetype.c:1831-1845 */
         if( ( !s->p.intra_refresh || frm->i_frame == 0 ) && frm->i_frame - s->i_last_keyframe >= s->p.keyint_max )
         {
@@ -832,6 +840,8 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
         if( !f ) return -1;
         f->i_frame = s->i_input++;
         f->slot = slot;
+        f->i_type = f->i_forced_type = s->next_forced_type;      /* x264_frame_copy_picture, frame.c:370-376 */
+        s->next_forced_type = T_AUTO;
         f->b_scenecut = 1;
         s->slot_used[slot] = 1;
         s->next[s->n_next++] = f;
@@ -924,6 +934,13 @@ int x264cu_slicetype_set_shard( x264cu_slicetype_t *s, int rank, int world, x264
 {
     if( !s || s->i_input || world < 1 || world > 64 || rank < 0 || rank >= world || ( world > 1 && !fn ) ) return -1;
     s->shard_rank = rank; s->shard_world = world; s->shard_fn = fn; s->shard_user = user;
+    return 0;
+}
+
+int x264cu_slicetype_set_next_type( x264cu_slicetype_t *s, int type )
+{
+    if( !s || type < T_AUTO || type > T_KEYFRAME ) return -1;
+    s->next_forced_type = type;
     return 0;
 }
 
