@@ -620,7 +620,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for cpu_baseline")
-    ap.add_argument("--weightp", type=int, default=0, choices=[0, 1], help="lookahead workload: weightp analysis (slicetype.c:284-501) on")
+    ap.add_argument("--weightp", type=int, default=1, choices=[0, 1],
+                    help="lookahead workload: the lookahead weight analysis (slicetype.c:284-501) and psy, as in preset medium (default); 0: off")
     ap.add_argument("--quick", action="store_true", help="tuning runs: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
 

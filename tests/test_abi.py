@@ -30,3 +30,19 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in txt and "libx264ref" not in txt and "oracle/" not in txt, f
+
+
+def test_open_fails_loudly_without_a_device():
+    """there is no CPU fallback: on a machine without an sm_100 GPU x264cu_open returns -1 and says why"""
+    import ctypes as C
+    import shutil
+    import subprocess
+    import x264_b200 as x
+    if shutil.which("nvidia-smi") and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0:
+        import pytest
+        pytest.skip("a GPU is present")
+    L = x.lib()
+    h = C.c_void_p()
+    assert L.x264cu_open(C.byref(h), 0) == -1 and not h.value
+    msg = L.x264cu_strerror(None).decode()
+    assert "no CPU fallback" in msg or "CUDA" in msg, msg
