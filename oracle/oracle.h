@@ -16,7 +16,7 @@ extern "C" {
 enum { ORC_PIXEL_16x16, ORC_PIXEL_16x8, ORC_PIXEL_8x16, ORC_PIXEL_8x8, ORC_PIXEL_8x4, ORC_PIXEL_4x8,
        ORC_PIXEL_4x4, ORC_PIXEL_4x16, ORC_PIXEL_NB };
 enum { ORC_SAD, ORC_SSD, ORC_SATD, ORC_SA8D };
-enum { ORC_ME_DIA, ORC_ME_HEX, ORC_ME_UMH, ORC_ME_ESA };   /* x264.h X264_ME_DIA/HEX/UMH/ESA */
+enum { ORC_ME_DIA, ORC_ME_HEX, ORC_ME_UMH, ORC_ME_ESA, ORC_ME_TESA };   /* x264.h X264_ME_DIA/HEX/UMH/ESA/TESA */
 #define ORC_COST_MAX (1<<28)                             /* encoder/me.h:30 */
 #define ORC_PAD 32                                       /* common/frame.h:32-33 PADH/PADV */
 
@@ -83,6 +83,8 @@ typedef struct
 } orc_me_t;
 
 void orc_me_search_ref( const orc_me_ctx_t *c, orc_me_t *m, const int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );
+/* x264_me_refine_bidir_satd (me.c:1027-1183): refines m0->mv / m1->mv jointly; reads c->mv_min_spel / mv_max_spel / mbcmp_is_satd */
+void orc_me_refine_bidir_satd( const orc_me_ctx_t *c, orc_me_t *m0, orc_me_t *m1, int i_weight );
 
 /* ---- lowres lookahead (oracle_lookahead.c) ---- */
 typedef struct

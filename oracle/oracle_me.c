@@ -2,8 +2,9 @@
  * ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.h).  Scalar restatement of the reference's block-match
  * search: predictor stage, DIA / HEX / UMH integer search and the sub-pel refinement
  * (encoder/me.c:182-798 x264_me_search_ref, :865-992 refine_subpel), luma only (no chroma ME, which the
- * lookahead disables: slicetype.c:60).  fpelcmp is SAD (encoder.c:1409-1427, TESA excluded); mbcmp is SATD
- * iff the encoder's subme > 1.  Written from the algorithm as a small state machine over one `search_t`;
+ * lookahead disables: slicetype.c:60), the exhaustive searches ESA / TESA (me.c:618-771) with their successive-elimination
+ * prefilter, and x264_me_refine_bidir_satd (me.c:1027-1183).  fpelcmp is SAD, except under TESA where it is the same
+ * metric as mbcmp (encoder.c:1409-1427); mbcmp is SATD iff the encoder's subme > 1.  Written from the algorithm as a small state machine over one `search_t`;
  * tie-breaking follows the reference's packed (cost<<k)+index comparisons exactly (me.c:325-341, :369-418).
  *
  * Parity status: PINNED against the compiled reference's x264_me_search_ref (tests/test_oracle_me.py).
@@ -33,11 +34,16 @@ static inline int in_range( const search_t *s, int mx, int my )     /* CHECK_MVR
     return mx >= s->x_min && mx <= s->x_max && my >= s->y_min && my <= s->y_max;
 }
 
-/* integer-pel SAD against the (weighted) full-pel plane + mv bits: COST_MV's value, me.c:63-70 */
+/* fpelcmp is SATD only when the encoder runs TESA with subme > 1 (encoder.c:1409-1427) */
+static inline int fpel_satd( const search_t *s ) { return s->c->me_method == ORC_ME_TESA && s->c->mbcmp_is_satd; }
+
+/* integer-pel fpelcmp against the (weighted) full-pel plane: COST_MV's value without the mv bits, me.c:63-70 */
 static int sad_fpel( const search_t *s, int mx, int my )
 {
     const orc_me_t *m = s->m;
-    return orc_sad( m->p_fenc, m->fenc_stride, m->p_fref_w + (intptr_t)my*m->stride + mx, m->stride, s->bw, s->bh );
+    const uint8_t *r = m->p_fref_w + (intptr_t)my*m->stride + mx;
+    return fpel_satd( s ) ? orc_satd( m->p_fenc, m->fenc_stride, r, m->stride, s->bw, s->bh )
+                          : orc_sad ( m->p_fenc, m->fenc_stride, r, m->stride, s->bw, s->bh );
 }
 static inline int bits_fpel( const search_t *s, int mx, int my ) { return s->cmx[mx*4] + s->cmy[my*4]; }   /* BITS_MVD */
 static int cost_fpel( const search_t *s, int mx, int my ) { return sad_fpel( s, mx, my ) + bits_fpel( s, mx, my ); }
@@ -54,8 +60,8 @@ static int cost_qpel( const search_t *s, int mx, int my, int use_mbcmp )
     const orc_me_t *m = s->m;
     uint8_t blk[16*16];
     orc_mc_luma( blk, 16, m->p_fref, m->stride, mx, my, s->bw, s->bh, &m->weight );
-    int d = ( use_mbcmp && s->c->mbcmp_is_satd ) ? orc_satd( m->p_fenc, m->fenc_stride, blk, 16, s->bw, s->bh )
-                                                 : orc_sad ( m->p_fenc, m->fenc_stride, blk, 16, s->bw, s->bh );
+    int d = ( use_mbcmp ? s->c->mbcmp_is_satd : fpel_satd( s ) ) ? orc_satd( m->p_fenc, m->fenc_stride, blk, 16, s->bw, s->bh )
+                                                                 : orc_sad ( m->p_fenc, m->fenc_stride, blk, 16, s->bw, s->bh );
     return d + s->cmx[mx] + s->cmy[my];
 }
 
@@ -145,6 +151,126 @@ static void hex_search( search_t *s, int me_range )
     s->bmx += square1[packed & 15][0];
     s->bmy += square1[packed & 15][1];
     s->bcost = packed >> 4;
+}
+
+/* ---- exhaustive search with successive elimination, me.c:618-771 -------------------------------------------------------
+ * The reference keeps, per reference frame, an "integral" plane holding the pixel sum of the 8x8 (and 4x4) block at every
+ * position of the UNWEIGHTED padded plane (mc.c:424-456, :748-783; uint16 arithmetic, exact because 64*255 < 65536) and
+ * drops a position before measuring it when ads = sum over the block's 8x8 / 4x4 sub-blocks |dc(fenc) - dc(ref)| + the x mv
+ * cost reaches a threshold (pixel.c:759-803).  The sub-block layout per partition (me.c:637-654 with pixf.ads, pixel.c:860,
+ * :1660): 16x16 four 8x8s, 16x8 / 8x16 two 8x8s, 8x8 one, 8x4 / 4x8 two 4x4s, 4x4 one.  Here the sums are taken from the
+ * pixels directly.  ESA: threshold = the best cost, survivors go through COST_MV in raster order.  TESA: threshold
+ * 17/16 of the best SAD, survivors within sad_thresh/8 of the running best SAD are listed, the list is thinned to
+ * me_range/2 entries and those are measured with fpelcmp (SATD). */
+static int block_sum( const uint8_t *p, intptr_t stride, int w, int h )
+{
+    int v = 0;
+    for( int y = 0; y < h; y++ )
+        for( int x = 0; x < w; x++ )
+            v += p[y*stride + x];
+    return v;
+}
+
+typedef struct { int sb, nx, ny; int enc_dc[4]; } ads_t;
+
+static void ads_init( const search_t *s, ads_t *a )
+{
+    a->sb = ( s->bw >= 8 && s->bh >= 8 ) ? 8 : 4;
+    a->nx = s->bw / a->sb; a->ny = s->bh / a->sb;
+    for( int j = 0; j < a->ny; j++ )
+        for( int i = 0; i < a->nx; i++ )
+            a->enc_dc[j*a->nx + i] = block_sum( s->m->p_fenc + j*a->sb*s->m->fenc_stride + i*a->sb, s->m->fenc_stride, a->sb, a->sb );
+}
+
+static int ads_at( const search_t *s, const ads_t *a, int mx, int my )   /* pixf.ads' value without the mv cost */
+{
+    const orc_me_t *m = s->m;
+    const uint8_t *r = m->p_fref[0] + (intptr_t)my*m->stride + mx;      /* the integral image is built from the unweighted plane */
+    int v = 0;
+    for( int j = 0; j < a->ny; j++ )
+        for( int i = 0; i < a->nx; i++ )
+            v += abs( a->enc_dc[j*a->nx + i] - block_sum( r + j*a->sb*m->stride + i*a->sb, m->stride, a->sb, a->sb ) );
+    return v;
+}
+
+typedef struct { int sad; int16_t mv[2]; } mvsad_t;
+
+static void exhaustive_search( search_t *s, int me_range )
+{
+    const orc_me_t *m = s->m;
+    const int min_x = imax( s->bmx - me_range, s->x_min ), min_y = imax( s->bmy - me_range, s->y_min );
+    const int max_x = imin( s->bmx + me_range, s->x_max ), max_y = imin( s->bmy + me_range, s->y_max );
+    const int width = ( max_x - min_x + 3 ) & ~3;       /* rounded up: reaches up to 3 positions past mv_x_max, as the reference */
+    ads_t a;
+    ads_init( s, &a );
+    if( s->c->me_method == ORC_ME_ESA )
+    {   /* me.c:751-768: "just ADS and SAD" */
+        for( int my = min_y; my <= max_y; my++ )
+        {
+            int ycost = s->cmy[my*4];
+            if( s->bcost <= ycost )
+                continue;
+            const int thresh = s->bcost - ycost;        /* fixed for the whole row (me.c:760) */
+            for( int mx = min_x; mx < min_x + width; mx++ )
+                if( ads_at( s, &a, mx, my ) + s->cmx[mx*4] < thresh )
+                    try_fpel( s, mx, my );
+        }
+        return;
+    }
+    /* TESA, me.c:656-747 */
+    int rows = max_y - min_y + 1;
+    mvsad_t *list = malloc( sizeof(mvsad_t) * ( rows > 0 && width > 0 ? (size_t)rows * width : 1 ) );
+    int n = 0;
+    int sad_thresh = me_range <= 16 ? 10 : me_range <= 24 ? 11 : 12;
+    int bsad = orc_sad( m->p_fenc, m->fenc_stride, m->p_fref_w + (intptr_t)s->bmy*m->stride + s->bmx, m->stride, s->bw, s->bh )
+             + bits_fpel( s, s->bmx, s->bmy );
+    for( int my = min_y; my <= max_y; my++ )
+    {
+        int ycost = s->cmy[my*4];
+        if( bsad <= ycost )
+            continue;
+        bsad -= ycost;
+        const int athresh = bsad * 17 >> 4;
+        for( int mx = min_x; mx < min_x + width; mx++ )
+        {
+            if( ads_at( s, &a, mx, my ) + s->cmx[mx*4] >= athresh )
+                continue;
+            /* the x mv cost of the LISTING step is read at the position's index within the row, cost_fpel_mvx[xs[i]] (me.c:683,
+             * :699), not at min_x + xs[i] as the ADS step does (me.c:675): reproduced as is */
+            int sad = orc_sad( m->p_fenc, m->fenc_stride, m->p_fref_w + (intptr_t)my*m->stride + mx, m->stride, s->bw, s->bh )
+                    + s->cmx[( mx - min_x )*4];
+            if( sad < bsad * sad_thresh >> 3 )
+            {
+                if( sad < bsad ) bsad = sad;
+                list[n].sad = sad + ycost; list[n].mv[0] = mx; list[n].mv[1] = my;
+                n++;
+            }
+        }
+        bsad += ycost;
+    }
+    int limit = me_range >> 1;
+    sad_thresh = bsad * sad_thresh >> 3;
+    while( n > limit*2 && sad_thresh > bsad )
+    {   /* halve the admitted range and keep, in order, what is still inside it */
+        sad_thresh = ( sad_thresh + bsad ) >> 1;
+        int k = 0;
+        for( int j = 0; j < n; j++ )
+            if( list[j].sad <= sad_thresh )
+                list[k++] = list[j];
+        n = k;
+    }
+    while( n > limit )
+    {   /* drop the (first) worst, the last entry takes its place */
+        int bi = 0;
+        for( int i = 1; i < n; i++ )
+            if( list[i].sad > list[bi].sad )
+                bi = i;
+        n--;
+        list[bi] = list[n];
+    }
+    for( int i = 0; i < n; i++ )
+        try_fpel( s, list[i].mv[0], list[i].mv[1] );
+    free( list );
 }
 
 static void refine_subpel( search_t *s, int hpel_iters, int qpel_iters, int *p_halfpel_thresh, int b_refine_qpel );
@@ -278,22 +404,10 @@ void orc_me_search_ref( const orc_me_ctx_t *c, orc_me_t *m, const int16_t (*mvc)
     case ORC_ME_HEX:
         hex_search( s, me_range );
         break;
-    case ORC_ME_ESA:                                                    /* me.c:618-771, the "just ADS and SAD" branch */
-    {
-        /* The reference scans the window row by row; per row the ADS prefilter (pixf.ads on the integral image, me.c:760) drops
-         * positions whose lower bound |sum(fenc) - sum(ref)| + mv cost already reaches the best cost, the rest go through
-         * COST_MV_X3_ABS / COST_MV in ascending x.  sum|a-b| >= |sum a - sum b|, so a dropped position can never be strictly
-         * better: the result is the first strictly smaller cost in raster order over the whole window -- which is what is
-         * restated here (the ADS arithmetic itself is a CPU-side accelerator, not part of the result).  The window's width is
-         * rounded up to a multiple of 4 like the reference's, which can reach up to 3 positions past mv_x_max. */
-        const int min_x = imax( s->bmx - me_range, s->x_min ), min_y = imax( s->bmy - me_range, s->y_min );
-        const int max_x = imin( s->bmx + me_range, s->x_max ), max_y = imin( s->bmy + me_range, s->y_max );
-        const int width = ( max_x - min_x + 3 ) & ~3;
-        for( int my = min_y; my <= max_y; my++ )
-            for( int mx = min_x; mx < min_x + width; mx++ )
-                try_fpel( s, mx, my );
+    case ORC_ME_ESA:                                                    /* me.c:618-771 */
+    case ORC_ME_TESA:
+        exhaustive_search( s, me_range );
         break;
-    }
     case ORC_ME_UMH:                                                    /* me.c:422-616 */
     {
         static const uint8_t pixel_size_shift[7] = { 0, 1, 1, 2, 3, 3, 4 };
@@ -476,8 +590,8 @@ static void refine_subpel( search_t *s, int hpel_iters, int qpel_iters, int *p_h
         }
     }
 
-    if( !b_refine_qpel && c->mbcmp_is_satd )
-    {   /* re-measure the winner with mbcmp (SATD), me.c:925-929 */
+    if( !b_refine_qpel && c->mbcmp_is_satd && !fpel_satd( s ) )
+    {   /* re-measure the winner with mbcmp (SATD) when the half-pel steps used another metric, me.c:925-929 */
         bcost = cost_qpel( s, bmx, bmy, 1 );
         bdir = -1;
     }
@@ -531,4 +645,57 @@ static void refine_subpel( search_t *s, int hpel_iters, int qpel_iters, int *p_h
     m->mv[0] = bmx;
     m->mv[1] = bmy;
     m->cost_mv = s->cmx[bmx] + s->cmy[bmy];
+}
+
+/* ---- x264_me_refine_bidir_satd, encoder/me.c:1027-1183 with rd = 0 --------------------------------------------------------
+ * Joint refinement of the two vectors of a bi-predicted block: up to 8 passes; each pass measures the (list 0, list 1)
+ * vector pairs that differ from the current pair by +-1 quarter-pel in at most two of the four components (33 pairs, the
+ * current one only in the first pass), skipping pairs already measured -- remembered in a 4096-bit map indexed by the low 3
+ * bits of every component (so it aliases after a drift of 8, as the reference's) --, cost = mbcmp( fenc, avg( ref0, ref1,
+ * weight ) ) + the four mv costs; strictly smaller wins, first in table order on ties; stops when the centre stays. */
+static const uint8_t bidir_pairs[33] =        /* offset = base-3 digits - 1, in the order (m0x, m0y, m1x, m1y); me.c:1063-1074 */
+    { 40, 67, 13, 49, 31, 43, 37, 41, 39, 76, 4, 52, 28, 44, 36, 68, 12, 70, 10, 50, 30, 58, 22, 46, 34, 42, 38, 14, 66, 64, 16, 48, 32 };
+
+void orc_me_refine_bidir_satd( const orc_me_ctx_t *c, orc_me_t *m0, orc_me_t *m1, int i_weight )
+{
+    const int bw = orc_pixel_w[m0->i_pixel], bh = orc_pixel_h[m0->i_pixel];
+    int bm[4] = { m0->mv[0], m0->mv[1], m1->mv[0], m1->mv[1] };
+    for( int k = 0; k < 4; k++ )                                        /* me.c:1076-1080: too close to the window edge */
+        if( bm[k] < c->mv_min_spel[k&1] + 8 || bm[k] > c->mv_max_spel[k&1] - 8 )
+            return;
+    const uint16_t *tab[4] = { m0->p_cost_mv - m0->mvp[0], m0->p_cost_mv - m0->mvp[1], m1->p_cost_mv - m1->mvp[0], m1->p_cost_mv - m1->mvp[1] };
+    static const orc_weight_t none;
+    uint8_t visited[8][8][8];
+    memset( visited, 0, sizeof(visited) );
+    int bcost = ORC_COST_MAX;
+    for( int pass = 0; pass < 8; pass++ )
+    {
+        int bestj = 0;
+        for( int j = !!pass; j < 33; j++ )
+        {
+            int v[4], code = bidir_pairs[j];
+            for( int k = 0; k < 4; k++, code /= 3 )
+                v[k] = bm[k] + code % 3 - 1;
+            uint8_t *seen = &visited[v[0]&7][v[1]&7][v[2]&7];
+            if( pass && ( *seen & ( 1 << ( v[3]&7 ) ) ) )
+                continue;
+            *seen |= 1 << ( v[3]&7 );
+            uint8_t p0[16*16], p1[16*16], avg[16*16];
+            orc_mc_luma( p0, 16, m0->p_fref, m0->stride, v[0], v[1], bw, bh, &none );
+            orc_mc_luma( p1, 16, m1->p_fref, m1->stride, v[2], v[3], bw, bh, &none );
+            orc_pixel_avg( avg, 16, p0, 16, p1, 16, bw, bh, i_weight );
+            int cost = ( c->mbcmp_is_satd ? orc_satd( m0->p_fenc, m0->fenc_stride, avg, 16, bw, bh )
+                                          : orc_sad ( m0->p_fenc, m0->fenc_stride, avg, 16, bw, bh ) )
+                     + tab[0][v[0]] + tab[1][v[1]] + tab[2][v[2]] + tab[3][v[3]];
+            if( cost < bcost ) { bcost = cost; bestj = j; }
+        }
+        if( !bestj )
+            break;
+        int code = bidir_pairs[bestj];
+        for( int k = 0; k < 4; k++, code /= 3 )
+            bm[k] += code % 3 - 1;
+    }
+    m0->mv[0] = bm[0]; m0->mv[1] = bm[1];
+    m1->mv[0] = bm[2]; m1->mv[1] = bm[3];
+    m0->cost = m1->cost = bcost;                                        /* not an output of the reference: kept for the tests */
 }

@@ -292,6 +292,7 @@ static void me_search_common( x264_t *h, xref_me_args_t *a, uint8_t *fenc, intpt
     int save_range = h->param.analyse.i_me_range;
     h->param.analyse.i_me_range = a->me_range;
     h->mb.i_me_method = a->me_method;
+    h->mb.i_qp = a->qp;                                 /* ESA / TESA take the x mv costs from cost_mv_fpel[h->mb.i_qp] (me.c:639) */
     h->mb.i_subpel_refine = a->subpel_refine;
     h->mb.b_chroma_me = 0;
     for( int i = 0; i < 2; i++ )
@@ -315,6 +316,46 @@ XREF_API void xref_me_search( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr
                               uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride )
 {
     me_search_common( hv, a, fenc, fenc_stride, f0, f1, f2, f3, fref_w, stride, NULL );
+}
+
+/* x264_me_refine_bidir_satd (encoder/me.c:1027-1183, rd = 0) on caller-supplied planes: f0[4] / f1[4] = F,H,V,C planes of the
+ * list-0 / list-1 reference at the block origin.  mv0 / mv1 are updated in place. */
+XREF_API void xref_me_refine_bidir_satd( void *hv, int i_pixel, int qp, uint8_t *fenc, intptr_t fenc_stride,
+                                         uint8_t **f0, uint8_t **f1, intptr_t stride, int16_t *mv0, int16_t *mvp0,
+                                         int16_t *mv1, int16_t *mvp1, int i_weight, const int *mv_min_spel, const int *mv_max_spel )
+{
+    x264_t *h = hv;
+    tables_init();
+    ALIGNED_ARRAY_64( pixel, fenc_buf,[16*16] );
+    ALIGNED_ARRAY_64( pixel, fdec_buf,[32*FDEC_STRIDE] );
+    int bw = x264_pixel_size[i_pixel].w, bh = x264_pixel_size[i_pixel].h;
+    for( int y = 0; y < bh; y++ )
+        memcpy( fenc_buf + y*FENC_STRIDE, fenc + y*fenc_stride, bw );
+    x264_me_t m[2];
+    memset( m, 0, sizeof(m) );
+    for( int l = 0; l < 2; l++ )
+    {
+        m[l].i_pixel = i_pixel;
+        m[l].p_cost_mv = h->cost_mv[qp];
+        m[l].p_fenc[0] = fenc_buf;
+        m[l].i_stride[0] = stride;
+        for( int k = 0; k < 4; k++ ) m[l].p_fref[k] = ( l ? f1 : f0 )[k];
+        m[l].p_fref_w = m[l].p_fref[0];
+        m[l].weight = x264_weight_none;
+        m[l].mvp[0] = ( l ? mvp1 : mvp0 )[0]; m[l].mvp[1] = ( l ? mvp1 : mvp0 )[1];
+        m[l].mv[0] = ( l ? mv1 : mv0 )[0]; m[l].mv[1] = ( l ? mv1 : mv0 )[1];
+    }
+    pixel *save = h->mb.pic.p_fdec[0];
+    h->mb.pic.p_fdec[0] = fdec_buf;
+    for( int i = 0; i < 2; i++ )
+    {
+        h->mb.mv_min_spel[i] = mv_min_spel[i];
+        h->mb.mv_max_spel[i] = mv_max_spel[i];
+    }
+    x264_me_refine_bidir_satd( h, &m[0], &m[1], i_weight );
+    h->mb.pic.p_fdec[0] = save;
+    mv0[0] = m[0].mv[0]; mv0[1] = m[0].mv[1];
+    mv1[0] = m[1].mv[0]; mv1[1] = m[1].mv[1];
 }
 
 /* ESA / TESA read the reference frame's integral image (me.c:636-760), which x264_frame_filter builds when the encoder was
@@ -363,8 +404,20 @@ XREF_API int xref_me_search_frame( void *hv, xref_me_args_t *a, uint8_t *fenc, i
     intptr_t st = f->i_stride[0], off = by*st + bx;
     x264_frame_t *save = h->fenc;
     h->fenc = f;                                        /* me.c:645 reads h->fenc->i_lines[0] for the 4x4 plane of the integral */
+    pixel *wbuf = NULL, *fref_w = f->filtered[0][0] + off;
+    if( a->wt_en )
+    {   /* the weighted full-pel plane of a weighted reference (encoder.c:2141-2166 builds it the same way): the whole padded plane */
+        int lines = f->i_lines[0] + 2*PADV;
+        wbuf = x264_malloc( st * lines );
+        if( !wbuf ) return -1;
+        x264_weight_t wt; make_weight( &wt, 1, a->wt_scale, a->wt_denom, a->wt_offset );
+        wt.weightfn = h->mc.weight;
+        x264_weight_scale_plane( h, wbuf, st, f->filtered[0][0] - PADV*st - PADH_ALIGN, st, st, lines, &wt );
+        fref_w = wbuf + PADV*st + PADH_ALIGN + off;
+    }
     me_search_common( h, a, fenc, fenc_stride, f->filtered[0][0] + off, f->filtered[0][1] + off, f->filtered[0][2] + off,
-                      f->filtered[0][3] + off, f->filtered[0][0] + off, st, f->integral + off );
+                      f->filtered[0][3] + off, fref_w, st, f->integral + off );
+    if( wbuf ) x264_free( wbuf );
     h->fenc = save;
     return 0;
 #undef f
