@@ -43,7 +43,7 @@ enum x264cu_metric_e                       /* members of x264_pixel_function_t, 
     X264CU_SA8D = 3                        /* pixf.sa8d[]  common/pixel.c:334-381 (16x16 and 8x8 only) */
 };
 
-enum x264cu_me_e { X264CU_ME_DIA = 0, X264CU_ME_HEX = 1, X264CU_ME_UMH = 2, X264CU_ME_ESA = 3 };   /* x264.h X264_ME_* */
+enum x264cu_me_e { X264CU_ME_DIA = 0, X264CU_ME_HEX = 1, X264CU_ME_UMH = 2, X264CU_ME_ESA = 3, X264CU_ME_TESA = 4 };   /* x264.h X264_ME_* */
 
 typedef struct x264cu_ctx x264cu_ctx_t;
 
@@ -392,8 +392,8 @@ long x264cu_slicetype_cost_requests( x264cu_slicetype_t *st );
 
 /* ------------------------------------------------------------------------------------------------
  * Batched twin of x264_me_search_ref + refine_subpel (encoder/me.h:58-60, encoder/me.c:182-992): one job = one call.
- * Luma only (no chroma ME), DIA / HEX / UMH / ESA (exhaustive, me.c:618-771; TESA is not built), every partition size and
- * sub-pel level.  One warp runs one search with the
+ * Luma only (no chroma ME), DIA / HEX / UMH / ESA / TESA (the exhaustive searches of me.c:618-771, with their successive-
+ * elimination prefilter where it decides the result), every partition size and sub-pel level.  One warp runs one search with the
  * reference's control flow; jobs are independent (their predictors are inputs), which is how the full-resolution
  * motion-estimation stage is replayed from recorded x264_me_t inputs (BASELINE config 3).
  * ---------------------------------------------------------------------------------------------- */
@@ -419,10 +419,10 @@ typedef struct
 
 typedef struct
 {
-    int me_method;                   /* h->mb.i_me_method (X264CU_ME_DIA/HEX/UMH) */
+    int me_method;                   /* h->mb.i_me_method (X264CU_ME_DIA .. X264CU_ME_TESA; esa: me_range <= 120, tesa: <= 64) */
     int subpel_refine;               /* h->mb.i_subpel_refine */
     int me_range;                    /* h->param.analyse.i_me_range */
-    int mbcmp_satd;                  /* encoder.c:1409-1427: mbcmp is SATD iff the encoder's subme > 1 */
+    int mbcmp_satd;                  /* encoder.c:1409-1427: mbcmp is SATD iff the encoder's subme > 1; under TESA fpelcmp follows it */
     int lambda;                      /* a->i_lambda: cost_mv = lambda * bits (analyse.c:143-157) */
     int mv_range;                    /* h->param.analyse.i_mv_range: sizes the cost table */
     int weight_enabled, weight_scale, weight_denom, weight_offset;   /* m->weight[0] (common/mc.h:235-245) */
@@ -434,6 +434,30 @@ int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *params,
                             const uint8_t *d_fenc, intptr_t fenc_stride,
                             const uint8_t *const d_fref[4], const uint8_t *d_fref_w, intptr_t ref_stride,
                             const x264cu_me_job_t *d_jobs, int n, x264cu_me_result_t *d_results );
+
+/* Batched twin of x264_me_refine_bidir_satd (encoder/me.h:63, encoder/me.c:1027-1183): joint +-1 quarter-pel refinement of
+ * the two vectors of a bi-predicted partition, one job = one call.  params: mbcmp_satd, lambda and mv_range are read. */
+typedef struct
+{
+    int32_t  i_pixel;                /* m0->i_pixel */
+    uint32_t fenc_off;               /* byte offset of the block in the fenc plane */
+    uint32_t ref0_off, ref1_off;     /* byte offsets of the co-located block in the list-0 / list-1 reference planes */
+    int16_t  mv[4];                  /* m0->mv[0..1], m1->mv[0..1] */
+    int16_t  mvp[4];                 /* m0->mvp, m1->mvp */
+    int16_t  mv_min_spel[2], mv_max_spel[2];   /* h->mb.mv_min_spel / mv_max_spel */
+    int32_t  i_weight;               /* bipred weight of list 0 (32 = plain average; pixel_avg_weight_wxh otherwise) */
+} x264cu_bidir_job_t;
+
+typedef struct
+{
+    int16_t mv[4];                   /* refined m0->mv, m1->mv (the inputs when the pair is within 8 of the window edge) */
+    int32_t cost;                    /* best mbcmp + mv costs seen (not an output of the reference; COST_MAX = 1<<28 on early return) */
+} x264cu_bidir_result_t;
+
+int x264cu_me_refine_bidir_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *params,
+                                  const uint8_t *d_fenc, intptr_t fenc_stride,
+                                  const uint8_t *const d_fref0[4], const uint8_t *const d_fref1[4], intptr_t ref_stride,
+                                  const x264cu_bidir_job_t *d_jobs, int n, x264cu_bidir_result_t *d_results );
 
 #ifdef __cplusplus
 }

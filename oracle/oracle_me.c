@@ -660,6 +660,7 @@ void orc_me_refine_bidir_satd( const orc_me_ctx_t *c, orc_me_t *m0, orc_me_t *m1
 {
     const int bw = orc_pixel_w[m0->i_pixel], bh = orc_pixel_h[m0->i_pixel];
     int bm[4] = { m0->mv[0], m0->mv[1], m1->mv[0], m1->mv[1] };
+    m0->cost = m1->cost = ORC_COST_MAX;
     for( int k = 0; k < 4; k++ )                                        /* me.c:1076-1080: too close to the window edge */
         if( bm[k] < c->mv_min_spel[k&1] + 8 || bm[k] > c->mv_max_spel[k&1] - 8 )
             return;

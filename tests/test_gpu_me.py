@@ -95,14 +95,99 @@ def run_group(ctx, kind, method, subpel, me_range, satd, wt, rng, n_jobs=96):
 
 
 @pytest.mark.parametrize("kind", ["texture", "flat", "noise"])
-@pytest.mark.parametrize("method", [0, 1, 2, 3])
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4])
 def test_me_search_batch_matches_oracle(ctx, kind, method):
+    """method 3 / 4 = ESA / TESA (me.c:618-771): with a weighted reference the ADS prefilter (sums of the unweighted plane) decides
+    which positions are measured; under TESA fpelcmp is SATD when mbcmp is"""
     rng = np.random.default_rng(17 * method + len(kind))
     for subpel in (0, 1, 2, 3, 4, 5, 6, 7, 9):
-        me_range = int(rng.choice([4, 8, 16] if method != 2 else [16, 24, 32]))
+        me_range = int(rng.choice([16, 24, 32] if method == 2 else [4, 8, 16, 24] if method == 4 else [4, 8, 16]))
         satd = int(subpel > 1 and rng.random() < 0.8)
         wt = (1, int(rng.integers(40, 90)), 6, int(rng.integers(-4, 5))) if rng.random() < 0.3 else (0, 0, 0, 0)
         run_group(ctx, kind, method, subpel, me_range, satd, wt, rng)
+
+
+def test_me_search_batch_tesa_many_jobs(ctx):
+    """more TESA jobs than warps in flight share the bounded candidate-list scratch (each warp walks several jobs)"""
+    rng = np.random.default_rng(5)
+    run_group(ctx, "flat", 4, 7, 16, 1, (0, 0, 0, 0), rng, n_jobs=700)
+    run_group(ctx, "texture", 4, 2, 32, 1, (1, 70, 6, -2), rng, n_jobs=64)
+
+
+@pytest.mark.parametrize("kind", ["texture", "flat"])
+@pytest.mark.parametrize("satd", [0, 1])
+def test_me_refine_bidir_batch_matches_oracle(ctx, kind, satd):
+    """x264cu_me_refine_bidir_batch against the oracle's x264_me_refine_bidir_satd (pinned to the reference in
+    tests/test_oracle_me.py): every partition size, bipred weights 32 / 21 / 43 / -10 / 64, pairs near the window edge"""
+    o = oracle()
+    o.orc_me_refine_bidir_satd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    o.orc_me_refine_bidir_satd.restype = None
+    rng = np.random.default_rng(3 + satd + len(kind))
+    fenc_l, ref0_l = _content(kind, rng)
+    _, ref1_l = _content(kind, rng)
+    if kind == "texture":
+        ref1_l = np.ascontiguousarray(np.roll(ref0_l, (3, -2), (0, 1)))
+    pl0, pl1 = make_ref_planes(np.ascontiguousarray(ref0_l)), make_ref_planes(np.ascontiguousarray(ref1_l))
+    st = pl0[0].stride
+    fenc = PaddedPlane(W, H, stride=st)
+    fenc.inner()[:] = fenc_l
+    mv_range, lam = 64, 2
+    n = 2 * 4 * mv_range
+    tab = np.zeros(2 * n + 1, np.uint16)
+    o.orc_cost_mv_table(tab, n, lam)
+    n_jobs = 300
+    jobs = np.zeros(n_jobs, x.bidir_job_dtype)
+    want = []
+    for k in range(n_jobs):
+        ip = int(rng.integers(0, 7))
+        bw, bh = PIXEL_W[ip], PIXEL_H[ip]
+        bx = int(rng.integers(0, (W - bw) // 4 + 1)) * 4
+        by = int(rng.integers(0, (H - bh) // 4 + 1)) * 4
+        mvr = 4 * mv_range
+        lim_min = np.array([max(4 * (-bx - 24), -mvr), max(4 * (-by - 24), -mvr)])
+        lim_max = np.array([min(4 * (W - bx - bw + 24), mvr - 1), min(4 * (H - by - bh + 24), mvr - 1)])
+        spread = int(rng.choice([6, 30, 120]))
+        mv0 = np.clip(rng.integers(-spread, spread + 1, 2), lim_min, lim_max)
+        mv1 = np.clip(rng.integers(-spread, spread + 1, 2), lim_min, lim_max)
+        mvp0, mvp1 = mv0 + rng.integers(-6, 7, 2), mv1 + rng.integers(-6, 7, 2)
+        weight = int(rng.choice([32, 32, 21, 43, -10, 64]))
+        off = pl0[0].off(bx, by)
+        j = jobs[k]
+        j["i_pixel"], j["fenc_off"], j["ref0_off"], j["ref1_off"] = ip, fenc.off(bx, by), off, off
+        j["mv"], j["mvp"] = np.concatenate([mv0, mv1]), np.concatenate([mvp0, mvp1])
+        j["mv_min_spel"], j["mv_max_spel"], j["i_weight"] = lim_min, lim_max, weight
+        c = OrcMeCtx()
+        c.me_method, c.subpel_refine, c.me_range, c.mbcmp_is_satd = 1, 7, 16, satd
+        for i in range(2):
+            c.mv_min_spel[i], c.mv_max_spel[i] = int(lim_min[i]), int(lim_max[i])
+        ms = []
+        for pl, mv, mvp in ((pl0, mv0, mvp0), (pl1, mv1, mvp1)):
+            m = OrcMe()
+            m.i_pixel = ip
+            m.p_cost_mv = tab.ctypes.data + 2 * n
+            for i in range(4):
+                m.p_fref[i] = pl[i].buf.ctypes.data + off
+            m.p_fref_w = pl[0].buf.ctypes.data + off
+            m.p_fenc = fenc.buf.ctypes.data + fenc.off(bx, by)
+            m.fenc_stride, m.stride = st, st
+            m.weight = OrcWeight(0, 0, 0, 0)
+            m.mvp[0], m.mvp[1] = int(mvp[0]), int(mvp[1])
+            m.mv[0], m.mv[1] = int(mv[0]), int(mv[1])
+            ms.append(m)
+        o.orc_me_refine_bidir_satd(C.byref(c), C.byref(ms[0]), C.byref(ms[1]), weight)
+        want.append((ms[0].mv[0], ms[0].mv[1], ms[1].mv[0], ms[1].mv[1], ms[0].cost))
+    d_fenc = ctx.upload(fenc.buf)
+    d0, d1 = [ctx.upload(p.buf) for p in pl0], [ctx.upload(p.buf) for p in pl1]
+    params = x.MeParams(1, 7, 16, satd, lam, mv_range, 0, 0, 0, 0)
+    res = x.me_refine_bidir_batch(ctx, params, d_fenc, st, d0, d1, st, jobs)
+    for p in [d_fenc] + d0 + d1:
+        ctx.free(p)
+    moved = 0
+    for k in range(n_jobs):
+        got = tuple(int(v) for v in res[k]["mv"]) + (int(res[k]["cost"]),)
+        assert got == want[k], (kind, satd, k, jobs[k], got, want[k])
+        moved += got[:4] != tuple(int(v) for v in jobs[k]["mv"])
+    assert moved > 50
 
 
 def test_me_search_batch_4k_frame_of_macroblocks(ctx):

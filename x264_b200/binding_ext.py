@@ -28,6 +28,10 @@ me_job_dtype = np.dtype([("i_pixel", np.int32), ("fenc_off", np.uint32), ("ref_o
                          ("mvc", np.int16, (8, 2)), ("i_mvc", np.int32), ("mv_min_spel", np.int16, (2,)),
                          ("mv_max_spel", np.int16, (2,)), ("halfpel_thresh", np.int32)])
 me_result_dtype = np.dtype([("mv", np.int16, (2,)), ("cost", np.int32), ("cost_mv", np.int32), ("halfpel_thresh", np.int32)])
+bidir_job_dtype = np.dtype([("i_pixel", np.int32), ("fenc_off", np.uint32), ("ref0_off", np.uint32), ("ref1_off", np.uint32),
+                            ("mv", np.int16, (4,)), ("mvp", np.int16, (4,)), ("mv_min_spel", np.int16, (2,)),
+                            ("mv_max_spel", np.int16, (2,)), ("i_weight", np.int32)])
+bidir_result_dtype = np.dtype([("mv", np.int16, (4,)), ("cost", np.int32)])
 
 
 class SlicetypeParams(C.Structure):
@@ -43,6 +47,7 @@ TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "BREF", 5: "B"}
 def bind(L):
     vp, ci, ss = C.c_void_p, C.c_int, C.c_ssize_t
     L.x264cu_me_search_batch.argtypes = [vp, C.POINTER(MeParams), vp, ss, C.POINTER(vp), vp, ss, vp, ci, vp]
+    L.x264cu_me_refine_bidir_batch.argtypes = [vp, C.POINTER(MeParams), vp, ss, C.POINTER(vp), C.POINTER(vp), ss, vp, ci, vp]
     L.x264cu_slicetype_open.argtypes = [vp, C.POINTER(SlicetypeParams), C.POINTER(vp)]
     L.x264cu_slicetype_close.argtypes = [vp]
     L.x264cu_slicetype_step.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
@@ -340,6 +345,21 @@ def me_search_batch(ctx, params, d_fenc, fenc_stride, d_fref, d_fref_w, ref_stri
     ctx.check(ctx.L.x264cu_me_search_batch(ctx.h, C.byref(params), int(d_fenc), fenc_stride, arr,
                                            int(d_fref_w) if d_fref_w else None, ref_stride, d_jobs, n, d_res))
     out = ctx.download(d_res, (n,), me_result_dtype)
+    ctx.free(d_jobs)
+    ctx.free(d_res)
+    return out
+
+
+def me_refine_bidir_batch(ctx, params, d_fenc, fenc_stride, d_fref0, d_fref1, ref_stride, jobs):
+    """jobs: numpy array of bidir_job_dtype (host) -> numpy array of bidir_result_dtype.  d_* are device addresses."""
+    assert jobs.dtype == bidir_job_dtype and bidir_job_dtype.itemsize == 44 and bidir_result_dtype.itemsize == 12
+    n = len(jobs)
+    d_jobs = ctx.upload(jobs)
+    d_res = ctx.malloc(max(n, 1) * bidir_result_dtype.itemsize)
+    a0 = (C.c_void_p * 4)(*[int(p) for p in d_fref0])
+    a1 = (C.c_void_p * 4)(*[int(p) for p in d_fref1])
+    ctx.check(ctx.L.x264cu_me_refine_bidir_batch(ctx.h, C.byref(params), int(d_fenc), fenc_stride, a0, a1, ref_stride, d_jobs, n, d_res))
+    out = ctx.download(d_res, (n,), bidir_result_dtype)
     ctx.free(d_jobs)
     ctx.free(d_res)
     return out

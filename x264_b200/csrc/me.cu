@@ -1,4 +1,5 @@
-// x264cu_me_search_batch: warp-per-search replay of x264_me_search_ref (encoder/me.c:182-992).  Device code: me_dev.cuh.
+// x264cu_me_search_batch: warp-per-search replay of x264_me_search_ref (encoder/me.c:182-992); x264cu_me_refine_bidir_batch: of
+// x264_me_refine_bidir_satd (me.c:1027-1183).  Device code: me_dev.cuh.
 #include "ctx.h"
 #include "me_dev.cuh"
 #include <math.h>
@@ -15,12 +16,12 @@ struct MeResult { int16_t mv[2]; int32_t cost, cost_mv, halfpel_thresh; };
 static_assert( sizeof( MeJob ) == sizeof( x264cu_me_job_t ) && sizeof( MeResult ) == sizeof( x264cu_me_result_t ), "ABI structs" );
 
 template <int BW, int BH>
-__device__ __noinline__ void run_job( const MeShared &g, const MeJob &j, int lane, MeResult &r )
+__device__ __noinline__ void run_job( const MeShared &g, const MeJob &j, int lane, MeResult &r, uint2 *tesa_list )
 {
     int mvx, mvy, cost, cost_mv, thresh = j.halfpel_thresh;
     int16_t lim[4] = { j.mv_min_spel[0], j.mv_min_spel[1], j.mv_max_spel[0], j.mv_max_spel[1] };
     me_search_generic<BW, BH>( g, j.i_pixel, j.fenc_off, j.ref_off, j.mvp[0], j.mvp[1], &j.mvc[0][0], j.i_mvc, lim, thresh, lane,
-                               mvx, mvy, cost, cost_mv );
+                               mvx, mvy, cost, cost_mv, tesa_list );
     r.mv[0] = (int16_t)mvx; r.mv[1] = (int16_t)mvy; r.cost = cost; r.cost_mv = cost_mv; r.halfpel_thresh = thresh;
 }
 
@@ -28,21 +29,53 @@ __global__ void __launch_bounds__( 128 )
 me_search_kernel( MeShared g, const MeJob *__restrict__ jobs, int n, MeResult *__restrict__ results )
 {
     const int lane = threadIdx.x & 31;
-    const int w = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
-    if( w >= n ) return;
-    MeJob j = jobs[w];                           // every lane holds the (uniform) job
-    MeResult r;
-    switch( j.i_pixel )
+    const int w0 = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5, nw = ( gridDim.x * blockDim.x ) >> 5;
+    uint2 *tesa_list = g.tesa_list ? g.tesa_list + (size_t)w0 * g.tesa_cap : nullptr;
+    for( int w = w0; w < n; w += nw )            // one job per warp, except TESA whose warps (and candidate lists) are bounded
     {
-        case X264CU_PIXEL_16x16: run_job<16, 16>( g, j, lane, r ); break;
-        case X264CU_PIXEL_16x8:  run_job<16, 8>( g, j, lane, r ); break;
-        case X264CU_PIXEL_8x16:  run_job<8, 16>( g, j, lane, r ); break;
-        case X264CU_PIXEL_8x8:   run_job<8, 8>( g, j, lane, r ); break;
-        case X264CU_PIXEL_8x4:   run_job<8, 4>( g, j, lane, r ); break;
-        case X264CU_PIXEL_4x8:   run_job<4, 8>( g, j, lane, r ); break;
-        default:                 run_job<4, 4>( g, j, lane, r ); break;
+        MeJob j = jobs[w];                       // every lane holds the (uniform) job
+        MeResult r;
+        switch( j.i_pixel )
+        {
+            case X264CU_PIXEL_16x16: run_job<16, 16>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_16x8:  run_job<16, 8>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_8x16:  run_job<8, 16>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_8x8:   run_job<8, 8>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_8x4:   run_job<8, 4>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_4x8:   run_job<4, 8>( g, j, lane, r, tesa_list ); break;
+            default:                 run_job<4, 4>( g, j, lane, r, tesa_list ); break;
+        }
+        if( lane == 0 ) results[w] = r;
     }
-    if( lane == 0 ) results[w] = r;
+}
+
+// cost_mv[lambda] (analyse.c:143-157, :179-188), same float expressions as the reference; kept in this context's scratch slot 5
+// (nobody else's) and rebuilt when (lambda, range) change.  Returns the table's centre.
+static const uint16_t *me_cost_table( x264cu_ctx_t *ctx, int lambda, int mv_range )
+{
+    const int len = 2 * 4 * mv_range;
+    const void *before = ctx->scratch[5];
+    uint16_t *d_tab = (uint16_t *)x264cu_scratch( ctx, 5, ( 2 * len + 1 ) * 2 + 64 );
+    if( !d_tab ) return nullptr;
+    if( ctx->me_tab_lambda != lambda || ctx->me_tab_range != mv_range || before != (const void *)d_tab )
+    {
+        std::vector<uint16_t> tab( 2 * len + 1 );
+        for( int i = 0; i <= len; i++ )
+        {
+            float l = i ? log2f( (float)( i + 1 ) ) * 2.0f + 1.718f : 0.718f;
+            int c = (int)( lambda * l + .5f );
+            if( c > 65535 ) c = 65535;
+            tab[len + i] = tab[len - i] = (uint16_t)c;
+        }
+        if( cudaMemcpyAsync( d_tab, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice, ctx->stream ) != cudaSuccess ||
+            cudaStreamSynchronize( ctx->stream ) != cudaSuccess )
+        {
+            x264cu_fail( ctx, "me cost table: %s", cudaGetErrorString( cudaGetLastError() ) );
+            return nullptr;
+        }
+        ctx->me_tab_lambda = lambda; ctx->me_tab_range = mv_range;
+    }
+    return d_tab + len;
 }
 
 extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *p, const uint8_t *d_fenc, intptr_t fenc_stride,
@@ -51,43 +84,103 @@ extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params
 {
     if( !ctx || !p ) return -1;
     if( n <= 0 ) return 0;
-    if( p->me_method < X264CU_ME_DIA || p->me_method > X264CU_ME_ESA )
-        return x264cu_fail( ctx, "me_search_batch: method %d not supported (tesa is outside this backend)", p->me_method );
+    if( p->me_method < X264CU_ME_DIA || p->me_method > X264CU_ME_TESA )
+        return x264cu_fail( ctx, "me_search_batch: unknown method %d", p->me_method );
     if( p->me_method == X264CU_ME_ESA && p->me_range > 120 )
         return x264cu_fail( ctx, "me_search_batch: esa me_range %d > 120", p->me_range );
-    if( p->subpel_refine < 0 || p->subpel_refine > 11 || p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 )
+    if( p->me_method == X264CU_ME_TESA && p->me_range > 64 )
+        return x264cu_fail( ctx, "me_search_batch: tesa me_range %d > 64", p->me_range );
+    if( p->subpel_refine < 0 || p->subpel_refine > 11 || p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 || p->me_range < 1 )
         return x264cu_fail( ctx, "me_search_batch: bad parameters" );
-    // cost_mv[lambda] (analyse.c:143-157, :179-188), same float expressions as the reference; kept in this context's scratch
-    // slot 5 (nobody else's) and rebuilt when (lambda, range) change
-    const int len = 2 * 4 * p->mv_range;
-    const void *before = ctx->scratch[5];
-    uint16_t *d_tab = (uint16_t *)x264cu_scratch( ctx, 5, ( 2 * len + 1 ) * 2 + 64 );
+    const uint16_t *d_tab = me_cost_table( ctx, p->lambda, p->mv_range );
     if( !d_tab ) return -1;
-    if( ctx->me_tab_lambda != p->lambda || ctx->me_tab_range != p->mv_range || before != (const void *)d_tab )
-    {
-        std::vector<uint16_t> tab( 2 * len + 1 );
-        for( int i = 0; i <= len; i++ )
-        {
-            float l = i ? log2f( (float)( i + 1 ) ) * 2.0f + 1.718f : 0.718f;
-            int c = (int)( p->lambda * l + .5f );
-            if( c > 65535 ) c = 65535;
-            tab[len + i] = tab[len - i] = (uint16_t)c;
-        }
-        CU_CHECK( ctx, cudaMemcpyAsync( d_tab, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice, ctx->stream ) );
-        CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
-        ctx->me_tab_lambda = p->lambda; ctx->me_tab_range = p->mv_range;
-    }
     MeShared g;
     g.fenc = d_fenc; g.fenc_stride = (int)fenc_stride;
     for( int i = 0; i < 4; i++ ) g.fref[i] = d_fref[i];
     g.fref_w = d_fref_w ? d_fref_w : d_fref[0];
     g.stride = (int)ref_stride;
-    g.cost_mv = d_tab + len;
+    g.cost_mv = d_tab;
     g.me_method = p->me_method; g.subpel_refine = p->subpel_refine; g.me_range = p->me_range; g.satd = p->mbcmp_satd;
+    g.fpel_satd = p->mbcmp_satd && p->me_method == X264CU_ME_TESA;                   // encoder.c:1409-1427
+    g.tesa_list = nullptr; g.tesa_cap = 0;
     g.w.enabled = p->weight_enabled; g.w.scale = p->weight_scale; g.w.denom = p->weight_denom; g.w.offset = p->weight_offset;
     const int warps_per_block = 4;
-    me_search_kernel<<<( n + warps_per_block - 1 ) / warps_per_block, warps_per_block * 32, 0, ctx->stream>>>(
-        g, (const MeJob *)d_jobs, n, (MeResult *)d_results );
+    int blocks = ( n + warps_per_block - 1 ) / warps_per_block;
+    if( p->me_method == X264CU_ME_TESA )
+    {   // a warp's candidate list can hold every position of the window: (2r+1) rows of up to 2r+4 (me.c:627-630); the warps
+        // in flight are bounded so that the lists stay within 256 MB and each warp walks several jobs
+        g.tesa_cap = ( 2 * p->me_range + 1 ) * ( 2 * p->me_range + 4 );
+        const size_t per_block = (size_t)warps_per_block * g.tesa_cap * sizeof(uint2);
+        int max_blocks = (int)( ( (size_t)256 << 20 ) / per_block );
+        max_blocks = max_blocks < 1 ? 1 : max_blocks > ctx->sm_count * 8 ? ctx->sm_count * 8 : max_blocks;
+        if( blocks > max_blocks ) blocks = max_blocks;
+        g.tesa_list = (uint2 *)x264cu_scratch( ctx, 9, (size_t)blocks * per_block );
+        if( !g.tesa_list ) return -1;
+    }
+    me_search_kernel<<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, (const MeJob *)d_jobs, n, (MeResult *)d_results );
+    CU_LAUNCH_CHECK( ctx );
+    return 0;
+}
+
+// ---- x264cu_me_refine_bidir_batch ------------------------------------------------------------------------------------------
+struct BidirJob                                 // == x264cu_bidir_job_t
+{
+    int32_t i_pixel; uint32_t fenc_off, ref0_off, ref1_off; int16_t mv[4], mvp[4]; int16_t mv_min_spel[2], mv_max_spel[2]; int32_t i_weight;
+};
+struct BidirResult { int16_t mv[4]; int32_t cost; };
+static_assert( sizeof( BidirJob ) == sizeof( x264cu_bidir_job_t ) && sizeof( BidirResult ) == sizeof( x264cu_bidir_result_t ), "ABI structs" );
+
+template <int BW, int BH>
+__device__ __noinline__ void run_bidir( const BidirShared &g, const BidirJob &j, int lane, uint32_t *visited, BidirResult &r )
+{
+    int bm[4], cost;
+    int16_t lim[4] = { j.mv_min_spel[0], j.mv_min_spel[1], j.mv_max_spel[0], j.mv_max_spel[1] };
+    me_refine_bidir<BW, BH>( g, j.fenc_off, j.ref0_off, j.ref1_off, j.mv, j.mvp, lim, j.i_weight, lane, visited, bm, cost );
+    for( int k = 0; k < 4; k++ ) r.mv[k] = (int16_t)bm[k];
+    r.cost = cost;
+}
+
+__global__ void __launch_bounds__( 128 )
+me_bidir_kernel( BidirShared g, const BidirJob *__restrict__ jobs, int n, BidirResult *__restrict__ results )
+{
+    __shared__ uint32_t visited[4][128];
+    const int lane = threadIdx.x & 31, wb = threadIdx.x >> 5;
+    const int w = blockIdx.x * 4 + wb;
+    if( w >= n ) return;
+    BidirJob j = jobs[w];
+    BidirResult r;
+    switch( j.i_pixel )
+    {
+        case X264CU_PIXEL_16x16: run_bidir<16, 16>( g, j, lane, visited[wb], r ); break;
+        case X264CU_PIXEL_16x8:  run_bidir<16, 8>( g, j, lane, visited[wb], r ); break;
+        case X264CU_PIXEL_8x16:  run_bidir<8, 16>( g, j, lane, visited[wb], r ); break;
+        case X264CU_PIXEL_8x8:   run_bidir<8, 8>( g, j, lane, visited[wb], r ); break;
+        case X264CU_PIXEL_8x4:   run_bidir<8, 4>( g, j, lane, visited[wb], r ); break;
+        case X264CU_PIXEL_4x8:   run_bidir<4, 8>( g, j, lane, visited[wb], r ); break;
+        default:                 run_bidir<4, 4>( g, j, lane, visited[wb], r ); break;
+    }
+    if( lane == 0 ) results[w] = r;
+}
+
+extern "C" int x264cu_me_refine_bidir_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *p, const uint8_t *d_fenc, intptr_t fenc_stride,
+                                             const uint8_t *const d_fref0[4], const uint8_t *const d_fref1[4], intptr_t ref_stride,
+                                             const x264cu_bidir_job_t *d_jobs, int n, x264cu_bidir_result_t *d_results )
+{
+    if( !ctx || !p ) return -1;
+    if( n <= 0 ) return 0;
+    if( !d_fenc || !d_fref0 || !d_fref1 || !d_jobs || !d_results )
+        return x264cu_fail( ctx, "me_refine_bidir_batch: null argument" );
+    if( p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 )
+        return x264cu_fail( ctx, "me_refine_bidir_batch: bad parameters" );
+    const uint16_t *d_tab = me_cost_table( ctx, p->lambda, p->mv_range );
+    if( !d_tab ) return -1;
+    BidirShared g;
+    g.fenc = d_fenc; g.fenc_stride = (int)fenc_stride;
+    for( int i = 0; i < 4; i++ ) { g.fref0[i] = d_fref0[i]; g.fref1[i] = d_fref1[i]; }
+    g.stride = (int)ref_stride;
+    g.cost_mv = d_tab;
+    g.satd = p->mbcmp_satd;
+    me_bidir_kernel<<<( n + 3 ) / 4, 128, 0, ctx->stream>>>( g, (const BidirJob *)d_jobs, n, (BidirResult *)d_results );
     CU_LAUNCH_CHECK( ctx );
     return 0;
 }

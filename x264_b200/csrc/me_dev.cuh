@@ -1,6 +1,6 @@
 // Generic warp-per-search block matcher: x264_me_search_ref + refine_subpel (encoder/me.c:182-992) for every luma
-// partition size, DIA / HEX / UMH, every sub-pel level (subpel_iterations, me.c:38-50), optional weighted reference and
-// half-pel early-termination threshold; no chroma ME, no ESA/TESA.
+// partition size, DIA / HEX / UMH / ESA / TESA, every sub-pel level (subpel_iterations, me.c:38-50), optional weighted reference
+// and half-pel early-termination threshold; no chroma ME.  Also x264_me_refine_bidir_satd (me.c:1027-1183).
 //
 // One warp runs one search with the reference's exact control flow (warp-uniform); every step's candidates are evaluated
 // in parallel: a WxH block is covered by L = (W/4)*(H/4) lanes (one 4x4 each), so S = 32/L candidates per round.
@@ -15,6 +15,11 @@ namespace x264cu {
 // i-th signed 4-bit entry of a packed table (keeps the small offset tables in immediates instead of local memory)
 __device__ __forceinline__ int nib( unsigned long long tab, int i ) { return (int)( (long long)( tab << ( 60 - 4*i ) ) >> 60 ); }
 
+// pair j of x264_me_refine_bidir_satd's table (me.c:1063-1074) as base-3 digits, offset = digit - 1, order (m0x, m0y, m1x, m1y)
+__constant__ uint8_t c_bidir_pairs[33] =
+    { 40, 67, 13, 49, 31, 43, 37, 41, 39, 76, 4, 52, 28, 44, 36, 68, 12, 70, 10, 50, 30, 58, 22, 46, 34, 42, 38, 14, 66, 64, 16, 48, 32 };
+__device__ __forceinline__ int bidir_code( int j ) { return c_bidir_pairs[j]; }
+
 struct MeShared                       // per-launch constants
 {
     const uint8_t *fenc; int fenc_stride;
@@ -22,7 +27,9 @@ struct MeShared                       // per-launch constants
     const uint16_t *cost_mv;          // centred table in global memory
     int me_method, subpel_refine, me_range;
     int satd;                         // mbcmp is SATD (encoder subme > 1)
+    int fpel_satd;                    // fpelcmp is SATD too: TESA with subme > 1 (encoder.c:1409-1427)
     LaWeight w;
+    uint2 *tesa_list; int tesa_cap;   // TESA: per-warp candidate lists (sad, packed mv), tesa_cap entries each
 };
 
 template <int BW, int BH>
@@ -38,8 +45,9 @@ struct MeWarp
     int x_min, y_min, x_max, y_max;
     int min_spel_x, min_spel_y, max_spel_x, max_spel_y;
     LaWeight w;
-    bool satd;
+    bool satd, fpel_satd;
     int slot;
+    int fsum, gl;                     // ADS: pixel sum of this lane's 4x4 of fenc; lane index within the candidate group
     // search state (uniform)
     int bmx, bmy, bcost;
 
@@ -57,14 +65,14 @@ struct MeWarp
         const uint8_t *s = fref_w + my * stride + mx;
 #pragma unroll
         for( int r = 0; r < 4; r++ ) b[r] = ldg4u( s + r * stride );
-        return group_sum( sad4x4( fenc, b ) );
+        return group_sum( fpel_satd ? satd4x4( fenc, b ) : sad4x4( fenc, b ) );        // fpelcmp
     }
     __device__ __forceinline__ int cost_fpel( int mx, int my ) const { return sad_fpel( mx, my ) + bits_fpel( mx, my ); }
     __device__ __forceinline__ int cost_qpel( int mx, int my, bool use_mbcmp ) const
     {
         uint32_t b[4];
         qpel4x4_p( fref0, fref1, fref2, fref3, stride, w, mx, my, b );
-        int d = ( use_mbcmp && satd ) ? satd4x4( fenc, b ) : sad4x4( fenc, b );
+        int d = ( use_mbcmp ? satd : fpel_satd ) ? satd4x4( fenc, b ) : sad4x4( fenc, b );
         return group_sum( d ) + __ldg( cost_mv + ( mx - mvpx ) ) + __ldg( cost_mv + ( my - mvpy ) );
     }
 
@@ -168,17 +176,179 @@ struct MeWarp
         bmx += sqx( w ); bmy += sqy( w );
         bcost = best >> 4;
     }
+
+    // ---- exhaustive searches, me.c:618-771 ----
+    // pixf.sad (always SAD) of the block at a full-pel position of the weighted plane, and pixf.ads' value without the mv cost
+    // (pixel.c:759-803): sum over the block's 8x8 (4x4 for partitions below 8x8) sub-blocks of |dc(fenc) - dc(ref)|, the
+    // reference's dc taken from the UNWEIGHTED plane like the integral image it is read from (mc.c:748-783)
+    __device__ __forceinline__ void sad_ads( int mx, int my, int &sad, int &ads ) const
+    {
+        uint32_t b[4];
+        const int o = my * stride + mx;
+#pragma unroll
+        for( int r = 0; r < 4; r++ ) b[r] = ldg4u( fref_w + o + r * stride );
+        sad = group_sum( sad4x4( fenc, b ) );
+        if( fref_w != fref0 )
+        {
+#pragma unroll
+            for( int r = 0; r < 4; r++ ) b[r] = ldg4u( fref0 + o + r * stride );
+        }
+        int d = fsum;
+#pragma unroll
+        for( int r = 0; r < 4; r++ ) d -= __dp4a( b[r], 0x01010101u, 0u );
+        if( BW >= 8 && BH >= 8 )
+        {
+            d += __shfl_xor_sync( 0xffffffffu, d, 1 );
+            d += __shfl_xor_sync( 0xffffffffu, d, LX );
+            d = ( ( gl % LX ) | ( gl / LX ) ) & 1 ? 0 : abs( d );
+        }
+        else
+            d = abs( d );
+        ads = group_sum( d );
+    }
+
+    // ESA, me.c:751-768: per row the positions whose ads + x mv cost stay below the best cost (less the row's y cost) are
+    // measured in ascending x.  Without a weighted reference ads is a lower bound of the SAD, the prefilter cannot drop a
+    // winner and it is skipped; with one (the sums come from the unweighted plane) it decides and is applied.
+    __device__ void esa( int me_range )
+    {
+        const int min_x = max( bmx - me_range, x_min ), min_y = max( bmy - me_range, y_min );
+        const int max_x = min( bmx + me_range, x_max ), max_y = min( bmy + me_range, y_max );
+        const int width = ( max_x - min_x + 3 ) & ~3;      // rounded up as in the reference: up to 3 positions past mv_x_max
+        const bool filter = fref_w != fref0;
+        for( int my = min_y; my <= max_y; my++ )
+        {
+            const int ycost = __ldg( cost_mv + ( my*4 - mvpy ) );
+            if( bcost <= ycost )
+                continue;
+            const int thresh = bcost - ycost;
+            for( int base = 0; base < width; base += S )
+            {
+                const int i = base + slot;
+                const int cx = min_x + min( i, width - 1 );
+                const int xcost = __ldg( cost_mv + ( cx*4 - mvpx ) );
+                int sad, ads = 0;
+                if( filter ) sad_ads( cx, my, sad, ads );
+                else sad = sad_fpel( cx, my );
+                const bool ok = i < width && ads + xcost < thresh;
+                int key = ok ? ( ( sad + xcost + ycost ) << 8 ) | slot : 0x7fffffff;
+                key = warp_min( key );
+                if( key != 0x7fffffff && ( key >> 8 ) < bcost )
+                {
+                    bcost = key >> 8;
+                    bmx = min_x + base + ( key & 255 ); bmy = my;
+                }
+            }
+        }
+    }
+
+    // TESA, me.c:656-747: ADS threshold (17/16 of the best SAD), SAD threshold (sad_thresh/8 of the running best), the list of
+    // survivors thinned to me_range/2 entries, then fpelcmp (SATD) on those.  `list` = this warp's scratch in global memory.
+    __device__ void tesa( int me_range, uint2 *list )
+    {
+        const int lane = slot * L + gl;
+        const int min_x = max( bmx - me_range, x_min ), min_y = max( bmy - me_range, y_min );
+        const int max_x = min( bmx + me_range, x_max ), max_y = min( bmy + me_range, y_max );
+        const int width = ( max_x - min_x + 3 ) & ~3;
+        int n = 0;
+        int sad_thresh = me_range <= 16 ? 10 : me_range <= 24 ? 11 : 12;
+        int bsad, unused;
+        sad_ads( bmx, bmy, bsad, unused );
+        bsad += bits_fpel( bmx, bmy );
+        for( int my = min_y; my <= max_y; my++ )
+        {
+            const int ycost = __ldg( cost_mv + ( my*4 - mvpy ) );
+            if( bsad <= ycost )
+                continue;
+            bsad -= ycost;
+            const int athresh = bsad * 17 >> 4;
+            for( int base = 0; base < width; base += S )
+            {
+                const int i = min( base + slot, width - 1 );
+                const int cx = min_x + i;
+                int sad, ads;
+                sad_ads( cx, my, sad, ads );
+                const int pass = base + slot < width && ads + __ldg( cost_mv + ( cx*4 - mvpx ) ) < athresh;
+                // the listing step reads the x mv cost at the position's index within the row (cost_fpel_mvx[xs[i]], me.c:683, :699)
+                const int v = sad + __ldg( cost_mv + ( i*4 - mvpx ) );
+#pragma unroll 1
+                for( int k = 0; k < S; k++ )
+                {
+                    const int pk = __shfl_sync( 0xffffffffu, pass, k * L ), vk = __shfl_sync( 0xffffffffu, v, k * L );
+                    if( pk && vk < ( bsad * sad_thresh >> 3 ) )
+                    {
+                        bsad = min( bsad, vk );
+                        if( lane == 0 ) list[n] = make_uint2( (uint32_t)( vk + ycost ), pack_mv( min_x + base + k, my ) );
+                        n++;
+                    }
+                }
+            }
+            bsad += ycost;
+        }
+        __syncwarp();
+        const int limit = me_range >> 1;
+        sad_thresh = bsad * sad_thresh >> 3;
+        while( n > limit*2 && sad_thresh > bsad )
+        {   // halve the admitted range; keep, in order, what is still inside it
+            sad_thresh = ( sad_thresh + bsad ) >> 1;
+            int k = 0;
+            for( int base = 0; base < n; base += 32 )
+            {
+                const int i = base + lane;
+                uint2 e = make_uint2( 0, 0 );
+                if( i < n ) e = list[i];
+                const bool keep = i < n && (int)e.x <= sad_thresh;
+                const uint32_t mask = __ballot_sync( 0xffffffffu, keep );
+                __syncwarp();
+                if( keep ) list[k + __popc( mask & ( ( 1u << lane ) - 1 ) )] = e;
+                k += __popc( mask );
+                __syncwarp();
+            }
+            n = k;
+        }
+        while( n > limit )
+        {   // drop the first worst entry, the last one takes its place
+            int msad = -1, midx = 0x7fffffff;
+            for( int i = lane; i < n; i += 32 )
+            {
+                const int sd = (int)list[i].x;
+                if( sd > msad ) { msad = sd; midx = i; }
+            }
+            const int wsad = __reduce_max_sync( 0xffffffffu, msad );
+            const int bi = __reduce_min_sync( 0xffffffffu, msad == wsad ? midx : 0x7fffffff );
+            n--;
+            if( lane == 0 ) list[bi] = list[n];
+            __syncwarp();
+        }
+        for( int base = 0; base < n; base += S )
+        {
+            const int i = base + slot;
+            const uint2 e = list[min( i, n - 1 )];
+            const int cx = (int16_t)( e.y & 0xffff ), cy = (int16_t)( e.y >> 16 );
+            const int c = cost_fpel( cx, cy );
+            int key = i < n ? ( c << 8 ) | slot : 0x7fffffff;
+            key = warp_min( key );
+            if( key != 0x7fffffff && ( key >> 8 ) < bcost )
+            {
+                const uint2 w = list[base + ( key & 255 )];
+                bcost = key >> 8;
+                bmx = (int16_t)( w.y & 0xffff ); bmy = (int16_t)( w.y >> 16 );
+            }
+        }
+        __syncwarp();
+    }
 };
 
 // mvc: up to 8 candidate vectors; thresh_io: half-pel early-termination threshold (< 0 = none)
 template <int BW, int BH>
 __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc_off, uint32_t ref_off, int mvpx, int mvpy,
                                    const int16_t *mvc, int i_mvc, const int16_t *limits /* min_x,min_y,max_x,max_y spel */,
-                                   int &thresh_io, int lane, int &out_mvx, int &out_mvy, int &out_cost, int &out_cost_mv )
+                                   int &thresh_io, int lane, int &out_mvx, int &out_mvy, int &out_cost, int &out_cost_mv, uint2 *tesa_list )
 {
     using M = MeWarp<BW, BH>;
     M m;
     const int gl = lane % M::L;
+    m.gl = gl; m.fpel_satd = g.fpel_satd != 0;
     const int sx = ( gl % M::LX ) * 4, sy = ( gl / M::LX ) * 4;
     m.slot = lane / M::L;
     m.stride = g.stride; m.cost_mv = g.cost_mv; m.w = g.w; m.satd = g.satd != 0;
@@ -187,6 +357,9 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
         const uint8_t *f = g.fenc + fenc_off + sy * g.fenc_stride + sx;
 #pragma unroll
         for( int r = 0; r < 4; r++ ) m.fenc[r] = ldg4u( f + r * g.fenc_stride );
+        m.fsum = 0;
+#pragma unroll
+        for( int r = 0; r < 4; r++ ) m.fsum = __dp4a( m.fenc[r], 0x01010101u, (uint32_t)m.fsum );
         const int o = ref_off + sy * g.stride + sx;
         m.fref0 = g.fref[0] + o; m.fref1 = g.fref[1] + o; m.fref2 = g.fref[2] + o; m.fref3 = g.fref[3] + o;
         m.fref_w = g.fref_w + o;
@@ -319,18 +492,9 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
     else if( g.me_method == X264CU_ME_HEX )
         m.hex_refine( me_range );
     else if( g.me_method == X264CU_ME_ESA )
-    {   // me.c:618-771, the "just ADS and SAD" branch.  The reference's ADS prefilter (pixf.ads over the integral image) only
-        // drops positions whose lower bound |sum(fenc) - sum(ref)| + mv cost already reaches the best cost: sum|a-b| >= |sum a -
-        // sum b|, so none of them could be strictly better.  The result is therefore the first strictly smaller cost in raster
-        // order over the window, which the warp computes by brute force, S positions per round, row after row (32/L SADs per
-        // round: no integral images, no prefilter).  The window's width is rounded up to a multiple of 4 as in the reference
-        // (up to 3 positions past mv_x_max, never range-checked).
-        const int min_x = max( m.bmx - me_range, m.x_min ), min_y = max( m.bmy - me_range, m.y_min );
-        const int max_x = min( m.bmx + me_range, m.x_max ), max_y = min( m.bmy + me_range, m.y_max );
-        const int width = ( max_x - min_x + 3 ) & ~3;
-        for( int my = min_y; my <= max_y; my++ )
-            m.try_list_v( width, min_x, my, []( int i ) { return i; }, []( int ) { return 0; }, []( int, int ) { return true; } );
-    }
+        m.esa( me_range );
+    else if( g.me_method == X264CU_ME_TESA )
+        m.tesa( me_range, tesa_list );
     else
     {   // UMH, me.c:422-616
         const int shift = i_pixel == 0 ? 0 : i_pixel <= 2 ? 1 : i_pixel == 3 ? 2 : i_pixel <= 5 ? 3 : 4;   // pixel_size_shift
@@ -471,7 +635,7 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
                 if( diamond( 2, false, -1 ) < 0 )
                     break;
         }
-        if( m.satd )
+        if( m.satd && !m.fpel_satd )                              // mbcmp != fpelcmp: re-measure the winner, me.c:925-929
             qcost = m.cost_qpel( qx, qy, true );
         bool early = false;
         if( thresh_io >= 0 )
@@ -503,5 +667,102 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
 
 #undef CX
 #undef CY
+
+// ---- x264_me_refine_bidir_satd, me.c:1027-1183 (rd = 0) ---------------------------------------------------------------------
+// One warp refines one (list 0, list 1) vector pair.  A pass measures the pairs that differ from the current one by +-1
+// quarter-pel in at most two of the four components -- 33 pairs (the reference's dia4d table, me.c:1063-1074, kept here as
+// base-3 digits), S = 32/L of them per round -- skipping pairs already measured (the reference's 4096-bit map indexed by the low
+// three bits of each component, in shared memory), cost = mbcmp( fenc, avg( ref0, ref1, weight ) ) + four mv costs; strictly
+// smaller wins, first in table order on ties; up to 8 passes, until the centre stays.
+__device__ __forceinline__ uint32_t avg4_bipred( uint32_t a, uint32_t b, int weight )       // pixel_avg_wxh / _weight_wxh, mc.c:49-75
+{
+    if( weight == 32 )
+        return __vavgu4( a, b );
+    uint32_t out = 0;
+#pragma unroll
+    for( int i = 0; i < 4; i++ )
+    {
+        const int p = ( a >> ( 8*i ) ) & 255, q = ( b >> ( 8*i ) ) & 255;
+        const int v = ( p * weight + q * ( 64 - weight ) + 32 ) >> 6;
+        out |= (uint32_t)min( max( v, 0 ), 255 ) << ( 8*i );
+    }
+    return out;
+}
+
+struct BidirShared
+{
+    const uint8_t *fenc; int fenc_stride;
+    const uint8_t *fref0[4], *fref1[4]; int stride;
+    const uint16_t *cost_mv;
+    int satd;
+};
+
+template <int BW, int BH>
+__device__ void me_refine_bidir( const BidirShared &g, uint32_t fenc_off, uint32_t ref0_off, uint32_t ref1_off, const int16_t *mv_in /* m0x m0y m1x m1y */,
+                                 const int16_t *mvp /* same order */, const int16_t *limits /* min_x,min_y,max_x,max_y spel */, int weight,
+                                 int lane, uint32_t *visited /* 128 words of shared memory, this warp's */, int bm[4], int &out_cost )
+{
+    constexpr int LX = BW / 4, L = LX * ( BH / 4 ), S = 32 / L;
+    const int gl = lane % L, slot = lane / L;
+    const int sx = ( gl % LX ) * 4, sy = ( gl / LX ) * 4;
+    uint32_t fenc[4];
+    {
+        const uint8_t *f = g.fenc + fenc_off + sy * g.fenc_stride + sx;
+#pragma unroll
+        for( int r = 0; r < 4; r++ ) fenc[r] = ldg4u( f + r * g.fenc_stride );
+    }
+    const int o0 = ref0_off + sy * g.stride + sx, o1 = ref1_off + sy * g.stride + sx;
+#pragma unroll
+    for( int k = 0; k < 4; k++ ) bm[k] = mv_in[k];
+    out_cost = LA_COST_MAX;
+    for( int k = 0; k < 4; k++ )                                   // me.c:1076-1080: too close to the window's edge
+        if( bm[k] < limits[k & 1] + 8 || bm[k] > limits[2 + ( k & 1 )] - 8 )
+            return;
+    for( int i = lane; i < 128; i += 32 ) visited[i] = 0;
+    __syncwarp();
+    LaWeight none; none.enabled = 0; none.scale = 0; none.denom = 0; none.offset = 0;
+    int bcost = LA_COST_MAX;
+    for( int pass = 0; pass < 8; pass++ )
+    {
+        int best = 0x7fffffff;
+        const int first = pass ? 1 : 0;
+        for( int base = first; base < 33; base += S )
+        {
+            const int j = min( base + slot, 32 );
+            int code = bidir_code( j );
+            int v[4];
+#pragma unroll
+            for( int k = 0; k < 4; k++, code /= 3 ) v[k] = bm[k] + code % 3 - 1;
+            const int word = ( ( v[0] & 7 ) << 4 ) | ( ( v[1] & 7 ) << 1 ) | ( ( v[2] & 7 ) >> 2 );
+            const uint32_t bit = 1u << ( ( ( v[2] & 3 ) << 3 ) | ( v[3] & 7 ) );
+            const bool fresh = base + slot < 33 && ( !pass || !( visited[word] & bit ) );
+            uint32_t p0[4], p1[4];
+            qpel4x4_p( g.fref0[0] + o0, g.fref0[1] + o0, g.fref0[2] + o0, g.fref0[3] + o0, g.stride, none, v[0], v[1], p0 );
+            qpel4x4_p( g.fref1[0] + o1, g.fref1[1] + o1, g.fref1[2] + o1, g.fref1[3] + o1, g.stride, none, v[2], v[3], p1 );
+#pragma unroll
+            for( int r = 0; r < 4; r++ ) p0[r] = avg4_bipred( p0[r], p1[r], weight );
+            int d = g.satd ? satd4x4( fenc, p0 ) : sad4x4( fenc, p0 );
+#pragma unroll
+            for( int m = 1; m < L; m <<= 1 ) d += __shfl_xor_sync( 0xffffffffu, d, m );
+            d += __ldg( g.cost_mv + ( v[0] - mvp[0] ) ) + __ldg( g.cost_mv + ( v[1] - mvp[1] ) )
+               + __ldg( g.cost_mv + ( v[2] - mvp[2] ) ) + __ldg( g.cost_mv + ( v[3] - mvp[3] ) );
+            __syncwarp();
+            if( fresh && gl == 0 ) atomicOr( &visited[word], bit );
+            __syncwarp();
+            const int key = fresh ? ( d << 6 ) | j : 0x7fffffff;
+            best = min( best, warp_min( key ) );
+        }
+        if( best == 0x7fffffff || ( best >> 6 ) >= bcost )
+            break;
+        const int bestj = best & 63;
+        bcost = best >> 6;
+        if( !bestj )
+            break;
+        int code = bidir_code( bestj );
+#pragma unroll
+        for( int k = 0; k < 4; k++, code /= 3 ) bm[k] += code % 3 - 1;
+    }
+    out_cost = bcost;
+}
 
 } // namespace x264cu
