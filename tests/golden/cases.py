@@ -63,6 +63,8 @@ ME_GROUPS = [  # (method, subpel_refine, me_range, mbcmp_is_satd, weight)
     (0, 2, 16, 1, (0, 0, 0, 0)), (0, 5, 8, 1, (0, 0, 0, 0)), (1, 1, 16, 0, (0, 0, 0, 0)), (1, 4, 16, 1, (0, 0, 0, 0)),
     (1, 7, 16, 1, (1, 70, 6, -3)), (2, 3, 24, 1, (0, 0, 0, 0)), (2, 9, 32, 1, (0, 0, 0, 0)), (2, 6, 16, 1, (1, 55, 6, 4)),
     (3, 2, 8, 1, (0, 0, 0, 0)), (3, 7, 16, 1, (0, 0, 0, 0)),      # ESA (reference side: xref_me_search_frame, its own integral image)
+    (3, 7, 16, 1, (1, 62, 6, 3)),                                  # ESA against a weighted reference: the ADS prefilter decides
+    (4, 7, 16, 1, (0, 0, 0, 0)), (4, 2, 24, 1, (1, 75, 6, -2)), (4, 0, 8, 1, (0, 0, 0, 0)),      # TESA (fpelcmp = SATD)
 ]
 ME_JOBS = 40
 
@@ -100,6 +102,35 @@ def me_jobs(group_index):
         jobs.append(dict(ip=ip, bx=bx, by=by, lim_min=lim_min, lim_max=lim_max, i_mvc=i_mvc, mvp=[int(mvp[0]), int(mvp[1])],
                          mvc=mvcs.astype(np.int16), use_thresh=use_thresh, thresh=thresh))
     return jobs
+
+
+# ---- x264_me_refine_bidir_satd (encoder/me.c:1027-1183) --------------------------------------------------------------------
+BIDIR_CASES = [(1, 7), (0, 1)]          # (mbcmp is SATD, seed)
+BIDIR_JOBS = 60
+
+
+def bidir_case(ci):
+    satd, seed = BIDIR_CASES[ci]
+    rng = np.random.default_rng(seed)
+    fenc_l, ref0_l = me_content(20 + seed)
+    ref1_l = np.ascontiguousarray(np.roll(ref0_l, (3, -2), (0, 1)))
+    jobs = []
+    for _ in range(BIDIR_JOBS):
+        ip = int(rng.integers(0, 7))
+        bw, bh = PIXEL_W[ip], PIXEL_H[ip]
+        bx = int(rng.integers(0, (ME_W - bw) // 4 + 1)) * 4
+        by = int(rng.integers(0, (ME_H - bh) // 4 + 1)) * 4
+        mvr = 4 * ME_MV_RANGE
+        lim_min = np.array([max(4 * (-bx - 24), -mvr), max(4 * (-by - 24), -mvr)])
+        lim_max = np.array([min(4 * (ME_W - bx - bw + 24), mvr - 1), min(4 * (ME_H - by - bh + 24), mvr - 1)])
+        spread = int(rng.choice([6, 30, 120]))
+        mv0 = np.clip(rng.integers(-spread, spread + 1, 2), lim_min, lim_max)
+        mv1 = np.clip(rng.integers(-spread, spread + 1, 2), lim_min, lim_max)
+        mvp0, mvp1 = mv0 + rng.integers(-6, 7, 2), mv1 + rng.integers(-6, 7, 2)
+        weight = int(rng.choice([32, 32, 21, 43, -10]))
+        jobs.append(dict(ip=ip, bx=bx, by=by, lim_min=[int(v) for v in lim_min], lim_max=[int(v) for v in lim_max],
+                         mv=[int(v) for v in np.concatenate([mv0, mv1])], mvp=[int(v) for v in np.concatenate([mvp0, mvp1])], weight=weight))
+    return fenc_l, ref0_l, ref1_l, jobs
 
 
 # ---- slicetype_frame_cost (encoder/slicetype.c:836-995) --------------------------------------------------------------

@@ -137,9 +137,9 @@ def run_me(backend, gi, ctx=None):
     n = 2 * 4 * G.ME_MV_RANGE
     if backend == "ref":
         r = ref()
-        esa = method == 3
+        esa = method >= 3
         r.xref_me_search_frame.argtypes = [C.c_void_p, C.POINTER(XrefMeArgs), C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int]
-        hnd = r.xref_open(G.ME_W, G.ME_H, b"medium", (b"subme=7" if satd else b"subme=1") + (b":me=esa:merange=32:partitions=all" if esa else b""), 0)
+        hnd = r.xref_open(G.ME_W, G.ME_H, b"medium", (b"subme=7" if satd else b"subme=1") + (b":me=%s:merange=32:partitions=all" % (b"tesa" if method == 4 else b"esa") if esa else b""), 0)
         assert hnd
         ref_l = np.ascontiguousarray(ref_l)
         for k, j in enumerate(jobs):
@@ -203,6 +203,85 @@ def run_me(backend, gi, ctx=None):
             ctx.free(p)
         out[:, 0], out[:, 1], out[:, 2] = res["mv"][:, 0], res["mv"][:, 1], res["cost"]
         out[:, 3] = [int(res[k]["halfpel_thresh"]) if jobs[k]["use_thresh"] else -1 for k in range(len(jobs))]
+    return out, dig
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_bidir(backend, ci, ctx=None):
+    """-> int16 [BIDIR_JOBS, 4] = the refined (m0x, m0y, m1x, m1y) of x264_me_refine_bidir_satd"""
+    _libs._bind_me()
+    satd, _ = G.BIDIR_CASES[ci]
+    fenc_l, ref0_l, ref1_l, jobs = G.bidir_case(ci)
+    pl0, pl1 = make_ref_planes(np.ascontiguousarray(ref0_l)), make_ref_planes(np.ascontiguousarray(ref1_l))
+    st = pl0[0].stride
+    fenc = PaddedPlane(G.ME_W, G.ME_H, stride=st)
+    fenc.inner()[:] = fenc_l
+    dig = G.digest(fenc.buf, *[p.buf for p in pl0], *[p.buf for p in pl1])
+    out = np.zeros((len(jobs), 4), np.int16)
+    n = 2 * 4 * G.ME_MV_RANGE
+    if backend == "ref":
+        r = ref()
+        r.xref_me_refine_bidir_satd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        r.xref_me_refine_bidir_satd.restype = None
+        hnd = r.xref_open(G.ME_W, G.ME_H, b"medium", b"subme=7" if satd else b"subme=1", 0)
+        assert hnd
+        for k, j in enumerate(jobs):
+            off = pl0[0].off(j["bx"], j["by"])
+            f0 = (C.c_void_p * 4)(*[p.buf.ctypes.data + off for p in pl0])
+            f1 = (C.c_void_p * 4)(*[p.buf.ctypes.data + off for p in pl1])
+            mv = np.array(j["mv"], np.int16)
+            mvp = np.array(j["mvp"], np.int16)
+            a0, a1 = mv[:2].copy(), mv[2:].copy()
+            p0, p1 = mvp[:2].copy(), mvp[2:].copy()
+            lmin, lmax = np.array(j["lim_min"], np.int32), np.array(j["lim_max"], np.int32)
+            r.xref_me_refine_bidir_satd(hnd, j["ip"], 12, ptr(fenc.buf, fenc.off(j["bx"], j["by"])), st, f0, f1, st, ptr(a0), ptr(p0), ptr(a1), ptr(p1),
+                                        j["weight"], ptr(lmin), ptr(lmax))
+            out[k] = (a0[0], a0[1], a1[0], a1[1])
+        r.xref_close(hnd)
+    elif backend == "oracle":
+        o = oracle()
+        o.orc_me_refine_bidir_satd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        o.orc_me_refine_bidir_satd.restype = None
+        tab = np.zeros(2 * n + 1, np.uint16)
+        o.orc_cost_mv_table(tab, n, 1)
+        for k, j in enumerate(jobs):
+            off = pl0[0].off(j["bx"], j["by"])
+            c = OrcMeCtx()
+            c.me_method, c.subpel_refine, c.me_range, c.mbcmp_is_satd = 1, 7, 16, satd
+            for i in range(2):
+                c.mv_min_spel[i], c.mv_max_spel[i] = j["lim_min"][i], j["lim_max"][i]
+            ms = []
+            for li, pl in enumerate((pl0, pl1)):
+                m = OrcMe()
+                m.i_pixel = j["ip"]
+                m.p_cost_mv = tab.ctypes.data + 2 * n
+                for i in range(4):
+                    m.p_fref[i] = pl[i].buf.ctypes.data + off
+                m.p_fref_w = pl[0].buf.ctypes.data + off
+                m.p_fenc = fenc.buf.ctypes.data + fenc.off(j["bx"], j["by"])
+                m.fenc_stride, m.stride = st, st
+                m.weight = OrcWeight(0, 0, 0, 0)
+                m.mvp[0], m.mvp[1] = j["mvp"][2 * li], j["mvp"][2 * li + 1]
+                m.mv[0], m.mv[1] = j["mv"][2 * li], j["mv"][2 * li + 1]
+                ms.append(m)
+            o.orc_me_refine_bidir_satd(C.byref(c), C.byref(ms[0]), C.byref(ms[1]), j["weight"])
+            out[k] = (ms[0].mv[0], ms[0].mv[1], ms[1].mv[0], ms[1].mv[1])
+    else:
+        import x264_b200 as x
+        ja = np.zeros(len(jobs), x.bidir_job_dtype)
+        for k, j in enumerate(jobs):
+            e = ja[k]
+            off = pl0[0].off(j["bx"], j["by"])
+            e["i_pixel"], e["fenc_off"], e["ref0_off"], e["ref1_off"] = j["ip"], fenc.off(j["bx"], j["by"]), off, off
+            e["mv"], e["mvp"], e["mv_min_spel"], e["mv_max_spel"], e["i_weight"] = j["mv"], j["mvp"], j["lim_min"], j["lim_max"], j["weight"]
+        d_fenc = ctx.upload(fenc.buf)
+        d0, d1 = [ctx.upload(p.buf) for p in pl0], [ctx.upload(p.buf) for p in pl1]
+        params = x.MeParams(1, 7, 16, satd, 1, G.ME_MV_RANGE, 0, 0, 0, 0)
+        res = x.me_refine_bidir_batch(ctx, params, d_fenc, st, d0, d1, st, ja)
+        for p in [d_fenc] + d0 + d1:
+            ctx.free(p)
+        out[:] = res["mv"]
     return out, dig
 
 

@@ -60,6 +60,15 @@ def test_me_search(request, backend, gi):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("ci", range(len(G.BIDIR_CASES)))
+def test_me_refine_bidir(request, backend, ci):
+    got, dig = R.run_bidir(backend, ci, _ctx(request, backend))
+    _check_inputs("bidir_%d" % ci, dig)
+    want = GOLD["bidir_%d" % ci]
+    assert np.array_equal(got, want), (G.BIDIR_CASES[ci], np.argwhere(got != want)[:5])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("ci", range(len(G.LA_CASES)))
 def test_lookahead_frame_cost(request, backend, ci):
     res, _, dig = R.run_la(backend, ci, GOLD["la_%d_params" % ci], _ctx(request, backend))
