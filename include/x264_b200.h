@@ -203,7 +203,7 @@ typedef struct
     int weighted_bipred;          /* h->param.analyse.b_weighted_bipred */
     int aq_mode;                  /* h->param.rc.i_aq_mode != 0 */
     int mb_tree;                  /* h->param.rc.b_mb_tree */
-    int vbv;                      /* h->param.rc.i_vbv_buffer_size != 0 */
+    int vbv;                      /* h->param.rc.i_vbv_buffer_size != 0: row SATDs kept, edge macroblocks costed, VBV lookahead in slicetype */
     int n_slots;                  /* frames resident in HBM at once (>= lookahead + bframes + 3) */
     int weighted_pred;            /* h->param.analyse.i_weighted_pred: non-zero runs the lookahead weight analysis (slicetype.c:284-501)
                                      on first P-type searches; -1 = X264_WEIGHTP_FAKE (encoder.c:1316-1317), which also records
@@ -303,6 +303,11 @@ int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames
  * CLIP_DURATION(frame->f_duration) * 256 / MBTREE_PRECISION ), strength = 5 * (1 - rc.f_qcompress) (slicetype.c:1031-1038);
  * fps_factor = 0: f_qp_offset = f_qp_offset_aq (the lookahead-less intra case, slicetype.c:1121-1123) */
 int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_factor, int ref0_distance, float strength );
+/* slicetype_frame_cost_recalculate( h, frames, p0, p1, b ) (slicetype.c:999-1024), used by x264_rc_analyse_slice and the VBV
+ * lookahead: the cost of a requested (slot = frames[b], dist0 = b-p0, dist1 = p1-b) with every macroblock's lowres cost scaled by
+ * x264_exp2fix8 of its quantiser offset -- f_qp_offset (MB-tree's), or f_qp_offset_aq when b_type (a B picture).  Rewrites
+ * i_row_satds[dist0][dist1] on the device; *h_score = the returned cost, h_row_satd (mb_height ints, may be NULL) = the rows. */
+int x264cu_lookahead_frame_cost_recalculate( x264cu_lookahead_t *la, int slot, int dist0, int dist1, int b_type, int *h_score, int32_t *h_row_satd );
 int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *h_qp_offset );          /* f_qp_offset, one per MB */
 int x264cu_lookahead_get_propagate_cost( x264cu_lookahead_t *la, int slot, uint16_t *h_propagate_cost );
 /* f_weighted_cost_delta[dist_minus1] (slicetype.c:462-463; set only with weighted_pred < 0 = X264_WEIGHTP_FAKE) */
@@ -387,6 +392,19 @@ int  x264cu_slicetype_slot_of( x264cu_slicetype_t *st, int frame );
  * call): MB-tree's quantiser offsets when mb_tree is set.  mb_count floats.  Non-B pictures only: B pictures are coded with
  * f_qp_offset_aq (slicetype.c:1003), which the caller supplied, and have left the lookahead by then (-1). */
 int  x264cu_slicetype_get_qp_offset( x264cu_slicetype_t *st, int frame, float *h_qp_offset );
+/* x264_rc_analyse_slice (slicetype.c:1976-2030) for the picture the last x264cu_slicetype_step returned (it stays in the
+ * lookahead until the next step): *cost = fdec->i_satd -- the memoised cost of the picture against the references it will be
+ * coded with, recalculated with MB-tree's quantiser offsets when mb_tree is set (slicetype_frame_cost_recalculate), the AQ
+ * weighted cost otherwise when aq_mode is set --, h_row_satd (mb_height ints, may be NULL) = fdec->i_row_satd, h_row_satd_intra
+ * (may be NULL; non-I pictures) = i_row_satds[0][0].  The rows are defined with la.vbv or mb_tree, as in the reference.  B
+ * pictures need la.vbv (slicetype.c:1916); rc_cqp: -1 (the reference does not call it).  Not built: the intra-refresh column
+ * correction (slicetype.c:2015-2036; la.vbv with intra_refresh is rejected at open). */
+int  x264cu_slicetype_rc_analyse_slice( x264cu_slicetype_t *st, int frame, int *cost, int *h_row_satd, int *h_row_satd_intra );
+/* VBV lookahead (vbv_lookahead, slicetype.c:1225-1286; la.vbv and rc_lookahead > 0): i_planned_type[] / i_planned_satd[] of a
+ * non-B picture the last step returned = the types and costs of the pictures coded after it, as far as the lookahead has
+ * decided them.  Returns the number of entries (the reference terminates the list with X264_TYPE_AUTO), -1 on error.  The
+ * f_planned_cpb_duration[] of the reference (picture durations, no analysis) is not produced. */
+int  x264cu_slicetype_get_planned( x264cu_slicetype_t *st, int frame, int *h_type, int *h_satd, int max_entries );
 /* number of slicetype_frame_cost requests issued so far (memo hits included) */
 long x264cu_slicetype_cost_requests( x264cu_slicetype_t *st );
 

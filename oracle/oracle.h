@@ -143,6 +143,8 @@ void orc_la_mbtree_propagate( const orc_la_params_t *p, orc_la_frame_t **frames,
  * strength = 5 * (1 - qcompress) */
 void orc_la_mbtree_finish( orc_la_frame_t *f, int fps_factor, int ref0_distance, float strength );
 void orc_la_mbtree_reset( orc_la_frame_t *f );
+/* slicetype_frame_cost_recalculate (slicetype.c:999-1024) */
+int  orc_la_frame_cost_recalculate( const orc_la_params_t *p, orc_la_frame_t **frames, int p0, int p1, int b, int b_is_b_type );
 void orc_la_frame_set_qp_offset_aq( orc_la_frame_t *f, const float *aq );
 void orc_la_frame_get_mbtree( orc_la_frame_t *f, int what, int i, void *out );
 float orc_log2( uint32_t x );           /* x264_log2, common/base.h:226-230 */

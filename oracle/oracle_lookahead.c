@@ -794,3 +794,45 @@ void orc_la_mbtree_finish( orc_la_frame_t *f, int fps_factor, int ref0_distance,
         }
     }
 }
+
+/* slicetype_frame_cost_recalculate, slicetype.c:999-1024: the frame cost with every macroblock's lowres cost scaled by
+ * x264_exp2fix8 of its quantiser offset (MB-tree's f_qp_offset; f_qp_offset_aq for B pictures); rewrites
+ * row_satds[b-p0][p1-b] and returns the sum over the interior macroblocks (all of them for frames <= 2 macroblocks wide / high). */
+static int la_exp2fix8( float x )                                /* x264_exp2fix8, common/base.h:218-224 */
+{
+    static uint8_t lut[64];
+    static int init = 0;
+    if( !init )
+    {   /* x264_exp2_lut (common/tables.c:58-64): round( 256 * (2^(i/64) - 1) ) */
+        for( int i = 0; i < 64; i++ ) lut[i] = (uint8_t)( 256.0 * ( pow( 2.0, i / 64.0 ) - 1.0 ) + 0.5 );
+        init = 1;
+    }
+    int i = x * ( -64.f / 6.f ) + 512.5f;
+    if( i < 0 ) return 0;
+    if( i > 1023 ) return 0xffff;
+    return ( lut[i & 63] + 256 ) << ( i >> 6 ) >> 8;
+}
+
+int orc_la_frame_cost_recalculate( const orc_la_params_t *p, orc_la_frame_t **frames, int p0, int p1, int b, int b_is_b_type )
+{
+    orc_la_frame_t *f = frames[b];
+    const float *qp_offset = b_is_b_type ? f->qp_offset_aq : f->qp_offset;
+    const uint16_t *costs = f->lowres_costs[b-p0][p1-b];
+    int *row_satd = f->row_satds[b-p0][p1-b];
+    const int w = p->mb_width, h = p->mb_height;
+    int score = 0;
+    for( int y = h - 1; y >= 0; y-- )
+    {
+        row_satd[y] = 0;
+        for( int x = w - 1; x >= 0; x-- )
+        {
+            /* LOWRES_COST_MASK, frame.h:110; lowres_costs[0][0] IS i_intra_cost in the reference (frame.c:287) */
+            int cost = ( b == p0 && b == p1 ? (uint16_t)f->intra_cost[x + y*w] : costs[x + y*w] ) & 0x3fff;
+            cost = ( cost * la_exp2fix8( qp_offset[x + y*w] ) + 128 ) >> 8;
+            row_satd[y] += cost;
+            if( ( y > 0 && y < h - 1 && x > 0 && x < w - 1 ) || w <= 2 || h <= 2 )
+                score += cost;
+        }
+    }
+    return score;
+}

@@ -551,6 +551,26 @@ XREF_API void xref_la_mbtree( void *lav, int num_frames, int b_intra )
     xref_la_t *la = lav;
     macroblock_tree( la->h, &la->a, la->frames, num_frames, b_intra );
 }
+/* slicetype_frame_cost_recalculate( h, frames, p0, p1, b ) (slicetype.c:999-1024); frames[b]->i_type picks the offsets */
+XREF_API int xref_la_frame_cost_recalculate( void *lav, int p0, int p1, int b )
+{
+    xref_la_t *la = lav;
+    return slicetype_frame_cost_recalculate( la->h, la->frames, p0, p1, b );
+}
+/* the same by frame (idx as in xref_la_get) and distances, with the picture type given: b_type != 0 = a B picture */
+XREF_API int xref_la_frame_cost_recalculate_at( void *lav, int idx, int i0, int i1, int b_type, int *rows )
+{
+    xref_la_t *la = lav;
+    x264_frame_t *fr[2*X264_BFRAME_MAX + 8] = { NULL };
+    x264_frame_t *f = XREF_LA_FRAME( la, idx );
+    int save = f->i_type;
+    f->i_type = b_type ? X264_TYPE_B : X264_TYPE_P;
+    fr[i0] = f;
+    int score = slicetype_frame_cost_recalculate( la->h, fr, 0, i0 + i1, i0 );
+    f->i_type = save;
+    if( rows ) memcpy( rows, f->i_row_satds[i0][i1], la->h->mb.i_mb_height * sizeof(int) );
+    return score;
+}
 /* what: 0 f_qp_offset, 1 f_qp_offset_aq (float per MB), 2 i_propagate_cost (u16 per MB), 3 f_weighted_cost_delta[i] (one float) */
 XREF_API void xref_la_get_mbtree( void *lav, int idx, int what, int i, void *out )
 {
@@ -616,6 +636,30 @@ XREF_API void xref_set_qp_capture( float *buf ) { xref_qp_capture = buf; }
 #define XREF_CAPTURE_QP() do { if( xref_qp_capture && h->fenc ) \
     memcpy( xref_qp_capture + (size_t)n_out * h->mb.i_mb_count, h->fenc->f_qp_offset, h->mb.i_mb_count * sizeof(float) ); } while( 0 )
 
+/* when set: xref_encode_types also stores, per coded frame, `stride` ints: [0] = the cost x264_rc_analyse_slice returns for it
+ * (called again here right after the frame was coded: same inputs, same result; -1 where the encoder does not call it: B
+ * pictures without VBV, CQP), [1 .. mb_height] = its i_row_satd, then n = the number of planned entries (VBV lookahead,
+ * slicetype.c:1225-1286), i_planned_type[0..31] and i_planned_satd[0..31] */
+static int *xref_rc_capture; static int xref_rc_stride;
+XREF_API void xref_set_rc_capture( int *buf, int stride ) { xref_rc_capture = buf; xref_rc_stride = stride; }
+static void capture_rc( x264_t *h, int n_out )
+{
+    if( !xref_rc_capture || !h->fenc ) return;
+    int *o = xref_rc_capture + (size_t)n_out * xref_rc_stride;
+    int mbh = h->mb.i_mb_height;
+    o[0] = -1;
+    if( h->param.rc.i_rc_method != X264_RC_CQP && ( !IS_X264_TYPE_B( h->fenc->i_type ) || h->param.rc.i_vbv_buffer_size ) )
+    {
+        o[0] = x264_rc_analyse_slice( h );
+        memcpy( o + 1, h->fenc->i_row_satd, mbh * sizeof(int) );
+    }
+    int n = 0;
+    if( !IS_X264_TYPE_B( h->fenc->i_type ) && h->param.rc.i_vbv_buffer_size && h->param.rc.i_lookahead )
+        while( n < 32 && h->fenc->i_planned_type[n] != X264_TYPE_AUTO ) n++;
+    o[1 + mbh] = n;
+    for( int i = 0; i < n; i++ ) { o[2 + mbh + i] = h->fenc->i_planned_type[i]; o[2 + mbh + 32 + i] = h->fenc->i_planned_satd[i]; }
+}
+
 /* when set: pic_in.i_type of picture i (X264_TYPE_*; forced frame types as a qpfile / an application would give them) */
 static const int *xref_forced_types;
 XREF_API void xref_set_forced_types( const int *types ) { xref_forced_types = types; }
@@ -642,13 +686,13 @@ XREF_API int xref_encode_types( void *hv, const uint8_t *luma, int n, int *out_i
         pic_in.i_type = xref_forced_types ? xref_forced_types[i] : X264_TYPE_AUTO;
         int sz = x264_encoder_encode( h, &nal, &i_nal, &pic_in, &pic_out );
         if( sz < 0 ) { free( chroma ); return -1; }
-        if( sz > 0 ) { XREF_CAPTURE_QP(); out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
+        if( sz > 0 ) { XREF_CAPTURE_QP(); capture_rc( h, n_out ); out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
     }
     while( x264_encoder_delayed_frames( h ) > 0 )
     {
         int sz = x264_encoder_encode( h, &nal, &i_nal, NULL, &pic_out );
         if( sz < 0 ) { free( chroma ); return -1; }
-        if( sz > 0 ) { XREF_CAPTURE_QP(); out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
+        if( sz > 0 ) { XREF_CAPTURE_QP(); capture_rc( h, n_out ); out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; n_out++; }
     }
     free( chroma );
     return n_out;

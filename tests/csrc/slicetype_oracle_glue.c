@@ -117,6 +117,20 @@ int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *out
     return 0;
 }
 
+int x264cu_lookahead_frame_cost_recalculate( x264cu_lookahead_t *la, int slot, int i0, int i1, int b_type, int *score, int32_t *rows )
+{
+    orc_la_frame_t *fr[2*16 + 8] = { 0 };
+    fr[i0] = la->slots[slot];
+    *score = orc_la_frame_cost_recalculate( &la->p, fr, 0, i0 + i1, i0, b_type );
+    if( rows ) memcpy( rows, la->slots[slot]->row_satds[i0][i1], la->p.mb_height * sizeof(int) );
+    return 0;
+}
+int x264cu_lookahead_get_row_satds( x264cu_lookahead_t *la, int slot, int i0, int i1, int32_t *rows )
+{
+    memcpy( rows, la->slots[slot]->row_satds[i0][i1], la->p.mb_height * sizeof(int) );
+    return 0;
+}
+
 /* sharded-stream entries: nothing travels in the CPU harness (every search is computed where it is asked for) */
 size_t x264cu_lookahead_search_bytes( x264cu_lookahead_t *la ) { (void)la; return 8; }
 void *x264cu_lookahead_exchange_stream( x264cu_lookahead_t *la ) { (void)la; return 0; }

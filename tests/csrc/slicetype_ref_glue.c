@@ -94,6 +94,17 @@ int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_fa
     return 0;
 }
 int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *out ) { xref_la_get_mbtree( la->la, slot + 300, 0, 0, out ); return 0; }
+int xref_la_frame_cost_recalculate_at( void *la, int idx, int i0, int i1, int b_type, int *rows );
+int x264cu_lookahead_frame_cost_recalculate( x264cu_lookahead_t *la, int slot, int i0, int i1, int b_type, int *score, int32_t *rows )
+{
+    *score = xref_la_frame_cost_recalculate_at( la->la, slot + 300, i0, i1, b_type, rows );
+    return 0;
+}
+int x264cu_lookahead_get_row_satds( x264cu_lookahead_t *la, int slot, int i0, int i1, int32_t *rows )
+{
+    xref_la_get( la->la, slot + 300, 5, i0, i1, rows );
+    return 0;
+}
 
 /* sharded-stream entries: nothing travels in the CPU harness (every search is computed where it is asked for) */
 size_t x264cu_lookahead_search_bytes( x264cu_lookahead_t *la ) { (void)la; return 8; }

@@ -61,8 +61,11 @@ def test_mbtree_replay_matches_oracle(ctx, cfg):
     slots = list(range(nfr))
     fps_prop, fps_fin, strength = np.float32(0.5 / 256), 512, np.float32(5.0) * (np.float32(1.0) - np.float32(0.6))
 
+    requested = []
+
     def cost(p0, p1, b):
         assert la.frame_cost(slots, p0, p1, b) == o.orc_la_frame_cost(C.byref(p), tab.ctypes.data + 2 * n, ofr, p0, p1, b), (p0, p1, b)
+        requested.append((p0, p1, b))
 
     def reset(i):
         la.mbtree_reset(i)
@@ -103,6 +106,16 @@ def test_mbtree_replay_matches_oracle(ctx, cfg):
                 wd = C.c_float()
                 o.orc_la_frame_get_mbtree(ofr[k], 3, d, C.byref(wd))
                 assert la.get_weighted_cost_delta(k, d) == wd.value, ("weighted_cost_delta", k, d)
+        # slicetype_frame_cost_recalculate (slicetype.c:999-1024) of every requested cost
+        o.orc_la_frame_cost_recalculate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        for p0, p1, b in requested:
+            is_b = int(all_types[b] in (T_B, T_BREF))
+            want = o.orc_la_frame_cost_recalculate(C.byref(p), ofr, p0, p1, b, is_b)
+            rows = np.zeros(p.mb_height, np.int32)
+            o.orc_la_frame_get(ofr[b], 5, b - p0, p1 - b, ptr(rows))
+            got, got_rows = la.frame_cost_recalculate(b, b - p0, p1 - b, is_b)
+            assert got == want and np.array_equal(got_rows, rows), ("recalculate", p0, p1, b, got, want)
+            assert np.array_equal(la.get_row_satds(b, b - p0, p1 - b), rows)
     finally:
         la.close()
         for k in range(nfr):

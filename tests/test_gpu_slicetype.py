@@ -108,3 +108,23 @@ def test_gpu_forced_frame_types(ctx, case):
     finally:
         st.close()
     assert got == want, (case, [z for z in zip(got, want) if z[0] != z[1]][:6])
+
+
+@pytest.mark.parametrize("case", host.RC_CASES)
+def test_gpu_rc_analyse_slice_and_vbv_lookahead(ctx, case):
+    """x264_rc_analyse_slice's cost / row SATDs (slicetype_frame_cost_recalculate with MB-tree) and the VBV lookahead's planned
+    types / costs: what the reference ENCODER's rate control was given, picture by picture"""
+    preset, opts, (w, h), n, cut = case
+    frames = synth_sequence(w, h, n, seed=n + w + 5, cut_at=cut)
+    if not have_ref():
+        pytest.skip("compiled reference did not travel")
+    rc_ref, rc_got = {}, {}
+    p, want = host.reference_types(preset, opts, w, h, frames, rc_out=rc_ref)
+    chroma = [(np.full(((h + 1) // 2, (w + 1) // 2), 128, np.uint8),) * 2] * n if p.la.aq_mode else None
+    st = x.Slicetype.from_params(ctx, p)
+    try:
+        got = st.decide(frames, chroma=chroma, rc_out=rc_got, vbv=bool(p.la.vbv))
+    finally:
+        st.close()
+    analysed, planned = host.rc_compare(want, got, rc_ref, rc_got, p.la.vbv)
+    assert analysed >= 10 and (planned > 20 or not p.la.vbv)

@@ -114,9 +114,11 @@ def test_mbtree_matches_reference(case):
             o.orc_la_frame_set_qscale(ofr[i], q)
             o.orc_la_frame_set_qp_offset_aq(ofr[i], ptr(aq))
         all_types = [T_P] + types
+        requested = []
         def cost(p0, p1, b):
             s1, s2 = r.xref_la_frame_cost(la, p0, p1, b), o.orc_la_frame_cost(C.byref(p), tab.ctypes.data + 2 * n, ofr, p0, p1, b)
             assert s1 == s2, (p0, p1, b)
+            requested.append((p0, p1, b))
         fps_prop = np.float32(dur) / (np.float32(dur) * np.float32(256.0)) * np.float32(0.5)
         fps_fin = int(round(dur / dur * 256 / 0.5))
         strength = np.float32(5.0) * (np.float32(1.0) - np.float32(0.6))
@@ -153,6 +155,20 @@ def test_mbtree_matches_reference(case):
                 assert wa.value == wb.value, ("weighted_cost_delta", k, d, wa.value, wb.value)
         assert checked_nonzero
         assert exact == total, "f_qp_offset bit-exact on %d of %d macroblocks" % (exact, total)
+        # slicetype_frame_cost_recalculate (slicetype.c:999-1024) of every requested cost: MB-tree's offsets for P / I, AQ's for B
+        r.xref_la_frame_cost_recalculate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        o.orc_la_frame_cost_recalculate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        changed = 0
+        for p0, p1, b in requested:
+            before = r.xref_la_frame_cost(la, p0, p1, b)
+            s1 = r.xref_la_frame_cost_recalculate(la, p0, p1, b)
+            s2 = o.orc_la_frame_cost_recalculate(C.byref(p), ofr, p0, p1, b, int(is_b(all_types[b])))
+            assert s1 == s2, ("recalculate", p0, p1, b, s1, s2)
+            ra = np.zeros(p.mb_height, np.int32); rb = np.zeros(p.mb_height, np.int32)
+            r.xref_la_get(la, b, 5, b - p0, p1 - b, ptr(ra)); o.orc_la_frame_get(ofr[b], 5, b - p0, p1 - b, ptr(rb))
+            assert np.array_equal(ra, rb), ("recalculate rows", p0, p1, b)
+            changed += s1 != before
+        assert changed or not p.aq_mode
         for k in range(nfr):
             o.orc_la_frame_delete(ofr[k])
         r.xref_la_free(la)

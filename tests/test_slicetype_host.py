@@ -47,7 +47,7 @@ def params_from_ref(hnd, w, h):
     return p
 
 
-def decide_with(lib, p, frames, qp_out=None, chroma=None, forced=None):
+def decide_with(lib, p, frames, qp_out=None, chroma=None, forced=None, rc_out=None):
     """qp_out: dict filled with frame -> f_qp_offset (MB-tree's output) for every non-B picture, read when it is returned;
     chroma: (cb, cr) planes fed with every picture through x264cu_slicetype_step_i420 (adaptive quantisation inside)"""
     lib.x264cu_slicetype_open.argtypes = [C.c_void_p, C.POINTER(SlicetypeParams), C.POINTER(C.c_void_p)]
@@ -60,8 +60,21 @@ def decide_with(lib, p, frames, qp_out=None, chroma=None, forced=None):
     lib.x264cu_slicetype_get_qp_offset.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     nmb = ((p.la.width + 15) // 16) * ((p.la.height + 15) // 16)
 
+    mbh = (p.la.height + 15) // 16
+    lib.x264cu_slicetype_rc_analyse_slice.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+    lib.x264cu_slicetype_get_planned.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+
     def note():
         out.append((fr.value, ty.value))
+        if rc_out is not None:
+            # x264_rc_analyse_slice of the picture just returned: (cost, rows, planned types, planned costs)
+            cost, rows = C.c_int(-1), np.zeros(mbh, np.int32)
+            if ty.value not in (4, 5) or p.la.vbv:
+                assert lib.x264cu_slicetype_rc_analyse_slice(st, fr.value, C.byref(cost), rows.ctypes.data, None) == 0
+            pt, ps = np.zeros(32, np.int32), np.zeros(32, np.int32)
+            k = lib.x264cu_slicetype_get_planned(st, fr.value, pt.ctypes.data, ps.ctypes.data, 32) if p.la.vbv and p.rc_lookahead and ty.value not in (4, 5) else 0
+            assert k >= 0
+            rc_out[fr.value] = (cost.value, rows, list(pt[:k]), list(ps[:k]))
         if qp_out is not None and ty.value not in (4, 5):
             q = np.zeros(nmb, np.float32)
             assert lib.x264cu_slicetype_get_qp_offset(st, fr.value, q.ctypes.data) == 0
@@ -88,7 +101,7 @@ def decide_with(lib, p, frames, qp_out=None, chroma=None, forced=None):
     return out
 
 
-def reference_types(preset, opts, w, h, frames, qp_out=None, forced=None):
+def reference_types(preset, opts, w, h, frames, qp_out=None, forced=None, rc_out=None):
     """qp_out: dict filled with frame -> the f_qp_offset array the reference encoder used for it"""
     r = ref()
     r.xref_encode_types.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -104,13 +117,24 @@ def reference_types(preset, opts, w, h, frames, qp_out=None, forced=None):
         nmb = ((w + 15) // 16) * ((h + 15) // 16)
         cap = np.zeros((n + 8, nmb), np.float32)
         r.xref_set_qp_capture(cap.ctypes.data if qp_out is not None else None)
+        mbh = (h + 15) // 16
+        stride = 2 + mbh + 64
+        rc_cap = np.zeros((n + 8, stride), np.int32)
+        r.xref_set_rc_capture.argtypes = [C.c_void_p, C.c_int]
+        r.xref_set_rc_capture(rc_cap.ctypes.data if rc_out is not None else None, stride)
         r.xref_set_forced_types.argtypes = [C.c_void_p]
         ft = (C.c_int * n)(*[int(t) for t in forced]) if forced is not None else None
         r.xref_set_forced_types(ft)
         k = r.xref_encode_types(hnd, luma.ctypes.data, n, idx, typ)
         r.xref_set_forced_types(None)
         r.xref_set_qp_capture(None)
+        r.xref_set_rc_capture(None, 0)
         assert k == n
+        if rc_out is not None:
+            for i in range(k):
+                c = rc_cap[i]
+                np_ = int(c[1 + mbh])
+                rc_out[idx[i]] = (int(c[0]), c[1:1 + mbh].copy(), list(c[2 + mbh:2 + mbh + np_]), list(c[2 + mbh + 32:2 + mbh + 32 + np_]))
         if qp_out is not None:
             for i in range(k):
                 qp_out[idx[i]] = cap[i].copy()
@@ -214,3 +238,46 @@ def test_forced_frame_types_match_reference_encoder(case):
     got = decide_with(slicetype_oracle_lib(), p, frames, forced=forced)
     assert got == want, (case, [x for x in zip(got, want) if x[0] != x[1]][:6])
     assert all(dict(want)[i] in ((1, 2) if t == 6 else (t,)) for i, t in forced_at.items() if t in (1, 6)), "forced keyframes were honoured"
+
+
+# x264_rc_analyse_slice (slicetype.c:1976-2030) and the VBV lookahead (vbv_lookahead, slicetype.c:1225-1286): the cost and row
+# SATDs the reference ENCODER's rate control was given for every picture it called it for, and the planned types / costs it left
+# with every non-B picture, against the product's host logic.  With a VBV the B pictures are analysed too, the delay follows
+# rc-lookahead, the whole lookahead is analysed every time and MB-tree finishes every referenced picture.
+RC_CASES = [
+    ("medium", "weightp=0:no-psy=1:bframes=3:rc-lookahead=10:keyint=30:min-keyint=3", (112, 80), 44, 17),                       # ABR/CRF, no VBV
+    ("medium", "weightp=0:no-psy=1:no-mbtree=1:aq-mode=0:bframes=2:rc-lookahead=8", (96, 64), 40, 21),                        # plain cost
+    ("medium", "weightp=0:no-psy=1:bframes=3:rc-lookahead=10:keyint=30:vbv-maxrate=400:vbv-bufsize=300", (112, 80), 44, 17),   # VBV + MB-tree
+    ("medium", "weightp=0:no-psy=1:no-mbtree=1:bframes=3:b-adapt=2:rc-lookahead=12:vbv-maxrate=400:vbv-bufsize=300", (96, 64), 40, 23),
+    ("medium", "bframes=3:rc-lookahead=12:keyint=40:vbv-maxrate=500:vbv-bufsize=400", (112, 80), 44, 19),                       # the default path + VBV
+    ("medium", "weightp=0:no-psy=1:bframes=0:rc-lookahead=6:vbv-maxrate=300:vbv-bufsize=200", (64, 64), 30, 11),
+]
+
+
+def rc_compare(want, got, rc_ref, rc_got, vbv):
+    assert got == want, [x for x in zip(got, want) if x[0] != x[1]][:6]
+    analysed = planned = 0
+    for fr, ty in want:
+        a, b = rc_ref[fr], rc_got[fr]
+        if a[0] >= 0:
+            assert a[0] == b[0], ("cost", fr, ty, a[0], b[0])
+            analysed += 1
+            if vbv:
+                assert np.array_equal(a[1], b[1]), ("row satds", fr, ty)
+        if vbv and ty not in (4, 5):
+            assert a[2] == b[2] and a[3] == b[3], ("planned", fr, ty, a[2], b[2], a[3], b[3])
+            planned += len(a[2])
+    return analysed, planned
+
+
+@pytest.mark.parametrize("case", RC_CASES)
+def test_rc_analyse_slice_and_vbv_lookahead_match_reference_encoder(case):
+    preset, opts, (w, h), n, cut = case
+    frames = synth_sequence(w, h, n, seed=n + w + 5, cut_at=cut)
+    rc_ref, rc_got = {}, {}
+    p, want = reference_types(preset, opts, w, h, frames, rc_out=rc_ref)
+    # with adaptive quantisation on the pictures go in as I420 (chroma 128, as the reference harness feeds it): AQ runs inside
+    chroma = (np.full(((h + 1) // 2, (w + 1) // 2), 128, np.uint8),) * 2 if p.la.aq_mode else None
+    got = decide_with(slicetype_oracle_lib(), p, frames, rc_out=rc_got, chroma=chroma)
+    analysed, planned = rc_compare(want, got, rc_ref, rc_got, p.la.vbv)
+    assert analysed >= 10 and (planned > 20 or not p.la.vbv)

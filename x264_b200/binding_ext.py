@@ -58,6 +58,8 @@ def bind(L):
     L.x264cu_slicetype_get_qp_offset.argtypes = [vp, ci, vp]
     L.x264cu_slicetype_set_shard.argtypes = [vp, ci, ci, vp, vp]
     L.x264cu_slicetype_set_next_type.argtypes = [vp, ci]
+    L.x264cu_slicetype_rc_analyse_slice.argtypes = [vp, ci, vp, vp, vp]
+    L.x264cu_slicetype_get_planned.argtypes = [vp, ci, vp, vp, ci]
     L.x264cu_slicetype_step_i420.argtypes = [vp, vp, ss, vp, vp, ss, C.POINTER(ci), C.POINTER(ci)]
     L.x264cu_slicetype_lookahead.argtypes = [vp]
     L.x264cu_slicetype_lookahead.restype = vp
@@ -67,6 +69,7 @@ def bind(L):
     L.x264cu_lookahead_mbtree_swap.argtypes = [vp, ci, ci]
     L.x264cu_lookahead_mbtree_propagate.argtypes = [vp, C.POINTER(ci), ci, ci, ci, ci, C.c_float]
     L.x264cu_lookahead_mbtree_finish.argtypes = [vp, ci, ci, ci, C.c_float]
+    L.x264cu_lookahead_frame_cost_recalculate.argtypes = [vp, ci, ci, ci, ci, vp, vp]
     L.x264cu_lookahead_get_qp_offset.argtypes = [vp, ci, vp]
     L.x264cu_lookahead_get_propagate_cost.argtypes = [vp, ci, vp]
     L.x264cu_lookahead_get_weighted_cost_delta.argtypes = [vp, ci, ci]
@@ -187,6 +190,13 @@ class Lookahead:
     def mbtree_finish(self, slot, fps_factor, ref0_distance, strength):
         self.ctx.check(self.L.x264cu_lookahead_mbtree_finish(self.h, slot, int(fps_factor), int(ref0_distance), float(strength)))
 
+    def frame_cost_recalculate(self, slot, dist0, dist1, b_type):
+        """slicetype_frame_cost_recalculate -> (cost, row satds)"""
+        score = C.c_int()
+        rows = np.zeros(self.mb_h, np.int32)
+        self.ctx.check(self.L.x264cu_lookahead_frame_cost_recalculate(self.h, slot, dist0, dist1, int(b_type), C.addressof(score), rows.ctypes.data))
+        return score.value, rows
+
     def get_qp_offset(self, slot):
         out = np.zeros(self.mb_count, np.float32)
         self.ctx.check(self.L.x264cu_lookahead_get_qp_offset(self.h, slot, out.ctypes.data))
@@ -234,6 +244,7 @@ class Slicetype:
             raise X264CUError("x264cu_slicetype_open failed: " + ctx.L.x264cu_strerror(ctx.h).decode())
         self.h = h
         self.mb_count = ((width + 15) // 16) * ((height + 15) // 16)
+        self.mb_h = (height + 15) // 16
 
     @classmethod
     def from_params(cls, ctx, p):
@@ -307,13 +318,32 @@ class Slicetype:
     def set_next_type(self, t):
         self.ctx.check(self.L.x264cu_slicetype_set_next_type(self.h, int(t)))
 
-    def decide(self, frames, qp_out=None, chroma=None, forced=None):
+    def rc_analyse_slice(self, frame):
+        """x264_rc_analyse_slice of the picture step() just returned -> (cost, row satds)"""
+        cost = C.c_int()
+        rows = np.zeros(self.mb_h, np.int32)
+        self.ctx.check(self.L.x264cu_slicetype_rc_analyse_slice(self.h, int(frame), C.addressof(cost), rows.ctypes.data, None))
+        return cost.value, rows
+
+    def get_planned(self, frame, max_entries=32):
+        """i_planned_type / i_planned_satd (VBV lookahead) of a non-B picture step() just returned"""
+        t, sd = np.zeros(max_entries, np.int32), np.zeros(max_entries, np.int32)
+        k = self.L.x264cu_slicetype_get_planned(self.h, int(frame), t.ctypes.data, sd.ctypes.data, max_entries)
+        if k < 0:
+            raise RuntimeError("x264cu_slicetype_get_planned failed")
+        return list(t[:k]), list(sd[:k])
+
+    def decide(self, frames, qp_out=None, chroma=None, forced=None, rc_out=None, vbv=False):
         """qp_out: dict filled with frame -> f_qp_offset for every non-B picture; chroma: [(cb, cr)] per picture -> step_i420;
         forced: pic_in.i_type per picture (0 = auto)"""
         out = []
 
         def note(fr, ty):
             out.append((fr, ty))
+            if rc_out is not None:      # (cost, rows, planned types, planned costs) as tests/test_slicetype_host.py collects them
+                cost, rows = (-1, np.zeros(self.mb_h, np.int32)) if ty in (4, 5) and not vbv else self.rc_analyse_slice(fr)
+                pt, ps = self.get_planned(fr) if vbv and ty not in (4, 5) else ([], [])
+                rc_out[fr] = (cost, rows, pt, ps)
             if qp_out is not None and ty not in (4, 5):
                 qp_out[fr] = self.get_qp_offset(fr)
 

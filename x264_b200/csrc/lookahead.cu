@@ -782,6 +782,40 @@ mbtree_finish_kernel( int mb_count, const int32_t *__restrict__ intra, const uin
     qp[mb] = __fsub_rn( qp_aq[mb], __fmul_rn( strength, ratio ) );
 }
 
+// slicetype_frame_cost_recalculate, slicetype.c:999-1024: one CTA per macroblock row; integer sums (order-free)
+__constant__ uint8_t c_exp2_lut[64];         // x264_exp2_lut, common/tables.c:58-64
+
+__global__ void __launch_bounds__( 128 )
+recalculate_kernel( int mb_w, int mb_h, const uint16_t *__restrict__ costs, const int32_t *__restrict__ intra, const float *__restrict__ qp_offset,
+                    int32_t *__restrict__ row_satd, int *__restrict__ score )
+{
+    __shared__ int s_row[4], s_in[4];
+    const int y = blockIdx.x;
+    const bool all = mb_w <= 2 || mb_h <= 2, row_in = y > 0 && y < mb_h - 1;
+    int row = 0, in = 0;
+    for( int x = threadIdx.x; x < mb_w; x += blockDim.x )
+    {
+        const int mb = x + y * mb_w;
+        // x264_exp2fix8 (base.h:218-224): the product and the sum are rounded separately, as the reference's build does
+        const int i = __float2int_rz( __fadd_rn( __fmul_rn( qp_offset[mb], -64.f / 6.f ), 512.5f ) );
+        const int q = i < 0 ? 0 : i > 1023 ? 0xffff : (int)( ( ( (unsigned)c_exp2_lut[i & 63] + 256u ) << ( i >> 6 ) ) >> 8 );
+        // lowres_costs[0][0] IS i_intra_cost (a u16 array) in the reference (frame.c:287): the intra request reads that one
+        const int lc = intra ? ( intra[mb] & 0xffff ) : costs[mb];
+        const int cost = ( ( lc & 0x3fff ) * q + 128 ) >> 8;
+        row += cost;
+        if( all || ( row_in && x > 0 && x < mb_w - 1 ) ) in += cost;
+    }
+#pragma unroll
+    for( int m = 16; m; m >>= 1 ) { row += __shfl_xor_sync( 0xffffffffu, row, m ); in += __shfl_xor_sync( 0xffffffffu, in, m ); }
+    if( !( threadIdx.x & 31 ) ) { s_row[threadIdx.x >> 5] = row; s_in[threadIdx.x >> 5] = in; }
+    __syncthreads();
+    if( !threadIdx.x )
+    {
+        row_satd[y] = s_row[0] + s_row[1] + s_row[2] + s_row[3];
+        atomicAdd( score, s_in[0] + s_in[1] + s_in[2] + s_in[3] );
+    }
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -1078,6 +1112,16 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
         if( cudaMemcpyToSymbol( c_log2_lut, lut, sizeof( lut ) ) != cudaSuccess )
         {
             x264cu_fail( ctx, "lookahead_open: log2 table upload failed" );
+            x264cu_lookahead_close( la );
+            return -1;
+        }
+    }
+    {   // x264_exp2_lut (common/tables.c:58-64): round( 256 * (2^(i/64) - 1) )
+        uint8_t e2[64];
+        for( int i = 0; i < 64; i++ ) e2[i] = (uint8_t)( 256.0 * ( pow( 2.0, i / 64.0 ) - 1.0 ) + 0.5 );
+        if( cudaMemcpyToSymbol( c_exp2_lut, e2, sizeof( e2 ) ) != cudaSuccess )
+        {
+            x264cu_fail( ctx, "lookahead_open: exp2 table upload failed" );
             x264cu_lookahead_close( la );
             return -1;
         }
@@ -1656,6 +1700,33 @@ int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_fa
                                                                                   f.dev.qp_offset_aq, f.dev.qp_offset, fps_factor, weightdelta, strength );
     CU_LAUNCH_CHECK( ctx );
     return la_mt_end( la, { slot } );
+}
+
+int x264cu_lookahead_frame_cost_recalculate( x264cu_lookahead_t *la, int slot, int dist0, int dist1, int b_type, int *h_score, int32_t *h_row_satd )
+{
+    if( !la || !h_score ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    const LaDims &d = la->d;
+    if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use ) return x264cu_fail( ctx, "frame_cost_recalculate: empty slot %d", slot );
+    if( dist0 < 0 || dist1 < 0 || dist0 > d.B + 1 || dist1 > d.B + 1 ) return x264cu_fail( ctx, "frame_cost_recalculate: bad distances" );
+    LaSlotHost &f = la->slots[slot];
+    if( f.cost_est[dist0][dist1] < 0 )
+        return x264cu_fail( ctx, "frame_cost_recalculate: the cost (%d,%d) of slot %d has not been requested", dist0, dist1, slot );
+    if( la_slot_ready( la, slot ) || la_mt_begin( la ) ) return -1;
+    int *d_score = (int *)x264cu_scratch( ctx, 10, 64 );
+    if( !d_score ) return -1;
+    int32_t *rows = f.dev.row_satds + (size_t)( dist0 * ( d.B + 2 ) + dist1 ) * d.mb_h;
+    CU_CHECK( ctx, cudaMemsetAsync( d_score, 0, sizeof(int), la->mt_stream ) );
+    recalculate_kernel<<<d.mb_h, 128, 0, la->mt_stream>>>( d.mb_w, d.mb_h, f.dev.costs + (size_t)( dist0 * ( d.B + 2 ) + dist1 ) * d.mb_count,
+                                                          !dist0 && !dist1 ? f.dev.intra : nullptr, b_type ? f.dev.qp_offset_aq : f.dev.qp_offset, rows, d_score );
+    CU_LAUNCH_CHECK( ctx );
+    f.row_satds_valid[dist0][dist1] = true;
+    CU_CHECK( ctx, cudaMemcpyAsync( h_score, d_score, sizeof(int), cudaMemcpyDeviceToHost, la->mt_stream ) );
+    if( h_row_satd )
+        CU_CHECK( ctx, cudaMemcpyAsync( h_row_satd, rows, (size_t)d.mb_h * 4, cudaMemcpyDeviceToHost, la->mt_stream ) );
+    if( la_mt_end( la, { slot } ) ) return -1;
+    CU_CHECK( ctx, cudaStreamSynchronize( la->mt_stream ) );
+    return 0;
 }
 
 int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *h_qp_offset )

@@ -37,6 +37,9 @@ typedef struct
     int i_type, i_forced_type;
     int b_scenecut;       /* frame.c:792 */
     int i_bframes;
+    int rc_d0, rc_d1;     /* (b-p0, p1-b) of the cost x264_rc_analyse_slice reads for this picture (slicetype.c:1896-1935, :1985-1996) */
+    int n_planned;        /* VBV lookahead (slicetype.c:1225-1286): i_planned_type / i_planned_satd of the coming pictures */
+    int planned_type[LOOKAHEAD_MAX + 1], planned_satd[LOOKAHEAD_MAX + 1];
 } st_frame_t;
 
 struct x264cu_slicetype
@@ -73,6 +76,8 @@ struct x264cu_slicetype
     void *shard_user;
     int xj_slot[256], xj_list[256], xj_dist[256], xj_owner[256], xj_frame[256], n_xj;
     int next_forced_type;                 /* pic_in->i_type of the next queued picture (x264cu_slicetype_set_next_type) */
+    st_frame_t *handed;                   /* the picture the last step returned: kept (slot included) until the next step */
+    int vbv_lookahead;                    /* h->param.rc.i_vbv_buffer_size && h->param.rc.i_lookahead */
 };
 
 int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame );
@@ -106,6 +111,61 @@ static void cost_est( x264cu_slicetype_t *s, st_frame_t *f, int i0, int i1, int 
     if( x264cu_lookahead_get_cost_est( s->la, f->slot, i0, i1, &a, &aq, &m ) ) s->failed = 1;
     if( ce ) *ce = a;
     if( imb ) *imb = m;
+}
+
+/* slicetype_frame_cost_recalculate, slicetype.c:999-1024 */
+static int frame_cost_recalculate( x264cu_slicetype_t *s, st_frame_t *f, int i0, int i1, int *rows )
+{
+    int score = 0;
+    if( x264cu_lookahead_frame_cost_recalculate( s->la, f->slot, i0, i1, IS_B( f->i_type ), &score, rows ) ) s->failed = 1;
+    return score;
+}
+
+/* vbv_frame_cost, slicetype.c:1186-1197 */
+static int vbv_frame_cost( x264cu_slicetype_t *s, st_frame_t **frames, int p0, int p1, int b )
+{
+    int cost = frame_cost( s, frames, p0, p1, b );
+    if( s->p.la.aq_mode )
+    {
+        if( s->p.la.mb_tree )
+            return frame_cost_recalculate( s, frames[b], b - p0, p1 - b, NULL );
+        int a = 0, aq = 0, m = 0;
+        if( x264cu_lookahead_get_cost_est( s->la, frames[b]->slot, b - p0, p1 - b, &a, &aq, &m ) ) s->failed = 1;
+        return aq;
+    }
+    return cost;
+}
+
+/* vbv_lookahead, slicetype.c:1225-1286: the planned types and costs of the pictures after the next non-B one, in coded order,
+ * left with that picture for the rate control (constant frame rate: the cpb durations of the reference are not produced) */
+static void vbv_lookahead( x264cu_slicetype_t *s, st_frame_t **frames, int num_frames, int keyframe )
+{
+    int last_nonb = 0, cur_nonb = 1, idx = 0;
+    while( cur_nonb < num_frames && IS_B( frames[cur_nonb]->i_type ) )
+        cur_nonb++;
+    st_frame_t *dst = frames[keyframe ? last_nonb : cur_nonb];
+    const int skip = keyframe ? -1 : cur_nonb;               /* the cost of the picture holding the plan is not part of it */
+    while( cur_nonb < num_frames )
+    {
+        if( cur_nonb != skip )
+        {
+            int p0 = IS_I( frames[cur_nonb]->i_type ) ? cur_nonb : last_nonb;
+            dst->planned_satd[idx] = vbv_frame_cost( s, frames, p0, cur_nonb, cur_nonb );
+            dst->planned_type[idx] = frames[cur_nonb]->i_type;
+            idx++;
+        }
+        for( int i = last_nonb + 1; i < cur_nonb; i++, idx++ )   /* the B pictures, coded after their non-B */
+        {
+            dst->planned_satd[idx] = vbv_frame_cost( s, frames, last_nonb, cur_nonb, i );
+            dst->planned_type[idx] = T_B;
+        }
+        last_nonb = cur_nonb;
+        cur_nonb++;
+        while( cur_nonb <= num_frames && IS_B( frames[cur_nonb]->i_type ) )
+            cur_nonb++;
+    }
+    dst->planned_type[idx] = T_AUTO;
+    dst->n_planned = idx;
 }
 
 /* slicetype.c:1288-1330 */
@@ -242,6 +302,8 @@ static void mbtree_reset( x264cu_slicetype_t *s, st_frame_t *f )
     if( x264cu_lookahead_mbtree_reset( s->la, f->slot ) ) s->failed = 1;
 }
 
+static void mbtree_finish( x264cu_slicetype_t *s, st_frame_t *f, float average_duration, int ref0_distance );
+
 /* macroblock_tree_propagate, slicetype.c:1050-1089 (constant frame rate: every picture lasts s->duration) */
 static void mbtree_propagate( x264cu_slicetype_t *s, st_frame_t **frames, float average_duration, int p0, int p1, int b, int referenced )
 {
@@ -249,6 +311,8 @@ static void mbtree_propagate( x264cu_slicetype_t *s, st_frame_t **frames, float 
     for( int i = p0; i <= p1; i++ ) slots[i] = frames[i]->slot;
     float fps_factor = clip_duration( s->duration ) / ( clip_duration( average_duration ) * 256.0f ) * MBTREE_PRECISION;
     if( x264cu_lookahead_mbtree_propagate( s->la, slots, p0, p1, b, referenced, fps_factor ) ) s->failed = 1;
+    if( s->vbv_lookahead && referenced )                      /* slicetype.c:1087-1088 */
+        mbtree_finish( s, frames[b], average_duration, b == p1 ? b - p0 : 0 );
 }
 
 /* macroblock_tree_finish, slicetype.c:1029-1048 */
@@ -338,7 +402,7 @@ static void macroblock_tree( x264cu_slicetype_t *s, st_frame_t **frames, int num
         if( x264cu_lookahead_mbtree_swap( s->la, frames[last_nonb]->slot, frames[0]->slot ) ) s->failed = 1;
     }
     mbtree_finish( s, frames[last_nonb], average_duration, last_nonb );
-    if( s->p.b_pyramid && bframes > 1 )          /* vbv lookahead is not part of this backend (rejected at open) */
+    if( s->p.b_pyramid && bframes > 1 && !s->p.la.vbv )
         mbtree_finish( s, frames[last_nonb + ( bframes + 1 ) / 2], average_duration, 0 );
 }
 
@@ -366,7 +430,7 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
     }
     keyint_limit = s->p.keyint_max - frames[0]->i_frame + s->i_last_keyframe - 1;
     orig_num_frames = num_frames = s->p.intra_refresh ? framecnt : framecnt < keyint_limit ? framecnt : keyint_limit;
-    if( s->p.psy && s->p.la.mb_tree )
+    if( ( s->p.psy && s->p.la.mb_tree ) || s->vbv_lookahead )
         num_frames = framecnt;
     else if( s->p.open_gop && num_frames < framecnt )
         num_frames++;
@@ -536,6 +600,8 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
             }
         }
     }
+    if( s->vbv_lookahead )
+        vbv_lookahead( s, frames, num_frames, keyframe );
     /* Restore frametypes for all frames that haven't actually been decided yet. */
     for( int j = reset_start; j <= num_frames; j++ )
         frames[j]->i_type = frames[j]->i_forced_type;
@@ -549,7 +615,7 @@ static int slicetype_decide( x264cu_slicetype_t *s )
     int bframes, brefs;
     if( !s->n_next )
         return 0;
-    if( ( s->p.la.bframes && s->p.b_adapt ) || s->p.scenecut_threshold || s->p.la.mb_tree )
+    if( ( s->p.la.bframes && s->p.b_adapt ) || s->p.scenecut_threshold || s->p.la.mb_tree || s->vbv_lookahead )
         slicetype_analyse( s, 0 );
 
     for( bframes = 0, brefs = 0;; bframes++ )
@@ -614,6 +680,24 @@ static int slicetype_decide( x264cu_slicetype_t *s )
         memcpy( &frames[1], s->next, ( bframes + 1 ) * sizeof( st_frame_t * ) );
         p0 = IS_I( s->next[bframes]->i_type ) ? bframes + 1 : 0;
         frame_cost( s, frames, p0, p1, b );
+        frames[b]->rc_d0 = b - p0; frames[b]->rc_d1 = 0;
+        if( ( p0 != p1 || bframes ) && s->p.la.vbv )
+        {   /* the intra costs and the B pictures' costs for the row SATDs, slicetype.c:1916-1934 */
+            frame_cost( s, frames, b, b, b );
+            p0 = 0;
+            for( b = 1; b <= bframes; b++ )
+            {
+                if( frames[b]->i_type == T_B )
+                    for( p1 = b; frames[p1]->i_type == T_B; )
+                        p1++;
+                else
+                    p1 = bframes + 1;
+                frame_cost( s, frames, p0, p1, b );
+                frames[b]->rc_d0 = b - p0; frames[b]->rc_d1 = p1 - b;
+                if( frames[b]->i_type == T_BREF )
+                    p0 = b;
+            }
+        }
     }
     /* shift sequence to coded order */
     if( bframes )
@@ -675,7 +759,7 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
 {
     if( !ctx || !p || !out ) return -1;
     *out = NULL;
-    if( p->la.vbv || p->keyint_max < 1 || p->keyint_min < 1 || p->b_adapt < 0 || p->b_adapt > 2 || p->b_pyramid < 0 || p->b_pyramid > 2 )
+    if( ( p->la.vbv && p->intra_refresh ) || p->keyint_max < 1 || p->keyint_min < 1 || p->b_adapt < 0 || p->b_adapt > 2 || p->b_pyramid < 0 || p->b_pyramid > 2 )
         return -1;
     x264cu_slicetype_t *s = calloc( 1, sizeof( *s ) );
     if( !s ) return -1;
@@ -683,10 +767,11 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
     s->p = *p;
     /* encoder.c:1602-1609 */
     s->delay = p->b_adapt == 2 ? ( p->la.bframes > 3 ? p->la.bframes : 3 ) * 4 : p->la.bframes;
-    if( p->la.mb_tree && p->rc_lookahead > s->delay )
+    if( ( p->la.mb_tree || p->la.vbv ) && p->rc_lookahead > s->delay )
         s->delay = p->rc_lookahead;
     s->slicetype_length = s->delay;
-    s->b_analyse_keyframe = p->la.mb_tree != 0;
+    s->vbv_lookahead = p->la.vbv && p->rc_lookahead;
+    s->b_analyse_keyframe = p->la.mb_tree || s->vbv_lookahead;      /* lookahead.c:140 */
     s->i_last_keyframe = -p->keyint_max;
     s->n_slots = s->delay + p->la.bframes + 8 + ST_RUN_AHEAD_MAX;
     s->slot_used = calloc( s->n_slots, 1 );
@@ -724,6 +809,7 @@ void x264cu_slicetype_close( x264cu_slicetype_t *s )
     if( !s ) return;
     for( int i = 0; i < s->n_next; i++ ) free( s->next[i] );
     for( int i = 0; i < s->n_current; i++ ) if( s->current[i] != s->last_nonb ) free( s->current[i] );
+    if( s->handed && s->handed != s->last_nonb ) free( s->handed );
     free( s->last_nonb );
     if( getenv( "X264CU_STATS" ) )
         fprintf( stderr, "x264cu slicetype host time: step %.1f ms = frame_put %.1f + search_batch %.1f + frame_cost %.1f (%ld calls) + logic %.1f\n",
@@ -823,6 +909,11 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
 {
     if( !s || !out_frame || !out_type ) return -1;
     *out_frame = -1; *out_type = T_AUTO;
+    if( s->handed )
+    {   /* the picture returned by the previous call leaves now (its slot with it), unless it is still the last non-B one */
+        if( s->handed != s->last_nonb ) release_frame( s, s->handed );
+        s->handed = NULL;
+    }
     if( luma )
     {
         int slot = -1;
@@ -890,8 +981,7 @@ static int step_common( x264cu_slicetype_t *s, const uint8_t *luma, int on_devic
     s->n_current--;
     *out_frame = f->i_frame;
     *out_type = f->i_type;
-    if( f != s->last_nonb )
-        release_frame( s, f );
+    s->handed = f;
     return 0;
 }
 
@@ -952,6 +1042,7 @@ int x264cu_slicetype_slot_of( x264cu_slicetype_t *s, int frame )
 {
     if( !s ) return -1;
     if( s->last_nonb && s->last_nonb->i_frame == frame ) return s->last_nonb->slot;
+    if( s->handed && s->handed->i_frame == frame ) return s->handed->slot;
     for( int i = 0; i < s->n_next; i++ ) if( s->next[i]->i_frame == frame ) return s->next[i]->slot;
     for( int i = 0; i < s->n_current; i++ ) if( s->current[i]->i_frame == frame ) return s->current[i]->slot;
     return -1;
@@ -963,6 +1054,58 @@ int x264cu_slicetype_get_qp_offset( x264cu_slicetype_t *s, int frame, float *h_q
     int slot = x264cu_slicetype_slot_of( s, frame );
     if( slot < 0 ) return -1;
     return x264cu_lookahead_get_qp_offset( s->la, slot, h_qp_offset );
+}
+
+static st_frame_t *find_held( x264cu_slicetype_t *s, int frame )
+{
+    if( s->handed && s->handed->i_frame == frame ) return s->handed;
+    if( s->last_nonb && s->last_nonb->i_frame == frame ) return s->last_nonb;
+    for( int i = 0; i < s->n_current; i++ ) if( s->current[i]->i_frame == frame ) return s->current[i];
+    return NULL;
+}
+
+/* x264_rc_analyse_slice, slicetype.c:1976-2030, for a picture the last x264cu_slicetype_step returned */
+int x264cu_slicetype_rc_analyse_slice( x264cu_slicetype_t *s, int frame, int *cost_out, int *h_row_satd, int *h_row_satd_intra )
+{
+    if( !s || !cost_out || s->p.rc_cqp ) return -1;
+    st_frame_t *f = find_held( s, frame );
+    if( !f ) return -1;
+    if( IS_B( f->i_type ) && !s->p.la.vbv ) return -1;      /* their costs are requested only for the VBV row SATDs (slicetype.c:1916) */
+    const int i0 = IS_I( f->i_type ) ? 0 : f->rc_d0, i1 = IS_I( f->i_type ) ? 0 : f->rc_d1;
+    int cost = 0, aq = 0, m = 0;
+    if( x264cu_lookahead_get_cost_est( s->la, f->slot, i0, i1, &cost, &aq, &m ) || cost < 0 ) return -1;
+    if( s->p.la.mb_tree )
+    {
+        cost = frame_cost_recalculate( s, f, i0, i1, h_row_satd );
+        if( !IS_I( f->i_type ) && s->p.la.vbv )
+        {   /* slicetype_frame_cost_recalculate( h, frames, b, b, b ): the intra rows with the same offsets */
+            int t = 0;
+            if( x264cu_lookahead_frame_cost_recalculate( s->la, f->slot, 0, 0, IS_B( f->i_type ), &t, NULL ) ) s->failed = 1;
+        }
+    }
+    else
+    {
+        if( s->p.la.aq_mode ) cost = aq;
+        if( h_row_satd && x264cu_lookahead_get_row_satds( s->la, f->slot, i0, i1, h_row_satd ) ) s->failed = 1;
+    }
+    if( h_row_satd_intra && !IS_I( f->i_type ) && x264cu_lookahead_get_row_satds( s->la, f->slot, 0, 0, h_row_satd_intra ) ) s->failed = 1;
+    *cost_out = cost;
+    return s->failed ? -1 : 0;
+}
+
+/* i_planned_type / i_planned_satd of a non-B picture the last step returned (VBV lookahead); returns the number of entries */
+int x264cu_slicetype_get_planned( x264cu_slicetype_t *s, int frame, int *h_type, int *h_satd, int max_entries )
+{
+    if( !s || !s->vbv_lookahead ) return -1;
+    st_frame_t *f = find_held( s, frame );
+    if( !f ) return -1;
+    int n = f->n_planned < max_entries ? f->n_planned : max_entries;
+    for( int i = 0; i < n; i++ )
+    {
+        if( h_type ) h_type[i] = f->planned_type[i];
+        if( h_satd ) h_satd[i] = f->planned_satd[i];
+    }
+    return n;
 }
 
 long x264cu_slicetype_cost_requests( x264cu_slicetype_t *s ) { return s ? s->requests : 0; }
