@@ -29,6 +29,7 @@ struct x264cu_ctx
     struct x264cu_lookahead *lookahead = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaStream_t> aux_streams;   // streams of live lookahead objects: x264cu_sync waits for them too
+    std::vector<const void *> smem_attr_done; // kernels whose dynamic shared-memory limit has been raised on THIS context's device
 };
 
 int  x264cu_fail( x264cu_ctx *ctx, const char *fmt, ... );

@@ -455,11 +455,13 @@ static int launch_mvfield( x264cu_ctx *ctx, const x264cu_planes_t *fenc, const x
     p.ref_origin = ref->d_origin; p.ref_stride = ref->stride; p.ref_plane_pitch = ref->plane_pitch;
     auto kern = mvfield_kernel<METRIC, BW, BH, TW, TH, R, NSTAGE, NWARPS>;
     size_t smem = NSTAGE * T::STAGE_BYTES + 128 + 64 + NSTAGE * 8 + 64;
-    static bool attr_set = false;
+    // the attribute is per device: remembered per context (one context = one device), not per process
+    bool attr_set = false;
+    for( const void *k : ctx->smem_attr_done ) attr_set |= k == (const void *)kern;
     if( !attr_set )
     {
         CU_CHECK( ctx, cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
-        attr_set = true;
+        ctx->smem_attr_done.push_back( (const void *)kern );
     }
     int ctas_per_sm = (int)( ( 227 * 1024 ) / ( smem + 1024 ) );
     if( ctas_per_sm > 4 ) ctas_per_sm = 4;
@@ -544,8 +546,8 @@ int x264cu_pixel_cmp_mvfield( x264cu_ctx_t *ctx, int metric, int i_pixel, const 
     if( fenc->n_planes <= 0 ) return 0;
     if( metric == X264CU_SATD && i_pixel == X264CU_PIXEL_16x16 )
     {   // tuning hook (profiling only): alternative tile / pipeline shapes for the headline kernel
-        static int cfg = -1;
-        if( cfg < 0 ) { const char *e = getenv( "X264CU_MVF_CFG" ); cfg = e ? atoi( e ) : 0; }
+        const char *e = getenv( "X264CU_MVF_CFG" );
+        const int cfg = e ? atoi( e ) : 0;
         switch( cfg )
         {
             case 1: return launch_mvfield<M_SATD, 16, 16, 128, 128, 16, 2, 8>( ctx, fenc, ref, k_cands, d_mv, d_out );

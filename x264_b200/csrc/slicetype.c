@@ -77,6 +77,7 @@ struct x264cu_slicetype
     int xj_slot[256], xj_list[256], xj_dist[256], xj_owner[256], xj_frame[256], n_xj;
     int next_forced_type;                 /* pic_in->i_type of the next queued picture (x264cu_slicetype_set_next_type) */
     st_frame_t *handed;                   /* the picture the last step returned: kept (slot included) until the next step */
+    char best_paths[BFRAME_MAX + 1][LOOKAHEAD_MAX + 1];   /* the trellis of b-adapt 2, slicetype.c:1559-1561 */
     int vbv_lookahead;                    /* h->param.rc.i_vbv_buffer_size && h->param.rc.i_lookahead */
 };
 
@@ -463,8 +464,8 @@ static void slicetype_analyse( x264cu_slicetype_t *s, int intra_minigop )
         {
             if( num_frames > 1 )
             {
-                static char best_paths[BFRAME_MAX + 1][LOOKAHEAD_MAX + 1];
-                memset( best_paths, 0, sizeof( best_paths ) );
+                char ( *best_paths )[LOOKAHEAD_MAX + 1] = s->best_paths;          /* per object: several streams may run in one process */
+                memset( s->best_paths, 0, sizeof( s->best_paths ) );
                 strcpy( best_paths[1], "P" );
                 int best_path_index = num_frames % ( BFRAME_MAX + 1 );
                 for( int j = 2; j <= num_frames; j++ )
