@@ -453,6 +453,26 @@ int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *params,
                             const uint8_t *const d_fref[4], const uint8_t *d_fref_w, intptr_t ref_stride,
                             const x264cu_me_job_t *d_jobs, int n, x264cu_me_result_t *d_results );
 
+/* Batched twin of x264_me_refine_qpel (refdupe = 0; encoder/me.h:59, me.c:800-809) and x264_me_refine_qpel_refdupe (refdupe = 1;
+ * me.h:60, me.c:811-814): the sub-pel refinement continued from a stored vector and cost.  params: subpel_refine =
+ * h->mb.i_subpel_refine, mbcmp_satd, lambda, mv_range and the weight are read.  Results as x264cu_me_result_t (halfpel_thresh is
+ * the updated *p_halfpel_thresh of the refdupe form, -1 otherwise). */
+typedef struct
+{
+    int32_t  i_pixel;                /* m->i_pixel */
+    uint32_t fenc_off, ref_off;      /* byte offsets of the block in the fenc plane / of the co-located block in the reference planes */
+    int16_t  mvp[2];                 /* m->mvp */
+    int16_t  mv[2];                  /* m->mv on entry */
+    int32_t  cost;                   /* m->cost on entry */
+    int32_t  i_ref_cost;             /* m->i_ref_cost: taken off the cost of 8x8 and larger partitions by x264_me_refine_qpel */
+    int16_t  mv_min_spel[2], mv_max_spel[2];
+    int32_t  halfpel_thresh;         /* refdupe: *p_halfpel_thresh, or -1 for NULL */
+} x264cu_me_refine_job_t;
+
+int x264cu_me_refine_qpel_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *params, int refdupe,
+                                 const uint8_t *d_fenc, intptr_t fenc_stride, const uint8_t *const d_fref[4], intptr_t ref_stride,
+                                 const x264cu_me_refine_job_t *d_jobs, int n, x264cu_me_result_t *d_results );
+
 /* Batched twin of x264_me_refine_bidir_satd (encoder/me.h:63, encoder/me.c:1027-1183): joint +-1 quarter-pel refinement of
  * the two vectors of a bi-predicted partition, one job = one call.  params: mbcmp_satd, lambda and mv_range are read. */
 typedef struct

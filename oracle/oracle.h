@@ -83,6 +83,8 @@ typedef struct
 } orc_me_t;
 
 void orc_me_search_ref( const orc_me_ctx_t *c, orc_me_t *m, const int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );
+/* x264_me_refine_qpel (mode 0) / x264_me_refine_qpel_refdupe (mode 1), me.c:800-814: continue from m->mv / m->cost */
+void orc_me_refine_qpel( const orc_me_ctx_t *c, orc_me_t *m, int mode, int i_ref_cost, int *p_halfpel_thresh );
 /* x264_me_refine_bidir_satd (me.c:1027-1183): refines m0->mv / m1->mv jointly; reads c->mv_min_spel / mv_max_spel / mbcmp_is_satd */
 void orc_me_refine_bidir_satd( const orc_me_ctx_t *c, orc_me_t *m0, orc_me_t *m1, int i_weight );
 

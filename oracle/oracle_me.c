@@ -647,6 +647,30 @@ static void refine_subpel( search_t *s, int hpel_iters, int qpel_iters, int *p_h
     m->cost_mv = s->cmx[bmx] + s->cmy[bmy];
 }
 
+/* ---- x264_me_refine_qpel / x264_me_refine_qpel_refdupe, encoder/me.c:800-814 ---------------------------------------------
+ * Both continue from m->mv / m->cost.  mode 0 (refine_qpel): the iteration counts of the FINAL refinement
+ * (subpel_iterations[subme][0..1]), every direction tried in each quarter-pel round and no re-measurement of the start;
+ * partitions of 8x8 and larger first give back i_ref_cost.  mode 1 (refdupe): quarter-pel rounds only, at most two. */
+void orc_me_refine_qpel( const orc_me_ctx_t *c, orc_me_t *m, int mode, int i_ref_cost, int *p_halfpel_thresh )
+{
+    static const uint8_t subpel_iterations[12][4] =                  /* me.c:38-50 */
+        { {0,0,0,0}, {1,1,0,0}, {0,1,1,0}, {0,2,1,0}, {0,2,1,1}, {0,2,1,2}, {0,0,2,2}, {0,0,2,2},
+          {0,0,4,10}, {0,0,4,10}, {0,0,4,10}, {0,0,4,10} };
+    search_t S, *s = &S;
+    s->c = c; s->m = m;
+    s->bw = orc_pixel_w[m->i_pixel]; s->bh = orc_pixel_h[m->i_pixel];
+    s->cmx = m->p_cost_mv - m->mvp[0];
+    s->cmy = m->p_cost_mv - m->mvp[1];
+    if( mode == 0 )
+    {
+        if( m->i_pixel <= ORC_PIXEL_8x8 )
+            m->cost -= i_ref_cost;
+        refine_subpel( s, subpel_iterations[c->subpel_refine][0], subpel_iterations[c->subpel_refine][1], NULL, 1 );
+    }
+    else
+        refine_subpel( s, 0, imin( 2, subpel_iterations[c->subpel_refine][3] ), p_halfpel_thresh, 0 );
+}
+
 /* ---- x264_me_refine_bidir_satd, encoder/me.c:1027-1183 with rd = 0 --------------------------------------------------------
  * Joint refinement of the two vectors of a bi-predicted block: up to 8 passes; each pass measures the (list 0, list 1)
  * vector pairs that differ from the current pair by +-1 quarter-pel in at most two of the four components (33 pairs, the

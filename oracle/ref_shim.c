@@ -318,6 +318,47 @@ XREF_API void xref_me_search( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr
     me_search_common( hv, a, fenc, fenc_stride, f0, f1, f2, f3, fref_w, stride, NULL );
 }
 
+/* x264_me_refine_qpel (mode 0) / x264_me_refine_qpel_refdupe (mode 1) (encoder/me.c:800-814) on caller-supplied planes, from
+ * a->mv / a->cost; a->qp, a->subpel_refine, limits, mvp, weights and the half-pel threshold as in xref_me_search */
+XREF_API void xref_me_refine_qpel( void *hv, xref_me_args_t *a, int mode, int i_ref_cost, uint8_t *fenc, intptr_t fenc_stride,
+                                   uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, intptr_t stride )
+{
+    x264_t *h = hv;
+    tables_init();
+    ALIGNED_ARRAY_64( pixel, fenc_buf,[16*16] );
+    int bw = x264_pixel_size[a->i_pixel].w, bh = x264_pixel_size[a->i_pixel].h;
+    for( int y = 0; y < bh; y++ )
+        memcpy( fenc_buf + y*FENC_STRIDE, fenc + y*fenc_stride, bw );
+    x264_weight_t wt; make_weight( &wt, a->wt_en, a->wt_scale, a->wt_denom, a->wt_offset );
+    if( a->wt_en ) wt.weightfn = h->mc.weight;
+    x264_me_t m;
+    memset( &m, 0, sizeof(m) );
+    m.i_pixel = a->i_pixel;
+    m.p_cost_mv = h->cost_mv[a->qp];
+    m.i_ref_cost = i_ref_cost;
+    m.weight = &wt;
+    m.p_fref[0] = f0; m.p_fref[1] = f1; m.p_fref[2] = f2; m.p_fref[3] = f3;
+    m.p_fref_w = f0;
+    m.p_fenc[0] = fenc_buf;
+    m.i_stride[0] = stride;
+    m.mvp[0] = a->mvp[0]; m.mvp[1] = a->mvp[1];
+    m.mv[0] = a->mv[0]; m.mv[1] = a->mv[1];
+    m.cost = a->cost;
+    h->mb.i_subpel_refine = a->subpel_refine;
+    h->mb.b_chroma_me = 0;
+    for( int i = 0; i < 2; i++ )
+    {
+        h->mb.mv_min_spel[i] = a->mv_min_spel[i];
+        h->mb.mv_max_spel[i] = a->mv_max_spel[i];
+    }
+    int thresh = a->halfpel_thresh;
+    if( mode == 0 ) x264_me_refine_qpel( h, &m );
+    else            x264_me_refine_qpel_refdupe( h, &m, a->use_thresh ? &thresh : NULL );
+    a->mv[0] = m.mv[0]; a->mv[1] = m.mv[1];
+    a->cost = m.cost; a->cost_mv = m.cost_mv;
+    a->thresh_out = thresh;
+}
+
 /* x264_me_refine_bidir_satd (encoder/me.c:1027-1183, rd = 0) on caller-supplied planes: f0[4] / f1[4] = F,H,V,C planes of the
  * list-0 / list-1 reference at the block origin.  mv0 / mv1 are updated in place. */
 XREF_API void xref_me_refine_bidir_satd( void *hv, int i_pixel, int qp, uint8_t *fenc, intptr_t fenc_stride,

@@ -190,6 +190,79 @@ def test_me_refine_bidir_batch_matches_oracle(ctx, kind, satd):
     assert moved > 50
 
 
+@pytest.mark.parametrize("kind", ["texture", "flat"])
+@pytest.mark.parametrize("refdupe", [0, 1])
+def test_me_refine_qpel_batch_matches_oracle(ctx, kind, refdupe):
+    """x264cu_me_refine_qpel_batch against the oracle's x264_me_refine_qpel / _refdupe (pinned to the reference in
+    tests/test_oracle_me.py): every sub-pel level incl. the simplified level 1, weights, half-pel thresholds"""
+    o = oracle()
+    o.orc_me_refine_qpel.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    o.orc_me_refine_qpel.restype = None
+    rng = np.random.default_rng(11 + refdupe + len(kind))
+    mv_range, lam = 64, 1
+    n = 2 * 4 * mv_range
+    tab = np.zeros(2 * n + 1, np.uint16)
+    o.orc_cost_mv_table(tab, n, lam)
+    moved = 0
+    for subpel in (1, 2, 3, 4, 5, 6, 7, 9):
+        satd = int(subpel > 1 and rng.random() < 0.8)
+        wt = (1, int(rng.integers(40, 90)), 6, int(rng.integers(-4, 5))) if rng.random() < 0.3 else (0, 0, 0, 0)
+        fenc_l, ref_l = _content(kind, rng)
+        planes = make_ref_planes(ref_l)
+        st = planes[0].stride
+        fenc = PaddedPlane(W, H, stride=st)
+        fenc.inner()[:] = fenc_l
+        n_jobs = 64
+        jobs = np.zeros(n_jobs, x.me_refine_job_dtype)
+        want = []
+        for k in range(n_jobs):
+            ip = int(rng.integers(0, 7))
+            bw, bh = PIXEL_W[ip], PIXEL_H[ip]
+            bx = int(rng.integers(0, (W - bw) // 4 + 1)) * 4
+            by = int(rng.integers(0, (H - bh) // 4 + 1)) * 4
+            mvr = 4 * mv_range
+            lim_min = [max(4 * (-bx - 24), -mvr), max(4 * (-by - 24), -mvr)]
+            lim_max = [min(4 * (W - bx - bw + 24), mvr - 1), min(4 * (H - by - bh + 24), mvr - 1)]
+            spread = int(rng.choice([4, 20, 90]))
+            mv = np.clip(rng.integers(-spread, spread + 1, 2), lim_min, lim_max)
+            mvp = mv + rng.integers(-6, 7, 2)
+            cost, ref_cost = int(rng.integers(50, 6000)), int(rng.integers(0, 5))
+            use_thresh = bool(refdupe and rng.random() < 0.4)
+            thresh = int(rng.integers(50, 6000)) if use_thresh else -1
+            off = planes[0].off(bx, by)
+            j = jobs[k]
+            j["i_pixel"], j["fenc_off"], j["ref_off"], j["mvp"], j["mv"] = ip, fenc.off(bx, by), off, mvp, mv
+            j["cost"], j["i_ref_cost"], j["mv_min_spel"], j["mv_max_spel"], j["halfpel_thresh"] = cost, ref_cost, lim_min, lim_max, thresh
+            c = OrcMeCtx()
+            c.me_method, c.subpel_refine, c.me_range, c.mbcmp_is_satd = 1, subpel, 16, satd
+            for i in range(2):
+                c.mv_min_spel[i], c.mv_max_spel[i] = lim_min[i], lim_max[i]
+            m = OrcMe()
+            m.i_pixel = ip
+            m.p_cost_mv = tab.ctypes.data + 2 * n
+            for i in range(4):
+                m.p_fref[i] = planes[i].buf.ctypes.data + off
+            m.p_fref_w = planes[0].buf.ctypes.data + off
+            m.p_fenc = fenc.buf.ctypes.data + fenc.off(bx, by)
+            m.fenc_stride, m.stride = st, st
+            m.weight = OrcWeight(*wt)
+            m.mvp[0], m.mvp[1], m.mv[0], m.mv[1], m.cost = int(mvp[0]), int(mvp[1]), int(mv[0]), int(mv[1]), cost
+            th = C.c_int(thresh)
+            o.orc_me_refine_qpel(C.byref(c), C.byref(m), refdupe, ref_cost, C.byref(th) if use_thresh else None)
+            want.append((m.mv[0], m.mv[1], m.cost, th.value if use_thresh else -1))
+            moved += (m.mv[0], m.mv[1]) != (int(mv[0]), int(mv[1]))
+        d_fenc = ctx.upload(fenc.buf)
+        d_pl = [ctx.upload(p.buf) for p in planes]
+        params = x.MeParams(1, subpel, 16, satd, lam, mv_range, *wt)
+        res = x.me_refine_qpel_batch(ctx, params, refdupe, d_fenc, st, d_pl, st, jobs)
+        for p in [d_fenc] + d_pl:
+            ctx.free(p)
+        for k in range(n_jobs):
+            got = (int(res[k]["mv"][0]), int(res[k]["mv"][1]), int(res[k]["cost"]), int(res[k]["halfpel_thresh"]))
+            assert got == want[k], (kind, refdupe, subpel, satd, wt, k, jobs[k], got, want[k])
+    assert moved > 30
+
+
 def test_me_search_batch_4k_frame_of_macroblocks(ctx):
     """BASELINE config 3 shape: every 16x16 macroblock of a 4K frame, UMH merange 64, subme 9 -- against the oracle on a
     random subset (the oracle is scalar), and a determinism check on all 32 400 jobs"""

@@ -272,3 +272,81 @@ def test_refine_bidir_satd_matches_reference(subme_param, kind):
         assert moved > 20
     finally:
         r.xref_close(hnd)
+
+
+@pytest.mark.parametrize("subme_param", [1, 7])
+@pytest.mark.parametrize("kind", ["texture", "flat"])
+def test_refine_qpel_matches_reference(subme_param, kind):
+    """x264_me_refine_qpel / x264_me_refine_qpel_refdupe (me.c:800-814): the final refinement of a stored vector, every h->mb
+    sub-pel level (level 1 takes the simplified SAD quarter-pel diamond, me.c:965-985), weights, half-pel thresholds"""
+    _libs._bind_me()
+    o, r = oracle(), ref()
+    r.xref_me_refine_qpel.argtypes = [C.c_void_p, C.POINTER(XrefMeArgs), C.c_int, C.c_int, C.c_void_p, C.c_ssize_t] + [C.c_void_p] * 4 + [C.c_ssize_t]
+    r.xref_me_refine_qpel.restype = None
+    o.orc_me_refine_qpel.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    o.orc_me_refine_qpel.restype = None
+    hnd = r.xref_open(W, H, b"medium", ("subme=%d" % subme_param).encode(), 0)
+    assert hnd
+    try:
+        n = 2 * 4 * r.xref_param(hnd, b"mvrange")
+        tab = np.zeros(2 * n + 1, np.uint16)
+        r.xref_cost_mv_table_qp(hnd, 12, tab, n)
+        rng = np.random.default_rng(9 * subme_param + len(kind))
+        moved = 0
+        for rep in range(4):
+            fenc_l, ref_l = _content(kind, rng)
+            planes = make_ref_planes(ref_l)
+            st = planes[0].stride
+            fenc = PaddedPlane(W, H, stride=st)
+            fenc.inner()[:] = fenc_l
+            for _ in range(60):
+                ip = int(rng.integers(0, 7))
+                bw, bh = PIXEL_W[ip], PIXEL_H[ip]
+                bx = int(rng.integers(0, (W - bw) // 4 + 1)) * 4
+                by = int(rng.integers(0, (H - bh) // 4 + 1)) * 4
+                mode = int(rng.integers(0, 2))
+                subpel = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 9, 11]))
+                mvr = 4 * 64
+                lim_min = [max(4 * (-bx - 24), -mvr), max(4 * (-by - 24), -mvr)]
+                lim_max = [min(4 * (W - bx - bw + 24), mvr - 1), min(4 * (H - by - bh + 24), mvr - 1)]
+                spread = int(rng.choice([4, 20, 90]))
+                mv = np.clip(rng.integers(-spread, spread + 1, 2), lim_min, lim_max)
+                mvp = mv + rng.integers(-6, 7, 2)
+                cost = int(rng.integers(50, 6000))
+                ref_cost = int(rng.integers(0, 5))
+                wt = (1, int(rng.integers(40, 90)), 6, int(rng.integers(-4, 5))) if rng.random() < 0.25 else (0, 0, 0, 0)
+                use_thresh = mode == 1 and rng.random() < 0.4
+                thresh = int(rng.integers(50, 6000))
+                off = planes[0].off(bx, by)
+                a = XrefMeArgs()
+                a.i_pixel, a.me_method, a.subpel_refine, a.me_range, a.qp = ip, 1, subpel, 16, 12
+                for i in range(2):
+                    a.mv_min_spel[i], a.mv_max_spel[i], a.mvp[i], a.mv[i] = lim_min[i], lim_max[i], int(mvp[i]), int(mv[i])
+                a.cost = cost
+                a.wt_en, a.wt_scale, a.wt_denom, a.wt_offset = wt
+                a.use_thresh, a.halfpel_thresh = int(use_thresh), thresh
+                r.xref_me_refine_qpel(hnd, C.byref(a), mode, ref_cost, ptr(fenc.buf, fenc.off(bx, by)), st, *[ptr(p.buf, off) for p in planes], st)
+                c = OrcMeCtx()
+                c.me_method, c.subpel_refine, c.me_range, c.mbcmp_is_satd = 1, subpel, 16, int(subme_param > 1)
+                for i in range(2):
+                    c.mv_min_spel[i], c.mv_max_spel[i] = lim_min[i], lim_max[i]
+                m = OrcMe()
+                m.i_pixel = ip
+                m.p_cost_mv = tab.ctypes.data + 2 * n
+                for i in range(4):
+                    m.p_fref[i] = planes[i].buf.ctypes.data + off
+                m.p_fref_w = planes[0].buf.ctypes.data + off
+                m.p_fenc = fenc.buf.ctypes.data + fenc.off(bx, by)
+                m.fenc_stride, m.stride = st, st
+                m.weight = OrcWeight(*wt)
+                m.mvp[0], m.mvp[1], m.mv[0], m.mv[1], m.cost = int(mvp[0]), int(mvp[1]), int(mv[0]), int(mv[1]), cost
+                th = C.c_int(thresh)
+                o.orc_me_refine_qpel(C.byref(c), C.byref(m), mode, ref_cost, C.byref(th) if use_thresh else None)
+                key = (kind, ip, mode, subpel, tuple(mv), tuple(mvp), cost, wt, use_thresh, thresh)
+                assert (m.mv[0], m.mv[1], m.cost) == (a.mv[0], a.mv[1], a.cost), key
+                if use_thresh:
+                    assert th.value == a.thresh_out, key
+                moved += (m.mv[0], m.mv[1]) != (int(mv[0]), int(mv[1]))
+        assert moved > 20
+    finally:
+        r.xref_close(hnd)

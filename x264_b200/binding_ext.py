@@ -32,6 +32,9 @@ bidir_job_dtype = np.dtype([("i_pixel", np.int32), ("fenc_off", np.uint32), ("re
                             ("mv", np.int16, (4,)), ("mvp", np.int16, (4,)), ("mv_min_spel", np.int16, (2,)),
                             ("mv_max_spel", np.int16, (2,)), ("i_weight", np.int32)])
 bidir_result_dtype = np.dtype([("mv", np.int16, (4,)), ("cost", np.int32)])
+me_refine_job_dtype = np.dtype([("i_pixel", np.int32), ("fenc_off", np.uint32), ("ref_off", np.uint32), ("mvp", np.int16, (2,)),
+                                ("mv", np.int16, (2,)), ("cost", np.int32), ("i_ref_cost", np.int32), ("mv_min_spel", np.int16, (2,)),
+                                ("mv_max_spel", np.int16, (2,)), ("halfpel_thresh", np.int32)])
 
 
 class SlicetypeParams(C.Structure):
@@ -48,6 +51,7 @@ def bind(L):
     vp, ci, ss = C.c_void_p, C.c_int, C.c_ssize_t
     L.x264cu_me_search_batch.argtypes = [vp, C.POINTER(MeParams), vp, ss, C.POINTER(vp), vp, ss, vp, ci, vp]
     L.x264cu_me_refine_bidir_batch.argtypes = [vp, C.POINTER(MeParams), vp, ss, C.POINTER(vp), C.POINTER(vp), ss, vp, ci, vp]
+    L.x264cu_me_refine_qpel_batch.argtypes = [vp, C.POINTER(MeParams), ci, vp, ss, C.POINTER(vp), ss, vp, ci, vp]
     L.x264cu_slicetype_open.argtypes = [vp, C.POINTER(SlicetypeParams), C.POINTER(vp)]
     L.x264cu_slicetype_close.argtypes = [vp]
     L.x264cu_slicetype_step.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
@@ -390,6 +394,20 @@ def me_refine_bidir_batch(ctx, params, d_fenc, fenc_stride, d_fref0, d_fref1, re
     a1 = (C.c_void_p * 4)(*[int(p) for p in d_fref1])
     ctx.check(ctx.L.x264cu_me_refine_bidir_batch(ctx.h, C.byref(params), int(d_fenc), fenc_stride, a0, a1, ref_stride, d_jobs, n, d_res))
     out = ctx.download(d_res, (n,), bidir_result_dtype)
+    ctx.free(d_jobs)
+    ctx.free(d_res)
+    return out
+
+
+def me_refine_qpel_batch(ctx, params, refdupe, d_fenc, fenc_stride, d_fref, ref_stride, jobs):
+    """jobs: numpy array of me_refine_job_dtype (host) -> numpy array of me_result_dtype.  d_* are device addresses."""
+    assert jobs.dtype == me_refine_job_dtype and me_refine_job_dtype.itemsize == 40
+    n = len(jobs)
+    d_jobs = ctx.upload(jobs)
+    d_res = ctx.malloc(max(n, 1) * me_result_dtype.itemsize)
+    arr = (C.c_void_p * 4)(*[int(p) for p in d_fref])
+    ctx.check(ctx.L.x264cu_me_refine_qpel_batch(ctx.h, C.byref(params), int(refdupe), int(d_fenc), fenc_stride, arr, ref_stride, d_jobs, n, d_res))
+    out = ctx.download(d_res, (n,), me_result_dtype)
     ctx.free(d_jobs)
     ctx.free(d_res)
     return out

@@ -184,3 +184,83 @@ extern "C" int x264cu_me_refine_bidir_batch( x264cu_ctx_t *ctx, const x264cu_me_
     CU_LAUNCH_CHECK( ctx );
     return 0;
 }
+
+// ---- x264cu_me_refine_qpel_batch: x264_me_refine_qpel / x264_me_refine_qpel_refdupe, me.c:800-814 ---------------------------
+struct RefineJob                                // == x264cu_me_refine_job_t
+{
+    int32_t i_pixel; uint32_t fenc_off, ref_off; int16_t mvp[2], mv[2]; int32_t cost, i_ref_cost; int16_t mv_min_spel[2], mv_max_spel[2];
+    int32_t halfpel_thresh;
+};
+static_assert( sizeof( RefineJob ) == sizeof( x264cu_me_refine_job_t ), "ABI structs" );
+
+template <int BW, int BH>
+__device__ __noinline__ void run_refine( const MeShared &g, const RefineJob &j, int mode, int lane, MeResult &r )
+{
+    MeWarp<BW, BH> m;
+    int16_t lim[4] = { j.mv_min_spel[0], j.mv_min_spel[1], j.mv_max_spel[0], j.mv_max_spel[1] };
+    me_warp_setup<BW, BH>( m, g, j.fenc_off, j.ref_off, j.mvp[0], j.mvp[1], lim, lane );
+    m.bmx = m.bmy = 0; m.bcost = LA_COST_MAX;
+    const int subpel = g.subpel_refine;
+    int qx = j.mv[0], qy = j.mv[1], qcost = j.cost, thresh = -1;
+    if( mode == 0 )
+    {   // subpel_iterations[subme][0..1]: refine_hpel, refine_qpel (me.c:38-50)
+        const int hpel = subpel == 1 ? 1 : 0, qpel = subpel == 0 ? 0 : subpel <= 2 ? 1 : subpel <= 5 ? 2 : 0;
+        if( j.i_pixel <= X264CU_PIXEL_8x8 ) qcost -= j.i_ref_cost;
+        me_refine_subpel<BW, BH>( m, subpel, hpel, qpel, true, thresh, qx, qy, qcost );
+    }
+    else
+    {   // at most two quarter-pel rounds of me_qpel = subpel_iterations[subme][3]
+        const int me_qpel = subpel < 4 ? 0 : subpel == 4 ? 1 : subpel < 8 ? 2 : 10;
+        thresh = j.halfpel_thresh;
+        me_refine_subpel<BW, BH>( m, subpel, 0, min( 2, me_qpel ), false, thresh, qx, qy, qcost );
+    }
+    r.mv[0] = (int16_t)qx; r.mv[1] = (int16_t)qy; r.cost = qcost; r.halfpel_thresh = thresh;
+    r.cost_mv = __ldg( g.cost_mv + ( qx - j.mvp[0] ) ) + __ldg( g.cost_mv + ( qy - j.mvp[1] ) );
+}
+
+__global__ void __launch_bounds__( 128 )
+me_refine_kernel( MeShared g, int mode, const RefineJob *__restrict__ jobs, int n, MeResult *__restrict__ results )
+{
+    const int lane = threadIdx.x & 31;
+    const int w = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5;
+    if( w >= n ) return;
+    RefineJob j = jobs[w];
+    MeResult r;
+    switch( j.i_pixel )
+    {
+        case X264CU_PIXEL_16x16: run_refine<16, 16>( g, j, mode, lane, r ); break;
+        case X264CU_PIXEL_16x8:  run_refine<16, 8>( g, j, mode, lane, r ); break;
+        case X264CU_PIXEL_8x16:  run_refine<8, 16>( g, j, mode, lane, r ); break;
+        case X264CU_PIXEL_8x8:   run_refine<8, 8>( g, j, mode, lane, r ); break;
+        case X264CU_PIXEL_8x4:   run_refine<8, 4>( g, j, mode, lane, r ); break;
+        case X264CU_PIXEL_4x8:   run_refine<4, 8>( g, j, mode, lane, r ); break;
+        default:                 run_refine<4, 4>( g, j, mode, lane, r ); break;
+    }
+    if( lane == 0 ) results[w] = r;
+}
+
+extern "C" int x264cu_me_refine_qpel_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *p, int refdupe, const uint8_t *d_fenc, intptr_t fenc_stride,
+                                            const uint8_t *const d_fref[4], intptr_t ref_stride,
+                                            const x264cu_me_refine_job_t *d_jobs, int n, x264cu_me_result_t *d_results )
+{
+    if( !ctx || !p ) return -1;
+    if( n <= 0 ) return 0;
+    if( !d_fenc || !d_fref || !d_jobs || !d_results ) return x264cu_fail( ctx, "me_refine_qpel_batch: null argument" );
+    if( p->subpel_refine < 0 || p->subpel_refine > 11 || p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 )
+        return x264cu_fail( ctx, "me_refine_qpel_batch: bad parameters" );
+    const uint16_t *d_tab = me_cost_table( ctx, p->lambda, p->mv_range );
+    if( !d_tab ) return -1;
+    MeShared g;
+    g.fenc = d_fenc; g.fenc_stride = (int)fenc_stride;
+    for( int i = 0; i < 4; i++ ) g.fref[i] = d_fref[i];
+    g.fref_w = d_fref[0];
+    g.stride = (int)ref_stride;
+    g.cost_mv = d_tab;
+    g.me_method = p->me_method; g.subpel_refine = p->subpel_refine; g.me_range = p->me_range; g.satd = p->mbcmp_satd;
+    g.fpel_satd = p->mbcmp_satd && p->me_method == X264CU_ME_TESA;
+    g.tesa_list = nullptr; g.tesa_cap = 0;
+    g.w.enabled = p->weight_enabled; g.w.scale = p->weight_scale; g.w.denom = p->weight_denom; g.w.offset = p->weight_offset;
+    me_refine_kernel<<<( n + 3 ) / 4, 128, 0, ctx->stream>>>( g, !!refdupe, (const RefineJob *)d_jobs, n, (MeResult *)d_results );
+    CU_LAUNCH_CHECK( ctx );
+    return 0;
+}

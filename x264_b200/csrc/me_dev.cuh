@@ -339,14 +339,12 @@ struct MeWarp
     }
 };
 
-// mvc: up to 8 candidate vectors; thresh_io: half-pel early-termination threshold (< 0 = none)
+// per-lane state of one search: the lane's 4x4 of fenc, its corner in the reference planes, the window
 template <int BW, int BH>
-__device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc_off, uint32_t ref_off, int mvpx, int mvpy,
-                                   const int16_t *mvc, int i_mvc, const int16_t *limits /* min_x,min_y,max_x,max_y spel */,
-                                   int &thresh_io, int lane, int &out_mvx, int &out_mvy, int &out_cost, int &out_cost_mv, uint2 *tesa_list )
+__device__ __forceinline__ void me_warp_setup( MeWarp<BW, BH> &m, const MeShared &g, uint32_t fenc_off, uint32_t ref_off, int mvpx, int mvpy,
+                                               const int16_t *limits /* min_x,min_y,max_x,max_y spel */, int lane )
 {
     using M = MeWarp<BW, BH>;
-    M m;
     const int gl = lane % M::L;
     m.gl = gl; m.fpel_satd = g.fpel_satd != 0;
     const int sx = ( gl % M::LX ) * 4, sy = ( gl / M::LX ) * 4;
@@ -366,6 +364,88 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
     }
     m.min_spel_x = limits[0]; m.min_spel_y = limits[1]; m.max_spel_x = limits[2]; m.max_spel_y = limits[3];
     m.x_min = m.min_spel_x >> 2; m.y_min = m.min_spel_y >> 2; m.x_max = m.max_spel_x >> 2; m.y_max = m.max_spel_y >> 2;
+}
+
+// refine_subpel( h, m, hpel_iters, qpel_iters, p_halfpel_thresh, b_refine_qpel ), me.c:865-992, from (qx, qy, qcost)
+template <int BW, int BH>
+__device__ void me_refine_subpel( MeWarp<BW, BH> &m, int subpel, int hpel_iters, int qpel_iters, bool b_refine_qpel, int &thresh_io,
+                                  int &qx, int &qy, int &qcost )
+{
+    using M = MeWarp<BW, BH>;
+    const int mvpx = m.mvpx, mvpy = m.mvpy;
+    auto diamond = [&]( int step, bool use_mbcmp, int skip_dir ) {
+        // candidates (0,-s) (0,+s) (-s,0) (+s,0); returns the winning direction or -1; updates qx,qy,qcost
+        int best = 0x7fffffff;
+        for( int base = 0; base < 4; base += M::S )
+        {
+            const int dir = base + m.slot;
+            const int dd = min( dir, 3 );
+            const int dx = dd == 2 ? -step : dd == 3 ? step : 0, dy = dd == 0 ? -step : dd == 1 ? step : 0;
+            const bool ok = dir < 4 && dir != skip_dir;
+            const int c = m.cost_qpel( qx + dx, qy + dy, use_mbcmp );
+            int key = ok ? ( c << 2 ) + dir : 0x7fffffff;
+            best = min( best, warp_min( key ) );
+        }
+        if( best != 0x7fffffff && ( best >> 2 ) < qcost )
+        {
+            const int dir = best & 3;
+            qcost = best >> 2;
+            qx += dir == 2 ? -step : dir == 3 ? step : 0;
+            qy += dir == 0 ? -step : dir == 1 ? step : 0;
+            return dir;
+        }
+        return -1;
+    };
+    if( hpel_iters )
+    {
+        if( subpel < 3 )
+        {
+            int px = clip3i( mvpx, m.min_spel_x + 2, m.max_spel_x - 2 ), py = clip3i( mvpy, m.min_spel_y + 2, m.max_spel_y - 2 );
+            if( ( px - qx ) | ( py - qy ) )
+            {
+                int c = m.cost_qpel( px, py, false );
+                if( c < qcost ) { qcost = c; qx = px; qy = py; }
+            }
+        }
+        for( int i = hpel_iters; i > 0; i-- )
+            if( diamond( 2, false, -1 ) < 0 )
+                break;
+    }
+    if( !b_refine_qpel && m.satd && !m.fpel_satd )               // mbcmp != fpelcmp: re-measure the winner, me.c:925-929
+        qcost = m.cost_qpel( qx, qy, true );
+    if( thresh_io >= 0 )
+    {
+        if( ( qcost * 7 ) >> 3 > thresh_io ) return;
+        else if( qcost < thresh_io ) thresh_io = qcost;
+    }
+    const bool inside = qy > m.min_spel_y && qy < m.max_spel_y && qx > m.min_spel_x && qx < m.max_spel_x;
+    if( subpel != 1 )
+    {
+        int bdir = -1;
+        for( int i = qpel_iters; i > 0; i-- )
+        {
+            if( qy <= m.min_spel_y || qy >= m.max_spel_y || qx <= m.min_spel_x || qx >= m.max_spel_x )
+                break;
+            const int odir = bdir;
+            const int d = diamond( 1, true, !b_refine_qpel && odir >= 0 ? ( odir ^ 1 ) : -1 );     // never straight back, me.c:828
+            if( d < 0 )
+                break;
+            bdir = d;
+        }
+    }
+    else if( inside )
+        diamond( 1, false, -1 );                                 // subme 1: one fpelcmp quarter-pel diamond, me.c:965-985
+}
+
+// mvc: up to 8 candidate vectors; thresh_io: half-pel early-termination threshold (< 0 = none)
+template <int BW, int BH>
+__device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc_off, uint32_t ref_off, int mvpx, int mvpy,
+                                   const int16_t *mvc, int i_mvc, const int16_t *limits /* min_x,min_y,max_x,max_y spel */,
+                                   int &thresh_io, int lane, int &out_mvx, int &out_mvy, int &out_cost, int &out_cost_mv, uint2 *tesa_list )
+{
+    using M = MeWarp<BW, BH>;
+    M m;
+    me_warp_setup<BW, BH>( m, g, fenc_off, ref_off, mvpx, mvpy, limits, lane );
     m.bcost = LA_COST_MAX;
     int me_range = g.me_range;
     const int subpel = g.subpel_refine;
@@ -597,69 +677,7 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
         // subpel_iterations[subme][2..3]: me_hpel, me_qpel
         const int hpel_iters = subpel < 8 ? ( subpel >= 6 ? 2 : 1 ) : 4;
         const int qpel_iters = subpel < 4 ? 0 : subpel == 4 ? 1 : subpel < 8 ? 2 : 10;
-        auto diamond = [&]( int step, bool use_mbcmp, int skip_dir ) {
-            // candidates (0,-s) (0,+s) (-s,0) (+s,0); returns the winning direction or -1; updates qx,qy,qcost
-            int best = 0x7fffffff;
-            for( int base = 0; base < 4; base += M::S )
-            {
-                const int dir = base + m.slot;
-                const int dd = min( dir, 3 );
-                const int dx = dd == 2 ? -step : dd == 3 ? step : 0, dy = dd == 0 ? -step : dd == 1 ? step : 0;
-                const bool ok = dir < 4 && dir != skip_dir;
-                const int c = m.cost_qpel( qx + dx, qy + dy, use_mbcmp );
-                int key = ok ? ( c << 2 ) + dir : 0x7fffffff;
-                best = min( best, warp_min( key ) );
-            }
-            if( best != 0x7fffffff && ( best >> 2 ) < qcost )
-            {
-                const int dir = best & 3;
-                qcost = best >> 2;
-                qx += dir == 2 ? -step : dir == 3 ? step : 0;
-                qy += dir == 0 ? -step : dir == 1 ? step : 0;
-                return dir;
-            }
-            return -1;
-        };
-        if( hpel_iters )
-        {
-            if( subpel < 3 )
-            {
-                int px = clip3i( mvpx, m.min_spel_x + 2, m.max_spel_x - 2 ), py = clip3i( mvpy, m.min_spel_y + 2, m.max_spel_y - 2 );
-                if( ( px - qx ) | ( py - qy ) )
-                {
-                    int c = m.cost_qpel( px, py, false );
-                    if( c < qcost ) { qcost = c; qx = px; qy = py; }
-                }
-            }
-            for( int i = hpel_iters; i > 0; i-- )
-                if( diamond( 2, false, -1 ) < 0 )
-                    break;
-        }
-        if( m.satd && !m.fpel_satd )                              // mbcmp != fpelcmp: re-measure the winner, me.c:925-929
-            qcost = m.cost_qpel( qx, qy, true );
-        bool early = false;
-        if( thresh_io >= 0 )
-        {
-            if( ( qcost * 7 ) >> 3 > thresh_io ) early = true;
-            else if( qcost < thresh_io ) thresh_io = qcost;
-        }
-        if( !early )
-        {
-            if( subpel != 1 )
-            {
-                int bdir = -1;
-                for( int i = qpel_iters; i > 0; i-- )
-                {
-                    if( qy <= m.min_spel_y || qy >= m.max_spel_y || qx <= m.min_spel_x || qx >= m.max_spel_x )
-                        break;
-                    const int odir = bdir;
-                    const int d = diamond( 1, true, odir >= 0 ? ( odir ^ 1 ) : -1 );
-                    if( d < 0 )
-                        break;
-                    bdir = d;
-                }
-            }
-        }
+        me_refine_subpel<BW, BH>( m, subpel, hpel_iters, qpel_iters, false, thresh_io, qx, qy, qcost );
     }
     out_mvx = qx; out_mvy = qy; out_cost = qcost;
     out_cost_mv = __ldg( g.cost_mv + ( qx - mvpx ) ) + __ldg( g.cost_mv + ( qy - mvpy ) );
