@@ -368,7 +368,7 @@ __device__ __forceinline__ void me_warp_setup( MeWarp<BW, BH> &m, const MeShared
 
 // refine_subpel( h, m, hpel_iters, qpel_iters, p_halfpel_thresh, b_refine_qpel ), me.c:865-992, from (qx, qy, qcost)
 template <int BW, int BH>
-__device__ void me_refine_subpel( MeWarp<BW, BH> &m, int subpel, int hpel_iters, int qpel_iters, bool b_refine_qpel, int &thresh_io,
+__device__ __forceinline__ void me_refine_subpel( MeWarp<BW, BH> &m, int subpel, int hpel_iters, int qpel_iters, bool b_refine_qpel, int &thresh_io,
                                   int &qx, int &qy, int &qcost )
 {
     using M = MeWarp<BW, BH>;
