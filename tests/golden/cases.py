@@ -133,6 +133,32 @@ def bidir_case(ci):
     return fenc_l, ref0_l, ref1_l, jobs
 
 
+# ---- x264_me_refine_qpel / x264_me_refine_qpel_refdupe (encoder/me.c:800-814) ------------------------------------------------
+REFINE_CASES = [(0, 1, 5, (0, 0, 0, 0)), (0, 0, 1, (0, 0, 0, 0)), (1, 1, 7, (1, 66, 6, -2)), (1, 1, 9, (0, 0, 0, 0))]   # (refdupe, satd, subme, weight)
+REFINE_JOBS = 50
+
+
+def refine_case(ci):
+    rng = np.random.default_rng(70 + ci)
+    fenc_l, ref_l = me_content(40 + ci)
+    jobs = []
+    for _ in range(REFINE_JOBS):
+        ip = int(rng.integers(0, 7))
+        bw, bh = PIXEL_W[ip], PIXEL_H[ip]
+        bx = int(rng.integers(0, (ME_W - bw) // 4 + 1)) * 4
+        by = int(rng.integers(0, (ME_H - bh) // 4 + 1)) * 4
+        mvr = 4 * ME_MV_RANGE
+        lim_min = [max(4 * (-bx - 24), -mvr), max(4 * (-by - 24), -mvr)]
+        lim_max = [min(4 * (ME_W - bx - bw + 24), mvr - 1), min(4 * (ME_H - by - bh + 24), mvr - 1)]
+        spread = int(rng.choice([4, 20, 90]))
+        mv = np.clip(rng.integers(-spread, spread + 1, 2), lim_min, lim_max)
+        mvp = mv + rng.integers(-6, 7, 2)
+        use_thresh = bool(REFINE_CASES[ci][0] and rng.random() < 0.4)
+        jobs.append(dict(ip=ip, bx=bx, by=by, lim_min=lim_min, lim_max=lim_max, mv=[int(mv[0]), int(mv[1])], mvp=[int(mvp[0]), int(mvp[1])],
+                         cost=int(rng.integers(50, 6000)), ref_cost=int(rng.integers(0, 5)), use_thresh=use_thresh, thresh=int(rng.integers(50, 6000))))
+    return fenc_l, ref_l, jobs
+
+
 # ---- slicetype_frame_cost (encoder/slicetype.c:836-995) --------------------------------------------------------------
 LA_CASES = [  # (preset, reference option string, (w, h)) ; the GPU / oracle parameters are stored in the fixture
     ("medium", "weightp=0:bframes=3", (112, 80)),

@@ -27,6 +27,8 @@ def main():
     out["hpel"], out["hpel_in"] = R.run_hpel("ref")
     for gi in range(len(G.ME_GROUPS)):
         out["me_%d" % gi], out["me_%d_in" % gi] = R.run_me("ref", gi)
+    for ci in range(len(G.REFINE_CASES)):
+        out["refine_%d" % ci], out["refine_%d_in" % ci] = R.run_refine("ref", ci)
     for ci in range(len(G.BIDIR_CASES)):
         out["bidir_%d" % ci], out["bidir_%d_in" % ci] = R.run_bidir("ref", ci)
     for ci in range(len(G.LA_CASES)):

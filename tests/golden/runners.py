@@ -207,6 +207,82 @@ def run_me(backend, gi, ctx=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def run_refine(backend, ci, ctx=None):
+    """-> int32 [REFINE_JOBS, 4] = (mvx, mvy, cost, half-pel threshold after the call or -1) of x264_me_refine_qpel(_refdupe)"""
+    _libs._bind_me()
+    refdupe, satd, subpel, wt = G.REFINE_CASES[ci]
+    fenc_l, ref_l, jobs = G.refine_case(ci)
+    planes = make_ref_planes(np.ascontiguousarray(ref_l))
+    st = planes[0].stride
+    fenc = PaddedPlane(G.ME_W, G.ME_H, stride=st)
+    fenc.inner()[:] = fenc_l
+    dig = G.digest(fenc.buf, *[p.buf for p in planes])
+    out = np.zeros((len(jobs), 4), np.int32)
+    n = 2 * 4 * G.ME_MV_RANGE
+    if backend == "ref":
+        r = ref()
+        r.xref_me_refine_qpel.argtypes = [C.c_void_p, C.POINTER(XrefMeArgs), C.c_int, C.c_int, C.c_void_p, C.c_ssize_t] + [C.c_void_p] * 4 + [C.c_ssize_t]
+        r.xref_me_refine_qpel.restype = None
+        hnd = r.xref_open(G.ME_W, G.ME_H, b"medium", b"subme=7" if satd else b"subme=1", 0)
+        assert hnd
+        for k, j in enumerate(jobs):
+            off = planes[0].off(j["bx"], j["by"])
+            a = XrefMeArgs()
+            a.i_pixel, a.me_method, a.subpel_refine, a.me_range, a.qp = j["ip"], 1, subpel, 16, 12
+            for i in range(2):
+                a.mv_min_spel[i], a.mv_max_spel[i], a.mvp[i], a.mv[i] = j["lim_min"][i], j["lim_max"][i], j["mvp"][i], j["mv"][i]
+            a.cost = j["cost"]
+            a.wt_en, a.wt_scale, a.wt_denom, a.wt_offset = wt
+            a.use_thresh, a.halfpel_thresh = int(j["use_thresh"]), j["thresh"]
+            r.xref_me_refine_qpel(hnd, C.byref(a), refdupe, j["ref_cost"], ptr(fenc.buf, fenc.off(j["bx"], j["by"])), st, *[ptr(p.buf, off) for p in planes], st)
+            out[k] = (a.mv[0], a.mv[1], a.cost, a.thresh_out if j["use_thresh"] else -1)
+        r.xref_close(hnd)
+    elif backend == "oracle":
+        o = oracle()
+        o.orc_me_refine_qpel.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        o.orc_me_refine_qpel.restype = None
+        tab = np.zeros(2 * n + 1, np.uint16)
+        o.orc_cost_mv_table(tab, n, 1)
+        for k, j in enumerate(jobs):
+            off = planes[0].off(j["bx"], j["by"])
+            c = OrcMeCtx()
+            c.me_method, c.subpel_refine, c.me_range, c.mbcmp_is_satd = 1, subpel, 16, satd
+            for i in range(2):
+                c.mv_min_spel[i], c.mv_max_spel[i] = j["lim_min"][i], j["lim_max"][i]
+            m = OrcMe()
+            m.i_pixel = j["ip"]
+            m.p_cost_mv = tab.ctypes.data + 2 * n
+            for i in range(4):
+                m.p_fref[i] = planes[i].buf.ctypes.data + off
+            m.p_fref_w = planes[0].buf.ctypes.data + off
+            m.p_fenc = fenc.buf.ctypes.data + fenc.off(j["bx"], j["by"])
+            m.fenc_stride, m.stride = st, st
+            m.weight = OrcWeight(*wt)
+            m.mvp[0], m.mvp[1], m.mv[0], m.mv[1], m.cost = j["mvp"][0], j["mvp"][1], j["mv"][0], j["mv"][1], j["cost"]
+            th = C.c_int(j["thresh"])
+            o.orc_me_refine_qpel(C.byref(c), C.byref(m), refdupe, j["ref_cost"], C.byref(th) if j["use_thresh"] else None)
+            out[k] = (m.mv[0], m.mv[1], m.cost, th.value if j["use_thresh"] else -1)
+    else:
+        import x264_b200 as x
+        ja = np.zeros(len(jobs), x.me_refine_job_dtype)
+        for k, j in enumerate(jobs):
+            e = ja[k]
+            e["i_pixel"], e["fenc_off"], e["ref_off"] = j["ip"], fenc.off(j["bx"], j["by"]), planes[0].off(j["bx"], j["by"])
+            e["mvp"], e["mv"], e["cost"], e["i_ref_cost"] = j["mvp"], j["mv"], j["cost"], j["ref_cost"]
+            e["mv_min_spel"], e["mv_max_spel"] = j["lim_min"], j["lim_max"]
+            e["halfpel_thresh"] = j["thresh"] if j["use_thresh"] else -1
+        d_fenc = ctx.upload(fenc.buf)
+        d_pl = [ctx.upload(p.buf) for p in planes]
+        params = x.MeParams(1, subpel, 16, satd, 1, G.ME_MV_RANGE, *wt)
+        res = x.me_refine_qpel_batch(ctx, params, refdupe, d_fenc, st, d_pl, st, ja)
+        for p in [d_fenc] + d_pl:
+            ctx.free(p)
+        out[:, 0], out[:, 1], out[:, 2] = res["mv"][:, 0], res["mv"][:, 1], res["cost"]
+        out[:, 3] = [int(res[k]["halfpel_thresh"]) if jobs[k]["use_thresh"] else -1 for k in range(len(jobs))]
+    return out, dig
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def run_bidir(backend, ci, ctx=None):
     """-> int16 [BIDIR_JOBS, 4] = the refined (m0x, m0y, m1x, m1y) of x264_me_refine_bidir_satd"""
     _libs._bind_me()

@@ -60,6 +60,15 @@ def test_me_search(request, backend, gi):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("ci", range(len(G.REFINE_CASES)))
+def test_me_refine_qpel(request, backend, ci):
+    got, dig = R.run_refine(backend, ci, _ctx(request, backend))
+    _check_inputs("refine_%d" % ci, dig)
+    want = GOLD["refine_%d" % ci]
+    assert np.array_equal(got, want), (G.REFINE_CASES[ci], np.argwhere(got != want)[:5])
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("ci", range(len(G.BIDIR_CASES)))
 def test_me_refine_bidir(request, backend, ci):
     got, dig = R.run_bidir(backend, ci, _ctx(request, backend))
