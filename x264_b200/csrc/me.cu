@@ -15,16 +15,17 @@ struct MeJob                                    // == x264cu_me_job_t
 struct MeResult { int16_t mv[2]; int32_t cost, cost_mv, halfpel_thresh; };
 static_assert( sizeof( MeJob ) == sizeof( x264cu_me_job_t ) && sizeof( MeResult ) == sizeof( x264cu_me_result_t ), "ABI structs" );
 
-template <int BW, int BH>
+template <int BW, int BH, bool EXH>
 __device__ __noinline__ void run_job( const MeShared &g, const MeJob &j, int lane, MeResult &r, uint2 *tesa_list )
 {
     int mvx, mvy, cost, cost_mv, thresh = j.halfpel_thresh;
     int16_t lim[4] = { j.mv_min_spel[0], j.mv_min_spel[1], j.mv_max_spel[0], j.mv_max_spel[1] };
-    me_search_generic<BW, BH>( g, j.i_pixel, j.fenc_off, j.ref_off, j.mvp[0], j.mvp[1], &j.mvc[0][0], j.i_mvc, lim, thresh, lane,
+    me_search_generic<BW, BH, EXH>( g, j.i_pixel, j.fenc_off, j.ref_off, j.mvp[0], j.mvp[1], &j.mvc[0][0], j.i_mvc, lim, thresh, lane,
                                mvx, mvy, cost, cost_mv, tesa_list );
     r.mv[0] = (int16_t)mvx; r.mv[1] = (int16_t)mvy; r.cost = cost; r.cost_mv = cost_mv; r.halfpel_thresh = thresh;
 }
 
+template <bool EXH>
 __global__ void __launch_bounds__( 128 )
 me_search_kernel( MeShared g, const MeJob *__restrict__ jobs, int n, MeResult *__restrict__ results )
 {
@@ -37,13 +38,13 @@ me_search_kernel( MeShared g, const MeJob *__restrict__ jobs, int n, MeResult *_
         MeResult r;
         switch( j.i_pixel )
         {
-            case X264CU_PIXEL_16x16: run_job<16, 16>( g, j, lane, r, tesa_list ); break;
-            case X264CU_PIXEL_16x8:  run_job<16, 8>( g, j, lane, r, tesa_list ); break;
-            case X264CU_PIXEL_8x16:  run_job<8, 16>( g, j, lane, r, tesa_list ); break;
-            case X264CU_PIXEL_8x8:   run_job<8, 8>( g, j, lane, r, tesa_list ); break;
-            case X264CU_PIXEL_8x4:   run_job<8, 4>( g, j, lane, r, tesa_list ); break;
-            case X264CU_PIXEL_4x8:   run_job<4, 8>( g, j, lane, r, tesa_list ); break;
-            default:                 run_job<4, 4>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_16x16: run_job<16, 16, EXH>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_16x8:  run_job<16, 8, EXH>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_8x16:  run_job<8, 16, EXH>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_8x8:   run_job<8, 8, EXH>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_8x4:   run_job<8, 4, EXH>( g, j, lane, r, tesa_list ); break;
+            case X264CU_PIXEL_4x8:   run_job<4, 8, EXH>( g, j, lane, r, tesa_list ); break;
+            default:                 run_job<4, 4, EXH>( g, j, lane, r, tesa_list ); break;
         }
         if( lane == 0 ) results[w] = r;
     }
@@ -117,7 +118,10 @@ extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params
         g.tesa_list = (uint2 *)x264cu_scratch( ctx, 9, (size_t)blocks * per_block );
         if( !g.tesa_list ) return -1;
     }
-    me_search_kernel<<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, (const MeJob *)d_jobs, n, (MeResult *)d_results );
+    if( p->me_method >= X264CU_ME_ESA )
+        me_search_kernel<true><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, (const MeJob *)d_jobs, n, (MeResult *)d_results );
+    else
+        me_search_kernel<false><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, (const MeJob *)d_jobs, n, (MeResult *)d_results );
     CU_LAUNCH_CHECK( ctx );
     return 0;
 }

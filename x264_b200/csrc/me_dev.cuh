@@ -438,7 +438,9 @@ __device__ __forceinline__ void me_refine_subpel( MeWarp<BW, BH> &m, int subpel,
 }
 
 // mvc: up to 8 candidate vectors; thresh_io: half-pel early-termination threshold (< 0 = none)
-template <int BW, int BH>
+// EXH: the exhaustive searches (ESA / TESA) are compiled in; the kernel of the other methods is built without them (their
+// candidate-list code costs it 48 registers: 1.40 -> 1.61 ms per 4K picture of UMH merange-64 searches)
+template <int BW, int BH, bool EXH>
 __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc_off, uint32_t ref_off, int mvpx, int mvpy,
                                    const int16_t *mvc, int i_mvc, const int16_t *limits /* min_x,min_y,max_x,max_y spel */,
                                    int &thresh_io, int lane, int &out_mvx, int &out_mvy, int &out_cost, int &out_cost_mv, uint2 *tesa_list )
@@ -571,9 +573,9 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
     }
     else if( g.me_method == X264CU_ME_HEX )
         m.hex_refine( me_range );
-    else if( g.me_method == X264CU_ME_ESA )
+    else if( EXH && g.me_method == X264CU_ME_ESA )
         m.esa( me_range );
-    else if( g.me_method == X264CU_ME_TESA )
+    else if( EXH && g.me_method == X264CU_ME_TESA )
         m.tesa( me_range, tesa_list );
     else
     {   // UMH, me.c:422-616
