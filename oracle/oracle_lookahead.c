@@ -211,11 +211,12 @@ static void pred8x8_dir( uint8_t *s, const edge_t *e, int mode )
                      * then along the top (predict.c:824-851) */
             {
                 int i = 2*( 7 - y ) + x;
-                if( i < 16 )
+                if( i == 15 )
+                    v = F2( EL(e,0), ET(e,-1), ET(e,0) );
+                else if( i < 16 )
                 {
                     int k = 6 - ( i >> 1 );                  /* pair k uses l[k], l[k+1] (k = -1 is the corner) */
                     v = ( i & 1 ) ? F2( EL(e,k-1), EL(e,k), EL(e,k+1) ) : F1( EL(e,k), EL(e,k+1) );
-                    if( i == 15 ) v = F2( EL(e,0), ET(e,-1), ET(e,0) );
                 }
                 else
                 {
