@@ -16,8 +16,6 @@ namespace {
 __constant__ float c_aq_log2_lut[128];       // x264_log2_lut (common/tables.c:66-85)
 __constant__ uint8_t c_aq_exp2_lut[64];      // x264_exp2_lut (common/tables.c:58-64)
 
-__device__ __forceinline__ int clampi( int v, int lo, int hi ) { return min( max( v, lo ), hi ); }
-
 __global__ void __launch_bounds__( 256 )
 aq_kernel( const uint8_t *__restrict__ luma, intptr_t stride, const uint8_t *__restrict__ cb, const uint8_t *__restrict__ cr,
            intptr_t cstride, int width, int height, int mb_w, int mb_count, int active, int aq_mode, float strength,

@@ -14,20 +14,6 @@ __device__ __forceinline__ int clampi( int v, int lo, int hi ) { return min( max
 // ------------------------------------------------------------------------------------------------
 // lowres: thread = 4 horizontally adjacent output pixels of all four planes
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t filt4( const int *r0, const int *r1, int o )
-{
-    // FILTER(a,b,c,d) = ((((a+b+1)>>1)+((c+d+1)>>1)+1)>>1) with a,b vertical pair at x, c,d at x+1 (mc.c:494-500)
-    uint32_t out = 0;
-#pragma unroll
-    for( int i = 0; i < 4; i++ )
-    {
-        int a = r0[2*i+o], b = r1[2*i+o], c = r0[2*i+1+o], d = r1[2*i+1+o];
-        int v = ( ( ( a + b + 1 ) >> 1 ) + ( ( c + d + 1 ) >> 1 ) + 1 ) >> 1;
-        out |= (uint32_t)v << ( 8*i );
-    }
-    return out;
-}
-
 __global__ void __launch_bounds__( 256 )
 lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, int height,
                uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, int wl, int ll, int fast_ok )
