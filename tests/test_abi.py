@@ -46,3 +46,23 @@ def test_open_fails_loudly_without_a_device():
     assert L.x264cu_open(C.byref(h), 0) == -1 and not h.value
     msg = L.x264cu_strerror(None).decode()
     assert "no CPU fallback" in msg or "CUDA" in msg, msg
+
+
+def test_entry_points_reject_null_handles_without_a_device():
+    """every batched / stateful entry point returns -1 for a NULL context or object before touching CUDA (the reference's hooks
+    return -1 and leave the fallback to the caller); nothing here needs a GPU"""
+    import ctypes as C
+    import x264_b200 as x
+    L = x.lib()
+    n = None
+    assert L.x264cu_me_search_batch(n, n, n, 0, n, n, 0, n, 1, n) == -1
+    assert L.x264cu_me_refine_qpel_batch(n, n, 0, n, 0, n, 0, n, 1, n) == -1
+    assert L.x264cu_me_refine_bidir_batch(n, n, n, 0, n, n, 0, n, 1, n) == -1
+    L.x264cu_lookahead_frame_cost_recalculate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    assert L.x264cu_lookahead_frame_cost_recalculate(n, 0, 0, 0, 0, n, n) == -1
+    L.x264cu_slicetype_rc_analyse_slice.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert L.x264cu_slicetype_rc_analyse_slice(n, 0, n, n, n) == -1
+    L.x264cu_slicetype_get_planned.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    assert L.x264cu_slicetype_get_planned(n, 0, n, n, 0) == -1
+    L.x264cu_slicetype_get_qp_offset.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    assert L.x264cu_slicetype_get_qp_offset(n, 0, n) == -1
