@@ -760,7 +760,9 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
 {
     if( !ctx || !p || !out ) return -1;
     *out = NULL;
-    if( ( p->la.vbv && p->intra_refresh ) || p->keyint_max < 1 || p->keyint_min < 1 || p->b_adapt < 0 || p->b_adapt > 2 || p->b_pyramid < 0 || p->b_pyramid > 2 )
+    /* rc.i_lookahead is clipped to X264_LOOKAHEAD_MAX by the reference (encoder.c:1112); the frame lists are sized for it */
+    if( p->rc_lookahead < 0 || p->rc_lookahead > LOOKAHEAD_MAX || p->la.bframes < 0 || p->la.bframes > BFRAME_MAX ||
+        ( p->la.vbv && p->intra_refresh ) || p->keyint_max < 1 || p->keyint_min < 1 || p->b_adapt < 0 || p->b_adapt > 2 || p->b_pyramid < 0 || p->b_pyramid > 2 )
         return -1;
     x264cu_slicetype_t *s = calloc( 1, sizeof( *s ) );
     if( !s ) return -1;
