@@ -706,7 +706,7 @@ void orc_la_frame_get_mbtree( orc_la_frame_t *f, int what, int i, void *out )
     }
 }
 
-static void clip_add( uint16_t *s, int x ) { int v = *s + x; *s = v > 65535 ? 65535 : v; }       /* MC_CLIP_ADD, mc.h */
+static void clip_add( uint16_t *s, int x ) { int v = *s + x; *s = v > 32767 ? 32767 : v; }       /* MC_CLIP_ADD, common/mc.h:29: (1<<15)-1 */
 
 void orc_la_mbtree_propagate( const orc_la_params_t *p, orc_la_frame_t **frames, int p0, int p1, int b, int referenced, float fps_factor )
 {

@@ -28,12 +28,16 @@ REPLAY = [
     (112, 80, 3, 0, 0, [T_B, T_B, T_P, T_B, T_P], False),
     (112, 80, 3, -1, 1, [T_P, T_B, T_BREF, T_B, T_P], True),
     (352, 288, 2, 1, 1, [T_B, T_P, T_B, T_B, T_P], False),
+    # static content, long chain: i_propagate_cost saturates at MC_CLIP_ADD's (1<<15)-1 (common/mc.h:29); wp = "static" marker
+    (112, 80, 2, "static", 0, [T_P, T_B, T_P] * 12, False),
 ]
 
 
 @pytest.mark.parametrize("cfg", REPLAY)
 def test_mbtree_replay_matches_oracle(ctx, cfg):
     w, h, bframes, wp, aq_on, types, b_pyramid = cfg
+    static = wp == "static"
+    wp = 0 if static else wp
     o = oracle()
     p = OrcLaParams()
     p.width, p.height, p.mb_width, p.mb_height = w, h, (w + 15) // 16, (h + 15) // 16
@@ -41,6 +45,9 @@ def test_mbtree_replay_matches_oracle(ctx, cfg):
     p.bframes, p.bframe_bias, p.weighted_bipred, p.aq_mode, p.vbv, p.do_edges, p.weighted_pred = bframes, 0, 1, aq_on, 0, 1, wp
     nfr = len(types) + 1
     frames = synth_sequence(w, h, nfr, seed=w + 7, cut_at=None)
+    if static:
+        noise = np.random.default_rng(11)
+        frames = [np.clip(frames[0].astype(np.int16) + noise.integers(-1, 2, frames[0].shape), 0, 255).astype(np.uint8) for _ in frames]
     if wp:
         frames = [np.clip(f.astype(np.float32) * (0.55 + 0.09 * i) + 3 * i, 0, 255).astype(np.uint8) for i, f in enumerate(frames)]
     n = 2 * 4 * p.mv_range
@@ -90,13 +97,16 @@ def test_mbtree_replay_matches_oracle(ctx, cfg):
                 prev = k
         touched = replay_macroblock_tree(all_types, b_pyramid, cost, reset, propagate, finish)
         seen = False
+        peak = 0
         for k in sorted(touched):
             want = np.zeros(nmb, np.uint16)
             o.orc_la_frame_get_mbtree(ofr[k], 2, 0, ptr(want))
             got = la.get_propagate_cost(k)
             assert np.array_equal(got, want), ("propagate_cost", k, np.argwhere(got != want)[:5])
             seen |= bool(want.any())
+            peak = max(peak, int(got.max()))
         assert seen
+        assert peak == 32767 if static else peak <= 32767
         for k in range(1, nfr):
             want = np.zeros(nmb, np.float32)
             o.orc_la_frame_get_mbtree(ofr[k], 0, 0, ptr(want))

@@ -18,6 +18,8 @@ CASES = [
     ("weightp=0:no-psy=1:bframes=3:aq-mode=0:b-pyramid=none", (112, 80), [T_B, T_B, T_P, T_B, T_P], False),
     ("weightp=0:bframes=3:aq-mode=1", (112, 80), [T_P, T_B, T_BREF, T_B, T_P], True),       # fake weights + pyramid + AQ
     ("weightp=2:bframes=2:aq-mode=1:b-pyramid=none", (96, 64), [T_B, T_P, T_B, T_B, T_P], True),
+    # static content over a long chain: i_propagate_cost reaches MC_CLIP_ADD's ceiling (1<<15)-1 (common/mc.h:29)
+    ("weightp=0:bframes=2:aq-mode=0:b-pyramid=none", (112, 80), [T_P, T_B, T_P] * 12, "static"),
 ]
 
 
@@ -94,7 +96,10 @@ def test_mbtree_matches_reference(case):
         assert p.do_edges
         nfr = len(types) + 1
         frames = synth_sequence(w, h, nfr, seed=w + 7, cut_at=None)
-        if fade:
+        if fade == "static":
+            noise = np.random.default_rng(11)
+            frames = [np.clip(frames[0].astype(np.int16) + noise.integers(-1, 2, frames[0].shape), 0, 255).astype(np.uint8) for _ in frames]
+        elif fade:
             frames = [np.clip(f.astype(np.float32) * (0.55 + 0.09 * i) + 3 * i, 0, 255).astype(np.uint8) for i, f in enumerate(frames)]
         n = 2 * 4 * p.mv_range
         tab = np.zeros(2 * n + 1, np.uint16)
@@ -139,12 +144,14 @@ def test_mbtree_matches_reference(case):
         is_b = lambda t: t in (T_B, T_BREF)
         exact = total = 0
         checked_nonzero = False
+        peak = 0
         for k in range(1, nfr):          # frame 0 (the previous GOP's last non-B) is never touched with b_intra = 0: uninitialised in the reference
             a = np.zeros(nmb, np.uint16); b = np.zeros(nmb, np.uint16)
             r.xref_la_get_mbtree(la, k, 2, 0, ptr(a)); o.orc_la_frame_get_mbtree(ofr[k], 2, 0, ptr(b))
             if k in touched:
                 assert np.array_equal(a, b), ("propagate_cost", k, np.argwhere(a != b)[:5], a[a != b][:5], b[a != b][:5])
                 checked_nonzero |= bool(a.any())
+                peak = max(peak, int(a.max()))
             qa = np.zeros(nmb, np.float32); qb = np.zeros(nmb, np.float32)
             r.xref_la_get_mbtree(la, k, 0, 0, ptr(qa)); o.orc_la_frame_get_mbtree(ofr[k], 0, 0, ptr(qb))
             assert np.allclose(qa, qb, atol=1e-4, rtol=0), ("qp_offset", k, np.abs(qa - qb).max())
@@ -154,6 +161,9 @@ def test_mbtree_matches_reference(case):
                 r.xref_la_get_mbtree(la, k, 3, d, C.byref(wa)); o.orc_la_frame_get_mbtree(ofr[k], 3, d, C.byref(wb))
                 assert wa.value == wb.value, ("weighted_cost_delta", k, d, wa.value, wb.value)
         assert checked_nonzero
+        assert peak <= 32767
+        if fade == "static":
+            assert peak == 32767, "the static case is meant to saturate i_propagate_cost (peak %d)" % peak
         assert exact == total, "f_qp_offset bit-exact on %d of %d macroblocks" % (exact, total)
         # slicetype_frame_cost_recalculate (slicetype.c:999-1024) of every requested cost: MB-tree's offsets for P / I, AQ's for B
         r.xref_la_frame_cost_recalculate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]

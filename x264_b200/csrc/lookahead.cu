@@ -28,6 +28,7 @@ static inline double la_now() { timespec t; clock_gettime( CLOCK_MONOTONIC, &t )
 #define LOWRES_COST_MASK 0x3fff          /* common/frame.h:107-112 */
 #define LOWRES_COST_SHIFT 14
 #define LA_MAX_B ( X264CU_BFRAME_MAX )
+#define LA_PROPAGATE_MAX 32767u          /* MC_CLIP_ADD's ceiling, common/mc.h:29 */
 
 struct LaDims
 {
@@ -51,7 +52,7 @@ struct LaSlotDev
     uint16_t *qscale;                // [mb_count]
     int32_t *row_satds;              // [(B+2)*(B+2)][mb_h]
     unsigned long long *recs;        // [2][B+1][mb_count] (generation << 32 | mv): how the rows of a search hand over vectors
-    unsigned int *propagate;         // [mb_count] i_propagate_cost as a 32-bit accumulator (the reference's u16 saturates: clamped when read)
+    unsigned int *propagate;         // [mb_count] i_propagate_cost as a 32-bit accumulator (the reference's u16 saturates at 32767: clamped when read)
     float *qp_offset, *qp_offset_aq; // [mb_count] f_qp_offset / f_qp_offset_aq
 };
 
@@ -698,8 +699,8 @@ weight_plane_kernel( const uint32_t *__restrict__ src, uint32_t *__restrict__ ds
 // ------------------------------------------------------------------------------------------------
 // MB-tree: macroblock_tree_propagate (slicetype.c:1050-1089) = mbtree_propagate_cost + mbtree_propagate_list
 // (common/mc.c:511-598) and macroblock_tree_finish (slicetype.c:1029-1048), one thread per macroblock.
-// The reference adds into u16 arrays with saturation, MB after MB; every addend is >= 0, so the result is
-// min( sum, 65535 ) whatever the order: here 32-bit atomics, clamped where the value is read.
+// The reference adds into u16 arrays saturating at (1<<15)-1 (MC_CLIP_ADD, common/mc.h:29), MB after MB; every addend is >= 0,
+// so the result is min( sum, 32767 ) whatever the order: here 32-bit atomics, clamped where the value is read.
 // Float expressions are evaluated operation by operation (no FMA contraction) in the reference's order.
 // ------------------------------------------------------------------------------------------------
 struct LaMbtreeArgs
@@ -724,7 +725,7 @@ mbtree_propagate_kernel( LaDims d, LaMbtreeArgs A )
     const int lc = A.lowres_costs[mb];
     const int inter_cost = min( intra_cost, lc & LOWRES_COST_MASK );
     const float propagate_intra = (float)( intra_cost * (int)A.qscale[mb] );
-    const float propagate_in = (float)( A.prop_in ? min( A.prop_in[mb], 65535u ) : 0u );
+    const float propagate_in = (float)( A.prop_in ? min( A.prop_in[mb], LA_PROPAGATE_MAX ) : 0u );
     const float propagate_amount = __fadd_rn( propagate_in, __fmul_rn( propagate_intra, A.fps_factor ) );
     const float num = (float)( intra_cost - inter_cost ), denom = (float)intra_cost;
     const int amount = min( __float2int_rz( __fadd_rn( __fdiv_rn( __fmul_rn( propagate_amount, num ), denom ), 0.5f ) ), 32767 );
@@ -769,7 +770,7 @@ mbtree_finish_kernel( int mb_count, const int32_t *__restrict__ intra, const uin
     if( mb >= mb_count ) return;
     const int intra_cost = ( (int)(uint16_t)intra[mb] * (int)qscale[mb] + 128 ) >> 8;
     if( !intra_cost ) return;
-    const int propagate_cost = (int)( ( min( propagate[mb], 65535u ) * (unsigned)fps_factor + 128u ) >> 8 );
+    const int propagate_cost = (int)( ( min( propagate[mb], LA_PROPAGATE_MAX ) * (unsigned)fps_factor + 128u ) >> 8 );
     // x264_log2( a ) - x264_log2( b ) + weightdelta (base.h:226-230).  The reference is built with -ffast-math (configure:1413),
     // which lets the compiler re-associate the five float terms; this is the association gcc 13 -O3 emits for
     // slicetype.c:1044 (read from the disassembly of the compiled reference): bit-identical to that build,
@@ -1743,7 +1744,7 @@ int x264cu_lookahead_get_propagate_cost( x264cu_lookahead_t *la, int slot, uint1
     std::vector<unsigned int> tmp( la->d.mb_count );
     CU_CHECK( la->ctx, cudaMemcpyAsync( tmp.data(), la->slots[slot].dev.propagate, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->mt_stream ) );
     CU_CHECK( la->ctx, cudaStreamSynchronize( la->mt_stream ) );
-    for( int i = 0; i < la->d.mb_count; i++ ) h_out[i] = (uint16_t)( tmp[i] > 65535u ? 65535u : tmp[i] );
+    for( int i = 0; i < la->d.mb_count; i++ ) h_out[i] = (uint16_t)( tmp[i] > LA_PROPAGATE_MAX ? LA_PROPAGATE_MAX : tmp[i] );
     return 0;
 }
 
