@@ -178,6 +178,7 @@ extern "C" int x264cu_adaptive_quant_frame( x264cu_ctx_t *ctx, const uint8_t *d_
                                             const uint8_t *d_cr, intptr_t chroma_stride, int width, int height, int aq_mode,
                                             float aq_strength, float *d_qp_offset_aq, uint16_t *d_inv_qscale, uint64_t *h_stats )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( !d_luma || !d_cb || !d_cr || !d_qp_offset_aq || !d_inv_qscale || width < 1 || height < 1 )
         return x264cu_fail( ctx, "adaptive_quant_frame: bad arguments" );

@@ -6,7 +6,7 @@
 #include <stdarg.h>
 #include <string.h>
 
-static std::string g_open_error;
+static thread_local std::string g_open_error;    // the reason of this thread's last failed x264cu_open
 
 int x264cu_fail( x264cu_ctx *ctx, const char *fmt, ... )
 {
@@ -120,6 +120,7 @@ void *x264cu_stream( x264cu_ctx_t *ctx ) { return ctx ? (void *)ctx->stream : nu
 
 int x264cu_sync( x264cu_ctx_t *ctx )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
     for( cudaStream_t st : ctx->aux_streams )          // uploads / prefetched searches of the lookahead (x264_opencl_flush)
@@ -129,6 +130,7 @@ int x264cu_sync( x264cu_ctx_t *ctx )
 
 int x264cu_timer_start( x264cu_ctx_t *ctx )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( !ctx->ev0 )
     {
@@ -141,6 +143,7 @@ int x264cu_timer_start( x264cu_ctx_t *ctx )
 
 int x264cu_timer_stop( x264cu_ctx_t *ctx, float *elapsed_ms )
 {
+    X264CU_ENTER( ctx );
     if( !ctx || !ctx->ev0 ) return -1;
     CU_CHECK( ctx, cudaEventRecord( ctx->ev1, ctx->stream ) );
     CU_CHECK( ctx, cudaEventSynchronize( ctx->ev1 ) );
@@ -154,6 +157,7 @@ uint64_t x264cu_launch_count( x264cu_ctx_t *ctx ) { return ctx ? ctx->launches :
 
 void *x264cu_malloc( x264cu_ctx_t *ctx, size_t bytes )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return nullptr;
     void *p = nullptr;
     cudaSetDevice( ctx->device );
@@ -167,11 +171,13 @@ void *x264cu_malloc( x264cu_ctx_t *ctx, size_t bytes )
 
 void x264cu_free( x264cu_ctx_t *ctx, void *p )
 {
+    X264CU_ENTER( ctx );
     if( ctx && p ) { cudaSetDevice( ctx->device ); cudaFree( p ); }
 }
 
 void *x264cu_malloc_host( x264cu_ctx_t *ctx, size_t bytes )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return nullptr;
     void *p = nullptr;
     if( cudaMallocHost( &p, bytes ) != cudaSuccess )
@@ -186,6 +192,7 @@ void x264cu_free_host( x264cu_ctx_t *ctx, void *p ) { if( ctx && p ) cudaFreeHos
 
 int x264cu_memcpy_h2d( x264cu_ctx_t *ctx, void *d, const void *h, size_t bytes )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     CU_CHECK( ctx, cudaMemcpyAsync( d, h, bytes, cudaMemcpyHostToDevice, ctx->stream ) );
     return 0;
@@ -193,6 +200,7 @@ int x264cu_memcpy_h2d( x264cu_ctx_t *ctx, void *d, const void *h, size_t bytes )
 
 int x264cu_memcpy_d2h( x264cu_ctx_t *ctx, void *h, const void *d, size_t bytes )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     CU_CHECK( ctx, cudaMemcpyAsync( h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream ) );
     CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
@@ -201,6 +209,7 @@ int x264cu_memcpy_d2h( x264cu_ctx_t *ctx, void *h, const void *d, size_t bytes )
 
 int x264cu_memset( x264cu_ctx_t *ctx, void *d, int value, size_t bytes )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     CU_CHECK( ctx, cudaMemsetAsync( d, value, bytes, ctx->stream ) );
     return 0;

@@ -41,6 +41,13 @@ int  x264cu_adaptive_quant_frame_on( x264cu_ctx *ctx, cudaStream_t stream, const
                                      const uint8_t *d_cr, intptr_t chroma_stride, int width, int height, int aq_mode, float aq_strength,
                                      float *d_qp_offset_aq, uint16_t *d_inv_qscale, float *d_q4, unsigned long long *d_stats );
 
+// The current device is per-thread state: every public entry point selects its context's device first, so that a context may be
+// used from a thread other than the one that opened it and contexts on different GPUs may live in one process.
+#define X264CU_ENTER( ctx ) do { if( ctx ) cudaSetDevice( ( ctx )->device ); } while( 0 )
+#define X264CU_ENTER_LA( la ) do { if( la ) cudaSetDevice( x264cu_lookahead_ctx( la )->device ); } while( 0 )
+struct x264cu_lookahead;
+x264cu_ctx *x264cu_lookahead_ctx( struct x264cu_lookahead *la );
+
 #define CU_CHECK( ctx, call )                                                                      \
     do {                                                                                           \
         cudaError_t e_ = ( call );                                                                 \

@@ -239,6 +239,7 @@ extern "C" {
 int x264cu_frame_init_lowres( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, int width, int height,
                               uint8_t *const d_lowres[4], intptr_t lowres_stride )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     return x264cu_frame_init_lowres_on( ctx, ctx->stream, d_luma, luma_stride, width, height, d_lowres, lowres_stride );
 }
@@ -246,6 +247,7 @@ int x264cu_frame_init_lowres( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t
 int x264cu_hpel_filter( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, int width, int height,
                         uint8_t *d_h, uint8_t *d_v, uint8_t *d_c, int expand_src )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( width < 1 || height < 1 ) return x264cu_fail( ctx, "hpel_filter: bad size" );
     const bool words = !( ( (uintptr_t)d_src | (uintptr_t)d_h | (uintptr_t)d_v | (uintptr_t)d_c | (uintptr_t)stride ) & 3 ) && !( width & 3 );

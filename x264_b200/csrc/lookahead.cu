@@ -839,8 +839,10 @@ struct LaSlotHost
     bool stats_ready;
     LaWeight weight;                 // fenc->weight[0][0] of the last lookahead analysis
     float weighted_cost_delta[LA_MAX_B + 1];   // f_weighted_cost_delta (slicetype.c:462-463, X264_WEIGHTP_FAKE only)
-    int last_search_ev = -1;         // event (ring index, sequence number) of the last prefetch launch that reads this slot
-    unsigned long long last_search_seq = 0;
+    // event (ring index, sequence number) of the last launch that reads or writes this slot on each of the two search streams
+    // ([0], [1]: they are not ordered against each other) and of the last import on the exchange stream ([2])
+    int last_search_ev[3] = { -1, -1, -1 };
+    unsigned long long last_search_seq[3] = { 0, 0, 0 };
     cudaEvent_t ev_ready = nullptr;  // recorded on the upload stream when the picture's planes / reset arrays are in place
     bool main_waited = true;         // the context's stream has been ordered after ev_ready
     bool xch_dirty = false;
@@ -915,6 +917,7 @@ static int la_stride_lowres( int wl )
 }
 
 extern "C" void x264cu_lookahead_close_internal( x264cu_ctx *ctx ) { (void)ctx; }
+x264cu_ctx *x264cu_lookahead_ctx( x264cu_lookahead *la ) { return la->ctx; }
 
 extern "C" {
 
@@ -972,12 +975,15 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     for( int i = 0; i < 2; i++ )
         if( la->search_streams[i] ) { cudaStreamSynchronize( la->search_streams[i] ); cudaStreamDestroy( la->search_streams[i] ); }
     for( int i = 0; i < la->n_ev; i++ ) cudaEventDestroy( la->ev[i] );
+    for( int i = 0; i < 64; i++ )
+        for( int k = 0; k < 2; k++ ) if( la->tm_ev[i][k] ) cudaEventDestroy( la->tm_ev[i][k] );
     if( la->ev_main ) cudaEventDestroy( la->ev_main );
     delete la;
 }
 
 int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p, x264cu_lookahead_t **out )
 {
+    X264CU_ENTER( ctx );
     if( !ctx || !p || !out ) return -1;
     *out = nullptr;
     if( p->width < 16 || p->height < 16 ) return x264cu_fail( ctx, "lookahead_open: picture %dx%d too small", p->width, p->height );
@@ -1199,9 +1205,12 @@ static int la_put_begin( x264cu_lookahead *la, int slot )
         s.mt_last = 0;
     }
     // a ring entry recorded again since belongs to a launch that had finished by then (search_batch waits before reuse)
-    if( s.last_search_ev >= 0 && la->ev_seq[s.last_search_ev] == s.last_search_seq )
-        CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev[s.last_search_ev], 0 ) );
-    s.last_search_ev = -1;
+    for( int k = 0; k < 3; k++ )
+    {
+        if( s.last_search_ev[k] >= 0 && la->ev_seq[s.last_search_ev[k]] == s.last_search_seq[k] )
+            CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev[s.last_search_ev[k]], 0 ) );
+        s.last_search_ev[k] = -1;
+    }
     return 0;
 }
 
@@ -1256,6 +1265,7 @@ static int la_slot_ready( x264cu_lookahead *la, int slot )
 int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const uint8_t *d_luma, intptr_t luma_stride,
                                        const uint16_t *h_inv_qscale )
 {
+    X264CU_ENTER_LA( la );
     if( !la ) return -1;
     if( slot < 0 || slot >= (int)la->slots.size() ) return x264cu_fail( la->ctx, "frame_put: slot %d out of range", slot );
     // d_luma is complete in the context's stream order (la_put_begin orders the upload stream after that stream)
@@ -1265,6 +1275,7 @@ int x264cu_lookahead_frame_put_device( x264cu_lookahead_t *la, int slot, const u
 
 void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on )
 {
+    X264CU_ENTER_LA( la );
     if( la ) la->async_upload = on <= 0 ? 0 : on == 1 ? 4 : on > LA_ZC_DEPTH ? LA_ZC_DEPTH : on;
 }
 
@@ -1324,12 +1335,14 @@ static int la_put_host( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma,
 int x264cu_lookahead_frame_put( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
                                 const uint16_t *h_inv_qscale )
 {
+    X264CU_ENTER_LA( la );
     return la_put_host( la, slot, h_luma, luma_stride, h_inv_qscale, nullptr, nullptr, 0, 0, 0.f );
 }
 
 int x264cu_lookahead_frame_put_i420( x264cu_lookahead_t *la, int slot, const uint8_t *h_luma, intptr_t luma_stride,
                                      const uint8_t *h_cb, const uint8_t *h_cr, intptr_t chroma_stride, int aq_mode, float aq_strength )
 {
+    X264CU_ENTER_LA( la );
     if( !la || !h_cb || !h_cr ) return -1;
     if( aq_mode < 0 || aq_mode > 3 ) return x264cu_fail( la->ctx, "frame_put_i420: aq-mode %d out of range", aq_mode );
     return la_put_host( la, slot, h_luma, luma_stride, nullptr, h_cb, h_cr, chroma_stride, aq_mode, aq_strength );
@@ -1403,6 +1416,7 @@ static int la_wait_pending( x264cu_lookahead *la, LaSlotHost &s, int list, int d
 
 int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int *fenc, const int *ref, const int *list, const int *dist )
 {
+    X264CU_ENTER_LA( la );
     if( !la ) return -1;
     x264cu_ctx *ctx = la->ctx;
     // everything queued so far on the main stream (lowres planes, vector resets) must be visible to the searches
@@ -1452,7 +1466,7 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
         la->ev_seq[e] = la->ev_seq_next++;
         for( auto &m : marks ) la->slots[m.slot].pending[m.list][m.dm1] = e;
         for( int i = 0; i < n_jobs; i++ )
-            for( int sl : { fenc[i], ref[i] } ) { la->slots[sl].last_search_ev = e; la->slots[sl].last_search_seq = la->ev_seq[e]; }
+            for( int sl : { fenc[i], ref[i] } ) { la->slots[sl].last_search_ev[si] = e; la->slots[sl].last_search_seq[si] = la->ev_seq[e]; }
         la->last_prefetch_ev = e;
         la->last_ev_of[si] = e;
     }
@@ -1461,6 +1475,7 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n_jobs, const int
 
 int x264cu_lookahead_search_stats( x264cu_lookahead_t *la, double *busy_ms, long *launches, long *searches )
 {
+    X264CU_ENTER_LA( la );
     if( !la ) return -1;
     for( int i = 0; i < 64; i++ )
         if( la->tm_live[i] )
@@ -1479,6 +1494,7 @@ int x264cu_lookahead_search_stats( x264cu_lookahead_t *la, double *busy_ms, long
 
 int x264cu_lookahead_join( x264cu_lookahead_t *la )
 {
+    X264CU_ENTER_LA( la );
     if( !la ) return -1;
     for( int i = 0; i < 2; i++ )
         if( la->last_ev_of[i] >= 0 )
@@ -1607,6 +1623,7 @@ static int la_mt_begin( x264cu_lookahead *la )
 /* ---- MB-tree (slicetype.c:1029-1184) ---- */
 int x264cu_lookahead_frame_set_qp_offset_aq( x264cu_lookahead_t *la, int slot, const float *h_aq )
 {
+    X264CU_ENTER_LA( la );
     if( la_check_slot( la, slot ) || la_mt_begin( la ) ) return -1;
     x264cu_ctx *ctx = la->ctx;
     LaSlotHost &s = la->slots[slot];
@@ -1624,6 +1641,7 @@ int x264cu_lookahead_frame_set_qp_offset_aq( x264cu_lookahead_t *la, int slot, c
 
 int x264cu_lookahead_mbtree_reset( x264cu_lookahead_t *la, int slot )
 {
+    X264CU_ENTER_LA( la );
     if( !la ) return -1;
     if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use ) return x264cu_fail( la->ctx, "mbtree_reset: empty slot %d", slot );
     if( la_slot_ready( la, slot ) || la_mt_begin( la ) ) return -1;
@@ -1643,6 +1661,7 @@ int x264cu_lookahead_mbtree_swap( x264cu_lookahead_t *la, int slot_a, int slot_b
 
 int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int referenced, float fps_factor )
 {
+    X264CU_ENTER_LA( la );
     if( !la || !frames ) return -1;
     x264cu_ctx *ctx = la->ctx;
     const LaDims &d = la->d;
@@ -1683,6 +1702,7 @@ int x264cu_lookahead_mbtree_propagate( x264cu_lookahead_t *la, const int *frames
 
 int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_factor, int ref0_distance, float strength )
 {
+    X264CU_ENTER_LA( la );
     if( !la ) return -1;
     x264cu_ctx *ctx = la->ctx;
     if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use ) return x264cu_fail( ctx, "mbtree_finish: empty slot %d", slot );
@@ -1705,6 +1725,7 @@ int x264cu_lookahead_mbtree_finish( x264cu_lookahead_t *la, int slot, int fps_fa
 
 int x264cu_lookahead_frame_cost_recalculate( x264cu_lookahead_t *la, int slot, int dist0, int dist1, int b_type, int *h_score, int32_t *h_row_satd )
 {
+    X264CU_ENTER_LA( la );
     if( !la || !h_score ) return -1;
     x264cu_ctx *ctx = la->ctx;
     const LaDims &d = la->d;
@@ -1732,6 +1753,7 @@ int x264cu_lookahead_frame_cost_recalculate( x264cu_lookahead_t *la, int slot, i
 
 int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *h_qp_offset )
 {
+    X264CU_ENTER_LA( la );
     if( la_check_slot( la, slot ) || la_mt_begin( la ) ) return -1;
     CU_CHECK( la->ctx, cudaMemcpyAsync( h_qp_offset, la->slots[slot].dev.qp_offset, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->mt_stream ) );
     CU_CHECK( la->ctx, cudaStreamSynchronize( la->mt_stream ) );
@@ -1740,6 +1762,7 @@ int x264cu_lookahead_get_qp_offset( x264cu_lookahead_t *la, int slot, float *h_q
 
 int x264cu_lookahead_get_propagate_cost( x264cu_lookahead_t *la, int slot, uint16_t *h_out )
 {
+    X264CU_ENTER_LA( la );
     if( la_check_slot( la, slot ) || la_mt_begin( la ) ) return -1;
     std::vector<unsigned int> tmp( la->d.mb_count );
     CU_CHECK( la->ctx, cudaMemcpyAsync( tmp.data(), la->slots[slot].dev.propagate, (size_t)la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->mt_stream ) );
@@ -1750,6 +1773,7 @@ int x264cu_lookahead_get_propagate_cost( x264cu_lookahead_t *la, int slot, uint1
 
 float x264cu_lookahead_get_weighted_cost_delta( x264cu_lookahead_t *la, int slot, int dist_minus1 )
 {
+    X264CU_ENTER_LA( la );
     if( !la || slot < 0 || slot >= (int)la->slots.size() || dist_minus1 < 0 || dist_minus1 > la->d.B ) return -1.0f;
     return la->slots[slot].weighted_cost_delta[dist_minus1];
 }
@@ -1761,6 +1785,7 @@ void *x264cu_lookahead_exchange_stream( x264cu_lookahead_t *la ) { return la ? (
 
 static int la_xch_args( x264cu_lookahead *la, int slot, int list, int dist, const char *who )
 {
+    X264CU_ENTER_LA( la );
     if( slot < 0 || slot >= (int)la->slots.size() || !la->slots[slot].in_use || list < 0 || list > 1 || dist < 1 || dist > la->d.B + 1 ||
         ( list == 1 && !la->d.B ) )
         return x264cu_fail( la->ctx, "%s: bad search (slot %d, list %d, distance %d)", who, slot, list, dist );
@@ -1769,6 +1794,7 @@ static int la_xch_args( x264cu_lookahead *la, int slot, int list, int dist, cons
 
 int x264cu_lookahead_export_search( x264cu_lookahead_t *la, int slot, int list, int dist, void *d_dst )
 {
+    X264CU_ENTER_LA( la );
     if( !la || !d_dst ) return -1;
     if( la_xch_args( la, slot, list, dist, "export_search" ) ) return -1;
     x264cu_ctx *ctx = la->ctx;
@@ -1786,6 +1812,7 @@ int x264cu_lookahead_export_search( x264cu_lookahead_t *la, int slot, int list, 
 
 int x264cu_lookahead_import_search( x264cu_lookahead_t *la, int slot, int list, int dist, const void *d_src )
 {
+    X264CU_ENTER_LA( la );
     if( !la || !d_src ) return -1;
     if( la_xch_args( la, slot, list, dist, "import_search" ) ) return -1;
     x264cu_ctx *ctx = la->ctx;
@@ -1817,7 +1844,7 @@ int x264cu_lookahead_import_done( x264cu_lookahead_t *la )
     {
         LaSlotHost &s = la->slots[m.slot];
         s.pending[m.list][m.dm1] = e;
-        s.last_search_ev = e; s.last_search_seq = la->ev_seq[e];
+        s.last_search_ev[2] = e; s.last_search_seq[2] = la->ev_seq[e];
     }
     la->xch_marks.clear();
     return 0;
@@ -1825,6 +1852,7 @@ int x264cu_lookahead_import_done( x264cu_lookahead_t *la )
 
 int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int fenc_slot, int ref_slot )
 {
+    X264CU_ENTER_LA( la );
     if( !la ) return -1;
     if( !la->p.weighted_pred ) return 1;
     for( int s : { fenc_slot, ref_slot } )
@@ -1844,6 +1872,7 @@ int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int fenc_slot, int 
 
 int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
 {
+    X264CU_ENTER_LA( la );
     if( !la || !frames || !score ) return -1;
     x264cu_ctx *ctx = la->ctx;
     const LaDims &d = la->d;
@@ -1985,6 +2014,7 @@ static int la_check_slot( x264cu_lookahead *la, int slot )
 
 int x264cu_lookahead_get_mvs( x264cu_lookahead_t *la, int slot, int list, int dist_minus1, int16_t *h_mvs, int32_t *h_mv_costs )
 {
+    X264CU_ENTER_LA( la );
     if( la_check_slot( la, slot ) ) return -1;
     const LaDims &d = la->d;
     if( list < 0 || list > 1 || dist_minus1 < 0 || dist_minus1 > d.B ) return x264cu_fail( la->ctx, "get_mvs: bad index" );
@@ -2008,6 +2038,7 @@ int x264cu_lookahead_get_weight( x264cu_lookahead_t *la, int slot, int *out4 )
 
 int x264cu_lookahead_get_costs( x264cu_lookahead_t *la, int slot, int i0, int i1, uint16_t *h_out )
 {
+    X264CU_ENTER_LA( la );
     if( la_check_slot( la, slot ) ) return -1;
     const LaDims &d = la->d;
     if( i0 < 0 || i1 < 0 || i0 > d.B + 1 || i1 > d.B + 1 ) return x264cu_fail( la->ctx, "get_costs: bad index" );
@@ -2018,6 +2049,7 @@ int x264cu_lookahead_get_costs( x264cu_lookahead_t *la, int slot, int i0, int i1
 
 int x264cu_lookahead_get_intra( x264cu_lookahead_t *la, int slot, int32_t *h_out )
 {
+    X264CU_ENTER_LA( la );
     if( la_check_slot( la, slot ) ) return -1;
     CU_CHECK( la->ctx, cudaMemcpyAsync( h_out, la->slots[slot].dev.intra, la->d.mb_count * 4, cudaMemcpyDeviceToHost, la->ctx->stream ) );
     CU_CHECK( la->ctx, cudaStreamSynchronize( la->ctx->stream ) );
@@ -2026,6 +2058,7 @@ int x264cu_lookahead_get_intra( x264cu_lookahead_t *la, int slot, int32_t *h_out
 
 int x264cu_lookahead_get_row_satds( x264cu_lookahead_t *la, int slot, int i0, int i1, int32_t *h_rows )
 {
+    X264CU_ENTER_LA( la );
     if( la_check_slot( la, slot ) ) return -1;
     const LaDims &d = la->d;
     if( i0 < 0 || i1 < 0 || i0 > d.B + 1 || i1 > d.B + 1 ) return x264cu_fail( la->ctx, "get_row_satds: bad index" );
@@ -2051,6 +2084,7 @@ int x264cu_lookahead_get_cost_est( x264cu_lookahead_t *la, int slot, int i0, int
 
 int x264cu_lookahead_get_lowres_plane( x264cu_lookahead_t *la, int slot, int plane, uint8_t *h_out, intptr_t *stride )
 {
+    X264CU_ENTER_LA( la );
     if( la_check_slot( la, slot ) ) return -1;
     if( plane < 0 || plane > 3 ) return x264cu_fail( la->ctx, "get_lowres_plane: bad plane" );
     const LaDims &d = la->d;

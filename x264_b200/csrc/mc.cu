@@ -132,6 +132,7 @@ extern "C" {
 int x264cu_mc_luma_batch( x264cu_ctx_t *ctx, const uint8_t *const d_src[4], intptr_t src_stride, int i_pixel,
                           const x264cu_mc_job_t *d_jobs, int n, const int weight[4], uint8_t *d_dst )
 {
+    X264CU_ENTER( ctx );
     static const int W[8] = { 16, 16, 8, 8, 8, 4, 4, 4 }, H[8] = { 16, 8, 16, 8, 4, 8, 4, 16 };
     if( !ctx ) return -1;
     if( i_pixel < 0 || i_pixel >= X264CU_PIXEL_NB ) return x264cu_fail( ctx, "mc_luma_batch: bad i_pixel %d", i_pixel );
@@ -151,6 +152,7 @@ int x264cu_mc_luma_batch( x264cu_ctx_t *ctx, const uint8_t *const d_src[4], intp
 
 int x264cu_pixel_avg_batch( x264cu_ctx_t *ctx, int i_pixel, const uint8_t *d_a, const uint8_t *d_b, int n, int weight, uint8_t *d_dst )
 {
+    X264CU_ENTER( ctx );
     static const int W[8] = { 16, 16, 8, 8, 8, 4, 4, 4 }, H[8] = { 16, 8, 16, 8, 4, 8, 4, 16 };
     if( !ctx ) return -1;
     if( i_pixel < 0 || i_pixel >= X264CU_PIXEL_NB ) return x264cu_fail( ctx, "pixel_avg_batch: bad i_pixel %d", i_pixel );
@@ -167,6 +169,7 @@ int x264cu_pixel_avg_batch( x264cu_ctx_t *ctx, int i_pixel, const uint8_t *d_a, 
 int x264cu_weight_scale_plane( x264cu_ctx_t *ctx, const uint8_t *d_src, uint8_t *d_dst, intptr_t stride, int width, int height,
                                const int weight[4] )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( !d_src || !d_dst || !weight || width < 1 || height < 1 ) return x264cu_fail( ctx, "weight_scale_plane: bad arguments" );
     LaWeight w = { 1, weight[1], weight[2], weight[3] };
@@ -178,6 +181,7 @@ int x264cu_weight_scale_plane( x264cu_ctx_t *ctx, const uint8_t *d_src, uint8_t 
 int x264cu_pixel_ssd_wxh( x264cu_ctx_t *ctx, const uint8_t *d_pix1, intptr_t stride1, const uint8_t *d_pix2, intptr_t stride2,
                           int width, int height, uint64_t *h_ssd )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( !d_pix1 || !d_pix2 || !h_ssd || width < 0 || height < 0 ) return x264cu_fail( ctx, "pixel_ssd_wxh: bad arguments" );
     *h_ssd = 0;

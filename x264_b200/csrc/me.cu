@@ -83,8 +83,11 @@ extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params
                                        const uint8_t *const d_fref[4], const uint8_t *d_fref_w, intptr_t ref_stride,
                                        const x264cu_me_job_t *d_jobs, int n, x264cu_me_result_t *d_results )
 {
+    X264CU_ENTER( ctx );
     if( !ctx || !p ) return -1;
     if( n <= 0 ) return 0;
+    if( !d_fenc || !d_fref || !d_fref[0] || !d_fref[1] || !d_fref[2] || !d_fref[3] || !d_jobs || !d_results )
+        return x264cu_fail( ctx, "me_search_batch: null argument" );
     if( p->me_method < X264CU_ME_DIA || p->me_method > X264CU_ME_TESA )
         return x264cu_fail( ctx, "me_search_batch: unknown method %d", p->me_method );
     if( p->me_method == X264CU_ME_ESA && p->me_range > 120 )
@@ -170,6 +173,7 @@ extern "C" int x264cu_me_refine_bidir_batch( x264cu_ctx_t *ctx, const x264cu_me_
                                              const uint8_t *const d_fref0[4], const uint8_t *const d_fref1[4], intptr_t ref_stride,
                                              const x264cu_bidir_job_t *d_jobs, int n, x264cu_bidir_result_t *d_results )
 {
+    X264CU_ENTER( ctx );
     if( !ctx || !p ) return -1;
     if( n <= 0 ) return 0;
     if( !d_fenc || !d_fref0 || !d_fref1 || !d_jobs || !d_results )
@@ -247,6 +251,7 @@ extern "C" int x264cu_me_refine_qpel_batch( x264cu_ctx_t *ctx, const x264cu_me_p
                                             const uint8_t *const d_fref[4], intptr_t ref_stride,
                                             const x264cu_me_refine_job_t *d_jobs, int n, x264cu_me_result_t *d_results )
 {
+    X264CU_ENTER( ctx );
     if( !ctx || !p ) return -1;
     if( n <= 0 ) return 0;
     if( !d_fenc || !d_fref || !d_jobs || !d_results ) return x264cu_fail( ctx, "me_refine_qpel_batch: null argument" );

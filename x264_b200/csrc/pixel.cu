@@ -490,6 +490,7 @@ extern "C" {
 int x264cu_pixel_cmp_batch( x264cu_ctx_t *ctx, int metric, int i_pixel, const uint8_t *d_fenc, intptr_t fenc_stride,
                             const uint8_t *d_ref, intptr_t ref_stride, const x264cu_cand_t *d_cand, int n, int32_t *d_out )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( n <= 0 ) return 0;
     if( (unsigned)i_pixel >= X264CU_PIXEL_NB ) return x264cu_fail( ctx, "bad block size index %d", i_pixel );
@@ -500,6 +501,7 @@ int x264cu_pixel_cmp_x4_batch( x264cu_ctx_t *ctx, int metric, int i_pixel, int n
                                intptr_t fenc_stride, const uint8_t *d_ref, intptr_t ref_stride,
                                const x264cu_cand_x4_t *d_cand, int n, int32_t *d_out )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( n <= 0 ) return 0;
     if( (unsigned)i_pixel >= X264CU_PIXEL_NB ) return x264cu_fail( ctx, "bad block size index %d", i_pixel );
@@ -516,6 +518,7 @@ int x264cu_pixel_cmp_batch_host( x264cu_ctx_t *ctx, int metric, int i_pixel, con
                                  intptr_t fenc_stride, const uint8_t *h_ref, size_t ref_bytes, intptr_t ref_stride,
                                  const x264cu_cand_t *h_cand, int n, int32_t *h_out )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( n <= 0 ) return 0;
     uint8_t *df = (uint8_t *)x264cu_scratch( ctx, 0, fenc_bytes + 16 );
@@ -535,6 +538,7 @@ int x264cu_pixel_cmp_batch_host( x264cu_ctx_t *ctx, int metric, int i_pixel, con
 int x264cu_pixel_cmp_mvfield( x264cu_ctx_t *ctx, int metric, int i_pixel, const x264cu_planes_t *fenc,
                               const x264cu_planes_t *ref, int k_cands, const int16_t *d_mv, int32_t *d_out )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( !fenc || !ref || k_cands <= 0 ) return x264cu_fail( ctx, "mvfield: bad arguments" );
     if( (unsigned)i_pixel >= X264CU_PIXEL_NB ) return x264cu_fail( ctx, "bad block size index %d", i_pixel );
@@ -576,6 +580,7 @@ int x264cu_pixel_cmp_mvfield_host( x264cu_ctx_t *ctx, int metric, int i_pixel, c
                                    const uint8_t *h_ref_base, intptr_t stride, intptr_t plane_pitch, int width, int height,
                                    int n_planes, int k_cands, const int16_t *h_mv, int32_t *h_out )
 {
+    X264CU_ENTER( ctx );
     if( !ctx ) return -1;
     if( (unsigned)i_pixel >= X264CU_PIXEL_NB ) return x264cu_fail( ctx, "bad block size index %d", i_pixel );
     size_t bytes = (size_t)plane_pitch * n_planes;

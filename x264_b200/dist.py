@@ -33,6 +33,9 @@ class ShardExchange:
             if phase == 0:
                 if self.send is None or self.send.numel() < n:
                     dev = self.device if self.device is not None else "cpu"
+                    if self.send is not None and self.device is not None:
+                        # imports from the old receive buffer may still be in flight on the exchange stream
+                        torch.cuda.ExternalStream(int(stream), device=self.device).synchronize()
                     self.send = torch.zeros(n, dtype=torch.uint8, device=dev)
                     self.recv = torch.zeros(n * self.world, dtype=torch.uint8, device=dev)
                 self.cur = n
