@@ -51,6 +51,9 @@ void orc_pixel_avg( uint8_t *dst, intptr_t sd, const uint8_t *a, intptr_t sa, co
                     int w, int h, int weight );
 void orc_mc_weight( uint8_t *dst, intptr_t sd, const uint8_t *src, intptr_t ss, const orc_weight_t *wt, int w, int h );
 void orc_weight_scale_plane( uint8_t *dst, intptr_t sd, const uint8_t *src, intptr_t ss, int w, int h, const orc_weight_t *wt );
+/* mc_chroma (common/mc.c:251-283) for one component (0 = U, 1 = V) of an NV12 plane; w x h chroma pixels */
+void orc_mc_chroma( uint8_t *dst, intptr_t dst_stride, const uint8_t *src_uv, intptr_t src_stride,
+                    int mvx, int mvy, int w, int h, int comp );
 /* table[0 .. 2*len] with the zero-mvd entry at table[len]; len = 2*4*mv_range */
 void orc_cost_mv_table( uint16_t *table, int len, int lambda );
 
@@ -64,6 +67,7 @@ typedef struct
     int mbcmp_is_satd;      /* encoder.c:1409-1427: mbcmp = SATD iff param subme > 1 */
     int mv_min_spel[2], mv_max_spel[2];     /* h->mb.mv_min_spel / mv_max_spel */
     int mv_limit_fpel[2][2];                /* h->mb.mv_limit_fpel */
+    int chroma_me;          /* h->mb.b_chroma_me (common/macroblock.c:507); 4:2:0, progressive */
 } orc_me_ctx_t;
 
 typedef struct
@@ -80,6 +84,12 @@ typedef struct
     /* out */
     int cost_mv, cost;
     int16_t mv[2];
+    /* chroma ME (c->chroma_me, partitions >= 8x8; me.c:826-857): NV12 planes at the block's chroma origin */
+    const uint8_t *p_fref_uv;      /* m->p_fref[4] */
+    intptr_t stride_uv;            /* m->i_stride[1] */
+    const uint8_t *p_fenc_uv;      /* the source picture's interleaved chroma (the reference reads de-interleaved copies, p_fenc[1..2]) */
+    intptr_t fenc_uv_stride;
+    orc_weight_t weight_uv[2];     /* m->weight[1], m->weight[2] */
 } orc_me_t;
 
 void orc_me_search_ref( const orc_me_ctx_t *c, orc_me_t *m, const int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );

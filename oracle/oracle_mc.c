@@ -126,6 +126,22 @@ void orc_mc_luma( uint8_t *dst, intptr_t dst_stride, const uint8_t *const src[4]
         orc_mc_weight( dst, dst_stride, dst, dst_stride, wt, w, h );
 }
 
+/* common/mc.c:251-283 mc_chroma: one plane (comp 0 = U, 1 = V) of an interleaved NV12 reference at an eighth-pel
+ * chroma vector, bilinear weights (8-dx)(8-dy), dx(8-dy), (8-dx)dy, dx*dy, rounded (+32) >> 6 */
+void orc_mc_chroma( uint8_t *dst, intptr_t dst_stride, const uint8_t *src_uv, intptr_t src_stride,
+                    int mvx, int mvy, int w, int h, int comp )
+{
+    const int dx = mvx & 7, dy = mvy & 7;
+    const int w00 = ( 8 - dx ) * ( 8 - dy ), w01 = dx * ( 8 - dy ), w10 = ( 8 - dx ) * dy, w11 = dx * dy;
+    const uint8_t *row = src_uv + (intptr_t)( mvy >> 3 ) * src_stride + ( mvx >> 3 ) * 2 + comp;
+    for( int y = 0; y < h; y++, row += src_stride )
+        for( int x = 0; x < w; x++ )
+        {
+            const uint8_t *t = row + 2*x, *b = t + src_stride;
+            dst[y*dst_stride + x] = ( w00*t[0] + w01*t[2] + w10*b[0] + w11*b[2] + 32 ) >> 6;
+        }
+}
+
 /* common/mc.c:49-111 pixel_avg_WxH: weight==32 -> rounded mean, else implicit bipred weights */
 void orc_pixel_avg( uint8_t *dst, intptr_t sd, const uint8_t *a, intptr_t sa, const uint8_t *b, intptr_t sb,
                     int w, int h, int weight )

@@ -1,8 +1,8 @@
 /*
  * ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.h).  Scalar restatement of the reference's block-match
  * search: predictor stage, DIA / HEX / UMH integer search and the sub-pel refinement
- * (encoder/me.c:182-798 x264_me_search_ref, :865-992 refine_subpel), luma only (no chroma ME, which the
- * lookahead disables: slicetype.c:60), the exhaustive searches ESA / TESA (me.c:618-771) with their successive-elimination
+ * (encoder/me.c:182-798 x264_me_search_ref, :865-992 refine_subpel) with the chroma branch of the quarter-pel
+ * refinement (me.c:826-857, 4:2:0; the lookahead disables it: slicetype.c:60), the exhaustive searches ESA / TESA (me.c:618-771) with their successive-elimination
  * prefilter, and x264_me_refine_bidir_satd (me.c:1027-1183).  fpelcmp is SAD, except under TESA where it is the same
  * metric as mbcmp (encoder.c:1409-1427); mbcmp is SATD iff the encoder's subme > 1.  Written from the algorithm as a small state machine over one `search_t`;
  * tie-breaking follows the reference's packed (cost<<k)+index comparisons exactly (me.c:325-341, :369-418).
@@ -62,7 +62,25 @@ static int cost_qpel( const search_t *s, int mx, int my, int use_mbcmp )
     orc_mc_luma( blk, 16, m->p_fref, m->stride, mx, my, s->bw, s->bh, &m->weight );
     int d = ( use_mbcmp ? s->c->mbcmp_is_satd : fpel_satd( s ) ) ? orc_satd( m->p_fenc, m->fenc_stride, blk, 16, s->bw, s->bh )
                                                                  : orc_sad ( m->p_fenc, m->fenc_stride, blk, 16, s->bw, s->bh );
-    return d + s->cmx[mx] + s->cmy[my];
+    d += s->cmx[mx] + s->cmy[my];
+    if( use_mbcmp && s->c->chroma_me && m->i_pixel <= ORC_PIXEL_8x8 )
+    {   /* COST_MV_SATD's chroma branch, me.c:826-857 (4:2:0): both planes at the luma vector read in eighth-pels, their explicit
+         * weights, mbcmp of the half-size block.  The reference stops adding once the sum reaches the best cost, which cannot
+         * change what is accepted (partial sums only grow) -- so the whole sum is formed here. */
+        const int cw = s->bw >> 1, ch = s->bh >> 1;
+        for( int comp = 0; comp < 2; comp++ )
+        {
+            uint8_t pred[8*8], src[8*8];
+            orc_mc_chroma( pred, 8, m->p_fref_uv, m->stride_uv, mx, my, cw, ch, comp );
+            if( m->weight_uv[comp].enabled )
+                orc_mc_weight( pred, 8, pred, 8, &m->weight_uv[comp], cw, ch );
+            for( int y = 0; y < ch; y++ )
+                for( int x = 0; x < cw; x++ )
+                    src[y*8 + x] = m->p_fenc_uv[y*m->fenc_uv_stride + 2*x + comp];
+            d += s->c->mbcmp_is_satd ? orc_satd( src, 8, pred, 8, cw, ch ) : orc_sad( src, 8, pred, 8, cw, ch );
+        }
+    }
+    return d;
 }
 
 /* four full-pel candidates around (ox,oy), each a plain strict-less update in order: COST_MV_X4, me.c:100-118 */
@@ -590,8 +608,8 @@ static void refine_subpel( search_t *s, int hpel_iters, int qpel_iters, int *p_h
         }
     }
 
-    if( !b_refine_qpel && c->mbcmp_is_satd && !fpel_satd( s ) )
-    {   /* re-measure the winner with mbcmp (SATD) when the half-pel steps used another metric, me.c:925-929 */
+    if( !b_refine_qpel && ( ( c->mbcmp_is_satd && !fpel_satd( s ) ) || ( c->chroma_me && m->i_pixel <= ORC_PIXEL_8x8 ) ) )
+    {   /* re-measure the winner with mbcmp (SATD) when the half-pel steps used another metric or left the chroma out, me.c:925-929 */
         bcost = cost_qpel( s, bmx, bmy, 1 );
         bdir = -1;
     }

@@ -264,25 +264,54 @@ typedef struct
     int cost, cost_mv, thresh_out;
 } xref_me_args_t;
 
+/* chroma ME (h->mb.b_chroma_me, me.c:826-857): NV12 planes at the block's chroma origin and the weights of the two planes */
+typedef struct
+{
+    uint8_t *fenc_uv; intptr_t fenc_uv_stride;
+    uint8_t *fref_uv; intptr_t fref_uv_stride;
+    int wt[2][4];                      /* m->weight[1], m->weight[2]: enabled, scale, denom, offset */
+} xref_chroma_t;
+
 /* Drives the reference's x264_me_search_ref (encoder/me.c:182) on caller-supplied planes.
  * fref[0..3] = F,H,V,C plane pointers at the block origin, fref_w = weighted full-pel plane (or fref[0]). */
 static void me_search_common( x264_t *h, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
-                              uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride, uint16_t *integral )
+                              uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride, uint16_t *integral,
+                              const xref_chroma_t *ch )
 {
     tables_init();
     ALIGNED_ARRAY_64( pixel, fenc_buf,[16*16] );
+    ALIGNED_ARRAY_64( pixel, fenc_c,[16*8] );          /* U at column 0, V at column 8, FENC_STRIDE: the layout of h->mb.pic.fenc_buf's chroma */
     int bw = x264_pixel_size[a->i_pixel].w, bh = x264_pixel_size[a->i_pixel].h;
     for( int y = 0; y < bh; y++ )
         memcpy( fenc_buf + y*FENC_STRIDE, fenc + y*fenc_stride, bw );
-    x264_weight_t wt; make_weight( &wt, a->wt_en, a->wt_scale, a->wt_denom, a->wt_offset );
-    if( a->wt_en ) wt.weightfn = h->mc.weight;
+    x264_weight_t wt[3];
+    make_weight( &wt[0], a->wt_en, a->wt_scale, a->wt_denom, a->wt_offset );
+    make_weight( &wt[1], 0, 0, 0, 0 ); make_weight( &wt[2], 0, 0, 0, 0 );
+    if( a->wt_en ) wt[0].weightfn = h->mc.weight;
     x264_me_t m;
     memset( &m, 0, sizeof(m) );
+    if( ch )
+    {
+        for( int y = 0; y < bh/2; y++ )
+            for( int x = 0; x < bw/2; x++ )
+            {
+                fenc_c[y*FENC_STRIDE + x]     = ch->fenc_uv[y*ch->fenc_uv_stride + 2*x];
+                fenc_c[y*FENC_STRIDE + 8 + x] = ch->fenc_uv[y*ch->fenc_uv_stride + 2*x + 1];
+            }
+        m.p_fenc[1] = fenc_c; m.p_fenc[2] = fenc_c + 8;
+        m.p_fref[4] = ch->fref_uv;
+        m.i_stride[1] = ch->fref_uv_stride;
+        for( int k = 0; k < 2; k++ )
+        {
+            make_weight( &wt[1+k], ch->wt[k][0], ch->wt[k][1], ch->wt[k][2], ch->wt[k][3] );
+            if( ch->wt[k][0] ) wt[1+k].weightfn = h->mc.weight;
+        }
+    }
     m.i_pixel = a->i_pixel;
     m.p_cost_mv = h->cost_mv[a->qp];
     m.i_ref_cost = 0;
     m.i_ref = 0;
-    m.weight = &wt;
+    m.weight = wt;
     m.p_fref[0] = f0; m.p_fref[1] = f1; m.p_fref[2] = f2; m.p_fref[3] = f3;
     m.p_fref_w = fref_w;
     m.integral = integral;
@@ -294,7 +323,8 @@ static void me_search_common( x264_t *h, xref_me_args_t *a, uint8_t *fenc, intpt
     h->mb.i_me_method = a->me_method;
     h->mb.i_qp = a->qp;                                 /* ESA / TESA take the x mv costs from cost_mv_fpel[h->mb.i_qp] (me.c:639) */
     h->mb.i_subpel_refine = a->subpel_refine;
-    h->mb.b_chroma_me = 0;
+    h->mb.b_chroma_me = ch != NULL;
+    h->mb.b_interlaced = 0;
     for( int i = 0; i < 2; i++ )
     {
         h->mb.mv_min_spel[i] = a->mv_min_spel[i];
@@ -307,6 +337,7 @@ static void me_search_common( x264_t *h, xref_me_args_t *a, uint8_t *fenc, intpt
     int thresh = a->halfpel_thresh;
     x264_me_search_ref( h, &m, mvc, a->i_mvc, a->use_thresh ? &thresh : NULL );
     h->param.analyse.i_me_range = save_range;
+    h->mb.b_chroma_me = 0;
     a->mv[0] = m.mv[0]; a->mv[1] = m.mv[1];
     a->cost = m.cost; a->cost_mv = m.cost_mv;
     a->thresh_out = thresh;
@@ -315,7 +346,15 @@ static void me_search_common( x264_t *h, xref_me_args_t *a, uint8_t *fenc, intpt
 XREF_API void xref_me_search( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
                               uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride )
 {
-    me_search_common( hv, a, fenc, fenc_stride, f0, f1, f2, f3, fref_w, stride, NULL );
+    me_search_common( hv, a, fenc, fenc_stride, f0, f1, f2, f3, fref_w, stride, NULL, NULL );
+}
+
+/* the same with chroma ME on (refine_subpel's COST_MV_SATD chroma branch, me.c:826-857; partitions of 8x8 and larger) */
+XREF_API void xref_me_search_chroma( void *hv, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
+                                     uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride,
+                                     const xref_chroma_t *ch )
+{
+    me_search_common( hv, a, fenc, fenc_stride, f0, f1, f2, f3, fref_w, stride, NULL, ch );
 }
 
 /* x264_me_refine_qpel (mode 0) / x264_me_refine_qpel_refdupe (mode 1) (encoder/me.c:800-814) on caller-supplied planes, from
@@ -457,7 +496,7 @@ XREF_API int xref_me_search_frame( void *hv, xref_me_args_t *a, uint8_t *fenc, i
         fref_w = wbuf + PADV*st + PADH_ALIGN + off;
     }
     me_search_common( h, a, fenc, fenc_stride, f->filtered[0][0] + off, f->filtered[0][1] + off, f->filtered[0][2] + off,
-                      f->filtered[0][3] + off, fref_w, st, f->integral + off );
+                      f->filtered[0][3] + off, fref_w, st, f->integral + off, NULL );
     if( wbuf ) x264_free( wbuf );
     h->fenc = save;
     return 0;

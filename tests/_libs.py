@@ -155,15 +155,23 @@ class XrefMeArgs(C.Structure):
                 ("mv", C.c_int16 * 2), ("cost", C.c_int), ("cost_mv", C.c_int), ("thresh_out", C.c_int)]
 
 
+class XrefChroma(C.Structure):
+    _fields_ = [("fenc_uv", C.c_void_p), ("fenc_uv_stride", C.c_ssize_t), ("fref_uv", C.c_void_p), ("fref_uv_stride", C.c_ssize_t),
+                ("wt", (C.c_int * 4) * 2)]
+
+
 class OrcMeCtx(C.Structure):
     _fields_ = [("me_method", C.c_int), ("subpel_refine", C.c_int), ("me_range", C.c_int), ("mbcmp_is_satd", C.c_int),
-                ("mv_min_spel", C.c_int * 2), ("mv_max_spel", C.c_int * 2), ("mv_limit_fpel", (C.c_int * 2) * 2)]
+                ("mv_min_spel", C.c_int * 2), ("mv_max_spel", C.c_int * 2), ("mv_limit_fpel", (C.c_int * 2) * 2),
+                ("chroma_me", C.c_int)]
 
 
 class OrcMe(C.Structure):
     _fields_ = [("i_pixel", C.c_int), ("p_cost_mv", C.c_void_p), ("p_fref", C.c_void_p * 4), ("p_fref_w", C.c_void_p),
                 ("p_fenc", C.c_void_p), ("fenc_stride", C.c_ssize_t), ("stride", C.c_ssize_t), ("weight", OrcWeight),
-                ("mvp", C.c_int16 * 2), ("cost_mv", C.c_int), ("cost", C.c_int), ("mv", C.c_int16 * 2)]
+                ("mvp", C.c_int16 * 2), ("cost_mv", C.c_int), ("cost", C.c_int), ("mv", C.c_int16 * 2),
+                ("p_fref_uv", C.c_void_p), ("stride_uv", C.c_ssize_t), ("p_fenc_uv", C.c_void_p), ("fenc_uv_stride", C.c_ssize_t),
+                ("weight_uv", OrcWeight * 2)]
 
 
 def _bind_me():
@@ -173,6 +181,7 @@ def _bind_me():
         r = ref()
         vp = C.c_void_p
         r.xref_me_search.argtypes = [vp, C.POINTER(XrefMeArgs), vp, C.c_ssize_t, vp, vp, vp, vp, vp, C.c_ssize_t]
+        r.xref_me_search_chroma.argtypes = [vp, C.POINTER(XrefMeArgs), vp, C.c_ssize_t, vp, vp, vp, vp, vp, C.c_ssize_t, C.POINTER(XrefChroma)]
         r.xref_cost_mv_table_qp.argtypes = [vp, C.c_int, u16p, C.c_int]
 
 

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import pytest
 import _libs
-from _libs import (oracle, ref, have_ref, ptr, PaddedPlane, OrcWeight, OrcMeCtx, OrcMe, XrefMeArgs, synth_luma,
+from _libs import (oracle, ref, have_ref, ptr, PaddedPlane, OrcWeight, OrcMeCtx, OrcMe, XrefMeArgs, XrefChroma, synth_luma,
                    make_ref_planes, PIXEL_W, PIXEL_H)
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason="compiled reference not present")
@@ -24,20 +24,34 @@ def _content(kind, rng):
     return rng.integers(0, 256, (H, W), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8)
 
 
-def run_case(hnd, subme_param, cost_tab, centre, kind, rng, n_blocks):
+def chroma_pair(kind, rng, st):
+    """NV12 chroma of the two pictures (W bytes x H/2 rows, padded like the luma: a superset of the reference's 16-pixel border);
+    the reference picture's chroma is the source's moved by a fraction of a pixel so that the eighth-pel weights matter"""
+    base = synth_luma(W + 16, H // 2 + 16, seed=int(rng.integers(1 << 30)), kind="noise" if kind == "noise" else "texture")
+    fc, rc = PaddedPlane(W, H // 2, stride=st), PaddedPlane(W, H // 2, stride=st)
+    fc.inner()[:] = base[4:4 + H // 2, 4:4 + W]
+    rc.inner()[:] = np.clip(base[5:5 + H // 2, 6:6 + W].astype(np.int16) + rng.integers(-2, 3, (H // 2, W)), 0, 255).astype(np.uint8)
+    fc.fill_border()
+    rc.fill_border()
+    return fc, rc
+
+
+def run_case(hnd, subme_param, cost_tab, centre, kind, rng, n_blocks, chroma=False):
     o, r = oracle(), ref()
     fenc_l, ref_l = _content(kind, rng)
     planes = make_ref_planes(ref_l)
     st = planes[0].stride
     fenc = PaddedPlane(W, H, stride=st)
     fenc.inner()[:] = fenc_l
+    if chroma:
+        fenc_c, ref_c = chroma_pair(kind, rng, st)
     for _ in range(n_blocks):
-        ip = int(rng.integers(0, 7))
+        ip = int(rng.integers(0, 4 if chroma and rng.random() < 0.8 else 7))
         bw, bh = PIXEL_W[ip], PIXEL_H[ip]
         bx = int(rng.integers(0, (W - bw) // 4 + 1)) * 4
         by = int(rng.integers(0, (H - bh) // 4 + 1)) * 4
         method = int(rng.integers(0, 3))
-        subpel = int(rng.choice([0, 1, 2, 3, 4, 5, 6, 7, 9]))
+        subpel = int(rng.choice([5, 6, 7, 9, 2, 4] if chroma else [0, 1, 2, 3, 4, 5, 6, 7, 9]))
         me_range = int(rng.choice([4, 8, 16] if method < 2 else [16, 24, 32]))
         mvr = 4 * 64
         lim_min = [max(4 * (-bx - 24), -mvr), max(4 * (-by - 24), -mvr)]
@@ -68,8 +82,21 @@ def run_case(hnd, subme_param, cost_tab, centre, kind, rng, n_blocks):
         a.wt_en, a.wt_scale, a.wt_denom, a.wt_offset = wt
         use_thresh = rng.random() < 0.2
         a.use_thresh, a.halfpel_thresh = int(use_thresh), int(rng.integers(50, 3000))
-        r.xref_me_search(hnd, C.byref(a), ptr(fenc.buf, fenc.off(bx, by)), st,
-                         *[ptr(p.buf, off) for p in planes], ptr(wplane.buf, off), st)
+        if chroma:
+            xc = XrefChroma()
+            coff = ref_c.off(bx & ~1, by // 2)             # NV12: chroma pair x/2 starts at byte 2*(x/2)
+            xc.fenc_uv, xc.fenc_uv_stride = fenc_c.buf.ctypes.data + fenc_c.off(bx & ~1, by // 2), st
+            xc.fref_uv, xc.fref_uv_stride = ref_c.buf.ctypes.data + coff, st
+            wuv = [(1, int(rng.integers(40, 90)), int(rng.integers(0, 7)), int(rng.integers(-6, 7))) if rng.random() < 0.3 else (0, 0, 0, 0)
+                   for _ in range(2)]
+            for k in range(2):
+                for j in range(4):
+                    xc.wt[k][j] = wuv[k][j]
+            r.xref_me_search_chroma(hnd, C.byref(a), ptr(fenc.buf, fenc.off(bx, by)), st,
+                                    *[ptr(p.buf, off) for p in planes], ptr(wplane.buf, off), st, C.byref(xc))
+        else:
+            r.xref_me_search(hnd, C.byref(a), ptr(fenc.buf, fenc.off(bx, by)), st,
+                             *[ptr(p.buf, off) for p in planes], ptr(wplane.buf, off), st)
         c = OrcMeCtx()
         c.me_method, c.subpel_refine, c.me_range, c.mbcmp_is_satd = method, subpel, me_range, int(subme_param > 1)
         for i in range(2):
@@ -85,6 +112,10 @@ def run_case(hnd, subme_param, cost_tab, centre, kind, rng, n_blocks):
         m.fenc_stride, m.stride = st, st
         m.weight = OrcWeight(*wt)
         m.mvp[0], m.mvp[1] = int(mvp[0]), int(mvp[1])
+        if chroma:
+            c.chroma_me = 1
+            m.p_fref_uv, m.stride_uv, m.p_fenc_uv, m.fenc_uv_stride = xc.fref_uv, st, xc.fenc_uv, st
+            m.weight_uv[0], m.weight_uv[1] = OrcWeight(*wuv[0]), OrcWeight(*wuv[1])
         mvc_arr = np.ascontiguousarray(mvcs.astype(np.int16))
         th = C.c_int(a.halfpel_thresh)
         o.orc_me_search_ref(C.byref(c), C.byref(m), ptr(mvc_arr), i_mvc, C.byref(th) if use_thresh else None)
@@ -108,6 +139,25 @@ def test_me_search_matches_reference(subme_param, kind):
         rng = np.random.default_rng(100 * subme_param + len(kind))
         for _ in range(6):
             run_case(hnd, subme_param, tab, n, kind, rng, 60)
+    finally:
+        r.xref_close(hnd)
+
+
+@pytest.mark.parametrize("kind", ["texture", "flat", "noise"])
+def test_me_search_chroma_matches_reference(kind):
+    """chroma ME (h->mb.b_chroma_me: P slices at subme >= 5, common/macroblock.c:507): the chroma branch of COST_MV_SATD
+    (me.c:826-857) and mc_chroma (common/mc.c:251-283), weighted chroma planes included"""
+    _libs._bind_me()
+    r = ref()
+    hnd = r.xref_open(W, H, b"medium", b"subme=7", 0)
+    assert hnd
+    try:
+        n = 2 * 4 * r.xref_param(hnd, b"mvrange")
+        tab = np.zeros(2 * n + 1, np.uint16)
+        r.xref_cost_mv_table_qp(hnd, 12, tab, n)
+        rng = np.random.default_rng(4242 + len(kind))
+        for _ in range(6):
+            run_case(hnd, 7, tab, n, kind, rng, 60, chroma=True)
     finally:
         r.xref_close(hnd)
 
