@@ -410,10 +410,11 @@ long x264cu_slicetype_cost_requests( x264cu_slicetype_t *st );
 
 /* ------------------------------------------------------------------------------------------------
  * Batched twin of x264_me_search_ref + refine_subpel (encoder/me.h:58-60, encoder/me.c:182-992): one job = one call.
- * Luma only (no chroma ME), DIA / HEX / UMH / ESA / TESA (the exhaustive searches of me.c:618-771, with their successive-
+ * DIA / HEX / UMH / ESA / TESA (the exhaustive searches of me.c:618-771, with their successive-
  * elimination prefilter where it decides the result), every partition size and sub-pel level.  One warp runs one search with the
  * reference's control flow; jobs are independent (their predictors are inputs), which is how the full-resolution
- * motion-estimation stage is replayed from recorded x264_me_t inputs (BASELINE config 3).
+ * motion-estimation stage is replayed from recorded x264_me_t inputs (BASELINE config 3).  This entry is luma only and takes one
+ * reference picture and one lambda per call; x264cu_me_search_frame below takes a whole picture's searches, chroma ME included.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct
 {
@@ -421,9 +422,9 @@ typedef struct
     uint32_t fenc_off;               /* byte offset of the block in the fenc plane */
     uint32_t ref_off;                /* byte offset of the co-located block in each reference plane */
     int16_t  mvp[2];                 /* m->mvp */
-    int16_t  mvc[8][2];              /* candidate predictors (mvc argument) */
-    int32_t  i_mvc;                  /* 0..8 */
-    int16_t  mv_min_spel[2], mv_max_spel[2];   /* h->mb.mv_min_spel / mv_max_spel; mv_limit_fpel = these >> 2 */
+    int16_t  mvc[9][2];              /* candidate predictors (mvc argument): up to 9 in B slices (x264_mb_predict_mv_ref16x16, common/mvpred.c:519-610) */
+    int32_t  i_mvc;                  /* 0..9 */
+    int16_t  mv_min_spel[2], mv_max_spel[2];   /* h->mb.mv_min_spel / mv_max_spel; mv_limit_fpel follows from them and params.fpel_border */
     int32_t  halfpel_thresh;         /* *p_halfpel_thresh, or -1 for NULL */
 } x264cu_me_job_t;
 
@@ -444,6 +445,8 @@ typedef struct
     int lambda;                      /* a->i_lambda: cost_mv = lambda * bits (analyse.c:143-157) */
     int mv_range;                    /* h->param.analyse.i_mv_range: sizes the cost table */
     int weight_enabled, weight_scale, weight_denom, weight_offset;   /* m->weight[0] (common/mc.h:235-245) */
+    int fpel_border;                 /* h->mb.mv_limit_fpel = (mv_min_spel >> 2) + fpel_border .. (mv_max_spel >> 2) - fpel_border: 6 in the
+                                        encoder's analysis (i_fpel_border, analyse.c:333-349), 0 in the lookahead (slicetype.c:550-562) */
 } x264cu_me_params_t;
 
 /* d_fref[4]: F,H,V,C plane origins of the reference (x264cu_hpel_filter output), d_fref_w: the weighted full-pel plane or
@@ -452,6 +455,43 @@ int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *params,
                             const uint8_t *d_fenc, intptr_t fenc_stride,
                             const uint8_t *const d_fref[4], const uint8_t *d_fref_w, intptr_t ref_stride,
                             const x264cu_me_job_t *d_jobs, int n, x264cu_me_result_t *d_results );
+
+/* The motion searches of one coded picture in ONE launch (BASELINE config 3: the x264_me_t stream x264_mb_analyse_inter_* feeds
+ * to x264_me_search_ref, encoder/analyse.c:1287-1938): every job names the reference picture it searches -- any entry of either
+ * list, weighted duplicates included (h->fref[list][i_ref], h->sh.weight[i_ref][0..2]) -- and its lambda (a->i_lambda follows the
+ * macroblock's quantiser: AQ, MB-tree, VBV).  With chroma_me (h->mb.b_chroma_me, common/macroblock.c:507: P slices at subme >= 5,
+ * B slices at subme >= 9) the quarter-pel refinement of partitions >= 8x8 adds the two chroma planes' costs (COST_MV_SATD's chroma
+ * branch, me.c:826-857: mc_chroma, common/mc.c:251-283, the planes' explicit weights, mbcmp of the half-size block; 4:2:0,
+ * progressive).  Plane pointers are pixel (0,0) of each plane; fenc_off / ref_off of the jobs are byte offsets from there (the
+ * chroma origin of a block is derived from them: row y/2, byte 2*(x/2) of the interleaved plane). */
+typedef struct
+{
+    const uint8_t *d_fref[4];        /* fref->filtered[0][0..3]: F,H,V,C (x264cu_hpel_filter output) */
+    const uint8_t *d_fref_w;         /* the weighted full-pel plane (fref->weighted[0]) or NULL = d_fref[0] */
+    const uint8_t *d_fref_uv;        /* fref->plane[1]: NV12 chroma (padded), or NULL without chroma ME */
+    int weight[3][4];                /* m->weight[0..2] = { enabled, i_scale, i_denom, i_offset } (common/mc.h:235-245) */
+} x264cu_me_ref_t;
+
+typedef struct
+{
+    const uint8_t *d_fenc; intptr_t fenc_stride;          /* fenc->plane[0] */
+    const uint8_t *d_fenc_uv; intptr_t fenc_uv_stride;    /* fenc->plane[1] (NV12), or NULL without chroma ME */
+    intptr_t ref_stride, ref_uv_stride;                   /* shared by all references */
+    const x264cu_me_ref_t *refs; int n_refs;              /* host array, <= 64 */
+    const int *lambdas; int n_lambdas;                    /* host array of the distinct lambdas in use, <= 128 */
+    int chroma_me;                                        /* h->mb.b_chroma_me */
+} x264cu_me_frame_t;
+
+typedef struct
+{
+    x264cu_me_job_t job;
+    int16_t i_ref;                   /* index into x264cu_me_frame_t.refs */
+    int16_t i_lambda;                /* index into x264cu_me_frame_t.lambdas */
+} x264cu_me_frame_job_t;
+
+/* params: me_method, subpel_refine, me_range, mbcmp_satd and mv_range are read (lambda and the weight come with each job) */
+int x264cu_me_search_frame( x264cu_ctx_t *ctx, const x264cu_me_params_t *params, const x264cu_me_frame_t *frame,
+                            const x264cu_me_frame_job_t *d_jobs, int n, x264cu_me_result_t *d_results );
 
 /* Batched twin of x264_me_refine_qpel (refdupe = 0; encoder/me.h:59, me.c:800-809) and x264_me_refine_qpel_refdupe (refdupe = 1;
  * me.h:60, me.c:811-814): the sub-pel refinement continued from a stored vector and cost.  params: subpel_refine =

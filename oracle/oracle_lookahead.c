@@ -285,6 +285,7 @@ static void la_mb_cost( la_t *L, int mb_x, int mb_y )
     const int lowres_penalty = 4;
     orc_me_t m[2];
     orc_me_ctx_t c;
+    memset( &c, 0, sizeof( c ) );          /* no chroma ME in the lookahead (slicetype.c:60) */
     memset( m, 0, sizeof( m ) );
 
     if( p0 != p1 )

@@ -5,7 +5,17 @@
  * the file-static slicetype_* functions can be driven directly, and calls the reference's own functions.
  * Used by tests/ to pin oracle/ and the CUDA path, and by bench.py --impl reference as the CPU arm.
  */
+/* every x264_me_search_ref / x264_me_search call of the analysis goes through a recorder (xref_me_trace_*, below): the macro of
+ * encoder/me.h is re-pointed before the reference's analyse.c is compiled; the recorder calls the real function */
+#include "common/common.h"
+#include "encoder/macroblock.h"
+#include "encoder/me.h"
+#undef x264_me_search_ref
+#define x264_me_search_ref xref_traced_me_search_ref
+static void xref_traced_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh );
 #include "encoder/analyse.c"          /* brings in common/common.h, me.h, slicetype.c, rdo.c ... */
+#undef x264_me_search_ref
+#define x264_me_search_ref x264_template(me_search_ref)
 
 #include <stdio.h>
 #include <string.h>
@@ -806,4 +816,224 @@ XREF_API int xref_aq_frame( void *hv, const uint8_t *luma, const uint8_t *cb, co
     for( int i = 0; i < 3; i++ ) { stats[i] = f->i_pixel_sum[i]; stats[3+i] = f->i_pixel_ssd[i]; }
     x264_frame_push_unused( h, f );
     return 0;
+}
+
+
+/* ------------------------------------------------------------------ recorded x264_me_t stream ------- */
+/* BASELINE config 3: every x264_me_t the reference's analysis hands to x264_me_search_ref while it encodes
+ * (analyse.c:1287, :1392-1785, :1938, :2231-2491: all partition sizes, every reference of both lists), with the result the
+ * reference got, plus copies of the planes those searches read -- so that the whole stream can be replayed elsewhere. */
+typedef struct
+{
+    int32_t i_pixel, bx, by, ref_idx, qp, lambda, i_mvc, thresh_in;     /* ref_idx: index into the traced frame's reference table */
+    int16_t mvp[2], mvc[9][2], lim[4];                                   /* lim = mv_min_spel[0..1], mv_max_spel[0..1] */
+    int16_t mv[2];
+    int32_t cost, cost_mv, thresh_out;
+} xref_me_rec_t;
+
+typedef struct
+{
+    int list, i_ref, display, weighted;
+    int weight[3][4];
+    const pixel *key;                    /* h->mb.pic.p_fref[list][i_ref][0] - MB offset: identifies the planes */
+    const x264_weight_t *wkey;
+    uint8_t *planes[4], *wplane, *uv;    /* copies, origin at PADV*stride + PADH (luma) / (PADV/2)*stride_uv + PADH (chroma) */
+} xref_trace_ref_t;
+
+typedef struct
+{
+    int coded, display, slice_type, chroma_me, me_method, subpel, me_range, mbcmp_satd, mv_range, fpel_border;
+    int width, height, stride, lines, stride_uv, lines_uv;
+    uint8_t *fenc, *fenc_uv;             /* plane[0] / plane[1] of the source picture, from pixel (0,0) */
+    xref_trace_ref_t refs[40]; int n_refs;
+    xref_me_rec_t *recs; int n_recs, cap;
+} xref_trace_frame_t;
+
+static xref_trace_frame_t *trace_frames; static int trace_n, trace_max, trace_skip, trace_on, trace_last_coded = -1;
+
+static uint8_t *trace_copy_padded( const pixel *origin, int stride, int lines, int padv )
+{
+    size_t n = (size_t)stride * ( lines + 2*padv );
+    uint8_t *p = calloc( n, 1 );
+    if( p ) memcpy( p, origin - (intptr_t)padv*stride - PADH, n - 64 );
+    return p;
+}
+
+static xref_trace_frame_t *trace_frame_for( x264_t *h )
+{
+    if( h->i_frame != trace_last_coded )
+    {
+        trace_last_coded = h->i_frame;
+        if( h->i_frame < trace_skip || trace_n >= trace_max ) return NULL;
+        xref_trace_frame_t *f = &trace_frames[trace_n++];
+        memset( f, 0, sizeof(*f) );
+        f->coded = h->i_frame; f->display = h->fenc->i_frame; f->slice_type = h->sh.i_type;
+        f->chroma_me = h->mb.b_chroma_me; f->me_method = h->mb.i_me_method; f->subpel = h->mb.i_subpel_refine;
+        f->me_range = h->param.analyse.i_me_range; f->mbcmp_satd = h->pixf.mbcmp[0] == h->pixf.satd[0];
+        f->mv_range = h->param.analyse.i_mv_range; f->fpel_border = 6;                /* i_fpel_border, analyse.c:333 */
+        f->width = h->param.i_width; f->height = h->param.i_height;
+        f->stride = h->fenc->i_stride[0]; f->lines = h->fenc->i_lines[0];
+        f->stride_uv = h->fenc->i_stride[1]; f->lines_uv = h->fenc->i_lines[1];
+        f->fenc = malloc( (size_t)f->stride * f->lines ); f->fenc_uv = malloc( (size_t)f->stride_uv * f->lines_uv );
+        memcpy( f->fenc, h->fenc->plane[0], (size_t)f->stride * f->lines - 64 );
+        memcpy( f->fenc_uv, h->fenc->plane[1], (size_t)f->stride_uv * f->lines_uv - 64 );
+    }
+    else if( !trace_n || trace_frames[trace_n-1].coded != h->i_frame )
+        return NULL;
+    return &trace_frames[trace_n-1];
+}
+
+static void xref_traced_me_search_ref( x264_t *h, x264_me_t *m, int16_t (*mvc)[2], int i_mvc, int *p_halfpel_thresh )
+{
+    xref_trace_frame_t *f = NULL;
+    xref_me_rec_t rec;
+    int list = -1;
+    if( trace_on && h->fenc && m->i_stride[0] == h->mb.pic.i_stride[0] )
+    {   /* a call of the full-resolution analysis reads one of the current macroblock's reference windows (LOAD_HPELS,
+         * analyse.c:1217-1246); the lookahead's lowres searches (slicetype.c:694) do not and are left out */
+        for( int l = 0; l < 2 && list < 0; l++ )
+            if( m->i_ref >= 0 && m->i_ref < h->mb.pic.i_fref[l] )
+            {
+                intptr_t d = m->p_fref[0] - h->mb.pic.p_fref[l][m->i_ref][0];
+                if( d >= 0 && d < 16*m->i_stride[0] && d % m->i_stride[0] < 16 ) list = l;
+            }
+        if( list >= 0 ) f = trace_frame_for( h );
+    }
+    if( f )
+    {
+        intptr_t d = m->p_fenc[0] - h->mb.pic.p_fenc[0];
+        int xoff = d % FENC_STRIDE, yoff = d / FENC_STRIDE;
+        const pixel *key = h->mb.pic.p_fref[list][m->i_ref][0] - ( 16*h->mb.i_mb_x + 16*h->mb.i_mb_y*(intptr_t)m->i_stride[0] );
+        int r;
+        for( r = 0; r < f->n_refs; r++ )
+            if( f->refs[r].key == key && f->refs[r].wkey == m->weight && f->refs[r].list == list ) break;
+        if( r == f->n_refs && r < 40 )
+        {
+            xref_trace_ref_t *t = &f->refs[f->n_refs++];
+            x264_frame_t *fr = h->fref[list][m->i_ref];
+            t->list = list; t->i_ref = m->i_ref; t->display = fr->i_frame; t->key = key; t->wkey = m->weight;
+            for( int k = 0; k < 3; k++ )
+            {
+                t->weight[k][0] = m->weight[k].weightfn != NULL; t->weight[k][1] = m->weight[k].i_scale;
+                t->weight[k][2] = m->weight[k].i_denom; t->weight[k][3] = m->weight[k].i_offset;
+            }
+            for( int k = 0; k < 4; k++ ) t->planes[k] = trace_copy_padded( fr->filtered[0][k], f->stride, f->lines, PADV );
+            t->uv = trace_copy_padded( fr->plane[1], f->stride_uv, f->lines_uv, PADV >> 1 );
+            t->weighted = m->p_fref_w != m->p_fref[0];
+            if( t->weighted ) t->wplane = trace_copy_padded( h->fenc->weighted[m->i_ref], f->stride, f->lines, PADV );
+        }
+        if( r >= 40 ) f = NULL;
+        else
+        {
+            memset( &rec, 0, sizeof(rec) );
+            rec.i_pixel = m->i_pixel; rec.bx = 16*h->mb.i_mb_x + xoff; rec.by = 16*h->mb.i_mb_y + yoff; rec.ref_idx = r;
+            rec.qp = -1;
+            for( int q = 0; q <= QP_MAX; q++ ) if( h->cost_mv[q] == m->p_cost_mv ) rec.qp = q;
+            rec.lambda = rec.qp >= 0 ? x264_lambda_tab[rec.qp] : -1;
+            rec.i_mvc = i_mvc; rec.thresh_in = p_halfpel_thresh ? *p_halfpel_thresh : -1;
+            rec.mvp[0] = m->mvp[0]; rec.mvp[1] = m->mvp[1];
+            for( int i = 0; i < i_mvc && i < 9; i++ ) { rec.mvc[i][0] = mvc[i][0]; rec.mvc[i][1] = mvc[i][1]; }
+            rec.lim[0] = h->mb.mv_min_spel[0]; rec.lim[1] = h->mb.mv_min_spel[1];
+            rec.lim[2] = h->mb.mv_max_spel[0]; rec.lim[3] = h->mb.mv_max_spel[1];
+        }
+    }
+    x264_me_search_ref( h, m, mvc, i_mvc, p_halfpel_thresh );
+    if( f )
+    {
+        rec.mv[0] = m->mv[0]; rec.mv[1] = m->mv[1]; rec.cost = m->cost; rec.cost_mv = m->cost_mv;
+        rec.thresh_out = p_halfpel_thresh ? *p_halfpel_thresh : -1;
+        if( f->n_recs == f->cap )
+        {
+            f->cap = f->cap ? 2*f->cap : 1 << 16;
+            f->recs = realloc( f->recs, (size_t)f->cap * sizeof(rec) );
+        }
+        f->recs[f->n_recs++] = rec;
+    }
+}
+
+XREF_API void xref_me_trace_free( void )
+{
+    for( int i = 0; i < trace_n; i++ )
+    {
+        xref_trace_frame_t *f = &trace_frames[i];
+        free( f->fenc ); free( f->fenc_uv ); free( f->recs );
+        for( int r = 0; r < f->n_refs; r++ )
+        {
+            for( int k = 0; k < 4; k++ ) free( f->refs[r].planes[k] );
+            free( f->refs[r].wplane ); free( f->refs[r].uv );
+        }
+    }
+    free( trace_frames ); trace_frames = NULL; trace_n = trace_max = 0; trace_on = 0; trace_last_coded = -1;
+}
+/* record the searches of up to max_frames coded pictures, starting with coded picture number `skip` */
+XREF_API int xref_me_trace_start( int max_frames, int skip )
+{
+    xref_me_trace_free();
+    trace_frames = calloc( max_frames, sizeof(*trace_frames) );
+    if( !trace_frames ) return -1;
+    trace_max = max_frames; trace_skip = skip; trace_on = 1;
+    return 0;
+}
+XREF_API void xref_me_trace_stop( void ) { trace_on = 0; }
+XREF_API int xref_me_trace_frames( void ) { return trace_n; }
+/* info[0..17] = coded, display, slice_type, chroma_me, me_method, subpel, me_range, mbcmp_satd, mv_range, fpel_border, width,
+ * height, stride, lines, stride_uv, lines_uv, n_refs, n_recs */
+XREF_API int xref_me_trace_frame_info( int i, int *info )
+{
+    if( i < 0 || i >= trace_n ) return -1;
+    xref_trace_frame_t *f = &trace_frames[i];
+    memcpy( info, &f->coded, 16 * sizeof(int) );
+    info[16] = f->n_refs; info[17] = f->n_recs;
+    return 0;
+}
+XREF_API const void *xref_me_trace_recs( int i ) { return i >= 0 && i < trace_n ? trace_frames[i].recs : NULL; }
+/* which: -1 fenc luma, -2 fenc chroma (ref ignored); 0..3 F,H,V,C of reference `ref`, 4 its weighted plane (or NULL), 5 its chroma */
+XREF_API const void *xref_me_trace_plane( int i, int ref, int which )
+{
+    if( i < 0 || i >= trace_n ) return NULL;
+    xref_trace_frame_t *f = &trace_frames[i];
+    if( which == -1 ) return f->fenc;
+    if( which == -2 ) return f->fenc_uv;
+    if( ref < 0 || ref >= f->n_refs ) return NULL;
+    return which < 4 ? f->refs[ref].planes[which] : which == 4 ? f->refs[ref].wplane : f->refs[ref].uv;
+}
+/* info[0..15] = list, i_ref, display, weighted, weight[3][4] */
+XREF_API int xref_me_trace_ref_info( int i, int ref, int *info )
+{
+    if( i < 0 || i >= trace_n || ref < 0 || ref >= trace_frames[i].n_refs ) return -1;
+    memcpy( info, &trace_frames[i].refs[ref].list, 16 * sizeof(int) );
+    return 0;
+}
+
+/* Encode n I420 pictures (planes packed: luma w*h, then Cb, then Cr, picture after picture) with the opened encoder; the
+ * bitstream is discarded.  Returns the number of frames output. */
+XREF_API int xref_encode_i420( void *hv, const uint8_t *yuv, int n )
+{
+    x264_t *h = hv;
+    int w = h->param.i_width, ht = h->param.i_height;
+    int cw = ( w + 1 ) / 2, ch = ( ht + 1 ) / 2;
+    size_t fsz = (size_t)w*ht + 2*(size_t)cw*ch;
+    int n_out = 0;
+    x264_nal_t *nal; int i_nal;
+    x264_picture_t pic_in, pic_out;
+    for( int i = 0; i < n; i++ )
+    {
+        x264_picture_init( &pic_in );
+        pic_in.img.i_csp = X264_CSP_I420;
+        pic_in.img.i_plane = 3;
+        pic_in.img.plane[0] = (uint8_t*)yuv + i*fsz;             pic_in.img.i_stride[0] = w;
+        pic_in.img.plane[1] = pic_in.img.plane[0] + (size_t)w*ht; pic_in.img.i_stride[1] = cw;
+        pic_in.img.plane[2] = pic_in.img.plane[1] + (size_t)cw*ch; pic_in.img.i_stride[2] = cw;
+        pic_in.i_pts = i;
+        int r = x264_encoder_encode( h, &nal, &i_nal, &pic_in, &pic_out );
+        if( r < 0 ) return -1;
+        if( r > 0 ) n_out++;
+    }
+    while( x264_encoder_delayed_frames( h ) )
+    {
+        int r = x264_encoder_encode( h, &nal, &i_nal, NULL, &pic_out );
+        if( r < 0 ) return -1;
+        if( r > 0 ) n_out++;
+    }
+    return n_out;
 }

@@ -191,7 +191,8 @@ def run_me(backend, gi, ctx=None):
         for k, j in enumerate(jobs):
             e = ja[k]
             e["i_pixel"], e["fenc_off"], e["ref_off"] = j["ip"], fenc.off(j["bx"], j["by"]), planes[0].off(j["bx"], j["by"])
-            e["mvp"], e["mvc"], e["i_mvc"] = j["mvp"], j["mvc"], j["i_mvc"]
+            e["mvp"], e["i_mvc"] = j["mvp"], j["i_mvc"]
+            e["mvc"][:8] = j["mvc"]
             e["mv_min_spel"], e["mv_max_spel"] = j["lim_min"], j["lim_max"]
             e["halfpel_thresh"] = j["thresh"] if j["use_thresh"] else -1
         d_fenc = ctx.upload(fenc.buf)

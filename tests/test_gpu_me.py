@@ -7,7 +7,7 @@ import pytest
 import x264_b200 as x
 import _libs
 from _libs import oracle, ptr, PaddedPlane, OrcWeight, OrcMeCtx, OrcMe, make_ref_planes, PIXEL_W, PIXEL_H
-from test_oracle_me import _content, W, H
+from test_oracle_me import _content, chroma_pair, W, H
 
 pytestmark = pytest.mark.gpu
 
@@ -48,10 +48,10 @@ def run_group(ctx, kind, method, subpel, me_range, satd, wt, rng, n_jobs=96):
         mvr = 4 * mv_range
         lim_min = [max(4 * (-bx - 24), -mvr), max(4 * (-by - 24), -mvr)]
         lim_max = [min(4 * (W - bx - bw + 24), mvr - 1), min(4 * (H - by - bh + 24), mvr - 1)]
-        i_mvc = int(rng.integers(0, 9))
+        i_mvc = int(rng.integers(0, 10))
         spread = int(rng.choice([2, 12, 50]))
         mvp = rng.integers(-spread, spread + 1, 2)
-        mvcs = rng.integers(-spread, spread + 1, (8, 2))
+        mvcs = rng.integers(-spread, spread + 1, (9, 2))
         if rng.random() < 0.3:
             mvp[:] = 0
         if rng.random() < 0.3 and i_mvc:
@@ -105,6 +105,111 @@ def test_me_search_batch_matches_oracle(ctx, kind, method):
         satd = int(subpel > 1 and rng.random() < 0.8)
         wt = (1, int(rng.integers(40, 90)), 6, int(rng.integers(-4, 5))) if rng.random() < 0.3 else (0, 0, 0, 0)
         run_group(ctx, kind, method, subpel, me_range, satd, wt, rng)
+
+
+@pytest.mark.parametrize("kind", ["texture", "flat", "noise"])
+@pytest.mark.parametrize("method", [1, 2])
+def test_me_search_frame_chroma_multiref_matches_oracle(ctx, kind, method):
+    """x264cu_me_search_frame: one launch over jobs that name their reference picture (three of them, weighted luma / chroma
+    planes) and their lambda, with chroma ME (me.c:826-857, mc.c:251-283) -- against the oracle's chroma ME, which
+    tests/test_oracle_me.py pins to the compiled reference"""
+    o = oracle()
+    rng = np.random.default_rng(911 * method + len(kind))
+    mv_range = 64
+    n = 2 * 4 * mv_range
+    lambdas = [1, 3, 7, 12]
+    tabs = []
+    for lam in lambdas:
+        t = np.zeros(2 * n + 1, np.uint16)
+        o.orc_cost_mv_table(t, n, lam)
+        tabs.append(t)
+    for subpel in (5, 7, 9, 4):
+        me_range = int(rng.choice([16, 24] if method == 2 else [8, 16]))
+        fenc_l, _ = _content(kind, rng)
+        st = PaddedPlane(W, H).stride
+        fenc = PaddedPlane(W, H, stride=st)
+        fenc.inner()[:] = fenc_l
+        refs = []
+        for _ in range(3):
+            _, ref_l = _content(kind, rng)
+            planes = make_ref_planes(ref_l, stride=st)
+            wt = [(1, int(rng.integers(40, 90)), 6, int(rng.integers(-4, 5))) if rng.random() < 0.4 else (0, 0, 0, 0)] + \
+                 [(1, int(rng.integers(40, 90)), int(rng.integers(0, 7)), int(rng.integers(-6, 7))) if rng.random() < 0.4 else (0, 0, 0, 0)
+                  for _ in range(2)]
+            if wt[0][0]:
+                wplane = PaddedPlane(W, H, stride=st)
+                ow = OrcWeight(*wt[0])
+                o.orc_weight_scale_plane(ptr(wplane.buf), st, ptr(planes[0].buf), st, st, H + 64, C.byref(ow))
+            else:
+                wplane = planes[0]
+            fc, rc = chroma_pair(kind, rng, st)
+            refs.append((planes, wplane, rc, wt))
+        fenc_c, _ = chroma_pair(kind, rng, st)
+        n_jobs = 160
+        jobs = np.zeros(n_jobs, x.me_frame_job_dtype)
+        want = []
+        for k in range(n_jobs):
+            ip = int(rng.integers(0, 4 if rng.random() < 0.8 else 7))
+            bw, bh = PIXEL_W[ip], PIXEL_H[ip]
+            bx = int(rng.integers(0, (W - bw) // 8 + 1)) * 8 if ip < 4 else int(rng.integers(0, (W - bw) // 4 + 1)) * 4
+            by = int(rng.integers(0, (H - bh) // 8 + 1)) * 8 if ip < 4 else int(rng.integers(0, (H - bh) // 4 + 1)) * 4
+            mvr = 4 * mv_range
+            lim_min = [max(4 * (-bx - 24), -mvr), max(4 * (-by - 24), -mvr)]
+            lim_max = [min(4 * (W - bx - bw + 24), mvr - 1), min(4 * (H - by - bh + 24), mvr - 1)]
+            i_mvc = int(rng.integers(0, 10))
+            spread = int(rng.choice([2, 12, 50]))
+            mvp = rng.integers(-spread, spread + 1, 2)
+            mvcs = rng.integers(-spread, spread + 1, (9, 2))
+            use_thresh = rng.random() < 0.2
+            thresh = int(rng.integers(50, 3000)) if use_thresh else -1
+            i_ref, i_lam = int(rng.integers(0, 3)), int(rng.integers(0, len(lambdas)))
+            planes, wplane, rc, wt = refs[i_ref]
+            j = jobs[k]
+            j["job"]["i_pixel"], j["job"]["fenc_off"], j["job"]["ref_off"] = ip, by * st + bx, by * st + bx
+            j["job"]["mvp"], j["job"]["mvc"], j["job"]["i_mvc"] = mvp, mvcs, i_mvc
+            j["job"]["mv_min_spel"], j["job"]["mv_max_spel"], j["job"]["halfpel_thresh"] = lim_min, lim_max, thresh
+            j["i_ref"], j["i_lambda"] = i_ref, i_lam
+            c = OrcMeCtx()
+            c.me_method, c.subpel_refine, c.me_range, c.mbcmp_is_satd, c.chroma_me = method, subpel, me_range, 1, 1
+            for i in range(2):
+                c.mv_min_spel[i], c.mv_max_spel[i] = lim_min[i], lim_max[i]
+                c.mv_limit_fpel[0][i], c.mv_limit_fpel[1][i] = lim_min[i] >> 2, lim_max[i] >> 2
+            m = OrcMe()
+            m.i_pixel = ip
+            m.p_cost_mv = tabs[i_lam].ctypes.data + 2 * n
+            off = planes[0].off(bx, by)
+            for i in range(4):
+                m.p_fref[i] = planes[i].buf.ctypes.data + off
+            m.p_fref_w = wplane.buf.ctypes.data + off
+            m.p_fenc = fenc.buf.ctypes.data + fenc.off(bx, by)
+            m.fenc_stride, m.stride = st, st
+            m.weight = OrcWeight(*wt[0])
+            m.mvp[0], m.mvp[1] = int(mvp[0]), int(mvp[1])
+            m.p_fref_uv, m.stride_uv = rc.buf.ctypes.data + rc.off(bx & ~1, by // 2), st
+            m.p_fenc_uv, m.fenc_uv_stride = fenc_c.buf.ctypes.data + fenc_c.off(bx & ~1, by // 2), st
+            m.weight_uv[0], m.weight_uv[1] = OrcWeight(*wt[1]), OrcWeight(*wt[2])
+            mvc_arr = np.ascontiguousarray(mvcs.astype(np.int16))
+            th = C.c_int(thresh)
+            o.orc_me_search_ref(C.byref(c), C.byref(m), ptr(mvc_arr), i_mvc, C.byref(th) if use_thresh else None)
+            want.append((m.mv[0], m.mv[1], m.cost, th.value if use_thresh else -1))
+        live = []
+        def up(pl):
+            d = ctx.upload(pl.buf)
+            live.append(d)
+            return d + pl.origin
+        d_fenc, d_fenc_c = up(fenc), up(fenc_c)
+        dev_refs = []
+        for planes, wplane, rc, wt in refs:
+            d_pl = [up(p) for p in planes]
+            dev_refs.append((d_pl, up(wplane) if wt[0][0] else None, up(rc), wt))
+        frame, keep = x.make_me_frame(d_fenc, st, d_fenc_c, st, st, st, dev_refs, lambdas, 1)
+        params = x.MeParams(method, subpel, me_range, 1, 1, mv_range, 0, 0, 0, 0)
+        res = x.me_search_frame(ctx, params, frame, jobs)
+        for d in live:
+            ctx.free(d)
+        for k in range(n_jobs):
+            got = (int(res[k]["mv"][0]), int(res[k]["mv"][1]), int(res[k]["cost"]), int(res[k]["halfpel_thresh"]))
+            assert got == want[k], (kind, method, subpel, k, jobs[k], got, want[k])
 
 
 def test_me_search_batch_tesa_many_jobs(ctx):
@@ -287,7 +392,7 @@ def test_me_search_batch_4k_frame_of_macroblocks(ctx):
     jobs["fenc_off"] = (fenc.origin + yy * 16 * st + xx * 16).reshape(-1)
     jobs["ref_off"] = jobs["fenc_off"]
     jobs["mvp"] = rng.integers(-20, 21, (mbw * mbh, 2))
-    jobs["mvc"] = rng.integers(-30, 31, (mbw * mbh, 8, 2))
+    jobs["mvc"][:, :8] = rng.integers(-30, 31, (mbw * mbh, 8, 2))
     jobs["i_mvc"] = rng.integers(0, 6, mbw * mbh)
     mvr = 4 * 512
     jobs["mv_min_spel"][:, 0] = np.maximum(4 * (-16 * xx - 24), -mvr).reshape(-1)

@@ -46,7 +46,7 @@ for name, method, me_range, subpel in (("umh_merange64_subme9", 2, 64, 9), ("umh
     jobs["fenc_off"] = (fenc.origin + yy * 16 * st + xx * 16).reshape(-1)
     jobs["ref_off"] = jobs["fenc_off"]
     jobs["mvp"] = rng.integers(-20, 21, (n, 2))
-    jobs["mvc"] = rng.integers(-30, 31, (n, 8, 2))
+    jobs["mvc"][:, :8] = rng.integers(-30, 31, (n, 8, 2))
     jobs["i_mvc"] = rng.integers(0, 6, n)
     mvr = 4 * 512
     jobs["mv_min_spel"][:, 0] = np.maximum(4 * (-16 * xx - 24), -mvr).reshape(-1)

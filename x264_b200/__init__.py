@@ -11,7 +11,8 @@ from .binding import (lib, lib_path, Context, X264CUError, PIXEL_W, PIXEL_H, PIX
 
 from .binding_ext import (Lookahead, LookaheadParams, Slicetype, SlicetypeParams, TYPE_NAMES, MeParams, me_job_dtype,
                           me_result_dtype, me_search_batch, bidir_job_dtype, bidir_result_dtype, me_refine_bidir_batch,
-                          me_refine_job_dtype, me_refine_qpel_batch)
+                          me_refine_job_dtype, me_refine_qpel_batch, me_frame_job_dtype, MeRef, MeFrame, make_me_frame,
+                          me_search_frame)
 
-__all__ = ["me_refine_job_dtype", "me_refine_qpel_batch", "bidir_job_dtype", "bidir_result_dtype", "me_refine_bidir_batch", "MeParams", "me_job_dtype", "me_result_dtype", "me_search_batch", "Lookahead", "LookaheadParams", "Slicetype", "SlicetypeParams", "TYPE_NAMES", "lib", "lib_path", "Context", "X264CUError", "PIXEL_W", "PIXEL_H", "PIXEL_NAMES", "cand_dtype",
+__all__ = ["me_frame_job_dtype", "MeRef", "MeFrame", "make_me_frame", "me_search_frame", "me_refine_job_dtype", "me_refine_qpel_batch", "bidir_job_dtype", "bidir_result_dtype", "me_refine_bidir_batch", "MeParams", "me_job_dtype", "me_result_dtype", "me_search_batch", "Lookahead", "LookaheadParams", "Slicetype", "SlicetypeParams", "TYPE_NAMES", "lib", "lib_path", "Context", "X264CUError", "PIXEL_W", "PIXEL_H", "PIXEL_NAMES", "cand_dtype",
            "cand_x4_dtype", "SAD", "SSD", "SATD", "SA8D", "PAD", "exported_symbols", "header_symbols"]

@@ -11,7 +11,7 @@ class LookaheadParams(C.Structure):
 
 class MeJob(C.Structure):
     _fields_ = [("i_pixel", C.c_int32), ("fenc_off", C.c_uint32), ("ref_off", C.c_uint32), ("mvp", C.c_int16 * 2),
-                ("mvc", (C.c_int16 * 2) * 8), ("i_mvc", C.c_int32), ("mv_min_spel", C.c_int16 * 2), ("mv_max_spel", C.c_int16 * 2),
+                ("mvc", (C.c_int16 * 2) * 9), ("i_mvc", C.c_int32), ("mv_min_spel", C.c_int16 * 2), ("mv_max_spel", C.c_int16 * 2),
                 ("halfpel_thresh", C.c_int32)]
 
 
@@ -21,12 +21,25 @@ class MeResult(C.Structure):
 
 class MeParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("me_method", "subpel_refine", "me_range", "mbcmp_satd", "lambda_", "mv_range",
-                                       "weight_enabled", "weight_scale", "weight_denom", "weight_offset")]
+                                       "weight_enabled", "weight_scale", "weight_denom", "weight_offset", "fpel_border")]
 
 
 me_job_dtype = np.dtype([("i_pixel", np.int32), ("fenc_off", np.uint32), ("ref_off", np.uint32), ("mvp", np.int16, (2,)),
-                         ("mvc", np.int16, (8, 2)), ("i_mvc", np.int32), ("mv_min_spel", np.int16, (2,)),
+                         ("mvc", np.int16, (9, 2)), ("i_mvc", np.int32), ("mv_min_spel", np.int16, (2,)),
                          ("mv_max_spel", np.int16, (2,)), ("halfpel_thresh", np.int32)])
+me_frame_job_dtype = np.dtype([("job", me_job_dtype), ("i_ref", np.int16), ("i_lambda", np.int16)])
+
+
+class MeRef(C.Structure):
+    _fields_ = [("d_fref", C.c_void_p * 4), ("d_fref_w", C.c_void_p), ("d_fref_uv", C.c_void_p), ("weight", (C.c_int * 4) * 3)]
+
+
+class MeFrame(C.Structure):
+    _fields_ = [("d_fenc", C.c_void_p), ("fenc_stride", C.c_ssize_t), ("d_fenc_uv", C.c_void_p), ("fenc_uv_stride", C.c_ssize_t),
+                ("ref_stride", C.c_ssize_t), ("ref_uv_stride", C.c_ssize_t), ("refs", C.POINTER(MeRef)), ("n_refs", C.c_int),
+                ("lambdas", C.POINTER(C.c_int)), ("n_lambdas", C.c_int), ("chroma_me", C.c_int)]
+
+
 me_result_dtype = np.dtype([("mv", np.int16, (2,)), ("cost", np.int32), ("cost_mv", np.int32), ("halfpel_thresh", np.int32)])
 bidir_job_dtype = np.dtype([("i_pixel", np.int32), ("fenc_off", np.uint32), ("ref0_off", np.uint32), ("ref1_off", np.uint32),
                             ("mv", np.int16, (4,)), ("mvp", np.int16, (4,)), ("mv_min_spel", np.int16, (2,)),
@@ -50,6 +63,7 @@ TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "BREF", 5: "B"}
 def bind(L):
     vp, ci, ss = C.c_void_p, C.c_int, C.c_ssize_t
     L.x264cu_me_search_batch.argtypes = [vp, C.POINTER(MeParams), vp, ss, C.POINTER(vp), vp, ss, vp, ci, vp]
+    L.x264cu_me_search_frame.argtypes = [vp, C.POINTER(MeParams), C.POINTER(MeFrame), vp, ci, vp]
     L.x264cu_me_refine_bidir_batch.argtypes = [vp, C.POINTER(MeParams), vp, ss, C.POINTER(vp), C.POINTER(vp), ss, vp, ci, vp]
     L.x264cu_me_refine_qpel_batch.argtypes = [vp, C.POINTER(MeParams), ci, vp, ss, C.POINTER(vp), ss, vp, ci, vp]
     L.x264cu_slicetype_open.argtypes = [vp, C.POINTER(SlicetypeParams), C.POINTER(vp)]
@@ -378,6 +392,36 @@ def me_search_batch(ctx, params, d_fenc, fenc_stride, d_fref, d_fref_w, ref_stri
     arr = (C.c_void_p * 4)(*[int(p) for p in d_fref])
     ctx.check(ctx.L.x264cu_me_search_batch(ctx.h, C.byref(params), int(d_fenc), fenc_stride, arr,
                                            int(d_fref_w) if d_fref_w else None, ref_stride, d_jobs, n, d_res))
+    out = ctx.download(d_res, (n,), me_result_dtype)
+    ctx.free(d_jobs)
+    ctx.free(d_res)
+    return out
+
+
+def make_me_frame(d_fenc, fenc_stride, d_fenc_uv, fenc_uv_stride, ref_stride, ref_uv_stride, refs, lambdas, chroma_me):
+    """refs: [(d_fref[4], d_fref_w or None, d_fref_uv or None, weights[3][4])] -> (MeFrame, keep-alive objects)"""
+    arr = (MeRef * len(refs))()
+    for i, (pl, w, uv, wt) in enumerate(refs):
+        for k in range(4):
+            arr[i].d_fref[k] = int(pl[k])
+        arr[i].d_fref_w = int(w) if w else None
+        arr[i].d_fref_uv = int(uv) if uv else None
+        for k in range(3):
+            for j in range(4):
+                arr[i].weight[k][j] = int(wt[k][j])
+    lam = (C.c_int * len(lambdas))(*[int(v) for v in lambdas])
+    f = MeFrame(int(d_fenc), fenc_stride, int(d_fenc_uv) if d_fenc_uv else None, fenc_uv_stride, ref_stride, ref_uv_stride,
+                arr, len(refs), lam, len(lambdas), int(chroma_me))
+    return f, (arr, lam)
+
+
+def me_search_frame(ctx, params, frame, jobs):
+    """jobs: numpy array of me_frame_job_dtype (host) -> numpy array of me_result_dtype"""
+    assert jobs.dtype == me_frame_job_dtype and me_frame_job_dtype.itemsize == C.sizeof(MeJob) + 4
+    n = len(jobs)
+    d_jobs = ctx.upload(jobs)
+    d_res = ctx.malloc(max(n, 1) * me_result_dtype.itemsize)
+    ctx.check(ctx.L.x264cu_me_search_frame(ctx.h, C.byref(params), C.byref(frame), d_jobs, n, d_res))
     out = ctx.download(d_res, (n,), me_result_dtype)
     ctx.free(d_jobs)
     ctx.free(d_res)

@@ -97,7 +97,7 @@ void x264cu_close( x264cu_ctx_t *ctx )
     cudaSetDevice( ctx->device );
     cudaStreamSynchronize( ctx->stream );
     x264cu_lookahead_close_internal( ctx );
-    for( int i = 0; i < 12; i++ )
+    for( int i = 0; i < 16; i++ )
         if( ctx->scratch[i] ) cudaFree( ctx->scratch[i] );
     if( ctx->ev0 ) { cudaEventDestroy( ctx->ev0 ); cudaEventDestroy( ctx->ev1 ); }
     cudaStreamDestroy( ctx->stream );

@@ -22,10 +22,11 @@ struct x264cu_ctx
                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill ) = nullptr;
     // scratch for the *_host entry points (grown on demand)
-    void *scratch[12] = {};
-    size_t scratch_bytes[12] = {};
+    void *scratch[16] = {};
+    size_t scratch_bytes[16] = {};
     bool aq_tables = false;                      // x264cu_adaptive_quant_frame's constant tables uploaded
     int me_tab_lambda = -1, me_tab_range = -1;   // which cost_mv table scratch slot 5 currently holds (x264cu_me_search_batch)
+    std::vector<int> me_tabs_lambdas; int me_tabs_range = -1;   // ... and the per-lambda tables of slot 11 (x264cu_me_search_frame)
     struct x264cu_lookahead *lookahead = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaStream_t> aux_streams;   // streams of live lookahead objects: x264cu_sync waits for them too

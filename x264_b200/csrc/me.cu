@@ -3,17 +3,23 @@
 #include "ctx.h"
 #include "me_dev.cuh"
 #include <math.h>
+#include <string.h>
 #include <vector>
 
 using namespace x264cu;
 
 struct MeJob                                    // == x264cu_me_job_t
 {
-    int32_t i_pixel; uint32_t fenc_off, ref_off; int16_t mvp[2]; int16_t mvc[8][2]; int32_t i_mvc;
+    int32_t i_pixel; uint32_t fenc_off, ref_off; int16_t mvp[2]; int16_t mvc[9][2]; int32_t i_mvc;
     int16_t mv_min_spel[2], mv_max_spel[2]; int32_t halfpel_thresh;
 };
 struct MeResult { int16_t mv[2]; int32_t cost, cost_mv, halfpel_thresh; };
-static_assert( sizeof( MeJob ) == sizeof( x264cu_me_job_t ) && sizeof( MeResult ) == sizeof( x264cu_me_result_t ), "ABI structs" );
+struct MeFrameJob { MeJob job; int16_t i_ref, i_lambda; };          // == x264cu_me_frame_job_t
+static_assert( sizeof( MeJob ) == sizeof( x264cu_me_job_t ) && sizeof( MeResult ) == sizeof( x264cu_me_result_t ) &&
+               sizeof( MeFrameJob ) == sizeof( x264cu_me_frame_job_t ), "ABI structs" );
+// one reference picture of a frame-level batch, as the kernel reads it
+struct MeRefDev { const uint8_t *fref[4], *fref_w, *fref_uv; LaWeight w[3]; };
+struct MeFrameDev { const MeRefDev *refs; const uint16_t *tabs; int tab_stride; int job_bytes; };   // refs == NULL: plain MeJob array
 
 template <int BW, int BH, bool EXH>
 __device__ __noinline__ void run_job( const MeShared &g, const MeJob &j, int lane, MeResult &r, uint2 *tesa_list )
@@ -27,14 +33,26 @@ __device__ __noinline__ void run_job( const MeShared &g, const MeJob &j, int lan
 
 template <bool EXH>
 __global__ void __launch_bounds__( 128 )
-me_search_kernel( MeShared g, const MeJob *__restrict__ jobs, int n, MeResult *__restrict__ results )
+me_search_kernel( MeShared g0, MeFrameDev fd, const char *__restrict__ jobs, int n, MeResult *__restrict__ results )
 {
     const int lane = threadIdx.x & 31;
     const int w0 = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5, nw = ( gridDim.x * blockDim.x ) >> 5;
-    uint2 *tesa_list = g.tesa_list ? g.tesa_list + (size_t)w0 * g.tesa_cap : nullptr;
+    uint2 *tesa_list = g0.tesa_list ? g0.tesa_list + (size_t)w0 * g0.tesa_cap : nullptr;
     for( int w = w0; w < n; w += nw )            // one job per warp, except TESA whose warps (and candidate lists) are bounded
     {
-        MeJob j = jobs[w];                       // every lane holds the (uniform) job
+        const char *jp = jobs + (size_t)w * fd.job_bytes;
+        MeJob j = *(const MeJob *)jp;            // every lane holds the (uniform) job
+        MeShared g = g0;
+        if( fd.refs )
+        {   // frame-level batch: the job names its reference picture and its lambda
+            const int i_ref = ( (const MeFrameJob *)jp )->i_ref, i_lambda = ( (const MeFrameJob *)jp )->i_lambda;
+            const MeRefDev &rf = fd.refs[i_ref];
+#pragma unroll
+            for( int i = 0; i < 4; i++ ) g.fref[i] = rf.fref[i];
+            g.fref_w = rf.fref_w; g.fref_uv = rf.fref_uv;
+            g.w = rf.w[0]; g.wc[0] = rf.w[1]; g.wc[1] = rf.w[2];
+            g.cost_mv = fd.tabs + (size_t)i_lambda * fd.tab_stride;
+        }
         MeResult r;
         switch( j.i_pixel )
         {
@@ -50,8 +68,19 @@ me_search_kernel( MeShared g, const MeJob *__restrict__ jobs, int n, MeResult *_
     }
 }
 
-// cost_mv[lambda] (analyse.c:143-157, :179-188), same float expressions as the reference; kept in this context's scratch slot 5
-// (nobody else's) and rebuilt when (lambda, range) change.  Returns the table's centre.
+// cost_mv[lambda] (analyse.c:143-157, :179-188), same float expressions as the reference
+static void me_fill_cost_table( uint16_t *tab, int len, int lambda )
+{
+    for( int i = 0; i <= len; i++ )
+    {
+        float l = i ? log2f( (float)( i + 1 ) ) * 2.0f + 1.718f : 0.718f;
+        int c = (int)( lambda * l + .5f );
+        if( c > 65535 ) c = 65535;
+        tab[len + i] = tab[len - i] = (uint16_t)c;
+    }
+}
+
+// kept in this context's scratch slot 5 (nobody else's) and rebuilt when (lambda, range) change.  Returns the table's centre.
 static const uint16_t *me_cost_table( x264cu_ctx_t *ctx, int lambda, int mv_range )
 {
     const int len = 2 * 4 * mv_range;
@@ -61,13 +90,7 @@ static const uint16_t *me_cost_table( x264cu_ctx_t *ctx, int lambda, int mv_rang
     if( ctx->me_tab_lambda != lambda || ctx->me_tab_range != mv_range || before != (const void *)d_tab )
     {
         std::vector<uint16_t> tab( 2 * len + 1 );
-        for( int i = 0; i <= len; i++ )
-        {
-            float l = i ? log2f( (float)( i + 1 ) ) * 2.0f + 1.718f : 0.718f;
-            int c = (int)( lambda * l + .5f );
-            if( c > 65535 ) c = 65535;
-            tab[len + i] = tab[len - i] = (uint16_t)c;
-        }
+        me_fill_cost_table( tab.data(), len, lambda );
         if( cudaMemcpyAsync( d_tab, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice, ctx->stream ) != cudaSuccess ||
             cudaStreamSynchronize( ctx->stream ) != cudaSuccess )
         {
@@ -79,6 +102,9 @@ static const uint16_t *me_cost_table( x264cu_ctx_t *ctx, int lambda, int mv_rang
     return d_tab + len;
 }
 
+static int me_launch( x264cu_ctx_t *ctx, const x264cu_me_params_t *p, MeShared &g, const MeFrameDev &fd, const void *d_jobs, int n,
+                      x264cu_me_result_t *d_results );
+
 extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params_t *p, const uint8_t *d_fenc, intptr_t fenc_stride,
                                        const uint8_t *const d_fref[4], const uint8_t *d_fref_w, intptr_t ref_stride,
                                        const x264cu_me_job_t *d_jobs, int n, x264cu_me_result_t *d_results )
@@ -88,26 +114,100 @@ extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params
     if( n <= 0 ) return 0;
     if( !d_fenc || !d_fref || !d_fref[0] || !d_fref[1] || !d_fref[2] || !d_fref[3] || !d_jobs || !d_results )
         return x264cu_fail( ctx, "me_search_batch: null argument" );
+    if( p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 )
+        return x264cu_fail( ctx, "me_search_batch: bad parameters" );
+    const uint16_t *d_tab = me_cost_table( ctx, p->lambda, p->mv_range );
+    if( !d_tab ) return -1;
+    MeShared g;
+    memset( &g, 0, sizeof( g ) );
+    g.fenc = d_fenc; g.fenc_stride = (int)fenc_stride;
+    for( int i = 0; i < 4; i++ ) g.fref[i] = d_fref[i];
+    g.fref_w = d_fref_w ? d_fref_w : d_fref[0];
+    g.stride = (int)ref_stride;
+    g.cost_mv = d_tab;
+    g.w.enabled = p->weight_enabled; g.w.scale = p->weight_scale; g.w.denom = p->weight_denom; g.w.offset = p->weight_offset;
+    MeFrameDev fd = { nullptr, nullptr, 0, (int)sizeof( MeJob ) };
+    return me_launch( ctx, p, g, fd, d_jobs, n, d_results );
+}
+
+// x264cu_me_search_frame: the searches of one coded picture in one launch -- every job names its reference picture (multi-ref,
+// both lists, weighted duplicates) and its lambda (per-macroblock quantisers: AQ, MB-tree, VBV)
+extern "C" int x264cu_me_search_frame( x264cu_ctx_t *ctx, const x264cu_me_params_t *p, const x264cu_me_frame_t *f,
+                                       const x264cu_me_frame_job_t *d_jobs, int n, x264cu_me_result_t *d_results )
+{
+    X264CU_ENTER( ctx );
+    if( !ctx || !p || !f ) return -1;
+    if( n <= 0 ) return 0;
+    if( !f->d_fenc || !f->refs || f->n_refs < 1 || f->n_refs > 64 || !f->lambdas || f->n_lambdas < 1 || f->n_lambdas > 128 || !d_jobs || !d_results )
+        return x264cu_fail( ctx, "me_search_frame: null / out-of-range argument" );
+    if( p->mv_range < 32 || p->mv_range > 4096 )
+        return x264cu_fail( ctx, "me_search_frame: bad parameters" );
+    if( f->chroma_me && ( !f->d_fenc_uv || f->fenc_uv_stride <= 0 || f->ref_uv_stride <= 0 ) )
+        return x264cu_fail( ctx, "me_search_frame: chroma ME without chroma planes" );
+    const int len = 2 * 4 * p->mv_range, tab_stride = 2 * len + 2;
+    std::vector<MeRefDev> refs( f->n_refs );
+    for( int i = 0; i < f->n_refs; i++ )
+    {
+        const x264cu_me_ref_t &r = f->refs[i];
+        for( int k = 0; k < 4; k++ )
+        {
+            if( !r.d_fref[k] ) return x264cu_fail( ctx, "me_search_frame: reference %d lacks plane %d", i, k );
+            refs[i].fref[k] = r.d_fref[k];
+        }
+        refs[i].fref_w = r.d_fref_w ? r.d_fref_w : r.d_fref[0];
+        refs[i].fref_uv = r.d_fref_uv;
+        if( f->chroma_me && !r.d_fref_uv ) return x264cu_fail( ctx, "me_search_frame: chroma ME, reference %d has no chroma plane", i );
+        for( int k = 0; k < 3; k++ )
+        {
+            refs[i].w[k].enabled = r.weight[k][0]; refs[i].w[k].scale = r.weight[k][1];
+            refs[i].w[k].denom = r.weight[k][2]; refs[i].w[k].offset = r.weight[k][3];
+        }
+    }
+    for( int i = 0; i < f->n_lambdas; i++ )
+        if( f->lambdas[i] < 1 ) return x264cu_fail( ctx, "me_search_frame: lambda %d", f->lambdas[i] );
+    // the cost tables of the lambdas in use, kept until the list changes
+    const void *before = ctx->scratch[11];
+    uint16_t *d_tabs = (uint16_t *)x264cu_scratch( ctx, 11, (size_t)f->n_lambdas * tab_stride * 2 + 64 );
+    if( !d_tabs ) return -1;
+    std::vector<int> want( f->lambdas, f->lambdas + f->n_lambdas );
+    if( before != (const void *)d_tabs || ctx->me_tabs_range != p->mv_range || ctx->me_tabs_lambdas != want )
+    {
+        std::vector<uint16_t> tabs( (size_t)f->n_lambdas * tab_stride );
+        for( int i = 0; i < f->n_lambdas; i++ )
+            me_fill_cost_table( tabs.data() + (size_t)i * tab_stride, len, f->lambdas[i] );
+        CU_CHECK( ctx, cudaMemcpyAsync( d_tabs, tabs.data(), tabs.size() * 2, cudaMemcpyHostToDevice, ctx->stream ) );
+        CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) );
+        ctx->me_tabs_lambdas = want; ctx->me_tabs_range = p->mv_range;
+    }
+    MeRefDev *d_refs = (MeRefDev *)x264cu_scratch( ctx, 12, 64 * sizeof( MeRefDev ) );
+    if( !d_refs ) return -1;
+    CU_CHECK( ctx, cudaMemcpyAsync( d_refs, refs.data(), refs.size() * sizeof( MeRefDev ), cudaMemcpyHostToDevice, ctx->stream ) );
+    MeShared g;
+    memset( &g, 0, sizeof( g ) );
+    g.fenc = f->d_fenc; g.fenc_stride = (int)f->fenc_stride;
+    g.stride = (int)f->ref_stride;
+    g.chroma = f->chroma_me != 0;
+    g.fenc_uv = f->d_fenc_uv; g.fenc_uv_stride = (int)f->fenc_uv_stride; g.ref_uv_stride = (int)f->ref_uv_stride;
+    MeFrameDev fd = { d_refs, d_tabs + len, tab_stride, (int)sizeof( MeFrameJob ) };
+    return me_launch( ctx, p, g, fd, d_jobs, n, d_results );
+}
+
+static int me_launch( x264cu_ctx_t *ctx, const x264cu_me_params_t *p, MeShared &g, const MeFrameDev &fd, const void *d_jobs, int n,
+                      x264cu_me_result_t *d_results )
+{
     if( p->me_method < X264CU_ME_DIA || p->me_method > X264CU_ME_TESA )
         return x264cu_fail( ctx, "me_search_batch: unknown method %d", p->me_method );
     if( p->me_method == X264CU_ME_ESA && p->me_range > 120 )
         return x264cu_fail( ctx, "me_search_batch: esa me_range %d > 120", p->me_range );
     if( p->me_method == X264CU_ME_TESA && p->me_range > 64 )
         return x264cu_fail( ctx, "me_search_batch: tesa me_range %d > 64", p->me_range );
-    if( p->subpel_refine < 0 || p->subpel_refine > 11 || p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 || p->me_range < 1 )
+    if( p->subpel_refine < 0 || p->subpel_refine > 11 || p->me_range < 1 )
         return x264cu_fail( ctx, "me_search_batch: bad parameters" );
-    const uint16_t *d_tab = me_cost_table( ctx, p->lambda, p->mv_range );
-    if( !d_tab ) return -1;
-    MeShared g;
-    g.fenc = d_fenc; g.fenc_stride = (int)fenc_stride;
-    for( int i = 0; i < 4; i++ ) g.fref[i] = d_fref[i];
-    g.fref_w = d_fref_w ? d_fref_w : d_fref[0];
-    g.stride = (int)ref_stride;
-    g.cost_mv = d_tab;
+    if( p->fpel_border < 0 || p->fpel_border > 16 ) return x264cu_fail( ctx, "me_search_batch: fpel_border %d", p->fpel_border );
     g.me_method = p->me_method; g.subpel_refine = p->subpel_refine; g.me_range = p->me_range; g.satd = p->mbcmp_satd;
+    g.fpel_border = p->fpel_border;
     g.fpel_satd = p->mbcmp_satd && p->me_method == X264CU_ME_TESA;                   // encoder.c:1409-1427
     g.tesa_list = nullptr; g.tesa_cap = 0;
-    g.w.enabled = p->weight_enabled; g.w.scale = p->weight_scale; g.w.denom = p->weight_denom; g.w.offset = p->weight_offset;
     const int warps_per_block = 4;
     int blocks = ( n + warps_per_block - 1 ) / warps_per_block;
     if( p->me_method == X264CU_ME_TESA )
@@ -122,9 +222,9 @@ extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params
         if( !g.tesa_list ) return -1;
     }
     if( p->me_method >= X264CU_ME_ESA )
-        me_search_kernel<true><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, (const MeJob *)d_jobs, n, (MeResult *)d_results );
+        me_search_kernel<true><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, fd, (const char *)d_jobs, n, (MeResult *)d_results );
     else
-        me_search_kernel<false><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, (const MeJob *)d_jobs, n, (MeResult *)d_results );
+        me_search_kernel<false><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, fd, (const char *)d_jobs, n, (MeResult *)d_results );
     CU_LAUNCH_CHECK( ctx );
     return 0;
 }
@@ -260,6 +360,7 @@ extern "C" int x264cu_me_refine_qpel_batch( x264cu_ctx_t *ctx, const x264cu_me_p
     const uint16_t *d_tab = me_cost_table( ctx, p->lambda, p->mv_range );
     if( !d_tab ) return -1;
     MeShared g;
+    memset( &g, 0, sizeof( g ) );
     g.fenc = d_fenc; g.fenc_stride = (int)fenc_stride;
     for( int i = 0; i < 4; i++ ) g.fref[i] = d_fref[i];
     g.fref_w = d_fref[0];

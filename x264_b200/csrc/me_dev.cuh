@@ -1,6 +1,7 @@
 // Generic warp-per-search block matcher: x264_me_search_ref + refine_subpel (encoder/me.c:182-992) for every luma
-// partition size, DIA / HEX / UMH / ESA / TESA, every sub-pel level (subpel_iterations, me.c:38-50), optional weighted reference
-// and half-pel early-termination threshold; no chroma ME.  Also x264_me_refine_bidir_satd (me.c:1027-1183).
+// partition size, DIA / HEX / UMH / ESA / TESA, every sub-pel level (subpel_iterations, me.c:38-50), optional weighted reference,
+// half-pel early-termination threshold and chroma ME (the chroma branch of COST_MV_SATD, me.c:826-857, with mc_chroma,
+// common/mc.c:251-283; 4:2:0).  Also x264_me_refine_bidir_satd (me.c:1027-1183).
 //
 // One warp runs one search with the reference's exact control flow (warp-uniform); every step's candidates are evaluated
 // in parallel: a WxH block is covered by L = (W/4)*(H/4) lanes (one 4x4 each), so S = 32/L candidates per round.
@@ -27,9 +28,15 @@ struct MeShared                       // per-launch constants
     const uint16_t *cost_mv;          // centred table in global memory
     int me_method, subpel_refine, me_range;
     int satd;                         // mbcmp is SATD (encoder subme > 1)
+    int fpel_border;                  // mv_limit_fpel = (mv_min_spel >> 2) + border .. (mv_max_spel >> 2) - border (analyse.c:333-349)
     int fpel_satd;                    // fpelcmp is SATD too: TESA with subme > 1 (encoder.c:1409-1427)
     LaWeight w;
     uint2 *tesa_list; int tesa_cap;   // TESA: per-warp candidate lists (sad, packed mv), tesa_cap entries each
+    // chroma ME (h->mb.b_chroma_me): NV12 planes, pixel (0,0) of each; the weights of the two chroma planes (m->weight[1..2])
+    int chroma;
+    const uint8_t *fenc_uv; int fenc_uv_stride;
+    const uint8_t *fref_uv; int ref_uv_stride;
+    LaWeight wc[2];
 };
 
 template <int BW, int BH>
@@ -48,6 +55,12 @@ struct MeWarp
     bool satd, fpel_satd;
     int slot;
     int fsum, gl;                     // ADS: pixel sum of this lane's 4x4 of fenc; lane index within the candidate group
+    // chroma ME: the first L/4 lanes of a candidate group take the 4x4 blocks of U, the next L/4 those of V
+    bool chroma, cact;                // chroma ME on for this search (uniform) / this lane holds a chroma block
+    uint32_t cfenc[4];                // the lane's 4x4 of the source's chroma plane
+    const uint8_t *cref;              // its corner in the reference's NV12 plane (component offset included)
+    int cstride;
+    LaWeight cw;
     // search state (uniform)
     int bmx, bmy, bcost;
 
@@ -68,11 +81,49 @@ struct MeWarp
         return group_sum( fpel_satd ? satd4x4( fenc, b ) : sad4x4( fenc, b ) );        // fpelcmp
     }
     __device__ __forceinline__ int cost_fpel( int mx, int my ) const { return sad_fpel( mx, my ) + bits_fpel( mx, my ); }
+    // mc_chroma (common/mc.c:251-283) of this lane's 4x4 chroma block at the luma vector read in eighth-pels, the plane's
+    // explicit weight, mbcmp against the source: this lane's share of COST_MV_SATD's chroma terms (me.c:843-855).  The reference
+    // stops adding once the sum reaches the best cost; partial sums only grow, so what is accepted is the same with the whole sum.
+    __device__ __noinline__ int chroma_cost( int mx, int my ) const
+    {
+        const int dx = mx & 7, dy = my & 7;
+        const int w00 = ( 8 - dx ) * ( 8 - dy ), w01 = dx * ( 8 - dy ), w10 = ( 8 - dx ) * dy, w11 = dx * dy;
+        const uint8_t *s = cref + ( my >> 3 ) * cstride + ( mx >> 3 ) * 2;
+        uint32_t lo, hi;                           // samples 0..3 and sample 4 of the row above the one being produced
+        {
+            const uint32_t a = ldg4u( s ), b = ldg4u( s + 4 );
+            lo = __byte_perm( a, b, 0x6420 ); hi = ldg4u( s + 8 ) & 0xff;
+        }
+        uint32_t p[4];
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+        {
+            s += cstride;
+            const uint32_t a = ldg4u( s ), b = ldg4u( s + 4 );
+            const uint32_t nlo = __byte_perm( a, b, 0x6420 ), nhi = ldg4u( s + 8 ) & 0xff;
+            uint32_t out = 0;
+#pragma unroll
+            for( int k = 0; k < 4; k++ )
+            {
+                const int t0 = ( lo >> ( 8*k ) ) & 255, t1 = k < 3 ? ( lo >> ( 8*k + 8 ) ) & 255 : (int)hi;
+                const int b0 = ( nlo >> ( 8*k ) ) & 255, b1 = k < 3 ? ( nlo >> ( 8*k + 8 ) ) & 255 : (int)nhi;
+                out |= (uint32_t)( ( w00*t0 + w01*t1 + w10*b0 + w11*b1 + 32 ) >> 6 ) << ( 8*k );
+            }
+            p[r] = cw.enabled ? weight4( out, cw ) : out;
+            lo = nlo; hi = nhi;
+        }
+        return satd ? satd4x4( cfenc, p ) : sad4x4( cfenc, p );
+    }
     __device__ __forceinline__ int cost_qpel( int mx, int my, bool use_mbcmp ) const
     {
         uint32_t b[4];
         qpel4x4_p( fref0, fref1, fref2, fref3, stride, w, mx, my, b );
         int d = ( use_mbcmp ? satd : fpel_satd ) ? satd4x4( fenc, b ) : sad4x4( fenc, b );
+        if( BW >= 8 && BH >= 8 && chroma && use_mbcmp )
+        {
+            const int dc = chroma_cost( mx, my );          // every lane runs it (lanes without a block read a valid address)
+            d += cact ? dc : 0;
+        }
         return group_sum( d ) + __ldg( cost_mv + ( mx - mvpx ) ) + __ldg( cost_mv + ( my - mvpy ) );
     }
 
@@ -362,8 +413,27 @@ __device__ __forceinline__ void me_warp_setup( MeWarp<BW, BH> &m, const MeShared
         m.fref0 = g.fref[0] + o; m.fref1 = g.fref[1] + o; m.fref2 = g.fref[2] + o; m.fref3 = g.fref[3] + o;
         m.fref_w = g.fref_w + o;
     }
+    m.chroma = false; m.cact = false;
+    if( BW >= 8 && BH >= 8 && g.chroma )
+    {   // the block's chroma origin from its luma offset: (x, y) -> row y/2, byte 2*(x/2) of the interleaved plane
+        constexpr int QL = M::L / 4, CLX = M::LX / 2;
+        m.chroma = true;
+        m.cact = gl < 2 * QL;
+        const int comp = gl < QL ? 0 : 1, idx = m.cact ? gl - comp * QL : 0;
+        const int cbx = ( idx % CLX ) * 4, cby = ( idx / CLX ) * 4;
+        const int fy = fenc_off / g.fenc_stride, fx = fenc_off - fy * g.fenc_stride;
+        const int ry = ref_off / g.stride, rx = ref_off - ry * g.stride;
+        const uint8_t *f = g.fenc_uv + ( ( fy >> 1 ) + cby ) * g.fenc_uv_stride + ( fx & ~1 ) + 2 * cbx + comp;
+#pragma unroll
+        for( int r = 0; r < 4; r++ )
+            m.cfenc[r] = __byte_perm( ldg4u( f + r * g.fenc_uv_stride ), ldg4u( f + r * g.fenc_uv_stride + 4 ), 0x6420 );
+        m.cref = g.fref_uv + ( ( ry >> 1 ) + cby ) * g.ref_uv_stride + ( rx & ~1 ) + 2 * cbx + comp;
+        m.cstride = g.ref_uv_stride;
+        m.cw = g.wc[comp];
+    }
     m.min_spel_x = limits[0]; m.min_spel_y = limits[1]; m.max_spel_x = limits[2]; m.max_spel_y = limits[3];
-    m.x_min = m.min_spel_x >> 2; m.y_min = m.min_spel_y >> 2; m.x_max = m.max_spel_x >> 2; m.y_max = m.max_spel_y >> 2;
+    m.x_min = ( m.min_spel_x >> 2 ) + g.fpel_border; m.y_min = ( m.min_spel_y >> 2 ) + g.fpel_border;
+    m.x_max = ( m.max_spel_x >> 2 ) - g.fpel_border; m.y_max = ( m.max_spel_y >> 2 ) - g.fpel_border;
 }
 
 // refine_subpel( h, m, hpel_iters, qpel_iters, p_halfpel_thresh, b_refine_qpel ), me.c:865-992, from (qx, qy, qcost)
@@ -411,8 +481,8 @@ __device__ __forceinline__ void me_refine_subpel( MeWarp<BW, BH> &m, int subpel,
             if( diamond( 2, false, -1 ) < 0 )
                 break;
     }
-    if( !b_refine_qpel && m.satd && !m.fpel_satd )               // mbcmp != fpelcmp: re-measure the winner, me.c:925-929
-        qcost = m.cost_qpel( qx, qy, true );
+    if( !b_refine_qpel && ( ( m.satd && !m.fpel_satd ) || ( BW >= 8 && BH >= 8 && m.chroma ) ) )    // mbcmp != fpelcmp, or chroma to add:
+        qcost = m.cost_qpel( qx, qy, true );                                                         // re-measure the winner, me.c:925-929
     if( thresh_io >= 0 )
     {
         if( ( qcost * 7 ) >> 3 > thresh_io ) return;
@@ -437,7 +507,7 @@ __device__ __forceinline__ void me_refine_subpel( MeWarp<BW, BH> &m, int subpel,
         diamond( 1, false, -1 );                                 // subme 1: one fpelcmp quarter-pel diamond, me.c:965-985
 }
 
-// mvc: up to 8 candidate vectors; thresh_io: half-pel early-termination threshold (< 0 = none)
+// mvc: up to 9 candidate vectors; thresh_io: half-pel early-termination threshold (< 0 = none)
 // EXH: the exhaustive searches (ESA / TESA) are compiled in; the kernel of the other methods is built without them (their
 // candidate-list code costs it 48 registers: 1.40 -> 1.61 ms per 4K picture of UMH merange-64 searches)
 template <int BW, int BH, bool EXH>
@@ -457,12 +527,12 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
     // ---- predictor stage, me.c:216-318 ----
     // candidates kept as packed (x | y<<16) words in ONE local array (two dynamically indexed local arrays were seen
     // to alias in the generated code)
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;      // packed (x | y<<16), kept in registers
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;      // packed (x | y<<16), kept in registers
     int n = 0;
-    auto cget = [&]( int k ) { return k == 0 ? c0 : k == 1 ? c1 : k == 2 ? c2 : k == 3 ? c3 : k == 4 ? c4 : k == 5 ? c5 : k == 6 ? c6 : c7; };
+    auto cget = [&]( int k ) { return k == 0 ? c0 : k == 1 ? c1 : k == 2 ? c2 : k == 3 ? c3 : k == 4 ? c4 : k == 5 ? c5 : k == 6 ? c6 : k == 7 ? c7 : c8; };
     auto cput = [&]( int k, uint32_t v ) {
         if( k == 0 ) c0 = v; else if( k == 1 ) c1 = v; else if( k == 2 ) c2 = v; else if( k == 3 ) c3 = v;
-        else if( k == 4 ) c4 = v; else if( k == 5 ) c5 = v; else if( k == 6 ) c6 = v; else c7 = v; };
+        else if( k == 4 ) c4 = v; else if( k == 5 ) c5 = v; else if( k == 6 ) c6 = v; else if( k == 7 ) c7 = v; else c8 = v; };
 #define CX( k ) ( (int)(int16_t)( cget( k ) & 0xffff ) )
 #define CY( k ) ( (int)(int16_t)( cget( k ) >> 16 ) )
     if( subpel >= 3 )
@@ -470,7 +540,7 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
         int bpx = clip3i( mvpx, m.x_min*4, m.x_max*4 ), bpy = clip3i( mvpy, m.y_min*4, m.y_max*4 );
         pmv = pack_mv( bpx, bpy );
         pmx = LA_FPEL( bpx ); pmy = LA_FPEL( bpy );
-        for( int i = 0; i < 8; i++ )
+        for( int i = 0; i < 9; i++ )
         {
             if( i >= i_mvc ) break;
             int vx = mvc[2*i], vy = mvc[2*i+1];
@@ -520,7 +590,7 @@ __device__ void me_search_generic( const MeShared &g, int i_pixel, uint32_t fenc
         m.bmy = pmy = clip3i( LA_FPEL( mvpy ), m.y_min, m.y_max );
         pmv = pack_mv( m.bmx, m.bmy );
         m.bcost = m.sad_fpel( m.bmx, m.bmy );                     // no mv cost on the rounded predictor (me.c:283-291)
-        for( int i = 0; i < 8; i++ )
+        for( int i = 0; i < 9; i++ )
         {
             if( i >= i_mvc ) break;
             int rx = ( mvc[2*i] + 2 ) >> 2, ry = ( mvc[2*i+1] + 2 ) >> 2;
