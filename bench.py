@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the x264 ME / lookahead cost path on B200 (see BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload satd|lookahead]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload satd|lookahead|me|sweep]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic input:
   workload satd      : 16x16 SATD of every macroblock of 32 synthetic 4K frame pairs (1 036 800 candidates, each
                        against a reference block displaced by a random full-pel vector within +-16) -- the
                        "16x16 SATD macroblocks/s vs HBM roofline" half of BASELINE.json's metric.
-  workload lookahead : lowres lookahead frames/s at 4K (added when the lookahead kernels are in place).
+  workload lookahead : lowres lookahead frames/s at 4K (default; the 16x16 SATD line rides on it).
+  workload me        : BASELINE configs[2]: the x264_me_t stream of a 4K --preset slower --me umh --merange 64 encode, recorded from
+                       the reference encoder on this box and replayed through x264cu_me_search_frame (100 % parity checked).
+  workload sweep     : BASELINE configs[4]: SAD / SATD / SSD x 4x4..16x16, HBM-roofline fraction per cell.
 `value` is measured with the inputs resident in HBM; `e2e` goes through the host-buffer C-ABI entry point with
 pinned host memory, H2D/D2H copies inside the timed region.  Under torchrun (N>1) every rank processes its own
 batch (weak scaling, no data-path collective); timing is the max over ranks of device-event time.
@@ -349,24 +352,45 @@ def make_la_frames(seed, n, alloc):
     return out
 
 
-def cpu_lookahead_rate(frames, budget_s, weightp=0, threads=1):
-    """the same decision workload on the host: the product's host slice-type logic over the reference's own
-    slicetype_frame_cost / macroblock_tree_propagate (oracle/_ref) -- or over the oracle port if the reference did not travel.
-    threads > 1: the reference's own sliced lookahead (--lookahead-threads, slicetype.c:902-944; at most
-    X264_LOOKAHEAD_THREAD_MAX = 16).  Its results then differ slightly from the one-thread ones (the MV predictors at slice
-    boundaries, slicetype.c:668) -- the reference's documented trade-off; throughput is what is measured here."""
+def ref_lookahead_types(frames, n, weightp, threads):
+    """The reference's OWN lookahead stage with its stock control flow (oracle/ref_shim.c: xref_lookahead_types = steps 1-4 of
+    x264_encoder_encode, encoder.c:3360-3445: x264_frame_copy_picture, x264_adaptive_quant_frame, x264_frame_init_lowres,
+    x264_lookahead_put_frame / _get_frames -> x264_slicetype_decide / _analyse / macroblock_tree) over the first n pictures of
+    the cyclic clip `frames`, flushed at the end.  threads > 1: the reference's sliced lookahead (lookahead-threads, at most
+    X264_LOOKAHEAD_THREAD_MAX = 16), whose results differ slightly from the one-thread ones (slicetype.c:668).
+    -> ([(display index, type)] in coded order, seconds)"""
     import _libs
-    from x264_b200.binding_ext import SlicetypeParams, LookaheadParams
+    r = _libs.ref()
+    r.xref_lookahead_types.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    opts = LA_REF_OPTS_W if weightp else LA_REF_OPTS
+    if threads > 1:
+        opts += b":threads=%d:lookahead-threads=%d:sync-lookahead=0" % (threads, threads)
+    hnd = r.xref_open(LA_W, LA_H, b"medium", opts, 0)
+    assert hnd
+    clip = np.ascontiguousarray(np.stack([frames[i % len(frames)] for i in range(n)]))
+    idx, ty = (C.c_int * n)(), (C.c_int * n)()
+    t0 = time.perf_counter()
+    k = r.xref_lookahead_types(hnd, clip.ctypes.data, n, idx, ty)
+    dt = time.perf_counter() - t0
+    r.xref_close(hnd)
+    assert k == n, (k, n)
+    return [(int(idx[i]), int(ty[i])) for i in range(k)], dt
+
+
+def cpu_lookahead_rate(frames, budget_s, weightp=0, threads=1):
+    """the same decision workload on the host cores: the unmodified reference's lookahead stage (ref_lookahead_types), or --
+    only if oracle/_ref did not travel -- the product's host logic over the oracle port"""
+    import _libs
     threads = max(1, min(int(threads), 16))
     if _libs.have_ref():
-        lib, kind = _libs.slicetype_ref_lib(), "reference"
-        opts = LA_REF_OPTS_W if weightp else LA_REF_OPTS
-        if threads > 1:
-            opts += b":threads=%d:lookahead-threads=%d" % (threads, threads)
-        cpu_lookahead_rate._opts = opts                      # keep the bytes alive: the glue stores the pointer
-        lib.slicetype_ref_glue_config(b"medium", opts)
-    else:
-        lib, kind, threads = _libs.slicetype_oracle_lib(), "port", 1
+        # pictures to feed: enough for a steady state (several times the 40-picture lookahead), bounded by the budget
+        est = 25.0 if threads > 1 else 6.0                   # pictures/s seen on this pool's hosts
+        n = int(max(56, min(4 * len(frames), budget_s * est)))
+        types, dt = ref_lookahead_types(frames, n, weightp, threads)
+        return n / dt, "reference", threads, "%d 4K pictures through the reference's own lookahead stage (stock x264_slicetype_decide control flow, " \
+            "cyclic %d-picture clip, flushed) in %.1f s, %d lookahead thread%s" % (n, len(frames), dt, threads, "s" if threads > 1 else ""), types
+    from x264_b200.binding_ext import SlicetypeParams, LookaheadParams
+    lib, kind, threads = _libs.slicetype_oracle_lib(), "port", 1
     la = LookaheadParams(LA_W, LA_H, *[LA_OPTS[k] for k in ("subpel_refine", "me_method", "me_range", "mv_range", "bframes",
                                                             "bframe_bias", "weighted_bipred", "aq_mode", "mb_tree", "vbv")], 0, int(weightp))
     p = SlicetypeParams(la, *[dict(LA_ST, psy=1 if weightp else 0)[k] for k in ("keyint_max", "keyint_min", "scenecut_threshold", "b_adapt", "b_pyramid",
@@ -380,15 +404,13 @@ def cpu_lookahead_rate(frames, budget_s, weightp=0, threads=1):
     t0 = time.perf_counter()
     fed = decided = 0
     types = []
-    # feed until the budget is spent (at least lookahead+2 pictures so that decisions are actually made), then flush
-    while fed < len(frames) and (time.perf_counter() - t0 < budget_s or decided < 2):
-        f = frames[fed]
+    while fed < 4 * len(frames) and (time.perf_counter() - t0 < budget_s or decided < 2):
+        f = frames[fed % len(frames)]
         assert lib.x264cu_slicetype_step(st, f.ctypes.data, f.shape[1], None, C.byref(fr), C.byref(ty)) == 0
         fed += 1
         if fr.value >= 0:
             decided += 1
             types.append((fr.value, ty.value))
-    t_feed = time.perf_counter() - t0
     while True:
         assert lib.x264cu_slicetype_step(st, None, 0, None, C.byref(fr), C.byref(ty)) == 0
         if fr.value < 0:
@@ -397,8 +419,7 @@ def cpu_lookahead_rate(frames, budget_s, weightp=0, threads=1):
         types.append((fr.value, ty.value))
     t = time.perf_counter() - t0
     lib.x264cu_slicetype_close(st)
-    return decided / t, kind, threads, "%d 4K pictures decided in %.1f s (fed %d in %.1f s), %d lookahead thread%s" % (
-        decided, t, fed, t_feed, threads, "s" if threads > 1 else ""), types
+    return decided / t, kind, threads, "%d 4K pictures decided in %.1f s by the oracle port, 1 thread" % (decided, t), types
 
 
 def run_lookahead_b200(args, rank, world, local, dist):
@@ -525,8 +546,11 @@ def run_lookahead_b200(args, rank, world, local, dist):
     # ---- e2e: host pictures through the public entry point, H2D inside --------------------------------
     st = make_st()
     st.set_async_upload(4)        # the pictures live in page-locked memory and are not touched while queued (as x264 holds its frames)
+    all_types = []                # every decision from picture 0 on: compared with the reference's own below
     for i in range(n):
-        st.step(frames[i])
+        fr, ty = st.step(frames[i])
+        if fr >= 0:
+            all_types.append((fr, ty))
     barrier(dist, local)
     t1 = time.perf_counter()
     e2e_steps = 3 if args.quick else max(1, min(args.steps, 10))
@@ -536,6 +560,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
             fr, ty = st.step(frames[i])
             if fr >= 0:
                 e2e_types.append((fr, ty))
+                all_types.append((fr, ty))
     ctx.sync()
     barrier(dist, local)
     e2e_s = max_over_ranks(dist, time.perf_counter() - t1, local)
@@ -579,11 +604,19 @@ def run_lookahead_b200(args, rank, world, local, dist):
         res["sharded_stream"] = sharded
     if rank == 0 and world == 1 and not args.quick:
         rate, kind, cores, sample, _ = cpu_lookahead_rate(frames, args.cpu_budget, args.weightp, os.cpu_count() or 1)
-        rate1, _, _, sample1, _ = cpu_lookahead_rate(frames, args.cpu_budget / 2, args.weightp, 1)
+        rate1, _, _, sample1, types1 = cpu_lookahead_rate(frames, args.cpu_budget, args.weightp, 1)
+        # in-run parity: the reference's one-thread decisions (its documented deterministic mode) against the B200 arm's on the
+        # same cyclic clip; the reference was flushed after its last picture, so only decisions taken with a full lookahead count
+        n_ref = len(types1)
+        keep = max(0, n_ref - LA_ST["rc_lookahead"] - LA_OPTS["bframes"] - 2)
+        got = [t_ for t_ in all_types][:keep]
+        res["config"]["parity_spot_check"] = {"decisions_compared": keep, "identical": bool(keep > 0 and got == types1[:keep]),
+                                              "against": "reference x264_slicetype_decide, 1 lookahead thread, %d pictures" % n_ref}
         res["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
                                "value_1_thread": rate1, "sample_1_thread": sample1,
-                               "note": "the reference's sliced lookahead (--lookahead-threads) on all host cores it can use (max 16); with "
-                                       "one thread it returns exactly the decisions the B200 arm is checked against"}
+                               "note": "the unmodified reference's lookahead stage (stock control flow) with its sliced lookahead threads on all "
+                                       "host cores it can use (max 16); with one thread it returns exactly the decisions the B200 arm is "
+                                       "checked against (parity_spot_check)"}
     ctx.close()
     return res
 
@@ -603,12 +636,296 @@ def run_lookahead_reference(args, rank, world):
         "config": {"workload": "3840x2160 lowres lookahead + slice-type decision, bounded sample per step, same settings as the b200 arm"},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference slicetype_frame_cost + macroblock_tree_propagate (encoder/slicetype.c, C path: no nasm in the image) under the same "
-                "host decision logic, the reference's own sliced lookahead threads on all host cores (max 16)",
+        "note": "the unmodified reference's own lookahead stage (x264_lookahead_put_frame / _get_frames -> x264_slicetype_decide, "
+                "encoder/lookahead.c, encoder/slicetype.c; C path: no nasm in the image) with its sliced lookahead threads on all host cores (max 16)",
     }
 
 
-WORKLOADS = {"satd": (run_satd_b200, run_satd_reference), "lookahead": (run_lookahead_b200, run_lookahead_reference)}
+# ------------------------------------------------------------------------------------------------------
+# workload "me": full-resolution motion estimation (BASELINE configs[2]): the x264_me_t stream of a 3840x2160 --preset slower
+# --me umh --merange 64 encode, recorded from the reference encoder on this box, replayed through x264cu_me_search_frame
+# ------------------------------------------------------------------------------------------------------
+ME_OPTS = b"me=umh:merange=64:threads=1"
+ME_FRAMES_IN, ME_TRACED = 6, 3
+
+
+def me_record(seed=2160):
+    import _me_trace as T
+    t0 = time.perf_counter()
+    frames = T.record(W4K, H4K, ME_FRAMES_IN, ME_OPTS, max_frames=ME_TRACED, skip=1, seed=seed)
+    return T, frames, time.perf_counter() - t0
+
+
+def me_check(T, t, got):
+    want, ee = T.expected(t), T.early_exit(t)
+    bad = (got[:, [0, 1, 2, 4]] != want[:, [0, 1, 2, 4]]).any(1) | ((got[:, 3] != want[:, 3]) & ~ee)
+    return int(bad.sum())
+
+
+def me_algorithmic_bytes(t):
+    """every plane a picture's searches can read once (source luma + chroma, per reference 4 luma planes + chroma + the weighted
+    plane), the job records in and the results out"""
+    luma, chroma = t.stride * t.lines, t.stride_uv * t.lines_uv
+    b = luma + chroma
+    for rf in t.refs:
+        b += 4 * luma + chroma + (luma if rf["weighted"] else 0)
+    return b + t.n_recs * (72 + 16)
+
+
+def run_me_b200(args, rank, world, local, dist):
+    import x264_b200 as x
+    T, frames, rec_s = me_record()
+    ctx = x.Context(local)
+    info = ctx.device_info()
+    devs = [T.DeviceTrace(ctx, t, x) for t in frames]
+    n_search = sum(d.n for d in devs)
+
+    def step():
+        for d in devs:
+            d.launch()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.sync()
+    bad = sum(me_check(T, t, d.results()) for t, d in zip(frames, devs))
+    sampler = ClockSampler(local)
+    barrier(dist, local)
+    sampler.start()
+    l0 = ctx.launches
+    t_wall0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop()
+    ctx.sync()
+    barrier(dist, local)
+    wall = time.perf_counter() - t_wall0
+    launches = ctx.launches - l0
+    ms = max_over_ranks(dist, ms, local)
+    clocks = sampler.stop()
+    per_pic = []
+    for d in devs:                                  # each picture alone (its own launch duration)
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(5):
+            d.launch()
+        per_pic.append(ctx.timer_stop() / 5)
+
+    # e2e: planes, job records in page-locked host memory -> HBM -> searches -> results back on the host, every step
+    host = []
+    for t in frames:
+        bufs = [t.fenc, t.fenc_uv, t.recs]
+        for rf in t.refs:
+            bufs += rf["planes"] + [rf["uv"]] + ([rf["wplane"]] if rf["weighted"] else [])
+        pinned = []
+        for b_ in bufs:
+            hb = ctx.malloc_host(b_.nbytes)
+            hb[:] = b_.view(np.uint8).reshape(-1)
+            pinned.append(hb)
+        host.append(pinned)
+    h2d = sum(b_.nbytes for hb in host for b_ in hb)
+    e2e_steps = 1 if args.quick else max(1, min(args.steps, 5))
+
+    e2e_devs = []
+    for t, hb in zip(frames, host):
+        t2 = T.TraceFrame()
+        t2.__dict__.update(t.__dict__)
+        it = iter(hb)
+        t2.fenc, t2.fenc_uv = next(it), next(it)
+        t2.recs = np.frombuffer(next(it), T.REC)
+        t2.refs = []
+        for rf in t.refs:
+            r2 = dict(rf)
+            r2["planes"] = [next(it) for _ in range(4)]
+            r2["uv"] = next(it)
+            r2["wplane"] = next(it) if rf["weighted"] else None
+            t2.refs.append(r2)
+        e2e_devs.append(T.DeviceTrace(ctx, t2, x))         # device buffers allocated once; every step copies into them again
+
+    def step_e2e(check=False):
+        nbad = 0
+        for t, d in zip(frames, e2e_devs):
+            d.reupload()
+            d.launch()
+            got = d.results()
+            if check:
+                nbad += me_check(T, t, got)
+        return nbad
+
+    bad += step_e2e(check=True)
+    barrier(dist, local)
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    ctx.sync()
+    barrier(dist, local)
+    e2e_s = max_over_ranks(dist, time.perf_counter() - t1, local)
+
+    ms_step = ms / args.steps
+    peaks, peak_src = measured_peaks()
+    alg = sum(me_algorithmic_bytes(t) for t in frames)
+    achieved = alg / (ms_step * 1e-3) / 1e9
+    res = {
+        "metric": "fullres_me_searches_per_sec_4k", "value": n_search * world / (ms_step * 1e-3), "unit": "searches/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: 3840x2160 --preset slower --me umh --merange 64 (subme 9, chroma ME, ref 8, weightp 2, "
+                               "aq 1): EVERY x264_me_t the reference encoder passed to x264_me_search_ref while coding pictures %s of a "
+                               "%d-picture synthetic clip (recorded on this box in %.1f s of CPU), %d searches per step, all partition sizes, "
+                               "multi-ref, per-macroblock lambdas" % ([("PB"[t.slice_type], t.display) for t in frames], ME_FRAMES_IN, rec_s, n_search),
+                   "pictures": [{"coded": t.coded, "type": "PB"[t.slice_type], "searches": d.n, "refs": t.n_refs, "ms": m_}
+                                for t, d, m_ in zip(frames, devs, per_pic)],
+                   "l2": "one step reads %.0f MB of planes and job records > 126 MB L2" % (alg / 1e6),
+                   "parity": "%d of %d searches differ from the reference's recorded (mv, cost, cost_mv, threshold)" % (bad, 2 * n_search),
+                   "multi_gpu": "replicas only (full-res ME depends on reconstructed references): every rank replays the stream"},
+        "clocks": clocks,
+        "e2e": {"value": n_search * world * e2e_steps / e2e_s, "unit": "searches/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(16 * n_search), "api": "x264cu_me_search_frame (page-locked host planes and jobs uploaded every step)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peak_src, "kernel": "me_search_kernel<false>", "algorithmic_bytes_per_launch": alg / len(frames),
+                     "note": "one warp per search walking the reference's own candidate order: bounded by L1/issue latency, not by HBM; "
+                             "see profiles/ for the ncu summary"},
+        "wall_s": wall, "sm_count": info["sm_count"], "parity_ok": bad == 0,
+    }
+    if rank == 0 and world == 1 and not args.quick:
+        cores = os.cpu_count() or 1
+        t = frames[0]
+        n_s = min(t.n_recs, 40000)
+        _, dt1 = T.replay_reference(t, ME_OPTS, 1, sel=slice(0, n_s // 8))
+        big = max(frames, key=lambda f: f.n_recs)
+        n_b = min(big.n_recs, int(args.cpu_budget * 2500 * cores))
+        got, dt = T.replay_reference(big, ME_OPTS, cores, sel=slice(0, n_b))
+        res["cpu_baseline"] = {"value": n_b / dt, "unit": "searches/s", "cores": cores, "kind": "reference",
+                               "sample": "x264_me_search_ref (C path: no nasm in the image) on the first %d recorded searches of coded picture %d, "
+                                         "%d threads with one encoder handle each" % (n_b, big.coded, cores),
+                               "value_1_thread": (n_s // 8) / dt1}
+    for d in devs + e2e_devs:
+        d.close()
+    ctx.close()
+    return res
+
+
+def run_me_reference(args, rank, world):
+    T, frames, rec_s = me_record()
+    cores = os.cpu_count() or 1
+    big = max(frames, key=lambda f: f.n_recs)
+    rates = []
+    n_b = 0
+    for i in range(args.warmup + args.steps):
+        n_b = min(big.n_recs, int(args.cpu_budget / max(1, args.steps) * 2500 * cores))
+        _, dt = T.replay_reference(big, ME_OPTS, cores, sel=slice(0, n_b))
+        if i >= args.warmup:
+            rates.append(n_b / dt)
+    v = float(np.mean(rates))
+    n_search = sum(t.n_recs for t in frames)
+    return {
+        "impl": "reference", "metric": "fullres_me_searches_per_sec_4k", "value": v, "unit": "searches/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_search / v * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: the same recorded x264_me_t stream; bounded sample of %d searches per step" % n_b},
+        "cpu_baseline": {"value": v, "unit": "searches/s", "cores": cores, "kind": "reference",
+                         "sample": "x264_me_search_ref on the first %d recorded searches of coded picture %d" % (n_b, big.coded)},
+        "e2e": {"value": v, "unit": "searches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference x264_me_search_ref (encoder/me.c:182, C path: no nasm in the image), one encoder handle per host thread",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------
+# workload "sweep": BASELINE configs[4], the SAD / SATD / SSD microbench over the block sizes of x264_pixel_function_t
+# ------------------------------------------------------------------------------------------------------
+SWEEP_SIZES = [(6, "4x4"), (5, "4x8"), (4, "8x4"), (3, "8x8"), (2, "8x16"), (1, "16x8"), (0, "16x16")]
+SWEEP_METRICS = [(0, "sad"), (2, "satd"), (1, "ssd")]
+
+
+def run_sweep_b200(args, rank, world, local, dist):
+    import x264_b200 as x
+    import _libs
+    ctx = x.Context(local)
+    info = ctx.device_info()
+    fenc, ref, mv16, stride, pitch = make_satd_inputs(1 + rank, N_PAIRS, lambda n: ctx.malloc_host(n))
+    d_fenc, d_ref = ctx.malloc(fenc.nbytes + 256), ctx.malloc(ref.nbytes + 256)
+    ctx.h2d(d_fenc, fenc)
+    ctx.h2d(d_ref, ref)
+    org = PAD * stride + PAD
+    pf = (d_fenc + org, stride, pitch, W4K, H4K, N_PAIRS)
+    pr = (d_ref + org, stride, pitch, W4K, H4K, N_PAIRS)
+    peaks, peak_src = measured_peaks()
+    rng = np.random.default_rng(100 + rank)
+    cells = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    total_launches, t_all = 0, time.perf_counter()
+    parity_ok = True
+    cpu = rank == 0 and world == 1 and not args.quick
+    cfn = (_libs.ref().xref_pixel_cmp_batch if _libs.have_ref() else _libs.oracle().orc_pixel_cmp_batch)
+    for ip, sname in SWEEP_SIZES:
+        bw, bh = x.PIXEL_W[ip], x.PIXEL_H[ip]
+        nbx, nby = W4K // bw, H4K // bh
+        n_cand = N_PAIRS * nbx * nby
+        mv = rng.integers(-16, 17, (1, N_PAIRS, nby, nbx, 2)).astype(np.int16)
+        d_mv = ctx.upload(mv)
+        d_out = ctx.malloc(n_cand * 4)
+        # checker's candidate list for plane 0 (bounded)
+        by, bx = np.mgrid[0:nby, 0:nbx]
+        c0 = np.zeros(nby * nbx, x.cand_dtype)
+        c0["fenc_off"] = (org + by * bh * stride + bx * bw).reshape(-1)
+        c0["ref_off"] = (org + (by * bh + mv[0, 0, :, :, 1]) * stride + bx * bw + mv[0, 0, :, :, 0]).reshape(-1)
+        n_chk = min(len(c0), 20000)
+        for mi, mname in SWEEP_METRICS:
+            call = lambda: ctx.pixel_cmp_mvfield(mi, ip, pf, pr, 1, d_mv, d_out)
+            for _ in range(3):
+                call()
+            ctx.sync()
+            l0 = ctx.launches
+            ctx.timer_start()
+            for _ in range(args.steps):
+                call()
+            ms = max_over_ranks(dist, ctx.timer_stop(), local) / args.steps
+            total_launches += ctx.launches - l0
+            got = ctx.download(d_out, (n_cand,), np.int32)[:n_chk]
+            want = np.zeros(n_chk, np.int32)
+            cfn(mi, ip, fenc[:pitch], stride, ref[:pitch], stride, c0[:n_chk], n_chk, want)
+            ok = bool(np.array_equal(got, want))
+            parity_ok &= ok
+            alg = (2 * bw * bh + 4) * n_cand
+            cell = {"candidates": n_cand, "ms": ms, "blocks_per_s": n_cand * world / (ms * 1e-3), "GB_s": alg / (ms * 1e-3) / 1e9,
+                    "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "parity": ok}
+            if cpu:
+                n_cpu = min(len(c0), 200000)
+                outc = np.zeros(n_cpu, np.int32)
+                t0 = time.perf_counter()
+                cfn(mi, ip, fenc[:pitch], stride, ref[:pitch], stride, c0[:n_cpu], n_cpu, outc)
+                cell["cpu_blocks_per_s_1_thread"] = n_cpu / (time.perf_counter() - t0)
+            cells["%s_%s" % (mname, sname)] = cell
+        ctx.free(d_mv)
+        ctx.free(d_out)
+    clocks = sampler.stop()
+    wall = time.perf_counter() - t_all
+    head = cells["satd_16x16"]
+    res = {
+        "metric": "satd_16x16_macroblocks_per_sec_4k", "value": head["blocks_per_s"], "unit": "macroblocks/s",
+        "n_gpus": world, "steps": args.steps, "warmup": 3, "ms_per_step": head["ms"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4]: SAD / SATD / SSD x 4x4 .. 16x16 over every block of %d random 3840x2160 luma frame "
+                               "pairs per GPU (>= 1 036 800 candidates per cell), ref displaced by a random full-pel mv in +-16" % N_PAIRS,
+                   "l2": "inputs %.0f MB per launch > 126 MB L2, no flush needed" % ((fenc.nbytes + ref.nbytes) / 1e6),
+                   "parity_spot_check": parity_ok,
+                   "cpu": "reference C path (pixf.sad/satd/ssd, no nasm in the image), one thread, bounded sample" if cpu else None},
+        "cells": cells, "clocks": clocks, "gpu_launches": int(total_launches),
+        "e2e": None,
+        "roofline": {"bound": "hbm", "achieved": head["GB_s"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": head["frac"],
+                     "traffic": None, "peak_source": peak_src, "kernel": "mvfield_kernel<SATD,16,16>",
+                     "algorithmic_bytes_per_launch": ALG_BYTES_16x16 * head["candidates"],
+                     "note": "algorithmic bytes per candidate = 2*W*H + 4 (SURVEY 8d); every cell's fraction is in `cells`"},
+        "wall_s": wall, "sm_count": info["sm_count"],
+    }
+    ctx.close()
+    return res
+
+
+WORKLOADS = {"satd": (run_satd_b200, run_satd_reference), "lookahead": (run_lookahead_b200, run_lookahead_reference),
+             "me": (run_me_b200, run_me_reference), "sweep": (run_sweep_b200, run_satd_reference)}
 DEFAULT_WORKLOAD = "lookahead"
 
 

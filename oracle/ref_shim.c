@@ -284,6 +284,7 @@ typedef struct
 
 /* Drives the reference's x264_me_search_ref (encoder/me.c:182) on caller-supplied planes.
  * fref[0..3] = F,H,V,C plane pointers at the block origin, fref_w = weighted full-pel plane (or fref[0]). */
+static __thread int g_fpel_border;           /* i_fpel_border of the encoder's analysis (analyse.c:333-349); 0 = the lookahead's limits */
 static void me_search_common( x264_t *h, xref_me_args_t *a, uint8_t *fenc, intptr_t fenc_stride,
                               uint8_t *f0, uint8_t *f1, uint8_t *f2, uint8_t *f3, uint8_t *fref_w, intptr_t stride, uint16_t *integral,
                               const xref_chroma_t *ch )
@@ -339,8 +340,8 @@ static void me_search_common( x264_t *h, xref_me_args_t *a, uint8_t *fenc, intpt
     {
         h->mb.mv_min_spel[i] = a->mv_min_spel[i];
         h->mb.mv_max_spel[i] = a->mv_max_spel[i];
-        h->mb.mv_limit_fpel[0][i] = a->mv_min_spel[i] >> 2;
-        h->mb.mv_limit_fpel[1][i] = a->mv_max_spel[i] >> 2;
+        h->mb.mv_limit_fpel[0][i] = ( a->mv_min_spel[i] >> 2 ) + g_fpel_border;
+        h->mb.mv_limit_fpel[1][i] = ( a->mv_max_spel[i] >> 2 ) - g_fpel_border;
     }
     ALIGNED_ARRAY_8( int16_t, mvc,[16],[2] );
     memcpy( mvc, a->mvc, sizeof(mvc) );
@@ -1035,5 +1036,104 @@ XREF_API int xref_encode_i420( void *hv, const uint8_t *yuv, int n )
         if( r < 0 ) return -1;
         if( r > 0 ) n_out++;
     }
+    return n_out;
+}
+
+
+/* Re-run the reference's x264_me_search_ref on recorded searches (xref_me_rec_t) against caller-held copies of the planes: the
+ * CPU arm of bench.py --workload me (one encoder handle per thread) and a self-check of the recorder.  info = the 18 ints of
+ * xref_me_trace_frame_info; planes as xref_me_trace_plane returns them; out = 5 ints per search: mv, cost, cost_mv, threshold. */
+typedef struct { uint8_t *planes[4], *wplane, *uv; int weight[3][4]; } xref_replay_ref_t;
+
+XREF_API void xref_me_replay( void *hv, const int *info, uint8_t *fenc, uint8_t *fenc_uv, const xref_replay_ref_t *refs,
+                              const xref_me_rec_t *recs, int n, int32_t *out )
+{
+    x264_t *h = hv;
+    const int chroma_me = info[3], me_method = info[4], subpel = info[5], me_range = info[6];
+    const int stride = info[12], stride_uv = info[14];
+    const intptr_t lo = (intptr_t)PADV*stride + PADH, co = (intptr_t)(PADV>>1)*stride_uv + PADH;
+    g_fpel_border = info[9];
+    for( int i = 0; i < n; i++ )
+    {
+        const xref_me_rec_t *r = &recs[i];
+        const xref_replay_ref_t *f = &refs[r->ref_idx];
+        xref_me_args_t a;
+        memset( &a, 0, sizeof(a) );
+        a.i_pixel = r->i_pixel; a.me_method = me_method; a.subpel_refine = subpel; a.me_range = me_range; a.qp = r->qp;
+        for( int k = 0; k < 2; k++ ) { a.mv_min_spel[k] = r->lim[k]; a.mv_max_spel[k] = r->lim[2+k]; a.mvp[k] = r->mvp[k]; }
+        a.i_mvc = r->i_mvc;
+        memcpy( a.mvc, r->mvc, sizeof(r->mvc) );
+        a.wt_en = f->weight[0][0]; a.wt_scale = f->weight[0][1]; a.wt_denom = f->weight[0][2]; a.wt_offset = f->weight[0][3];
+        a.use_thresh = r->thresh_in >= 0; a.halfpel_thresh = r->thresh_in;
+        intptr_t off = lo + (intptr_t)r->by*stride + r->bx;
+        xref_chroma_t ch;
+        ch.fenc_uv = fenc_uv + (intptr_t)(r->by>>1)*stride_uv + (r->bx&~1); ch.fenc_uv_stride = stride_uv;
+        ch.fref_uv = f->uv + co + (intptr_t)(r->by>>1)*stride_uv + (r->bx&~1); ch.fref_uv_stride = stride_uv;
+        memcpy( ch.wt, f->weight[1], sizeof(ch.wt) );
+        me_search_common( h, &a, fenc + (intptr_t)r->by*stride + r->bx, stride, f->planes[0] + off, f->planes[1] + off,
+                          f->planes[2] + off, f->planes[3] + off, ( f->wplane ? f->wplane : f->planes[0] ) + off, stride, NULL,
+                          chroma_me ? &ch : NULL );
+        out[5*i] = a.mv[0]; out[5*i+1] = a.mv[1]; out[5*i+2] = a.cost; out[5*i+3] = a.cost_mv; out[5*i+4] = a.use_thresh ? a.thresh_out : -1;
+    }
+    g_fpel_border = 0;
+}
+
+
+/* ------------------------------------------------------------------ the lookahead stage alone, stock control flow ---- */
+/* Steps 1-4 of x264_encoder_encode (encoder.c:3360-3445) without the slice encoding behind them: x264_frame_copy_picture,
+ * x264_adaptive_quant_frame, x264_frame_init_lowres, x264_lookahead_put_frame, and -- once the delay is filled --
+ * x264_lookahead_get_frames, i.e. the reference's own x264_slicetype_decide / x264_slicetype_analyse / macroblock_tree with its own
+ * request order, threads (lookahead-threads) and memoisation.  Every frame the encoder would have picked up next is reported
+ * (display index, decided type) and handed back to the frame pool.  luma: n pictures of width*height, chroma = 128.
+ * Returns the number of frames decided.  This is bench.py --impl reference for the lookahead workload. */
+XREF_API int xref_lookahead_types( void *hv, const uint8_t *luma, int n, int *out_idx, int *out_type )
+{
+    x264_t *h = hv;
+    int w = h->param.i_width, ht = h->param.i_height;
+    int cw = ( w + 1 ) / 2, ch = ( ht + 1 ) / 2;
+    uint8_t *chroma = malloc( (size_t)cw * ch );
+    if( !chroma ) return -1;
+    memset( chroma, 128, (size_t)cw * ch );
+    int n_out = 0;
+    for( int i = 0; i <= n; i++ )
+    {
+        int flushing = i == n;
+        if( !flushing )
+        {
+            x264_picture_t pic;
+            x264_picture_init( &pic );
+            pic.img.i_csp = X264_CSP_I420;
+            pic.img.i_plane = 3;
+            pic.img.plane[0] = (uint8_t*)luma + (size_t)i*w*ht; pic.img.i_stride[0] = w;
+            pic.img.plane[1] = chroma; pic.img.i_stride[1] = cw;
+            pic.img.plane[2] = chroma; pic.img.i_stride[2] = cw;
+            pic.i_pts = i;
+            if( xref_forced_types ) pic.i_type = xref_forced_types[i];
+            x264_frame_t *fenc = x264_frame_pop_unused( h, 0 );
+            if( !fenc || x264_frame_copy_picture( h, fenc, &pic ) < 0 ) { free( chroma ); return -1; }
+            if( h->param.i_width != 16 * h->mb.i_mb_width || h->param.i_height != 16 * h->mb.i_mb_height )
+                x264_frame_expand_border_mod16( h, fenc );
+            fenc->i_frame = h->frames.i_input++;
+            fenc->i_pic_struct = PIC_STRUCT_PROGRESSIVE;
+            x264_adaptive_quant_frame( h, fenc, NULL );
+            if( h->frames.b_have_lowres )
+                x264_frame_init_lowres( h, fenc );
+            x264_lookahead_put_frame( h, fenc );
+            if( h->frames.i_input <= h->frames.i_delay + 1 - h->i_thread_frames )
+                continue;
+        }
+        do
+        {
+            h->i_frame++;
+            if( !h->frames.current[0] )
+                x264_lookahead_get_frames( h );
+            if( !h->frames.current[0] )
+                break;
+            x264_frame_t *f = x264_frame_shift( h->frames.current );
+            out_idx[n_out] = f->i_frame; out_type[n_out] = f->i_type; n_out++;
+            x264_frame_push_unused( h, f );
+        } while( flushing );
+    }
+    free( chroma );
     return n_out;
 }

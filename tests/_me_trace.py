@@ -191,9 +191,12 @@ class DeviceTrace:
         self.ctx, self.t, self.x = ctx, t, x
         self.live = []
 
+        self.pairs = []                       # (device buffer, host array): what reupload() copies again
+
         def up(a, origin=0):
             d = ctx.upload(a)
             self.live.append(d)
+            self.pairs.append((d, a))
             return d + origin
         lo, co = luma_origin(t), chroma_origin(t)
         d_fenc, d_fenc_uv = up(t.fenc), up(t.fenc_uv)
@@ -205,8 +208,14 @@ class DeviceTrace:
         self.params = x.MeParams(t.me_method, t.subpel, t.me_range, t.mbcmp_satd, 1, t.mv_range, 0, 0, 0, 0, t.fpel_border)
         self.n = len(self.jobs)
         self.d_jobs = ctx.upload(self.jobs)
+        self.pairs.append((self.d_jobs, self.jobs))
         self.d_res = ctx.malloc(max(self.n, 1) * x.me_result_dtype.itemsize)
         self.live += [self.d_jobs, self.d_res]
+
+    def reupload(self):
+        """host -> HBM copy of every plane and of the job records again (bench.py's end-to-end leg)"""
+        for d, a in self.pairs:
+            self.ctx.h2d(d, a)
 
     def launch(self):
         self.ctx.check(self.ctx.L.x264cu_me_search_frame(self.ctx.h, C.byref(self.params), C.byref(self.frame), self.d_jobs, self.n, self.d_res))
@@ -235,3 +244,51 @@ def early_exit(t):
     """searches that left refine_subpel at the half-pel threshold (me.c:934-943): cost_mv is not written"""
     r = t.recs
     return (r["thresh_in"] >= 0) & ((r["cost"].astype(np.int64) * 7 >> 3) > r["thresh_in"])
+
+
+class ReplayRef(C.Structure):
+    _fields_ = [("planes", C.c_void_p * 4), ("wplane", C.c_void_p), ("uv", C.c_void_p), ("weight", (C.c_int * 4) * 3)]
+
+
+def replay_reference(t, opts, n_threads=1, preset=b"slower", sel=None):
+    """the reference's own x264_me_search_ref over the recorded searches of picture t, spread over n_threads host threads
+    (one encoder handle each: x264_t is per-thread state) -> (results int32 [n, 5], seconds of wall time)"""
+    import threading
+    import time
+    r = ref()
+    vp = C.c_void_p
+    r.xref_me_replay.argtypes = [vp, C.POINTER(C.c_int), vp, vp, C.POINTER(ReplayRef), vp, C.c_int, vp]
+    recs = np.ascontiguousarray(t.recs if sel is None else t.recs[sel])
+    n = len(recs)
+    info = (C.c_int * 18)(*[int(getattr(t, k)) for k in INFO])
+    refs = (ReplayRef * len(t.refs))()
+    for i, rf in enumerate(t.refs):
+        for k in range(4):
+            refs[i].planes[k] = rf["planes"][k].ctypes.data
+        refs[i].wplane = rf["wplane"].ctypes.data if rf["weighted"] else None
+        refs[i].uv = rf["uv"].ctypes.data
+        for a in range(3):
+            for b in range(4):
+                refs[i].weight[a][b] = rf["weight"][a][b]
+    out = np.zeros((n, 5), np.int32)
+    n_threads = max(1, min(n_threads, n))
+    handles = [r.xref_open(t.width, t.height, preset, opts, 0) for _ in range(n_threads)]
+    assert all(handles)
+    bounds = [n * i // n_threads for i in range(n_threads + 1)]
+
+    def work(k):
+        lo, hi = bounds[k], bounds[k + 1]
+        r.xref_me_replay(handles[k], info, t.fenc.ctypes.data, t.fenc_uv.ctypes.data, refs,
+                         recs.ctypes.data + lo * REC.itemsize, hi - lo, out.ctypes.data + lo * 20)
+    try:
+        th = [threading.Thread(target=work, args=(k,)) for k in range(n_threads)]
+        t0 = time.perf_counter()
+        for x_ in th:
+            x_.start()
+        for x_ in th:
+            x_.join()
+        dt = time.perf_counter() - t0
+    finally:
+        for hnd in handles:
+            r.xref_close(hnd)
+    return out, dt

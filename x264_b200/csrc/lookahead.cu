@@ -19,11 +19,15 @@
 
 using namespace x264cu;
 
-#include <time.h>
-// host-side wait accounting (printed at close when X264CU_STATS is set): where the calling thread blocks on the GPU
 struct LaHostStats { double put_sync = 0, cost_sync = 0, weight_sync = 0, ev_sync = 0; long n_put = 0, n_cost = 0, n_weight = 0, n_batch = 0, n_jobs = 0; };
+#ifdef X264CU_TUNING
+// tuning build only: host-side wait accounting (printed at close when X264CU_STATS is set): where the calling thread blocks
+#include <time.h>
 static inline double la_now() { timespec t; clock_gettime( CLOCK_MONOTONIC, &t ); return t.tv_sec + 1e-9 * t.tv_nsec; }
 #define LA_TIMED( acc, cnt, stmt ) do { double _t = la_now(); stmt; ( acc ) += la_now() - _t; ( cnt )++; } while( 0 )
+#else
+#define LA_TIMED( acc, cnt, stmt ) do { stmt; } while( 0 )
+#endif
 
 #define LOWRES_COST_MASK 0x3fff          /* common/frame.h:107-112 */
 #define LOWRES_COST_SHIFT 14
@@ -991,10 +995,12 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     if( p->me_method < X264CU_ME_DIA || p->me_method > 4 )          // esa / tesa included: the lookahead never goes beyond hex (slicetype.c:50)
         return x264cu_fail( ctx, "lookahead_open: me_method %d out of range", p->me_method );
     if( p->n_slots < 2 ) return x264cu_fail( ctx, "lookahead_open: need at least 2 frame slots" );
-    if( p->mv_range < 32 || p->mv_range > 4096 ) return x264cu_fail( ctx, "lookahead_open: mv_range %d out of range", p->mv_range );
+    if( p->mv_range < 32 || p->mv_range > 8192 ) return x264cu_fail( ctx, "lookahead_open: mv_range %d out of range", p->mv_range );
     x264cu_lookahead *la = new x264cu_lookahead;
     la->ctx = ctx; la->p = *p;
+#ifdef X264CU_TUNING
     la->stats_on = getenv( "X264CU_STATS" ) != nullptr;
+#endif
     LaDims &d = la->d;
     d.mb_w = ( p->width + 15 ) >> 4; d.mb_h = ( p->height + 15 ) >> 4; d.mb_count = d.mb_w * d.mb_h;
     la->wl = d.mb_w * 8; la->ll = d.mb_h * 8;

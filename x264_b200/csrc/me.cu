@@ -114,7 +114,7 @@ extern "C" int x264cu_me_search_batch( x264cu_ctx_t *ctx, const x264cu_me_params
     if( n <= 0 ) return 0;
     if( !d_fenc || !d_fref || !d_fref[0] || !d_fref[1] || !d_fref[2] || !d_fref[3] || !d_jobs || !d_results )
         return x264cu_fail( ctx, "me_search_batch: null argument" );
-    if( p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 )
+    if( p->lambda < 1 || p->mv_range < 32 || p->mv_range > 8192 )
         return x264cu_fail( ctx, "me_search_batch: bad parameters" );
     const uint16_t *d_tab = me_cost_table( ctx, p->lambda, p->mv_range );
     if( !d_tab ) return -1;
@@ -140,7 +140,7 @@ extern "C" int x264cu_me_search_frame( x264cu_ctx_t *ctx, const x264cu_me_params
     if( n <= 0 ) return 0;
     if( !f->d_fenc || !f->refs || f->n_refs < 1 || f->n_refs > 64 || !f->lambdas || f->n_lambdas < 1 || f->n_lambdas > 128 || !d_jobs || !d_results )
         return x264cu_fail( ctx, "me_search_frame: null / out-of-range argument" );
-    if( p->mv_range < 32 || p->mv_range > 4096 )
+    if( p->mv_range < 32 || p->mv_range > 8192 )
         return x264cu_fail( ctx, "me_search_frame: bad parameters" );
     if( f->chroma_me && ( !f->d_fenc_uv || f->fenc_uv_stride <= 0 || f->ref_uv_stride <= 0 ) )
         return x264cu_fail( ctx, "me_search_frame: chroma ME without chroma planes" );
@@ -278,7 +278,7 @@ extern "C" int x264cu_me_refine_bidir_batch( x264cu_ctx_t *ctx, const x264cu_me_
     if( n <= 0 ) return 0;
     if( !d_fenc || !d_fref0 || !d_fref1 || !d_jobs || !d_results )
         return x264cu_fail( ctx, "me_refine_bidir_batch: null argument" );
-    if( p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 )
+    if( p->lambda < 1 || p->mv_range < 32 || p->mv_range > 8192 )
         return x264cu_fail( ctx, "me_refine_bidir_batch: bad parameters" );
     const uint16_t *d_tab = me_cost_table( ctx, p->lambda, p->mv_range );
     if( !d_tab ) return -1;
@@ -355,7 +355,7 @@ extern "C" int x264cu_me_refine_qpel_batch( x264cu_ctx_t *ctx, const x264cu_me_p
     if( !ctx || !p ) return -1;
     if( n <= 0 ) return 0;
     if( !d_fenc || !d_fref || !d_jobs || !d_results ) return x264cu_fail( ctx, "me_refine_qpel_batch: null argument" );
-    if( p->subpel_refine < 0 || p->subpel_refine > 11 || p->lambda < 1 || p->mv_range < 32 || p->mv_range > 4096 )
+    if( p->subpel_refine < 0 || p->subpel_refine > 11 || p->lambda < 1 || p->mv_range < 32 || p->mv_range > 8192 )
         return x264cu_fail( ctx, "me_refine_qpel_batch: bad parameters" );
     const uint16_t *d_tab = me_cost_table( ctx, p->lambda, p->mv_range );
     if( !d_tab ) return -1;

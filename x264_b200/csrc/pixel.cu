@@ -548,8 +548,9 @@ int x264cu_pixel_cmp_mvfield( x264cu_ctx_t *ctx, int metric, int i_pixel, const 
         return x264cu_fail( ctx, "mvfield: %dx%d is not a multiple of the %dx%d block", fenc->width, fenc->height,
                             k_pixel_w[i_pixel], k_pixel_h[i_pixel] );
     if( fenc->n_planes <= 0 ) return 0;
+#ifdef X264CU_TUNING        /* tuning build only (x264_b200/build.py --variant tuning -DX264CU_TUNING): not in the product library */
     if( metric == X264CU_SATD && i_pixel == X264CU_PIXEL_16x16 )
-    {   // tuning hook (profiling only): alternative tile / pipeline shapes for the headline kernel
+    {   // alternative tile / pipeline shapes for the headline kernel
         const char *e = getenv( "X264CU_MVF_CFG" );
         const int cfg = e ? atoi( e ) : 0;
         switch( cfg )
@@ -563,6 +564,7 @@ int x264cu_pixel_cmp_mvfield( x264cu_ctx_t *ctx, int metric, int i_pixel, const 
             default: break;
         }
     }
+#endif
     switch( metric )
     {
         case X264CU_SAD:  MVF_SIZE( M_SAD ) break;
