@@ -320,7 +320,8 @@ float x264cu_lookahead_get_weighted_cost_delta( x264cu_lookahead_t *la, int slot
  * x264cu_lookahead_frame_cost exactly where the reference calls slicetype_frame_cost -- MB-tree's and the
  * rate control's cost requests included, because the memoised B costs depend on request order
  * (slicetype.c:629-642).  Plain C; no device code.
- * Not covered: VBV lookahead (rejected at open), 2-pass stats, blu-ray compatible open-GOP.
+ * Not covered: 2-pass statistics, blu-ray compatible open-GOP, the planned cpb durations of the VBV plan and the intra-refresh
+ * column correction of x264_rc_analyse_slice (la.vbv together with intra_refresh is rejected at open).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct x264cu_slicetype x264cu_slicetype_t;
 
@@ -336,8 +337,9 @@ typedef struct
     int frame_reference;          /* h->param.i_frame_reference */
     int rc_cqp;                   /* h->param.rc.i_rc_method == X264_RC_CQP */
     int fps_num, fps_den;         /* h->param.i_fps_num / i_fps_den (constant frame rate); 0 = 25/1.  MB-tree's duration factors */
-    float qcompress;              /* h->param.rc.f_qcompress; 0 = 0.6.  MB-tree strength = 5 * (1 - qcompress) */
-    float aq_strength;            /* h->param.rc.f_aq_strength; 0 = 1.0.  Used by x264cu_slicetype_step_i420 (la.aq_mode = the mode, 0..3) */
+    float qcompress;              /* h->param.rc.f_qcompress (0..1; 0 is legal: MB-tree strength = 5 * (1 - qcompress)); negative = the default 0.6 */
+    float aq_strength;            /* h->param.rc.f_aq_strength; 0 switches adaptive quantisation off as in the reference (encoder.c:1094-1097);
+                                     negative = the default 1.0.  Used by x264cu_slicetype_step_i420 (la.aq_mode = the mode, 0..3) */
     int open_gop;                 /* h->param.b_open_gop (without b_bluray_compat) */
     int intra_refresh;            /* h->param.b_intra_refresh: no keyframes but the first, scene cuts become I pictures */
 } x264cu_slicetype_params_t;
@@ -369,6 +371,9 @@ void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *st, int prefetch );
  * analysis never looks at more than i_slicetype_length+1 pictures (b_deterministic, slicetype.c:1480-1485), so the
  * decisions do not change -- only the searches of the newest pictures get time to finish on the second stream. */
 void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *st, int pictures );
+/* pictures whose searches are gathered into one prefetch launch (1..16; default 12 for lookaheads >= 12, else 1; before the first
+ * picture).  A launch needs several dozen independent searches to fill the GPU; the decisions do not depend on it. */
+void x264cu_slicetype_set_prefetch_group( x264cu_slicetype_t *st, int pictures );
 /* pic_in->i_type of the NEXT picture queued with x264cu_slicetype_step* (forced frame types: a qpfile, an application's keyframe
  * request; X264CU_TYPE_KEYFRAME = IDR, or I with open-GOP); AUTO again afterwards.  The analysis respects it exactly as
  * x264_slicetype_analyse / x264_slicetype_decide do (i_forced_type, slicetype.c:1534-1539, :1656, :1690-1738, :1803-1828). */

@@ -56,6 +56,14 @@ class SlicetypeParams(C.Structure):
                                                                   "fps_num", "fps_den")] + [("qcompress", C.c_float), ("aq_strength", C.c_float),
                                                                                                   ("open_gop", C.c_int), ("intra_refresh", C.c_int)]
 
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        # negative = the reference's defaults (0.6 / 1.0); zero is a legal value of both
+        if len(a) <= 12 and "qcompress" not in kw:
+            self.qcompress = -1.0
+        if len(a) <= 13 and "aq_strength" not in kw:
+            self.aq_strength = -1.0
+
 
 TYPE_NAMES = {0: "AUTO", 1: "IDR", 2: "I", 3: "P", 4: "BREF", 5: "B"}
 
@@ -247,7 +255,7 @@ class Slicetype:
     decide(frames) runs a whole sequence the way x264_encoder_encode would and returns [(display_index, type)] in coded order."""
 
     def __init__(self, ctx, width, height, keyint_max=250, keyint_min=25, scenecut_threshold=40, b_adapt=1, b_pyramid=2,
-                 rc_lookahead=40, psy=1, frame_reference=3, rc_cqp=0, fps_num=0, fps_den=0, qcompress=0.0, aq_strength=0.0, open_gop=0, intra_refresh=0, **la_kwargs):
+                 rc_lookahead=40, psy=1, frame_reference=3, rc_cqp=0, fps_num=0, fps_den=0, qcompress=-1.0, aq_strength=-1.0, open_gop=0, intra_refresh=0, **la_kwargs):
         self.ctx, self.L = ctx, ctx.L
         la = dict(subpel_refine=7, me_method=1, me_range=16, mv_range=512, bframes=3, bframe_bias=0, weighted_bipred=1,
                   aq_mode=1, mb_tree=1, vbv=0, n_slots=0, weighted_pred=0)
