@@ -489,6 +489,11 @@ def run_st(backend, ci, params_bytes=None, ctx=None):
         p, types = host.reference_types(preset, opts, w, h, frames)
     else:
         p = SlicetypeParams.from_buffer_copy(bytes(params_bytes))
+        # the fixture was written when 0 meant "the reference's default" for these two; a negative value says that now
+        if p.qcompress == 0:
+            p.qcompress = -1.0
+        if p.aq_strength == 0:
+            p.aq_strength = -1.0
         if backend == "oracle":
             types = host.decide_with(_libs.slicetype_oracle_lib(), p, frames)
         else:
@@ -542,6 +547,11 @@ def run_mbtree(backend, params_bytes=None, ctx=None):
         p, types = host.reference_types(preset, opts, w, h, frames, qp)
     else:
         p = SlicetypeParams.from_buffer_copy(bytes(params_bytes))
+        # the fixture was written when 0 meant "the reference's default" for these two; a negative value says that now
+        if p.qcompress == 0:
+            p.qcompress = -1.0
+        if p.aq_strength == 0:
+            p.aq_strength = -1.0
         if backend == "oracle":
             types = host.decide_with(_libs.slicetype_oracle_lib(), p, frames, qp)
         else:
