@@ -1137,3 +1137,52 @@ XREF_API int xref_lookahead_types( void *hv, const uint8_t *luma, int n, int *ou
     free( chroma );
     return n_out;
 }
+
+
+/* The same as xref_encode_i420, also reporting what came out: an FNV-1a hash over every byte of the bitstream, its size, and the
+ * display index / type of each coded frame.  Used to show that the encoder's OUTPUT is unchanged when its lookahead runs behind
+ * the offload hooks (libx264ref_b200.so, integration/x264_b200_hooks.c). */
+XREF_API int xref_encode_i420_hash( void *hv, const uint8_t *yuv, int n, uint64_t *hash, int64_t *bytes, int *out_idx, int *out_type )
+{
+    x264_t *h = hv;
+    int w = h->param.i_width, ht = h->param.i_height;
+    int cw = ( w + 1 ) / 2, ch = ( ht + 1 ) / 2;
+    size_t fsz = (size_t)w*ht + 2*(size_t)cw*ch;
+    int n_out = 0;
+    uint64_t hv64 = 1469598103934665603ull;
+    int64_t total = 0;
+    x264_nal_t *nal; int i_nal;
+    x264_picture_t pic_in, pic_out;
+    for( int i = 0; i < n || x264_encoder_delayed_frames( h ); i++ )
+    {
+        int r;
+        if( i < n )
+        {
+            x264_picture_init( &pic_in );
+            pic_in.img.i_csp = X264_CSP_I420;
+            pic_in.img.i_plane = 3;
+            pic_in.img.plane[0] = (uint8_t*)yuv + i*fsz;             pic_in.img.i_stride[0] = w;
+            pic_in.img.plane[1] = pic_in.img.plane[0] + (size_t)w*ht; pic_in.img.i_stride[1] = cw;
+            pic_in.img.plane[2] = pic_in.img.plane[1] + (size_t)cw*ch; pic_in.img.i_stride[2] = cw;
+            pic_in.i_pts = i;
+            r = x264_encoder_encode( h, &nal, &i_nal, &pic_in, &pic_out );
+        }
+        else
+            r = x264_encoder_encode( h, &nal, &i_nal, NULL, &pic_out );
+        if( r < 0 ) return -1;
+        if( r > 0 )
+        {
+            for( int k = 0; k < i_nal; k++ )
+                for( int j = 0; j < nal[k].i_payload; j++ )
+                    hv64 = ( hv64 ^ nal[k].p_payload[j] ) * 1099511628211ull;
+            total += r;
+            if( out_idx ) { out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; }
+            n_out++;
+        }
+    }
+    *hash = hv64; *bytes = total;
+    return n_out;
+}
+
+/* 1 if the encoder behind hv still has its offload hooks switched on (h->param.b_opencl survives only if the backend came up) */
+XREF_API int xref_offload_active( void *hv ) { return ((x264_t*)hv)->param.b_opencl; }
