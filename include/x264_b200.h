@@ -258,6 +258,19 @@ int    x264cu_lookahead_export_search( x264cu_lookahead_t *la, int slot, int lis
 int    x264cu_lookahead_import_search( x264cu_lookahead_t *la, int slot, int list, int dist, const void *d_src );
 int    x264cu_lookahead_import_done( x264cu_lookahead_t *la );
 
+/* Cost requests answered ahead of time: finalize -- everything slicetype_mb_cost does once the vectors exist (slicetype.c:579-652,
+ * :706-790) -- of n triples in ONE launch, their result records read back in one copy.  Triple i = (picture in b_slot[i], list-0
+ * reference in p0_slot[i] at distance d0[i] >= 1, list-1 reference in p1_slot[i] at distance d1[i]; d1 = 0: a P cost, p1_slot =
+ * b_slot).  Computed in the variant that uses the later reference's list-0 vectors for the temporal-direct candidate
+ * (slicetype.c:629-642), which is what the reference's request order yields nearly always; x264cu_lookahead_frame_cost uses the
+ * record when the request it serves is of that variant and falls back to computing on demand otherwise, so results never depend
+ * on what was speculated.  Triples whose searches have not been launched (or were weighted), that are already answered, and every
+ * triple when row sums are kept (vbv) are skipped.  Runs on its own low-priority stream behind the searches it reads. */
+int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b_slot, const int *p0_slot, const int *p1_slot,
+                                     const int *d0, const int *d1 );
+/* triples computed ahead of time so far; *hits = cost requests served from them, *misses = computed on demand */
+long x264cu_lookahead_speculation_stats( x264cu_lookahead_t *la, long *hits, long *misses );
+
 /* 1 if x264_weights_analyse( fenc, ref ) would leave at its early exit (means and variances of the two pictures agree:
  * no weight, slicetype.c:316-330) -- then the list-0 search of that pair is the same whether it is first requested as a P or
  * as a B cost, and may be run ahead of time with x264cu_lookahead_search_batch.  0 if a weight may be chosen (fade): that
@@ -371,6 +384,10 @@ void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *st, int prefetch );
  * analysis never looks at more than i_slicetype_length+1 pictures (b_deterministic, slicetype.c:1480-1485), so the
  * decisions do not change -- only the searches of the newest pictures get time to finish on the second stream. */
 void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *st, int pictures );
+/* speculate = 1 (default): with every prefetch launch, all cost requests the decision can make about the new pictures are computed
+ * too (x264cu_lookahead_finalize_batch) -- a request then costs the calling thread a table lookup instead of a launch, a copy and
+ * a wait.  0: every request is computed when it is made.  The decisions are identical either way. */
+void x264cu_slicetype_set_speculation( x264cu_slicetype_t *st, int speculate );
 /* pictures whose searches are gathered into one prefetch launch (1..16; default 12 for lookaheads >= 12, else 1; before the first
  * picture).  A launch needs several dozen independent searches to fill the GPU; the decisions do not depend on it. */
 void x264cu_slicetype_set_prefetch_group( x264cu_slicetype_t *st, int pictures );

@@ -1140,7 +1140,7 @@ XREF_API int xref_lookahead_types( void *hv, const uint8_t *luma, int n, int *ou
 
 
 /* The same as xref_encode_i420, also reporting what came out: an FNV-1a hash over every byte of the bitstream, its size, and the
- * display index / type of each coded frame.  Used to show that the encoder's OUTPUT is unchanged when its lookahead runs behind
+ * display index / type of each coded frame (SEI units excepted: they spell out the options).  Used to show that the encoder's OUTPUT is unchanged when its lookahead runs behind
  * the offload hooks (libx264ref_b200.so, integration/x264_b200_hooks.c). */
 XREF_API int xref_encode_i420_hash( void *hv, const uint8_t *yuv, int n, uint64_t *hash, int64_t *bytes, int *out_idx, int *out_type )
 {
@@ -1173,9 +1173,13 @@ XREF_API int xref_encode_i420_hash( void *hv, const uint8_t *yuv, int n, uint64_
         if( r > 0 )
         {
             for( int k = 0; k < i_nal; k++ )
+            {   /* the SEI carries the option string ("... opencl=1", x264_param2string, common/base.c:1446): everything but it */
+                if( nal[k].i_type == NAL_SEI )
+                    continue;
                 for( int j = 0; j < nal[k].i_payload; j++ )
                     hv64 = ( hv64 ^ nal[k].p_payload[j] ) * 1099511628211ull;
-            total += r;
+                total += nal[k].i_payload;
+            }
             if( out_idx ) { out_idx[n_out] = (int)pic_out.i_pts; out_type[n_out] = pic_out.i_type; }
             n_out++;
         }

@@ -83,6 +83,11 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n, const int *fen
     (void)la; (void)n; (void)fenc; (void)ref; (void)list; (void)dist;
     return 0;
 }
+/* answering cost requests ahead of time is a scheduling matter too: here every request is computed when it is made */
+int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b, const int *p0, const int *p1, const int *d0, const int *d1 )
+{
+    (void)la; (void)n; (void)b; (void)p0; (void)p1; (void)d0; (void)d1; return 0;
+}
 void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on ) { (void)la; (void)on; }
 int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int a, int b ) { (void)la; (void)a; (void)b; return 0; }
 

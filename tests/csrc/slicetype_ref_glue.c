@@ -51,6 +51,11 @@ int x264cu_lookahead_search_batch( x264cu_lookahead_t *la, int n, const int *a, 
 {
     (void)la; (void)n; (void)a; (void)b; (void)c; (void)d; return 0;
 }
+/* answering cost requests ahead of time is a scheduling matter too: here every request is computed when it is made */
+int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b, const int *p0, const int *p1, const int *d0, const int *d1 )
+{
+    (void)la; (void)n; (void)b; (void)p0; (void)p1; (void)d0; (void)d1; return 0;
+}
 int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
 {
     /* the reference takes a frames[] array of frame pointers: map indices p0..p1 to the slots' frames */

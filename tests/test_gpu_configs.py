@@ -139,3 +139,33 @@ def test_odd_and_tiny_sizes_match_oracle_harness(ctx, wh):
     got = gpu_decide(ctx, p, frames)
     want = host.decide_with(slicetype_oracle_lib(), p, frames)
     assert got == want, [z for z in zip(got, want) if z[0] != z[1]][:6]
+
+
+@pytest.mark.parametrize("cfg", [dict(bframes=3, b_adapt=1, rc_lookahead=40), dict(bframes=5, b_adapt=2, rc_lookahead=30),
+                                 dict(bframes=3, b_adapt=1, rc_lookahead=40, weighted_pred=1), dict(bframes=8, b_adapt=2, rc_lookahead=60)])
+def test_speculative_cost_requests_do_not_change_anything(ctx, cfg):
+    """x264cu_lookahead_finalize_batch answers cost requests ahead of time in the variant the reference's order usually yields;
+    a request of the other variant is computed on demand.  Decisions and MB-tree offsets with and without it, and against the
+    oracle-backed host logic, must be identical -- and the speculation must actually be used."""
+    w, h, n = 640, 368, 90
+    frames = big_sequence(w, h, n, seed=77, cut_at=41)
+    if cfg.get("weighted_pred"):
+        for i in range(10):
+            frames[i] = np.clip(frames[i].astype(np.float32) * (0.4 + 0.06 * i) + 2 * i, 0, 255).astype(np.uint8)
+    p = slicetype_params(w, h, **cfg)
+    res = {}
+    for spec in (1, 0):
+        st = x.Slicetype.from_params(ctx, p)
+        try:
+            st.set_speculation(spec)
+            qp = {}
+            res[spec] = (st.decide(frames, qp), qp, st.speculation_stats())
+        finally:
+            st.close()
+    assert res[1][0] == res[0][0]
+    assert res[1][1].keys() == res[0][1].keys() and all(np.array_equal(res[1][1][k], res[0][1][k]) for k in res[0][1])
+    launched, hits, misses = res[1][2]
+    assert launched > 0 and hits > misses, res[1][2]
+    assert res[0][2][0] == 0 and res[0][2][1] == 0
+    want = host.decide_with(slicetype_oracle_lib(), p, frames, {})
+    assert res[1][0] == want

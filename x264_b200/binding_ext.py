@@ -80,6 +80,11 @@ def bind(L):
     L.x264cu_slicetype_step_device.argtypes = [vp, vp, ss, vp, C.POINTER(ci), C.POINTER(ci)]
     L.x264cu_slicetype_set_prefetch.argtypes = [vp, ci]
     L.x264cu_slicetype_set_run_ahead.argtypes = [vp, ci]
+    L.x264cu_slicetype_set_speculation.argtypes = [vp, ci]
+    L.x264cu_slicetype_set_prefetch_group.argtypes = [vp, ci]
+    L.x264cu_lookahead_speculation_stats.restype = C.c_long
+    L.x264cu_lookahead_speculation_stats.argtypes = [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+    L.x264cu_lookahead_finalize_batch.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     L.x264cu_slicetype_set_async_upload.argtypes = [vp, ci]
     L.x264cu_slicetype_get_qp_offset.argtypes = [vp, ci, vp]
     L.x264cu_slicetype_set_shard.argtypes = [vp, ci, ci, vp, vp]
@@ -318,6 +323,18 @@ class Slicetype:
 
     def set_run_ahead(self, k):
         self.L.x264cu_slicetype_set_run_ahead(self.h, int(k))
+
+    def set_speculation(self, on):
+        self.L.x264cu_slicetype_set_speculation(self.h, int(on))
+
+    def set_prefetch_group(self, k):
+        self.L.x264cu_slicetype_set_prefetch_group(self.h, int(k))
+
+    def speculation_stats(self):
+        """(triples computed ahead of time, cost requests served from them, cost requests computed on demand)"""
+        hits, misses = C.c_long(), C.c_long()
+        n = self.L.x264cu_lookahead_speculation_stats(self.L.x264cu_slicetype_lookahead(self.h), C.byref(hits), C.byref(misses))
+        return int(n), hits.value, misses.value
 
     def set_async_upload(self, on):
         """page-locked pictures passed to step() are read in place; keep them unmodified until four more pictures have been queued"""

@@ -504,8 +504,7 @@ __device__ __forceinline__ uint32_t avg4w( uint32_t a, uint32_t b, int weight ) 
 // 128-thread blocks at <= 64 registers: one fits on an SM beside two resident search CTAs (LA_FIN_THREADS * 64 registers are
 // what the search kernel's register cap leaves free), so a cost request does not wait for a search CTA to retire
 #define LA_FIN_THREADS 128
-__global__ void __launch_bounds__( LA_FIN_THREADS, 8 )
-finalize_kernel( LaDims d, LaFinalizeArgs A )
+__device__ __forceinline__ void finalize_body( const LaDims &d, const LaFinalizeArgs &A )
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = lane & 3;
@@ -628,12 +627,26 @@ finalize_kernel( LaDims d, LaFinalizeArgs A )
     }
     if( lead )
     {
-        if( A.b_inter ) atomicAdd( &A.row_inter[mb_y], bcost_aq );
-        atomicAdd( &A.row_intra[mb_y], icost_aq );
+        if( A.b_inter && A.row_inter ) atomicAdd( &A.row_inter[mb_y], bcost_aq );
+        if( A.row_intra ) atomicAdd( &A.row_intra[mb_y], icost_aq );
         A.costs[mb] = (uint16_t)( min( bcost, LOWRES_COST_MASK ) + ( list_used << LOWRES_COST_SHIFT ) );
         // i_intra_cost IS lowres_costs[0][0] in the reference (frame.c:287): an I request leaves the clipped value behind
         if( !A.b_inter ) A.intra[mb] = min( bcost, LOWRES_COST_MASK );
     }
+}
+
+__global__ void __launch_bounds__( LA_FIN_THREADS, 8 )
+finalize_kernel( LaDims d, LaFinalizeArgs A )
+{
+    finalize_body( d, A );
+}
+
+// many cost requests in one launch (x264cu_lookahead_finalize_batch): blockIdx.y selects the request
+__global__ void __launch_bounds__( LA_FIN_THREADS, 8 )
+finalize_batch_kernel( LaDims d, const LaFinalizeArgs *__restrict__ args )
+{
+    const LaFinalizeArgs A = args[blockIdx.y];
+    finalize_body( d, A );
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -845,8 +858,11 @@ struct LaSlotHost
     float weighted_cost_delta[LA_MAX_B + 1];   // f_weighted_cost_delta (slicetype.c:462-463, X264_WEIGHTP_FAKE only)
     // event (ring index, sequence number) of the last launch that reads or writes this slot on each of the two search streams
     // ([0], [1]: they are not ordered against each other) and of the last import on the exchange stream ([2])
-    int last_search_ev[3] = { -1, -1, -1 };
-    unsigned long long last_search_seq[3] = { 0, 0, 0 };
+    // ... and of the last batch of speculative cost requests ([3])
+    int last_search_ev[4] = { -1, -1, -1, -1 };
+    unsigned long long last_search_seq[4] = { 0, 0, 0, 0 };
+    // cost requests answered ahead of time (x264cu_lookahead_finalize_batch): which batch holds the record of (b-p0, p1-b)
+    struct Spec { unsigned long long batch; int index; } spec[LA_MAX_B + 2][LA_MAX_B + 2];
     cudaEvent_t ev_ready = nullptr;  // recorded on the upload stream when the picture's planes / reset arrays are in place
     bool main_waited = true;         // the context's stream has been ordered after ev_ready
     bool xch_dirty = false;
@@ -910,6 +926,16 @@ struct x264cu_lookahead
     unsigned int *d_tickets = nullptr;   // work-distribution counters of the search launches (ring of 64)
     unsigned int ticket_next = 0;
     uint8_t *d_weight_plane = nullptr;   // h->mb.p_weight_buf[0]: weighted copy of one reference F plane (padded)
+    // speculative cost requests: a ring of batches, each with its request descriptors and result records on both sides
+#define LA_SPEC_RING 128
+#define LA_SPEC_MAX 4096             /* requests per batch */
+    cudaStream_t spec_stream = nullptr;
+    LaFinalizeArgs *h_spec_args = nullptr, *d_spec_args = nullptr;    // [LA_SPEC_MAX]: staging of one batch's descriptors
+    cudaEvent_t spec_args_ev = nullptr;                               // the staging buffer's last upload
+    int32_t *d_spec_rec = nullptr, *h_spec_rec = nullptr;             // [LA_SPEC_RING][LA_SPEC_MAX][8]
+    cudaEvent_t spec_ev[LA_SPEC_RING] = {};                           // batch complete, records on the host
+    unsigned long long spec_seq[LA_SPEC_RING] = {}, spec_next = 1;    // which batch each ring entry holds
+    long spec_hits = 0, spec_misses = 0, spec_launched = 0;
     unsigned long long *h_stats = nullptr;
 };
 
@@ -933,6 +959,7 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     if( la->up_stream ) cudaStreamSynchronize( la->up_stream );
     if( la->xch_stream ) cudaStreamSynchronize( la->xch_stream );
     if( la->mt_stream ) cudaStreamSynchronize( la->mt_stream );
+    if( la->spec_stream ) cudaStreamSynchronize( la->spec_stream );
     for( int i = 0; i < 2; i++ ) if( la->search_streams[i] ) cudaStreamSynchronize( la->search_streams[i] );
     if( la->stats_on )
     {
@@ -962,11 +989,15 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     {
         auto &ax = la->ctx->aux_streams;
         for( size_t i = 0; i < ax.size(); )
-            if( ax[i] == la->up_stream || ax[i] == la->xch_stream || ax[i] == la->mt_stream || ax[i] == la->search_streams[0] || ax[i] == la->search_streams[1] ) ax.erase( ax.begin() + i ); else i++;
+            if( ax[i] == la->up_stream || ax[i] == la->xch_stream || ax[i] == la->mt_stream || ax[i] == la->spec_stream || ax[i] == la->search_streams[0] || ax[i] == la->search_streams[1] ) ax.erase( ax.begin() + i ); else i++;
     }
     if( la->up_stream ) { cudaStreamSynchronize( la->up_stream ); cudaStreamDestroy( la->up_stream ); }
     if( la->xch_stream ) { cudaStreamSynchronize( la->xch_stream ); cudaStreamDestroy( la->xch_stream ); }
     if( la->mt_stream ) { cudaStreamSynchronize( la->mt_stream ); cudaStreamDestroy( la->mt_stream ); }
+    if( la->spec_stream ) { cudaStreamSynchronize( la->spec_stream ); cudaStreamDestroy( la->spec_stream ); }
+    cudaFreeHost( la->h_spec_args ); cudaFreeHost( la->h_spec_rec ); cudaFree( la->d_spec_args ); cudaFree( la->d_spec_rec );
+    if( la->spec_args_ev ) cudaEventDestroy( la->spec_args_ev );
+    for( int i = 0; i < LA_SPEC_RING; i++ ) if( la->spec_ev[i] ) cudaEventDestroy( la->spec_ev[i] );
     if( la->ev_mt_dep ) cudaEventDestroy( la->ev_mt_dep );
     for( int i = 0; i < 32; i++ ) if( la->ev_mt_ckpt[i] ) cudaEventDestroy( la->ev_mt_ckpt[i] );
     for( int i = 0; i < 2; i++ ) { cudaFreeHost( la->h_luma[i] ); if( la->h_luma_ev[i] ) cudaEventDestroy( la->h_luma_ev[i] ); }
@@ -1073,6 +1104,14 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     if( ok && cudaStreamCreateWithPriority( &la->up_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaStreamCreateWithPriority( &la->xch_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaStreamCreateWithPriority( &la->mt_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
+    if( ok && cudaStreamCreateWithPriority( &la->spec_stream, cudaStreamNonBlocking, prio_lo ) != cudaSuccess ) ok = false;
+    if( ok && cudaMallocHost( (void **)&la->h_spec_args, sizeof( LaFinalizeArgs ) * LA_SPEC_MAX ) != cudaSuccess ) ok = false;
+    if( ok && cudaMallocHost( (void **)&la->h_spec_rec, (size_t)LA_SPEC_RING * LA_SPEC_MAX * 32 ) != cudaSuccess ) ok = false;
+    alloc( (void **)&la->d_spec_args, sizeof( LaFinalizeArgs ) * LA_SPEC_MAX );
+    alloc( (void **)&la->d_spec_rec, (size_t)LA_SPEC_RING * LA_SPEC_MAX * 32 );
+    if( ok && cudaEventCreateWithFlags( &la->spec_args_ev, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
+    for( int i = 0; i < LA_SPEC_RING; i++ )
+        if( ok && cudaEventCreateWithFlags( &la->spec_ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->ev_mt_dep, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     for( int i = 0; i < 32; i++ )
         if( ok && cudaEventCreateWithFlags( &la->ev_mt_ckpt[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
@@ -1142,6 +1181,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     ctx->aux_streams.push_back( la->up_stream );
     ctx->aux_streams.push_back( la->xch_stream );
     ctx->aux_streams.push_back( la->mt_stream );
+    ctx->aux_streams.push_back( la->spec_stream );
     for( int i = 0; i < 2; i++ ) ctx->aux_streams.push_back( la->search_streams[i] );
     *out = la;
     return 0;
@@ -1160,6 +1200,7 @@ static int la_reset_slot( x264cu_lookahead *la, int slot, const uint16_t *h_inv_
     memset( s.searched, 0, sizeof( s.searched ) );
     memset( s.requested, 0, sizeof( s.requested ) );
     memset( s.pending, -1, sizeof( s.pending ) );
+    memset( s.spec, 0, sizeof( s.spec ) );
     s.b_intra_calculated = 0;
     s.gen++;
     s.intra_on_device = false;
@@ -1211,7 +1252,7 @@ static int la_put_begin( x264cu_lookahead *la, int slot )
         s.mt_last = 0;
     }
     // a ring entry recorded again since belongs to a launch that had finished by then (search_batch waits before reuse)
-    for( int k = 0; k < 3; k++ )
+    for( int k = 0; k < 4; k++ )
     {
         if( s.last_search_ev[k] >= 0 && la->ev_seq[s.last_search_ev[k]] == s.last_search_seq[k] )
             CU_CHECK( ctx, cudaStreamWaitEvent( la->up_stream, la->ev[s.last_search_ev[k]], 0 ) );
@@ -1876,6 +1917,101 @@ int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int fenc_slot, int 
     return fabsf( ref_mean - fenc_mean ) < 0.5f && fabsf( 1.f - guess_scale ) < epsilon;
 }
 
+/* Cost requests answered ahead of time.  finalize (the bidir candidates, the list / intra choice, the sums) of a triple is a pure
+ * function of three pictures' planes and vectors, given which of two variants applies: with or without the temporal-direct
+ * vectors of the later reference (slicetype.c:629-642 -- whether that reference's P search had been ASKED FOR by then, which only
+ * the host's request order knows).  The decision nearly always asks in an order that has them (path cost: the P cost first), so
+ * that variant is computed for every triple a window can ask about as soon as its searches are queued: n triples in ONE launch,
+ * their records read back in ONE copy.  x264cu_lookahead_frame_cost then finds the record instead of launching, copying back and
+ * waiting per request; a request that needs the other variant, a weighted search or row sums (VBV) takes the on-demand path. */
+int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b_slot, const int *p0_slot, const int *p1_slot,
+                                     const int *d0, const int *d1 )
+{
+    X264CU_ENTER_LA( la );
+    if( !la || ( n > 0 && ( !b_slot || !p0_slot || !p1_slot || !d0 || !d1 ) ) ) return -1;
+    x264cu_ctx *ctx = la->ctx;
+    const LaDims &d = la->d;
+    if( n <= 0 || la->p.vbv ) return 0;
+    if( n > LA_SPEC_MAX ) n = LA_SPEC_MAX;
+    const int B1 = d.B + 1, B2w = d.B + 2;
+    const int ring = (int)( la->spec_next % LA_SPEC_RING );
+    // ring entry reuse (its batch is hundreds of pictures old) and the descriptor staging buffer (its last upload)
+    CU_CHECK( ctx, cudaEventSynchronize( la->spec_ev[ring] ) );
+    CU_CHECK( ctx, cudaEventSynchronize( la->spec_args_ev ) );
+    int32_t *d_rec = la->d_spec_rec + (size_t)ring * LA_SPEC_MAX * 8;
+    std::vector<char> ev_seen( la->n_ev, 0 ), slot_seen( la->slots.size(), 0 );
+    auto wait_ev = [&]( int e ) -> int {
+        if( e >= 0 && !ev_seen[e] ) { ev_seen[e] = 1; CU_CHECK( ctx, cudaStreamWaitEvent( la->spec_stream, la->ev[e], 0 ) ); }
+        return 0;
+    };
+    int m = 0;
+    for( int i = 0; i < n; i++ )
+    {
+        const int sb = b_slot[i], s0 = p0_slot[i], s1 = p1_slot[i], i0 = d0[i], i1 = d1[i];
+        for( int sl : { sb, s0, s1 } )
+            if( sl < 0 || sl >= (int)la->slots.size() || !la->slots[sl].in_use ) return x264cu_fail( ctx, "finalize_batch: empty slot %d", sl );
+        if( i0 < 1 || i1 < 0 || i0 > B1 || i1 > d.B || i0 + i1 > B1 ) return x264cu_fail( ctx, "finalize_batch: bad distances (%d,%d)", i0, i1 );
+        LaSlotHost &fenc = la->slots[sb], &f1 = la->slots[s1];
+        // only triples whose searches exist (unweighted, launched ahead of time) and that have not been answered yet
+        if( fenc.cost_est[i0][i1] >= 0 || fenc.spec[i0][i1].batch || !fenc.searched[0][i0 - 1] ) continue;
+        if( i1 && ( !fenc.searched[1][i1 - 1] || !f1.searched[0][i0 + i1 - 1] ) ) continue;
+        for( int sl : { sb, s0, s1 } )
+            if( !slot_seen[sl] ) { slot_seen[sl] = 1; CU_CHECK( ctx, cudaStreamWaitEvent( la->spec_stream, la->slots[sl].ev_ready, 0 ) ); }
+        if( wait_ev( fenc.pending[0][i0 - 1] ) ) return -1;
+        if( i1 && ( wait_ev( fenc.pending[1][i1 - 1] ) || wait_ev( f1.pending[0][i0 + i1 - 1] ) ) ) return -1;
+        LaFinalizeArgs &A = la->h_spec_args[m];
+        memset( &A, 0, sizeof( A ) );
+        A.fenc = fenc.dev.planes[0];
+        for( int k = 0; k < 4; k++ ) { A.ref0[k] = la->slots[s0].dev.planes[k]; A.ref1[k] = f1.dev.planes[k]; }
+        A.b_inter = 1; A.b_bidir = i1 != 0;
+        A.mvs0 = fenc.dev.mvs + (size_t)( 0 * B1 + i0 - 1 ) * d.mb_count * 2;
+        A.cost0 = fenc.dev.mv_costs + (size_t)( 0 * B1 + i0 - 1 ) * d.mb_count;
+        if( i1 )
+        {
+            A.mvs1 = fenc.dev.mvs + (size_t)( 1 * B1 + i1 - 1 ) * d.mb_count * 2;
+            A.cost1 = fenc.dev.mv_costs + (size_t)( 1 * B1 + i1 - 1 ) * d.mb_count;
+            A.mvr = f1.dev.mvs + (size_t)( 0 * B1 + i0 + i1 - 1 ) * d.mb_count * 2;
+        }
+        A.intra = fenc.dev.intra; A.qscale = fenc.dev.qscale;
+        A.costs = fenc.dev.costs + (size_t)( i0 * B2w + i1 ) * d.mb_count;
+        A.row_inter = nullptr; A.row_intra = nullptr;               // row sums are a VBV matter: on demand
+        A.record = d_rec + m * 8;
+        A.dist_scale_factor = i1 ? ( ( i0 << 8 ) + ( ( i0 + i1 ) >> 1 ) ) / ( i0 + i1 ) : 128;
+        A.bipred_weight = d.bipred_weighted ? 64 - ( A.dist_scale_factor >> 2 ) : 32;
+        fenc.spec[i0][i1].batch = la->spec_next; fenc.spec[i0][i1].index = m;
+        m++;
+    }
+    if( !m ) return 0;
+    CU_CHECK( ctx, cudaMemcpyAsync( la->d_spec_args, la->h_spec_args, sizeof( LaFinalizeArgs ) * m, cudaMemcpyHostToDevice, la->spec_stream ) );
+    CU_CHECK( ctx, cudaEventRecord( la->spec_args_ev, la->spec_stream ) );
+    CU_CHECK( ctx, cudaMemsetAsync( d_rec, 0, (size_t)m * 32, la->spec_stream ) );
+    const dim3 grid( ( d.mb_count + LA_FIN_THREADS / 4 - 1 ) / ( LA_FIN_THREADS / 4 ), m );
+    finalize_batch_kernel<<<grid, LA_FIN_THREADS, 0, la->spec_stream>>>( d, la->d_spec_args );
+    CU_LAUNCH_CHECK( ctx );
+    CU_CHECK( ctx, cudaMemcpyAsync( la->h_spec_rec + (size_t)ring * LA_SPEC_MAX * 8, d_rec, (size_t)m * 32, cudaMemcpyDeviceToHost, la->spec_stream ) );
+    CU_CHECK( ctx, cudaEventRecord( la->spec_ev[ring], la->spec_stream ) );
+    la->spec_seq[ring] = la->spec_next++;
+    la->spec_launched += m;
+    {   // the slots' next uploads wait for this batch (it reads their planes and vectors)
+        const int e = la->ev_next;
+        la->ev_next = ( la->ev_next + 1 ) % la->n_ev;
+        CU_CHECK( ctx, cudaEventSynchronize( la->ev[e] ) );
+        CU_CHECK( ctx, cudaEventRecord( la->ev[e], la->spec_stream ) );
+        la->ev_seq[e] = la->ev_seq_next++;
+        for( size_t sl = 0; sl < la->slots.size(); sl++ )
+            if( slot_seen[sl] ) { la->slots[sl].last_search_ev[3] = e; la->slots[sl].last_search_seq[3] = la->ev_seq[e]; }
+    }
+    return 0;
+}
+
+long x264cu_lookahead_speculation_stats( x264cu_lookahead_t *la, long *hits, long *misses )
+{
+    if( !la ) return -1;
+    if( hits ) *hits = la->spec_hits;
+    if( misses ) *misses = la->spec_misses;
+    return la->spec_launched;
+}
+
 int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
 {
     X264CU_ENTER_LA( la );
@@ -1935,6 +2071,43 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
             n++;
         }
     }
+    // accumulator hand-over in the reference's order, slicetype.c:946-989; r = {cost_est, cost_est_aq, intra_mbs, intra cost_est, intra cost_est_aq}
+    auto account = [&]( const int32_t *r ) {
+        if( b == p1 ) fenc.intra_mbs[i0] = r[2];
+        if( !fenc.b_intra_calculated ) { fenc.cost_est[0][0] = 0; fenc.cost_est_aq[0][0] = 0; }
+        fenc.cost_est[i0][i1] = 0; fenc.cost_est_aq[i0][i1] = 0;
+        if( !fenc.b_intra_calculated ) { fenc.cost_est[0][0] += r[3]; fenc.cost_est_aq[0][0] += r[4]; }
+        fenc.cost_est[i0][i1] += r[0]; fenc.cost_est_aq[i0][i1] += r[1];
+        if( la->p.vbv )
+        {
+            fenc.row_satds_valid[i0][i1] = true;
+            if( !fenc.b_intra_calculated ) fenc.row_satds_valid[0][0] = true;
+        }
+        int sc = fenc.cost_est[i0][i1];
+        if( b != p1 ) sc = (int)( (uint64_t)sc * 100 / ( 120 + la->p.bframe_bias ) );
+        else fenc.b_intra_calculated = 1;
+        fenc.cost_est[i0][i1] = sc;
+        *score = sc;
+    };
+    {   // answered ahead of time?  (x264cu_lookahead_finalize_batch: the variant WITH the later reference's vectors)
+        const LaSlotHost::Spec &sp = fenc.spec[i0][i1];
+        const bool mvr_wanted = b < p1 && p1 - p0 - 1 <= d.B && la->slots[s1].requested[0][p1 - p0 - 1];
+        if( sp.batch && !n && b != p0 && !la->p.vbv && fenc.intra_on_device && ( b == p1 || mvr_wanted ) &&
+            la->spec_seq[sp.batch % LA_SPEC_RING] == sp.batch )
+        {
+            const int ring = (int)( sp.batch % LA_SPEC_RING );
+            LA_TIMED( la->st.cost_sync, la->st.n_cost, CU_CHECK( ctx, cudaEventSynchronize( la->spec_ev[ring] ) ) );
+            account( la->h_spec_rec + ( (size_t)ring * LA_SPEC_MAX + sp.index ) * 8 );
+            la->spec_hits++;
+            return 0;
+        }
+        if( sp.batch )
+        {   // the on-demand path rewrites lowres_costs of this triple: not before the batch that also writes them is through
+            const int ring = (int)( sp.batch % LA_SPEC_RING );
+            if( la->spec_seq[ring] == sp.batch ) CU_CHECK( ctx, cudaStreamWaitEvent( ctx->stream, la->spec_ev[ring], 0 ) );
+        }
+        la->spec_misses++;
+    }
     if( !fenc.intra_on_device )
     {
         intra_kernel<<<( d.mb_count + 63 ) / 64, 256, 0, ctx->stream>>>( d, fenc.dev.planes[0], fenc.dev.intra );
@@ -1989,23 +2162,7 @@ int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int 
     CU_CHECK( ctx, cudaMemcpyAsync( la->h_record, la->d_record, 32, cudaMemcpyDeviceToHost, ctx->stream ) );
     LA_TIMED( la->st.cost_sync, la->st.n_cost, CU_CHECK( ctx, cudaStreamSynchronize( ctx->stream ) ) );
 
-    // accumulator hand-over in the reference's order, slicetype.c:946-989
-    const int32_t *r = la->h_record;
-    if( b == p1 ) fenc.intra_mbs[i0] = r[2];
-    if( !fenc.b_intra_calculated ) { fenc.cost_est[0][0] = 0; fenc.cost_est_aq[0][0] = 0; }
-    fenc.cost_est[i0][i1] = 0; fenc.cost_est_aq[i0][i1] = 0;
-    if( !fenc.b_intra_calculated ) { fenc.cost_est[0][0] += r[3]; fenc.cost_est_aq[0][0] += r[4]; }
-    fenc.cost_est[i0][i1] += r[0]; fenc.cost_est_aq[i0][i1] += r[1];
-    if( la->p.vbv )
-    {
-        fenc.row_satds_valid[i0][i1] = true;
-        if( !fenc.b_intra_calculated ) fenc.row_satds_valid[0][0] = true;
-    }
-    int sc = fenc.cost_est[i0][i1];
-    if( b != p1 ) sc = (int)( (uint64_t)sc * 100 / ( 120 + la->p.bframe_bias ) );
-    else fenc.b_intra_calculated = 1;
-    fenc.cost_est[i0][i1] = sc;
-    *score = sc;
+    account( la->h_record );
     return 0;
 }
 

@@ -71,6 +71,7 @@ struct x264cu_slicetype
     int next_asked;                      /* type forced on the next queued picture */
     /* prefetch: every search the decision could ask for is launched ahead of time, in groups */
     int prefetch, group, in_group, run_ahead;
+    int speculate;                       /* cost requests computed with the searches (x264cu_lookahead_finalize_batch) */
     picture_t *recent[GAP_MAX + 2];      /* the last bframes+1 queued pictures, newest first */
     int n_recent;
     struct { int fenc_slot, ref_slot, list, dist, fenc_no, ref_no; } job[JOBS_MAX];
@@ -845,6 +846,7 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
     if( s->aq_strength == 0 )
         s->p.la.aq_mode = 0;
     s->prefetch = 1;
+    s->speculate = 1;
     /* measured at 4K (B200), pictures per launch / run-ahead: 4/8 -> 1000 pictures/s, 8/16 -> 1260, 12/24 -> 1410: a launch
      * needs several dozen independent wavefronts to fill the 148 SMs */
     s->group = s->horizon >= 12 ? 12 : 1;
@@ -913,6 +915,34 @@ static int exchange_previous_group( x264cu_slicetype_t *s )
     return x264cu_lookahead_import_done( s->la );
 }
 
+/* Every cost request the decision can make once these searches exist: a list-0 search of picture X against picture Y, d = X - Y
+ * apart, completes the P triple (Y, X, X) and the B triples (Y, X, b) of the pictures in between (their own two searches were
+ * launched when b and X arrived). */
+static int speculate_group( x264cu_slicetype_t *s, int n, const int *fenc, const int *ref, const int *list, const int *dist, const int *number )
+{
+    enum { TRIPLES_MAX = 4096 };
+    int *t = malloc( 5 * TRIPLES_MAX * sizeof( int ) ), m = 0;
+    if( !t ) return -1;
+    int *tb = t, *t0 = t + TRIPLES_MAX, *t1 = t + 2 * TRIPLES_MAX, *td0 = t + 3 * TRIPLES_MAX, *td1 = t + 4 * TRIPLES_MAX;
+    for( int i = 0; i < n; i++ )
+    {
+        if( list[i] )
+            continue;
+        const int x_no = number[i], d = dist[i];
+        for( int k = 0; k < d && m < TRIPLES_MAX; k++ )
+        {   /* k = 0: the P triple; k > 0: the B picture k pictures before X */
+            const int b_slot = k ? x264cu_slicetype_slot_of( s, x_no - k ) : fenc[i];
+            if( b_slot < 0 )
+                continue;
+            tb[m] = b_slot; t0[m] = ref[i]; t1[m] = fenc[i]; td0[m] = d - k; td1[m] = k;
+            m++;
+        }
+    }
+    const int rc = m ? x264cu_lookahead_finalize_batch( s->la, m, tb, t0, t1, td0, td1 ) : 0;
+    free( t );
+    return rc;
+}
+
 /* launch the gathered searches; jobs whose pictures have left their slots in the meantime are dropped */
 static int launch_group( x264cu_slicetype_t *s )
 {
@@ -952,7 +982,9 @@ static int launch_group( x264cu_slicetype_t *s )
         s->n_sent = n;
         n = mine;
     }
-    return n && x264cu_lookahead_search_batch( s->la, n, fenc, ref, list, dist ) ? -1 : 0;
+    if( n && x264cu_lookahead_search_batch( s->la, n, fenc, ref, list, dist ) )
+        return -1;
+    return s->speculate && s->world <= 1 ? speculate_group( s, n, fenc, ref, list, dist, number ) : 0;
 }
 
 /* every (picture, earlier picture) pair the decision could ask about: list 0 at distance d <= bframes+1 from the new
@@ -1071,6 +1103,8 @@ void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *s, int pictures )
 {
     if( s && !s->fed && pictures >= 0 && pictures <= AHEAD_MAX ) s->run_ahead = pictures;
 }
+
+void x264cu_slicetype_set_speculation( x264cu_slicetype_t *s, int speculate ) { if( s ) s->speculate = !!speculate; }
 
 void x264cu_slicetype_set_prefetch_group( x264cu_slicetype_t *s, int pictures )
 {
