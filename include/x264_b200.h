@@ -404,9 +404,18 @@ void x264cu_slicetype_set_async_upload( x264cu_slicetype_t *st, int on );
  * does the collective (the caller owns the communicator: torch.distributed / NCCL):
  *   phase 0: provide two device buffers, *d_send of bytes_per_rank and *d_recv of world * bytes_per_rank bytes
  *   phase 1: all-gather d_send of every rank into d_recv (rank r's block at r * bytes_per_rank), enqueued on `stream`
+ *   phases 2 / 3: the same for a second, independent pair of buffers (the exchange of cost-request results)
  * and returns 0 / -1.  Frame types and MB-tree offsets are those of a single GPU (tested). */
 typedef int (*x264cu_exchange_fn)( void *user, int phase, size_t bytes_per_rank, void **d_send, void **d_recv, void *stream );
 int  x264cu_slicetype_set_shard( x264cu_slicetype_t *st, int rank, int world, x264cu_exchange_fn fn, void *user );
+/* x264cu_lookahead_finalize_batch with the triples split between the GPUs of a sharded stream: triple i is computed by rank
+ * owner[i] (x264cu_slicetype uses the display index of its picture b, modulo world -- the rank that also ran b's searches), and
+ * every rank receives every result -- the 32-byte record and lowres_costs[b-p0][p1-b] of each triple -- in ONE all-gather per
+ * window: the same callback with phases 2 (buffers) and 3 (collective), so that it can keep this exchange's buffers apart from
+ * the search exchange's.  All ranks must call it with the same list. */
+int  x264cu_lookahead_finalize_batch_sharded( x264cu_lookahead_t *la, int n, const int *b_slot, const int *p0_slot, const int *p1_slot,
+                                              const int *d0, const int *d1, const int *owner, int rank, int world,
+                                              x264cu_exchange_fn exchange, void *user );
 /* the lookahead object underneath (for reading per-MB results) and the slot a display index currently occupies (-1 if gone) */
 x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *st );
 int  x264cu_slicetype_slot_of( x264cu_slicetype_t *st, int frame );

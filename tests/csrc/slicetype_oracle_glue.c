@@ -88,6 +88,11 @@ int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b
 {
     (void)la; (void)n; (void)b; (void)p0; (void)p1; (void)d0; (void)d1; return 0;
 }
+int x264cu_lookahead_finalize_batch_sharded( x264cu_lookahead_t *la, int n, const int *b, const int *p0, const int *p1, const int *d0, const int *d1,
+                                             const int *owner, int rank, int world, x264cu_exchange_fn fn, void *user )
+{
+    (void)la; (void)n; (void)b; (void)p0; (void)p1; (void)d0; (void)d1; (void)owner; (void)rank; (void)world; (void)fn; (void)user; return 0;
+}
 void x264cu_lookahead_set_async_upload( x264cu_lookahead_t *la, int on ) { (void)la; (void)on; }
 int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int a, int b ) { (void)la; (void)a; (void)b; return 0; }
 

@@ -56,6 +56,11 @@ int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b
 {
     (void)la; (void)n; (void)b; (void)p0; (void)p1; (void)d0; (void)d1; return 0;
 }
+int x264cu_lookahead_finalize_batch_sharded( x264cu_lookahead_t *la, int n, const int *b, const int *p0, const int *p1, const int *d0, const int *d1,
+                                             const int *owner, int rank, int world, x264cu_exchange_fn fn, void *user )
+{
+    (void)la; (void)n; (void)b; (void)p0; (void)p1; (void)d0; (void)d1; (void)owner; (void)rank; (void)world; (void)fn; (void)user; return 0;
+}
 int x264cu_lookahead_frame_cost( x264cu_lookahead_t *la, const int *frames, int p0, int p1, int b, int *score )
 {
     /* the reference takes a frames[] array of frame pointers: map indices p0..p1 to the slots' frames */

@@ -932,6 +932,7 @@ struct x264cu_lookahead
     cudaStream_t spec_stream = nullptr;
     LaFinalizeArgs *h_spec_args = nullptr, *d_spec_args = nullptr;    // [LA_SPEC_MAX]: staging of one batch's descriptors
     cudaEvent_t spec_args_ev = nullptr;                               // the staging buffer's last upload
+    cudaEvent_t spec_done_ev = nullptr;                               // sharded: a batch's results are in the send buffer
     int32_t *d_spec_rec = nullptr, *h_spec_rec = nullptr;             // [LA_SPEC_RING][LA_SPEC_MAX][8]
     cudaEvent_t spec_ev[LA_SPEC_RING] = {};                           // batch complete, records on the host
     unsigned long long spec_seq[LA_SPEC_RING] = {}, spec_next = 1;    // which batch each ring entry holds
@@ -997,6 +998,7 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     if( la->spec_stream ) { cudaStreamSynchronize( la->spec_stream ); cudaStreamDestroy( la->spec_stream ); }
     cudaFreeHost( la->h_spec_args ); cudaFreeHost( la->h_spec_rec ); cudaFree( la->d_spec_args ); cudaFree( la->d_spec_rec );
     if( la->spec_args_ev ) cudaEventDestroy( la->spec_args_ev );
+    if( la->spec_done_ev ) cudaEventDestroy( la->spec_done_ev );
     for( int i = 0; i < LA_SPEC_RING; i++ ) if( la->spec_ev[i] ) cudaEventDestroy( la->spec_ev[i] );
     if( la->ev_mt_dep ) cudaEventDestroy( la->ev_mt_dep );
     for( int i = 0; i < 32; i++ ) if( la->ev_mt_ckpt[i] ) cudaEventDestroy( la->ev_mt_ckpt[i] );
@@ -1110,6 +1112,7 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     alloc( (void **)&la->d_spec_args, sizeof( LaFinalizeArgs ) * LA_SPEC_MAX );
     alloc( (void **)&la->d_spec_rec, (size_t)LA_SPEC_RING * LA_SPEC_MAX * 32 );
     if( ok && cudaEventCreateWithFlags( &la->spec_args_ev, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
+    if( ok && cudaEventCreateWithFlags( &la->spec_done_ev, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     for( int i = 0; i < LA_SPEC_RING; i++ )
         if( ok && cudaEventCreateWithFlags( &la->spec_ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->ev_mt_dep, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
@@ -1924,8 +1927,8 @@ int x264cu_lookahead_weight_trivial( x264cu_lookahead_t *la, int fenc_slot, int 
  * that variant is computed for every triple a window can ask about as soon as its searches are queued: n triples in ONE launch,
  * their records read back in ONE copy.  x264cu_lookahead_frame_cost then finds the record instead of launching, copying back and
  * waiting per request; a request that needs the other variant, a weighted search or row sums (VBV) takes the on-demand path. */
-int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b_slot, const int *p0_slot, const int *p1_slot,
-                                     const int *d0, const int *d1 )
+static int la_finalize_batch( x264cu_lookahead_t *la, int n, const int *b_slot, const int *p0_slot, const int *p1_slot,
+                              const int *d0, const int *d1, const int *owner, int rank, int world, x264cu_exchange_fn exchange, void *user )
 {
     X264CU_ENTER_LA( la );
     if( !la || ( n > 0 && ( !b_slot || !p0_slot || !p1_slot || !d0 || !d1 ) ) ) return -1;
@@ -1933,6 +1936,13 @@ int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b
     const LaDims &d = la->d;
     if( n <= 0 || la->p.vbv ) return 0;
     if( n > LA_SPEC_MAX ) n = LA_SPEC_MAX;
+    const bool sharded = world > 1;
+    // sharded: the triples are split between the ranks (owner[i]); every rank walks the same list and filters it by the same
+    // (replicated) state, so all agree on which triples exist, whose they are and where their results sit in the exchange:
+    // rank r's block = [most x 32 B records][most x cost_bytes lowres_costs], its k-th triple at index k of both parts
+    std::vector<int> rank_count( sharded ? world : 1, 0 );
+    struct Kept { int slot, i0, i1, owner, k; };
+    std::vector<Kept> kept;
     const int B1 = d.B + 1, B2w = d.B + 2;
     const int ring = (int)( la->spec_next % LA_SPEC_RING );
     // ring entry reuse (its batch is hundreds of pictures old) and the descriptor staging buffer (its last upload)
@@ -1959,6 +1969,14 @@ int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b
             if( !slot_seen[sl] ) { slot_seen[sl] = 1; CU_CHECK( ctx, cudaStreamWaitEvent( la->spec_stream, la->slots[sl].ev_ready, 0 ) ); }
         if( wait_ev( fenc.pending[0][i0 - 1] ) ) return -1;
         if( i1 && ( wait_ev( fenc.pending[1][i1 - 1] ) || wait_ev( f1.pending[0][i0 + i1 - 1] ) ) ) return -1;
+        const int own = sharded ? owner[i] : 0;
+        if( sharded )
+        {
+            if( own < 0 || own >= world ) return x264cu_fail( ctx, "finalize_batch: owner %d of %d ranks", own, world );
+            kept.push_back( Kept{ sb, i0, i1, own, rank_count[own]++ } );
+            fenc.spec[i0][i1].batch = la->spec_next;               // index set once the blocks' size is known
+            if( own != rank ) continue;
+        }
         LaFinalizeArgs &A = la->h_spec_args[m];
         memset( &A, 0, sizeof( A ) );
         A.fenc = fenc.dev.planes[0];
@@ -1981,27 +1999,86 @@ int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b
         fenc.spec[i0][i1].batch = la->spec_next; fenc.spec[i0][i1].index = m;
         m++;
     }
-    if( !m ) return 0;
-    CU_CHECK( ctx, cudaMemcpyAsync( la->d_spec_args, la->h_spec_args, sizeof( LaFinalizeArgs ) * m, cudaMemcpyHostToDevice, la->spec_stream ) );
-    CU_CHECK( ctx, cudaEventRecord( la->spec_args_ev, la->spec_stream ) );
-    CU_CHECK( ctx, cudaMemsetAsync( d_rec, 0, (size_t)m * 32, la->spec_stream ) );
-    const dim3 grid( ( d.mb_count + LA_FIN_THREADS / 4 - 1 ) / ( LA_FIN_THREADS / 4 ), m );
-    finalize_batch_kernel<<<grid, LA_FIN_THREADS, 0, la->spec_stream>>>( d, la->d_spec_args );
-    CU_LAUNCH_CHECK( ctx );
-    CU_CHECK( ctx, cudaMemcpyAsync( la->h_spec_rec + (size_t)ring * LA_SPEC_MAX * 8, d_rec, (size_t)m * 32, cudaMemcpyDeviceToHost, la->spec_stream ) );
-    CU_CHECK( ctx, cudaEventRecord( la->spec_ev[ring], la->spec_stream ) );
+    if( !m && kept.empty() ) return 0;
+    if( m )
+    {
+        CU_CHECK( ctx, cudaMemcpyAsync( la->d_spec_args, la->h_spec_args, sizeof( LaFinalizeArgs ) * m, cudaMemcpyHostToDevice, la->spec_stream ) );
+        CU_CHECK( ctx, cudaEventRecord( la->spec_args_ev, la->spec_stream ) );
+        CU_CHECK( ctx, cudaMemsetAsync( d_rec, 0, (size_t)m * 32, la->spec_stream ) );
+        const dim3 grid( ( d.mb_count + LA_FIN_THREADS / 4 - 1 ) / ( LA_FIN_THREADS / 4 ), m );
+        finalize_batch_kernel<<<grid, LA_FIN_THREADS, 0, la->spec_stream>>>( d, la->d_spec_args );
+        CU_LAUNCH_CHECK( ctx );
+    }
+    int32_t *h_rec = la->h_spec_rec + (size_t)ring * LA_SPEC_MAX * 8;
+    if( !sharded )
+    {
+        CU_CHECK( ctx, cudaMemcpyAsync( h_rec, d_rec, (size_t)m * 32, cudaMemcpyDeviceToHost, la->spec_stream ) );
+        CU_CHECK( ctx, cudaEventRecord( la->spec_ev[ring], la->spec_stream ) );
+    }
+    else
+    {   // ONE all-gather of every rank's records and lowres_costs (the second exchange of a window; phases 2 / 3 of the callback)
+        int most = 0;
+        for( int r = 0; r < world; r++ ) most = rank_count[r] > most ? rank_count[r] : most;
+        if( world * most > LA_SPEC_MAX ) return x264cu_fail( ctx, "finalize_batch: %d triples on %d ranks exceed the batch size", most, world );
+        const size_t cost_bytes = ( (size_t)d.mb_count * 2 + 15 ) & ~(size_t)15, per_rank = (size_t)most * ( 32 + cost_bytes );
+        void *d_send = nullptr, *d_recv = nullptr;
+        if( exchange( user, 2, per_rank, &d_send, &d_recv, (void *)la->xch_stream ) || !d_send || !d_recv )
+            return x264cu_fail( ctx, "finalize_batch: the exchange callback gave no buffers" );
+        // my results into my block, behind the kernel -- and behind the previous batch's exchange, which reads the same buffers
+        if( la->spec_next > 1 )
+            CU_CHECK( ctx, cudaStreamWaitEvent( la->spec_stream, la->spec_ev[( la->spec_next - 1 ) % LA_SPEC_RING], 0 ) );
+        CU_CHECK( ctx, cudaMemcpyAsync( d_send, d_rec, (size_t)m * 32, cudaMemcpyDeviceToDevice, la->spec_stream ) );
+        for( const Kept &t : kept )
+            if( t.owner == rank )
+                CU_CHECK( ctx, cudaMemcpyAsync( (uint8_t *)d_send + (size_t)most * 32 + (size_t)t.k * cost_bytes,
+                                                la->slots[t.slot].dev.costs + (size_t)( t.i0 * B2w + t.i1 ) * d.mb_count, (size_t)d.mb_count * 2,
+                                                cudaMemcpyDeviceToDevice, la->spec_stream ) );
+        CU_CHECK( ctx, cudaEventRecord( la->spec_done_ev, la->spec_stream ) );
+        CU_CHECK( ctx, cudaStreamWaitEvent( la->xch_stream, la->spec_done_ev, 0 ) );
+        if( exchange( user, 3, per_rank, &d_send, &d_recv, (void *)la->xch_stream ) )
+            return x264cu_fail( ctx, "finalize_batch: the exchange failed" );
+        for( int r = 0; r < world; r++ )
+            if( rank_count[r] )
+                CU_CHECK( ctx, cudaMemcpyAsync( h_rec + (size_t)r * most * 8, (uint8_t *)d_recv + (size_t)r * per_rank, (size_t)rank_count[r] * 32,
+                                                cudaMemcpyDeviceToHost, la->xch_stream ) );
+        for( const Kept &t : kept )
+        {
+            la->slots[t.slot].spec[t.i0][t.i1].index = t.owner * most + t.k;
+            if( t.owner != rank )
+                CU_CHECK( ctx, cudaMemcpyAsync( la->slots[t.slot].dev.costs + (size_t)( t.i0 * B2w + t.i1 ) * d.mb_count,
+                                                (uint8_t *)d_recv + (size_t)t.owner * per_rank + (size_t)most * 32 + (size_t)t.k * cost_bytes,
+                                                (size_t)d.mb_count * 2, cudaMemcpyDeviceToDevice, la->xch_stream ) );
+        }
+        CU_CHECK( ctx, cudaEventRecord( la->spec_ev[ring], la->xch_stream ) );
+    }
     la->spec_seq[ring] = la->spec_next++;
     la->spec_launched += m;
     {   // the slots' next uploads wait for this batch (it reads their planes and vectors)
         const int e = la->ev_next;
         la->ev_next = ( la->ev_next + 1 ) % la->n_ev;
         CU_CHECK( ctx, cudaEventSynchronize( la->ev[e] ) );
-        CU_CHECK( ctx, cudaEventRecord( la->ev[e], la->spec_stream ) );
+        CU_CHECK( ctx, cudaEventRecord( la->ev[e], sharded ? la->xch_stream : la->spec_stream ) );
         la->ev_seq[e] = la->ev_seq_next++;
+        for( const Kept &t : kept ) slot_seen[t.slot] = 1;                 // imported lowres_costs are written into those
         for( size_t sl = 0; sl < la->slots.size(); sl++ )
             if( slot_seen[sl] ) { la->slots[sl].last_search_ev[3] = e; la->slots[sl].last_search_seq[3] = la->ev_seq[e]; }
     }
     return 0;
+}
+
+int x264cu_lookahead_finalize_batch( x264cu_lookahead_t *la, int n, const int *b_slot, const int *p0_slot, const int *p1_slot,
+                                     const int *d0, const int *d1 )
+{
+    return la_finalize_batch( la, n, b_slot, p0_slot, p1_slot, d0, d1, nullptr, 0, 1, nullptr, nullptr );
+}
+
+int x264cu_lookahead_finalize_batch_sharded( x264cu_lookahead_t *la, int n, const int *b_slot, const int *p0_slot, const int *p1_slot,
+                                             const int *d0, const int *d1, const int *owner, int rank, int world,
+                                             x264cu_exchange_fn exchange, void *user )
+{
+    if( la && ( world < 1 || rank < 0 || rank >= world || ( world > 1 && ( !owner || !exchange ) ) ) )
+        return x264cu_fail( la->ctx, "finalize_batch_sharded: bad rank %d of %d", rank, world );
+    return la_finalize_batch( la, n, b_slot, p0_slot, p1_slot, d0, d1, owner, rank, world, exchange, user );
 }
 
 long x264cu_lookahead_speculation_stats( x264cu_lookahead_t *la, long *hits, long *misses )

@@ -877,10 +877,10 @@ void x264cu_slicetype_close( x264cu_slicetype_t *s )
  * prefetch and the sharded stream
  * ============================================================================================================== */
 
-/* Sharded stream: all-gather the results of the previous group's searches (launched one group ago: nobody waits) and install
- * the ones searched on other GPUs.  Every rank holds the same job list, so the layout of the exchange is known everywhere:
+/* Sharded stream: all-gather the results of the group's searches (queued behind them on the exchange stream: the calling thread
+ * does not wait) and install the ones searched on other GPUs.  Every rank holds the same job list, so the layout of the exchange is known everywhere:
  * rank r's k-th job sits at r * bytes_per_rank + k * search_bytes. */
-static int exchange_previous_group( x264cu_slicetype_t *s )
+static int exchange_group( x264cu_slicetype_t *s )
 {
     if( !s->n_sent ) return 0;
     int per_owner[64] = { 0 }, most = 0;
@@ -921,9 +921,9 @@ static int exchange_previous_group( x264cu_slicetype_t *s )
 static int speculate_group( x264cu_slicetype_t *s, int n, const int *fenc, const int *ref, const int *list, const int *dist, const int *number )
 {
     enum { TRIPLES_MAX = 4096 };
-    int *t = malloc( 5 * TRIPLES_MAX * sizeof( int ) ), m = 0;
+    int *t = malloc( 6 * TRIPLES_MAX * sizeof( int ) ), m = 0;
     if( !t ) return -1;
-    int *tb = t, *t0 = t + TRIPLES_MAX, *t1 = t + 2 * TRIPLES_MAX, *td0 = t + 3 * TRIPLES_MAX, *td1 = t + 4 * TRIPLES_MAX;
+    int *tb = t, *t0 = t + TRIPLES_MAX, *t1 = t + 2 * TRIPLES_MAX, *td0 = t + 3 * TRIPLES_MAX, *td1 = t + 4 * TRIPLES_MAX, *own = t + 5 * TRIPLES_MAX;
     for( int i = 0; i < n; i++ )
     {
         if( list[i] )
@@ -935,10 +935,13 @@ static int speculate_group( x264cu_slicetype_t *s, int n, const int *fenc, const
             if( b_slot < 0 )
                 continue;
             tb[m] = b_slot; t0[m] = ref[i]; t1[m] = fenc[i]; td0[m] = d - k; td1[m] = k;
+            own[m] = s->world > 1 ? ( x_no - k ) % s->world : 0;    /* the rank that searched picture b computes its costs too */
             m++;
         }
     }
-    const int rc = m ? x264cu_lookahead_finalize_batch( s->la, m, tb, t0, t1, td0, td1 ) : 0;
+    const int rc = !m ? 0 : s->world > 1 ? x264cu_lookahead_finalize_batch_sharded( s->la, m, tb, t0, t1, td0, td1, own, s->rank, s->world,
+                                                                                    s->exchange, s->exchange_user )
+                                         : x264cu_lookahead_finalize_batch( s->la, m, tb, t0, t1, td0, td1 );
     free( t );
     return rc;
 }
@@ -964,9 +967,12 @@ static int launch_group( x264cu_slicetype_t *s )
     }
     s->n_job = 0;
     s->in_group = 0;
+    int all = n;
+    int a_fenc[JOBS_MAX], a_ref[JOBS_MAX], a_list[JOBS_MAX], a_dist[JOBS_MAX];
     if( s->world > 1 )
-    {   /* first the exchange of the group launched one flush ago, then this group's own share */
-        if( exchange_previous_group( s ) ) return -1;
+    {   /* this rank's share of the searches; the results are exchanged right behind them (nothing waits on the host) */
+        memcpy( a_fenc, fenc, n * sizeof( int ) ); memcpy( a_ref, ref, n * sizeof( int ) );
+        memcpy( a_list, list, n * sizeof( int ) ); memcpy( a_dist, dist, n * sizeof( int ) );
         int mine = 0;
         for( int i = 0; i < n; i++ )
         {
@@ -984,7 +990,12 @@ static int launch_group( x264cu_slicetype_t *s )
     }
     if( n && x264cu_lookahead_search_batch( s->la, n, fenc, ref, list, dist ) )
         return -1;
-    return s->speculate && s->world <= 1 ? speculate_group( s, n, fenc, ref, list, dist, number ) : 0;
+    if( s->world > 1 && exchange_group( s ) )
+        return -1;
+    if( !s->speculate )
+        return 0;
+    return s->world > 1 ? speculate_group( s, all, a_fenc, a_ref, a_list, a_dist, number )
+                        : speculate_group( s, n, fenc, ref, list, dist, number );
 }
 
 /* every (picture, earlier picture) pair the decision could ask about: list 0 at distance d <= bframes+1 from the new
@@ -1060,7 +1071,7 @@ static int step( x264cu_slicetype_t *s, const input_t *in, int *out_frame, int *
     else
     {
         if( s->n_job && launch_group( s ) ) return -1;
-        if( s->world > 1 && s->n_sent && exchange_previous_group( s ) ) return -1;
+        if( s->world > 1 && s->n_sent && exchange_group( s ) ) return -1;
     }
     pull_decided( s );
     if( s->broken ) return -1;

@@ -21,7 +21,7 @@ class ShardExchange:
         import torch
         self.torch, self.dist, self.device = torch, dist, device
         self.world = dist.get_world_size()
-        self.send = self.recv = None
+        self.buf = {0: [None, None], 1: [None, None]}      # channel -> [send, recv]: searches (phases 0/1), cost requests (phases 2/3)
         self.calls = 0
         self.bytes = 0
         self.cb = EXCHANGE_FN(self._call)          # keep the trampoline alive as long as this object
@@ -29,21 +29,24 @@ class ShardExchange:
     def _call(self, user, phase, per_rank, d_send, d_recv, stream):
         try:
             torch = self.torch
+            ch, phase = phase >> 1, phase & 1
             n = max(int(per_rank), 16)
+            send, recv = self.buf[ch]
             if phase == 0:
-                if self.send is None or self.send.numel() < n:
+                if send is None or send.numel() < n:
                     dev = self.device if self.device is not None else "cpu"
-                    if self.send is not None and self.device is not None:
-                        # imports from the old receive buffer may still be in flight on the exchange stream
+                    if send is not None and self.device is not None:
+                        # copies out of the old receive buffer may still be in flight on the exchange stream
                         torch.cuda.ExternalStream(int(stream), device=self.device).synchronize()
-                    self.send = torch.zeros(n, dtype=torch.uint8, device=dev)
-                    self.recv = torch.zeros(n * self.world, dtype=torch.uint8, device=dev)
-                self.cur = n
+                    grow = n + n // 4
+                    send = torch.zeros(grow, dtype=torch.uint8, device=dev)
+                    recv = torch.zeros(grow * self.world, dtype=torch.uint8, device=dev)
+                    self.buf[ch] = [send, recv]
                 # rank r's block must sit at r * per_rank: gather into a view of exactly world * per_rank bytes
-                d_send[0] = self.send.data_ptr()
-                d_recv[0] = self.recv.data_ptr()
+                d_send[0] = send.data_ptr()
+                d_recv[0] = recv.data_ptr()
                 return 0
-            send, recv = self.send[:int(per_rank)] if per_rank else self.send[:0], self.recv[:int(per_rank) * self.world]
+            send, recv = send[:int(per_rank)] if per_rank else send[:0], recv[:int(per_rank) * self.world]
             if per_rank:
                 if self.device is not None:
                     with torch.cuda.stream(torch.cuda.ExternalStream(int(stream), device=self.device)):
