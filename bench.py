@@ -333,8 +333,8 @@ LA_REF_OPTS_W = b"weightp=2:aq-mode=0:bframes=3:rc-lookahead=40"                
 LA_SEARCH_BYTES = LA_W * LA_H // 4 + LA_W * LA_H + 8 * ((LA_W + 15) // 16) * ((LA_H + 15) // 16)
 
 
-def make_la_frames(seed, n, alloc):
-    """synthetic 4K sequence: low-pass texture translated by a per-frame global motion + noise, one hard cut"""
+def make_la_frames(seed, n, alloc, LA_W=LA_W, LA_H=LA_H):
+    """synthetic sequence (4K unless told otherwise): low-pass texture translated by a per-frame global motion + noise, one hard cut"""
     rng = np.random.default_rng(seed)
     small = rng.integers(0, 256, (LA_H // 8 + 64, LA_W // 8 + 64)).astype(np.float32)
     k = np.ones(5, np.float32) / 5
@@ -422,6 +422,74 @@ def cpu_lookahead_rate(frames, budget_s, weightp=0, threads=1):
     return decided / t, kind, threads, "%d 4K pictures decided in %.1f s by the oracle port, 1 thread" % (decided, t), types
 
 
+C3_W, C3_H, C3_CLIP = 7680, 4320, 48
+C3_OPTS = dict(subpel_refine=7, me_method=1, me_range=16, mv_range=512, bframes=16, bframe_bias=0, weighted_bipred=1, aq_mode=0, mb_tree=1, vbv=0)
+C3_ST = dict(keyint_max=250, keyint_min=25, scenecut_threshold=40, b_adapt=2, b_pyramid=2, rc_lookahead=250, psy=0, frame_reference=3, rc_cqp=0)
+
+
+def run_config3(ctx, x, rank, world, local, dist, args):
+    """BASELINE configs[3]: ONE 7680x4320 stream, --rc-lookahead 250 --bframes 16 --b-adapt 2, sharded over the GPUs -- next to the same
+    stream on ONE GPU, measured by rank 0 alone in the same run (the other ranks wait)."""
+    import torch
+    from x264_b200 import dist as xd
+    frames = make_la_frames(4320, C3_CLIP, lambda b: np.empty(b, np.uint8), C3_W, C3_H)
+    d_frames = ctx.malloc(frames.nbytes + 256)
+    ctx.h2d(d_frames, frames)
+    warm, timed = C3_ST["rc_lookahead"] + 24 + 2 * 12 + 2, 96                       # past the first decision, then a steady state
+
+    def run(shard):
+        st = x.Slicetype(ctx, C3_W, C3_H, **C3_ST, **C3_OPTS, weighted_pred=0)
+        ex = None
+        if shard:
+            ex = xd.ShardExchange(dist, device=torch.device("cuda", local))
+            st.set_shard(rank, world, ex)
+        types = []
+
+        def feed(k0, k1):
+            for i in range(k0, k1):
+                fr, ty = st.step_device(d_frames + (i % C3_CLIP) * C3_W * C3_H, C3_W)
+                if fr >= 0:
+                    types.append((fr, ty))
+
+        feed(0, warm)
+        ctx.sync()
+        if shard:
+            barrier(dist, local)
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        feed(warm, warm + timed)
+        ms = ctx.timer_stop()
+        ctx.sync()
+        if shard:
+            ms = max_over_ranks(dist, ms, local)
+            barrier(dist, local)
+        wall = time.perf_counter() - t0
+        spec = st.speculation_stats()
+        st.close()
+        return timed / (ms * 1e-3), timed / wall, types, spec, ex
+
+    one = None
+    if rank == 0:
+        one = run(False)
+    barrier(dist, local)
+    many = run(True)
+    sig = torch.tensor([hash(tuple(many[2])) & 0x7fffffffffff], dtype=torch.int64, device=torch.device("cuda", local))
+    sigs = [torch.zeros_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig)
+    ctx.free(d_frames)
+    out = {"workload": "7680x4320, rc-lookahead 250, bframes 16, b-adapt 2, b-pyramid, mb-tree, scenecut 40; %d pictures timed after %d; "
+                       "cyclic %d-picture clip resident in HBM" % (timed, warm, C3_CLIP),
+           "frames_per_s_%d_gpus" % world: many[0], "wall_frames_per_s_%d_gpus" % world: many[1],
+           "same_decisions_on_every_rank": bool(all(int(t.item()) == int(sig.item()) for t in sigs)),
+           "exchanges": many[4].calls, "MB_per_exchange": many[4].bytes / max(many[4].calls, 1) / 1e6,
+           "cost_requests": {"computed_ahead": many[3][0], "served_from_them": many[3][1], "computed_on_demand": many[3][2]}}
+    if one is not None:
+        out["frames_per_s_1_gpu"], out["wall_frames_per_s_1_gpu"] = one[0], one[1]
+        out["speedup"] = many[0] / one[0]
+        out["same_decisions_as_1_gpu"] = one[2][:len(many[2])] == many[2][:len(one[2])]
+    return out
+
+
 def run_lookahead_b200(args, rank, world, local, dist):
     import x264_b200 as x
     ctx = x.Context(local)
@@ -479,43 +547,60 @@ def run_lookahead_b200(args, rank, world, local, dist):
         allrec = xd.unpack_records(xd.all_gather_records(dist, rec, device=torch.device("cuda", local)))
         gathered_streams = len(allrec)
 
-    # ---- ONE stream sharded over the GPUs: every rank is fed rank 0's pictures, searches split by picture, one
-    # all-gather of search results per prefetch group; reported beside the weak-scaling value, not instead of it ----------
+    # ---- ONE stream sharded over the GPUs: every rank is fed rank 0's pictures; the searches AND the cost requests of
+    # each prefetch group are split by picture, two all-gathers per group (search results; cost records + lowres_costs).  At N > 1
+    # this is the line's `value` (strong scaling of the N = 1 workload); the independent-streams figure above becomes `replicas`.
     sharded = None
     if dist is not None:
         import torch
         from x264_b200 import dist as xd
         same_frames = make_la_frames(2160, n, lambda b: ctx.malloc_host(b))
         ctx.h2d(d_frames, same_frames)
-        st = make_st()
-        ex = xd.ShardExchange(dist, device=torch.device("cuda", local))
-        st.set_shard(rank, world, ex)
-        sh_types = []
 
-        def step_sh():
-            for i in range(n):
-                fr, ty = st.step_device(d_frames + i * LA_W * LA_H, stride)
-                if fr >= 0:
-                    sh_types.append((fr, ty))
+        def sharded_run(host_input, steps):
+            st = make_st()
+            ex = xd.ShardExchange(dist, device=torch.device("cuda", local))
+            st.set_shard(rank, world, ex)
+            if host_input:
+                st.set_async_upload(4)
+            types = []
 
-        for _ in range(3):
-            step_sh()
-        ctx.sync()
-        barrier(dist, local)
-        sh_steps = max(1, min(args.steps, 10))
-        ctx.timer_start()
-        for _ in range(sh_steps):
-            step_sh()
-        sh_ms = max_over_ranks(dist, ctx.timer_stop(), local)
-        ctx.sync()
-        st.close()
+            def one_step():
+                for i in range(n):
+                    fr, ty = st.step(same_frames[i]) if host_input else st.step_device(d_frames + i * LA_W * LA_H, stride)
+                    if fr >= 0:
+                        types.append((fr, ty))
+
+            for _ in range(3):
+                one_step()
+            ctx.sync()
+            barrier(dist, local)
+            t0_ = time.perf_counter()
+            ctx.timer_start()
+            for _ in range(steps):
+                one_step()
+            ms_ = max_over_ranks(dist, ctx.timer_stop(), local)
+            ctx.sync()
+            barrier(dist, local)
+            wall_ = max_over_ranks(dist, time.perf_counter() - t0_, local)
+            spec = st.speculation_stats()
+            st.close()
+            return ms_, wall_, types, ex, spec
+
+        sh_steps = max(1, args.steps)
+        sh_ms, sh_wall, sh_types, ex, sh_spec = sharded_run(False, sh_steps)
+        e2e_sh_steps = 3 if args.quick else max(1, min(args.steps, 10))
+        _, e2e_sh_wall, e2e_sh_types, _, _ = sharded_run(True, e2e_sh_steps)
         # every rank must have taken the same decisions
         sig = torch.tensor([hash(tuple(sh_types)) & 0x7fffffffffff], dtype=torch.int64, device=torch.device("cuda", local))
         sigs = [torch.zeros_like(sig) for _ in range(world)]
         dist.all_gather(sigs, sig)
-        sharded = {"value": n * sh_steps / (sh_ms * 1e-3), "unit": "frames/s", "steps": sh_steps,
-                   "note": "ONE 4K stream over %d GPUs: searches split by picture, decisions replicated, one NCCL all-gather of search "
-                           "results per 12-picture group (%.1f MB gathered per exchange, %d exchanges)" % (world, ex.bytes / max(ex.calls, 1) / 1e6, ex.calls),
+        sharded = {"value": n * sh_steps / (sh_ms * 1e-3), "unit": "frames/s", "steps": sh_steps, "ms_per_step": sh_ms / sh_steps,
+                   "wall_frames_per_s": n * sh_steps / sh_wall,
+                   "e2e": n * e2e_sh_steps / e2e_sh_wall,
+                   "cost_requests": {"computed_ahead": sh_spec[0], "served_from_them": sh_spec[1], "computed_on_demand": sh_spec[2]},
+                   "note": "ONE 4K stream over %d GPUs: searches and cost requests split by picture, decisions replicated, two NCCL all-gathers "
+                           "per 12-picture group (%.1f MB gathered per exchange on average, %d exchanges)" % (world, ex.bytes / max(ex.calls, 1) / 1e6, ex.calls),
                    "same_decisions_on_every_rank": bool(all(int(t.item()) == int(sig.item()) for t in sigs))}
         ctx.h2d(d_frames, frames)
 
@@ -601,7 +686,13 @@ def run_lookahead_b200(args, rank, world, local, dist):
         "wall_s": wall, "sm_count": info["sm_count"],
     }
     if sharded is not None:
+        res["replicas"] = {"value": res["value"], "unit": "frames/s", "ms_per_step": res["ms_per_step"], "e2e": res["e2e"]["value"], "scaling": "weak",
+                           "note": "N independent 4K streams, one per GPU, no data-path collective (one all-gather of decision records)"}
+        res["value"], res["ms_per_step"], res["scaling"] = sharded["value"], sharded["ms_per_step"], "strong"
+        res["e2e"] = dict(res["e2e"], value=sharded["e2e"], api="x264cu_slicetype_step on every rank (sharded stream: each rank is fed the same page-locked host pictures)")
         res["sharded_stream"] = sharded
+        if not args.quick:
+            res["config3_8k"] = run_config3(ctx, x, rank, world, local, dist, args)
     if rank == 0 and world == 1 and not args.quick:
         rate, kind, cores, sample, _ = cpu_lookahead_rate(frames, args.cpu_budget, args.weightp, os.cpu_count() or 1)
         rate1, _, _, sample1, types1 = cpu_lookahead_rate(frames, args.cpu_budget, args.weightp, 1)

@@ -23,7 +23,7 @@ enum
     GAP_MAX = X264CU_BFRAME_MAX,         /* most B pictures between two anchors */
     AHEAD_MAX = 32,                      /* run-ahead pictures (set_run_ahead) */
     QUEUE_MAX = WIN_MAX + AHEAD_MAX + 8,
-    JOBS_MAX = 256
+    JOBS_MAX = 1024                      /* searches per prefetch launch group: 12 pictures x (2 bframes + 1) at bframes 16 = 396 */
 };
 #define SCORE_INF ( 1ULL << 60 )         /* COST_MAX64, encoder/me.h:31 */
 
