@@ -5,6 +5,9 @@
  *
  *   gcc -O2 -Iinclude examples/lookahead_host.c -o lookahead_host -Lx264_b200/csrc -lx264_b200 -Wl,-rpath,$PWD/x264_b200/csrc
  *   ./lookahead_host WIDTH HEIGHT FRAMES [raw 8-bit I420 file]      (without a file: a synthetic moving texture with a cut)
+ *   ./lookahead_host --ranks N WIDTH HEIGHT FRAMES [file]            ONE stream sharded over N GPUs: N processes (fork), one per
+ *                                                                    GPU, the all-gathers done by x264cu_exchange_nccl (NCCL over
+ *                                                                    NVLink); every rank takes the same decisions, rank 0 prints
  *
  * Raw I420 in (Y, Cb, Cr planes per picture, as x264's raw demuxer reads them, input/raw.c:43-170): adaptive quantisation
  * (aq-mode 1), lowres planes, lookahead, slice-type decision and MB-tree all run on the device (x264cu_slicetype_step_i420).
@@ -14,6 +17,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
+#include <sys/wait.h>
 #include "x264_b200.h"
 
 static const char *type_name( int t )
@@ -45,14 +50,23 @@ static void synth( uint8_t *luma, int w, int h, int i, int n )
 
 int main( int argc, char **argv )
 {
-    if( argc < 4 ) { fprintf( stderr, "usage: %s WIDTH HEIGHT FRAMES [luma.raw]\n", argv[0] ); return 2; }
+    int ranks = 1, rank = 0;
+    if( argc > 2 && !strcmp( argv[1], "--ranks" ) ) { ranks = atoi( argv[2] ); argv += 2; argc -= 2; }
+    if( argc < 4 || ranks < 1 || ranks > 8 ) { fprintf( stderr, "usage: %s [--ranks N] WIDTH HEIGHT FRAMES [pictures.i420]\n", argv[0] ); return 2; }
     const int w = atoi( argv[1] ), h = atoi( argv[2] );
     int n = atoi( argv[3] );
+    char id_path[64];
+    snprintf( id_path, sizeof( id_path ), "/tmp/x264cu_nccl_id_%d", (int)getpid() );
+    pid_t kids[8];
+    for( int r = 1; r < ranks; r++ )           /* one process per GPU; the parent is rank 0 */
+        if( !( kids[r] = fork() ) ) { rank = r; break; }
     FILE *in = argc > 4 ? fopen( argv[4], "rb" ) : NULL;
     if( argc > 4 && !in ) { perror( argv[4] ); return 2; }
 
     x264cu_ctx_t *ctx;
-    if( x264cu_open( &ctx, 0 ) ) { fprintf( stderr, "x264cu_open: %s\n", x264cu_strerror( NULL ) ); return 1; }   /* no CPU fallback */
+    if( x264cu_open( &ctx, rank ) ) { fprintf( stderr, "x264cu_open: %s\n", x264cu_strerror( NULL ) ); return 1; }   /* no CPU fallback */
+    x264cu_nccl_t *nc = NULL;
+    if( ranks > 1 && x264cu_nccl_open( ctx, rank, ranks, id_path, 120, &nc ) ) { fprintf( stderr, "rank %d: %s\n", rank, x264cu_strerror( ctx ) ); return 1; }
 
     x264cu_slicetype_params_t p;
     memset( &p, 0, sizeof( p ) );
@@ -63,6 +77,7 @@ int main( int argc, char **argv )
     p.psy = 0; p.frame_reference = 3; p.fps_num = 25; p.fps_den = 1; p.qcompress = 0.6f; p.aq_strength = 1.0f;
     x264cu_slicetype_t *st;
     if( x264cu_slicetype_open( ctx, &p, &st ) ) { fprintf( stderr, "slicetype_open: %s\n", x264cu_strerror( ctx ) ); return 1; }
+    if( ranks > 1 && x264cu_slicetype_set_shard( st, rank, ranks, x264cu_exchange_nccl, nc ) ) { fprintf( stderr, "set_shard failed\n" ); return 1; }
 
     const int mbs = ( ( w + 15 ) / 16 ) * ( ( h + 15 ) / 16 );
     const int cw = ( w + 1 ) / 2, ch = ( h + 1 ) / 2;
@@ -91,7 +106,10 @@ int main( int argc, char **argv )
                 for( int i = 0; i < mbs; i++ ) mean += qp[i];
                 mean /= mbs;
             }
-            printf( "frame %d type %s qp_offset_mean %.4f\n", frame, type_name( type ), mean );
+            if( rank == 0 )
+                printf( "frame %d type %s qp_offset_mean %.4f\n", frame, type_name( type ), mean );
+            else
+                fprintf( stderr, "rank %d frame %d type %s qp_offset_mean %.4f\n", rank, frame, type_name( type ), mean );
         }
         else if( !pic )
             break;                                                     /* flushing and nothing left */
@@ -99,7 +117,24 @@ int main( int argc, char **argv )
     free( qp );
     x264cu_free_host( ctx, luma );
     x264cu_slicetype_close( st );
+    if( nc )
+    {
+        unsigned long long bytes = 0;
+        long calls = x264cu_nccl_calls( nc, &bytes );
+        fprintf( stderr, "rank %d: %ld NCCL all-gathers, %.1f MB gathered\n", rank, calls, bytes / 1e6 );
+        x264cu_nccl_close( nc );
+    }
     x264cu_close( ctx );
     if( in ) fclose( in );
+    if( rank == 0 && ranks > 1 )
+    {
+        for( int r = 1; r < ranks; r++ )
+        {
+            int status = 0;
+            waitpid( kids[r], &status, 0 );
+            if( !WIFEXITED( status ) || WEXITSTATUS( status ) ) rc = 1;
+        }
+        remove( id_path );
+    }
     return rc;
 }

@@ -416,6 +416,19 @@ int  x264cu_slicetype_set_shard( x264cu_slicetype_t *st, int rank, int world, x2
 int  x264cu_lookahead_finalize_batch_sharded( x264cu_lookahead_t *la, int n, const int *b_slot, const int *p0_slot, const int *p1_slot,
                                               const int *d0, const int *d1, const int *owner, int rank, int world,
                                               x264cu_exchange_fn exchange, void *user );
+/* A ready-made exchange for hosts written in C: ncclAllGather over NVLink / NVSwitch.  libnccl.so.2 is loaded at run time (dlopen;
+ * X264CU_NCCL_LIB names another file), so linking libx264_b200 never pulls NCCL in.  One process per GPU:
+ *   x264cu_nccl_open: rank 0 creates the ncclUniqueId and publishes it in the file `id_path` (any path all ranks can read, e.g. on
+ *                     /dev/shm); the other ranks wait for it (timeout_s, 0 = 60) -- or
+ *   x264cu_nccl_wrap: use a communicator (ncclComm_t) the application already has;
+ * then  x264cu_slicetype_set_shard( st, rank, world, x264cu_exchange_nccl, nc ). */
+typedef struct x264cu_nccl x264cu_nccl_t;
+int  x264cu_nccl_open( x264cu_ctx_t *ctx, int rank, int world, const char *id_path, int timeout_s, x264cu_nccl_t **out );
+int  x264cu_nccl_wrap( x264cu_ctx_t *ctx, void *nccl_comm, int rank, int world, x264cu_nccl_t **out );
+void x264cu_nccl_close( x264cu_nccl_t *nc );
+int  x264cu_exchange_nccl( void *user, int phase, size_t bytes_per_rank, void **d_send, void **d_recv, void *stream );
+long x264cu_nccl_calls( x264cu_nccl_t *nc, unsigned long long *bytes );      /* exchanges so far, bytes gathered */
+
 /* the lookahead object underneath (for reading per-MB results) and the slot a display index currently occupies (-1 if gone) */
 x264cu_lookahead_t *x264cu_slicetype_lookahead( x264cu_slicetype_t *st );
 int  x264cu_slicetype_slot_of( x264cu_slicetype_t *st, int frame );

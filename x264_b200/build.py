@@ -57,7 +57,7 @@ def build(force=False, verbose=False, variant=None, defines=()):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("x264_b200: CUDA build failed")
-    cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lm"]
+    cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lm", "-ldl"]
     subprocess.check_call(cmd)
     return lib
 
