@@ -172,6 +172,20 @@ int x264cu_weight_scale_plane( x264cu_ctx_t *ctx, const uint8_t *d_src, uint8_t 
 int x264cu_pixel_ssd_wxh( x264cu_ctx_t *ctx, const uint8_t *d_pix1, intptr_t stride1, const uint8_t *d_pix2, intptr_t stride2,
                           int width, int height, uint64_t *h_ssd );
 
+/* Input staging (N4): the plane-copy entries of the mc table (common/mc.c:294-339, x264_mc_functions_t.plane_copy_swap /
+ * _interleave / _deinterleave; a plain plane_copy is cudaMemcpy2D) on planes in HBM: w x h byte PAIRS. */
+int x264cu_plane_copy_interleave( x264cu_ctx_t *ctx, uint8_t *d_dst, intptr_t dst_stride, const uint8_t *d_srcu, intptr_t srcu_stride,
+                                  const uint8_t *d_srcv, intptr_t srcv_stride, int w, int h );
+int x264cu_plane_copy_deinterleave( x264cu_ctx_t *ctx, uint8_t *d_dsta, intptr_t dsta_stride, uint8_t *d_dstb, intptr_t dstb_stride,
+                                    const uint8_t *d_src, intptr_t src_stride, int w, int h );
+int x264cu_plane_copy_swap( x264cu_ctx_t *ctx, uint8_t *d_dst, intptr_t dst_stride, const uint8_t *d_src, intptr_t src_stride, int w, int h );
+/* x264_frame_copy_picture (common/frame.c:363-480) for the 8-bit 4:2:0 colour spaces: a picture in host memory (x264_image_t:
+ * i_csp = X264_CSP_I420 2 / YV12 3 / NV12 4 / NV21 5, optionally | X264_CSP_VFLIP 0x1000; plane pointers and strides) becomes the
+ * reference's internal frame in HBM: the luma plane and ONE interleaved Cb/Cr plane (width/2 pairs x height/2 rows; d_chroma may
+ * be NULL).  Enqueued on the context's stream; the host planes may be reused after x264cu_sync. */
+int x264cu_frame_copy_picture( x264cu_ctx_t *ctx, int i_csp, const uint8_t *const h_plane[3], const int stride[3], int width, int height,
+                               uint8_t *d_luma, intptr_t luma_stride, uint8_t *d_chroma, intptr_t chroma_stride );
+
 /* x264_adaptive_quant_frame( h, frame, NULL ) (encoder/ratecontrol.c:305-420), aq-mode 0 - 3: per macroblock the AC energy of
  * the 16x16 luma block and the two 8x8 chroma blocks (ac_energy_mb), f_qp_offset_aq = aq_strength * 1.0397 * (x264_log2(energy)
  * - 14.427) and i_inv_qscale_factor = x264_exp2fix8 of it -- the two per-macroblock inputs of the lookahead (frame_put's

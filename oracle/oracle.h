@@ -54,6 +54,12 @@ void orc_weight_scale_plane( uint8_t *dst, intptr_t sd, const uint8_t *src, intp
 /* mc_chroma (common/mc.c:251-283) for one component (0 = U, 1 = V) of an NV12 plane; w x h chroma pixels */
 void orc_mc_chroma( uint8_t *dst, intptr_t dst_stride, const uint8_t *src_uv, intptr_t src_stride,
                     int mvx, int mvy, int w, int h, int comp );
+/* input staging: common/mc.c:294-339 and x264_frame_copy_picture (common/frame.c:363-480), 8-bit 4:2:0 colour spaces */
+void orc_plane_copy_interleave( uint8_t *dst, intptr_t sd, const uint8_t *u, intptr_t su, const uint8_t *v, intptr_t sv, int w, int h );
+void orc_plane_copy_deinterleave( uint8_t *a, intptr_t sa, uint8_t *b, intptr_t sb, const uint8_t *src, intptr_t ss, int w, int h );
+void orc_plane_copy_swap( uint8_t *dst, intptr_t sd, const uint8_t *src, intptr_t ss, int w, int h );
+int  orc_frame_copy_picture( int i_csp, const uint8_t *const plane[3], const int stride[3], int w, int h,
+                             uint8_t *luma, intptr_t sl, uint8_t *chroma, intptr_t sc );
 /* table[0 .. 2*len] with the zero-mvd entry at table[len]; len = 2*4*mv_range */
 void orc_cost_mv_table( uint16_t *table, int len, int lambda );
 

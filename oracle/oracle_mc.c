@@ -167,3 +167,64 @@ void orc_cost_mv_table( uint16_t *table, int len, int lambda )
         table[len+i] = table[len-i] = (uint16_t)c;
     }
 }
+
+
+/* ---- input staging: common/mc.c:294-339 (plane_copy, _swap, _interleave, _deinterleave) and x264_frame_copy_picture
+ * (common/frame.c:363-480) for the 8-bit 4:2:0 colour spaces ---------------------------------------------------------------- */
+void orc_plane_copy_interleave( uint8_t *dst, intptr_t sd, const uint8_t *u, intptr_t su, const uint8_t *v, intptr_t sv, int w, int h )
+{
+    for( int y = 0; y < h; y++ )
+        for( int x = 0; x < w; x++ )
+        {
+            dst[y*sd + 2*x]     = u[y*su + x];
+            dst[y*sd + 2*x + 1] = v[y*sv + x];
+        }
+}
+
+void orc_plane_copy_deinterleave( uint8_t *a, intptr_t sa, uint8_t *b, intptr_t sb, const uint8_t *src, intptr_t ss, int w, int h )
+{
+    for( int y = 0; y < h; y++ )
+        for( int x = 0; x < w; x++ )
+        {
+            a[y*sa + x] = src[y*ss + 2*x];
+            b[y*sb + x] = src[y*ss + 2*x + 1];
+        }
+}
+
+void orc_plane_copy_swap( uint8_t *dst, intptr_t sd, const uint8_t *src, intptr_t ss, int w, int h )
+{
+    for( int y = 0; y < h; y++ )
+        for( int x = 0; x < w; x++ )
+        {
+            dst[y*sd + 2*x]     = src[y*ss + 2*x + 1];
+            dst[y*sd + 2*x + 1] = src[y*ss + 2*x];
+        }
+}
+
+/* i_csp: X264_CSP_I420 2, YV12 3, NV12 4, NV21 5, | X264_CSP_VFLIP 0x1000 (x264.h:251-271); luma w x h, chroma (w/2 pairs) x (h/2) */
+int orc_frame_copy_picture( int i_csp, const uint8_t *const plane[3], const int stride[3], int w, int h,
+                            uint8_t *luma, intptr_t sl, uint8_t *chroma, intptr_t sc )
+{
+    const int csp = i_csp & 0xff, flip = ( i_csp & 0x1000 ) != 0, cw = w >> 1, ch = h >> 1;
+    if( csp < 2 || csp > 5 ) return -1;
+    const uint8_t *p[3]; intptr_t st[3];
+    for( int i = 0; i < 3; i++ )
+    {   /* get_plane_ptr, frame.c:342-358: a flipped plane starts at its last row and walks up */
+        const int rows = i ? ch : h;
+        p[i] = plane[i]; st[i] = stride[i];
+        if( flip && p[i] ) { p[i] += (intptr_t)( rows - 1 ) * stride[i]; st[i] = -st[i]; }
+    }
+    for( int y = 0; y < h; y++ )
+        memcpy( luma + y*sl, p[0] + y*st[0], w );
+    if( csp == 4 )
+        for( int y = 0; y < ch; y++ )
+            memcpy( chroma + y*sc, p[1] + y*st[1], 2*cw );
+    else if( csp == 5 )
+        orc_plane_copy_swap( chroma, sc, p[1], st[1], cw, ch );
+    else
+    {
+        const int iu = csp == 3 ? 2 : 1, iv = csp == 3 ? 1 : 2;
+        orc_plane_copy_interleave( chroma, sc, p[iu], st[iu], p[iv], st[iv], cw, ch );
+    }
+    return 0;
+}

@@ -1190,3 +1190,28 @@ XREF_API int xref_encode_i420_hash( void *hv, const uint8_t *yuv, int n, uint64_
 
 /* 1 if the encoder behind hv still has its offload hooks switched on (h->param.b_opencl survives only if the backend came up) */
 XREF_API int xref_offload_active( void *hv ) { return ((x264_t*)hv)->param.b_opencl; }
+
+
+/* x264_frame_copy_picture (common/frame.c:363-480) on a frame of the encoder's own pool: the picture as the reference lays it out
+ * internally -- out_luma = plane[0] (width x height, packed), out_uv = plane[1] (interleaved, width x height/2, packed) */
+XREF_API int xref_frame_copy_picture( void *hv, int i_csp, uint8_t *const plane[3], const int stride[3], uint8_t *out_luma, uint8_t *out_uv )
+{
+    x264_t *h = hv;
+    tables_init();
+    x264_picture_t pic;
+    x264_picture_init( &pic );
+    pic.img.i_csp = i_csp;
+    pic.img.i_plane = 3;
+    for( int i = 0; i < 3; i++ ) { pic.img.plane[i] = plane[i]; pic.img.i_stride[i] = stride[i]; }
+    x264_frame_t *f = x264_frame_pop_unused( h, 0 );
+    if( !f ) return -1;
+    int r = x264_frame_copy_picture( h, f, &pic );
+    if( !r )
+    {
+        int w = h->param.i_width, ht = h->param.i_height;
+        for( int y = 0; y < ht; y++ ) memcpy( out_luma + (size_t)y*w, f->plane[0] + (intptr_t)y*f->i_stride[0], w );
+        for( int y = 0; y < ht/2; y++ ) memcpy( out_uv + (size_t)y*w, f->plane[1] + (intptr_t)y*f->i_stride[1], w );
+    }
+    x264_frame_push_unused( h, f );
+    return r;
+}
