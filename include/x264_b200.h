@@ -172,6 +172,29 @@ int x264cu_weight_scale_plane( x264cu_ctx_t *ctx, const uint8_t *d_src, uint8_t 
 int x264cu_pixel_ssd_wxh( x264cu_ctx_t *ctx, const uint8_t *d_pix1, intptr_t stride1, const uint8_t *d_pix2, intptr_t stride2,
                           int width, int height, uint64_t *h_ssd );
 
+/* Successive elimination (a7).  x264cu_integral_init = what integral_init4h / 8h / 4v / 8v leave in frame->integral once
+ * x264_frame_filter has run over a reference frame (common/mc.c:424-456, :748-783): d_sum8[y*stride + x] = the sum of the 8x8 pixel
+ * box with its top-left corner at (x, y), for every position of the padded plane where the box fits ((-PAD .. width+PAD-8) x
+ * (-PAD .. height+PAD-8)); d_sum4 (may be NULL; the reference keeps it with sub-8x8 partitions) the same for 4x4 boxes.
+ * d_plane / d_sum8 / d_sum4 point at position (0,0); stride in ELEMENTS, the pixel plane's. */
+int x264cu_integral_init( x264cu_ctx_t *ctx, const uint8_t *d_plane, intptr_t stride, int width, int height,
+                          uint16_t *d_sum8, uint16_t *d_sum4 );
+/* pixf.ads[i_pixel] (x264_pixel_ads1 / 2 / 4, common/pixel.c:759-803) over many rows of candidates: job = one call --
+ * ( enc_dc, sums = d_sums + sums_off, delta, cost_mvx = d_cost_mvx + cost_off, width, thresh ).  For every job the indices i <
+ * width with  sum_k |enc_dc[k] - sums[i + offset_k]| + cost_mvx[i] < thresh  are written in ascending order to d_mvs + out_off
+ * (room for `width` entries) and their number to d_counts[job]: mvs[] and the return value of the reference's function. */
+typedef struct
+{
+    int32_t  enc_dc[4];              /* DC of the block's 8x8 (4x4) sub-blocks: me.c:644-651 */
+    uint32_t sums_off;               /* element offset of the row's first position in the sums plane */
+    int32_t  delta;                  /* me.c:639-649: 8 or 4, times the stride for 16x16, 8x16 and 4x8 */
+    uint32_t cost_off;               /* offset of cost_mvx[0] in d_cost_mvx */
+    int32_t  width, thresh;
+    uint32_t out_off;                /* where this job's list starts in d_mvs */
+} x264cu_ads_job_t;
+int x264cu_pixel_ads_batch( x264cu_ctx_t *ctx, int i_pixel, const uint16_t *d_sums, const uint16_t *d_cost_mvx,
+                            const x264cu_ads_job_t *d_jobs, int n, int32_t *d_counts, int16_t *d_mvs );
+
 /* Input staging (N4): the plane-copy entries of the mc table (common/mc.c:294-339, x264_mc_functions_t.plane_copy_swap /
  * _interleave / _deinterleave; a plain plane_copy is cudaMemcpy2D) on planes in HBM: w x h byte PAIRS. */
 int x264cu_plane_copy_interleave( x264cu_ctx_t *ctx, uint8_t *d_dst, intptr_t dst_stride, const uint8_t *d_srcu, intptr_t srcu_stride,

@@ -54,6 +54,9 @@ void orc_weight_scale_plane( uint8_t *dst, intptr_t sd, const uint8_t *src, intp
 /* mc_chroma (common/mc.c:251-283) for one component (0 = U, 1 = V) of an NV12 plane; w x h chroma pixels */
 void orc_mc_chroma( uint8_t *dst, intptr_t dst_stride, const uint8_t *src_uv, intptr_t src_stride,
                     int mvx, int mvy, int w, int h, int comp );
+/* successive elimination: pixf.ads[] (common/pixel.c:759-803), integral planes (common/mc.c:424-456, :748-783) */
+int  orc_pixel_ads( int k, const int enc_dc[4], const uint16_t *sums, int delta, const uint16_t *cost_mvx, int16_t *mvs, int width, int thresh );
+void orc_integral_init( const uint8_t *plane, intptr_t stride, int width, int height, int pad, uint16_t *sum8, uint16_t *sum4 );
 /* input staging: common/mc.c:294-339 and x264_frame_copy_picture (common/frame.c:363-480), 8-bit 4:2:0 colour spaces */
 void orc_plane_copy_interleave( uint8_t *dst, intptr_t sd, const uint8_t *u, intptr_t su, const uint8_t *v, intptr_t sv, int w, int h );
 void orc_plane_copy_deinterleave( uint8_t *a, intptr_t sa, uint8_t *b, intptr_t sb, const uint8_t *src, intptr_t ss, int w, int h );

@@ -163,3 +163,54 @@ void orc_pixel_cmp_mvfield( int metric, int i_pixel,
                                         ref + ((intptr_t)by*h + my)*ref_stride + bx*w + mx, ref_stride );
             }
 }
+
+
+/* ---- successive elimination: pixf.ads[] (common/pixel.c:759-803) and the integral image (common/mc.c:424-456, :748-783) ------ */
+/* k = 1, 2 or 4 terms (x264_pixel_ads1 / ads2 / ads4); returns the number of passing positions, their indices in mvs[] */
+int orc_pixel_ads( int k, const int enc_dc[4], const uint16_t *sums, int delta, const uint16_t *cost_mvx, int16_t *mvs, int width, int thresh )
+{
+    int nmv = 0;
+    for( int i = 0; i < width; i++ )
+    {
+        int ads = abs( enc_dc[0] - sums[i] ) + cost_mvx[i];
+        if( k == 2 ) ads += abs( enc_dc[1] - sums[i + delta] );
+        if( k == 4 ) ads += abs( enc_dc[1] - sums[i + 8] ) + abs( enc_dc[2] - sums[i + delta] ) + abs( enc_dc[3] - sums[i + delta + 8] );
+        if( ads < thresh )
+            mvs[nmv++] = i;
+    }
+    return nmv;
+}
+
+/* The integral planes as x264_frame_filter builds them row by row: a horizontal running box (integral_init4h / 8h) added to the
+ * row above (a vertical prefix, u16 wrap-around and all), then differences 4 / 8 rows apart (integral_init4v / 8v).  plane /
+ * sum8 / sum4 point at position (0,0); the padded plane is `pad` wide on every side; stride in elements.  Rows and columns are
+ * walked from -pad.  sum4 == NULL: the 8x8-only form (no sub-8x8 partitions). */
+void orc_integral_init( const uint8_t *plane, intptr_t stride, int width, int height, int pad, uint16_t *sum8, uint16_t *sum4 )
+{
+    const int n = sum4 ? 4 : 8, cols = width + 2*pad - n;             /* positions per row: x = -pad .. -pad + cols */
+    uint16_t *top = sum8 - (intptr_t)pad*stride - pad;
+    for( int x = 0; x <= cols + n; x++ ) top[x] = 0;                  /* the row above the first one (mc.c:757-760) */
+    for( int y = -pad; y < height + pad; y++ )
+    {
+        const uint8_t *pix = plane + (intptr_t)y*stride - pad;
+        uint16_t *row = sum8 + (intptr_t)( y + 1 )*stride - pad;      /* prefix row y+1 = box row y + prefix row y */
+        int v = 0;
+        for( int i = 0; i < n; i++ ) v += pix[i];
+        for( int x = 0; x <= cols; x++ )
+        {
+            row[x] = (uint16_t)( v + row[x - stride] );
+            if( x < cols ) v += pix[x + n] - pix[x];
+        }
+        if( y < 8 - pad )
+            continue;
+        uint16_t *s8 = row - 8*stride;                                /* final row y-7 */
+        if( sum4 )
+        {
+            uint16_t *s4 = sum4 + ( s8 - sum8 );
+            for( int x = 0; x <= cols; x++ ) s4[x] = (uint16_t)( s8[x + 4*stride] - s8[x] );
+            for( int x = 0; x <= cols - 4; x++ ) s8[x] = (uint16_t)( s8[x + 8*stride] + s8[x + 8*stride + 4] - s8[x] - s8[x + 4] );
+        }
+        else
+            for( int x = 0; x <= cols; x++ ) s8[x] = (uint16_t)( s8[x + 8*stride] - s8[x] );
+    }
+}

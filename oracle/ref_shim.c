@@ -1215,3 +1215,42 @@ XREF_API int xref_frame_copy_picture( void *hv, int i_csp, uint8_t *const plane[
     x264_frame_push_unused( h, f );
     return r;
 }
+
+
+/* pixf.ads[i_pixel] (common/pixel.c:759-803) */
+XREF_API int xref_pixel_ads( int i_pixel, int *enc_dc, uint16_t *sums, int delta, uint16_t *cost_mvx, int16_t *mvs, int width, int thresh )
+{
+    tables_init();
+    return g_pf.ads[i_pixel]( enc_dc, sums, delta, cost_mvx, mvs, width, thresh );
+}
+
+/* The integral planes x264_frame_filter leaves for a reference frame (common/mc.c:748-783; the encoder must have been opened with
+ * me=esa or tesa): out8 / out4 (out4 only with sub-8x8 partitions, else untouched) receive stride * (lines + 2*PADV) elements each,
+ * starting PADV rows and PADH columns before position (0,0).  *stride_out = the frame's stride.  Returns 1 if the 4x4 plane exists. */
+XREF_API int xref_frame_integral( void *hv, const uint8_t *luma, intptr_t luma_stride, uint16_t *out8, uint16_t *out4, int *stride_out )
+{
+    x264_t *h = hv;
+    x264_frame_t *f = x264_frame_pop_unused( h, 1 );
+    if( !f || !f->integral ) return -1;
+    int W = h->mb.i_mb_width*16, H = h->mb.i_mb_height*16;
+    for( int y = 0; y < H; y++ )
+        memcpy( f->plane[0] + y*f->i_stride[0], luma + y*luma_stride, W );
+    f->b_kept_as_ref = 1;
+    h->i_threadslice_start = 0;
+    h->i_threadslice_end = h->mb.i_mb_height;
+    for( int mb_y = 0; mb_y < h->mb.i_mb_height; mb_y++ )
+    {
+        int end = mb_y == h->mb.i_mb_height - 1;
+        x264_frame_expand_border( h, f, mb_y );
+        x264_frame_filter( h, f, mb_y, end );
+        x264_frame_expand_border_filtered( h, f, mb_y, end );
+    }
+    intptr_t st = f->i_stride[0];
+    size_t n = (size_t)st * ( f->i_lines[0] + 2*PADV );
+    memcpy( out8, f->integral - PADV*st - PADH, ( n - 64 ) * sizeof(uint16_t) );
+    int sub = h->frames.b_have_sub8x8_esa;
+    if( sub ) memcpy( out4, f->integral + n - PADV*st - PADH, ( n - 64 ) * sizeof(uint16_t) );
+    *stride_out = st;
+    x264_frame_push_unused( h, f );
+    return sub;
+}
