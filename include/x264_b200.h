@@ -142,12 +142,22 @@ int x264cu_pixel_cmp_mvfield_host( x264cu_ctx_t *ctx, int metric, int i_pixel,
 int x264cu_frame_init_lowres( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, int width, int height,
                               uint8_t *const d_lowres[4], intptr_t lowres_stride );
 
+/* the same for a stack of n_pictures pictures in one launch: picture p's luma at d_luma + p * luma_pitch, its four planes at
+ * d_lowres[i] + p * lowres_pitch */
+int x264cu_frame_init_lowres_batch( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, intptr_t luma_pitch, int n_pictures,
+                                    int width, int height, uint8_t *const d_lowres[4], intptr_t lowres_stride, intptr_t lowres_pitch );
+
 /* hpel_filter as driven over a whole frame by x264_frame_filter + x264_frame_expand_border_filtered
  * (common/mc.c:172-196, :704-746; common/frame.c:596-625): fills the H, V and C half-pel planes (origins given,
  * same stride, X264CU_PAD border) from a width x height luma plane; also (re)writes the border of d_src itself
  * when expand_src != 0 (x264_frame_expand_border, frame.c:562-594). */
 int x264cu_hpel_filter( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, int width, int height,
                         uint8_t *d_h, uint8_t *d_v, uint8_t *d_c, int expand_src );
+
+/* the same over a stack of n_planes pictures in one launch (plane p of each of the four stacks at + p * plane_pitch bytes): what a
+ * caller holding several reconstructed pictures -- or a measurement that wants inputs larger than the L2 -- uses */
+int x264cu_hpel_filter_batch( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, intptr_t plane_pitch, int n_planes, int width, int height,
+                              uint8_t *d_h, uint8_t *d_v, uint8_t *d_c, int expand_src );
 
 /* mc_luma / get_ref (common/mc.c:198-249, tables x264_hpel_ref0/1 common/tables.c:183-184): job i produces the w x h block
  * (i_pixel) of the reference at quarter-pel vector (mvx, mvy) -- one half-pel plane or the rounded mean of two, then the

@@ -16,7 +16,8 @@ __device__ __forceinline__ int clampi( int v, int lo, int hi ) { return min( max
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__( 256 )
 lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, int height,
-               uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, int wl, int ll, int fast_ok )
+               uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, int wl, int ll, int fast_ok,
+               int skip_x1 = 0, intptr_t src_pitch = 0, intptr_t dst_pitch = 0 )
 {
     // output domain incl. border: x in [-PAD, wl+PAD) in groups of 4, y in [-PAD, ll+PAD)
     const int groups_x = ( wl + 2*X264CU_PAD ) / 4;
@@ -24,6 +25,11 @@ lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, 
     const int oy = blockIdx.y - X264CU_PAD;
     if( gx >= groups_x ) return;
     const int ox = gx * 4 - X264CU_PAD;
+    // columns [0, skip_x1) of the picture's own rows are lowres_wide_kernel's
+    if( ox >= 0 && ox + 4 <= skip_x1 && oy >= 0 && oy < ll ) return;
+    src += (intptr_t)blockIdx.z * src_pitch;
+    d0 += (intptr_t)blockIdx.z * dst_pitch; dh += (intptr_t)blockIdx.z * dst_pitch;
+    dv += (intptr_t)blockIdx.z * dst_pitch; dc += (intptr_t)blockIdx.z * dst_pitch;
     const int y = clampi( oy, 0, ll-1 );
     if( fast_ok && ox >= 0 && ox + 4 <= wl && 2*( ox + 4 ) + 1 <= width )
     {   // columns 2ox .. 2ox+8 inside the picture (rows are clamped: the rows of the top / bottom border repeat the edge rows'
@@ -73,6 +79,55 @@ lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, 
     *(uint32_t *)( dh + (intptr_t)oy*dst_stride + ox ) = o1;
     *(uint32_t *)( dv + (intptr_t)oy*dst_stride + ox ) = o2;
     *(uint32_t *)( dc + (intptr_t)oy*dst_stride + ox ) = o3;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// lowres, wide path (16-byte aligned source rows): thread = 8 output pixels x 2 output rows of all four planes -- five source
+// rows of 16 + 1 bytes (128-bit loads), eight 64-bit stores; the filter itself as in lowres_kernel, on packed bytes.
+// Interior of the picture only; the border and the picture's last columns stay with lowres_kernel (launched on that band).
+// blockIdx.z = picture of a stack.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lowres_row8( const uint32_t a[5], const uint32_t b[5], uint8_t *p0, uint8_t *ph, uint8_t *pv, uint8_t *pc )
+{   // a = vertical mean of source rows (2y, 2y+1), b = of (2y+1, 2y+2): words 0..3 = columns 0..15, word 4 byte 0 = column 16
+    const uint32_t a_ev0 = __byte_perm( a[0], a[1], 0x6420 ), a_od0 = __byte_perm( a[0], a[1], 0x7531 );
+    const uint32_t a_ev1 = __byte_perm( a[2], a[3], 0x6420 ), a_od1 = __byte_perm( a[2], a[3], 0x7531 );
+    const uint32_t b_ev0 = __byte_perm( b[0], b[1], 0x6420 ), b_od0 = __byte_perm( b[0], b[1], 0x7531 );
+    const uint32_t b_ev1 = __byte_perm( b[2], b[3], 0x6420 ), b_od1 = __byte_perm( b[2], b[3], 0x7531 );
+    const uint32_t a_e20 = __byte_perm( a_ev0, a_ev1, 0x4321 ), a_e21 = __byte_perm( a_ev1, a[4], 0x4321 );
+    const uint32_t b_e20 = __byte_perm( b_ev0, b_ev1, 0x4321 ), b_e21 = __byte_perm( b_ev1, b[4], 0x4321 );
+    *(uint2 *)p0 = make_uint2( __vavgu4( a_ev0, a_od0 ), __vavgu4( a_ev1, a_od1 ) );
+    *(uint2 *)ph = make_uint2( __vavgu4( a_od0, a_e20 ), __vavgu4( a_od1, a_e21 ) );
+    *(uint2 *)pv = make_uint2( __vavgu4( b_ev0, b_od0 ), __vavgu4( b_ev1, b_od1 ) );
+    *(uint2 *)pc = make_uint2( __vavgu4( b_od0, b_e20 ), __vavgu4( b_od1, b_e21 ) );
+}
+
+__global__ void __launch_bounds__( 128 )
+lowres_wide_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, intptr_t src_pitch, int height,
+                    uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, intptr_t dst_pitch, int groups, int ll )
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * 2;                                  // output rows y, y+1 (ll is even)
+    if( g >= groups ) return;
+    src += (intptr_t)blockIdx.z * src_pitch;
+    const intptr_t doff = (intptr_t)blockIdx.z * dst_pitch + (intptr_t)y * dst_stride + 8 * g;
+    uint32_t r[5][5];
+#pragma unroll
+    for( int k = 0; k < 5; k++ )
+    {
+        const uint8_t *p = src + (intptr_t)min( 2 * y + k, height - 1 ) * src_stride + 16 * g;
+        const uint4 v = __ldg( (const uint4 *)p );
+        r[k][0] = v.x; r[k][1] = v.y; r[k][2] = v.z; r[k][3] = v.w;
+        r[k][4] = __ldg( (const uint32_t *)( p + 16 ) );
+    }
+    uint32_t m[4][5];                                              // vertical means of consecutive source rows
+#pragma unroll
+    for( int k = 0; k < 4; k++ )
+#pragma unroll
+        for( int i = 0; i < 5; i++ ) m[k][i] = __vavgu4( r[k][i], r[k + 1][i] );
+    lowres_row8( m[0], m[1], d0 + doff, dh + doff, dv + doff, dc + doff );
+    if( y + 1 < ll )
+        lowres_row8( m[2], m[3], d0 + doff + dst_stride, dh + doff + dst_stride, dv + doff + dst_stride, dc + doff + dst_stride );
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -212,26 +267,174 @@ hpel_words_kernel( const uint8_t *__restrict__ src, intptr_t stride, int width, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// hpel, packed path (16-byte aligned planes, width % 4 == 0): CTA = 128 x 32 output tile of the padded domain, 192 threads.
+// All arithmetic runs on packed data: the vertical taps on 16-bit fields, two pixels per 32-bit word (no carries between fields:
+// every partial sum stays within 16 bits once biased by 4112), the horizontal taps with dp4a on the bytes (H) and dp2a on the
+// biased 16-bit vertical sums (C), clamping with the packed min/max instructions (VIMNMX / VIADDMNMX .S16x2).
+//   phase 1  stage rows y0-2 .. y0+34, columns x0-16 .. x0+143 as 16-byte vectors (rows clamped at the picture's edge; tiles that
+//            reach over the left / right edge clamp byte by byte)
+//   phase 2  a thread walks 8 output rows of one 4-pixel column group down a sliding window of 6 unpacked rows: V plane + the
+//            biased vertical sums (v + 4112) into shared memory (mc.c:176-183)
+//   phase 3  H from the source row, C from the vertical sums (mc.c:184-193); 4 pixels per thread and step
+// ------------------------------------------------------------------------------------------------
+constexpr int PT_W = 128, PT_H = 32, PT_ROWS = PT_H + 5, PT_PITCH = 160, PT_VW = 72, PT_THREADS = 192;
+constexpr uint32_t PT_BIAS = 4112u * 0x00010001u;              // 4096 + 16: the rounding of the V plane rides along
+
+__device__ __forceinline__ int dp4a_u8s8( uint32_t a, int32_t b, int32_t c )
+{
+    int d;
+    asm( "dp4a.u32.s32 %0, %1, %2, %3;" : "=r"( d ) : "r"( a ), "r"( b ), "r"( c ) );
+    return d;
+}
+
+__global__ void __launch_bounds__( PT_THREADS )
+hpel_packed_kernel( const uint8_t *__restrict__ src, intptr_t stride, intptr_t pitch, int width, int height,
+                    uint8_t *dh, uint8_t *dv, uint8_t *dc, uint8_t *dsrc_border )
+{
+    __shared__ __align__( 16 ) uint8_t s_src[PT_ROWS][PT_PITCH];
+    __shared__ __align__( 16 ) uint32_t s_v[PT_H][PT_VW];          // two biased vertical sums per word
+    // a stack of pictures: blockIdx.z selects the plane (all five planes share stride and pitch)
+    const intptr_t poff = (intptr_t)blockIdx.z * pitch;
+    src += poff; dh += poff; dv += poff; dc += poff;
+    if( dsrc_border ) dsrc_border += poff;
+    const int x0 = blockIdx.x * PT_W - X264CU_PAD, y0 = blockIdx.y * PT_H - X264CU_PAD;
+    const bool x_inside = x0 - 16 >= 0 && x0 + PT_W + 16 <= width;
+    if( x_inside )
+    {
+        for( int i = threadIdx.x; i < PT_ROWS * ( PT_PITCH / 16 ); i += PT_THREADS )
+        {
+            const int r = i / ( PT_PITCH / 16 ), c = i - r * ( PT_PITCH / 16 );
+            const int sy = clampi( y0 + r - 2, 0, height - 1 );
+            *(uint4 *)&s_src[r][16 * c] = __ldg( (const uint4 *)( src + (intptr_t)sy * stride + x0 - 16 ) + c );
+        }
+    }
+    else
+    {
+        for( int i = threadIdx.x; i < PT_ROWS * PT_PITCH; i += PT_THREADS )
+        {
+            const int r = i / PT_PITCH, c = i - r * PT_PITCH;
+            const int sy = clampi( y0 + r - 2, 0, height - 1 ), sx = clampi( x0 + c - 16, 0, width - 1 );
+            s_src[r][c] = src[(intptr_t)sy * stride + sx];
+        }
+    }
+    __syncthreads();
+    const int full_w = width + 2 * X264CU_PAD, full_h = height + 2 * X264CU_PAD;
+    // ---- phase 2: word column wc covers x0-4+4wc .. +3 (wc = 0 .. 33), rows 8*chunk .. 8*chunk+7
+    if( threadIdx.x < 34 * ( PT_H / 8 ) )
+    {
+        const int chunk = threadIdx.x / 34, wc = threadIdx.x - chunk * 34;
+        const int r0 = chunk * 8;
+        uint32_t lo[6], hi[6];                                       // the window: rows r .. r+5, pixels (0,1) and (2,3) as 16-bit fields
+#pragma unroll
+        for( int k = 0; k < 5; k++ )
+        {
+            const uint32_t w = *(const uint32_t *)&s_src[r0 + k][12 + 4 * wc];
+            lo[k + 1] = __byte_perm( w, 0, 0x4140 ); hi[k + 1] = __byte_perm( w, 0, 0x4342 );
+        }
+        const int ox = x0 + 4 * ( wc - 1 );
+        const bool store_v = wc >= 1 && wc <= PT_W / 4 && ox + X264CU_PAD < full_w;
+#pragma unroll
+        for( int j = 0; j < 8; j++ )
+        {
+#pragma unroll
+            for( int k = 0; k < 5; k++ ) { lo[k] = lo[k + 1]; hi[k] = hi[k + 1]; }
+            const uint32_t w = *(const uint32_t *)&s_src[r0 + j + 5][12 + 4 * wc];
+            lo[5] = __byte_perm( w, 0, 0x4140 ); hi[5] = __byte_perm( w, 0, 0x4342 );
+            // (a + f) + 20 (c + d) - 5 (b + e), both fields at once
+            const uint32_t vl = ( lo[2] + lo[3] ) * 20u + ( lo[0] + lo[5] + PT_BIAS ) - ( lo[1] + lo[4] ) * 5u;
+            const uint32_t vh = ( hi[2] + hi[3] ) * 20u + ( hi[0] + hi[5] + PT_BIAS ) - ( hi[1] + hi[4] ) * 5u;
+            const int r = r0 + j;
+            *(uint2 *)&s_v[r][2 * wc] = make_uint2( vl, vh );
+            const int oy = y0 + r;
+            if( store_v && oy + X264CU_PAD < full_h )
+            {   // ((v + 16) >> 5) + 128 per field, then clamp( . - 128, 0, 255 )
+                const uint32_t pl = __viaddmin_s16x2_relu( ( vl >> 5 ) & 0x07ff07ffu, 0xff80ff80u, 0x00ff00ffu );
+                const uint32_t ph = __viaddmin_s16x2_relu( ( vh >> 5 ) & 0x07ff07ffu, 0xff80ff80u, 0x00ff00ffu );
+                *(uint32_t *)( dv + (intptr_t)oy * stride + ox ) = __byte_perm( pl, ph, 0x6420 );
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 3
+    for( int i = threadIdx.x; i < PT_H * ( PT_W / 4 ); i += PT_THREADS )
+    {
+        const int r = i >> 5, g = i & 31;
+        const int ox = x0 + 4 * g, oy = y0 + r;
+        if( ox + X264CU_PAD >= full_w || oy + X264CU_PAD >= full_h ) continue;
+        // H: taps (1,-5,20,20,-5,1) over bytes k+2 .. k+7 of the 12 bytes x-4 .. x+7
+        const uint32_t *sw = (const uint32_t *)&s_src[r + 2][12 + 4 * g];
+        const uint32_t s0 = sw[0], s1 = sw[1], s2 = sw[2];
+        const int T0123 = 0x1414FB01, T45 = 0x000001FB;
+        const int h0 = dp4a_u8s8( __funnelshift_r( s0, s1, 16 ), T0123, dp4a_u8s8( __funnelshift_r( s1, s2, 16 ), T45, 16 ) );
+        const int h1 = dp4a_u8s8( __funnelshift_r( s0, s1, 24 ), T0123, dp4a_u8s8( __funnelshift_r( s1, s2, 24 ), T45, 16 ) );
+        const int h2 = dp4a_u8s8( s1, T0123, dp4a_u8s8( s2, T45, 16 ) );
+        const int h3 = dp4a_u8s8( __funnelshift_r( s1, s2, 8 ), T0123, dp4a_u8s8( s2 >> 8, T45, 16 ) );
+        uint32_t h01 = __vimin_s16x2_relu( __byte_perm( h0, h1, 0x5410 ), 0x1fff1fffu );       // clamp( h + 16, 0, 8191 ), then >> 5
+        uint32_t h23 = __vimin_s16x2_relu( __byte_perm( h2, h3, 0x5410 ), 0x1fff1fffu );
+        h01 = ( h01 >> 5 ) & 0x00ff00ffu; h23 = ( h23 >> 5 ) & 0x00ff00ffu;
+        // C: the same taps over the biased vertical sums of columns x-2 .. x+6: fields 2 .. 10 of the twelve in vw[0..5]
+        const uint2 *vp = (const uint2 *)&s_v[r][2 * g];
+        const uint2 va = vp[0], vb = vp[1], vc = vp[2];
+        const uint32_t f12 = __funnelshift_r( va.y, vb.x, 16 ), f23 = __funnelshift_r( vb.x, vb.y, 16 ),
+                       f34 = __funnelshift_r( vb.y, vc.x, 16 ), f45 = __funnelshift_r( vc.x, vc.y, 16 );
+        const int U01 = 0x0000FB01, U23 = 0x00001414, U45 = 0x000001FB, C0 = 512 - 32 * 4112;
+        const int c0 = __dp2a_lo( (int)va.y, U01, __dp2a_lo( (int)vb.x, U23, __dp2a_lo( (int)vb.y, U45, C0 ) ) );
+        const int c1 = __dp2a_lo( (int)f12, U01, __dp2a_lo( (int)f23, U23, __dp2a_lo( (int)f34, U45, C0 ) ) );
+        const int c2 = __dp2a_lo( (int)vb.x, U01, __dp2a_lo( (int)vb.y, U23, __dp2a_lo( (int)vc.x, U45, C0 ) ) );
+        const int c3 = __dp2a_lo( (int)f23, U01, __dp2a_lo( (int)f34, U23, __dp2a_lo( (int)f45, U45, C0 ) ) );
+        const uint32_t c01 = __vimin_s16x2_relu( __byte_perm( c0 >> 10, c1 >> 10, 0x5410 ), 0x00ff00ffu );
+        const uint32_t c23 = __vimin_s16x2_relu( __byte_perm( c2 >> 10, c3 >> 10, 0x5410 ), 0x00ff00ffu );
+        const intptr_t o = (intptr_t)oy * stride + ox;
+        *(uint32_t *)( dh + o ) = __byte_perm( h01, h23, 0x6420 );
+        *(uint32_t *)( dc + o ) = __byte_perm( c01, c23, 0x6420 );
+        if( dsrc_border && ( ox < 0 || ox >= width || oy < 0 || oy >= height ) )
+            *(uint32_t *)( dsrc_border + o ) = s1;
+    }
+}
+
 } // namespace
 
 // the same launch on a stream of the caller's choice (the lookahead's upload stream)
+static int lowres_launch( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d_luma, intptr_t luma_stride, intptr_t luma_pitch, int n_pictures,
+                          int width, int height, uint8_t *const d_lowres[4], intptr_t lowres_stride, intptr_t lowres_pitch )
+{
+    if( width < 2 || height < 2 || n_pictures < 1 ) return x264cu_fail( ctx, "frame_init_lowres: bad size %dx%d", width, height );
+    const int wl = ( ( width + 15 ) >> 4 ) * 8, ll = ( ( height + 15 ) >> 4 ) * 8;
+    if( ( lowres_stride & 3 ) || lowres_stride < wl + 2*X264CU_PAD )
+        return x264cu_fail( ctx, "frame_init_lowres: lowres stride %ld too small / unaligned", (long)lowres_stride );
+    uintptr_t dst_bits = (uintptr_t)lowres_stride | (uintptr_t)lowres_pitch;
+    for( int i = 0; i < 4; i++ )
+    {
+        if( (uintptr_t)d_lowres[i] & 3 ) return x264cu_fail( ctx, "frame_init_lowres: plane origins must be 4-byte aligned" );
+        dst_bits |= (uintptr_t)d_lowres[i];
+    }
+    // the vector fast path needs 8-byte aligned source rows; otherwise every pixel takes the clamped path
+    const int aligned = !( (uintptr_t)d_luma & 7 ) && !( luma_stride & 7 ) && !( luma_pitch & 7 );
+    // interior columns in groups of 8 output pixels whose 17 source bytes lie inside the picture: the wide kernel
+    int groups = 0;
+    if( !( ( (uintptr_t)d_luma | (uintptr_t)luma_stride | (uintptr_t)luma_pitch ) & 15 ) && !( dst_bits & 7 ) )
+        groups = min( wl / 8, ( width - 17 ) / 16 + 1 );
+    if( groups > 0 && 16 * ( groups - 1 ) + 20 > luma_stride ) groups--;                 // the 4 bytes past column 16 must be readable
+    if( groups > 0 )
+    {
+        dim3 grid( ( groups + 127 ) / 128, ( ll + 1 ) / 2, n_pictures );
+        lowres_wide_kernel<<<grid, 128, 0, stream>>>( d_luma, luma_stride, luma_pitch, height, d_lowres[0], d_lowres[1], d_lowres[2], d_lowres[3],
+                                                      lowres_stride, lowres_pitch, groups, ll );
+        CU_LAUNCH_CHECK( ctx );
+    }
+    dim3 block( 256 ), grid( ( ( wl + 2*X264CU_PAD ) / 4 + 255 ) / 256, ll + 2*X264CU_PAD, n_pictures );
+    lowres_kernel<<<grid, block, 0, stream>>>( d_luma, luma_stride, width, height, d_lowres[0], d_lowres[1],
+                                               d_lowres[2], d_lowres[3], lowres_stride, wl, ll, aligned, 8 * max( groups, 0 ), luma_pitch, lowres_pitch );
+    CU_LAUNCH_CHECK( ctx );
+    return 0;
+}
+
 int x264cu_frame_init_lowres_on( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d_luma, intptr_t luma_stride, int width, int height,
                                  uint8_t *const d_lowres[4], intptr_t lowres_stride )
 {
     if( !ctx ) return -1;
-    if( width < 2 || height < 2 ) return x264cu_fail( ctx, "frame_init_lowres: bad size %dx%d", width, height );
-    const int wl = ( ( width + 15 ) >> 4 ) * 8, ll = ( ( height + 15 ) >> 4 ) * 8;
-    if( ( lowres_stride & 3 ) || lowres_stride < wl + 2*X264CU_PAD )
-        return x264cu_fail( ctx, "frame_init_lowres: lowres stride %ld too small / unaligned", (long)lowres_stride );
-    for( int i = 0; i < 4; i++ )
-        if( (uintptr_t)d_lowres[i] & 3 ) return x264cu_fail( ctx, "frame_init_lowres: plane origins must be 4-byte aligned" );
-    // the vector fast path needs 8-byte aligned source rows; otherwise every pixel takes the clamped path
-    const int aligned = !( (uintptr_t)d_luma & 7 ) && !( luma_stride & 7 );
-    dim3 block( 256 ), grid( ( ( wl + 2*X264CU_PAD ) / 4 + 255 ) / 256, ll + 2*X264CU_PAD );
-    lowres_kernel<<<grid, block, 0, stream>>>( d_luma, luma_stride, width, height, d_lowres[0], d_lowres[1],
-                                               d_lowres[2], d_lowres[3], lowres_stride, wl, ll, aligned );
-    CU_LAUNCH_CHECK( ctx );
-    return 0;
+    return lowres_launch( ctx, stream, d_luma, luma_stride, 0, 1, width, height, d_lowres, lowres_stride, 0 );
 }
 
 extern "C" {
@@ -244,24 +447,59 @@ int x264cu_frame_init_lowres( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t
     return x264cu_frame_init_lowres_on( ctx, ctx->stream, d_luma, luma_stride, width, height, d_lowres, lowres_stride );
 }
 
+static int hpel_launch( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, intptr_t pitch, int n_planes, int width, int height,
+                        uint8_t *d_h, uint8_t *d_v, uint8_t *d_c, int expand_src )
+{
+    if( width < 1 || height < 1 || n_planes < 1 ) return x264cu_fail( ctx, "hpel_filter: bad size" );
+    const uintptr_t all = (uintptr_t)d_src | (uintptr_t)d_h | (uintptr_t)d_v | (uintptr_t)d_c | (uintptr_t)stride | (uintptr_t)pitch;
+    if( !( all & 15 ) && !( width & 3 ) && width >= 8 )
+    {
+        dim3 grid( ( width + 2*X264CU_PAD + PT_W - 1 ) / PT_W, ( height + 2*X264CU_PAD + PT_H - 1 ) / PT_H, n_planes );
+        hpel_packed_kernel<<<grid, PT_THREADS, 0, ctx->stream>>>( d_src, stride, pitch, width, height, d_h, d_v, d_c, expand_src ? d_src : nullptr );
+        CU_LAUNCH_CHECK( ctx );
+        return 0;
+    }
+    for( int p = 0; p < n_planes; p++ )
+    {
+        const intptr_t o = (intptr_t)p * pitch;
+        const bool words = !( all & 3 ) && !( width & 3 );
+        if( words )
+        {
+            dim3 grid( ( width + 2*X264CU_PAD + FT_W - 1 ) / FT_W, ( height + 2*X264CU_PAD + FT_H - 1 ) / FT_H );
+            hpel_words_kernel<<<grid, 256, 0, ctx->stream>>>( d_src + o, stride, width, height, d_h + o, d_v + o, d_c + o, expand_src ? d_src + o : nullptr );
+        }
+        else
+        {
+            dim3 grid( ( width + 2*X264CU_PAD + HT_W - 1 ) / HT_W, ( height + 2*X264CU_PAD + HT_H - 1 ) / HT_H );
+            hpel_kernel<<<grid, 256, 0, ctx->stream>>>( d_src + o, stride, width, height, d_h + o, d_v + o, d_c + o, expand_src ? d_src + o : nullptr );
+        }
+        CU_LAUNCH_CHECK( ctx );
+    }
+    return 0;
+}
+
+int x264cu_frame_init_lowres_batch( x264cu_ctx_t *ctx, const uint8_t *d_luma, intptr_t luma_stride, intptr_t luma_pitch, int n_pictures,
+                                    int width, int height, uint8_t *const d_lowres[4], intptr_t lowres_stride, intptr_t lowres_pitch )
+{
+    X264CU_ENTER( ctx );
+    if( !ctx ) return -1;
+    return lowres_launch( ctx, ctx->stream, d_luma, luma_stride, luma_pitch, n_pictures, width, height, d_lowres, lowres_stride, lowres_pitch );
+}
+
 int x264cu_hpel_filter( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, int width, int height,
                         uint8_t *d_h, uint8_t *d_v, uint8_t *d_c, int expand_src )
 {
     X264CU_ENTER( ctx );
     if( !ctx ) return -1;
-    if( width < 1 || height < 1 ) return x264cu_fail( ctx, "hpel_filter: bad size" );
-    const bool words = !( ( (uintptr_t)d_src | (uintptr_t)d_h | (uintptr_t)d_v | (uintptr_t)d_c | (uintptr_t)stride ) & 3 ) && !( width & 3 );
-    if( words )
-    {
-        dim3 grid( ( width + 2*X264CU_PAD + FT_W - 1 ) / FT_W, ( height + 2*X264CU_PAD + FT_H - 1 ) / FT_H );
-        hpel_words_kernel<<<grid, 256, 0, ctx->stream>>>( d_src, stride, width, height, d_h, d_v, d_c, expand_src ? d_src : nullptr );
-        CU_LAUNCH_CHECK( ctx );
-        return 0;
-    }
-    dim3 grid( ( width + 2*X264CU_PAD + HT_W - 1 ) / HT_W, ( height + 2*X264CU_PAD + HT_H - 1 ) / HT_H );
-    hpel_kernel<<<grid, 256, 0, ctx->stream>>>( d_src, stride, width, height, d_h, d_v, d_c, expand_src ? d_src : nullptr );
-    CU_LAUNCH_CHECK( ctx );
-    return 0;
+    return hpel_launch( ctx, d_src, stride, 0, 1, width, height, d_h, d_v, d_c, expand_src );
+}
+
+int x264cu_hpel_filter_batch( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, intptr_t plane_pitch, int n_planes, int width, int height,
+                              uint8_t *d_h, uint8_t *d_v, uint8_t *d_c, int expand_src )
+{
+    X264CU_ENTER( ctx );
+    if( !ctx ) return -1;
+    return hpel_launch( ctx, d_src, stride, plane_pitch, n_planes, width, height, d_h, d_v, d_c, expand_src );
 }
 
 } // extern "C"
