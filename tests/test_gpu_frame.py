@@ -51,7 +51,7 @@ def test_frame_init_lowres(ctx, wh):
     ctx.free(d_planes)
 
 
-@pytest.mark.parametrize("wh", [(64, 48), (96, 80), (200, 120)])
+@pytest.mark.parametrize("wh", [(64, 48), (96, 80), (200, 120), (98, 50), (704, 368), (1920, 1080), (3840, 2160)])
 def test_hpel_filter(ctx, wh):
     w, h = wh
     luma = synth_luma(w, h, seed=3 * w + h, kind="noise")
@@ -68,3 +68,48 @@ def test_hpel_filter(ctx, wh):
         assert np.array_equal(got[:, :w + 2 * PAD], ref_planes[i].view()[:, :w + 2 * PAD]), "FHVC"[i]
     for p in d:
         ctx.free(p)
+
+
+def test_frame_kernels_over_a_stack_of_pictures(ctx):
+    """x264cu_hpel_filter_batch / x264cu_frame_init_lowres_batch: several pictures per launch give each picture's own result"""
+    vp, ss, ci = C.c_void_p, C.c_ssize_t, C.c_int
+    ctx.L.x264cu_frame_init_lowres_batch.argtypes = [vp, vp, ss, ss, ci, ci, ci, C.POINTER(vp), ss, ss]
+    ctx.L.x264cu_hpel_filter_batch.argtypes = [vp, vp, ss, ss, ci, ci, ci, vp, vp, vp, ci]
+    w, h, n = 704, 368, 3
+    lumas = [synth_luma(w, h, seed=50 + i, kind="noise") for i in range(n)]
+    # hpel
+    refs = [_libs.make_ref_planes(l) for l in lumas]
+    st, nbytes = refs[0][0].stride, refs[0][0].buf.size
+    pitch = (nbytes + 255) & ~255
+    d = [ctx.malloc(n * pitch + 256) for _ in range(4)]
+    for i, l in enumerate(lumas):
+        src = PaddedPlane(w, h, stride=st)
+        src.inner()[:] = l
+        ctx.h2d(d[0] + i * pitch, src.buf)
+    org = refs[0][0].origin
+    ctx.check(ctx.L.x264cu_hpel_filter_batch(ctx.h, d[0] + org, st, pitch, n, w, h, d[1] + org, d[2] + org, d[3] + org, 1))
+    for i in range(n):
+        for k in range(4):
+            got = ctx.download(d[k] + i * pitch, (h + 2 * PAD, st), np.uint8)
+            assert np.array_equal(got[:, :w + 2 * PAD], refs[i][k].view()[:, :w + 2 * PAD]), (i, "FHVC"[k])
+    for p_ in d:
+        ctx.free(p_)
+    # lowres
+    wl, ll = w // 2, h // 2
+    pl = PaddedPlane(wl, ll)
+    plane_bytes = (pl.buf.size + 255) & ~255
+    pitch_dst, pitch_src = 4 * plane_bytes, w * h
+    d_src, d_pl = ctx.malloc(n * pitch_src + 256), ctx.malloc(n * pitch_dst + 256)
+    for i, l in enumerate(lumas):
+        ctx.h2d(d_src + i * pitch_src, l)
+    darr = (vp * 4)(*[d_pl + k * plane_bytes + pl.origin for k in range(4)])
+    ctx.check(ctx.L.x264cu_frame_init_lowres_batch(ctx.h, d_src, w, pitch_src, n, w, h, darr, pl.stride, pitch_dst))
+    for i, l in enumerate(lumas):
+        want = [PaddedPlane(wl, ll) for _ in range(4)]
+        arr = (vp * 4)(*[p_.buf.ctypes.data + p_.origin for p_ in want])
+        oracle().orc_frame_init_lowres(ptr(l), w, w, h, arr, pl.stride, wl, ll)
+        for k in range(4):
+            got = ctx.download(d_pl + i * pitch_dst + k * plane_bytes, (ll + 2 * PAD, pl.stride), np.uint8)
+            assert np.array_equal(got[:, :wl + 2 * PAD], want[k].view()[:, :wl + 2 * PAD]), (i, "FHVC"[k])
+    ctx.free(d_src)
+    ctx.free(d_pl)
