@@ -930,8 +930,8 @@ struct x264cu_lookahead
 #define LA_SPEC_RING 128
 #define LA_SPEC_MAX 4096             /* requests per batch */
     cudaStream_t spec_stream = nullptr;
-    LaFinalizeArgs *h_spec_args = nullptr, *d_spec_args = nullptr;    // [LA_SPEC_MAX]: staging of one batch's descriptors
-    cudaEvent_t spec_args_ev = nullptr;                               // the staging buffer's last upload
+    LaFinalizeArgs *h_spec_args2[2] = {}, *d_spec_args2[2] = {};      // [LA_SPEC_MAX] each: descriptor staging, alternating per batch
+    cudaEvent_t spec_args_ev2[2] = {};                                // ... and the kernel that last read each
     cudaEvent_t spec_done_ev = nullptr;                               // sharded: a batch's results are in the send buffer
     int32_t *d_spec_rec = nullptr, *h_spec_rec = nullptr;             // [LA_SPEC_RING][LA_SPEC_MAX][8]
     cudaEvent_t spec_ev[LA_SPEC_RING] = {};                           // batch complete, records on the host
@@ -996,8 +996,12 @@ void x264cu_lookahead_close( x264cu_lookahead_t *la )
     if( la->xch_stream ) { cudaStreamSynchronize( la->xch_stream ); cudaStreamDestroy( la->xch_stream ); }
     if( la->mt_stream ) { cudaStreamSynchronize( la->mt_stream ); cudaStreamDestroy( la->mt_stream ); }
     if( la->spec_stream ) { cudaStreamSynchronize( la->spec_stream ); cudaStreamDestroy( la->spec_stream ); }
-    cudaFreeHost( la->h_spec_args ); cudaFreeHost( la->h_spec_rec ); cudaFree( la->d_spec_args ); cudaFree( la->d_spec_rec );
-    if( la->spec_args_ev ) cudaEventDestroy( la->spec_args_ev );
+    cudaFreeHost( la->h_spec_rec ); cudaFree( la->d_spec_rec );
+    for( int i = 0; i < 2; i++ )
+    {
+        cudaFreeHost( la->h_spec_args2[i] ); cudaFree( la->d_spec_args2[i] );
+        if( la->spec_args_ev2[i] ) cudaEventDestroy( la->spec_args_ev2[i] );
+    }
     if( la->spec_done_ev ) cudaEventDestroy( la->spec_done_ev );
     for( int i = 0; i < LA_SPEC_RING; i++ ) if( la->spec_ev[i] ) cudaEventDestroy( la->spec_ev[i] );
     if( la->ev_mt_dep ) cudaEventDestroy( la->ev_mt_dep );
@@ -1107,11 +1111,14 @@ int x264cu_lookahead_open( x264cu_ctx_t *ctx, const x264cu_lookahead_params_t *p
     if( ok && cudaStreamCreateWithPriority( &la->xch_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaStreamCreateWithPriority( &la->mt_stream, cudaStreamNonBlocking, prio_hi ) != cudaSuccess ) ok = false;
     if( ok && cudaStreamCreateWithPriority( &la->spec_stream, cudaStreamNonBlocking, prio_lo ) != cudaSuccess ) ok = false;
-    if( ok && cudaMallocHost( (void **)&la->h_spec_args, sizeof( LaFinalizeArgs ) * LA_SPEC_MAX ) != cudaSuccess ) ok = false;
+    for( int i = 0; i < 2; i++ )
+    {
+        if( ok && cudaMallocHost( (void **)&la->h_spec_args2[i], sizeof( LaFinalizeArgs ) * LA_SPEC_MAX ) != cudaSuccess ) ok = false;
+        alloc( (void **)&la->d_spec_args2[i], sizeof( LaFinalizeArgs ) * LA_SPEC_MAX );
+        if( ok && cudaEventCreateWithFlags( &la->spec_args_ev2[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
+    }
     if( ok && cudaMallocHost( (void **)&la->h_spec_rec, (size_t)LA_SPEC_RING * LA_SPEC_MAX * 32 ) != cudaSuccess ) ok = false;
-    alloc( (void **)&la->d_spec_args, sizeof( LaFinalizeArgs ) * LA_SPEC_MAX );
     alloc( (void **)&la->d_spec_rec, (size_t)LA_SPEC_RING * LA_SPEC_MAX * 32 );
-    if( ok && cudaEventCreateWithFlags( &la->spec_args_ev, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     if( ok && cudaEventCreateWithFlags( &la->spec_done_ev, cudaEventDisableTiming ) != cudaSuccess ) ok = false;
     for( int i = 0; i < LA_SPEC_RING; i++ )
         if( ok && cudaEventCreateWithFlags( &la->spec_ev[i], cudaEventDisableTiming ) != cudaSuccess ) ok = false;
@@ -1947,7 +1954,9 @@ static int la_finalize_batch( x264cu_lookahead_t *la, int n, const int *b_slot, 
     const int ring = (int)( la->spec_next % LA_SPEC_RING );
     // ring entry reuse (its batch is hundreds of pictures old) and the descriptor staging buffer (its last upload)
     CU_CHECK( ctx, cudaEventSynchronize( la->spec_ev[ring] ) );
-    CU_CHECK( ctx, cudaEventSynchronize( la->spec_args_ev ) );
+    const int stg = (int)( la->spec_next & 1 );
+    LaFinalizeArgs *h_args = la->h_spec_args2[stg], *d_args = la->d_spec_args2[stg];
+    CU_CHECK( ctx, cudaEventSynchronize( la->spec_args_ev2[stg] ) );         // the batch before last: long through
     int32_t *d_rec = la->d_spec_rec + (size_t)ring * LA_SPEC_MAX * 8;
     std::vector<char> ev_seen( la->n_ev, 0 ), slot_seen( la->slots.size(), 0 );
     auto wait_ev = [&]( int e ) -> int {
@@ -1977,7 +1986,7 @@ static int la_finalize_batch( x264cu_lookahead_t *la, int n, const int *b_slot, 
             fenc.spec[i0][i1].batch = la->spec_next;               // index set once the blocks' size is known
             if( own != rank ) continue;
         }
-        LaFinalizeArgs &A = la->h_spec_args[m];
+        LaFinalizeArgs &A = h_args[m];
         memset( &A, 0, sizeof( A ) );
         A.fenc = fenc.dev.planes[0];
         for( int k = 0; k < 4; k++ ) { A.ref0[k] = la->slots[s0].dev.planes[k]; A.ref1[k] = f1.dev.planes[k]; }
@@ -2002,12 +2011,12 @@ static int la_finalize_batch( x264cu_lookahead_t *la, int n, const int *b_slot, 
     if( !m && kept.empty() ) return 0;
     if( m )
     {
-        CU_CHECK( ctx, cudaMemcpyAsync( la->d_spec_args, la->h_spec_args, sizeof( LaFinalizeArgs ) * m, cudaMemcpyHostToDevice, la->spec_stream ) );
-        CU_CHECK( ctx, cudaEventRecord( la->spec_args_ev, la->spec_stream ) );
+        CU_CHECK( ctx, cudaMemcpyAsync( d_args, h_args, sizeof( LaFinalizeArgs ) * m, cudaMemcpyHostToDevice, la->spec_stream ) );
         CU_CHECK( ctx, cudaMemsetAsync( d_rec, 0, (size_t)m * 32, la->spec_stream ) );
         const dim3 grid( ( d.mb_count + LA_FIN_THREADS / 4 - 1 ) / ( LA_FIN_THREADS / 4 ), m );
-        finalize_batch_kernel<<<grid, LA_FIN_THREADS, 0, la->spec_stream>>>( d, la->d_spec_args );
+        finalize_batch_kernel<<<grid, LA_FIN_THREADS, 0, la->spec_stream>>>( d, d_args );
         CU_LAUNCH_CHECK( ctx );
+        CU_CHECK( ctx, cudaEventRecord( la->spec_args_ev2[stg], la->spec_stream ) );
     }
     int32_t *h_rec = la->h_spec_rec + (size_t)ring * LA_SPEC_MAX * 8;
     if( !sharded )
