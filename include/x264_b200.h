@@ -431,9 +431,11 @@ void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *st, int prefetch );
  * analysis never looks at more than i_slicetype_length+1 pictures (b_deterministic, slicetype.c:1480-1485), so the
  * decisions do not change -- only the searches of the newest pictures get time to finish on the second stream. */
 void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *st, int pictures );
-/* speculate = 1 (default): with every prefetch launch, all cost requests the decision can make about the new pictures are computed
- * too (x264cu_lookahead_finalize_batch) -- a request then costs the calling thread a table lookup instead of a launch, a copy and
- * a wait.  0: every request is computed when it is made.  The decisions are identical either way. */
+/* speculate = 1: with every prefetch launch, all cost requests the decision can make about the new pictures are computed too
+ * (x264cu_lookahead_finalize_batch) -- a request then costs the calling thread a table lookup instead of a launch, a copy and a
+ * wait.  0: every request is computed when it is made.  Default: on for a sharded stream (where it is what splits the cost
+ * requests between the GPUs), off on a single GPU (the searches' throughput is the bound there and the extra triples cost 5 %).
+ * The decisions are identical either way. */
 void x264cu_slicetype_set_speculation( x264cu_slicetype_t *st, int speculate );
 /* pictures whose searches are gathered into one prefetch launch (1..16; default 12 for lookaheads >= 12, else 1; before the first
  * picture).  A launch needs several dozen independent searches to fill the GPU; the decisions do not depend on it. */

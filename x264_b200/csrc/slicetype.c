@@ -71,7 +71,7 @@ struct x264cu_slicetype
     int next_asked;                      /* type forced on the next queued picture */
     /* prefetch: every search the decision could ask for is launched ahead of time, in groups */
     int prefetch, group, in_group, run_ahead;
-    int speculate;                       /* cost requests computed with the searches (x264cu_lookahead_finalize_batch) */
+    int speculate;                       /* cost requests computed with the searches (x264cu_lookahead_finalize_batch): 0 / 1, -1 = when sharded */
     picture_t *recent[GAP_MAX + 2];      /* the last bframes+1 queued pictures, newest first */
     int n_recent;
     struct { int fenc_slot, ref_slot, list, dist, fenc_no, ref_no; } job[JOBS_MAX];
@@ -846,7 +846,7 @@ int x264cu_slicetype_open( x264cu_ctx_t *ctx, const x264cu_slicetype_params_t *p
     if( s->aq_strength == 0 )
         s->p.la.aq_mode = 0;
     s->prefetch = 1;
-    s->speculate = 1;
+    s->speculate = -1;
     /* measured at 4K (B200), pictures per launch / run-ahead: 4/8 -> 1000 pictures/s, 8/16 -> 1260, 12/24 -> 1410: a launch
      * needs several dozen independent wavefronts to fill the 148 SMs */
     s->group = s->horizon >= 12 ? 12 : 1;
@@ -992,7 +992,9 @@ static int launch_group( x264cu_slicetype_t *s )
         return -1;
     if( s->world > 1 && exchange_group( s ) )
         return -1;
-    if( !s->speculate )
+    /* On one GPU the lookahead is bound by the searches' throughput and the extra triples cost more than the waits they save
+     * (measured at 4K: 1 396 -> 1 327 pictures/s); sharded, the cost requests are the replicated part that has to be split. */
+    if( !( s->speculate < 0 ? s->world > 1 : s->speculate ) )
         return 0;
     return s->world > 1 ? speculate_group( s, all, a_fenc, a_ref, a_list, a_dist, number )
                         : speculate_group( s, n, fenc, ref, list, dist, number );
