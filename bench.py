@@ -502,7 +502,12 @@ def run_lookahead_b200(args, rank, world, local, dist):
     la_st = dict(LA_ST, psy=1) if args.weightp else LA_ST
 
     def make_st():
-        return x.Slicetype(ctx, LA_W, LA_H, **la_st, **LA_OPTS, weighted_pred=args.weightp)
+        st_ = x.Slicetype(ctx, LA_W, LA_H, **la_st, **LA_OPTS, weighted_pred=args.weightp)
+        if args.group:
+            st_.set_prefetch_group(args.group)
+        if args.run_ahead is not None:
+            st_.set_run_ahead(args.run_ahead)
+        return st_
 
     # ---- device-resident pictures -----------------------------------------------------------------
     st = make_st()
@@ -1030,6 +1035,8 @@ def main():
     ap.add_argument("--weightp", type=int, default=1, choices=[0, 1],
                     help="lookahead workload: the lookahead weight analysis (slicetype.c:284-501) and psy, as in preset medium (default); 0: off")
     ap.add_argument("--quick", action="store_true", help="tuning runs: skip the e2e and cpu_baseline legs")
+    ap.add_argument("--group", type=int, default=0, help="lookahead workload: pictures per prefetch launch (0 = the library's default)")
+    ap.add_argument("--run-ahead", type=int, default=None, help="lookahead workload: pictures queued beyond the lookahead before deciding")
     args = ap.parse_args()
 
     if args.impl == "reference":

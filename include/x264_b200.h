@@ -426,7 +426,7 @@ int  x264cu_slicetype_step_device( x264cu_slicetype_t *st, const uint8_t *d_luma
  * launched at once on a second stream (the x264_opencl_slicetype_prep idea, encoder/slicetype-cl.c:653); 0: every search
  * runs on demand inside the cost request that needs it.  The decisions are identical either way. */
 void x264cu_slicetype_set_prefetch( x264cu_slicetype_t *st, int prefetch );
-/* pictures queued beyond the lookahead before a decision is taken (0..32; default 24 for lookaheads >= 12, else 0; must be
+/* pictures queued beyond the lookahead before a decision is taken (0..64; default 24 for lookaheads >= 12, else 0; must be
  * set before the first picture).  It is the synchronous twin of param.i_sync_lookahead (encoder.c:1137-1141, :1611): the
  * analysis never looks at more than i_slicetype_length+1 pictures (b_deterministic, slicetype.c:1480-1485), so the
  * decisions do not change -- only the searches of the newest pictures get time to finish on the second stream. */
@@ -437,7 +437,7 @@ void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *st, int pictures );
  * requests between the GPUs), off on a single GPU (the searches' throughput is the bound there and the extra triples cost 5 %).
  * The decisions are identical either way. */
 void x264cu_slicetype_set_speculation( x264cu_slicetype_t *st, int speculate );
-/* pictures whose searches are gathered into one prefetch launch (1..16; default 12 for lookaheads >= 12, else 1; before the first
+/* pictures whose searches are gathered into one prefetch launch (1..32; default 12 for lookaheads >= 12, else 1; before the first
  * picture).  A launch needs several dozen independent searches to fill the GPU; the decisions do not depend on it. */
 void x264cu_slicetype_set_prefetch_group( x264cu_slicetype_t *st, int pictures );
 /* pic_in->i_type of the NEXT picture queued with x264cu_slicetype_step* (forced frame types: a qpfile, an application's keyframe

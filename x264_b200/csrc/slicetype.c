@@ -21,7 +21,7 @@ enum
 {
     WIN_MAX = 250,                       /* X264_LOOKAHEAD_MAX, common/base.h:140 */
     GAP_MAX = X264CU_BFRAME_MAX,         /* most B pictures between two anchors */
-    AHEAD_MAX = 32,                      /* run-ahead pictures (set_run_ahead) */
+    AHEAD_MAX = 64,                      /* run-ahead pictures (set_run_ahead) */
     QUEUE_MAX = WIN_MAX + AHEAD_MAX + 8,
     JOBS_MAX = 1024                      /* searches per prefetch launch group: 12 pictures x (2 bframes + 1) at bframes 16 = 396 */
 };
@@ -1121,7 +1121,7 @@ void x264cu_slicetype_set_speculation( x264cu_slicetype_t *s, int speculate ) { 
 
 void x264cu_slicetype_set_prefetch_group( x264cu_slicetype_t *s, int pictures )
 {
-    if( s && !s->fed && pictures >= 1 && pictures <= 16 ) s->group = pictures;
+    if( s && !s->fed && pictures >= 1 && pictures <= 32 ) s->group = pictures;
 }
 
 int x264cu_slicetype_set_shard( x264cu_slicetype_t *s, int rank, int world, x264cu_exchange_fn fn, void *user )
