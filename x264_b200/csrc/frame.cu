@@ -19,14 +19,28 @@ lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, 
                uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, int wl, int ll, int fast_ok,
                int skip_x1 = 0, intptr_t src_pitch = 0, intptr_t dst_pitch = 0 )
 {
-    // output domain incl. border: x in [-PAD, wl+PAD) in groups of 4, y in [-PAD, ll+PAD)
+    // output domain incl. border: x in [-PAD, wl+PAD) in groups of 4, y in [-PAD, ll+PAD).  Columns [0, skip_x1) of the picture's
+    // own rows are lowres_wide_kernel's, so the threads are numbered over what is left: the two bands of PAD rows above and below
+    // the picture at full width, then per picture row the PAD/4 groups left of it and the groups from skip_x1 on.
     const int groups_x = ( wl + 2*X264CU_PAD ) / 4;
-    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int oy = blockIdx.y - X264CU_PAD;
-    if( gx >= groups_x ) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int band = 2 * X264CU_PAD * groups_x, left = X264CU_PAD / 4, per_row = groups_x - skip_x1 / 4;
+    int gx, oy;
+    if( t < band )
+    {
+        const int row = t / groups_x;
+        gx = t - row * groups_x;
+        oy = row < X264CU_PAD ? row - X264CU_PAD : ll + row - X264CU_PAD;
+    }
+    else
+    {
+        const int u = t - band;
+        oy = u / per_row;
+        if( oy >= ll ) return;
+        const int k = u - oy * per_row;
+        gx = k < left ? k : k + skip_x1 / 4;
+    }
     const int ox = gx * 4 - X264CU_PAD;
-    // columns [0, skip_x1) of the picture's own rows are lowres_wide_kernel's
-    if( ox >= 0 && ox + 4 <= skip_x1 && oy >= 0 && oy < ll ) return;
     src += (intptr_t)blockIdx.z * src_pitch;
     d0 += (intptr_t)blockIdx.z * dst_pitch; dh += (intptr_t)blockIdx.z * dst_pitch;
     dv += (intptr_t)blockIdx.z * dst_pitch; dc += (intptr_t)blockIdx.z * dst_pitch;
@@ -272,11 +286,11 @@ hpel_words_kernel( const uint8_t *__restrict__ src, intptr_t stride, int width, 
 // All arithmetic runs on packed data: the vertical taps on 16-bit fields, two pixels per 32-bit word (no carries between fields:
 // every partial sum stays within 16 bits once biased by 4112), the horizontal taps with dp4a on the bytes (H) and dp2a on the
 // biased 16-bit vertical sums (C), clamping with the packed min/max instructions (VIMNMX / VIADDMNMX .S16x2).
-//   phase 1  stage rows y0-2 .. y0+34, columns x0-16 .. x0+143 as 16-byte vectors (rows clamped at the picture's edge; tiles that
-//            reach over the left / right edge clamp byte by byte)
+//   phase 1  stage rows y0-2 .. y0+34, columns x0-16 .. x0+143: one TMA load of the box (cp.async.bulk.tensor, completion on an
+//            mbarrier) where it lies inside the picture; the tiles at the picture's edges stage 16-byte vectors with clamped rows
 //   phase 2  a thread walks 8 output rows of one 4-pixel column group down a sliding window of 6 unpacked rows: V plane + the
 //            biased vertical sums (v + 4112) into shared memory (mc.c:176-183)
-//   phase 3  H from the source row, C from the vertical sums (mc.c:184-193); 4 pixels per thread and step
+//   phase 3  H from the source row, C from the vertical sums (mc.c:184-193); 8 pixels per thread and step
 // ------------------------------------------------------------------------------------------------
 constexpr int PT_W = 128, PT_H = 32, PT_ROWS = PT_H + 5, PT_PITCH = 160, PT_VW = 72, PT_THREADS = 192;
 constexpr uint32_t PT_BIAS = 4112u * 0x00010001u;              // 4096 + 16: the rounding of the V plane rides along
@@ -288,42 +302,84 @@ __device__ __forceinline__ int dp4a_u8s8( uint32_t a, int32_t b, int32_t c )
     return d;
 }
 
-__global__ void __launch_bounds__( PT_THREADS )
-hpel_packed_kernel( const uint8_t *__restrict__ src, intptr_t stride, intptr_t pitch, int width, int height,
-                    uint8_t *dh, uint8_t *dv, uint8_t *dc, uint8_t *dsrc_border )
+// bytes 0 and 2 from a, bytes 1 and 3 from b
+__device__ __forceinline__ uint32_t byte_lanes( uint32_t a, uint32_t b )
 {
-    __shared__ __align__( 16 ) uint8_t s_src[PT_ROWS][PT_PITCH];
+    uint32_t d;
+    asm( "lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"( d ) : "r"( a ), "r"( b ), "r"( 0x00ff00ffu ) );
+    return d;
+}
+
+__global__ void __launch_bounds__( PT_THREADS )
+hpel_packed_kernel( const __grid_constant__ CUtensorMap tm_src, const uint8_t *__restrict__ src, intptr_t stride, intptr_t pitch, int width, int height,
+                    uint8_t *dh, uint8_t *dv, uint8_t *dc, uint8_t *dsrc_border, uint32_t less4096 )
+{   // less4096 = -4096 in both 16-bit fields: a kernel parameter, so that VIADDMNMX (one immediate only) reads it from the constant bank
+    __shared__ __align__( 128 ) uint8_t s_src[PT_ROWS][PT_PITCH];
     __shared__ __align__( 16 ) uint32_t s_v[PT_H][PT_VW];          // two biased vertical sums per word
     // a stack of pictures: blockIdx.z selects the plane (all five planes share stride and pitch)
     const intptr_t poff = (intptr_t)blockIdx.z * pitch;
     src += poff; dh += poff; dv += poff; dc += poff;
     if( dsrc_border ) dsrc_border += poff;
     const int x0 = blockIdx.x * PT_W - X264CU_PAD, y0 = blockIdx.y * PT_H - X264CU_PAD;
-    const bool x_inside = x0 - 16 >= 0 && x0 + PT_W + 16 <= width;
-    if( x_inside )
+    // the staged rectangle inside the picture: one TMA load of the whole box (the tensor map's out-of-bounds fill is zero, not
+    // the edge pixel, so the tiles at the picture's edges take the other path)
+    const bool inside = x0 - 16 >= 0 && x0 + PT_W + 16 <= width && y0 - 2 >= 0 && y0 + PT_ROWS - 2 <= height;
+    if( inside )
     {
+        __shared__ __align__( 8 ) uint64_t s_bar;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared( &s_bar );
+        if( threadIdx.x == 0 )
+        {
+            asm volatile( "mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"( bar ) );
+            asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+            asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"( bar ), "r"( PT_ROWS * PT_PITCH ) : "memory" );
+            asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                          ::"r"( (uint32_t)__cvta_generic_to_shared( &s_src[0][0] ) ), "l"( &tm_src ), "r"( bar ),
+                            "r"( x0 - 16 ), "r"( y0 - 2 ), "r"( (int)blockIdx.z ) : "memory" );
+        }
+        __syncthreads();                                           // the barrier's initialisation, for the waiting threads
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "HPEL_WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@p bra HPEL_DONE_%=;\n"
+            "bra HPEL_WAIT_%=;\n"
+            "HPEL_DONE_%=:\n"
+            "}\n" ::"r"( bar ) : "memory" );
+    }
+    else
+    {   // tiles at the picture's edges (rows clamped): 16-byte vectors where they lie inside the row, the edge pixel repeated where
+        // they lie outside, byte by byte where they straddle the edge
         for( int i = threadIdx.x; i < PT_ROWS * ( PT_PITCH / 16 ); i += PT_THREADS )
         {
             const int r = i / ( PT_PITCH / 16 ), c = i - r * ( PT_PITCH / 16 );
-            const int sy = clampi( y0 + r - 2, 0, height - 1 );
-            *(uint4 *)&s_src[r][16 * c] = __ldg( (const uint4 *)( src + (intptr_t)sy * stride + x0 - 16 ) + c );
+            const int sy = clampi( y0 + r - 2, 0, height - 1 ), lo = x0 - 16 + 16 * c;
+            const uint8_t *row = src + (intptr_t)sy * stride;
+            uint4 v;
+            if( lo >= 0 && lo + 16 <= width )
+                v = __ldg( (const uint4 *)( row + lo ) );
+            else if( lo + 16 <= 0 || lo >= width )
+                v.x = v.y = v.z = v.w = 0x01010101u * row[lo < 0 ? 0 : width - 1];
+            else
+            {
+                uint32_t w[4];
+#pragma unroll
+                for( int k = 0; k < 4; k++ )
+                    w[k] = row[clampi( lo + 4*k, 0, width - 1 )] | ( row[clampi( lo + 4*k + 1, 0, width - 1 )] << 8 ) |
+                           ( row[clampi( lo + 4*k + 2, 0, width - 1 )] << 16 ) | ( (uint32_t)row[clampi( lo + 4*k + 3, 0, width - 1 )] << 24 );
+                v = make_uint4( w[0], w[1], w[2], w[3] );
+            }
+            *(uint4 *)&s_src[r][16 * c] = v;
         }
+        __syncthreads();
     }
-    else
-    {
-        for( int i = threadIdx.x; i < PT_ROWS * PT_PITCH; i += PT_THREADS )
-        {
-            const int r = i / PT_PITCH, c = i - r * PT_PITCH;
-            const int sy = clampi( y0 + r - 2, 0, height - 1 ), sx = clampi( x0 + c - 16, 0, width - 1 );
-            s_src[r][c] = src[(intptr_t)sy * stride + sx];
-        }
-    }
-    __syncthreads();
     const int full_w = width + 2 * X264CU_PAD, full_h = height + 2 * X264CU_PAD;
-    // ---- phase 2: word column wc covers x0-4+4wc .. +3 (wc = 0 .. 33), rows 8*chunk .. 8*chunk+7
-    if( threadIdx.x < 34 * ( PT_H / 8 ) )
+    // ---- phase 2: word column wc covers x0-4+4wc .. +3 (wc = 0 .. 33).  Warps 0-3: the tile's own 32 columns, warp = rows
+    // 8*warp .. +7 down a sliding window; warps 4-5: the two columns either side that only the C plane's taps read, one row each
+    if( threadIdx.x < 128 )
     {
-        const int chunk = threadIdx.x / 34, wc = threadIdx.x - chunk * 34;
+        const int chunk = threadIdx.x >> 5, wc = 1 + ( threadIdx.x & 31 );
         const int r0 = chunk * 8;
         uint32_t lo[6], hi[6];                                       // the window: rows r .. r+5, pixels (0,1) and (2,3) as 16-bit fields
 #pragma unroll
@@ -333,7 +389,9 @@ hpel_packed_kernel( const uint8_t *__restrict__ src, intptr_t stride, intptr_t p
             lo[k + 1] = __byte_perm( w, 0, 0x4140 ); hi[k + 1] = __byte_perm( w, 0, 0x4342 );
         }
         const int ox = x0 + 4 * ( wc - 1 );
-        const bool store_v = wc >= 1 && wc <= PT_W / 4 && ox + X264CU_PAD < full_w;
+        const int rows_v = ox + X264CU_PAD < full_w ? full_h - X264CU_PAD - ( y0 + r0 ) : 0;      // rows of this chunk inside the domain
+        uint8_t *pv = dv + (intptr_t)( y0 + r0 ) * stride + ox;
+        asm( "" : "+l"( pv ) );                                      // one 64-bit row pointer carried down the rows
 #pragma unroll
         for( int j = 0; j < 8; j++ )
         {
@@ -344,52 +402,103 @@ hpel_packed_kernel( const uint8_t *__restrict__ src, intptr_t stride, intptr_t p
             // (a + f) + 20 (c + d) - 5 (b + e), both fields at once
             const uint32_t vl = ( lo[2] + lo[3] ) * 20u + ( lo[0] + lo[5] + PT_BIAS ) - ( lo[1] + lo[4] ) * 5u;
             const uint32_t vh = ( hi[2] + hi[3] ) * 20u + ( hi[0] + hi[5] + PT_BIAS ) - ( hi[1] + hi[4] ) * 5u;
-            const int r = r0 + j;
-            *(uint2 *)&s_v[r][2 * wc] = make_uint2( vl, vh );
-            const int oy = y0 + r;
-            if( store_v && oy + X264CU_PAD < full_h )
-            {   // ((v + 16) >> 5) + 128 per field, then clamp( . - 128, 0, 255 )
-                const uint32_t pl = __viaddmin_s16x2_relu( ( vl >> 5 ) & 0x07ff07ffu, 0xff80ff80u, 0x00ff00ffu );
-                const uint32_t ph = __viaddmin_s16x2_relu( ( vh >> 5 ) & 0x07ff07ffu, 0xff80ff80u, 0x00ff00ffu );
-                *(uint32_t *)( dv + (intptr_t)oy * stride + ox ) = __byte_perm( pl, ph, 0x6420 );
-            }
+            *(uint2 *)&s_v[r0 + j][2 * wc] = make_uint2( vl, vh );
+            // clamp( v + 16, 0, 8191 ) per field (the bias less 4096); times 8, the result >> 5 is the field's high byte
+            const uint32_t pl = __viaddmin_s16x2_relu( vl, less4096, 0x1fff1fffu ) << 3;
+            const uint32_t ph = __viaddmin_s16x2_relu( vh, less4096, 0x1fff1fffu ) << 3;
+            if( j < rows_v )
+                *(uint32_t *)pv = __byte_perm( pl, ph, 0x7531 );
+            pv += stride;
         }
     }
-    __syncthreads();
-    // ---- phase 3
-    for( int i = threadIdx.x; i < PT_H * ( PT_W / 4 ); i += PT_THREADS )
+    else
     {
-        const int r = i >> 5, g = i & 31;
-        const int ox = x0 + 4 * g, oy = y0 + r;
-        if( ox + X264CU_PAD >= full_w || oy + X264CU_PAD >= full_h ) continue;
-        // H: taps (1,-5,20,20,-5,1) over bytes k+2 .. k+7 of the 12 bytes x-4 .. x+7
-        const uint32_t *sw = (const uint32_t *)&s_src[r + 2][12 + 4 * g];
-        const uint32_t s0 = sw[0], s1 = sw[1], s2 = sw[2];
+        const int e = threadIdx.x - 128, r = e & 31, wc = e < 32 ? 0 : 33;
+        uint32_t vl = PT_BIAS, vh = PT_BIAS;
+#pragma unroll
+        for( int k = 0; k < 6; k++ )
+        {
+            const uint32_t w = *(const uint32_t *)&s_src[r + k][12 + 4 * wc];
+            const uint32_t tap = k == 0 || k == 5 ? 1u : k == 1 || k == 4 ? (uint32_t)-5 : 20u;
+            vl += __byte_perm( w, 0, 0x4140 ) * tap; vh += __byte_perm( w, 0, 0x4342 ) * tap;
+        }
+        *(uint2 *)&s_v[r][2 * wc] = make_uint2( vl, vh );
+    }
+    __syncthreads();
+    // ---- phase 3: 8 pixels per thread and step.  H from the source row, C from the vertical sums
+    // (192 threads = 12 rows of 16 groups: a thread keeps its group of columns and steps 12 rows down)
+    const int g = threadIdx.x & 15, ox = x0 + 8 * g;
+    const bool second = ox + 4 + X264CU_PAD < full_w;               // the domain's width is a multiple of 4, not of 8
+    if( ox + X264CU_PAD >= full_w ) return;
+    const bool col_out = ox < 0 || ox >= width, col_out2 = ox < 0 || ox + 4 >= width;
+    // only the tiles that reach outside the picture have source border to write
+    const bool border_tile = dsrc_border && ( x0 < 0 || x0 + PT_W > width || y0 < 0 || y0 + PT_H > height );
+    const int rb = threadIdx.x >> 4;
+    const intptr_t o0 = (intptr_t)( y0 + rb ) * stride + ox, step = (intptr_t)( PT_THREADS / 16 ) * stride;
+    uint8_t *ph = dh + o0, *pc = dc + o0;
+#pragma unroll
+    for( int r = rb; r < PT_H; r += PT_THREADS / 16, ph += step, pc += step )
+    {
+        const int oy = y0 + r;
+        if( oy + X264CU_PAD >= full_h ) break;
+        // H: taps (1,-5,20,20,-5,1); A[k] = the four bytes from column x+k-2 on, out of the 16 bytes x-4 .. x+11
+        const uint32_t *sw = (const uint32_t *)&s_src[r + 2][12 + 8 * g];
+        const uint32_t w0 = sw[0], w3 = sw[3];
+        const uint2 w12 = *(const uint2 *)( sw + 1 );
+        const uint32_t w1 = w12.x, w2 = w12.y;
+        uint32_t A[12];
+        A[0] = __funnelshift_r( w0, w1, 16 ); A[1] = __funnelshift_r( w0, w1, 24 ); A[2] = w1; A[3] = __funnelshift_r( w1, w2, 8 );
+        A[4] = __funnelshift_r( w1, w2, 16 ); A[5] = __funnelshift_r( w1, w2, 24 ); A[6] = w2; A[7] = __funnelshift_r( w2, w3, 8 );
+        A[8] = __funnelshift_r( w2, w3, 16 ); A[9] = __funnelshift_r( w2, w3, 24 ); A[10] = w3; A[11] = w3 >> 8;
         const int T0123 = 0x1414FB01, T45 = 0x000001FB;
-        const int h0 = dp4a_u8s8( __funnelshift_r( s0, s1, 16 ), T0123, dp4a_u8s8( __funnelshift_r( s1, s2, 16 ), T45, 16 ) );
-        const int h1 = dp4a_u8s8( __funnelshift_r( s0, s1, 24 ), T0123, dp4a_u8s8( __funnelshift_r( s1, s2, 24 ), T45, 16 ) );
-        const int h2 = dp4a_u8s8( s1, T0123, dp4a_u8s8( s2, T45, 16 ) );
-        const int h3 = dp4a_u8s8( __funnelshift_r( s1, s2, 8 ), T0123, dp4a_u8s8( s2 >> 8, T45, 16 ) );
-        uint32_t h01 = __vimin_s16x2_relu( __byte_perm( h0, h1, 0x5410 ), 0x1fff1fffu );       // clamp( h + 16, 0, 8191 ), then >> 5
-        uint32_t h23 = __vimin_s16x2_relu( __byte_perm( h2, h3, 0x5410 ), 0x1fff1fffu );
-        h01 = ( h01 >> 5 ) & 0x00ff00ffu; h23 = ( h23 >> 5 ) & 0x00ff00ffu;
-        // C: the same taps over the biased vertical sums of columns x-2 .. x+6: fields 2 .. 10 of the twelve in vw[0..5]
-        const uint2 *vp = (const uint2 *)&s_v[r][2 * g];
-        const uint2 va = vp[0], vb = vp[1], vc = vp[2];
-        const uint32_t f12 = __funnelshift_r( va.y, vb.x, 16 ), f23 = __funnelshift_r( vb.x, vb.y, 16 ),
-                       f34 = __funnelshift_r( vb.y, vc.x, 16 ), f45 = __funnelshift_r( vc.x, vc.y, 16 );
+        int hv[8];
+#pragma unroll
+        for( int k = 0; k < 8; k++ ) hv[k] = dp4a_u8s8( A[k], T0123, dp4a_u8s8( A[k + 4], T45, 16 ) );
+        // C: the same taps over the biased vertical sums; q[j] = the fields of columns x-4+2j, x-3+2j
+        const uint4 qa = *(const uint4 *)&s_v[r][4 * g], qb = *(const uint4 *)&s_v[r][4 * g + 4];
+        const uint32_t q1 = qa.y, q2 = qa.z, q3 = qa.w, q4 = qb.x, q5 = qb.y, q6 = qb.z, q7 = qb.w;
+        const uint32_t f12 = __funnelshift_r( q1, q2, 16 ), f23 = __funnelshift_r( q2, q3, 16 ), f34 = __funnelshift_r( q3, q4, 16 ),
+                       f45 = __funnelshift_r( q4, q5, 16 ), f56 = __funnelshift_r( q5, q6, 16 ), f67 = __funnelshift_r( q6, q7, 16 );
         const int U01 = 0x0000FB01, U23 = 0x00001414, U45 = 0x000001FB, C0 = 512 - 32 * 4112;
-        const int c0 = __dp2a_lo( (int)va.y, U01, __dp2a_lo( (int)vb.x, U23, __dp2a_lo( (int)vb.y, U45, C0 ) ) );
-        const int c1 = __dp2a_lo( (int)f12, U01, __dp2a_lo( (int)f23, U23, __dp2a_lo( (int)f34, U45, C0 ) ) );
-        const int c2 = __dp2a_lo( (int)vb.x, U01, __dp2a_lo( (int)vb.y, U23, __dp2a_lo( (int)vc.x, U45, C0 ) ) );
-        const int c3 = __dp2a_lo( (int)f23, U01, __dp2a_lo( (int)f34, U23, __dp2a_lo( (int)f45, U45, C0 ) ) );
-        const uint32_t c01 = __vimin_s16x2_relu( __byte_perm( c0 >> 10, c1 >> 10, 0x5410 ), 0x00ff00ffu );
-        const uint32_t c23 = __vimin_s16x2_relu( __byte_perm( c2 >> 10, c3 >> 10, 0x5410 ), 0x00ff00ffu );
-        const intptr_t o = (intptr_t)oy * stride + ox;
-        *(uint32_t *)( dh + o ) = __byte_perm( h01, h23, 0x6420 );
-        *(uint32_t *)( dc + o ) = __byte_perm( c01, c23, 0x6420 );
-        if( dsrc_border && ( ox < 0 || ox >= width || oy < 0 || oy >= height ) )
-            *(uint32_t *)( dsrc_border + o ) = s1;
+        int cv[8];
+        cv[0] = __dp2a_lo( (int)q1, U01, __dp2a_lo( (int)q2, U23, __dp2a_lo( (int)q3, U45, C0 ) ) );
+        cv[1] = __dp2a_lo( (int)f12, U01, __dp2a_lo( (int)f23, U23, __dp2a_lo( (int)f34, U45, C0 ) ) );
+        cv[2] = __dp2a_lo( (int)q2, U01, __dp2a_lo( (int)q3, U23, __dp2a_lo( (int)q4, U45, C0 ) ) );
+        cv[3] = __dp2a_lo( (int)f23, U01, __dp2a_lo( (int)f34, U23, __dp2a_lo( (int)f45, U45, C0 ) ) );
+        cv[4] = __dp2a_lo( (int)q3, U01, __dp2a_lo( (int)q4, U23, __dp2a_lo( (int)q5, U45, C0 ) ) );
+        cv[5] = __dp2a_lo( (int)f34, U01, __dp2a_lo( (int)f45, U23, __dp2a_lo( (int)f56, U45, C0 ) ) );
+        cv[6] = __dp2a_lo( (int)q4, U01, __dp2a_lo( (int)q5, U23, __dp2a_lo( (int)q6, U45, C0 ) ) );
+        cv[7] = __dp2a_lo( (int)f45, U01, __dp2a_lo( (int)f56, U23, __dp2a_lo( (int)f67, U45, C0 ) ) );
+        // four results to four bytes: pixels (0,2) and (1,3) share a word of 16-bit fields, so that the clamped fields shift straight
+        // into their byte lanes.  H: clamp( h + 16, 0, 8191 ) >> 5.  C: bytes 1-2 of c + 512 are c >> 8; clamp( ., 0, 1023 ) >> 2
+        uint32_t ho[2], co[2];
+#pragma unroll
+        for( int m = 0; m < 2; m++ )
+        {
+            const uint32_t h02 = __vimin_s16x2_relu( __byte_perm( hv[4*m], hv[4*m + 2], 0x5410 ), 0x1fff1fffu );
+            const uint32_t h13 = __vimin_s16x2_relu( __byte_perm( hv[4*m + 1], hv[4*m + 3], 0x5410 ), 0x1fff1fffu );
+            ho[m] = byte_lanes( h02 >> 5, h13 << 3 );
+            const uint32_t c02 = __vimin_s16x2_relu( __byte_perm( cv[4*m], cv[4*m + 2], 0x6521 ), 0x03ff03ffu );
+            const uint32_t c13 = __vimin_s16x2_relu( __byte_perm( cv[4*m + 1], cv[4*m + 3], 0x6521 ), 0x03ff03ffu );
+            co[m] = byte_lanes( c02 >> 2, c13 << 6 );
+        }
+        if( second )
+        {
+            *(uint2 *)ph = make_uint2( ho[0], ho[1] );
+            *(uint2 *)pc = make_uint2( co[0], co[1] );
+        }
+        else
+        {
+            *(uint32_t *)ph = ho[0];
+            *(uint32_t *)pc = co[0];
+        }
+        if( border_tile )
+        {
+            const bool row_out = oy < 0 || oy >= height;
+            uint8_t *ps = dsrc_border + (intptr_t)oy * stride + ox;
+            if( row_out || col_out ) *(uint32_t *)ps = w1;
+            if( second && ( row_out || col_out2 ) ) *(uint32_t *)( ps + 4 ) = w2;
+        }
     }
 }
 
@@ -423,9 +532,11 @@ static int lowres_launch( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d
                                                       lowres_stride, lowres_pitch, groups, ll );
         CU_LAUNCH_CHECK( ctx );
     }
-    dim3 block( 256 ), grid( ( ( wl + 2*X264CU_PAD ) / 4 + 255 ) / 256, ll + 2*X264CU_PAD, n_pictures );
+    const int skip = 8 * max( groups, 0 ), groups_x = ( wl + 2*X264CU_PAD ) / 4;
+    const long border_threads = 2L * X264CU_PAD * groups_x + (long)ll * ( groups_x - skip / 4 );
+    dim3 block( 256 ), grid( (unsigned)( ( border_threads + 255 ) / 256 ), 1, n_pictures );
     lowres_kernel<<<grid, block, 0, stream>>>( d_luma, luma_stride, width, height, d_lowres[0], d_lowres[1],
-                                               d_lowres[2], d_lowres[3], lowres_stride, wl, ll, aligned, 8 * max( groups, 0 ), luma_pitch, lowres_pitch );
+                                               d_lowres[2], d_lowres[3], lowres_stride, wl, ll, aligned, skip, luma_pitch, lowres_pitch );
     CU_LAUNCH_CHECK( ctx );
     return 0;
 }
@@ -454,8 +565,17 @@ static int hpel_launch( x264cu_ctx_t *ctx, uint8_t *d_src, intptr_t stride, intp
     const uintptr_t all = (uintptr_t)d_src | (uintptr_t)d_h | (uintptr_t)d_v | (uintptr_t)d_c | (uintptr_t)stride | (uintptr_t)pitch;
     if( !( all & 15 ) && !( width & 3 ) && width >= 8 )
     {
+        // the source pictures as a 3D tensor (column, row, picture) for the interior tiles' TMA loads
+        CUtensorMap tm;
+        cuuint64_t dims[3] = { (cuuint64_t)width, (cuuint64_t)height, (cuuint64_t)n_planes };
+        cuuint64_t strides[2] = { (cuuint64_t)stride, (cuuint64_t)( n_planes > 1 ? pitch : stride * height ) };
+        cuuint32_t box[3] = { PT_PITCH, PT_ROWS, 1 }, estr[3] = { 1, 1, 1 };
+        CUresult r = ctx->encode_tiled( &tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)d_src, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+        if( r != CUDA_SUCCESS ) return x264cu_fail( ctx, "hpel_filter: cuTensorMapEncodeTiled failed (%d)", (int)r );
         dim3 grid( ( width + 2*X264CU_PAD + PT_W - 1 ) / PT_W, ( height + 2*X264CU_PAD + PT_H - 1 ) / PT_H, n_planes );
-        hpel_packed_kernel<<<grid, PT_THREADS, 0, ctx->stream>>>( d_src, stride, pitch, width, height, d_h, d_v, d_c, expand_src ? d_src : nullptr );
+        hpel_packed_kernel<<<grid, PT_THREADS, 0, ctx->stream>>>( tm, d_src, stride, pitch, width, height, d_h, d_v, d_c, expand_src ? d_src : nullptr, 0xf000f000u );
         CU_LAUNCH_CHECK( ctx );
         return 0;
     }
