@@ -282,17 +282,21 @@ hpel_words_kernel( const uint8_t *__restrict__ src, intptr_t stride, int width, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// hpel, packed path (16-byte aligned planes, width % 4 == 0): CTA = 128 x 32 output tile of the padded domain, 192 threads.
+// hpel, packed path (16-byte aligned planes, width % 4 == 0): CTA = 128 x 32 output tile of the padded domain, 128 threads.
 // All arithmetic runs on packed data: the vertical taps on 16-bit fields, two pixels per 32-bit word (no carries between fields:
 // every partial sum stays within 16 bits once biased by 4112), the horizontal taps with dp4a on the bytes (H) and dp2a on the
 // biased 16-bit vertical sums (C), clamping with the packed min/max instructions (VIMNMX / VIADDMNMX .S16x2).
 //   phase 1  stage rows y0-2 .. y0+34, columns x0-16 .. x0+143: one TMA load of the box (cp.async.bulk.tensor, completion on an
 //            mbarrier) where it lies inside the picture; the tiles at the picture's edges stage 16-byte vectors with clamped rows
-//   phase 2  a thread walks 8 output rows of one 4-pixel column group down a sliding window of 6 unpacked rows: V plane + the
+//   phase 2  a thread walks 16 output rows of one 4-pixel column group down a sliding window of 6 unpacked rows: V plane + the
 //            biased vertical sums (v + 4112) into shared memory (mc.c:176-183)
 //   phase 3  H from the source row, C from the vertical sums (mc.c:184-193); 8 pixels per thread and step
 // ------------------------------------------------------------------------------------------------
-constexpr int PT_W = 128, PT_H = 32, PT_ROWS = PT_H + 5, PT_PITCH = 160, PT_VW = 72, PT_THREADS = 192;
+constexpr int PT_W = 128, PT_H = 32, PT_ROWS = PT_H + 5, PT_PITCH = 160, PT_VW = 72, PT_THREADS = 128;
+#ifndef HPEL_CHUNK
+#define HPEL_CHUNK 16
+#endif
+constexpr int PT_CHUNK = HPEL_CHUNK, PT_MAIN = 32 * ( PT_H / PT_CHUNK );   // rows per phase-2 walk; the threads walking
 constexpr uint32_t PT_BIAS = 4112u * 0x00010001u;              // 4096 + 16: the rounding of the V plane rides along
 
 __device__ __forceinline__ int dp4a_u8s8( uint32_t a, int32_t b, int32_t c )
@@ -375,12 +379,13 @@ hpel_packed_kernel( const __grid_constant__ CUtensorMap tm_src, const uint8_t *_
         __syncthreads();
     }
     const int full_w = width + 2 * X264CU_PAD, full_h = height + 2 * X264CU_PAD;
-    // ---- phase 2: word column wc covers x0-4+4wc .. +3 (wc = 0 .. 33).  Warps 0-3: the tile's own 32 columns, warp = rows
-    // 8*warp .. +7 down a sliding window; warps 4-5: the two columns either side that only the C plane's taps read, one row each
-    if( threadIdx.x < 128 )
+    // ---- phase 2: word column wc covers x0-4+4wc .. +3 (wc = 0 .. 33).  Warps 0-1: the tile's own 32 columns, warp = rows
+    // 16*warp .. +15 down a sliding window (the longer the walk, the fewer window refills); warps 2-3: the two columns either side
+    // that only the C plane's taps read, one row each
+    if( threadIdx.x < PT_MAIN )
     {
         const int chunk = threadIdx.x >> 5, wc = 1 + ( threadIdx.x & 31 );
-        const int r0 = chunk * 8;
+        const int r0 = chunk * PT_CHUNK;
         uint32_t lo[6], hi[6];                                       // the window: rows r .. r+5, pixels (0,1) and (2,3) as 16-bit fields
 #pragma unroll
         for( int k = 0; k < 5; k++ )
@@ -393,7 +398,7 @@ hpel_packed_kernel( const __grid_constant__ CUtensorMap tm_src, const uint8_t *_
         uint8_t *pv = dv + (intptr_t)( y0 + r0 ) * stride + ox;
         asm( "" : "+l"( pv ) );                                      // one 64-bit row pointer carried down the rows
 #pragma unroll
-        for( int j = 0; j < 8; j++ )
+        for( int j = 0; j < PT_CHUNK; j++ )
         {
 #pragma unroll
             for( int k = 0; k < 5; k++ ) { lo[k] = lo[k + 1]; hi[k] = hi[k + 1]; }
@@ -411,9 +416,9 @@ hpel_packed_kernel( const __grid_constant__ CUtensorMap tm_src, const uint8_t *_
             pv += stride;
         }
     }
-    else
+    else if( threadIdx.x < PT_MAIN + 64 )
     {
-        const int e = threadIdx.x - 128, r = e & 31, wc = e < 32 ? 0 : 33;
+        const int e = threadIdx.x - PT_MAIN, r = e & 31, wc = e < 32 ? 0 : 33;
         uint32_t vl = PT_BIAS, vh = PT_BIAS;
 #pragma unroll
         for( int k = 0; k < 6; k++ )
@@ -426,7 +431,7 @@ hpel_packed_kernel( const __grid_constant__ CUtensorMap tm_src, const uint8_t *_
     }
     __syncthreads();
     // ---- phase 3: 8 pixels per thread and step.  H from the source row, C from the vertical sums
-    // (192 threads = 12 rows of 16 groups: a thread keeps its group of columns and steps 12 rows down)
+    // (128 threads = 8 rows of 16 groups: a thread keeps its group of columns and steps 8 rows down)
     const int g = threadIdx.x & 15, ox = x0 + 8 * g;
     const bool second = ox + 4 + X264CU_PAD < full_w;               // the domain's width is a multiple of 4, not of 8
     if( ox + X264CU_PAD >= full_w ) return;

@@ -3,6 +3,7 @@
 #include "ctx.h"
 #include "me_dev.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -31,15 +32,72 @@ __device__ __noinline__ void run_job( const MeShared &g, const MeJob &j, int lan
     r.mv[0] = (int16_t)mvx; r.mv[1] = (int16_t)mvy; r.cost = cost; r.cost_mv = cost_mv; r.halfpel_thresh = thresh;
 }
 
+// ---- the order the jobs are walked in: by partition size ------------------------------------------------------------------
+// The search of each partition size is its own instantiation of the whole algorithm (run_job<BW,BH>: ~12 000 SASS instructions
+// each, 1.3 MB for the seven).  In the caller's order (macroblock by macroblock: 16x16, 8x8, 16x8 ... interleaved) the warps
+// resident on an SM run seven different instruction streams at once and stall on instruction fetch (ncu, round 2: 46 of the 51
+// cycles between two issues of a warp were "no instruction").  A stable counting sort by i_pixel in chunks of ME_ORDER_CHUNK jobs
+// makes the CTAs in flight share one instantiation; spatial order survives within a size, so the reference windows still meet in L2.
+constexpr int ME_ORDER_CHUNK = 1024, ME_CLASSES = 8;
+
+__global__ void __launch_bounds__( 256 )
+me_order_count_kernel( const char *__restrict__ jobs, int job_bytes, int n, int *__restrict__ counts )
+{
+    __shared__ int hist[ME_CLASSES];
+    if( threadIdx.x < ME_CLASSES ) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * ME_ORDER_CHUNK;
+    for( int i = base + threadIdx.x; i < min( base + ME_ORDER_CHUNK, n ); i += blockDim.x )
+        atomicAdd( &hist[min( (unsigned)*(const int32_t *)( jobs + (size_t)i * job_bytes ), (unsigned)ME_CLASSES - 1 )], 1 );
+    __syncthreads();
+    if( threadIdx.x < ME_CLASSES ) counts[blockIdx.x * ME_CLASSES + threadIdx.x] = hist[threadIdx.x];
+}
+
+// counts[chunk][class] -> where that chunk's jobs of that class start in the order (classes one after the other)
+__global__ void __launch_bounds__( 32 )
+me_order_scan_kernel( int *__restrict__ counts, int chunks )
+{
+    __shared__ int total[ME_CLASSES];
+    const int c = threadIdx.x;
+    if( c < ME_CLASSES )
+    {
+        int sum = 0;
+        for( int b = 0; b < chunks; b++ ) { const int v = counts[b * ME_CLASSES + c]; counts[b * ME_CLASSES + c] = sum; sum += v; }
+        total[c] = sum;
+    }
+    __syncthreads();
+    if( c < ME_CLASSES )
+    {
+        int base = 0;
+        for( int k = 0; k < c; k++ ) base += total[k];
+        for( int b = 0; b < chunks; b++ ) counts[b * ME_CLASSES + c] += base;
+    }
+}
+
+__global__ void __launch_bounds__( 256 )
+me_order_scatter_kernel( const char *__restrict__ jobs, int job_bytes, int n, const int *__restrict__ starts, int *__restrict__ order )
+{
+    __shared__ int cursor[ME_CLASSES];
+    if( threadIdx.x < ME_CLASSES ) cursor[threadIdx.x] = starts[blockIdx.x * ME_CLASSES + threadIdx.x];
+    __syncthreads();
+    const int base = blockIdx.x * ME_ORDER_CHUNK;
+    for( int i = base + threadIdx.x; i < min( base + ME_ORDER_CHUNK, n ); i += blockDim.x )
+        order[atomicAdd( &cursor[min( (unsigned)*(const int32_t *)( jobs + (size_t)i * job_bytes ), (unsigned)ME_CLASSES - 1 )], 1 )] = i;
+}
+
+#ifndef ME_MIN_CTAS
+#define ME_MIN_CTAS 1
+#endif
 template <bool EXH>
-__global__ void __launch_bounds__( 128 )
-me_search_kernel( MeShared g0, MeFrameDev fd, const char *__restrict__ jobs, int n, MeResult *__restrict__ results )
+__global__ void __launch_bounds__( 128, ME_MIN_CTAS )
+me_search_kernel( MeShared g0, MeFrameDev fd, const char *__restrict__ jobs, int n, MeResult *__restrict__ results, const int *__restrict__ order )
 {
     const int lane = threadIdx.x & 31;
     const int w0 = ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5, nw = ( gridDim.x * blockDim.x ) >> 5;
     uint2 *tesa_list = g0.tesa_list ? g0.tesa_list + (size_t)w0 * g0.tesa_cap : nullptr;
-    for( int w = w0; w < n; w += nw )            // one job per warp, except TESA whose warps (and candidate lists) are bounded
+    for( int wi = w0; wi < n; wi += nw )         // one job per warp, except TESA whose warps (and candidate lists) are bounded
     {
+        const int w = order ? order[wi] : wi;
         const char *jp = jobs + (size_t)w * fd.job_bytes;
         MeJob j = *(const MeJob *)jp;            // every lane holds the (uniform) job
         MeShared g = g0;
@@ -221,10 +279,25 @@ static int me_launch( x264cu_ctx_t *ctx, const x264cu_me_params_t *p, MeShared &
         g.tesa_list = (uint2 *)x264cu_scratch( ctx, 9, (size_t)blocks * per_block );
         if( !g.tesa_list ) return -1;
     }
+    int *d_order = nullptr;
+    bool by_size = n >= 4 * ME_ORDER_CHUNK;
+#ifdef X264CU_TUNING
+    if( getenv( "X264CU_ME_CALLER_ORDER" ) ) by_size = false;
+#endif
+    if( by_size )
+    {   // walk the jobs by partition size (see me_order_count_kernel)
+        const int chunks = ( n + ME_ORDER_CHUNK - 1 ) / ME_ORDER_CHUNK;
+        int *d_counts = (int *)x264cu_scratch( ctx, 15, ( (size_t)chunks * ME_CLASSES + n ) * sizeof(int) );
+        if( !d_counts ) return -1;
+        d_order = d_counts + (size_t)chunks * ME_CLASSES;
+        me_order_count_kernel<<<chunks, 256, 0, ctx->stream>>>( (const char *)d_jobs, fd.job_bytes, n, d_counts );
+        me_order_scan_kernel<<<1, 32, 0, ctx->stream>>>( d_counts, chunks );
+        me_order_scatter_kernel<<<chunks, 256, 0, ctx->stream>>>( (const char *)d_jobs, fd.job_bytes, n, d_counts, d_order );
+    }
     if( p->me_method >= X264CU_ME_ESA )
-        me_search_kernel<true><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, fd, (const char *)d_jobs, n, (MeResult *)d_results );
+        me_search_kernel<true><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, fd, (const char *)d_jobs, n, (MeResult *)d_results, d_order );
     else
-        me_search_kernel<false><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, fd, (const char *)d_jobs, n, (MeResult *)d_results );
+        me_search_kernel<false><<<blocks, warps_per_block * 32, 0, ctx->stream>>>( g, fd, (const char *)d_jobs, n, (MeResult *)d_results, d_order );
     CU_LAUNCH_CHECK( ctx );
     return 0;
 }
