@@ -85,8 +85,10 @@ me_order_scatter_kernel( const char *__restrict__ jobs, int job_bytes, int n, co
         order[atomicAdd( &cursor[min( (unsigned)*(const int32_t *)( jobs + (size_t)i * job_bytes ), (unsigned)ME_CLASSES - 1 )], 1 )] = i;
 }
 
+// 64 registers, 8 CTAs (32 warps) per SM: measured on the 4K preset-slower stream (profiles/README.md) 36.6 M searches/s with the
+// compiler's own choice (168 registers), 39.7 / 41.4 / 42.5 / 43.6 M at 4 / 5 / 6 / 8 CTAs per SM; no spills at 64
 #ifndef ME_MIN_CTAS
-#define ME_MIN_CTAS 1
+#define ME_MIN_CTAS 8
 #endif
 template <bool EXH>
 __global__ void __launch_bounds__( 128, ME_MIN_CTAS )

@@ -924,6 +924,12 @@ static int speculate_group( x264cu_slicetype_t *s, int n, const int *fenc, const
     int *t = malloc( 6 * TRIPLES_MAX * sizeof( int ) ), m = 0;
     if( !t ) return -1;
     int *tb = t, *t0 = t + TRIPLES_MAX, *t1 = t + 2 * TRIPLES_MAX, *td0 = t + 3 * TRIPLES_MAX, *td1 = t + 4 * TRIPLES_MAX, *own = t + 5 * TRIPLES_MAX;
+    /* With a B pyramid the trellis (slicetype_path_cost, slicetype.c:1310-1321) and MB-tree (:1143-1160) price a mini-GOP Y..X longer
+     * than two as: its middle picture against (Y, X), the pictures of each half against (Y, middle) / (middle, X).  So of the spans
+     * longer than a half can be, (bframes+1) - (bframes+1)/2, only the middle picture's triple is ever asked for: 61 instead of 150
+     * triples per picture at bframes 16.  (Anything else is still answered, on demand.) */
+    const int pyramid_paths = s->p.b_pyramid && s->p.b_adapt == 2 && s->p.la.bframes > 1 && !s->p.la.vbv;
+    const int half_span = ( s->p.la.bframes + 1 ) - ( s->p.la.bframes + 1 ) / 2;
     for( int i = 0; i < n; i++ )
     {
         if( list[i] )
@@ -931,6 +937,8 @@ static int speculate_group( x264cu_slicetype_t *s, int n, const int *fenc, const
         const int x_no = number[i], d = dist[i];
         for( int k = 0; k < d && m < TRIPLES_MAX; k++ )
         {   /* k = 0: the P triple; k > 0: the B picture k pictures before X */
+            if( k && pyramid_paths && d > half_span && k != d - d / 2 )
+                continue;
             const int b_slot = k ? x264cu_slicetype_slot_of( s, x_no - k ) : fenc[i];
             if( b_slot < 0 )
                 continue;
