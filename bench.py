@@ -330,6 +330,7 @@ LA_ST = dict(keyint_max=250, keyint_min=25, scenecut_threshold=40, b_adapt=1, b_
 LA_REF_OPTS = b"weightp=0:no-psy=1:aq-mode=0:bframes=3:rc-lookahead=40"          # the same configuration, reference spelling
 LA_REF_OPTS_W = b"weightp=2:aq-mode=0:bframes=3:rc-lookahead=40"                  # --weightp 1: preset medium's own weightp / psy
 # algorithmic bytes of one lowres motion search at WxH: fenc lowres + 4 reference lowres planes + 8 B/MB out
+LA_WARP_INSTR_PER_MB_SEARCH = 1334          # ncu --set full of search_kernel<8> (84-search launch): 3 631 M warp instructions / 2.72 M macroblock searches
 LA_SEARCH_BYTES = LA_W * LA_H // 4 + LA_W * LA_H + 8 * ((LA_W + 15) // 16) * ((LA_H + 15) // 16)
 
 
@@ -705,7 +706,18 @@ def run_lookahead_b200(args, rank, world, local, dist):
                      "share_of_step": live_ms / max(ms, 1e-9),
                      "ms_per_launch_alone_%d_searches" % n_jobs: search_ms, "ms_per_launch_alone_%d_searches" % len(jobs4): search4_ms,
                      "note": "dependency-bound wavefront (508 pipeline steps at 4K), not a streaming kernel: the planes of the ~13 "
-                             "pictures a launch touches stay in L2 (traffic << algorithmic bytes); see DESIGN.md"},
+                             "pictures a launch touches stay in L2 (traffic << algorithmic bytes); see DESIGN.md and issue_model",
+                     # what actually bounds this kernel: warp-instruction issue.  1 334 warp instructions per macroblock search (ncu,
+                     # profiles/r01b_search_kernel_ncu_full.txt) against the SMs' issue slots (4 schedulers per SM, one per clock)
+                     "issue_model": (lambda mbs, clk: {
+                         "warp_instructions_per_mb_search": LA_WARP_INSTR_PER_MB_SEARCH, "mb_searches_in_timed_region": live_searches * mbs,
+                         "issue_slots_per_s": info["sm_count"] * 4 * clk * 1e6,
+                         "min_ms_at_full_issue": live_searches * mbs * LA_WARP_INSTR_PER_MB_SEARCH / (info["sm_count"] * 4 * clk * 1e6) * 1e3,
+                         "timed_region_ms": ms,
+                         "frac_of_issue_peak": live_searches * mbs * LA_WARP_INSTR_PER_MB_SEARCH / (info["sm_count"] * 4 * clk * 1e6) / (ms * 1e-3),
+                         "note": "the whole step's wall time against the search kernels' instruction count alone (the other kernels' "
+                                 "instructions are not counted): ncu's own figure for the kernel in isolation is 43 % issue slots busy"})(
+                         ((LA_W // 2 + 7) // 8) * ((LA_H // 2 + 7) // 8), float((clocks or {}).get("sm_mhz") or 1965.0))},
         "wall_s": wall, "sm_count": info["sm_count"],
     }
     if sharded is not None:
