@@ -8,6 +8,7 @@
  *   ./lookahead_host --ranks N WIDTH HEIGHT FRAMES [file]            ONE stream sharded over N GPUs: N processes (fork), one per
  *                                                                    GPU, the all-gathers done by x264cu_exchange_nccl (NCCL over
  *                                                                    NVLink); every rank takes the same decisions, rank 0 prints
+ *   options before WIDTH: --bframes B --b-adapt A --rc-lookahead L   (defaults 3 / 1 / 20; BASELINE configs[3] is 16 / 2 / 250)
  *
  * Raw I420 in (Y, Cb, Cr planes per picture, as x264's raw demuxer reads them, input/raw.c:43-170): adaptive quantisation
  * (aq-mode 1), lowres planes, lookahead, slice-type decision and MB-tree all run on the device (x264cu_slicetype_step_i420).
@@ -50,9 +51,21 @@ static void synth( uint8_t *luma, int w, int h, int i, int n )
 
 int main( int argc, char **argv )
 {
-    int ranks = 1, rank = 0;
-    if( argc > 2 && !strcmp( argv[1], "--ranks" ) ) { ranks = atoi( argv[2] ); argv += 2; argc -= 2; }
-    if( argc < 4 || ranks < 1 || ranks > 8 ) { fprintf( stderr, "usage: %s [--ranks N] WIDTH HEIGHT FRAMES [pictures.i420]\n", argv[0] ); return 2; }
+    int ranks = 1, rank = 0, bframes = 3, b_adapt = 1, rc_lookahead = 20;
+    while( argc > 2 && argv[1][0] == '-' )
+    {
+        if( !strcmp( argv[1], "--ranks" ) ) ranks = atoi( argv[2] );
+        else if( !strcmp( argv[1], "--bframes" ) ) bframes = atoi( argv[2] );
+        else if( !strcmp( argv[1], "--b-adapt" ) ) b_adapt = atoi( argv[2] );
+        else if( !strcmp( argv[1], "--rc-lookahead" ) ) rc_lookahead = atoi( argv[2] );
+        else break;
+        argv += 2; argc -= 2;
+    }
+    if( argc < 4 || ranks < 1 || ranks > 8 )
+    {
+        fprintf( stderr, "usage: %s [--ranks N] [--bframes B] [--b-adapt A] [--rc-lookahead L] WIDTH HEIGHT FRAMES [pictures.i420]\n", argv[0] );
+        return 2;
+    }
     const int w = atoi( argv[1] ), h = atoi( argv[2] );
     int n = atoi( argv[3] );
     char id_path[64];
@@ -72,8 +85,8 @@ int main( int argc, char **argv )
     memset( &p, 0, sizeof( p ) );
     p.la.width = w; p.la.height = h;
     p.la.subpel_refine = 7; p.la.me_method = X264CU_ME_HEX; p.la.me_range = 16; p.la.mv_range = 512;     /* preset medium */
-    p.la.bframes = 3; p.la.weighted_bipred = 1; p.la.aq_mode = 1; p.la.mb_tree = 1; p.la.weighted_pred = 0;
-    p.keyint_max = 250; p.keyint_min = 25; p.scenecut_threshold = 40; p.b_adapt = 1; p.b_pyramid = 2; p.rc_lookahead = 20;
+    p.la.bframes = bframes; p.la.weighted_bipred = 1; p.la.aq_mode = 1; p.la.mb_tree = 1; p.la.weighted_pred = 0;
+    p.keyint_max = 250; p.keyint_min = 25; p.scenecut_threshold = 40; p.b_adapt = b_adapt; p.b_pyramid = 2; p.rc_lookahead = rc_lookahead;
     p.psy = 0; p.frame_reference = 3; p.fps_num = 25; p.fps_den = 1; p.qcompress = 0.6f; p.aq_strength = 1.0f;
     x264cu_slicetype_t *st;
     if( x264cu_slicetype_open( ctx, &p, &st ) ) { fprintf( stderr, "slicetype_open: %s\n", x264cu_strerror( ctx ) ); return 1; }
