@@ -141,9 +141,12 @@ def cand_list_for_frame(mv_f, stride):
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own pixel table (oracle/_ref) or, if it did not travel, the oracle port
 # ------------------------------------------------------------------------------------------------------
-def cpu_satd_rate(fenc, ref, mv, stride, pitch, budget_s, n_frames_sample):
+def cpu_satd_rate(fenc, ref, mv, stride, pitch, budget_s, n_frames_sample, lib=None):
+    """lib: another build of the reference (the auto-vectorised one) instead of the stock C path"""
     import _libs
-    if _libs.have_ref():
+    if lib is not None:
+        L, fn, kind = lib, "xref_pixel_cmp_batch", "reference (auto-vectorised C)"
+    elif _libs.have_ref():
         L, fn, kind = _libs.ref(), "xref_pixel_cmp_batch", "reference"
     else:
         L, fn, kind = _libs.oracle(), "orc_pixel_cmp_batch", "port"
@@ -291,6 +294,13 @@ def run_satd_b200(args, rank, world, local, dist):
     if rank == 0 and world == 1 and not args.quick:
         rate, kind, cores, sample = cpu_satd_rate(fenc, ref, mv, stride, pitch, args.cpu_budget, 8)
         res["cpu_baseline"] = {"value": rate, "unit": "macroblocks/s", "cores": cores, "kind": kind, "sample": sample}
+        import _libs
+        if _libs.ref_vec() is not None:
+            # a second, labelled row: the same C built -O3 -ftree-vectorize -march=x86-64-v3 (the reference's configure builds its C
+            # with -fno-tree-vectorize; its x86 asm cannot be assembled here: no nasm / yasm in the image, none in the wheelhouse)
+            rate_v, _, _, sample_v = cpu_satd_rate(fenc, ref, mv, stride, pitch, args.cpu_budget / 2, 8, lib=_libs.ref_vec())
+            res["cpu_baseline"]["autovectorized_c"] = {"value": rate_v, "unit": "macroblocks/s", "cores": cores, "sample": sample_v,
+                                                       "build": "oracle/Makefile.ref vec: -O3 -ffast-math -ftree-vectorize -march=x86-64-v3"}
     ctx.close()
     return res
 
@@ -353,7 +363,7 @@ def make_la_frames(seed, n, alloc, LA_W=LA_W, LA_H=LA_H):
     return out
 
 
-def ref_lookahead_types(frames, n, weightp, threads, size=None, opts=None):
+def ref_lookahead_types(frames, n, weightp, threads, size=None, opts=None, lib=None):
     """The reference's OWN lookahead stage with its stock control flow (oracle/ref_shim.c: xref_lookahead_types = steps 1-4 of
     x264_encoder_encode, encoder.c:3360-3445: x264_frame_copy_picture, x264_adaptive_quant_frame, x264_frame_init_lowres,
     x264_lookahead_put_frame / _get_frames -> x264_slicetype_decide / _analyse / macroblock_tree) over the first n pictures of
@@ -361,7 +371,7 @@ def ref_lookahead_types(frames, n, weightp, threads, size=None, opts=None):
     X264_LOOKAHEAD_THREAD_MAX = 16), whose results differ slightly from the one-thread ones (slicetype.c:668).
     -> ([(display index, type)] in coded order, seconds)"""
     import _libs
-    r = _libs.ref()
+    r = lib or _libs.ref()
     r.xref_lookahead_types.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     if opts is None:
         opts = LA_REF_OPTS_W if weightp else LA_REF_OPTS
@@ -753,8 +763,16 @@ def run_lookahead_b200(args, rank, world, local, dist):
         got = [t_ for t_ in all_types][:keep]
         res["config"]["parity_spot_check"] = {"decisions_compared": keep, "identical": bool(keep > 0 and got == types1[:keep]),
                                               "against": "reference x264_slicetype_decide, 1 lookahead thread, %d pictures" % n_ref}
+        vec = None
+        import _libs
+        if kind == "reference" and _libs.ref_vec() is not None:
+            n_v = int(max(56, min(4 * len(frames), args.cpu_budget * 25.0)))
+            _, dt_v = ref_lookahead_types(frames, n_v, args.weightp, cores, lib=_libs.ref_vec())
+            vec = {"value": n_v / dt_v, "unit": "frames/s", "cores": cores, "sample": "%d 4K pictures in %.1f s" % (n_v, dt_v),
+                   "build": "the same C auto-vectorised (oracle/Makefile.ref vec: -O3 -ffast-math -ftree-vectorize -march=x86-64-v3); "
+                            "the reference's x86 asm cannot be assembled here (no nasm / yasm in the image or the wheelhouse)"}
         res["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
-                               "value_1_thread": rate1, "sample_1_thread": sample1,
+                               "value_1_thread": rate1, "sample_1_thread": sample1, "autovectorized_c": vec,
                                "note": "the unmodified reference's lookahead stage (stock control flow) with its sliced lookahead threads on all "
                                        "host cores it can use (max 16); with one thread it returns exactly the decisions the B200 arm is "
                                        "checked against (parity_spot_check)"}
@@ -1030,6 +1048,7 @@ def run_sweep_b200(args, rank, world, local, dist):
     parity_ok = True
     cpu = rank == 0 and world == 1 and not args.quick
     cfn = (_libs.ref().xref_pixel_cmp_batch if _libs.have_ref() else _libs.oracle().orc_pixel_cmp_batch)
+    vec_lib = _libs.ref_vec() if cpu else None
     for ip, sname in SWEEP_SIZES:
         bw, bh = x.PIXEL_W[ip], x.PIXEL_H[ip]
         nbx, nby = W4K // bw, H4K // bh
@@ -1068,6 +1087,10 @@ def run_sweep_b200(args, rank, world, local, dist):
                 t0 = time.perf_counter()
                 cfn(mi, ip, fenc[:pitch], stride, ref[:pitch], stride, c0[:n_cpu], n_cpu, outc)
                 cell["cpu_blocks_per_s_1_thread"] = n_cpu / (time.perf_counter() - t0)
+                if vec_lib is not None:            # the same C, auto-vectorised for AVX2 (oracle/Makefile.ref vec): a labelled second column
+                    t0 = time.perf_counter()
+                    vec_lib.xref_pixel_cmp_batch(mi, ip, fenc[:pitch], stride, ref[:pitch], stride, c0[:n_cpu], n_cpu, outc)
+                    cell["cpu_autovectorized_blocks_per_s_1_thread"] = n_cpu / (time.perf_counter() - t0)
             cells["%s_%s" % (mname, sname)] = cell
         ctx.free(d_mv)
         ctx.free(d_out)
@@ -1082,7 +1105,8 @@ def run_sweep_b200(args, rank, world, local, dist):
                                "pairs per GPU (>= 1 036 800 candidates per cell), ref displaced by a random full-pel mv in +-16" % N_PAIRS,
                    "l2": "inputs %.0f MB per launch > 126 MB L2, no flush needed" % ((fenc.nbytes + ref.nbytes) / 1e6),
                    "parity_spot_check": parity_ok,
-                   "cpu": "reference C path (pixf.sad/satd/ssd, no nasm in the image), one thread, bounded sample" if cpu else None},
+                   "cpu": "reference C path (pixf.sad/satd/ssd; the x86 asm cannot be assembled: no nasm / yasm in the image or the wheelhouse), one "
+                          "thread, bounded sample; cpu_autovectorized_*: the same C built -O3 -ftree-vectorize -march=x86-64-v3" if cpu else None},
         "cells": cells, "clocks": clocks, "gpu_launches": int(total_launches),
         "e2e": None,
         "roofline": {"bound": "hbm", "achieved": head["GB_s"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": head["frac"],

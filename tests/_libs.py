@@ -46,6 +46,30 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+REF_VEC_SO = os.path.join(ROOT, "oracle", "_ref", "libx264ref_vec.so")
+_ref_vec = None
+
+
+def ref_vec():
+    """the reference's C path auto-vectorised for AVX2 (oracle/Makefile.ref, target vec): bench.py's second, labelled CPU row.
+    None if it did not travel or this host cannot run AVX2 code."""
+    global _ref_vec
+    if _ref_vec is None and os.path.exists(REF_VEC_SO):
+        try:
+            flags = open("/proc/cpuinfo").read()
+        except OSError:
+            flags = ""
+        if " avx2" in flags and " bmi2" in flags and " fma" in flags:
+            L = C.CDLL(REF_VEC_SO)
+            L.xref_open.restype = C.c_void_p
+            L.xref_open.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+            L.xref_close.argtypes = [C.c_void_p]
+            L.xref_pixel_cmp_batch.argtypes = [C.c_int, C.c_int, u8p, C.c_ssize_t, u8p, C.c_ssize_t, candp, C.c_int, i32p]
+            L.xref_lookahead_types.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            _ref_vec = L
+    return _ref_vec
+
+
 def ref():
     global _ref
     if _ref is None:

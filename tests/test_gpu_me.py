@@ -219,6 +219,15 @@ def test_me_search_batch_tesa_many_jobs(ctx):
     run_group(ctx, "texture", 4, 2, 32, 1, (1, 70, 6, -2), rng, n_jobs=64)
 
 
+def test_me_search_batch_large_batches_are_walked_by_partition_size(ctx):
+    """from 4 096 jobs on the kernel walks the jobs in the order of a device counting sort by i_pixel (me.cu: me_order_*_kernel;
+    one instruction stream per SM at a time): every result must still land in its caller's slot -- mixed sizes, two chunk
+    boundaries (1 024 jobs per chunk), a ragged tail"""
+    rng = np.random.default_rng(4096)
+    run_group(ctx, "texture", 1, 7, 16, 1, (0, 0, 0, 0), rng, n_jobs=4096 + 1024 + 37)
+    run_group(ctx, "noise", 2, 5, 24, 1, (1, 70, 6, -2), rng, n_jobs=4100)
+
+
 @pytest.mark.parametrize("kind", ["texture", "flat"])
 @pytest.mark.parametrize("satd", [0, 1])
 def test_me_refine_bidir_batch_matches_oracle(ctx, kind, satd):

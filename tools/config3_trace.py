@@ -2,7 +2,7 @@
 """BASELINE configs[3] (7680x4320, rc-lookahead 250, bframes 16, b-adapt 2) on ONE GPU, chunk by chunk: host wall time, pictures
 decided, searches launched and device time of the search launches per chunk of pictures fed.  Shows where the stream's time goes
 (first analysis of the 250-picture window vs. steady state) and that the steady-state figure bench.py reports is a steady state.
-  python tools/config3_trace.py [pictures] [chunk]"""
+  python tools/config3_trace.py [pictures] [chunk] [speculate 0|1]"""
 import json
 import os
 import sys
@@ -22,6 +22,8 @@ frames = bench.make_la_frames(4320, bench.C3_CLIP, lambda b: np.empty(b, np.uint
 d_frames = ctx.malloc(frames.nbytes + 256)
 ctx.h2d(d_frames, frames)
 st = x.Slicetype(ctx, bench.C3_W, bench.C3_H, **bench.C3_ST, **bench.C3_OPTS, weighted_pred=0)
+if len(sys.argv) > 3:
+    st.set_speculation(int(sys.argv[3]))          # default: only on a sharded stream
 rows = []
 t_all = time.perf_counter()
 prev = st.search_stats()
@@ -42,7 +44,7 @@ for k0 in range(0, total, chunk):
 ctx.sync()
 wall_all = time.perf_counter() - t_all
 names = {1: "I", 2: "P", 3: "b", 4: "B", 5: "i"}
-print(json.dumps({"pictures": total, "wall_s": wall_all, "overall_fed_per_s": total / wall_all, "chunks": rows,
+print(json.dumps({"speculation": st.speculation_stats(), "pictures": total, "wall_s": wall_all, "overall_fed_per_s": total / wall_all, "chunks": rows,
                   "types_tail": "".join(str(t) for t in types[-64:])}))
 st.close()
 ctx.close()

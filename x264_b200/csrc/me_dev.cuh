@@ -87,30 +87,30 @@ struct MeWarp
     __device__ __noinline__ int chroma_cost( int mx, int my ) const
     {
         const int dx = mx & 7, dy = my & 7;
-        const int w00 = ( 8 - dx ) * ( 8 - dy ), w01 = dx * ( 8 - dy ), w10 = ( 8 - dx ) * dy, w11 = dx * dy;
+        const uint32_t w00 = ( 8 - dx ) * ( 8 - dy ), w01 = dx * ( 8 - dy ), w10 = ( 8 - dx ) * dy, w11 = dx * dy;
         const uint8_t *s = cref + ( my >> 3 ) * cstride + ( mx >> 3 ) * 2;
-        uint32_t lo, hi;                           // samples 0..3 and sample 4 of the row above the one being produced
+        // a row of five samples as two words of 16-bit fields per tap position: samples (0,2) / (1,3) for the left tap, (1,3) / (2,4)
+        // for the right one -- the weighted sum of four samples is at most 64 * 255 + 32, so both fields of a word are summed at once
+        uint32_t e0, o0, e1;                       // fields (s0,s2), (s1,s3), (s2,s4) of the row above the one being produced
         {
-            const uint32_t a = ldg4u( s ), b = ldg4u( s + 4 );
-            lo = __byte_perm( a, b, 0x6420 ); hi = ldg4u( s + 8 ) & 0xff;
+            const uint32_t a = ldg4u( s ), b = ldg4u( s + 4 ), c = ldg4u( s + 8 ) & 0xff;
+            const uint32_t lo = __byte_perm( a, b, 0x6420 );
+            e0 = __byte_perm( lo, 0, 0x4240 ); o0 = __byte_perm( lo, 0, 0x4341 ); e1 = __byte_perm( lo, c, 0x5452 );
         }
         uint32_t p[4];
 #pragma unroll
         for( int r = 0; r < 4; r++ )
         {
             s += cstride;
-            const uint32_t a = ldg4u( s ), b = ldg4u( s + 4 );
-            const uint32_t nlo = __byte_perm( a, b, 0x6420 ), nhi = ldg4u( s + 8 ) & 0xff;
-            uint32_t out = 0;
-#pragma unroll
-            for( int k = 0; k < 4; k++ )
-            {
-                const int t0 = ( lo >> ( 8*k ) ) & 255, t1 = k < 3 ? ( lo >> ( 8*k + 8 ) ) & 255 : (int)hi;
-                const int b0 = ( nlo >> ( 8*k ) ) & 255, b1 = k < 3 ? ( nlo >> ( 8*k + 8 ) ) & 255 : (int)nhi;
-                out |= (uint32_t)( ( w00*t0 + w01*t1 + w10*b0 + w11*b1 + 32 ) >> 6 ) << ( 8*k );
-            }
+            const uint32_t a = ldg4u( s ), b = ldg4u( s + 4 ), c = ldg4u( s + 8 ) & 0xff;
+            const uint32_t lo = __byte_perm( a, b, 0x6420 );
+            const uint32_t ne0 = __byte_perm( lo, 0, 0x4240 ), no0 = __byte_perm( lo, 0, 0x4341 ), ne1 = __byte_perm( lo, c, 0x5452 );
+            // pixels 0 and 2: left taps e0 / ne0, right taps o0 / no0; pixels 1 and 3: left o0 / no0, right e1 / ne1
+            const uint32_t p02 = ( e0 * w00 + o0 * w01 + ne0 * w10 + no0 * w11 + 0x00200020u ) >> 6;
+            const uint32_t p13 = ( o0 * w00 + e1 * w01 + no0 * w10 + ne1 * w11 + 0x00200020u ) >> 6;
+            const uint32_t out = __byte_perm( p02, p13, 0x6240 );
             p[r] = cw.enabled ? weight4( out, cw ) : out;
-            lo = nlo; hi = nhi;
+            e0 = ne0; o0 = no0; e1 = ne1;
         }
         return satd ? satd4x4( cfenc, p ) : sad4x4( cfenc, p );
     }
