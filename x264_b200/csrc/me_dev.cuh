@@ -39,6 +39,11 @@ struct MeShared                       // per-launch constants
     LaWeight wc[2];
 };
 
+// the two cost functions every search step ends in: inlined at every call site, or one out-of-line copy per partition size
+#ifndef ME_COST_INLINE
+#define ME_COST_INLINE __forceinline__
+#endif
+
 template <int BW, int BH>
 struct MeWarp
 {
@@ -72,7 +77,7 @@ struct MeWarp
     }
     __device__ __forceinline__ bool in_range( int x, int y ) const { return x >= x_min && x <= x_max && y >= y_min && y <= y_max; }
     __device__ __forceinline__ int bits_fpel( int mx, int my ) const { return __ldg( cost_mv + ( mx*4 - mvpx ) ) + __ldg( cost_mv + ( my*4 - mvpy ) ); }
-    __device__ __forceinline__ int sad_fpel( int mx, int my ) const
+    __device__ ME_COST_INLINE int sad_fpel( int mx, int my ) const
     {
         uint32_t b[4];
         const uint8_t *s = fref_w + my * stride + mx;
@@ -114,7 +119,7 @@ struct MeWarp
         }
         return satd ? satd4x4( cfenc, p ) : sad4x4( cfenc, p );
     }
-    __device__ __forceinline__ int cost_qpel( int mx, int my, bool use_mbcmp ) const
+    __device__ ME_COST_INLINE int cost_qpel( int mx, int my, bool use_mbcmp ) const
     {
         uint32_t b[4];
         qpel4x4_p( fref0, fref1, fref2, fref3, stride, w, mx, my, b );
