@@ -434,8 +434,9 @@ void x264cu_slicetype_set_run_ahead( x264cu_slicetype_t *st, int pictures );
 /* speculate = 1: with every prefetch launch, all cost requests the decision can make about the new pictures are computed too
  * (x264cu_lookahead_finalize_batch) -- a request then costs the calling thread a table lookup instead of a launch, a copy and a
  * wait.  0: every request is computed when it is made.  Default: on for a sharded stream (where it is what splits the cost
- * requests between the GPUs), off on a single GPU (the searches' throughput is the bound there and the extra triples cost 5 %).
- * The decisions are identical either way. */
+ * requests between the GPUs) and, on a single GPU, for the trellis over a B pyramid (b_adapt 2, bframes > 1: a new GOP's first
+ * analysis asks for thousands of triples at once; +12 % at 8K / bframes 16); off otherwise (b_adapt 1's short windows: the
+ * searches' throughput is the bound and the extra triples cost 5 %).  The decisions are identical either way. */
 void x264cu_slicetype_set_speculation( x264cu_slicetype_t *st, int speculate );
 /* pictures whose searches are gathered into one prefetch launch (1..32; default 12 for lookaheads >= 12, else 1; before the first
  * picture).  A launch needs several dozen independent searches to fill the GPU; the decisions do not depend on it. */

@@ -71,7 +71,7 @@ struct x264cu_slicetype
     int next_asked;                      /* type forced on the next queued picture */
     /* prefetch: every search the decision could ask for is launched ahead of time, in groups */
     int prefetch, group, in_group, run_ahead;
-    int speculate;                       /* cost requests computed with the searches (x264cu_lookahead_finalize_batch): 0 / 1, -1 = when sharded */
+    int speculate;                       /* cost requests computed with the searches (x264cu_lookahead_finalize_batch): 0 / 1, -1 = when it pays (launch_group) */
     picture_t *recent[GAP_MAX + 2];      /* the last bframes+1 queued pictures, newest first */
     int n_recent;
     struct { int fenc_slot, ref_slot, list, dist, fenc_no, ref_no; } job[JOBS_MAX];
@@ -1000,9 +1000,13 @@ static int launch_group( x264cu_slicetype_t *s )
         return -1;
     if( s->world > 1 && exchange_group( s ) )
         return -1;
-    /* On one GPU the lookahead is bound by the searches' throughput and the extra triples cost more than the waits they save
-     * (measured at 4K: 1 396 -> 1 327 pictures/s); sharded, the cost requests are the replicated part that has to be split. */
-    if( !( s->speculate < 0 ? s->world > 1 : s->speculate ) )
+    /* Sharded, the cost requests are the replicated part that has to be split: always.  On one GPU it depends on the window: with
+     * the trellis over a B pyramid a new GOP's first analysis asks for ~18 000 triples at once (each one a launch + read-back when
+     * computed on demand), and computing them with the searches wins (8K, bframes 16: 57 -> 64 pictures/s); with the short windows
+     * of b-adapt 1 the lookahead is bound by the searches' throughput and the extra triples cost more than the waits they save
+     * (4K preset medium: 1 396 -> 1 327 pictures/s). */
+    const int long_windows = s->p.b_adapt == 2 && s->p.b_pyramid && s->p.la.bframes > 1 && !s->p.la.vbv;
+    if( !( s->speculate < 0 ? s->world > 1 || long_windows : s->speculate ) )
         return 0;
     return s->world > 1 ? speculate_group( s, all, a_fenc, a_ref, a_list, a_dist, number )
                         : speculate_group( s, n, fenc, ref, list, dist, number );
