@@ -20,38 +20,35 @@ lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, 
                int skip_x1 = 0, intptr_t src_pitch = 0, intptr_t dst_pitch = 0 )
 {
     // output domain incl. border: x in [-PAD, wl+PAD) in groups of 4, y in [-PAD, ll+PAD).  Columns [0, skip_x1) of the picture's
-    // own rows are lowres_wide_kernel's.  What is left is mostly replication (frame.c:627): the PAD rows above / below the picture
-    // repeat its first / last row, the PAD columns left / right of it its first / last pixel.  So the threads are numbered over the
-    // distinct values only -- one per column group for each of the two bands (stored PAD times), and per picture row one for the
-    // left border, one for the right (stored PAD/4 times each) and one per group from skip_x1 on.
-    const int groups_x = ( wl + 2*X264CU_PAD ) / 4, left = X264CU_PAD / 4;
+    // own rows are lowres_wide_kernel's, so the threads are numbered over what is left: the two bands of PAD rows above and below
+    // the picture at full width, then per picture row the PAD/4 groups left of it and the groups from skip_x1 on.
+    const int groups_x = ( wl + 2*X264CU_PAD ) / 4;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int per_row = 2 + ( wl - skip_x1 ) / 4;
-    int gx, oy, nrows = 1, ncols = 1;
-    if( t < 2 * groups_x )
+    const int band = 2 * X264CU_PAD * groups_x, left = X264CU_PAD / 4, per_row = groups_x - skip_x1 / 4;
+    int gx, oy;
+    if( t < band )
     {
-        const int bottom = t >= groups_x;
-        gx = t - bottom * groups_x;
-        oy = bottom ? ll : -X264CU_PAD;
-        nrows = X264CU_PAD;
+        const int row = t / groups_x;
+        gx = t - row * groups_x;
+        oy = row < X264CU_PAD ? row - X264CU_PAD : ll + row - X264CU_PAD;
     }
     else
     {
-        const int u = t - 2 * groups_x;
+        const int u = t - band;
         oy = u / per_row;
         if( oy >= ll ) return;
         const int k = u - oy * per_row;
-        if( k < 2 ) { gx = k ? groups_x - left : 0; ncols = left; }
-        else gx = left + skip_x1 / 4 + k - 2;
+        gx = k < left ? k : k + skip_x1 / 4;
     }
     const int ox = gx * 4 - X264CU_PAD;
     src += (intptr_t)blockIdx.z * src_pitch;
+    d0 += (intptr_t)blockIdx.z * dst_pitch; dh += (intptr_t)blockIdx.z * dst_pitch;
+    dv += (intptr_t)blockIdx.z * dst_pitch; dc += (intptr_t)blockIdx.z * dst_pitch;
     const int y = clampi( oy, 0, ll-1 );
-    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
     if( fast_ok && ox >= 0 && ox + 4 <= wl && 2*( ox + 4 ) + 1 <= width )
-    {   // columns 2ox .. 2ox+8 inside the picture (rows are clamped: the last source row repeats below the picture).  8-byte aligned
-        // vector loads; the whole filter runs on packed bytes: FILTER(a,b,c,d) = avg( avg(a,b), avg(c,d) ) with
-        // avg(x,y) = (x+y+1)>>1 = __vavgu4 (mc.c:494-500)
+    {   // columns 2ox .. 2ox+8 inside the picture (rows are clamped: the rows of the top / bottom border repeat the edge rows'
+        // results, the last source row repeats below the picture).  8-byte aligned vector loads; the whole filter runs on packed
+        // bytes: FILTER(a,b,c,d) = avg( avg(a,b), avg(c,d) ) with avg(x,y) = (x+y+1)>>1 = __vavgu4 (mc.c:494-500)
         uint32_t lo[3], hi[3], nx[3];
 #pragma unroll
         for( int r = 0; r < 3; r++ )
@@ -67,36 +64,35 @@ lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, 
         const uint32_t a_ev = __byte_perm( a_lo, a_hi, 0x6420 ), a_od = __byte_perm( a_lo, a_hi, 0x7531 );
         const uint32_t b_ev = __byte_perm( b_lo, b_hi, 0x6420 ), b_od = __byte_perm( b_lo, b_hi, 0x7531 );
         const uint32_t a_e2 = __byte_perm( a_ev, a_nx, 0x4321 ), b_e2 = __byte_perm( b_ev, b_nx, 0x4321 );
-        o0 = __vavgu4( a_ev, a_od ); o1 = __vavgu4( a_od, a_e2 ); o2 = __vavgu4( b_ev, b_od ); o3 = __vavgu4( b_od, b_e2 );
+        *(uint32_t *)( d0 + (intptr_t)oy*dst_stride + ox ) = __vavgu4( a_ev, a_od );
+        *(uint32_t *)( dh + (intptr_t)oy*dst_stride + ox ) = __vavgu4( a_od, a_e2 );
+        *(uint32_t *)( dv + (intptr_t)oy*dst_stride + ox ) = __vavgu4( b_ev, b_od );
+        *(uint32_t *)( dc + (intptr_t)oy*dst_stride + ox ) = __vavgu4( b_od, b_e2 );
+        return;
     }
-    else
-    {   // edges and border: per-pixel clamped coordinates (the picture is edge-replicated to the mod-16 size and one
-        // column / row beyond: mc.c:466-469, frame.c:640-665; the lowres border replicates the computed edge: frame.c:627)
-        for( int i = 0; i < 4; i++ )
-        {
-            const int x = clampi( ox + i, 0, wl-1 );
-            int s[3][3];
+    // edges and border: per-pixel clamped coordinates (the picture is edge-replicated to the mod-16 size and one
+    // column / row beyond: mc.c:466-469, frame.c:640-665; the lowres border replicates the computed edge: frame.c:627)
+    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+    for( int i = 0; i < 4; i++ )
+    {
+        const int x = clampi( ox + i, 0, wl-1 );
+        int s[3][3];
 #pragma unroll
-            for( int r = 0; r < 3; r++ )
+        for( int r = 0; r < 3; r++ )
 #pragma unroll
-                for( int c = 0; c < 3; c++ )
-                    s[r][c] = src[(intptr_t)min( 2*y + r, height-1 ) * src_stride + min( 2*x + c, width-1 )];
+            for( int c = 0; c < 3; c++ )
+                s[r][c] = src[(intptr_t)min( 2*y + r, height-1 ) * src_stride + min( 2*x + c, width-1 )];
 #define FILT( a, b, c, d ) ( ( ( ( (a) + (b) + 1 ) >> 1 ) + ( ( (c) + (d) + 1 ) >> 1 ) + 1 ) >> 1 )
-            o0 |= (uint32_t)FILT( s[0][0], s[1][0], s[0][1], s[1][1] ) << ( 8*i );
-            o1 |= (uint32_t)FILT( s[0][1], s[1][1], s[0][2], s[1][2] ) << ( 8*i );
-            o2 |= (uint32_t)FILT( s[1][0], s[2][0], s[1][1], s[2][1] ) << ( 8*i );
-            o3 |= (uint32_t)FILT( s[1][1], s[2][1], s[1][2], s[2][2] ) << ( 8*i );
+        o0 |= (uint32_t)FILT( s[0][0], s[1][0], s[0][1], s[1][1] ) << ( 8*i );
+        o1 |= (uint32_t)FILT( s[0][1], s[1][1], s[0][2], s[1][2] ) << ( 8*i );
+        o2 |= (uint32_t)FILT( s[1][0], s[2][0], s[1][1], s[2][1] ) << ( 8*i );
+        o3 |= (uint32_t)FILT( s[1][1], s[2][1], s[1][2], s[2][2] ) << ( 8*i );
 #undef FILT
-        }
     }
-    const intptr_t o = (intptr_t)blockIdx.z * dst_pitch + (intptr_t)oy * dst_stride + ox;
-    for( int r = 0; r < nrows; r++ )
-        for( int c = 0; c < ncols; c++ )
-        {
-            const intptr_t at = o + (intptr_t)r * dst_stride + 4 * c;
-            *(uint32_t *)( d0 + at ) = o0; *(uint32_t *)( dh + at ) = o1;
-            *(uint32_t *)( dv + at ) = o2; *(uint32_t *)( dc + at ) = o3;
-        }
+    *(uint32_t *)( d0 + (intptr_t)oy*dst_stride + ox ) = o0;
+    *(uint32_t *)( dh + (intptr_t)oy*dst_stride + ox ) = o1;
+    *(uint32_t *)( dv + (intptr_t)oy*dst_stride + ox ) = o2;
+    *(uint32_t *)( dc + (intptr_t)oy*dst_stride + ox ) = o3;
 }
 
 
@@ -318,11 +314,12 @@ __device__ __forceinline__ uint32_t byte_lanes( uint32_t a, uint32_t b )
     return d;
 }
 
-#ifdef HPEL_MIN_CTAS
-__global__ void __launch_bounds__( PT_THREADS, HPEL_MIN_CTAS )
-#else
-__global__ void __launch_bounds__( PT_THREADS )
+// 32 registers, 15 CTAs per SM (shared memory allows no more): measured cold at 4K 7.87 us per picture against 8.03 us with the
+// compiler's own choice (40 registers, 12 CTAs)
+#ifndef HPEL_MIN_CTAS
+#define HPEL_MIN_CTAS 15
 #endif
+__global__ void __launch_bounds__( PT_THREADS, HPEL_MIN_CTAS )
 hpel_packed_kernel( const __grid_constant__ CUtensorMap tm_src, const uint8_t *__restrict__ src, intptr_t stride, intptr_t pitch, int width, int height,
                     uint8_t *dh, uint8_t *dv, uint8_t *dc, uint8_t *dsrc_border, uint32_t less4096 )
 {   // less4096 = -4096 in both 16-bit fields: a kernel parameter, so that VIADDMNMX (one immediate only) reads it from the constant bank
@@ -546,7 +543,7 @@ static int lowres_launch( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d
         CU_LAUNCH_CHECK( ctx );
     }
     const int skip = 8 * max( groups, 0 ), groups_x = ( wl + 2*X264CU_PAD ) / 4;
-    const long border_threads = 2L * groups_x + (long)ll * ( 2 + ( wl - skip ) / 4 );      // the distinct border values, see the kernel
+    const long border_threads = 2L * X264CU_PAD * groups_x + (long)ll * ( groups_x - skip / 4 );
     dim3 block( 256 ), grid( (unsigned)( ( border_threads + 255 ) / 256 ), 1, n_pictures );
     lowres_kernel<<<grid, block, 0, stream>>>( d_luma, luma_stride, width, height, d_lowres[0], d_lowres[1],
                                                d_lowres[2], d_lowres[3], lowres_stride, wl, ll, aligned, skip, luma_pitch, lowres_pitch );
