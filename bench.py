@@ -750,6 +750,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
             res["config"]["n1_line"] = "the N = 1 line of this bench is the 4K stream (BASELINE configs[1]-style); value_1_gpu_same_workload is the "\
                                        "one-GPU figure for THIS workload, measured by rank 0 in this run -- the 1 -> N ratio to read"
             res["config"]["l2"] = "17 pictures' lowres planes (35 MB each) are live per search group: far beyond the 126 MB L2"
+            res["roofline"]["measured_on"] = "the 4K leg of this run (replicas): the dominant kernel is the same search_kernel<8>; gpu_launches and clocks are that leg's too"
             res["e2e"] = {"value": c3["e2e_frames_per_s_%d_gpus" % world], "unit": "frames/s", "h2d_bytes_per_step": c3["h2d_bytes_per_step"],
                           "d2h_bytes_per_step": c3["d2h_bytes_per_step"],
                           "api": "x264cu_slicetype_step on every rank (each rank is fed the same page-locked host pictures; whole stream, host clock)"}
