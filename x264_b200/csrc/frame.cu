@@ -1,5 +1,5 @@
 // Frame preparation kernels: the streaming (HBM-bound) entries of x264_mc_functions_t.
-//   lowres_kernel  : x264_frame_init_lowres + frame_init_lowres_core + expand_border_lowres
+//   lowres_fused_kernel : x264_frame_init_lowres + frame_init_lowres_core + expand_border_lowres
 //                    (common/mc.c:458-507, common/frame.c:627-631)            2*W*H algorithmic bytes / frame
 //   hpel_kernel    : hpel_filter over a frame + border expansion of the three planes
 //                    (common/mc.c:172-196, :704-746, common/frame.c:596-625)   4*W*H algorithmic bytes / frame
@@ -14,16 +14,15 @@ __device__ __forceinline__ int clampi( int v, int lo, int hi ) { return min( max
 // ------------------------------------------------------------------------------------------------
 // lowres: thread = 4 horizontally adjacent output pixels of all four planes
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__( 256 )
-lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, int height,
-               uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, int wl, int ll, int fast_ok,
-               int skip_x1 = 0, intptr_t src_pitch = 0, intptr_t dst_pitch = 0 )
+__device__ __forceinline__ void
+lowres_border_body( int t, int pic, const uint8_t *__restrict__ src, intptr_t src_stride, int width, int height,
+                    uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, int wl, int ll, int fast_ok,
+                    int skip_x1, intptr_t src_pitch, intptr_t dst_pitch )
 {
     // output domain incl. border: x in [-PAD, wl+PAD) in groups of 4, y in [-PAD, ll+PAD).  Columns [0, skip_x1) of the picture's
-    // own rows are lowres_wide_kernel's, so the threads are numbered over what is left: the two bands of PAD rows above and below
+    // own rows are lowres_wide_body's, so the threads are numbered over what is left: the two bands of PAD rows above and below
     // the picture at full width, then per picture row the PAD/4 groups left of it and the groups from skip_x1 on.
     const int groups_x = ( wl + 2*X264CU_PAD ) / 4;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int band = 2 * X264CU_PAD * groups_x, left = X264CU_PAD / 4, per_row = groups_x - skip_x1 / 4;
     int gx, oy;
     if( t < band )
@@ -41,9 +40,9 @@ lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, 
         gx = k < left ? k : k + skip_x1 / 4;
     }
     const int ox = gx * 4 - X264CU_PAD;
-    src += (intptr_t)blockIdx.z * src_pitch;
-    d0 += (intptr_t)blockIdx.z * dst_pitch; dh += (intptr_t)blockIdx.z * dst_pitch;
-    dv += (intptr_t)blockIdx.z * dst_pitch; dc += (intptr_t)blockIdx.z * dst_pitch;
+    src += (intptr_t)pic * src_pitch;
+    d0 += (intptr_t)pic * dst_pitch; dh += (intptr_t)pic * dst_pitch;
+    dv += (intptr_t)pic * dst_pitch; dc += (intptr_t)pic * dst_pitch;
     const int y = clampi( oy, 0, ll-1 );
     if( fast_ok && ox >= 0 && ox + 4 <= wl && 2*( ox + 4 ) + 1 <= width )
     {   // columns 2ox .. 2ox+8 inside the picture (rows are clamped: the rows of the top / bottom border repeat the edge rows'
@@ -98,8 +97,8 @@ lowres_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, int width, 
 
 // ------------------------------------------------------------------------------------------------
 // lowres, wide path (16-byte aligned source rows): thread = 8 output pixels x 2 output rows of all four planes -- five source
-// rows of 16 + 1 bytes (128-bit loads), eight 64-bit stores; the filter itself as in lowres_kernel, on packed bytes.
-// Interior of the picture only; the border and the picture's last columns stay with lowres_kernel (launched on that band).
+// rows of 16 + 1 bytes (128-bit loads), eight 64-bit stores; the filter itself as in lowres_border_body, on packed bytes.
+// Interior of the picture only; the border and the picture's last columns stay with lowres_border_body (the grid's last block rows).
 // blockIdx.z = picture of a stack.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void lowres_row8( const uint32_t a[5], const uint32_t b[5], uint8_t *p0, uint8_t *ph, uint8_t *pv, uint8_t *pc )
@@ -116,15 +115,13 @@ __device__ __forceinline__ void lowres_row8( const uint32_t a[5], const uint32_t
     *(uint2 *)pc = make_uint2( __vavgu4( b_od0, b_e20 ), __vavgu4( b_od1, b_e21 ) );
 }
 
-__global__ void __launch_bounds__( 128 )
-lowres_wide_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, intptr_t src_pitch, int height,
-                    uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, intptr_t dst_pitch, int groups, int ll )
-{
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * 2;                                  // output rows y, y+1 (ll is even)
+__device__ __forceinline__ void
+lowres_wide_body( int g, int y, int pic, const uint8_t *__restrict__ src, intptr_t src_stride, intptr_t src_pitch, int height,
+                  uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, intptr_t dst_pitch, int groups, int ll )
+{   // output rows y, y+1 (ll is even), columns 8g .. 8g+7
     if( g >= groups ) return;
-    src += (intptr_t)blockIdx.z * src_pitch;
-    const intptr_t doff = (intptr_t)blockIdx.z * dst_pitch + (intptr_t)y * dst_stride + 8 * g;
+    src += (intptr_t)pic * src_pitch;
+    const intptr_t doff = (intptr_t)pic * dst_pitch + (intptr_t)y * dst_stride + 8 * g;
     uint32_t r[5][5];
 #pragma unroll
     for( int k = 0; k < 5; k++ )
@@ -142,6 +139,22 @@ lowres_wide_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, intptr
     lowres_row8( m[0], m[1], d0 + doff, dh + doff, dv + doff, dc + doff );
     if( y + 1 < ll )
         lowres_row8( m[2], m[3], d0 + doff + dst_stride, dh + doff + dst_stride, dv + doff + dst_stride, dc + doff + dst_stride );
+}
+
+// ONE launch for a stack of pictures: block rows [0, wide_rows) of the grid run the wide body (one block row = two output rows),
+// the block rows after them are numbered linearly over the border tasks.  The border's scattered, mostly scalar work (7 % of the
+// output) then runs under the streaming blocks instead of after them.
+__global__ void __launch_bounds__( 128 )
+lowres_fused_kernel( const uint8_t *__restrict__ src, intptr_t src_stride, intptr_t src_pitch, int width, int height,
+                     uint8_t *d0, uint8_t *dh, uint8_t *dv, uint8_t *dc, intptr_t dst_stride, intptr_t dst_pitch,
+                     int groups, int wl, int ll, int fast_ok, int wide_rows )
+{
+    if( (int)blockIdx.y < wide_rows )
+        lowres_wide_body( blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * 2, blockIdx.z, src, src_stride, src_pitch, height,
+                          d0, dh, dv, dc, dst_stride, dst_pitch, groups, ll );
+    else
+        lowres_border_body( ( ( blockIdx.y - wide_rows ) * gridDim.x + blockIdx.x ) * blockDim.x + threadIdx.x, blockIdx.z,
+                            src, src_stride, width, height, d0, dh, dv, dc, dst_stride, wl, ll, fast_ok, 8 * groups, src_pitch, dst_pitch );
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -535,18 +548,14 @@ static int lowres_launch( x264cu_ctx *ctx, cudaStream_t stream, const uint8_t *d
     if( !( ( (uintptr_t)d_luma | (uintptr_t)luma_stride | (uintptr_t)luma_pitch ) & 15 ) && !( dst_bits & 7 ) )
         groups = min( wl / 8, ( width - 17 ) / 16 + 1 );
     if( groups > 0 && 16 * ( groups - 1 ) + 20 > luma_stride ) groups--;                 // the 4 bytes past column 16 must be readable
-    if( groups > 0 )
-    {
-        dim3 grid( ( groups + 127 ) / 128, ( ll + 1 ) / 2, n_pictures );
-        lowres_wide_kernel<<<grid, 128, 0, stream>>>( d_luma, luma_stride, luma_pitch, height, d_lowres[0], d_lowres[1], d_lowres[2], d_lowres[3],
-                                                      lowres_stride, lowres_pitch, groups, ll );
-        CU_LAUNCH_CHECK( ctx );
-    }
-    const int skip = 8 * max( groups, 0 ), groups_x = ( wl + 2*X264CU_PAD ) / 4;
-    const long border_threads = 2L * X264CU_PAD * groups_x + (long)ll * ( groups_x - skip / 4 );
-    dim3 block( 256 ), grid( (unsigned)( ( border_threads + 255 ) / 256 ), 1, n_pictures );
-    lowres_kernel<<<grid, block, 0, stream>>>( d_luma, luma_stride, width, height, d_lowres[0], d_lowres[1],
-                                               d_lowres[2], d_lowres[3], lowres_stride, wl, ll, aligned, skip, luma_pitch, lowres_pitch );
+    groups = max( groups, 0 );
+    const int groups_x = ( wl + 2*X264CU_PAD ) / 4;
+    const long border_threads = 2L * X264CU_PAD * groups_x + (long)ll * ( groups_x - 2 * groups );
+    const int blocks_x = groups ? ( groups + 127 ) / 128 : 8, wide_rows = groups ? ( ll + 1 ) / 2 : 0;
+    const int border_rows = (int)( ( border_threads + 128L * blocks_x - 1 ) / ( 128L * blocks_x ) );
+    dim3 grid( blocks_x, wide_rows + border_rows, n_pictures );
+    lowres_fused_kernel<<<grid, 128, 0, stream>>>( d_luma, luma_stride, luma_pitch, width, height, d_lowres[0], d_lowres[1], d_lowres[2],
+                                                   d_lowres[3], lowres_stride, lowres_pitch, groups, wl, ll, aligned, wide_rows );
     CU_LAUNCH_CHECK( ctx );
     return 0;
 }
