@@ -446,8 +446,9 @@ def run_config3(ctx, x, rank, world, local, dist, args):
     stream on ONE GPU, measured by rank 0 alone in the same run (the other ranks wait).  The WHOLE stream is timed, first picture in
     to last decision out: the host runs far ahead of the device here (a picture's 33 searches take ~24 ms of one GPU at 8K and the
     decisions arrive in bursts), so no window shorter than the stream is a steady state."""
-    import torch
-    from x264_b200 import dist as xd
+    if dist is not None:
+        import torch
+        from x264_b200 import dist as xd
     steps = max(args.steps, 10)                       # at least 320 pictures, so that the 250-picture lookahead fills
     total = C3_STEP * steps
     frames = make_la_frames(4320, C3_CLIP, lambda b: ctx.malloc_host(b), C3_W, C3_H)
@@ -487,6 +488,19 @@ def run_config3(ctx, x, rank, world, local, dist, args):
         st.close()
         return n_pic / (ms * 1e-3), n_pic / wall, types, spec, ex, busy, ms
 
+    if dist is None:
+        # one GPU (the N = 1 line carries this as an extra key, so that the 1 -> N series of this workload is complete)
+        run(False, False, C3_STEP * 3)
+        one = run(False, False, total)
+        e2e = run(False, True, total)
+        ctx.free(d_frames)
+        return {"workload": "BASELINE configs[3]: ONE 7680x4320 stream, rc-lookahead 250, bframes 16, b-adapt 2, b-pyramid, mb-tree, scenecut 40 "
+                            "(33 lowres searches per picture) on ONE GPU; the whole stream of %d pictures, first picture in to last decision "
+                            "out; what `value` is at N > 1" % total,
+                "pictures": total, "frames_per_s_1_gpu": one[0], "wall_frames_per_s_1_gpu": one[1], "e2e_frames_per_s_1_gpu": e2e[1],
+                "e2e_same_decisions": e2e[2] == one[2],
+                "searches": {"searches": one[5][2], "launches": one[5][1], "device_ms_of_search_launches": one[5][0]},
+                "cost_requests": {"computed_ahead": one[3][0], "served_from_them": one[3][1], "computed_on_demand": one[3][2]}}
     for _ in range(1):                                 # warm-up: a short sharded stream (allocator, NCCL channels, clocks)
         run(True, False, C3_STEP * min(max(args.warmup, 3), 4))
     one = None
@@ -754,6 +768,8 @@ def run_lookahead_b200(args, rank, world, local, dist):
             res["e2e"] = {"value": c3["e2e_frames_per_s_%d_gpus" % world], "unit": "frames/s", "h2d_bytes_per_step": c3["h2d_bytes_per_step"],
                           "d2h_bytes_per_step": c3["d2h_bytes_per_step"],
                           "api": "x264cu_slicetype_step on every rank (each rank is fed the same page-locked host pictures; whole stream, host clock)"}
+    if world == 1 and not args.quick:
+        res["config3_8k_one_gpu"] = run_config3(ctx, x, rank, world, local, None, args)
     if rank == 0 and world == 1 and not args.quick:
         rate, kind, cores, sample, _ = cpu_lookahead_rate(frames, args.cpu_budget, args.weightp, os.cpu_count() or 1)
         rate1, _, _, sample1, types1 = cpu_lookahead_rate(frames, args.cpu_budget, args.weightp, 1)
