@@ -2,7 +2,7 @@
 """BASELINE configs[3] (7680x4320, rc-lookahead 250, bframes 16, b-adapt 2) on ONE GPU, chunk by chunk: host wall time, pictures
 decided, searches launched and device time of the search launches per chunk of pictures fed.  Shows where the stream's time goes
 (first analysis of the 250-picture window vs. steady state) and that the steady-state figure bench.py reports is a steady state.
-  python tools/config3_trace.py [pictures] [chunk] [speculate 0|1] [width height]
+  python tools/config3_trace.py [pictures] [chunk] [speculate 0|1] [width height] [bframes rc_lookahead]
 (a small width x height leaves only the host logic and the launch overheads: what a sharded stream cannot split)"""
 import json
 import os
@@ -20,6 +20,9 @@ total = int(sys.argv[1]) if len(sys.argv) > 1 else 588
 chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 48
 if len(sys.argv) > 5:
     bench.C3_W, bench.C3_H = int(sys.argv[4]), int(sys.argv[5])
+if len(sys.argv) > 7:
+    bench.C3_OPTS = dict(bench.C3_OPTS, bframes=int(sys.argv[6]))
+    bench.C3_ST = dict(bench.C3_ST, rc_lookahead=int(sys.argv[7]))
 ctx = x.Context(0)
 frames = bench.make_la_frames(4320, bench.C3_CLIP, lambda b: np.empty(b, np.uint8), bench.C3_W, bench.C3_H)
 d_frames = ctx.malloc(frames.nbytes + 256)
