@@ -1,4 +1,4 @@
-"""worker for tests/test_dist_cpu.py::test_sharded_stream_*: python _shard_worker.py RANK WORLD PORT OUTFILE
+"""worker for tests/test_dist_cpu.py::test_sharded_stream_*: python _shard_worker.py RANK WORLD PORT OUTFILE [trellis]
 One picture stream sharded over WORLD ranks on CPU: the product's host logic (x264_b200/csrc/slicetype.c, sharded mode) over the
 oracle glue, the exchange callback over gloo.  Writes the decisions and the exchange statistics."""
 import ctypes as C
@@ -20,8 +20,9 @@ os.environ["MASTER_PORT"] = port
 dist.init_process_group("gloo", rank=rank, world_size=world)
 w, h, n = 96, 64, 70
 frames = synth_sequence(w, h, n, seed=5, cut_at=33)
-la = LookaheadParams(w, h, 7, 1, 16, 512, 3, 0, 1, 0, 1, 0, 0, 0)
-p = SlicetypeParams(la, 250, 25, 40, 1, 2, 20, 0, 3, 0)
+trellis = len(sys.argv) > 5 and sys.argv[5] == "trellis"       # BASELINE configs[3]'s kind of window: b-adapt 2 over a B pyramid, long mini-GOPs
+la = LookaheadParams(w, h, 7, 1, 16, 512, 8 if trellis else 3, 0, 1, 0, 1, 0, 0, 0)
+p = SlicetypeParams(la, 250, 25, 40, 2 if trellis else 1, 2, 40 if trellis else 20, 0, 3, 0)
 lib = slicetype_oracle_lib()
 lib.x264cu_slicetype_open.argtypes = [C.c_void_p, C.POINTER(SlicetypeParams), C.POINTER(C.c_void_p)]
 lib.x264cu_slicetype_step.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]

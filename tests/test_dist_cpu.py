@@ -31,10 +31,10 @@ def test_pack_unpack_roundtrip():
     assert xd.unpack_records(rec[None]) == {7: d}
 
 
-def _run_shard(tmp_path, world, tag):
-    port = str(30500 + (os.getpid() + world) % 1000)
+def _run_shard(tmp_path, world, tag, *extra):
+    port = str(30500 + (os.getpid() + world + 7 * len(extra)) % 1000)
     outs = [str(tmp_path / ("%s%d.json" % (tag, r))) for r in range(world)]
-    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "_shard_worker.py"), str(r), str(world), port, outs[r]])
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "_shard_worker.py"), str(r), str(world), port, outs[r]] + list(extra))
              for r in range(world)]
     for p in procs:
         assert p.wait(timeout=300) == 0
@@ -45,6 +45,17 @@ def test_sharded_stream_matches_single_rank(tmp_path):
     single = _run_shard(tmp_path, 1, "s")[0]
     both = _run_shard(tmp_path, 2, "d")
     assert single["exchanges"] == 0
+    for r in both:
+        assert r["types"] == single["types"]
+        assert r["exchanges"] >= 3 and r["exchanges"] == both[0]["exchanges"] and r["bytes"] == both[0]["bytes"]
+
+
+def test_sharded_trellis_stream_matches_single_rank(tmp_path):
+    """the same with BASELINE configs[3]'s kind of window (b-adapt 2 over a B pyramid, bframes 8): more searches per picture, the
+    pruned set of speculated triples, long mini-GOPs"""
+    single = _run_shard(tmp_path, 1, "ts", "trellis")[0]
+    both = _run_shard(tmp_path, 2, "td", "trellis")
+    assert len(single["types"]) == 70 and sum(t in (4, 5) for _, t in single["types"]) > 35
     for r in both:
         assert r["types"] == single["types"]
         assert r["exchanges"] >= 3 and r["exchanges"] == both[0]["exchanges"] and r["bytes"] == both[0]["bytes"]
