@@ -1013,9 +1013,14 @@ static int launch_group( x264cu_slicetype_t *s )
 }
 
 /* every (picture, earlier picture) pair the decision could ask about: list 0 at distance d <= bframes+1 from the new
- * picture, list 1 at distance d <= bframes towards it */
+ * picture, list 1 at distance d <= bframes towards it -- or, with a B pyramid, no further than half a mini-GOP: whoever prices
+ * a B picture then does it against the middle picture or the nearer anchor (the b-adapt 1 loop asks for (i, i+2, i+1) only,
+ * slicetype.c:1610; trellis :1310-1321; MB-tree :1143-1160; the rate control's nearest references, ratecontrol.c; only the VBV
+ * plan, :1262-1266, spans the whole mini-GOP).  Anything else would still be searched on demand. */
 static void note_searches_of( x264cu_slicetype_t *s, picture_t *f )
 {
+    const int span = s->p.la.bframes + 1;
+    const int l1_max = s->p.b_pyramid && s->p.la.bframes > 1 && !s->p.la.vbv ? span - span / 2 : s->p.la.bframes;
     for( int k = 0; k < s->n_recent; k++ )
     {
         picture_t *o = s->recent[k];
@@ -1025,7 +1030,7 @@ static void note_searches_of( x264cu_slicetype_t *s, picture_t *f )
         s->job[s->n_job].fenc_slot = f->slot; s->job[s->n_job].ref_slot = o->slot; s->job[s->n_job].list = 0; s->job[s->n_job].dist = d;
         s->job[s->n_job].fenc_no = f->number; s->job[s->n_job].ref_no = o->number;
         s->n_job++;
-        if( d <= s->p.la.bframes )
+        if( d <= l1_max )
         {
             s->job[s->n_job].fenc_slot = o->slot; s->job[s->n_job].ref_slot = f->slot; s->job[s->n_job].list = 1; s->job[s->n_job].dist = d;
             s->job[s->n_job].fenc_no = o->number; s->job[s->n_job].ref_no = f->number;
