@@ -716,7 +716,7 @@ def run_lookahead_b200(args, rank, world, local, dist):
                                "mb-tree requests, scenecut 40; lookahead weightp analysis %s, aq off)" % (n, "on" if args.weightp else "off"),
                    "l2": "each picture's 4 lowres planes (9.4 MB) stay L2-resident by design; pictures cycle through %d MB" % (frames.nbytes // 2**20),
                    "cost_requests_per_step": requests / args.steps, "decided_per_step": len(decided) / (args.steps + max(args.warmup, 3)),
-                   "scheduling": "searches prefetched on two low-priority streams in groups of 12 pictures (84 searches per launch), decisions run 24 pictures behind the newest one (sync-lookahead twin); uploads on their own stream",
+                   "scheduling": "searches prefetched on two low-priority streams in groups of 12 pictures (72 searches per launch: list 0 at distances 1-4, list 1 at distances 1-2 -- with a B pyramid nobody reads further), decisions run 24 pictures behind the newest one (sync-lookahead twin); uploads on their own stream",
                    "multi_gpu": "value / e2e: one independent stream per GPU (weak scaling), one NCCL all-gather of decision records (%d streams gathered); "
                                 "sharded_stream: ONE stream over all GPUs" % gathered_streams},
         "clocks": clocks,
