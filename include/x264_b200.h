@@ -501,6 +501,9 @@ int  x264cu_slicetype_rc_analyse_slice( x264cu_slicetype_t *st, int frame, int *
 int  x264cu_slicetype_get_planned( x264cu_slicetype_t *st, int frame, int *h_type, int *h_satd, int max_entries );
 /* number of slicetype_frame_cost requests issued so far (memo hits included) */
 long x264cu_slicetype_cost_requests( x264cu_slicetype_t *st );
+/* the largest distance p1-b any of those requests named for a B picture (p0 < b < p1).  The prefetcher launches list-1 searches up
+ * to half a mini-GOP under a B pyramid (nobody asks further: tests/test_slicetype_host.py sweeps it); farther ones run on demand. */
+int x264cu_slicetype_farthest_list1( x264cu_slicetype_t *st );
 
 /* ------------------------------------------------------------------------------------------------
  * Batched twin of x264_me_search_ref + refine_subpel (encoder/me.h:58-60, encoder/me.c:182-992): one job = one call.

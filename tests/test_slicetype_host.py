@@ -47,7 +47,7 @@ def params_from_ref(hnd, w, h):
     return p
 
 
-def decide_with(lib, p, frames, qp_out=None, chroma=None, forced=None, rc_out=None):
+def decide_with(lib, p, frames, qp_out=None, chroma=None, forced=None, rc_out=None, stats=None):
     """qp_out: dict filled with frame -> f_qp_offset (MB-tree's output) for every non-B picture, read when it is returned;
     chroma: (cb, cr) planes fed with every picture through x264cu_slicetype_step_i420 (adaptive quantisation inside)"""
     lib.x264cu_slicetype_open.argtypes = [C.c_void_p, C.POINTER(SlicetypeParams), C.POINTER(C.c_void_p)]
@@ -97,6 +97,9 @@ def decide_with(lib, p, frames, qp_out=None, chroma=None, forced=None, rc_out=No
         if fr.value < 0:
             break
         note()
+    if stats is not None:
+        lib.x264cu_slicetype_farthest_list1.argtypes = [C.c_void_p]
+        stats["farthest_list1"] = lib.x264cu_slicetype_farthest_list1(st)
     lib.x264cu_slicetype_close(st)
     return out
 
@@ -293,3 +296,28 @@ def test_rc_analyse_slice_and_vbv_lookahead_match_reference_encoder(case):
     got = decide_with(slicetype_oracle_lib(), p, frames, rc_out=rc_got, chroma=chroma)
     analysed, planned = rc_compare(want, got, rc_ref, rc_got, p.la.vbv)
     assert analysed >= 10 and (planned > 20 or not (p.la.vbv and p.rc_lookahead))
+
+
+@pytest.mark.parametrize("b_adapt", [0, 1, 2])
+@pytest.mark.parametrize("bframes", [2, 3, 5, 8, 16])
+def test_nobody_asks_for_list1_beyond_half_a_minigop_under_a_b_pyramid(b_adapt, bframes):
+    """what the prefetcher relies on (slicetype.c: note_searches_of): with a B pyramid and no VBV every consumer -- the b-adapt 1 loop,
+    the trellis, MB-tree, the rate control's costs -- prices a B picture against the middle picture or the nearer anchor, so no
+    request names a later reference further than (bframes+1) - (bframes+1)/2 pictures away.  With the rate control's reads included
+    (x264cu_slicetype_rc_analyse_slice of every picture), on sequences with a cut, a still stretch and noise."""
+    lib = slicetype_oracle_lib()
+    w, h, n = 64, 48, 56 if bframes < 16 else 72
+    worst = 0
+    for seed, mbtree in ((3, 1), (11, 0)):
+        frames = synth_sequence(w, h, n, seed=seed + bframes, cut_at=n // 2 + 3)
+        for i in range(8, 16):                       # a still stretch: long runs of B pictures
+            frames[i] = frames[8]
+        la = LookaheadParams(w, h, 2, 1, 16, 512, bframes, 0, 1, 0, mbtree, 0, 0, 0)
+        p = SlicetypeParams(la, 250, 25, 40, b_adapt, 2, 30, 0, 3, 0)
+        stats, rc = {}, {}
+        types = decide_with(lib, p, frames, rc_out=rc, stats=stats)
+        assert sorted(f for f, _ in types) == list(range(n))
+        assert any(t in (4, 5) for _, t in types)
+        worst = max(worst, stats["farthest_list1"])
+    span = bframes + 1
+    assert 1 <= worst <= span - span // 2, (worst, span)

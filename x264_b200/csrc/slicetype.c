@@ -65,6 +65,7 @@ struct x264cu_slicetype
     int n_slots;
     unsigned char *slot_busy;
     long requests;
+    int far_list1;                       /* the largest p1-b any request named for a B picture: what the list-1 prefetch has to cover */
     int mb_w, mb_h;
     int broken;                          /* a lookahead call failed */
     float tick, qcompress, aq_strength;  /* picture duration (constant frame rate), rc.f_qcompress, rc.f_aq_strength */
@@ -96,6 +97,8 @@ static int score3( x264cu_slicetype_t *s, picture_t **w, int p0, int p1, int b )
 {
     int *known = &w[b]->memo[b - p0][p1 - b];
     s->requests++;
+    if( b < p1 && b > p0 && p1 - b > s->far_list1 )
+        s->far_list1 = p1 - b;
     if( *known >= 0 )
         return *known;
     int slots[WIN_MAX + 4], v = 0;
@@ -1226,3 +1229,4 @@ int x264cu_slicetype_get_planned( x264cu_slicetype_t *s, int frame, int *h_type,
 }
 
 long x264cu_slicetype_cost_requests( x264cu_slicetype_t *s ) { return s ? s->requests : 0; }
+int x264cu_slicetype_farthest_list1( x264cu_slicetype_t *s ) { return s ? s->far_list1 : 0; }
